@@ -1,0 +1,128 @@
+"""CPU oracle for the randomisation-method summators -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may
+import this package.  ``gstools_b200`` never does.
+
+Two restatements of the same algorithm (see ``summate_oracle.c`` for the
+reference citations):
+
+* :func:`summate` / :func:`summate_incompr` -- the C/OpenMP library
+  ``liboracle.so`` built by ``oracle/Makefile`` (reference loop order, libm).
+* :func:`summate_np` / :func:`summate_incompr_np` -- a numpy restatement used to
+  cross-check the C build on small cases.
+
+Parity pin: ``tests/test_oracle_golden.py`` (golden values asserted by the
+reference's own tests, mode arrays produced by the reference's ``RandMeth``).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile ``liboracle.so`` with gcc (``make -C oracle``)."""
+    src = os.path.join(_HERE, "summate_oracle.c")
+    if (
+        force
+        or not os.path.exists(_LIB_PATH)
+        or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+    ):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    return _LIB_PATH
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        lib = ctypes.CDLL(_LIB_PATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        for name in ("oracle_summate", "oracle_summate_incompr"):
+            fn = getattr(lib, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [dp, dp, dp, dp, ctypes.c_int, ctypes.c_int64,
+                           ctypes.c_int64, dp, ctypes.c_int]
+        lib.oracle_max_threads.restype = ctypes.c_int
+        _lib = lib
+    return _lib
+
+
+def max_threads() -> int:
+    return int(_load().oracle_max_threads())
+
+
+def _prep(cov_samples, z_1, z_2, pos):
+    cov = np.ascontiguousarray(cov_samples, dtype=np.float64)
+    z1 = np.ascontiguousarray(z_1, dtype=np.float64)
+    z2 = np.ascontiguousarray(z_2, dtype=np.float64)
+    p = np.ascontiguousarray(pos, dtype=np.float64)
+    if cov.ndim != 2 or p.ndim != 2 or cov.shape[0] != p.shape[0]:
+        raise ValueError("oracle: cov_samples (d,N) and pos (d,n) must share d")
+    if z1.shape != (cov.shape[1],) or z2.shape != (cov.shape[1],):
+        raise ValueError("oracle: z_1, z_2 must have shape (N,)")
+    return cov, z1, z2, p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def summate(cov_samples, z_1, z_2, pos, num_threads=None):
+    """C/OpenMP oracle of ``summate`` (reference call site generator.py:42-48)."""
+    cov, z1, z2, p = _prep(cov_samples, z_1, z_2, pos)
+    out = np.zeros(p.shape[1], dtype=np.float64)
+    rc = _load().oracle_summate(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), cov.shape[0],
+                                cov.shape[1], p.shape[1], _ptr(out),
+                                int(num_threads or 0))
+    if rc:
+        raise RuntimeError(f"oracle_summate failed: {rc}")
+    return out
+
+
+def summate_incompr(cov_samples, z_1, z_2, pos, num_threads=None):
+    """C/OpenMP oracle of ``summate_incompr`` (generator.py:51-64)."""
+    cov, z1, z2, p = _prep(cov_samples, z_1, z_2, pos)
+    out = np.zeros((cov.shape[0], p.shape[1]), dtype=np.float64)
+    rc = _load().oracle_summate_incompr(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p),
+                                        cov.shape[0], cov.shape[1], p.shape[1],
+                                        _ptr(out), int(num_threads or 0))
+    if rc:
+        raise RuntimeError(f"oracle_summate_incompr failed: {rc}")
+    return out
+
+
+def summate_np(cov_samples, z_1, z_2, pos, num_threads=None):
+    """numpy restatement (small cases): phase matrix then two mat-vecs."""
+    cov, z1, z2, p = _prep(cov_samples, z_1, z_2, pos)
+    out = np.zeros(p.shape[1])
+    step = max(1, 2_000_000 // max(1, cov.shape[1]))
+    for a in range(0, p.shape[1], step):
+        phase = p[:, a:a + step].T @ cov            # (n, N)
+        out[a:a + step] = np.cos(phase) @ z1 + np.sin(phase) @ z2
+    return out
+
+
+def summate_incompr_np(cov_samples, z_1, z_2, pos, num_threads=None):
+    """numpy restatement of the projector form (generator.py:479-495)."""
+    cov, z1, z2, p = _prep(cov_samples, z_1, z_2, pos)
+    d = cov.shape[0]
+    k2 = np.sum(cov * cov, axis=0)
+    e1 = np.zeros((d, 1))
+    e1[0] = 1.0
+    proj = e1 - cov * cov[0] / k2                   # (d, N)
+    out = np.zeros((d, p.shape[1]))
+    step = max(1, 2_000_000 // max(1, cov.shape[1]))
+    for a in range(0, p.shape[1], step):
+        phase = p[:, a:a + step].T @ cov
+        amp = np.cos(phase) * z1 + np.sin(phase) * z2   # (n, N)
+        out[:, a:a + step] = proj @ amp.T
+    return out
