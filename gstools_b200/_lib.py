@@ -1,0 +1,104 @@
+"""ctypes binding of the C ABI declared in ``include/gsb200.h``.
+
+The product path fails loudly when the CUDA library is missing or when no GPU is
+present -- there is no CPU fallback (and nothing under ``oracle/`` is ever imported here).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import _build
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_int64_p = ctypes.POINTER(ctypes.c_int64)
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+
+MEM_HOST = 0
+MEM_DEVICE = 1
+
+# every symbol include/gsb200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "gsb_version": (_int, []),
+    "gsb_last_error": (ctypes.c_char_p, []),
+    "gsb_device_count": (_int, [ctypes.POINTER(_int)]),
+    "gsb_summate": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _int, _int, _vp]),
+    "gsb_summate_incompr": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _i64, _int,
+                                   _int, _vp]),
+    "gsb_summate_structured": (_int, [_vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64, _i64, _vp,
+                                      _int, _int, _vp]),
+    "gsb_summate_incompr_structured": (_int, [_vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64,
+                                              _i64, _vp, _int, _int, _vp]),
+    "gsb_scale_shift": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp]),
+    "gsb_set_option": (_int, [ctypes.c_char_p, _i64]),
+    "gsb_get_counter": (_i64, [ctypes.c_char_p]),
+    "gsb_measure_fp64_peak": (_int, [_int, _int, ctypes.c_double, _c_double_p]),
+}
+
+_lib = None
+
+
+class GSB200Error(RuntimeError):
+    """Device-side failure reported by the C ABI (CUDA error, no device, ...)."""
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load ``libgsb200.so`` (never builds implicitly on a machine without nvcc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is missing: build it with `python -m gstools_b200._build` "
+            "(or __graft_entry__.build()).  gstools_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().gsb_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == 1:
+        raise ValueError(f"{what}: {msg}")
+    raise GSB200Error(f"{what}: {msg}")
+
+
+def device_count() -> int:
+    c = _int(0)
+    check(load().gsb_device_count(ctypes.byref(c)), "gsb_device_count")
+    return int(c.value)
+
+
+def set_option(name: str, value: int):
+    check(load().gsb_set_option(name.encode(), int(value)), "gsb_set_option")
+
+
+def get_counter(name: str) -> int:
+    return int(load().gsb_get_counter(name.encode()))
+
+
+def measure_fp64_peak(device: int = 0, kind: int = 0, seconds: float = 0.3) -> float:
+    """Sustained FP64 FMA/s of the DFMA pipe (kind 0) or the DMMA tensor path (kind 1)."""
+    out = ctypes.c_double(0.0)
+    check(load().gsb_measure_fp64_peak(int(device), int(kind), float(seconds), ctypes.byref(out)),
+          "gsb_measure_fp64_peak")
+    return float(out.value)

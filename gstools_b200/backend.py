@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference's native summator interface.
+
+Same names, argument order and meaning as the functions gstools imports from
+gstools-cython / gstools_core (reference: src/gstools/field/generator.py:22-34)
+and calls at generator.py:48 and :64::
+
+    summate(cov_samples, z_1, z_2, pos, num_threads=None)         -> (n,)   float64
+    summate_incompr(cov_samples, z_1, z_2, pos, num_threads=None) -> (d, n) float64
+
+``num_threads`` is accepted for signature compatibility and ignored.
+
+Inputs may be numpy arrays (host path: the C ABI stages the copies, the result is a
+numpy array in pinned memory) or CUDA ``torch`` tensors (device path: zero copy, work
+is enqueued on the current torch stream, the result is a CUDA tensor).
+
+Everything runs through ``libgsb200.so``; there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import _lib
+
+__all__ = [
+    "summate",
+    "summate_incompr",
+    "summate_structured",
+    "summate_incompr_structured",
+    "scale_shift_",
+    "set_device",
+    "get_device",
+]
+
+_DEVICE = None
+_PIN_THRESHOLD = 1 << 16  # outputs of at least this many doubles are allocated pinned
+
+
+def set_device(index: int):
+    """Select the CUDA device used for numpy (host-buffer) calls."""
+    global _DEVICE
+    _DEVICE = int(index)
+
+
+def get_device() -> int:
+    if _DEVICE is not None:
+        return _DEVICE
+    env = os.environ.get("GSB200_DEVICE")
+    if env is not None:
+        return int(env)
+    if "LOCAL_RANK" in os.environ:  # one process per GPU under torchrun
+        return int(os.environ["LOCAL_RANK"])
+    return 0
+
+
+# ----------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------
+def _is_cuda_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and getattr(x, "is_cuda", False)
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _empty_host(shape):
+    """Uninitialised float64 host array; pinned when large so D2H runs at full PCIe speed."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    if n >= _PIN_THRESHOLD:
+        try:
+            torch = _torch()
+            if torch.cuda.is_available():
+                return torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True).numpy()
+        except Exception:  # pinned allocation is an optimisation only
+            pass
+    return np.empty(shape, dtype=np.float64)
+
+
+def _as_f64(a, name):
+    try:
+        arr = np.asarray(a, dtype=np.float64)
+    except (TypeError, ValueError) as exc:
+        raise TypeError(f"{name}: cannot be interpreted as a float64 array") from exc
+    return arr
+
+
+def _rows_contiguous(a):
+    """(array, leading dimension in elements) with unit inner stride; copies only when needed."""
+    n = a.shape[1]
+    if a.flags.c_contiguous:
+        return a, max(n, 1)
+    it = a.itemsize
+    if n > 0 and a.strides[1] == it and a.strides[0] > 0 and a.strides[0] % it == 0 \
+            and a.strides[0] // it >= n:
+        return a, a.strides[0] // it  # row-strided view (e.g. a point range of a bigger array)
+    return np.ascontiguousarray(a), max(n, 1)
+
+
+def _check_modes(cov, z1, z2):
+    if cov.ndim != 2:
+        raise ValueError("cov_samples must have shape (dim, mode_no)")
+    if z1.ndim != 1 or z2.ndim != 1 or z1.shape[0] != cov.shape[1] or z2.shape[0] != cov.shape[1]:
+        raise ValueError("z_1 and z_2 must have shape (mode_no,) matching cov_samples")
+
+
+def _ptr(a):
+    return a.ctypes.data
+
+
+# ----------------------------------------------------------------------------------------
+# flat (unstructured) entry points -- the reference signatures
+# ----------------------------------------------------------------------------------------
+def _flat(cov_samples, z_1, z_2, pos, vec):
+    lib = _lib.load()
+    if any(_is_cuda_tensor(x) for x in (cov_samples, z_1, z_2, pos)):
+        return _flat_device(lib, cov_samples, z_1, z_2, pos, vec)
+    cov = np.ascontiguousarray(_as_f64(cov_samples, "cov_samples"))
+    z1 = np.ascontiguousarray(_as_f64(z_1, "z_1"))
+    z2 = np.ascontiguousarray(_as_f64(z_2, "z_2"))
+    p = _as_f64(pos, "pos")
+    _check_modes(cov, z1, z2)
+    if p.ndim != 2 or p.shape[0] != cov.shape[0]:
+        raise ValueError("pos must have shape (dim, n) with the same dim as cov_samples")
+    dim, n_modes = cov.shape
+    n = p.shape[1]
+    p, ld = _rows_contiguous(p)
+    if vec:
+        out = _empty_host((dim, n))
+        rc = lib.gsb_summate_incompr(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n,
+                                     _ptr(out), max(n, 1), _lib.MEM_HOST, get_device(), None)
+        _lib.check(rc, "summate_incompr")
+    else:
+        out = _empty_host((n,))
+        rc = lib.gsb_summate(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n,
+                             _ptr(out), _lib.MEM_HOST, get_device(), None)
+        _lib.check(rc, "summate")
+    return out
+
+
+def _flat_device(lib, cov_samples, z_1, z_2, pos, vec):
+    torch = _torch()
+    dev = next(x.device for x in (pos, cov_samples, z_1, z_2) if _is_cuda_tensor(x))
+
+    def prep(x):
+        return torch.as_tensor(x, dtype=torch.float64, device=dev).contiguous()
+
+    cov, z1, z2, p = prep(cov_samples), prep(z_1), prep(z_2), prep(pos)
+    if cov.ndim != 2 or z1.ndim != 1 or z2.ndim != 1 or z1.shape[0] != cov.shape[1] \
+            or z2.shape[0] != cov.shape[1]:
+        raise ValueError("cov_samples must be (dim, mode_no); z_1, z_2 must be (mode_no,)")
+    if p.ndim != 2 or p.shape[0] != cov.shape[0]:
+        raise ValueError("pos must have shape (dim, n) with the same dim as cov_samples")
+    dim, n_modes = cov.shape
+    n = p.shape[1]
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if vec:
+        out = torch.empty((dim, n), dtype=torch.float64, device=dev)
+        rc = lib.gsb_summate_incompr(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(),
+                                     max(n, 1), dim, n_modes, n, out.data_ptr(), max(n, 1),
+                                     _lib.MEM_DEVICE, dev.index, stream)
+        _lib.check(rc, "summate_incompr")
+    else:
+        out = torch.empty((n,), dtype=torch.float64, device=dev)
+        rc = lib.gsb_summate(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), max(n, 1),
+                             dim, n_modes, n, out.data_ptr(), _lib.MEM_DEVICE, dev.index, stream)
+        _lib.check(rc, "summate")
+    return out
+
+
+def summate(cov_samples, z_1, z_2, pos, num_threads=None):
+    """B200 replacement of the native ``summate`` (generator.py:42-48, math :193-199)."""
+    return _flat(cov_samples, z_1, z_2, pos, vec=False)
+
+
+def summate_incompr(cov_samples, z_1, z_2, pos, num_threads=None):
+    """B200 replacement of the native ``summate_incompr`` (generator.py:51-64, math :479-495)."""
+    return _flat(cov_samples, z_1, z_2, pos, vec=True)
+
+
+# ----------------------------------------------------------------------------------------
+# structured (rectilinear mesh) entry points -- the side channel for mesh_type="structured"
+# ----------------------------------------------------------------------------------------
+def _structured(cov_samples, z_1, z_2, axes, matrix, vec):
+    lib = _lib.load()
+    axes = list(axes)
+    dim = len(axes)
+    if any(_is_cuda_tensor(x) for x in (cov_samples, z_1, z_2, *axes)):
+        return _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec)
+    cov = np.ascontiguousarray(_as_f64(cov_samples, "cov_samples"))
+    z1 = np.ascontiguousarray(_as_f64(z_1, "z_1"))
+    z2 = np.ascontiguousarray(_as_f64(z_2, "z_2"))
+    batched = cov.ndim == 3
+    if not batched:
+        _check_modes(cov, z1, z2)
+        cov3, z1b, z2b = cov[None], z1[None], z2[None]
+    else:
+        if z1.shape != (cov.shape[0], cov.shape[2]) or z2.shape != z1.shape:
+            raise ValueError("batched call: cov_samples (B, dim, N), z_1 / z_2 (B, N)")
+        cov3, z1b, z2b = cov, z1, z2
+    if cov3.shape[1] != dim:
+        raise ValueError("number of axes must equal the dim of cov_samples")
+    ax = [np.ascontiguousarray(_as_f64(a, "axes")).reshape(-1) for a in axes]
+    lens = (np.array([a.shape[0] for a in ax], dtype=np.int64))
+    cat = np.ascontiguousarray(np.concatenate(ax)) if dim else np.empty(0)
+    mat_ptr = None
+    if matrix is not None:
+        mat = np.ascontiguousarray(_as_f64(matrix, "matrix"))
+        if mat.shape != (dim, dim):
+            raise ValueError("matrix must have shape (dim, dim)")
+        mat_ptr = _ptr(mat)
+    shape = tuple(int(v) for v in lens)
+    n_batch, _, n_modes = cov3.shape
+    full = ((n_batch,) if batched else ()) + ((dim,) if vec else ()) + shape
+    out = _empty_host(full)
+    fn = lib.gsb_summate_incompr_structured if vec else lib.gsb_summate_structured
+    rc = fn(_ptr(cov3), _ptr(z1b), _ptr(z2b), _ptr(cat),
+            lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch, _ptr(out),
+            _lib.MEM_HOST, get_device(), None)
+    _lib.check(rc, "summate_incompr_structured" if vec else "summate_structured")
+    return out
+
+
+def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec):
+    torch = _torch()
+    dev = next(x.device for x in (cov_samples, z_1, z_2, *axes) if _is_cuda_tensor(x))
+
+    def prep(x):
+        return torch.as_tensor(x, dtype=torch.float64, device=dev).contiguous()
+
+    cov, z1, z2 = prep(cov_samples), prep(z_1), prep(z_2)
+    batched = cov.ndim == 3
+    if not batched:
+        cov, z1, z2 = cov[None], z1[None], z2[None]
+    dim = len(axes)
+    if cov.ndim != 3 or cov.shape[1] != dim or tuple(z1.shape) != (cov.shape[0], cov.shape[2]) \
+            or z2.shape != z1.shape:
+        raise ValueError("cov_samples (B, dim, N) / (dim, N); z_1, z_2 (B, N) / (N,); len(axes) == dim")
+    ax = [prep(a).reshape(-1) for a in axes]
+    lens = np.array([int(a.shape[0]) for a in ax], dtype=np.int64)
+    cat = torch.cat(ax) if dim else torch.empty(0, dtype=torch.float64, device=dev)
+    mat_ptr = None
+    if matrix is not None:
+        if _is_cuda_tensor(matrix):
+            matrix = matrix.detach().cpu().numpy()
+        mat = np.ascontiguousarray(_as_f64(matrix, "matrix"))
+        if mat.shape != (dim, dim):
+            raise ValueError("matrix must have shape (dim, dim)")
+        mat_ptr = _ptr(mat)  # host pointer: the ABI reads the tiny matrix on the host
+    shape = tuple(int(v) for v in lens)
+    n_batch, _, n_modes = cov.shape
+    full = ((n_batch,) if batched else ()) + ((dim,) if vec else ()) + shape
+    out = torch.empty(full, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    fn = lib.gsb_summate_incompr_structured if vec else lib.gsb_summate_structured
+    rc = fn(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), cat.data_ptr(),
+            lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch, out.data_ptr(),
+            _lib.MEM_DEVICE, dev.index, stream)
+    _lib.check(rc, "summate_incompr_structured" if vec else "summate_structured")
+    return out
+
+
+def summate_structured(cov_samples, z_1, z_2, axes, matrix=None):
+    """``summate`` on the mesh spanned by ``axes`` without the flat position array.
+
+    Equals ``summate(cov_samples, z_1, z_2, matrix @ generate_grid(axes)).reshape(shape)``
+    (reference: field/base.py:289-297, tools/geometric.py:340-356, covmodel/base.py:572-582).
+    ``cov_samples`` may carry a leading batch axis (ensembles of mode sets on one mesh).
+    """
+    return _structured(cov_samples, z_1, z_2, axes, matrix, vec=False)
+
+
+def summate_incompr_structured(cov_samples, z_1, z_2, axes, matrix=None):
+    """Vector-field variant of :func:`summate_structured`; returns ``(dim,) + shape``."""
+    return _structured(cov_samples, z_1, z_2, axes, matrix, vec=True)
+
+
+def scale_shift_(field, scale, shift=0.0):
+    """In-place ``field = scale*field + shift`` on a CUDA tensor (generator.py:269-270)."""
+    if not _is_cuda_tensor(field):
+        raise TypeError("scale_shift_ works on CUDA tensors; use numpy for host arrays")
+    torch = _torch()
+    if field.dtype != torch.float64 or not field.is_contiguous():
+        raise ValueError("field must be a contiguous float64 CUDA tensor")
+    stream = torch.cuda.current_stream(field.device).cuda_stream
+    rc = _lib.load().gsb_scale_shift(field.data_ptr(), field.numel(), float(scale), float(shift),
+                                     field.device.index, stream)
+    _lib.check(rc, "scale_shift")
+    return field

@@ -1,0 +1,120 @@
+// gsb_common.cuh -- error plumbing and sm_100a PTX helpers shared by the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+
+#include "../../include/gsb200.h"
+
+namespace gsb {
+
+// ---------------------------------------------------------------------------------------------
+// error handling: thread-local message, status codes, no exceptions across the C ABI
+// ---------------------------------------------------------------------------------------------
+inline std::string &last_error_ref()
+{
+    static thread_local std::string msg;
+    return msg;
+}
+
+inline int fail(int code, const std::string &msg)
+{
+    last_error_ref() = msg;
+    return code;
+}
+
+#define GSB_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            char buf__[512];                                                                   \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call,                      \
+                     cudaGetErrorString(e__), __FILE__, __LINE__);                             \
+            return ::gsb::fail(GSB_ERR_CUDA, buf__);                                           \
+        }                                                                                      \
+    } while (0)
+
+#define GSB_TRY(expr)                                                                          \
+    do {                                                                                       \
+        int rc__ = (expr);                                                                     \
+        if (rc__ != GSB_OK) return rc__;                                                       \
+    } while (0)
+
+extern std::atomic<int64_t> g_launches;  // kernels launched by this library (gsb_get_counter)
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (TMA unit, SASS UBLKCP) on sm_100a
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+                 : "memory");
+}
+
+// make barrier initialisation visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+// add pending transaction bytes WITHOUT arriving (the lane arrives later, after its own stores)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (complete_tx).
+// bytes must be a multiple of 16; src and dst 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
+__device__ __forceinline__ int lo32(double x) { return __double2loint(x); }
+
+}  // namespace gsb

@@ -1,0 +1,388 @@
+// gsb_separable.cuh -- separable summation on structured (rectilinear) meshes for sm_100a.
+//
+// On a structured mesh the position of grid node (i_0, ..., i_{d-1}) is M (a_0[i_0], ...,
+// a_{d-1}[i_{d-1}]) (reference: src/gstools/tools/geometric.py:340-356 generate_grid, then
+// src/gstools/covmodel/base.py:572-582 isometrize).  With k' = M^T k the phase splits per axis,
+//     k . x = sum_t k'_t a_t[i_t],
+// and the sum of the reference summator (src/gstools/field/generator.py:193-199) becomes
+//     u[row, c] = sum_j Re( A_j(row) * E_j(c) ) = sum_j  Ar[row,j] Cz[j,c] + (-Ai[row,j]) Sz[j,c]
+// with  A_j(row) = (z1_j - i z2_j) prod_{t<d-1} exp(i k'_{t,j} a_t[i_t])   (row = all axes but the last)
+//       E_j(c)   = exp(i k'_{d-1,j} a_{d-1}[c]) = Cz + i Sz               (c = last, contiguous axis).
+// That is a real fp64 contraction of depth 2N costing 2 DFMA per (point, mode) instead of the
+// ~D+17 of the direct kernel: all sin/cos work moves into per-axis tables of size (len_t x N)
+// built once per call with full-accuracy sincos.
+//
+// Kernel structure (one CTA per 128x128 output tile, 1 CTA/SM, warp specialised):
+//   * warps 8..11 = producer warpgroup (one thread per tile row; registers trimmed with
+//     setmaxnreg.dec so the consumers can hold their 64 accumulators).  Per pipeline stage of KC
+//     modes it (a) issues cp.async.bulk copies (TMA unit) of the Cz/Sz table slices into shared
+//     memory, signalled on the stage's "full" mbarrier, and (b) GENERATES the A operand on the
+//     fly: one complex product per (row, mode) from the L2-resident row-axis tables, written
+//     straight to shared memory.  The 4.2 GB A matrix of config 2 never exists in HBM.
+//   * warps 0..7 = consumers: 8x8 register tile per thread (64 fp64 accumulators), fragments
+//     fetched with conflict-free 16-byte LDS, 128 DFMA per mode per thread, modes accumulated
+//     in ascending order (deterministic, no atomics).  They release the stage on its "empty"
+//     mbarrier.
+//   * epilogue: registers -> global, 16-byte stores, full 128-byte lines per row segment.
+// The incompressible variant (generator.py:479-495) multiplies A by the projector p_t(k_j) and
+// runs one CTA column per vector component (2 d DFMA per pair).
+#pragma once
+
+#include "gsb_common.cuh"
+
+namespace gsb {
+
+constexpr int SEP_TM = 128;      // rows per CTA tile
+constexpr int SEP_TN = 128;      // columns per CTA tile
+constexpr int SEP_KC = 8;        // modes per pipeline stage
+constexpr int SEP_STAGES = 4;
+constexpr int SEP_CONSUMER_WARPS = 8;
+constexpr int SEP_PRODUCER_WARPS = 4;   // one full warpgroup, so setmaxnreg can rebalance registers
+constexpr int SEP_THREADS = (SEP_CONSUMER_WARPS + SEP_PRODUCER_WARPS) * 32;
+constexpr int SEP_REGS_PRODUCER = 56;
+constexpr int SEP_REGS_CONSUMER = 224;  // 128*56 + 256*224 = 64512 <= 65536
+constexpr int SEP_MAX_ROW_AXES = GSB_MAX_DIM - 1;
+
+// shared memory carve-up per stage: Ar[KC][TM], Ai[KC][TM], Bc[KC][TN], Bs[KC][TN] (doubles)
+constexpr int SEP_STAGE_DOUBLES = SEP_KC * (2 * SEP_TM + 2 * SEP_TN);
+constexpr size_t SEP_SMEM_BYTES =
+    (size_t)SEP_STAGES * SEP_STAGE_DOUBLES * sizeof(double) + 2 * SEP_STAGES * sizeof(uint64_t) + 128;
+
+struct SepParams {
+    // row-axis tables: E_t[j * len_t + i] = exp(i k'_{t,j} a_t[i]) as (cos, sin); t = 0 is
+    // pre-multiplied by (z1_j - i z2_j).  Modes j >= n_modes (padding) are zero.
+    const double2 *erow[SEP_MAX_ROW_AXES];
+    int64_t row_len[SEP_MAX_ROW_AXES];     // extent of each row axis in THIS launch (slab)
+    int64_t row_stride[SEP_MAX_ROW_AXES];  // full table width (entries per mode) of each row axis
+    int n_row_axes;
+    int64_t n_rows;        // prod(row_len)
+    // last-axis tables, planes of n_modes_pad x lc_pad doubles
+    const double *bc;
+    const double *bs;
+    int64_t lc;            // length of the last axis
+    int64_t lc_pad;        // padded to a multiple of SEP_TN
+    int n_modes_pad;       // multiple of SEP_KC
+    // incompressible projector p_t[j], (ncomp, n_modes_pad); nullptr for the scalar sum
+    const double *proj;
+    int ncomp;             // 1 (scalar) or dim (vector)
+    // per-batch strides (in elements) of the tables above; batch index = blockIdx.z / ncomp
+    int64_t erow_bstride[SEP_MAX_ROW_AXES];
+    int64_t b_bstride;
+    int64_t proj_bstride;
+    double *out;           // field f = batch*ncomp + comp starts at out + f*out_fstride; (n_rows, lc) inside
+    int64_t out_fstride;
+};
+
+// ---------------------------------------------------------------------------------------------
+// table builder: one thread per (axis entry, mode).  Full-accuracy sincos (libdevice), cost
+// O((sum_t len_t) N) -- negligible against the O(n N) contraction.
+// ---------------------------------------------------------------------------------------------
+struct TableParams {
+    const double *cov;     // (n_batch, dim, n_modes)
+    const double *z1;      // (n_batch, n_modes)
+    const double *z2;
+    const double *axes;    // concatenated axis coordinates
+    int64_t axis_off[GSB_MAX_DIM];
+    int64_t axis_len[GSB_MAX_DIM];
+    double matrix[GSB_MAX_DIM * GSB_MAX_DIM];  // row-major (dim x dim) isometrisation matrix
+    int dim;
+    int64_t n_modes;
+    int n_modes_pad;
+    int vec;               // build the projector table
+    double2 *erow[SEP_MAX_ROW_AXES];
+    int64_t erow_bstride[SEP_MAX_ROW_AXES];
+    double *bc;
+    double *bs;
+    int64_t lc_pad;
+    int64_t b_bstride;
+    double *proj;
+    int64_t proj_bstride;
+};
+
+__global__ void build_tables_kernel(const TableParams tp)
+{
+    const int t = blockIdx.y;                 // axis
+    const int64_t b = blockIdx.z;             // batch entry
+    const int64_t len = tp.axis_len[t];
+    const bool last = (t == tp.dim - 1);
+    const int64_t width = last ? tp.lc_pad : len;
+    const int64_t total = width * tp.n_modes_pad;
+    const double *cov = tp.cov + b * tp.dim * tp.n_modes;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = idx / width;
+        const int64_t i = idx - j * width;
+        double c = 0.0, s = 0.0;
+        if (j < tp.n_modes && i < len) {
+            // k'_t = sum_s M[s][t] k_s   (phase = k . (M a) = (M^T k) . a)
+            double kp = 0.0;
+            for (int s2 = 0; s2 < tp.dim; ++s2)
+                kp = fma(tp.matrix[s2 * tp.dim + t], cov[(int64_t)s2 * tp.n_modes + j], kp);
+            sincos(kp * tp.axes[tp.axis_off[t] + i], &s, &c);
+            if (t == 0 && !last) {  // fold the complex weight (z1 - i z2) into the first row axis
+                const double a = tp.z1[b * tp.n_modes + j], bb = tp.z2[b * tp.n_modes + j];
+                const double re = a * c + bb * s;
+                const double im = a * s - bb * c;
+                c = re;
+                s = im;
+            }
+        }
+        if (last) {
+            tp.bc[b * tp.b_bstride + j * tp.lc_pad + i] = c;
+            tp.bs[b * tp.b_bstride + j * tp.lc_pad + i] = s;
+        } else {
+            tp.erow[t][b * tp.erow_bstride[t] + j * len + i] = make_double2(c, s);
+        }
+    }
+    // projector table (vector field): p_c[j] = delta_c0 - k_c k_0 / |k|^2 on the ORIGINAL k
+    if (tp.vec && t == 0) {
+        for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < tp.n_modes_pad;
+             j += (int64_t)gridDim.x * blockDim.x) {
+            double k2 = 0.0;
+            if (j < tp.n_modes)
+                for (int s2 = 0; s2 < tp.dim; ++s2) {
+                    const double k = cov[(int64_t)s2 * tp.n_modes + j];
+                    k2 += k * k;
+                }
+            for (int c2 = 0; c2 < tp.dim; ++c2) {
+                double p = 0.0;
+                if (j < tp.n_modes) {
+                    const double e = (c2 == 0) ? 1.0 : 0.0;
+                    p = e - cov[(int64_t)c2 * tp.n_modes + j] * cov[j] / k2;
+                }
+                tp.proj[b * tp.proj_bstride + (int64_t)c2 * tp.n_modes_pad + j] = p;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the contraction kernel
+// ---------------------------------------------------------------------------------------------
+template <int NRA>  // number of row axes (dim - 1), 1..SEP_MAX_ROW_AXES
+__global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepParams prm)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage_base = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + SEP_STAGES * SEP_STAGE_DOUBLES);
+    uint64_t *empty = full + SEP_STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int64_t col0 = (int64_t)blockIdx.x * SEP_TN;
+    const int64_t row0 = (int64_t)blockIdx.y * SEP_TM;
+    const int comp = blockIdx.z % prm.ncomp;
+    const int64_t batch = blockIdx.z / prm.ncomp;
+    const int n_stages_total = prm.n_modes_pad / SEP_KC;
+
+    if (tid == 0) {
+        for (int s = 0; s < SEP_STAGES; ++s) {
+            mbar_init(&full[s], SEP_PRODUCER_WARPS * 32); // every producer thread arrives once
+            mbar_init(&empty[s], SEP_CONSUMER_WARPS);     // one arrive per consumer warp
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp >= SEP_CONSUMER_WARPS) {
+        // ============================= PRODUCER WARPGROUP ==============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SEP_REGS_PRODUCER));
+        const int prow = tid - SEP_CONSUMER_WARPS * 32;  // 0..127: the tile row this thread owns
+        const double2 *ep[NRA];
+        {
+            int64_t r = row0 + prow;
+            if (r >= prm.n_rows) r = prm.n_rows - 1;  // clamp; result is never stored
+#pragma unroll
+            for (int t = NRA - 1; t >= 0; --t) {
+                const int64_t it = r % prm.row_len[t];
+                r /= prm.row_len[t];
+                ep[t] = prm.erow[t] + batch * prm.erow_bstride[t] + it;
+            }
+        }
+        const double *bsrc = (prow < SEP_KC ? prm.bc : prm.bs) + batch * prm.b_bstride + col0;
+        const double *proj =
+            prm.proj ? prm.proj + batch * prm.proj_bstride + (int64_t)comp * prm.n_modes_pad : nullptr;
+
+        for (int s = 0; s < n_stages_total; ++s) {
+            const int slot = s % SEP_STAGES;
+            const int round = s / SEP_STAGES;
+            if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+            double *Ar = stage_base + slot * SEP_STAGE_DOUBLES;
+            double *Ai = Ar + SEP_KC * SEP_TM;
+            double *Bc = Ai + SEP_KC * SEP_TM;
+            const int64_t j0 = (int64_t)s * SEP_KC;
+
+            // (a) B operand: 2*KC bulk copies of one 1 KB table-row slice each (Bc rows, then Bs rows)
+            if (prow < 2 * SEP_KC) {
+                mbar_expect_tx(&full[slot], SEP_TN * sizeof(double));
+                bulk_g2s(Bc + prow * SEP_TN, bsrc + (j0 + (prow % SEP_KC)) * prm.lc_pad,
+                         SEP_TN * sizeof(double), &full[slot]);
+            }
+            // (b) A operand generated on the fly, KC/2 modes per batch of loads
+#pragma unroll
+            for (int kh = 0; kh < SEP_KC; kh += 4) {
+                double2 e[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e[u] = __ldg(ep[0] + (j0 + kh + u) * prm.row_stride[0]);
+#pragma unroll
+                for (int t = 1; t < NRA; ++t) {
+                    double2 f[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) f[u] = __ldg(ep[t] + (j0 + kh + u) * prm.row_stride[t]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double re = e[u].x * f[u].x - e[u].y * f[u].y;
+                        const double im = e[u].x * f[u].y + e[u].y * f[u].x;
+                        e[u].x = re;
+                        e[u].y = im;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double pj = proj ? proj[j0 + kh + u] : 1.0;
+                    Ar[(kh + u) * SEP_TM + prow] = pj * e[u].x;
+                    Ai[(kh + u) * SEP_TM + prow] = -(pj * e[u].y);
+                }
+            }
+            mbar_arrive(&full[slot]);  // release: this thread's A row is written
+        }
+    } else {
+        // ============================== CONSUMER WARPGROUPS ============================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SEP_REGS_CONSUMER));
+        const int wr = warp >> 1;        // 0..3 : 32-row band
+        const int wc = warp & 1;         // 0..1 : 64-column band
+        const int g = lane >> 3;         // 0..3
+        const int h = lane & 7;          // 0..7
+        // thread rows: wr*32 + 8*i + 2*g + {0,1}, i = 0..3 ; cols: wc*64 + 16*i + 2*h + {0,1}
+        const int arow = wr * 32 + 2 * g;
+        const int bcol = wc * 64 + 2 * h;
+
+        double acc[8][8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+
+        for (int s = 0; s < n_stages_total; ++s) {
+            const int slot = s % SEP_STAGES;
+            mbar_wait(&full[slot], (s / SEP_STAGES) & 1);
+            const double *Ar = stage_base + slot * SEP_STAGE_DOUBLES;
+            const double *Ai = Ar + SEP_KC * SEP_TM;
+            const double *Bc = Ai + SEP_KC * SEP_TM;
+            const double *Bs = Bc + SEP_KC * SEP_TN;
+#pragma unroll
+            for (int kc = 0; kc < SEP_KC; ++kc) {
+                double ar[8], ai[8], bc[8], bs[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double2 va = *reinterpret_cast<const double2 *>(Ar + kc * SEP_TM + arow + 8 * i);
+                    const double2 vi = *reinterpret_cast<const double2 *>(Ai + kc * SEP_TM + arow + 8 * i);
+                    const double2 vc = *reinterpret_cast<const double2 *>(Bc + kc * SEP_TN + bcol + 16 * i);
+                    const double2 vs = *reinterpret_cast<const double2 *>(Bs + kc * SEP_TN + bcol + 16 * i);
+                    ar[2 * i] = va.x; ar[2 * i + 1] = va.y;
+                    ai[2 * i] = vi.x; ai[2 * i + 1] = vi.y;
+                    bc[2 * i] = vc.x; bc[2 * i + 1] = vc.y;
+                    bs[2 * i] = vs.x; bs[2 * i + 1] = vs.y;
+                }
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) acc[a][b] = fma(ar[a], bc[b], acc[a][b]);
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) acc[a][b] = fma(ai[a], bs[b], acc[a][b]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+
+        // epilogue: out[batch][comp][row][col]
+        double *out = prm.out + (batch * prm.ncomp + comp) * prm.out_fstride;
+        const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int64_t row = row0 + arow + 8 * (a >> 1) + (a & 1);
+            if (row >= prm.n_rows) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t col = col0 + bcol + 16 * i;
+                double *dst = out + row * prm.lc + col;
+                if (vec2 && col + 1 < prm.lc) {
+                    *reinterpret_cast<double2 *>(dst) = make_double2(acc[a][2 * i], acc[a][2 * i + 1]);
+                } else {
+                    if (col < prm.lc) dst[0] = acc[a][2 * i];
+                    if (col + 1 < prm.lc) dst[1] = acc[a][2 * i + 1];
+                }
+            }
+        }
+    }
+}
+
+inline int launch_separable(const SepParams &prm, int64_t n_batch, cudaStream_t st)
+{
+    dim3 grid((unsigned)(prm.lc_pad / SEP_TN), (unsigned)((prm.n_rows + SEP_TM - 1) / SEP_TM),
+              (unsigned)(n_batch * prm.ncomp));
+    if (grid.y > 65535u || grid.z > 65535u)
+        return fail(GSB_ERR_ARGUMENT, "structured mesh too large for one launch (rows/128 or batch*ncomp > 65535)");
+#define GSB_SEP_CASE(N)                                                                        \
+    case N: {                                                                                  \
+        static bool attr_done = false;                                                         \
+        (void)attr_done;                                                                       \
+        GSB_CUDA(cudaFuncSetAttribute(separable_kernel<N>,                                     \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                      (int)SEP_SMEM_BYTES));                                   \
+        separable_kernel<N><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(prm);                   \
+        break;                                                                                 \
+    }
+    switch (prm.n_row_axes) {
+        GSB_SEP_CASE(1)
+        GSB_SEP_CASE(2)
+        GSB_SEP_CASE(3)
+        GSB_SEP_CASE(4)
+        GSB_SEP_CASE(5)
+        GSB_SEP_CASE(6)
+        GSB_SEP_CASE(7)
+    default:
+        return fail(GSB_ERR_ARGUMENT, "structured path needs 2 <= dim <= 8");
+    }
+#undef GSB_SEP_CASE
+    g_launches.fetch_add(1);
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+// device-side mesh expansion for meshes too small for the tiled kernel:
+// pos[t][r] = sum_s M[t][s] a_s[i_s(r)], r in C order (generate_grid + isometrize).
+struct ExpandParams {
+    const double *axes;
+    int64_t axis_off[GSB_MAX_DIM];
+    int64_t axis_len[GSB_MAX_DIM];
+    double matrix[GSB_MAX_DIM * GSB_MAX_DIM];
+    int dim;
+    int64_t n;
+    double *pos;  // (dim, n)
+};
+
+__global__ void expand_grid_kernel(const ExpandParams ep)
+{
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ep.n;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        double g[GSB_MAX_DIM];
+        int64_t rem = r;
+        for (int t = ep.dim - 1; t >= 0; --t) {
+            const int64_t it = rem % ep.axis_len[t];
+            rem /= ep.axis_len[t];
+            g[t] = ep.axes[ep.axis_off[t] + it];
+        }
+        for (int t = 0; t < ep.dim; ++t) {
+            // same left-to-right order as np.dot(matrix, pos) row t
+            double v = 0.0;
+            for (int s = 0; s < ep.dim; ++s) v += ep.matrix[t * ep.dim + s] * g[s];
+            ep.pos[(int64_t)t * ep.n + r] = v;
+        }
+    }
+}
+
+}  // namespace gsb

@@ -1,0 +1,131 @@
+/*
+ * gsb200.h -- C ABI of the B200-native randomisation-method summator.
+ *
+ * This is the drop-in boundary for the ONE hot path of GSTools: the native
+ * `summate` / `summate_incompr` functions that gstools imports from gstools-cython /
+ * gstools_core and dispatches through `_summate` / `_summate_incompr`.
+ * Every entry point cites the reference interface it replaces (paths relative to
+ * the reference repository root).
+ *
+ * Conventions
+ *   - All arrays are fp64, row-major.  `cov_samples` is (dim, n_modes), `z_1`/`z_2`
+ *     are (n_modes,), `pos` is (dim, n_pts) with row stride `pos_ld` (elements),
+ *     scalar output is (n_pts,), vector output is (dim, n_pts) with row stride `out_ld`.
+ *   - `mem` says where EVERY pointer of the call lives: GSB_MEM_HOST (the library
+ *     stages host<->device copies itself) or GSB_MEM_DEVICE (pointers are device
+ *     pointers on `device`, nothing is copied; work is enqueued on `stream` and the
+ *     call returns without synchronising).
+ *   - Inputs are never modified.  The caller owns all buffers.
+ *   - Return value: 0 on success, non-zero on error; gsb_last_error() then returns a
+ *     thread-local message.  No exception crosses this boundary.
+ *   - The sqrt(var/N) scale and the nugget are NOT applied here; as in the reference
+ *     they belong to the caller (src/gstools/field/generator.py:269-270, 561-567).
+ *   - There is no CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef GSB200_H
+#define GSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_MEM_HOST 0
+#define GSB_MEM_DEVICE 1
+
+#define GSB_OK 0
+#define GSB_ERR_ARGUMENT 1
+#define GSB_ERR_CUDA 2
+#define GSB_ERR_NO_DEVICE 3
+
+#define GSB_MAX_DIM 8
+
+/* Library version (major*10000 + minor*100 + patch). */
+int gsb_version(void);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char *gsb_last_error(void);
+
+/* Number of visible CUDA devices (0 when there is none; that is not an error). */
+int gsb_device_count(int *count);
+
+/*
+ * gsb_summate -- replaces gstools_cython.field.summate / gstools_core.summate
+ *   imported at src/gstools/field/generator.py:22,32; called at generator.py:48
+ *   as summate_fct(cov_samples, z_1, z_2, pos, num_threads).
+ *   out[i] = sum_j z_1[j] cos(k_j . x_i) + z_2[j] sin(k_j . x_i)     (generator.py:193-199)
+ * Unstructured ("direct") kernel; any dim in 1..GSB_MAX_DIM.
+ */
+int gsb_summate(const double *cov_samples, const double *z_1, const double *z_2,
+                const double *pos, int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts,
+                double *out, int mem, int device, void *stream);
+
+/*
+ * gsb_summate_incompr -- replaces gstools_cython.field.summate_incompr /
+ *   gstools_core.summate_incompr (generator.py:24,34; called at generator.py:64).
+ *   out[t,i] = sum_j p_t(k_j) (z_1[j] cos(k_j.x_i) + z_2[j] sin(k_j.x_i)),
+ *   p_t(k) = delta_{t0} - k_t k_0 / |k|^2                             (generator.py:479-495)
+ */
+int gsb_summate_incompr(const double *cov_samples, const double *z_1, const double *z_2,
+                        const double *pos, int64_t pos_ld, int dim, int64_t n_modes,
+                        int64_t n_pts, double *out, int64_t out_ld, int mem, int device,
+                        void *stream);
+
+/*
+ * gsb_summate_structured[_incompr] -- the same sums on a structured (rectilinear) mesh
+ * WITHOUT the flat (dim, n) position array.  The reference expands the mesh on the host
+ * (src/gstools/field/base.py:289-290 -> tools/geometric.py:340-356 generate_grid) and
+ * isometrises it (base.py:297 -> covmodel/base.py:572-582, pos_iso = matrix @ pos) before
+ * calling summate; this entry takes the axes and the (dim x dim) isometrisation matrix
+ * instead (matrix == NULL means identity) and evaluates
+ *     out[i_0,...,i_{d-1}] = summate(cov_samples, z_1, z_2, matrix @ (axes_0[i_0],...))
+ * in C order (last axis fastest), i.e. exactly the array the reference reshapes at
+ * src/gstools/field/srf.py:156.
+ *   axes      : all axis coordinates concatenated, sum(axis_len) doubles
+ *   axis_len  : dim entries
+ *   n_batch   : number of independent mode sets evaluated on the same mesh
+ *               (ensembles: examples/06_conditioned_fields/01_2D_condition_ensemble.py:32-35);
+ *               cov_samples is (n_batch, dim, n_modes), z_1/z_2 are (n_batch, n_modes),
+ *               out is (n_batch, n) resp. (n_batch, dim, n).  n_batch = 1 for a single field.
+ */
+int gsb_summate_structured(const double *cov_samples, const double *z_1, const double *z_2,
+                           const double *axes, const int64_t *axis_len, const double *matrix,
+                           int dim, int64_t n_modes, int64_t n_batch, double *out, int mem,
+                           int device, void *stream);
+
+int gsb_summate_incompr_structured(const double *cov_samples, const double *z_1,
+                                   const double *z_2, const double *axes,
+                                   const int64_t *axis_len, const double *matrix, int dim,
+                                   int64_t n_modes, int64_t n_batch, double *out, int mem,
+                                   int device, void *stream);
+
+/*
+ * Fused caller epilogue (reference: src/gstools/field/generator.py:269-270):
+ *   field[i] = scale * field[i] + shift     in place, device pointers only.
+ * Lets a device-resident caller keep the field on the GPU.
+ */
+int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int device,
+                    void *stream);
+
+/*
+ * Tuning / introspection.
+ *   gsb_set_option("structured_min_tiles", v): meshes with fewer 128x128 output tiles than v
+ *       are expanded on the device and sent through the direct kernel (default 64).
+ *   gsb_set_option("force_path", 0|1|2): 0 auto, 1 always direct, 2 always separable.
+ *   gsb_get_counter("launches"): CUDA kernels launched by this library so far (process-wide).
+ */
+int gsb_set_option(const char *name, int64_t value);
+int64_t gsb_get_counter(const char *name);
+
+/*
+ * FP64-pipe microbenchmark used as the roofline denominator: runs a register-resident
+ * DFMA loop on every SM and reports sustained DFMA/s (fused multiply-adds per second,
+ * 1 DFMA = 2 flop).  `kind` 0 = DFMA (CUDA cores), 1 = DMMA m8n8k4 (tensor path).
+ */
+int gsb_measure_fp64_peak(int device, int kind, double seconds, double *fma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB200_H */
