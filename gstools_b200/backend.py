@@ -149,7 +149,13 @@ def _flat_device(lib, cov_samples, z_1, z_2, pos, vec):
     def prep(x):
         return torch.as_tensor(x, dtype=torch.float64, device=dev).contiguous()
 
-    cov, z1, z2, p = prep(cov_samples), prep(z_1), prep(z_2), prep(pos)
+    cov, z1, z2 = prep(cov_samples), prep(z_1), prep(z_2)
+    p = torch.as_tensor(pos, dtype=torch.float64, device=dev)
+    ld = None
+    if p.ndim == 2 and p.shape[1] > 0 and p.stride(1) == 1 and p.stride(0) >= p.shape[1]:
+        ld = p.stride(0)  # row-strided view (a point range of a bigger array): no copy
+    else:
+        p = p.contiguous()
     if cov.ndim != 2 or z1.ndim != 1 or z2.ndim != 1 or z1.shape[0] != cov.shape[1] \
             or z2.shape[0] != cov.shape[1]:
         raise ValueError("cov_samples must be (dim, mode_no); z_1, z_2 must be (mode_no,)")
@@ -157,16 +163,17 @@ def _flat_device(lib, cov_samples, z_1, z_2, pos, vec):
         raise ValueError("pos must have shape (dim, n) with the same dim as cov_samples")
     dim, n_modes = cov.shape
     n = p.shape[1]
+    ld = ld or max(n, 1)
     stream = torch.cuda.current_stream(dev).cuda_stream
     if vec:
         out = torch.empty((dim, n), dtype=torch.float64, device=dev)
         rc = lib.gsb_summate_incompr(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(),
-                                     max(n, 1), dim, n_modes, n, out.data_ptr(), max(n, 1),
+                                     ld, dim, n_modes, n, out.data_ptr(), max(n, 1),
                                      _lib.MEM_DEVICE, dev.index, stream)
         _lib.check(rc, "summate_incompr")
     else:
         out = torch.empty((n,), dtype=torch.float64, device=dev)
-        rc = lib.gsb_summate(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), max(n, 1),
+        rc = lib.gsb_summate(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), ld,
                              dim, n_modes, n, out.data_ptr(), _lib.MEM_DEVICE, dev.index, stream)
         _lib.check(rc, "summate")
     return out

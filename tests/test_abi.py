@@ -1,0 +1,93 @@
+"""The C-ABI library: loads, exports every declared symbol, validates arguments.  CPU only
+(no compute call succeeds without a GPU -- and that failure must be loud)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(REPO, "include", "gsb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for must in ("gsb_summate", "gsb_summate_incompr", "gsb_summate_structured",
+                 "gsb_summate_incompr_structured", "gsb_last_error", "gsb_version"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(gsb):
+    lib = ctypes.CDLL(gsb._lib.lib_path())
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/gsb200.h but not exported"
+
+
+def test_binding_table_covers_header(gsb):
+    assert sorted(gsb._lib.SIGNATURES) == declared_symbols()
+
+
+def test_version_and_device_count(gsb):
+    assert gsb._lib.load().gsb_version() >= 100
+    assert gsb.device_count() >= 0
+
+
+def test_argument_errors_need_no_gpu(gsb):
+    lib = gsb._lib.load()
+    a = np.zeros(8)
+    p = a.ctypes.data
+    # dim out of range
+    assert lib.gsb_summate(p, p, p, p, 1, 0, 1, 1, p, 0, 0, None) == 1
+    assert b"dim" in lib.gsb_last_error()
+    # negative sizes
+    assert lib.gsb_summate(p, p, p, p, 1, 2, -1, 1, p, 0, 0, None) == 1
+    assert lib.gsb_summate(p, p, p, p, 1, 2, 1, -1, p, 0, 0, None) == 1
+    # NULL buffers
+    assert lib.gsb_summate(None, p, p, p, 1, 2, 1, 1, p, 0, 0, None) == 1
+    # leading dimension too small
+    assert lib.gsb_summate(p, p, p, p, 1, 2, 1, 4, p, 0, 0, None) == 1
+    # vector field dims (generator.py:514-517)
+    assert lib.gsb_summate_incompr(p, p, p, p, 1, 1, 1, 1, p, 1, 0, 0, None) == 1
+    # bad mem kind
+    assert lib.gsb_summate(p, p, p, p, 1, 2, 1, 1, p, 7, 0, None) == 1
+    # unknown option
+    assert lib.gsb_set_option(b"nope", 1) == 1
+    assert lib.gsb_get_counter(b"nope") == -1
+
+
+def test_empty_inputs_return_without_device(gsb):
+    out = gsb.summate(np.zeros((2, 4)), np.zeros(4), np.zeros(4), np.zeros((2, 0)))
+    assert out.shape == (0,)
+    out = gsb.summate_incompr(np.zeros((3, 4)), np.zeros(4), np.zeros(4), np.zeros((3, 0)))
+    assert out.shape == (3, 0)
+    out = gsb.summate_structured(np.zeros((2, 4)), np.zeros(4), np.zeros(4),
+                                 [np.zeros(0), np.zeros(3)])
+    assert out.shape == (0, 3)
+
+
+def test_no_cpu_fallback_is_loud(gsb):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(gsb.GSB200Error, match="no CPU fallback"):
+        gsb.summate(np.zeros((2, 4)), np.zeros(4), np.zeros(4), np.zeros((2, 3)))
+    with pytest.raises(gsb.GSB200Error):
+        gsb.summate_structured(np.zeros((2, 4)), np.zeros(4), np.zeros(4),
+                               [np.arange(3.0), np.arange(3.0)])
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(REPO, "gstools_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "liboracle" not in text, f

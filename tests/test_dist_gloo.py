@@ -1,0 +1,84 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: partition + gather.
+
+The compute function is injected (the CPU oracle stands in for the CUDA kernels), so what is
+covered here is exactly the host logic that runs unchanged with NCCL on the GPU box."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, tmpdir):
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    import oracle
+    from conftest import synth_modes
+    from gstools_b200 import dist as gdist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cov, z1, z2 = synth_modes(3, 64, seed=5)
+        # ---- flat points, uneven split (n = 1001) ----
+        pos = np.random.RandomState(0).uniform(0, 100, (3, 1001))
+        local, (lo, hi) = gdist.summate_sharded(cov, z1, z2, pos, compute=oracle.summate)
+        assert local.shape == (hi - lo,)
+        full = gdist.gather_field(local, 1001)
+        want = oracle.summate(cov, z1, z2, pos)
+        assert np.array_equal(full, want)
+        only0 = gdist.gather_field(local, 1001, dst=0)
+        assert (only0 is None) == (rank != 0)
+        if rank == 0:
+            assert np.array_equal(only0, want)
+        # ---- vector field: gather along the point axis (axis 1) ----
+        lv, _ = gdist.summate_sharded(cov, z1, z2, pos, incompr=True, compute=oracle.summate_incompr)
+        fv = gdist.gather_field(lv, 1001, axis=1)
+        assert np.array_equal(fv, oracle.summate_incompr(cov, z1, z2, pos))
+
+        # ---- structured slabs along axis 0 (7 x 5 x 4 mesh: uneven 4 + 3) ----
+        axes = [np.linspace(0, 9, 7), np.linspace(-3, 3, 5), np.arange(4.0)]
+
+        def struct_compute(c, a, b, ax, matrix):
+            grid = np.stack([g.reshape(-1) for g in np.meshgrid(*ax, indexing="ij")])
+            return oracle.summate(c, a, b, grid).reshape([len(x) for x in ax])
+
+        slab, (lo, hi) = gdist.summate_structured_sharded(cov, z1, z2, axes, compute=struct_compute)
+        assert slab.shape == (hi - lo, 5, 4)
+        field = gdist.gather_field(slab, 7)
+        assert np.array_equal(field, struct_compute(cov, z1, z2, axes, None))
+
+        # ---- ensemble: seeds sharded, no collective ----
+        sets = [synth_modes(3, 16, seed=s) for s in range(5)]
+        mine, (lo, hi) = gdist.ensemble_sharded(sets, lambda m: oracle.summate(*m, pos[:, :50]))
+        assert len(mine) == hi - lo and (lo, hi) == gdist.shard_range(5, rank, world)
+        for f, s in zip(mine, range(lo, hi)):
+            assert np.array_equal(f, oracle.summate(*sets[s], pos[:, :50]))
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    import oracle
+
+    oracle.build()
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

@@ -1,0 +1,138 @@
+"""The five BASELINE.json configs at FULL size on the GPU, checked through the oracle on samples
+and through size-independent properties (sign symmetry, slab/batch invariance, agreement of the
+two kernels)."""
+import numpy as np
+import pytest
+
+import bench_configs as bc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def sample_check(field_flat, cfg, oracle_mod, n_sample, seed, vec=False):
+    """max |GPU - oracle| * sqrt(var/N) on a random sample of mesh nodes (+ the 8 corners)."""
+    n = int(np.prod([len(a) for a in cfg["axes"]]))
+    rs = np.random.RandomState(seed)
+    idx = np.unique(np.concatenate([rs.randint(0, n, n_sample), [0, n - 1]]))
+    pos = bc.grid_points(cfg["axes"], cfg.get("matrix"), idx)
+    n_modes = cfg["cov"].shape[-1]
+    scale = np.sqrt(cfg["var"] / n_modes)
+    if vec:
+        want = oracle_mod.summate_incompr(cfg["cov"], cfg["z1"], cfg["z2"], pos)
+        return np.max(np.abs(field_flat[:, idx] - want)) * scale
+    want = oracle_mod.summate(cfg["cov"], cfg["z1"], cfg["z2"], pos)
+    return np.max(np.abs(field_flat[idx] - want)) * scale
+
+
+def test_config1_full(gsb, oracle_mod):
+    cfg = bc.config1()
+    scale = np.sqrt(1.0 / 1000)
+    for force in (1, 2):
+        gsb.set_option("force_path", force)
+        try:
+            got = gsb.summate_structured(cfg["cov"], cfg["z1"], cfg["z2"], cfg["axes"])
+        finally:
+            gsb.set_option("force_path", 0)
+        assert np.max(np.abs(got.reshape(-1) - cfg["raw"])) * scale <= TOL
+        assert np.max(np.abs(scale * got - cfg["field"])) <= TOL
+    flat = gsb.summate(cfg["cov"], cfg["z1"], cfg["z2"], cfg["pos"])
+    assert np.max(np.abs(flat - cfg["raw"])) * scale <= TOL
+
+
+def test_config2_full_512cubed(gsb, oracle_mod):
+    import torch
+
+    cfg = bc.config2(512)
+    dev = torch.device("cuda:0")
+    tc, t1, t2 = (torch.tensor(cfg[k], device=dev) for k in ("cov", "z1", "z2"))
+    axes = [torch.tensor(a, device=dev) for a in cfg["axes"]]
+    out = gsb.summate_structured(tc, t1, t2, axes)
+    assert tuple(out.shape) == (512, 512, 512)
+    flat = out.reshape(-1)
+    # oracle on 20000 random nodes + corners
+    n = 512 ** 3
+    rs = np.random.RandomState(1)
+    idx = np.unique(np.concatenate([rs.randint(0, n, 20000), [0, n - 1, 511, 512 * 511]]))
+    got = flat[torch.tensor(idx, device=dev)].cpu().numpy()
+    want = oracle_mod.summate(cfg["cov"], cfg["z1"], cfg["z2"], bc.grid_points(cfg["axes"], None, idx))
+    assert np.max(np.abs(got - want)) * np.sqrt(1.0 / 1000) <= TOL
+    # exact sign symmetry at full size: u(-z1, -z2) == -u(z1, z2) bit for bit
+    neg = gsb.summate_structured(tc, -t1, -t2, axes)
+    assert torch.equal(neg, -out)
+    del neg
+    # direct kernel on 4 whole x-planes agrees with the separable kernel
+    for ix in (0, 137, 300, 511):
+        yy, zz = np.meshgrid(cfg["axes"][1], cfg["axes"][2], indexing="ij")
+        pos = np.stack([np.full(yy.size, cfg["axes"][0][ix]), yy.reshape(-1), zz.reshape(-1)])
+        plane = gsb.summate(tc, t1, t2, torch.tensor(pos, device=dev)).reshape(512, 512)
+        assert float((plane - out[ix]).abs().max()) * np.sqrt(1.0 / 1000) <= TOL
+    # host-buffer route (slab pipeline, D2H) returns the same bits
+    host = gsb.summate_structured(cfg["cov"], cfg["z1"], cfg["z2"], cfg["axes"])
+    assert np.array_equal(host[::37], out[::37].cpu().numpy())
+
+
+def test_config3_full_20m_points(gsb, oracle_mod):
+    import torch
+
+    cfg = bc.config3(20_000_000)
+    dev = torch.device("cuda:0")
+    tpos = torch.tensor(cfg["pos"], device=dev)
+    out = gsb.summate(cfg["cov"], cfg["z1"], cfg["z2"], tpos)
+    idx = np.random.RandomState(2).randint(0, 20_000_000, 8000)
+    want = oracle_mod.summate(cfg["cov"], cfg["z1"], cfg["z2"], cfg["pos"][:, idx])
+    got = out[torch.tensor(idx, device=dev)].cpu().numpy()
+    assert np.max(np.abs(got - want)) * np.sqrt(1.0 / 10000) <= TOL
+    # value of a point is independent of the batch it is evaluated in (sharding unit)
+    sub = gsb.summate(cfg["cov"], cfg["z1"], cfg["z2"], tpos[:, 5_000_000:5_100_000])
+    assert torch.equal(sub, out[5_000_000:5_100_000])
+    # host-buffer route over pipelined chunks: same bits on a 6M-point prefix
+    host = gsb.summate(cfg["cov"][:, :500], cfg["z1"][:500], cfg["z2"][:500], cfg["pos"][:, :6_000_000])
+    devp = gsb.summate(cfg["cov"][:, :500], cfg["z1"][:500], cfg["z2"][:500], tpos[:, :6_000_000])
+    assert np.array_equal(host, devp.cpu().numpy())
+
+
+def test_config4_full_incompressible_256cubed(gsb, oracle_mod):
+    import torch
+
+    cfg = bc.config4(256)
+    dev = torch.device("cuda:0")
+    tc, t1, t2 = (torch.tensor(cfg[k], device=dev) for k in ("cov", "z1", "z2"))
+    axes = [torch.tensor(a, device=dev) for a in cfg["axes"]]
+    out = gsb.summate_incompr_structured(tc, t1, t2, axes)
+    assert tuple(out.shape) == (3, 256, 256, 256)
+    flat = out.reshape(3, -1).cpu().numpy()
+    assert sample_check(flat, cfg, oracle_mod, 8000, seed=3, vec=True) <= TOL
+    # incompressibility: the spectral projector makes every mode divergence free, so the
+    # analytic divergence sum_t k_t p_t(k) vanishes identically
+    k = cfg["cov"]
+    proj = np.eye(3)[:, 0][:, None] - k * k[0] / np.sum(k * k, axis=0)
+    assert np.max(np.abs(np.sum(k * proj, axis=0))) < 1e-15
+    # flat direct kernel on a sub-block agrees
+    sub_axes = [cfg["axes"][0][:8], cfg["axes"][1][100:140], cfg["axes"][2]]
+    pos = bc.grid_points(sub_axes)
+    direct = gsb.summate_incompr(cfg["cov"], cfg["z1"], cfg["z2"], pos).reshape(3, 8, 40, 256)
+    assert np.max(np.abs(direct - out[:, :8, 100:140].cpu().numpy())) * np.sqrt(1.0 / 1000) <= TOL
+
+
+def test_config5_full_ensemble_256x128cubed(gsb, oracle_mod):
+    import torch
+
+    cfg = bc.config5(128, 256)
+    dev = torch.device("cuda:0")
+    tc, t1, t2 = (torch.tensor(cfg[k], device=dev) for k in ("cov", "z1", "z2"))
+    axes = [torch.tensor(a, device=dev) for a in cfg["axes"]]
+    out = gsb.summate_structured(tc, t1, t2, axes)          # (256, 128, 128, 128): 4.3 GB
+    assert tuple(out.shape) == (256, 128, 128, 128)
+    n = 128 ** 3
+    rs = np.random.RandomState(4)
+    idx = rs.randint(0, n, 1500)
+    pos = bc.grid_points(cfg["axes"], None, idx)
+    tidx = torch.tensor(idx, device=dev)
+    for b in (0, 1, 7, 8, 100, 255):   # the reference's own draws (0..7) and synthetic ones
+        want = oracle_mod.summate(cfg["cov"][b], cfg["z1"][b], cfg["z2"][b], pos)
+        got = out[b].reshape(-1)[tidx].cpu().numpy()
+        assert np.max(np.abs(got - want)) * np.sqrt(1.0 / 1000) <= TOL
+    # one realisation computed alone == the same realisation inside the batch (seed sharding)
+    single = gsb.summate_structured(tc[37], t1[37], t2[37], axes)
+    assert torch.equal(single, out[37])

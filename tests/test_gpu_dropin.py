@@ -1,0 +1,184 @@
+"""Drop-in tests on the GPU: an UNMODIFIED gstools (baseline/_ref on the GPU box, /root/reference
+in the build container) with gstools_b200.enable() -- SRF / CondSRF run unchanged."""
+import numpy as np
+import pytest
+
+import refharness
+from conftest import load_golden
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not refharness.have_reference(), reason="reference gstools not present")]
+
+TOL = 1e-9
+
+
+@pytest.fixture()
+def gs_b200(gsb):
+    gs = refharness.import_gstools()
+    gsb.enable()
+    yield gs
+    gsb.disable()
+
+
+def test_config1_readme_example_through_srf(gs_b200, gsb):
+    """BASELINE.json configs[0]: gs.SRF(Gaussian(dim=2,var=1,len_scale=10), seed=20170519) on a
+    structured 100x100 grid (README example, tests/test_pgs.py:33-75)."""
+    gs = gs_b200
+    meta, d = load_golden("config1_gaussian2d_100x100")
+    srf = gs.SRF(gs.Gaussian(dim=2, var=1, len_scale=10), seed=20170519)
+    launches = gsb.get_counter("launches")
+    field = srf.structured([np.arange(100.0), np.arange(100.0)])
+    assert gsb.get_counter("launches") > launches, "the CUDA path did not run"
+    assert field.shape == (100, 100)
+    assert np.max(np.abs(field - d["field"])) <= TOL * np.sqrt(meta["var"])
+    # values quoted in SURVEY.md 8(d) for this config
+    assert abs(field[0, 0] - -0.221389860323504) < 1e-9
+    assert abs(field[50, 50] - 1.135479083967714) < 1e-9
+    # unstructured call on the same nodes gives the same field
+    x, y = np.meshgrid(np.arange(100.0), np.arange(100.0), indexing="ij")
+    f2 = srf((x.reshape(-1), y.reshape(-1)))
+    assert np.max(np.abs(f2.reshape(100, 100) - d["field"])) <= TOL
+
+
+def test_reference_randmeth_tests_on_gpu(gs_b200):
+    """tests/test_randmeth.py:33-71 rerun with the B200 backend active."""
+    gs = gs_b200
+    from gstools.field.generator import RandMeth
+
+    x = np.linspace(0.0, 10.0, 10)
+    y = np.linspace(-5.0, 5.0, 10)
+    z = np.linspace(-6.0, 8.0, 10)
+    m1 = gs.Gaussian(dim=1, var=1.5, len_scale=3.5)
+    m2 = gs.Gaussian(dim=2, var=1.5, len_scale=3.5)
+    m3 = gs.Gaussian(dim=3, var=1.5, len_scale=3.5)
+    rm1, rm2, rm3 = (RandMeth(m, mode_no=100, seed=19031977) for m in (m1, m2, m3))
+    modes = rm1((x,))
+    assert round(modes[0] - 3.19799030, 7) == 0 and round(modes[1] - 2.44848295, 7) == 0
+    modes = rm2((x, y))
+    assert round(modes[0] - 1.67318010, 7) == 0 and round(modes[1] - 2.12310269, 7) == 0
+    modes = rm3((x, y, z))
+    assert round(modes[0] - 1.3240234883187239, 7) == 0
+    assert round(modes[1] - 1.6367244277732766, 7) == 0
+    rm2.seed = 74893621
+    modes = rm2((x, y))
+    assert round(modes[0] - -1.94278053, 7) == 0 and round(modes[1] - -1.12401651, 7) == 0
+    rm2.mode_no = 800
+    modes = rm2((x, y))
+    assert round(modes[0] - -3.20809251, 7) == 0 and round(modes[1] - -2.62032778, 7) == 0
+
+
+def test_reference_incompr_tests_on_gpu(gs_b200):
+    """tests/test_incomprrandmeth.py:34-59 and tests/test_srf.py:259-275 with the B200 backend."""
+    gs = gs_b200
+    from gstools.field.generator import IncomprRandMeth
+
+    x = np.linspace(0.0, 10.0, 10)
+    y = np.linspace(-5.0, 5.0, 10)
+    z = np.linspace(-6.0, 8.0, 10)
+    rm = IncomprRandMeth(gs.Gaussian(dim=2, var=1.5, len_scale=2.5), mode_no=100, seed=19031977)
+    modes = rm((x, y))
+    assert round(modes[0, 0] - 0.50751115, 7) == 0
+    assert round(modes[0, 1] - 1.03291018, 7) == 0
+    assert round(modes[1, 1] - -0.22003005, 7) == 0
+    rm = IncomprRandMeth(gs.Gaussian(dim=3, var=1.5, len_scale=2.5), mode_no=100, seed=19031977)
+    modes = rm((x, y, z))
+    assert round(modes[0, 0] - 0.7924546333550331, 7) == 0
+    assert round(modes[0, 1] - 1.660747056686244, 7) == 0
+    assert round(modes[1, 0] - -0.28049855754819514, 7) == 0
+    srf = gs.SRF(gs.Gaussian(dim=2, var=1.5, len_scale=2.5), mean=(0.5, 0), generator="VectorField",
+                 seed=198412031)
+    srf.structured((np.linspace(0.0, 10.0, 9), np.linspace(-5.0, 5.0, 16)))
+    assert round(np.mean(srf.field[0]) - 1.3025621393180298, 7) == 0
+    assert round(np.mean(srf.field[1]) - -0.04729596839446052, 7) == 0
+    # tests/test_srf.py:259-275
+    srf = gs.SRF(gs.Gaussian(dim=2, var=0.5, len_scale=1.0), mean=0.3, mode_no=100,
+                 generator="IncomprRandMeth", mean_velocity=0.5)
+    rng = np.random.RandomState(123018)
+    xt, yt = rng.uniform(0.0, 10, 100), rng.uniform(0.0, 10, 100)
+    field = srf((xt, yt), seed=476356)
+    assert round(field[0, 0] - 1.23693272, 7) == 0 and round(field[0, 1] - 0.89242284, 7) == 0
+    field = srf((np.linspace(0.0, 12.0, 48), np.linspace(0.0, 10.0, 46)), seed=4734654,
+                mesh_type="structured")
+    assert round(field[0, 0, 0] - 1.07812013, 7) == 0 and round(field[0, 1, 0] - 1.06180674, 7) == 0
+
+
+def test_structured_side_channel_rotation_anisotropy(gs_b200, gsb):
+    """3D rotated + anisotropic model on non-uniform axes: the lazy structured route (no host
+    mesh expansion) reproduces the field the reference computed from the flat positions."""
+    gs = gs_b200
+    meta, d = load_golden("srf_exp3d_rot_anis_struct")
+    model = gs.Exponential(dim=3, var=2.0, len_scale=[12.0, 5.0, 3.0], angles=[0.4, -0.3, 0.7])
+    srf = gs.SRF(model, seed=20170519, mode_no=256)
+    gsb.set_option("force_path", 2)  # the mesh is small; force the separable kernel
+    try:
+        before = gsb.get_counter("separable_calls")
+        field = srf.structured([d["axis0"], d["axis1"], d["axis2"]])
+        assert gsb.get_counter("separable_calls") == before + 1
+    finally:
+        gsb.set_option("force_path", 0)
+    assert field.shape == d["field"].shape
+    assert np.max(np.abs(field - d["field"])) <= TOL * np.sqrt(2.0)
+    # relational checks of tests/test_srf.py:85-98,122-163 (anisotropy / rotation invariances)
+    x = np.linspace(0, 10, 21)
+    iso = gs.SRF(gs.Gaussian(dim=2, var=1.5, len_scale=4.0), mean=0.3, mode_no=100)
+    f_iso = iso((x, x), seed=825718662, mesh_type="structured")
+    ani = gs.SRF(gs.Gaussian(dim=2, var=1.5, len_scale=4.0, anis=0.5), mean=0.3, mode_no=100)
+    f_ani = ani((x, x), seed=825718662, mesh_type="structured")
+    assert abs(f_iso[0, 0] - f_ani[0, 0]) < 1e-9
+    assert abs(f_iso[0, 2] - f_ani[0, 1]) < 1e-9           # tests/test_srf.py:95-98
+    rot = gs.SRF(gs.Gaussian(dim=2, var=1.5, len_scale=4.0, angles=np.pi / 2.0), mean=0.3, mode_no=100)
+    xg, yg = np.linspace(-6, 6, 8), np.linspace(-6, 6, 8)
+    f0 = gs.SRF(gs.Gaussian(dim=2, var=1.5, len_scale=4.0), mean=0.3, mode_no=100)(
+        (xg, yg), seed=825718662, mesh_type="structured")
+    f1 = rot((xg, yg), seed=825718662, mesh_type="structured")
+    assert abs(f0[0, 0] - f1[0, -1]) < 1e-9                  # tests/test_srf.py:160-163
+    assert abs(f0[0, 1] - f1[1, -1]) < 1e-9
+
+
+def test_condsrf_ensemble_through_plugin(gs_b200, gsb):
+    """CondSRF (cond_srf.py:63-150): conditioned fields honour the data; kriging is reused
+    across seeds; every realisation's raw field comes from the GPU summator."""
+    gs = gs_b200
+    meta, d = load_golden("condsrf_1d")
+    krige = gs.krige.Ordinary(gs.Gaussian(dim=1, var=0.5, len_scale=2), [d["cond_pos"]], d["cond_val"])
+    csrf = gs.CondSRF(krige, mode_no=100)
+    f = csrf((d["gridx"],), seed=20170519)
+    assert np.max(np.abs(f - d["field"])) <= 1e-9
+    # 3D ensemble on a small structured mesh, seeds as in README.md:255-257
+    rs = np.random.RandomState(20170519)
+    cond_pos = rs.uniform(0, 15, (3, 20))
+    cond_val = rs.normal(size=20)
+    model = gs.Exponential(dim=3, var=1, len_scale=4)
+    krige = gs.krige.Ordinary(model, cond_pos, cond_val)
+    csrf = gs.CondSRF(krige, mode_no=200)
+    axes = [np.arange(16.0)] * 3
+    csrf.set_pos(axes, "structured")
+    seed = gs.random.MasterRNG(20170519)
+    launches = gsb.get_counter("launches")
+    fields = [csrf(seed=seed(), store=[f"fld{i}", False, False]) for i in range(4)]
+    assert gsb.get_counter("launches") >= launches + 4
+    assert all(f.shape == (16, 16, 16) for f in fields)
+    assert not np.allclose(fields[0], fields[1])
+    # conditioning: evaluate at the data locations
+    f_at = csrf(cond_pos, seed=123, mesh_type="unstructured")
+    assert np.max(np.abs(f_at - cond_val)) < 1e-6
+
+
+def test_backends_agree_and_switch_at_runtime(gs_b200, gsb):
+    """config flag is read at call time (docs/source/index.rst:131-132): flipping
+    USE_GSTOOLS_B200 switches an EXISTING generator between the GPU and the reference backend."""
+    gs = gs_b200
+    from gstools import config
+
+    srf = gs.SRF(gs.Exponential(dim=3, var=2.0, len_scale=5.0), seed=7, mode_no=300)
+    pos = np.random.RandomState(0).uniform(0, 50, (3, 4000))
+    f_gpu = srf(pos)
+    config.USE_GSTOOLS_B200 = False
+    try:
+        f_ref = srf(pos)
+        g_ref = srf.structured([np.arange(12.0)] * 3)
+    finally:
+        config.USE_GSTOOLS_B200 = True
+    g_gpu = srf.structured([np.arange(12.0)] * 3)
+    assert np.max(np.abs(f_gpu - f_ref)) <= TOL * np.sqrt(2.0)
+    assert np.max(np.abs(g_gpu - g_ref)) <= TOL * np.sqrt(2.0)

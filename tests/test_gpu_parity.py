@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures.  Tolerance from BASELINE.json north_star: max|delta| <= 1e-9 * sqrt(var) on the scaled
+field, i.e. max|delta_raw| <= 1e-9 * sqrt(N) on the raw sums (field = sqrt(var/N) * raw)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, synth_modes
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9  # relative to sqrt(var), see module docstring
+
+
+def raw_tol(n_modes):
+    return TOL * np.sqrt(max(n_modes, 1))
+
+
+def maxabs(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)))) if np.size(a) else 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures (recorded from the reference's own generators)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_boundary_arrays(name, gsb):
+    meta, d = load_golden(name)
+    fn = gsb.summate if meta["kind"] == "scalar" else gsb.summate_incompr
+    got = fn(d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
+    assert got.shape == d["raw"].shape and got.dtype == np.float64
+    assert maxabs(got, d["raw"]) <= raw_tol(d["cov_samples"].shape[1])
+
+
+@pytest.mark.parametrize("name", ["randmeth_1d", "randmeth_2d", "randmeth_3d", "randmeth_2d_reseed",
+                                  "randmeth_2d_modes800", "incompr_2d", "incompr_3d"])
+def test_reference_test_literals_on_gpu(name, gsb):
+    """The literals asserted in the reference's tests (tests/test_randmeth.py:33-71,
+    tests/test_incomprrandmeth.py:34-44), same 7-decimal criterion, computed on the GPU."""
+    meta, d = load_golden(name)
+    fn = gsb.summate if meta["kind"] == "scalar" else gsb.summate_incompr
+    n_modes = d["cov_samples"].shape[1]
+    field = np.sqrt(meta["var"] / n_modes) * fn(d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
+    if meta["kind"] == "incompr":
+        field[0] += 1.0  # mean_u * e1, generator.py:561-567
+    for a in meta["asserts"]:
+        assert round(field[tuple(a["index"])] - a["value"], a["places"]) == 0, a["cite"]
+
+
+# ---------------------------------------------------------------------------------------------
+# random inputs against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [1, 2, 3, 4, 6, 8])
+@pytest.mark.parametrize("n,n_modes", [(1, 1), (3, 7), (64, 128), (65, 129), (1000, 100),
+                                       (18945, 260), (75777, 33), (303105, 16)])
+def test_direct_scalar_vs_oracle(dim, n, n_modes, gsb, oracle_mod):
+    cov, z1, z2 = synth_modes(dim, n_modes, seed=dim * 1000 + n_modes)
+    pos = np.random.RandomState(n).uniform(-100, 500, (dim, n))
+    got = gsb.summate(cov, z1, z2, pos)
+    want = oracle_mod.summate(cov, z1, z2, pos)
+    assert maxabs(got, want) <= raw_tol(n_modes)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("n,n_modes", [(1, 1), (10, 100), (257, 130), (20000, 1000), (303105, 12)])
+def test_direct_incompr_vs_oracle(dim, n, n_modes, gsb, oracle_mod):
+    cov, z1, z2 = synth_modes(dim, n_modes, seed=dim * 77 + n_modes)
+    pos = np.random.RandomState(n).uniform(-100, 500, (dim, n))
+    got = gsb.summate_incompr(cov, z1, z2, pos)
+    want = oracle_mod.summate_incompr(cov, z1, z2, pos)
+    assert got.shape == (dim, n)
+    assert maxabs(got, want) <= raw_tol(n_modes)
+
+
+def test_mode_split_path_small_n_many_modes(gsb, oracle_mod):
+    """n so small that the grid cannot fill the SMs: modes are split over CTAs and reduced in
+    fixed order (deterministic)."""
+    cov, z1, z2 = synth_modes(3, 5000, seed=3)
+    pos = np.random.RandomState(0).uniform(0, 100, (3, 200))
+    a = gsb.summate(cov, z1, z2, pos)
+    b = gsb.summate(cov, z1, z2, pos)
+    assert np.array_equal(a, b)
+    assert maxabs(a, oracle_mod.summate(cov, z1, z2, pos)) <= raw_tol(5000)
+    av = gsb.summate_incompr(cov, z1, z2, pos)
+    assert maxabs(av, oracle_mod.summate_incompr(cov, z1, z2, pos)) <= raw_tol(5000)
+
+
+def test_edge_cases(gsb, oracle_mod):
+    cov, z1, z2 = synth_modes(2, 10, seed=1)
+    # no modes: zeros (the reference returns np.zeros + nothing added)
+    out = gsb.summate(cov[:, :0], z1[:0], z2[:0], np.ones((2, 5)))
+    assert np.array_equal(out, np.zeros(5))
+    out = gsb.summate_incompr(cov[:, :0], z1[:0], z2[:0], np.ones((2, 5)))
+    assert np.array_equal(out, np.zeros((2, 5)))
+    # x = 0 -> sum(z1)
+    assert abs(gsb.summate(cov, z1, z2, np.zeros((2, 1)))[0] - z1.sum()) < 1e-13
+    # a zero wave vector gives NaN in the projector, exactly like the reference loop (k2 == 0)
+    cov0 = cov.copy()
+    cov0[:, 3] = 0.0
+    got = gsb.summate_incompr(cov0, z1, z2, np.ones((2, 4)))
+    want = oracle_mod.summate_incompr(cov0, z1, z2, np.ones((2, 4)))
+    assert np.isnan(got).all() and np.isnan(want).all()
+    # scalar sum is unaffected by a zero wave vector
+    assert maxabs(gsb.summate(cov0, z1, z2, np.ones((2, 4))),
+                  oracle_mod.summate(cov0, z1, z2, np.ones((2, 4)))) <= raw_tol(10)
+
+
+def test_input_coercion_like_the_reference(gsb, oracle_mod):
+    cov, z1, z2 = synth_modes(3, 50, seed=2)
+    pos = np.random.RandomState(1).uniform(0, 50, (3, 333))
+    want = oracle_mod.summate(cov, z1, z2, pos)
+    # Fortran order, strided views, lists, read-only arrays, float32 / int positions
+    assert maxabs(gsb.summate(np.asfortranarray(cov), z1, z2, np.asfortranarray(pos)), want) <= raw_tol(50)
+    big = np.zeros((3, 1000))
+    big[:, 100:433] = pos
+    assert maxabs(gsb.summate(cov, z1, z2, big[:, 100:433]), want) <= raw_tol(50)
+    assert maxabs(gsb.summate(cov.tolist(), list(z1), list(z2), pos.tolist()), want) <= raw_tol(50)
+    ro = pos.copy()
+    ro.setflags(write=False)
+    assert maxabs(gsb.summate(cov, z1, z2, ro), want) <= raw_tol(50)
+    ipos = np.arange(30).reshape(3, 10)
+    assert maxabs(gsb.summate(cov, z1, z2, ipos), oracle_mod.summate(cov, z1, z2, ipos.astype(float))) <= raw_tol(50)
+    # inputs are never modified
+    c0, p0 = cov.copy(), pos.copy()
+    gsb.summate(cov, z1, z2, pos)
+    assert np.array_equal(cov, c0) and np.array_equal(pos, p0)
+    # num_threads is accepted and ignored (reference call passes 5 positional args)
+    assert np.array_equal(gsb.summate(cov, z1, z2, pos, 4), gsb.summate(cov, z1, z2, pos, None))
+
+
+def test_large_phases(gsb, oracle_mod):
+    """UTM-like coordinates and heavy-tailed wave numbers: |phase| up to ~1e6 rad.  Both
+    implementations carry |phase| * 1e-16 of rounding, far inside the tolerance."""
+    cov, z1, z2 = synth_modes(2, 1000, seed=5, len_scale=10.0)
+    pos = np.random.RandomState(2).uniform(4.0e5, 4.1e5, (2, 2000))
+    got = gsb.summate(cov, z1, z2, pos)
+    want = oracle_mod.summate(cov, z1, z2, pos)
+    assert maxabs(got, want) <= raw_tol(1000)
+
+
+def test_bitwise_determinism_and_linearity(gsb):
+    cov, z1, z2 = synth_modes(3, 300, seed=8)
+    pos = np.random.RandomState(3).uniform(0, 300, (3, 50000))
+    a = gsb.summate(cov, z1, z2, pos)
+    assert np.array_equal(a, gsb.summate(cov, z1, z2, pos))
+    # exact sign symmetry and exact scaling by a power of two
+    assert np.array_equal(-a, gsb.summate(cov, -z1, -z2, pos))
+    assert np.array_equal(4.0 * a, gsb.summate(cov, 4.0 * z1, 4.0 * z2, pos))
+    # additivity in the weights
+    rs = np.random.RandomState(4)
+    y1, y2 = rs.normal(size=300), rs.normal(size=300)
+    b = gsb.summate(cov, y1, y2, pos)
+    c = gsb.summate(cov, z1 + y1, z2 + y2, pos)
+    assert maxabs(a + b, c) <= raw_tol(300)
+    # a point's value does not depend on which other points are in the call
+    sub = gsb.summate(cov, z1, z2, pos[:, 1234:1300])
+    assert np.array_equal(sub, a[1234:1300])
+
+
+def test_device_tensor_path_matches_host_path(gsb):
+    import torch
+
+    cov, z1, z2 = synth_modes(3, 200, seed=9)
+    pos = np.random.RandomState(5).uniform(0, 300, (3, 70001))
+    host = gsb.summate(cov, z1, z2, pos)
+    dev = torch.device("cuda:0")
+    tc, t1, t2, tp = (torch.tensor(a, device=dev) for a in (cov, z1, z2, pos))
+    out = gsb.summate(tc, t1, t2, tp)
+    assert out.is_cuda and out.dtype == torch.float64 and out.shape == (70001,)
+    assert np.array_equal(out.cpu().numpy(), host)
+    # mixed: numpy modes + CUDA positions, and a strided point range without a copy
+    out2 = gsb.summate(cov, z1, z2, tp[:, 1000:3000])
+    assert np.array_equal(out2.cpu().numpy(), host[1000:3000])
+    v = gsb.summate_incompr(tc, t1, t2, tp)
+    assert np.array_equal(v.cpu().numpy(), gsb.summate_incompr(cov, z1, z2, pos))
+    # fused epilogue on device: sqrt(var/N) * s + shift (generator.py:269-270)
+    f = out.clone()
+    gsb.scale_shift_(f, 0.25, 1.5)
+    assert np.array_equal(f.cpu().numpy(), 0.25 * host + 1.5)
+    # non-default stream
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out3 = gsb.summate(tc, t1, t2, tp)
+    s.synchronize()
+    assert np.array_equal(out3.cpu().numpy(), host)
+
+
+def test_raw_c_abi_call_with_host_pointers(gsb, oracle_mod):
+    """Call the exported symbol directly, the way a foreign-language binding would."""
+    lib = ctypes.CDLL(gsb._lib.lib_path())
+    lib.gsb_summate.restype = ctypes.c_int
+    lib.gsb_last_error.restype = ctypes.c_char_p
+    cov, z1, z2 = synth_modes(2, 64, seed=4)
+    pos = np.ascontiguousarray(np.random.RandomState(6).uniform(0, 100, (2, 999)))
+    out = np.empty(999)
+    vp = ctypes.c_void_p
+    rc = lib.gsb_summate(vp(cov.ctypes.data), vp(z1.ctypes.data), vp(z2.ctypes.data),
+                         vp(pos.ctypes.data), ctypes.c_int64(999), ctypes.c_int(2),
+                         ctypes.c_int64(64), ctypes.c_int64(999), vp(out.ctypes.data),
+                         ctypes.c_int(0), ctypes.c_int(0), vp(None))
+    assert rc == 0, lib.gsb_last_error()
+    assert maxabs(out, oracle_mod.summate(cov, z1, z2, pos)) <= raw_tol(64)
+
+
+# ---------------------------------------------------------------------------------------------
+# structured meshes: separable kernel and the small-mesh (expand + direct) route
+# ---------------------------------------------------------------------------------------------
+STRUCT_CASES = [
+    (2, (100, 100), 1000),     # config 1 shape
+    (2, (3, 5), 10),
+    (2, (129, 131), 77),       # odd last axis: scalar stores
+    (2, (300, 517), 200),
+    (3, (40, 50, 130), 300),
+    (3, (7, 9, 257), 64),
+    (3, (64, 64, 256), 1000),
+    (4, (9, 10, 11, 140), 64),
+    (5, (3, 4, 5, 6, 130), 20),
+]
+
+
+@pytest.mark.parametrize("dim,lens,n_modes", STRUCT_CASES)
+@pytest.mark.parametrize("path", ["direct", "separable"])
+def test_structured_vs_oracle(dim, lens, n_modes, path, gsb, oracle_mod):
+    cov, z1, z2 = synth_modes(dim, n_modes, seed=7 + dim)
+    rs = np.random.RandomState(5)
+    axes = [np.sort(rs.uniform(0, 200, L)) for L in lens]    # non-uniform axes
+    mat = rs.normal(size=(dim, dim))                          # rotation + anisotropy + shear
+    grid = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+    pos = mat @ grid
+    want = oracle_mod.summate(cov, z1, z2, pos).reshape(lens)
+    gsb.set_option("force_path", 1 if path == "direct" else 2)
+    try:
+        got = gsb.summate_structured(cov, z1, z2, axes, mat)
+        assert got.shape == tuple(lens)
+        assert maxabs(got, want) <= raw_tol(n_modes)
+        if dim in (2, 3):
+            wv = oracle_mod.summate_incompr(cov, z1, z2, pos).reshape((dim,) + tuple(lens))
+            gv = gsb.summate_incompr_structured(cov, z1, z2, axes, mat)
+            assert gv.shape == (dim,) + tuple(lens)
+            assert maxabs(gv, wv) <= raw_tol(n_modes)
+    finally:
+        gsb.set_option("force_path", 0)
+
+
+def test_structured_identity_matrix_and_auto_path(gsb, oracle_mod):
+    cov, z1, z2 = synth_modes(3, 100, seed=1)
+    axes = [np.arange(30.0), np.arange(40.0), np.arange(200.0)]
+    grid = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+    want = oracle_mod.summate(cov, z1, z2, grid).reshape(30, 40, 200)
+    before = gsb.get_counter("separable_calls")
+    got = gsb.summate_structured(cov, z1, z2, axes)           # matrix=None -> identity
+    assert gsb.get_counter("separable_calls") == before + 1   # big enough for the tiled kernel
+    assert maxabs(got, want) <= raw_tol(100)
+    got_eye = gsb.summate_structured(cov, z1, z2, axes, np.eye(3))
+    assert np.array_equal(got, got_eye)
+    # tiny mesh -> expanded on the device, direct kernel
+    before = gsb.get_counter("direct_calls")
+    small = gsb.summate_structured(cov, z1, z2, [np.arange(4.0), np.arange(5.0), np.arange(6.0)])
+    assert gsb.get_counter("direct_calls") == before + 1
+    assert maxabs(small, want[:4, :5, :6]) <= raw_tol(100)
+
+
+def test_structured_batched_ensemble(gsb, oracle_mod):
+    n_batch, dim, lens, n_modes = 5, 3, (20, 30, 130), 100
+    sets = [synth_modes(dim, n_modes, seed=50 + b) for b in range(n_batch)]
+    cov = np.stack([s[0] for s in sets])
+    z1 = np.stack([s[1] for s in sets])
+    z2 = np.stack([s[2] for s in sets])
+    axes = [np.linspace(0, 50, L) for L in lens]
+    grid = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+    for force in (1, 2):
+        gsb.set_option("force_path", force)
+        try:
+            got = gsb.summate_structured(cov, z1, z2, axes)
+            assert got.shape == (n_batch,) + lens
+            for b in range(n_batch):
+                want = oracle_mod.summate(cov[b], z1[b], z2[b], grid).reshape(lens)
+                assert maxabs(got[b], want) <= raw_tol(n_modes)
+                # batching changes nothing bitwise
+                single = gsb.summate_structured(cov[b], z1[b], z2[b], axes)
+                assert np.array_equal(single, got[b])
+        finally:
+            gsb.set_option("force_path", 0)
+
+
+def test_structured_device_tensors_and_slab_consistency(gsb):
+    import torch
+
+    cov, z1, z2 = synth_modes(3, 128, seed=3)
+    axes = [np.arange(64.0), np.arange(96.0), np.arange(256.0)]
+    host = gsb.summate_structured(cov, z1, z2, axes)
+    dev = torch.device("cuda:0")
+    out = gsb.summate_structured(torch.tensor(cov, device=dev), torch.tensor(z1, device=dev),
+                                 torch.tensor(z2, device=dev),
+                                 [torch.tensor(a, device=dev) for a in axes])
+    assert out.is_cuda and tuple(out.shape) == (64, 96, 256)
+    assert np.array_equal(out.cpu().numpy(), host)
+    # the host route pipelines slabs along axis 0; a different slab size must not change a bit
+    gsb.set_option("slab_tiles", 40)
+    try:
+        assert np.array_equal(gsb.summate_structured(cov, z1, z2, axes), host)
+    finally:
+        gsb.set_option("slab_tiles", 148 * 6)
+    # a slab computed alone equals the same rows of the full field (multi-GPU sharding unit)
+    part = gsb.summate_structured(cov, z1, z2, [axes[0][16:48], axes[1], axes[2]])
+    assert np.array_equal(part, host[16:48])
+
+
+def test_separable_and_direct_kernels_agree(gsb):
+    """Two different algorithms (2 DFMA/pair contraction vs per-pair polynomial sincos) on the
+    same mesh."""
+    cov, z1, z2 = synth_modes(3, 1000, seed=11)
+    axes = [np.arange(96.0), np.arange(128.0), np.arange(384.0)]
+    gsb.set_option("force_path", 2)
+    sep = gsb.summate_structured(cov, z1, z2, axes)
+    gsb.set_option("force_path", 1)
+    try:
+        direct = gsb.summate_structured(cov, z1, z2, axes)
+    finally:
+        gsb.set_option("force_path", 0)
+    assert maxabs(sep, direct) <= raw_tol(1000)

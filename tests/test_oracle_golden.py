@@ -1,0 +1,105 @@
+"""The CPU oracle against the reference's golden values (the parity pin).  CPU only.
+
+Fixtures in tests/golden/*.npz were recorded from the UNMODIFIED reference generators
+(tests/golden/make_golden.py); every ``asserts`` entry is a literal value asserted by the
+reference's own tests (file:line stored in the fixture).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, synth_modes
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_reproduces_recorded_boundary(name, oracle_mod):
+    meta, d = load_golden(name)
+    fn = oracle_mod.summate if meta["kind"] == "scalar" else oracle_mod.summate_incompr
+    got = fn(d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
+    # same library, same libm: bit-for-bit
+    assert np.array_equal(got, d["raw"])
+
+
+@pytest.mark.parametrize("name", ["randmeth_1d", "randmeth_2d", "randmeth_3d", "randmeth_2d_reseed",
+                                  "randmeth_2d_modes800", "incompr_2d", "incompr_3d"])
+def test_oracle_matches_reference_test_literals(name, oracle_mod):
+    """sqrt(var/N) * oracle == the literals in tests/test_randmeth.py / test_incomprrandmeth.py."""
+    meta, d = load_golden(name)
+    fn = oracle_mod.summate if meta["kind"] == "scalar" else oracle_mod.summate_incompr
+    n_modes = d["cov_samples"].shape[1]
+    field = np.sqrt(meta["var"] / n_modes) * fn(d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
+    if meta["kind"] == "incompr":
+        # IncomprRandMeth.__call__ adds mean_u * e1 with mean_u = 1 (generator.py:561-567)
+        field[0] += 1.0
+    assert meta["asserts"], "fixture carries no reference literals"
+    for a in meta["asserts"]:
+        got = field[tuple(a["index"])]
+        assert round(got - a["value"], a["places"]) == 0, (a["cite"], got, a["value"])
+
+
+def test_oracle_3d_literals_are_16_digit(oracle_mod):
+    """tests/test_randmeth.py:45-46 holds 16-digit goldens: reproduce them to 1e-15."""
+    meta, d = load_golden("randmeth_3d")
+    field = np.sqrt(1.5 / 100) * oracle_mod.summate(d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
+    assert abs(field[0] - 1.3240234883187239) < 1e-15
+    assert abs(field[1] - 1.6367244277732766) < 1e-15
+
+
+def test_vector_mean_fixture(oracle_mod):
+    """tests/test_incomprrandmeth.py:50-59 (structured 9x16 vector field, default mode_no)."""
+    meta, d = load_golden("incompr_2d_vector_mean_struct")
+    assert abs(np.mean(d["field"][0]) - meta["mean0"]) < 1e-12
+    assert abs(np.mean(d["field"][1]) - meta["mean1"]) < 1e-12
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3, 4])
+def test_c_oracle_vs_numpy_restatement(dim, oracle_mod):
+    cov, z1, z2 = synth_modes(dim, 257, seed=dim)
+    pos = np.random.RandomState(3).uniform(-50, 300, (dim, 1234))
+    a = oracle_mod.summate(cov, z1, z2, pos)
+    b = oracle_mod.summate_np(cov, z1, z2, pos)
+    assert np.max(np.abs(a - b)) < 1e-11
+    if dim >= 2:
+        av = oracle_mod.summate_incompr(cov, z1, z2, pos)
+        bv = oracle_mod.summate_incompr_np(cov, z1, z2, pos)
+        assert np.max(np.abs(av - bv)) < 1e-11
+        # first component dominates: the projector is the identity minus a rank-1 term
+        assert av.shape == (dim, 1234)
+
+
+def test_oracle_threads_are_deterministic(oracle_mod):
+    cov, z1, z2 = synth_modes(3, 100, seed=9)
+    pos = np.random.RandomState(4).uniform(0, 100, (3, 5000))
+    a = oracle_mod.summate(cov, z1, z2, pos, num_threads=1)
+    b = oracle_mod.summate(cov, z1, z2, pos, num_threads=4)
+    assert np.array_equal(a, b)
+
+
+def test_oracle_edge_cases(oracle_mod):
+    cov, z1, z2 = synth_modes(2, 10, seed=1)
+    assert oracle_mod.summate(cov, z1, z2, np.zeros((2, 0))).shape == (0,)
+    out = oracle_mod.summate(cov[:, :0], z1[:0], z2[:0], np.zeros((2, 5)))
+    assert np.array_equal(out, np.zeros(5))
+    # x = 0: cos = 1, sin = 0 -> sum of z1
+    assert abs(oracle_mod.summate(cov, z1, z2, np.zeros((2, 1)))[0] - z1.sum()) < 1e-13
+    with pytest.raises(ValueError):
+        oracle_mod.summate(cov, z1[:-1], z2, np.zeros((2, 1)))
+
+
+def test_live_reference_matches_fixtures(oracle_mod):
+    """When the reference is importable (build container, or baseline/_ref on the GPU box) rerun
+    one generator live and compare with the committed fixture."""
+    import refharness
+
+    if not refharness.have_reference():
+        pytest.skip("reference gstools not present")
+    gs = refharness.import_gstools()
+    from gstools.field.generator import RandMeth
+
+    meta, d = load_golden("randmeth_3d")
+    rm = RandMeth(gs.Gaussian(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=19031977)
+    assert np.array_equal(rm._cov_sample, d["cov_samples"])
+    assert np.array_equal(rm._z_1, d["z_1"])
+    x = np.linspace(0.0, 10.0, 10)
+    y = np.linspace(-5.0, 5.0, 10)
+    z = np.linspace(-6.0, 8.0, 10)
+    assert np.allclose(rm((x, y, z)), d["field"], rtol=0, atol=1e-14)
