@@ -20,6 +20,7 @@ static std::atomic<int64_t> g_opt_structured_min_tiles{64};
 static std::atomic<int64_t> g_opt_force_path{0};
 static std::atomic<int64_t> g_opt_host_chunk_points{1 << 22};
 static std::atomic<int64_t> g_opt_slab_tiles{148 * 6};
+static std::atomic<int64_t> g_opt_sep_variant{0};  // 0 = DMMA, 1 = DFMA register tile
 static std::atomic<int64_t> g_cnt_direct{0}, g_cnt_separable{0};
 
 // ---------------------------------------------------------------------------------------------
@@ -142,7 +143,9 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
     const int64_t ctas = (n_pts + direct_cfg_points(cfg, dim) - 1) / direct_cfg_points(cfg, dim);
     const int n_tiles = (int)((n_modes_pad + DIRECT_TM - 1) / DIRECT_TM);
     int n_split = 1;
-    if (cfg == 0 && ctas < dev.sm_count && n_tiles > 1)
+    // Mode splitting (partials + fixed-order reduce) only for very small point sets with very
+    // many modes; everywhere else a point's bits do not depend on what else is in the call.
+    if (cfg == 0 && ctas * 8 < dev.sm_count && n_tiles >= 16)
         n_split = (int)std::min<int64_t>(n_tiles, (want + ctas - 1) / ctas);
     DirectParams prm;
     prm.recs = d_recs;
@@ -390,7 +393,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         s2.row_len[0] = nx;
         s2.n_rows = nx * rows_per_x;
         s2.out = d_out + x0 * rows_per_x * lc;
-        GSB_TRY(launch_separable(s2, n_batch, st));
+        GSB_TRY(launch_separable(s2, n_batch, (int)g_opt_sep_variant.load(), st));
         if (h_out && single_field) {
             GSB_CUDA(cudaEventRecord(ev, st));
             GSB_CUDA(cudaStreamWaitEvent(copy_st, ev, 0));
@@ -623,6 +626,7 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "force_path") g_opt_force_path = value;
     else if (n == "host_chunk_points") g_opt_host_chunk_points = value;
     else if (n == "slab_tiles") g_opt_slab_tiles = value;
+    else if (n == "sep_variant") g_opt_sep_variant = value;
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);
     return GSB_OK;
 }

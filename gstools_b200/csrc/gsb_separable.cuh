@@ -13,17 +13,18 @@
 // built once per call with full-accuracy sincos.
 //
 // Kernel structure (one CTA per 128x128 output tile, 1 CTA/SM, warp specialised):
-//   * warps 8..11 = producer warpgroup (one thread per tile row; registers trimmed with
-//     setmaxnreg.dec so the consumers can hold their 64 accumulators).  Per pipeline stage of KC
-//     modes it (a) issues cp.async.bulk copies (TMA unit) of the Cz/Sz table slices into shared
-//     memory, signalled on the stage's "full" mbarrier, and (b) GENERATES the A operand on the
-//     fly: one complex product per (row, mode) from the L2-resident row-axis tables, written
-//     straight to shared memory.  The 4.2 GB A matrix of config 2 never exists in HBM.
-//   * warps 0..7 = consumers: 8x8 register tile per thread (64 fp64 accumulators), fragments
-//     fetched with conflict-free 16-byte LDS, 128 DFMA per mode per thread, modes accumulated
-//     in ascending order (deterministic, no atomics).  They release the stage on its "empty"
-//     mbarrier.
-//   * epilogue: registers -> global, 16-byte stores, full 128-byte lines per row segment.
+//   * warps 8..11 = TMA warpgroup: one elected thread issues, per pipeline stage of KC modes, the
+//     cp.async.bulk copies (TMA unit) of the Cz/Sz table slices into shared memory, signalled on
+//     the stage's "full" mbarrier; the warpgroup gives its registers to the consumers
+//     (setmaxnreg.dec / .inc).
+//   * the A operand is GENERATED on the fly by the consumer threads, one stage ahead: one complex
+//     product per (row, mode) from the L2-resident row-axis tables, written straight to shared
+//     memory.  The 4.2 GB A matrix of config 2 never exists in HBM.
+//   * warps 0..7 = consumers: each warp owns a 32x64 block of the tile as 4x8 DMMA.8x8x4
+//     accumulator tiles (64 fp64 accumulators per thread); per 2 modes it fetches 4 + 8 fragment
+//     doubles with conflict-free LDS.64 and issues 32 DMMA; modes are accumulated in ascending
+//     order (deterministic, no atomics).  They release the stage on its "empty" mbarrier.
+//   * epilogue: registers -> global, 16-byte stores.
 // The incompressible variant (generator.py:479-495) multiplies A by the projector p_t(k_j) and
 // runs one CTA column per vector component (2 d DFMA per pair).
 #pragma once
@@ -39,8 +40,8 @@ constexpr int SEP_STAGES = 4;
 constexpr int SEP_CONSUMER_WARPS = 8;
 constexpr int SEP_PRODUCER_WARPS = 4;   // one full warpgroup, so setmaxnreg can rebalance registers
 constexpr int SEP_THREADS = (SEP_CONSUMER_WARPS + SEP_PRODUCER_WARPS) * 32;
-constexpr int SEP_REGS_PRODUCER = 56;
-constexpr int SEP_REGS_CONSUMER = 224;  // 128*56 + 256*224 = 64512 <= 65536
+constexpr int SEP_REGS_PRODUCER = 24;
+constexpr int SEP_REGS_CONSUMER = 240;  // 128*24 + 256*240 = 64512 <= 65536
 constexpr int SEP_MAX_ROW_AXES = GSB_MAX_DIM - 1;
 
 // shared memory carve-up per stage: Ar[KC][TM], Ai[KC][TM], Bc[KC][TN], Bs[KC][TN] (doubles)
@@ -158,13 +159,42 @@ __global__ void build_tables_kernel(const TableParams tp)
 
 // ---------------------------------------------------------------------------------------------
 // the contraction kernel
+//
+// Two consumer variants share the producer and the pipeline:
+//   MMA = true  (default): DMMA.8x8x4 (mma.sync m8n8k4 f64) on the tensor-core FP64 path.  B200
+//                runs it at the same FMA rate as DFMA, but one instruction carries 256 FMAs with
+//                8 register reads, so neither the register-file bandwidth (3 x 64-bit operands per
+//                DFMA exceed the 2 reads/clk the RF sustains once the operand-reuse cache is lost
+//                between warps) nor shared-memory fragment traffic limits the FP64 pipe.
+//   MMA = false: register-tiled DFMA (8x8 accumulators per thread), kept for the ablation in
+//                profiles/ (73 % of the FP64 peak vs the DMMA variant).
+// Shared-memory layouts per stage:
+//   MMA : A[row][SEP_AST]  k = 2*kc + part (part 0: p*Re A, part 1: -p*Im A), rows padded to 20
+//         doubles so that the 8x4 fragment loads (LDS.64) hit 32 distinct banks per half warp;
+//         B[2*kc + part][SEP_BST] (part 0: cos, part 1: sin), rows padded to 132 doubles likewise.
+//   DFMA: Ar[kc][128], Ai[kc][128], Bc[kc][128], Bs[kc][128].
 // ---------------------------------------------------------------------------------------------
-template <int NRA>  // number of row axes (dim - 1), 1..SEP_MAX_ROW_AXES
+constexpr int SEP_AST = 2 * SEP_KC + 4;   // A row stride (doubles), == 4 mod 16
+constexpr int SEP_BST = SEP_TN + 4;       // B row stride (doubles), == 4 mod 16
+constexpr int SEP_STAGE_DOUBLES_MMA = SEP_TM * SEP_AST + 2 * SEP_KC * SEP_BST;
+constexpr size_t SEP_SMEM_BYTES_MMA =
+    (size_t)SEP_STAGES * SEP_STAGE_DOUBLES_MMA * sizeof(double) + 2 * SEP_STAGES * sizeof(uint64_t) + 128;
+
+__device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int NRA, bool MMA>  // NRA = number of row axes (dim - 1), 1..SEP_MAX_ROW_AXES
 __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepParams prm)
 {
+    constexpr int STAGE_DOUBLES = MMA ? SEP_STAGE_DOUBLES_MMA : SEP_STAGE_DOUBLES;
+    constexpr int NCONS = SEP_CONSUMER_WARPS * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stage_base = reinterpret_cast<double *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + SEP_STAGES * SEP_STAGE_DOUBLES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + SEP_STAGES * STAGE_DOUBLES);
     uint64_t *empty = full + SEP_STAGES;
 
     const int tid = threadIdx.x;
@@ -178,86 +208,163 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
 
     if (tid == 0) {
         for (int s = 0; s < SEP_STAGES; ++s) {
-            mbar_init(&full[s], SEP_PRODUCER_WARPS * 32); // every producer thread arrives once
-            mbar_init(&empty[s], SEP_CONSUMER_WARPS);     // one arrive per consumer warp
+            mbar_init(&full[s], NCONS + 1);            // 256 A-operand writers + the TMA issuer
+            mbar_init(&empty[s], SEP_CONSUMER_WARPS);  // one arrive per consumer warp
         }
         fence_barrier_init();
     }
     __syncthreads();
 
     if (warp >= SEP_CONSUMER_WARPS) {
-        // ============================= PRODUCER WARPGROUP ==============================
+        // ================== TMA WARPGROUP: one thread feeds the B operand ==================
+        // Registers are handed to the consumers (setmaxnreg); the idle warps retire at once.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SEP_REGS_PRODUCER));
-        const int prow = tid - SEP_CONSUMER_WARPS * 32;  // 0..127: the tile row this thread owns
-        const double2 *ep[NRA];
-        {
-            int64_t r = row0 + prow;
-            if (r >= prm.n_rows) r = prm.n_rows - 1;  // clamp; result is never stored
-#pragma unroll
-            for (int t = NRA - 1; t >= 0; --t) {
-                const int64_t it = r % prm.row_len[t];
-                r /= prm.row_len[t];
-                ep[t] = prm.erow[t] + batch * prm.erow_bstride[t] + it;
-            }
-        }
-        const double *bsrc = (prow < SEP_KC ? prm.bc : prm.bs) + batch * prm.b_bstride + col0;
-        const double *proj =
-            prm.proj ? prm.proj + batch * prm.proj_bstride + (int64_t)comp * prm.n_modes_pad : nullptr;
-
+        if (tid != NCONS) return;
+        const double *bc = prm.bc + batch * prm.b_bstride + col0;
+        const double *bs = prm.bs + batch * prm.b_bstride + col0;
         for (int s = 0; s < n_stages_total; ++s) {
             const int slot = s % SEP_STAGES;
             const int round = s / SEP_STAGES;
             if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
-            double *Ar = stage_base + slot * SEP_STAGE_DOUBLES;
-            double *Ai = Ar + SEP_KC * SEP_TM;
-            double *Bc = Ai + SEP_KC * SEP_TM;
+            double *B = stage_base + slot * STAGE_DOUBLES + (MMA ? SEP_TM * SEP_AST : 2 * SEP_KC * SEP_TM);
             const int64_t j0 = (int64_t)s * SEP_KC;
+            mbar_arrive_expect_tx(&full[slot], 2 * SEP_KC * SEP_TN * sizeof(double));
+#pragma unroll
+            for (int kc = 0; kc < SEP_KC; ++kc) {
+                // MMA: smem row 2*kc + part      DFMA: smem row part*KC + kc      (part 0 cos, 1 sin)
+                double *dc = B + (MMA ? (2 * kc) * SEP_BST : kc * SEP_TN);
+                double *ds = B + (MMA ? (2 * kc + 1) * SEP_BST : (SEP_KC + kc) * SEP_TN);
+                bulk_g2s(dc, bc + (j0 + kc) * prm.lc_pad, SEP_TN * sizeof(double), &full[slot]);
+                bulk_g2s(ds, bs + (j0 + kc) * prm.lc_pad, SEP_TN * sizeof(double), &full[slot]);
+            }
+        }
+        return;
+    }
 
-            // (a) B operand: 2*KC bulk copies of one 1 KB table-row slice each (Bc rows, then Bs rows)
-            if (prow < 2 * SEP_KC) {
-                mbar_expect_tx(&full[slot], SEP_TN * sizeof(double));
-                bulk_g2s(Bc + prow * SEP_TN, bsrc + (j0 + (prow % SEP_KC)) * prm.lc_pad,
-                         SEP_TN * sizeof(double), &full[slot]);
+    // ================================ CONSUMER WARPGROUPS ================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SEP_REGS_CONSUMER));
+    const int wr = warp >> 1;        // 0..3 : 32-row band
+    const int wc = warp & 1;         // 0..1 : 64-column band
+    double *out = prm.out + (batch * prm.ncomp + comp) * prm.out_fstride;
+    const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+
+    // ---- cooperative generation of the A operand: thread -> (tile row, 4 of the KC modes) ----
+    // The loads for stage s+1 are issued before the contraction of stage s and consumed after
+    // it, so their L2 latency is hidden; the complex products run on the issuing warp's own
+    // FP64 slots (in order with its DMMAs -- a dedicated producer warp starves behind them).
+    const int grow = tid & (SEP_TM - 1);
+    const int gm0 = (tid >> 7) * (SEP_KC / 2);
+    const double2 *ep[NRA];
+    {
+        int64_t r = row0 + grow;
+        if (r >= prm.n_rows) r = prm.n_rows - 1;  // clamp; result is never stored
+#pragma unroll
+        for (int t = NRA - 1; t >= 0; --t) {
+            const int64_t it = r % prm.row_len[t];
+            r /= prm.row_len[t];
+            ep[t] = prm.erow[t] + batch * prm.erow_bstride[t] + it;
+        }
+    }
+    const double *proj =
+        prm.proj ? prm.proj + batch * prm.proj_bstride + (int64_t)comp * prm.n_modes_pad : nullptr;
+    double2 ge[NRA][SEP_KC / 2];
+    auto gen_load = [&](int s) {
+        const int64_t j = (int64_t)s * SEP_KC + gm0;
+#pragma unroll
+        for (int t = 0; t < NRA; ++t)
+#pragma unroll
+            for (int u = 0; u < SEP_KC / 2; ++u) ge[t][u] = __ldg(ep[t] + (j + u) * prm.row_stride[t]);
+    };
+    auto gen_store = [&](int s) {
+        const int slot = s % SEP_STAGES;
+        double *A = stage_base + slot * STAGE_DOUBLES;
+#pragma unroll
+        for (int u = 0; u < SEP_KC / 2; ++u) {
+            double2 e = ge[0][u];
+#pragma unroll
+            for (int t = 1; t < NRA; ++t) {
+                const double re = e.x * ge[t][u].x - e.y * ge[t][u].y;
+                const double im = e.x * ge[t][u].y + e.y * ge[t][u].x;
+                e.x = re;
+                e.y = im;
             }
-            // (b) A operand generated on the fly, KC/2 modes per batch of loads
+            if (proj) {
+                const double pj = proj[(int64_t)s * SEP_KC + gm0 + u];
+                e.x *= pj;
+                e.y *= pj;
+            }
+            if (MMA) {
+                *reinterpret_cast<double2 *>(A + grow * SEP_AST + 2 * (gm0 + u)) = make_double2(e.x, -e.y);
+            } else {
+                A[(gm0 + u) * SEP_TM + grow] = e.x;
+                A[(SEP_KC + gm0 + u) * SEP_TM + grow] = -e.y;
+            }
+        }
+        mbar_arrive(&full[slot]);  // release: this thread's part of the A tile is written
+    };
+
+    if (n_stages_total > 0) {
+        gen_load(0);
+        gen_store(0);
+    }
+
+    if (MMA) {
+        // warp tile 32 x 64 = 4 x 8 DMMA tiles of 8x8; fragment owner: g = lane/4, t = lane%4
+        const int g = lane >> 2;
+        const int t = lane & 3;
+        double acc[4][8][2];
 #pragma unroll
-            for (int kh = 0; kh < SEP_KC; kh += 4) {
-                double2 e[4];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) e[u] = __ldg(ep[0] + (j0 + kh + u) * prm.row_stride[0]);
+            for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const int a_off = (wr * 32 + g) * SEP_AST + t;   // + rt*8*SEP_AST + 4*k4
+        const int b_off = t * SEP_BST + wc * 64 + g;     // + 4*k4*SEP_BST + ct*8
+
+        for (int s = 0; s < n_stages_total; ++s) {
+            const int slot = s % SEP_STAGES;
+            if (s + 1 < n_stages_total) gen_load(s + 1);
+            mbar_wait(&full[slot], (s / SEP_STAGES) & 1);
+            const double *A = stage_base + slot * STAGE_DOUBLES;
+            const double *B = A + SEP_TM * SEP_AST;
 #pragma unroll
-                for (int t = 1; t < NRA; ++t) {
-                    double2 f[4];
+            for (int k4 = 0; k4 < SEP_KC / 2; ++k4) {   // 4 contraction indices = 2 modes
+                double af[4], bf[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) f[u] = __ldg(ep[t] + (j0 + kh + u) * prm.row_stride[t]);
+                for (int i = 0; i < 4; ++i) af[i] = A[a_off + i * 8 * SEP_AST + 4 * k4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const double re = e[u].x * f[u].x - e[u].y * f[u].y;
-                        const double im = e[u].x * f[u].y + e[u].y * f[u].x;
-                        e[u].x = re;
-                        e[u].y = im;
-                    }
-                }
+                for (int j = 0; j < 8; ++j) bf[j] = B[b_off + 4 * k4 * SEP_BST + j * 8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double pj = proj ? proj[j0 + kh + u] : 1.0;
-                    Ar[(kh + u) * SEP_TM + prow] = pj * e[u].x;
-                    Ai[(kh + u) * SEP_TM + prow] = -(pj * e[u].y);
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+            if (s + 1 < n_stages_total) gen_store(s + 1);
+        }
+        // epilogue: thread holds C[g][2t], C[g][2t+1] of every 8x8 tile
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t row = row0 + wr * 32 + i * 8 + g;
+            if (row >= prm.n_rows) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
+                double *dst = out + row * prm.lc + col;
+                if (vec2 && col + 1 < prm.lc) {
+                    *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+                } else {
+                    if (col < prm.lc) dst[0] = acc[i][j][0];
+                    if (col + 1 < prm.lc) dst[1] = acc[i][j][1];
                 }
             }
-            mbar_arrive(&full[slot]);  // release: this thread's A row is written
         }
     } else {
-        // ============================== CONSUMER WARPGROUPS ============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SEP_REGS_CONSUMER));
-        const int wr = warp >> 1;        // 0..3 : 32-row band
-        const int wc = warp & 1;         // 0..1 : 64-column band
         const int g = lane >> 3;         // 0..3
         const int h = lane & 7;          // 0..7
         // thread rows: wr*32 + 8*i + 2*g + {0,1}, i = 0..3 ; cols: wc*64 + 16*i + 2*h + {0,1}
         const int arow = wr * 32 + 2 * g;
         const int bcol = wc * 64 + 2 * h;
-
         double acc[8][8];
 #pragma unroll
         for (int a = 0; a < 8; ++a)
@@ -266,8 +373,9 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
 
         for (int s = 0; s < n_stages_total; ++s) {
             const int slot = s % SEP_STAGES;
+            if (s + 1 < n_stages_total) gen_load(s + 1);
             mbar_wait(&full[slot], (s / SEP_STAGES) & 1);
-            const double *Ar = stage_base + slot * SEP_STAGE_DOUBLES;
+            const double *Ar = stage_base + slot * STAGE_DOUBLES;
             const double *Ai = Ar + SEP_KC * SEP_TM;
             const double *Bc = Ai + SEP_KC * SEP_TM;
             const double *Bs = Bc + SEP_KC * SEP_TN;
@@ -296,11 +404,8 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
+            if (s + 1 < n_stages_total) gen_store(s + 1);
         }
-
-        // epilogue: out[batch][comp][row][col]
-        double *out = prm.out + (batch * prm.ncomp + comp) * prm.out_fstride;
-        const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
             const int64_t row = row0 + arow + 8 * (a >> 1) + (a & 1);
@@ -320,34 +425,39 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
     }
 }
 
-inline int launch_separable(const SepParams &prm, int64_t n_batch, cudaStream_t st)
+template <int NRA, bool MMA>
+inline int launch_separable_variant(const SepParams &prm, dim3 grid, cudaStream_t st)
+{
+    const size_t smem = MMA ? SEP_SMEM_BYTES_MMA : SEP_SMEM_BYTES;
+    GSB_CUDA(cudaFuncSetAttribute(separable_kernel<NRA, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    separable_kernel<NRA, MMA><<<grid, SEP_THREADS, smem, st>>>(prm);
+    return GSB_OK;
+}
+
+// variant: 0 = DMMA (default), 1 = DFMA register tile (ablation; dims 2 and 3 only)
+inline int launch_separable(const SepParams &prm, int64_t n_batch, int variant, cudaStream_t st)
 {
     dim3 grid((unsigned)(prm.lc_pad / SEP_TN), (unsigned)((prm.n_rows + SEP_TM - 1) / SEP_TM),
               (unsigned)(n_batch * prm.ncomp));
     if (grid.y > 65535u || grid.z > 65535u)
         return fail(GSB_ERR_ARGUMENT, "structured mesh too large for one launch (rows/128 or batch*ncomp > 65535)");
-#define GSB_SEP_CASE(N)                                                                        \
-    case N: {                                                                                  \
-        static bool attr_done = false;                                                         \
-        (void)attr_done;                                                                       \
-        GSB_CUDA(cudaFuncSetAttribute(separable_kernel<N>,                                     \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                      (int)SEP_SMEM_BYTES));                                   \
-        separable_kernel<N><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(prm);                   \
-        break;                                                                                 \
+    if (variant == 1 && prm.n_row_axes <= 2) {
+        if (prm.n_row_axes == 1) GSB_TRY((launch_separable_variant<1, false>(prm, grid, st)));
+        else GSB_TRY((launch_separable_variant<2, false>(prm, grid, st)));
+    } else {
+        switch (prm.n_row_axes) {
+        case 1: GSB_TRY((launch_separable_variant<1, true>(prm, grid, st))); break;
+        case 2: GSB_TRY((launch_separable_variant<2, true>(prm, grid, st))); break;
+        case 3: GSB_TRY((launch_separable_variant<3, true>(prm, grid, st))); break;
+        case 4: GSB_TRY((launch_separable_variant<4, true>(prm, grid, st))); break;
+        case 5: GSB_TRY((launch_separable_variant<5, true>(prm, grid, st))); break;
+        case 6: GSB_TRY((launch_separable_variant<6, true>(prm, grid, st))); break;
+        case 7: GSB_TRY((launch_separable_variant<7, true>(prm, grid, st))); break;
+        default:
+            return fail(GSB_ERR_ARGUMENT, "structured path needs 2 <= dim <= 8");
+        }
     }
-    switch (prm.n_row_axes) {
-        GSB_SEP_CASE(1)
-        GSB_SEP_CASE(2)
-        GSB_SEP_CASE(3)
-        GSB_SEP_CASE(4)
-        GSB_SEP_CASE(5)
-        GSB_SEP_CASE(6)
-        GSB_SEP_CASE(7)
-    default:
-        return fail(GSB_ERR_ARGUMENT, "structured path needs 2 <= dim <= 8");
-    }
-#undef GSB_SEP_CASE
     g_launches.fetch_add(1);
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;

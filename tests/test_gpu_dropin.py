@@ -118,21 +118,24 @@ def test_structured_side_channel_rotation_anisotropy(gs_b200, gsb):
         gsb.set_option("force_path", 0)
     assert field.shape == d["field"].shape
     assert np.max(np.abs(field - d["field"])) <= TOL * np.sqrt(2.0)
-    # relational checks of tests/test_srf.py:85-98,122-163 (anisotropy / rotation invariances)
-    x = np.linspace(0, 10, 21)
-    iso = gs.SRF(gs.Gaussian(dim=2, var=1.5, len_scale=4.0), mean=0.3, mode_no=100)
-    f_iso = iso((x, x), seed=825718662, mesh_type="structured")
-    ani = gs.SRF(gs.Gaussian(dim=2, var=1.5, len_scale=4.0, anis=0.5), mean=0.3, mode_no=100)
-    f_ani = ani((x, x), seed=825718662, mesh_type="structured")
-    assert abs(f_iso[0, 0] - f_ani[0, 0]) < 1e-9
-    assert abs(f_iso[0, 2] - f_ani[0, 1]) < 1e-9           # tests/test_srf.py:95-98
-    rot = gs.SRF(gs.Gaussian(dim=2, var=1.5, len_scale=4.0, angles=np.pi / 2.0), mean=0.3, mode_no=100)
-    xg, yg = np.linspace(-6, 6, 8), np.linspace(-6, 6, 8)
-    f0 = gs.SRF(gs.Gaussian(dim=2, var=1.5, len_scale=4.0), mean=0.3, mode_no=100)(
-        (xg, yg), seed=825718662, mesh_type="structured")
-    f1 = rot((xg, yg), seed=825718662, mesh_type="structured")
-    assert abs(f0[0, 0] - f1[0, -1]) < 1e-9                  # tests/test_srf.py:160-163
-    assert abs(f0[0, 1] - f1[1, -1]) < 1e-9
+    # relational checks of tests/test_srf.py:85-98 (anisotropy) and :144-163 (rotation), same
+    # grids, seed and 7-decimal criterion, structured route on the GPU
+    seed = 825718662
+    x_grid, y_grid = np.linspace(0.0, 12.0, 48), np.linspace(0.0, 10.0, 46)
+    model = gs.Gaussian(dim=2, var=1.5, len_scale=4.0)
+    f_iso = gs.SRF(model, mean=0.3, mode_no=100)((x_grid, y_grid), seed=seed, mesh_type="structured")
+    model.anis = 0.5
+    f_ani = gs.SRF(model, mean=0.3, mode_no=100)((x_grid, y_grid), seed=seed, mesh_type="structured")
+    assert round(f_iso[0, 0] - f_ani[0, 0], 7) == 0
+    assert round(f_iso[0, 4] - f_ani[0, 2], 7) == 0
+    assert round(f_iso[0, 10] - f_ani[0, 5], 7) == 0
+    xc = yc = np.linspace(-6.0, 6.0, 8)
+    model = gs.Gaussian(dim=2, var=1.5, len_scale=4.0, anis=0.25)
+    f0 = gs.SRF(model, mean=0.3, mode_no=100)((xc, yc), seed=seed, mesh_type="structured")
+    model.angles = -np.pi / 2.0
+    f1 = gs.SRF(model, mean=0.3, mode_no=100)((xc, yc), seed=seed, mesh_type="structured")
+    assert round(f0[0, 0] - f1[0, -1], 7) == 0
+    assert round(f0[1, 2] - f1[2, 6], 7) == 0
 
 
 def test_condsrf_ensemble_through_plugin(gs_b200, gsb):
