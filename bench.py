@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: randomisation-method field summation (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2]
+
+Workload (default, the config BASELINE.json's metric is quoted on): configs[1] -- SRF Exponential
+3D on a structured 512^3 mesh (134 217 728 points), mode_no = 1000; the mode set is the one the
+unmodified reference draws for seed 20170519 (tests/golden/config_modes.npz).  A "step" is one
+evaluation of the whole field.  With N > 1 GPUs the mesh is sharded into slabs along axis 0, one
+process per GPU, no collective on the data path (strong scaling: the total work is fixed, as
+BASELINE.json configs[1] states: "points sharded over 1/2/4/8 GPUs").
+
+Printed JSON (one line, rank 0):
+  value     point*modes/s, device-resident inputs, CUDA-event time summed over exactly K steps,
+            max over ranks (L2 is flushed between steps outside the event brackets)
+  e2e       same metric through the public numpy API gstools_b200.summate_structured():
+            host buffers in, host field out; H2D + D2H inside the timed region
+  roofline  FP64 pipe: algorithmic work = 2 DFMA (4 flop) per (point, mode) for the separable
+            kernel; peak = DFMA rate measured live by gsb_measure_fp64_peak
+  cpu_baseline  the C/OpenMP oracle (a port of the reference loop nest; the reference's own
+            gstools-cython / gstools_core binaries are not available) on a bounded point sample
+--impl reference times that CPU implementation as the whole step.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import bench_configs as bc  # noqa: E402
+
+METRIC = "RandMeth point*modes/s (fp64)"
+UNIT = "point*modes/s"
+NOMINAL_DFMA_PER_S = 148 * 64 * 1.965e9  # 18.61e12, SURVEY.md 8(d)
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------
+def make_workload(tag):
+    if tag == "c2":
+        cfg = bc.config2(512)
+        cfg.update(path="separable", work_per_pair_dfma=2, tag="C2")
+    elif tag == "c4":
+        cfg = bc.config4(256)
+        cfg.update(path="separable_incompr", work_per_pair_dfma=6, tag="C4")
+    elif tag == "c5":
+        cfg = bc.config5(128, 256)
+        cfg.update(path="separable_batched", work_per_pair_dfma=2, tag="C5")
+    elif tag == "c3":
+        cfg = bc.config3(20_000_000)
+        cfg.update(path="direct", work_per_pair_dfma=2 + 2 + 20, tag="C3")
+    elif tag == "c1":
+        cfg = bc.config1()
+        cfg.update(path="separable", work_per_pair_dfma=2, tag="C1")
+    else:
+        raise SystemExit(f"unknown workload {tag}")
+    return cfg
+
+
+def pairs_of(cfg):
+    n_modes = cfg["cov"].shape[-1]
+    n_batch = cfg["cov"].shape[0] if cfg["cov"].ndim == 3 else 1
+    if "axes" in cfg and cfg["path"] != "direct":
+        n = int(np.prod([len(a) for a in cfg["axes"]]))
+    else:
+        n = cfg["pos"].shape[1]
+    return n * n_modes * n_batch
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock, power and throttle reasons DURING the timed region (NVML, 20 ms period;
+    falls back to polling nvidia-smi)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []     # (sm_mhz, sm_max_mhz, power_w, reasons_bitmask or list)
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            uuid_index = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    uuid_index = int(vis.split(",")[index])
+                except ValueError:
+                    uuid_index = index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(uuid_index)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+        mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        reasons = []
+        for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            bit = getattr(n, attr, None)
+            if bit is None:
+                bit = getattr(n, attr.replace("ClocksEventReason", "ClocksThrottleReason"), 0)
+            if mask & bit:
+                reasons.append(name)
+        self.samples.append((float(sm), float(mx), float(pw), reasons))
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout
+        p = [x.strip() for x in out.strip().split(",")]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if p[3 + i].lower().startswith("active")]
+        self.samples.append((float(p[0]), float(p[1]), float(p[2]), reasons))
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thr.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        reasons = sorted({r for s in self.samples for r in s[3]})
+        return {"sm_mhz": statistics.median(s[0] for s in self.samples),
+                "sm_min_mhz": min(s[0] for s in self.samples),
+                "sm_max_mhz": max(s[1] for s in self.samples),
+                "power_w_max": max(s[2] for s in self.samples), "reasons": reasons,
+                "samples": len(self.samples),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (oracle/ is test + baseline infrastructure; never the product path)
+# ----------------------------------------------------------------------------------------------
+def cpu_sample_points(cfg, n_pts, offset=0):
+    """A contiguous range of the workload's points as a flat (dim, m) array."""
+    if cfg["path"] == "direct":
+        return np.ascontiguousarray(cfg["pos"][:, offset:offset + n_pts])
+    n = int(np.prod([len(a) for a in cfg["axes"]]))
+    idx = (np.arange(n_pts) + offset) % n
+    return bc.grid_points(cfg["axes"], cfg.get("matrix"), idx)
+
+
+def cpu_run(cfg, pos):
+    import oracle
+
+    cov, z1, z2 = cfg["cov"], cfg["z1"], cfg["z2"]
+    if cov.ndim == 3:
+        cov, z1, z2 = cov[0], z1[0], z2[0]
+    fn = oracle.summate_incompr if cfg["kind"] == "incompr" else oracle.summate
+    t0 = time.perf_counter()
+    fn(cov, z1, z2, pos)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(cfg, target_seconds=12.0):
+    import oracle
+
+    oracle.build()
+    n_modes = cfg["cov"].shape[-1]
+    probe = 65536
+    t = cpu_run(cfg, cpu_sample_points(cfg, probe))
+    rate = probe * n_modes / max(t, 1e-9)
+    m = int(min(max(probe, rate * target_seconds / n_modes), 4_000_000))
+    t = cpu_run(cfg, cpu_sample_points(cfg, m))
+    return {"value": m * n_modes / t, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
+            "sample": f"{m} contiguous points of the workload x {n_modes} modes "
+                      f"({m * n_modes:.3g} pairs, {t:.1f} s, C/OpenMP oracle, glibc libm)"}
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+
+    oracle.build()
+    n_modes = cfg["cov"].shape[-1]
+    probe = 65536
+    t = cpu_run(cfg, cpu_sample_points(cfg, probe))
+    rate = probe * n_modes / max(t, 1e-9)
+    budget = 150.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
+    m = int(min(max(probe, rate * min(budget, 20.0) / n_modes), 4_000_000))
+    for w in range(args.warmup):
+        cpu_run(cfg, cpu_sample_points(cfg, m, offset=w * m))
+    times = [cpu_run(cfg, cpu_sample_points(cfg, m, offset=(args.warmup + k) * m)) for k in range(args.steps)]
+    total = sum(times)
+    value = args.steps * m * n_modes / total
+    sample = (f"each step = {m} contiguous points of the workload x {n_modes} modes on the host CPU "
+              f"(C/OpenMP port of the reference loop nest, glibc libm); full-size time extrapolates linearly")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(cfg, args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, args):
+    c = {"workload": cfg["name"], "baseline_config": cfg["tag"], "path": cfg["path"],
+         "mode_no": int(cfg["cov"].shape[-1]), "dim": int(cfg["dim"]),
+         "modes": "drawn by the unmodified reference (seed 20170519), tests/golden/config_modes.npz",
+         "sharding": f"axis-0 slabs over {args.gpus} GPU(s), no collective",
+         "l2": "256 MiB flush buffer written between timed steps, outside the event brackets; "
+               "the 1.07 GB output exceeds L2"}
+    return c
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_b200_arm(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    import gstools_b200 as gsb
+    from gstools_b200.dist import shard_range
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 backend has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    gsb.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- this rank's share of the workload ----
+    structured = cfg["path"] != "direct"
+    vec = cfg["kind"] == "incompr"
+    batched = cfg["cov"].ndim == 3
+    if batched:                       # ensembles shard over realisations
+        lo, hi = shard_range(cfg["cov"].shape[0], rank, world)
+        h_cov, h_z1, h_z2 = cfg["cov"][lo:hi], cfg["z1"][lo:hi], cfg["z2"][lo:hi]
+        h_axes = [np.ascontiguousarray(a) for a in cfg["axes"]]
+    elif structured:                  # meshes shard over axis-0 slabs
+        lo, hi = shard_range(len(cfg["axes"][0]), rank, world)
+        h_cov, h_z1, h_z2 = cfg["cov"], cfg["z1"], cfg["z2"]
+        h_axes = [np.ascontiguousarray(cfg["axes"][0][lo:hi])] + [np.ascontiguousarray(a) for a in cfg["axes"][1:]]
+    else:                             # point sets shard over contiguous ranges
+        lo, hi = shard_range(cfg["pos"].shape[1], rank, world)
+        h_cov, h_z1, h_z2 = cfg["cov"], cfg["z1"], cfg["z2"]
+        h_pos = np.ascontiguousarray(cfg["pos"][:, lo:hi])
+    total_pairs = pairs_of(cfg)
+
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+    h_cov, h_z1, h_z2 = pin(h_cov), pin(h_z1), pin(h_z2)
+    d_cov, d_z1, d_z2 = (torch.tensor(a, device=dev) for a in (h_cov, h_z1, h_z2))
+    if structured:
+        h_axes = [pin(a) for a in h_axes]
+        d_axes = [torch.tensor(a, device=dev) for a in h_axes]
+        fn = gsb.summate_incompr_structured if vec else gsb.summate_structured
+
+        def step_device():
+            return fn(d_cov, d_z1, d_z2, d_axes, cfg.get("matrix"))
+
+        def step_host():
+            return fn(h_cov, h_z1, h_z2, h_axes, cfg.get("matrix"))
+
+        h2d = h_cov.nbytes + h_z1.nbytes + h_z2.nbytes + sum(a.nbytes for a in h_axes)
+    else:
+        h_pos = pin(h_pos)
+        d_pos = torch.tensor(h_pos, device=dev)
+        fn = gsb.summate_incompr if vec else gsb.summate
+
+        def step_device():
+            return fn(d_cov, d_z1, d_z2, d_pos)
+
+        def step_host():
+            return fn(h_cov, h_z1, h_z2, h_pos)
+
+        h2d = h_cov.nbytes + h_z1.nbytes + h_z2.nbytes + h_pos.nbytes
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    peak_dfma = gsb.measure_fp64_peak(local, 0, 0.4)
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        out = step_device()
+        del out
+    barrier()
+    gsb.set_option("time_kernels", 1)
+    gsb.kernel_times()
+    launches0 = gsb.get_counter("launches")
+    pairs = []
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.fill_(1)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = step_device()
+            e1.record()
+            pairs.append((e0, e1))
+            del out
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = gsb.get_counter("launches") - launches0
+    kern_ms, kern_n = gsb.kernel_times()
+    gsb.set_option("time_kernels", 0)
+    dev_s = sum(a.elapsed_time(b) for a, b in pairs) * 1e-3
+    t = torch.tensor([dev_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s = float(t.item())
+    value = args.steps * total_pairs / dev_s
+
+    # ---- end to end through the public numpy API (host in, host out) ----
+    out = None
+    for _ in range(max(args.warmup, 3)):     # also warms the pinned-host allocator
+        del out
+        out = step_host()
+    d2h = out.nbytes
+    del out
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step_host()
+        del out
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = args.steps * total_pairs / e2e_s
+
+    if rank == 0:
+        # dominant kernel: per-launch duration from events recorded around it on its stream
+        units = cfg["cov"].shape[0] if batched else (len(cfg["axes"][0]) if structured else cfg["pos"].shape[1])
+        share = (hi - lo) / units     # rank 0's part of the sharded workload
+        pairs_per_launch = total_pairs * share * args.steps / max(kern_n, 1)
+        flop_per_pair = 2.0 * cfg["work_per_pair_dfma"]
+        kern_s = kern_ms * 1e-3 / max(kern_n, 1)
+        achieved = pairs_per_launch * flop_per_pair / kern_s / 1e12 if kern_n else None
+        peak_tflops = 2.0 * peak_dfma / 1e12
+        traffic = None
+        prof = os.path.join(REPO, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get(cfg["tag"])
+            except Exception:
+                traffic = None
+        roofline = {
+            "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": (achieved / peak_tflops) if achieved else None, "traffic": traffic,
+            "kernel": "separable_kernel (DMMA.8x8x4)" if structured else "direct_kernel",
+            "kernel_ms_per_launch": 1e3 * kern_s, "launches_timed": kern_n,
+            "kernel_share_of_step": (kern_ms * 1e-3) / dev_s if dev_s else None,
+            "algorithmic_flop_per_pair": flop_per_pair,
+            "peak_source": "DFMA microbenchmark run in this process (gsb_measure_fp64_peak); "
+                           "MEASURED_PEAKS.json has no fp64 entry",
+            "frac_of_nominal_37.2_TFLOPs": (achieved / (2 * NOMINAL_DFMA_PER_S / 1e12)) if achieved else None,
+        }
+        cpu = cpu_baseline(cfg) if world == 1 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(cfg, args),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "api": "gstools_b200.summate_structured(numpy...) -> numpy (pinned)"
+                           if structured else "gstools_b200.summate(numpy...) -> numpy"},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks.summary(),
+            "wall_s_timed_region": t_wall,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    cfg = make_workload(args.workload)
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+    else:
+        run_b200_arm(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

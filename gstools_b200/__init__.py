@@ -13,7 +13,8 @@ The compute lives in ``libgsb200.so`` (C ABI in ``include/gsb200.h``); there is 
 """
 
 from . import _build, _lib
-from ._lib import GSB200Error, device_count, get_counter, measure_fp64_peak, set_option
+from ._lib import (GSB200Error, device_count, get_counter, kernel_times, measure_fp64_peak,
+                   set_option)
 from .backend import (
     get_device,
     scale_shift_,
@@ -42,6 +43,7 @@ __all__ = [
     "get_counter",
     "set_option",
     "measure_fp64_peak",
+    "kernel_times",
     "GSB200Error",
     "build",
 ]

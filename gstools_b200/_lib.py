@@ -35,6 +35,7 @@ SIGNATURES = {
     "gsb_scale_shift": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp]),
     "gsb_set_option": (_int, [ctypes.c_char_p, _i64]),
     "gsb_get_counter": (_i64, [ctypes.c_char_p]),
+    "gsb_kernel_times": (_int, [_c_double_p, _c_int64_p]),
     "gsb_measure_fp64_peak": (_int, [_int, _int, ctypes.c_double, _c_double_p]),
 }
 
@@ -94,6 +95,14 @@ def set_option(name: str, value: int):
 
 def get_counter(name: str) -> int:
     return int(load().gsb_get_counter(name.encode()))
+
+
+def kernel_times():
+    """(total_ms, n_launches) of the timed dominant kernels since the last call."""
+    ms = ctypes.c_double(0.0)
+    n = ctypes.c_int64(0)
+    check(load().gsb_kernel_times(ctypes.byref(ms), ctypes.byref(n)), "gsb_kernel_times")
+    return float(ms.value), int(n.value)
 
 
 def measure_fp64_peak(device: int = 0, kind: int = 0, seconds: float = 0.3) -> float:

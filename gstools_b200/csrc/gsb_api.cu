@@ -22,6 +22,29 @@ static std::atomic<int64_t> g_opt_host_chunk_points{1 << 22};
 static std::atomic<int64_t> g_opt_slab_tiles{148 * 6};
 static std::atomic<int64_t> g_opt_sep_variant{0};  // 0 = DMMA, 1 = DFMA register tile
 static std::atomic<int64_t> g_cnt_direct{0}, g_cnt_separable{0};
+// optional device-side timing of the dominant kernels (bench.py roofline): events recorded on the
+// launch stream around every direct / separable launch while the option "time_kernels" is 1
+static std::atomic<int64_t> g_opt_time_kernels{0};
+static std::mutex g_time_mutex;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_time_events;
+
+struct KernelTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t st;
+    explicit KernelTimer(cudaStream_t s) : st(s)
+    {
+        if (!g_opt_time_kernels.load()) return;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+        cudaEventRecord(e0, st);
+    }
+    ~KernelTimer()
+    {
+        if (!e0) return;
+        cudaEventRecord(e1, st);
+        std::lock_guard<std::mutex> lock(g_time_mutex);
+        g_time_events.emplace_back(e0, e1);
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // device bookkeeping
@@ -159,7 +182,10 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
     prm.partial = nullptr;
     const int ncomp = vec ? dim : 1;
     if (n_split > 1) GSB_TRY(scr.alloc(&prm.partial, (size_t)n_split * ncomp * n_pts));
-    GSB_TRY(launch_direct(dim, vec, prm, cfg, st));
+    {
+        KernelTimer timer(st);
+        GSB_TRY(launch_direct(dim, vec, prm, cfg, st));
+    }
     if (n_split > 1) {
         dim3 grid((unsigned)((n_pts + 255) / 256), (unsigned)ncomp);
         reduce_partials_kernel<<<grid, 256, 0, st>>>(prm.partial, n_split, ncomp, n_pts, d_out, out_ld);
@@ -393,7 +419,10 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         s2.row_len[0] = nx;
         s2.n_rows = nx * rows_per_x;
         s2.out = d_out + x0 * rows_per_x * lc;
-        GSB_TRY(launch_separable(s2, n_batch, (int)g_opt_sep_variant.load(), st));
+        {
+            KernelTimer timer(st);
+            GSB_TRY(launch_separable(s2, n_batch, (int)g_opt_sep_variant.load(), st));
+        }
         if (h_out && single_field) {
             GSB_CUDA(cudaEventRecord(ev, st));
             GSB_CUDA(cudaStreamWaitEvent(copy_st, ev, 0));
@@ -627,6 +656,7 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "host_chunk_points") g_opt_host_chunk_points = value;
     else if (n == "slab_tiles") g_opt_slab_tiles = value;
     else if (n == "sep_variant") g_opt_sep_variant = value;
+    else if (n == "time_kernels") g_opt_time_kernels = value;
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);
     return GSB_OK;
 }
@@ -639,6 +669,27 @@ int64_t gsb_get_counter(const char *name)
     if (n == "direct_calls") return g_cnt_direct.load();
     if (n == "separable_calls") return g_cnt_separable.load();
     return -1;
+}
+
+int gsb_kernel_times(double *total_ms, int64_t *n_launches)
+{
+    if (!total_ms || !n_launches) return fail(GSB_ERR_ARGUMENT, "NULL output pointer");
+    std::lock_guard<std::mutex> lock(g_time_mutex);
+    double tot = 0.0;
+    int64_t n = 0;
+    for (auto &ev : g_time_events) {
+        float ms = 0.f;
+        GSB_CUDA(cudaEventSynchronize(ev.second));
+        GSB_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        tot += ms;
+        ++n;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    g_time_events.clear();
+    *total_ms = tot;
+    *n_launches = n;
+    return GSB_OK;
 }
 
 int gsb_measure_fp64_peak(int device, int kind, double seconds, double *fma_per_s)

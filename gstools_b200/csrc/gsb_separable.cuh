@@ -36,7 +36,8 @@ namespace gsb {
 constexpr int SEP_TM = 128;      // rows per CTA tile
 constexpr int SEP_TN = 128;      // columns per CTA tile
 constexpr int SEP_KC = 8;        // modes per pipeline stage
-constexpr int SEP_STAGES = 4;
+constexpr int SEP_STAGES = 5;
+constexpr int SEP_LOOKAHEAD = 2;   // A operand is generated this many stages ahead (needs STAGES >= 2*LOOKAHEAD)
 constexpr int SEP_CONSUMER_WARPS = 8;
 constexpr int SEP_PRODUCER_WARPS = 4;   // one full warpgroup, so setmaxnreg can rebalance registers
 constexpr int SEP_THREADS = (SEP_CONSUMER_WARPS + SEP_PRODUCER_WARPS) * 32;
@@ -249,9 +250,13 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
     const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 
     // ---- cooperative generation of the A operand: thread -> (tile row, 4 of the KC modes) ----
-    // The loads for stage s+1 are issued before the contraction of stage s and consumed after
-    // it, so their L2 latency is hidden; the complex products run on the issuing warp's own
+    // The loads for stage s+LOOKAHEAD are issued before the contraction of stage s and consumed
+    // after it, so their L2 latency is hidden; the complex products run on the issuing warp's own
     // FP64 slots (in order with its DMMAs -- a dedicated producer warp starves behind them).
+    // LOOKAHEAD = 2 keeps the warps out of lock step: full[s+1] only needs every warp to have
+    // finished stage s-1.  Slot reuse is safe for STAGES >= 2*LOOKAHEAD: a thread writing stage
+    // s+LOOKAHEAD has passed full[s], which all threads arrived on after finishing stage
+    // s-LOOKAHEAD >= s+LOOKAHEAD-STAGES.
     const int grow = tid & (SEP_TM - 1);
     const int gm0 = (tid >> 7) * (SEP_KC / 2);
     const double2 *ep[NRA];
@@ -303,9 +308,12 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
         mbar_arrive(&full[slot]);  // release: this thread's part of the A tile is written
     };
 
-    if (n_stages_total > 0) {
-        gen_load(0);
-        gen_store(0);
+#pragma unroll
+    for (int p = 0; p < SEP_LOOKAHEAD; ++p) {
+        if (p < n_stages_total) {
+            gen_load(p);
+            gen_store(p);
+        }
     }
 
     if (MMA) {
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
 
         for (int s = 0; s < n_stages_total; ++s) {
             const int slot = s % SEP_STAGES;
-            if (s + 1 < n_stages_total) gen_load(s + 1);
+            if (s + SEP_LOOKAHEAD < n_stages_total) gen_load(s + SEP_LOOKAHEAD);
             mbar_wait(&full[slot], (s / SEP_STAGES) & 1);
             const double *A = stage_base + slot * STAGE_DOUBLES;
             const double *B = A + SEP_TM * SEP_AST;
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
-            if (s + 1 < n_stages_total) gen_store(s + 1);
+            if (s + SEP_LOOKAHEAD < n_stages_total) gen_store(s + SEP_LOOKAHEAD);
         }
         // epilogue: thread holds C[g][2t], C[g][2t+1] of every 8x8 tile
 #pragma unroll
@@ -373,7 +381,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
 
         for (int s = 0; s < n_stages_total; ++s) {
             const int slot = s % SEP_STAGES;
-            if (s + 1 < n_stages_total) gen_load(s + 1);
+            if (s + SEP_LOOKAHEAD < n_stages_total) gen_load(s + SEP_LOOKAHEAD);
             mbar_wait(&full[slot], (s / SEP_STAGES) & 1);
             const double *Ar = stage_base + slot * STAGE_DOUBLES;
             const double *Ai = Ar + SEP_KC * SEP_TM;
@@ -404,7 +412,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
-            if (s + 1 < n_stages_total) gen_store(s + 1);
+            if (s + SEP_LOOKAHEAD < n_stages_total) gen_store(s + SEP_LOOKAHEAD);
         }
 #pragma unroll
         for (int a = 0; a < 8; ++a) {

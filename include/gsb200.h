@@ -113,10 +113,21 @@ int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int de
  *   gsb_set_option("structured_min_tiles", v): meshes with fewer 128x128 output tiles than v
  *       are expanded on the device and sent through the direct kernel (default 64).
  *   gsb_set_option("force_path", 0|1|2): 0 auto, 1 always direct, 2 always separable.
- *   gsb_get_counter("launches"): CUDA kernels launched by this library so far (process-wide).
+ *   gsb_set_option("sep_variant", 0|1): separable consumer, 0 = DMMA.8x8x4 (default), 1 = DFMA tile.
+ *   gsb_set_option("time_kernels", 0|1): see gsb_kernel_times().
+ *   gsb_get_counter("launches"): CUDA kernels launched by this library so far (process-wide);
+ *   "direct_calls" / "separable_calls": how often each path ran.
  */
 int gsb_set_option(const char *name, int64_t value);
 int64_t gsb_get_counter(const char *name);
+
+/*
+ * Device-side timing of the dominant kernels (roofline evidence).  While the option
+ * "time_kernels" is 1, CUDA events are recorded on the launch stream around every direct /
+ * separable kernel launch.  gsb_kernel_times() waits for them, returns the summed duration and
+ * the number of launches since the previous call, and clears the list.
+ */
+int gsb_kernel_times(double *total_ms, int64_t *n_launches);
 
 /*
  * FP64-pipe microbenchmark used as the roofline denominator: runs a register-resident
