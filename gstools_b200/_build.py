@@ -12,7 +12,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libgsb200.so")
+LIB = os.environ.get("GSB200_LIB") or os.path.join(HERE, "libgsb200.so")
 SOURCES = ["gsb_api.cu"]
 HEADERS = ["gsb_common.cuh", "gsb_direct.cuh", "gsb_separable.cuh", "sincos_coeffs.cuh"]
 NVCC_FLAGS = [
@@ -39,11 +39,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > lib_m for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Build ``libgsb200.so`` if it is missing or older than its sources."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out=None) -> str:
+    """Build ``libgsb200.so`` if it is missing or older than its sources.
+
+    ``defines`` / ``out`` build a tuning variant (e.g. ``defines=["GSB_SEP_KC=16"]``) next to it.
+    """
+    target = out or LIB
+    if not force and out is None and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", target + ".tmp",
+           *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)
@@ -51,8 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
     subprocess.check_call(cmd, env=env)
-    os.replace(LIB + ".tmp", LIB)
-    return LIB
+    os.replace(target + ".tmp", target)
+    return target
 
 
 if __name__ == "__main__":

@@ -35,20 +35,21 @@ namespace gsb {
 
 constexpr int SEP_TM = 128;      // rows per CTA tile
 constexpr int SEP_TN = 128;      // columns per CTA tile
-constexpr int SEP_KC = 8;        // modes per pipeline stage
-constexpr int SEP_STAGES = 5;
-constexpr int SEP_LOOKAHEAD = 2;   // A operand is generated this many stages ahead (needs STAGES >= 2*LOOKAHEAD)
-constexpr int SEP_CONSUMER_WARPS = 8;
-constexpr int SEP_PRODUCER_WARPS = 4;   // one full warpgroup, so setmaxnreg can rebalance registers
-constexpr int SEP_THREADS = (SEP_CONSUMER_WARPS + SEP_PRODUCER_WARPS) * 32;
-constexpr int SEP_REGS_PRODUCER = 24;
-constexpr int SEP_REGS_CONSUMER = 240;  // 128*24 + 256*240 = 64512 <= 65536
+#ifndef GSB_SEP_KC
+#define GSB_SEP_KC 8
+#endif
+#ifndef GSB_SEP_STAGES
+#define GSB_SEP_STAGES 5
+#endif
+#ifndef GSB_SEP_LOOKAHEAD
+#define GSB_SEP_LOOKAHEAD 2
+#endif
+constexpr int SEP_KC = GSB_SEP_KC;        // modes per pipeline stage (multiple of 4)
+constexpr int SEP_STAGES = GSB_SEP_STAGES;
+constexpr int SEP_LOOKAHEAD = GSB_SEP_LOOKAHEAD;   // A operand is generated this many stages ahead (needs STAGES >= 2*LOOKAHEAD)
+static_assert(SEP_KC % 4 == 0 && SEP_STAGES >= 2 * SEP_LOOKAHEAD + 1, "pipeline shape");
 constexpr int SEP_MAX_ROW_AXES = GSB_MAX_DIM - 1;
 
-// shared memory carve-up per stage: Ar[KC][TM], Ai[KC][TM], Bc[KC][TN], Bs[KC][TN] (doubles)
-constexpr int SEP_STAGE_DOUBLES = SEP_KC * (2 * SEP_TM + 2 * SEP_TN);
-constexpr size_t SEP_SMEM_BYTES =
-    (size_t)SEP_STAGES * SEP_STAGE_DOUBLES * sizeof(double) + 2 * SEP_STAGES * sizeof(uint64_t) + 128;
 
 struct SepParams {
     // row-axis tables: E_t[j * len_t + i] = exp(i k'_{t,j} a_t[i]) as (cos, sin); t = 0 is
@@ -161,25 +162,40 @@ __global__ void build_tables_kernel(const TableParams tp)
 // ---------------------------------------------------------------------------------------------
 // the contraction kernel
 //
-// Two consumer variants share the producer and the pipeline:
-//   MMA = true  (default): DMMA.8x8x4 (mma.sync m8n8k4 f64) on the tensor-core FP64 path.  B200
-//                runs it at the same FMA rate as DFMA, but one instruction carries 256 FMAs with
-//                8 register reads, so neither the register-file bandwidth (3 x 64-bit operands per
-//                DFMA exceed the 2 reads/clk the RF sustains once the operand-reuse cache is lost
-//                between warps) nor shared-memory fragment traffic limits the FP64 pipe.
-//   MMA = false: register-tiled DFMA (8x8 accumulators per thread), kept for the ablation in
-//                profiles/ (73 % of the FP64 peak vs the DMMA variant).
-// Shared-memory layouts per stage:
-//   MMA : A[row][SEP_AST]  k = 2*kc + part (part 0: p*Re A, part 1: -p*Im A), rows padded to 20
-//         doubles so that the 8x4 fragment loads (LDS.64) hit 32 distinct banks per half warp;
-//         B[2*kc + part][SEP_BST] (part 0: cos, part 1: sin), rows padded to 132 doubles likewise.
-//   DFMA: Ar[kc][128], Ai[kc][128], Bc[kc][128], Bs[kc][128].
+// The consumers run DMMA.8x8x4 (mma.sync m8n8k4 f64) on the tensor-core FP64 path.  B200 executes
+// it at the same FMA rate as DFMA (measured 18.5 vs 18.4 TFMA/s), but one instruction carries 256
+// FMAs with 8 register reads, so neither the register file (3 x 64-bit operands per DFMA exceed
+// the 2 reads/clk it sustains once the operand-reuse cache is lost between warps: a register-tiled
+// DFMA version of this kernel measured 73 % of the FP64 peak, profiles/) nor shared-memory
+// fragment traffic limits the pipe.
+// Shared-memory layout per stage:
+//   A[row][SEP_AST]           k = 2*kc + part (part 0: p*Re A, part 1: -p*Im A); rows padded to
+//                             2*KC+4 doubles so the 8x4 fragment loads (LDS.64) hit 32 distinct
+//                             banks per half warp;
+//   B[2*kc + part][SEP_BST]   part 0: cos, part 1: sin; rows padded to 132 doubles likewise.
+// Two warp configurations (template CFG), no warp specialisation (every warp contracts, every
+// thread generates part of A, thread 0 issues the TMA copies):
+//   CFG 0: 16 warps (4 per SM sub-partition), warp tile 32x32 = 4x4 DMMA tiles, 32 accumulators
+//          per thread, 512 threads x 128 registers;
+//   CFG 1:  8 warps (2 per sub-partition), warp tile 32x64 = 4x8 DMMA tiles, 64 accumulators per
+//          thread, 256 threads x 255 registers.
 // ---------------------------------------------------------------------------------------------
-constexpr int SEP_AST = 2 * SEP_KC + 4;   // A row stride (doubles), == 4 mod 16
-constexpr int SEP_BST = SEP_TN + 4;       // B row stride (doubles), == 4 mod 16
-constexpr int SEP_STAGE_DOUBLES_MMA = SEP_TM * SEP_AST + 2 * SEP_KC * SEP_BST;
-constexpr size_t SEP_SMEM_BYTES_MMA =
-    (size_t)SEP_STAGES * SEP_STAGE_DOUBLES_MMA * sizeof(double) + 2 * SEP_STAGES * sizeof(uint64_t) + 128;
+constexpr int SEP_AST = 2 * SEP_KC + 4;   // A row stride (doubles)
+constexpr int SEP_BST = SEP_TN + 4;       // B row stride (doubles)
+constexpr int SEP_STAGE_DOUBLES = SEP_TM * SEP_AST + 2 * SEP_KC * SEP_BST;
+constexpr size_t SEP_SMEM_BYTES =
+    (size_t)SEP_STAGES * SEP_STAGE_DOUBLES * sizeof(double) + SEP_STAGES * sizeof(uint64_t) + 128;
+
+template <int CFG>
+struct SepCfg;
+template <>
+struct SepCfg<0> {
+    static constexpr int WARPS = 16, WCOLS = 4, RT = 4, CT = 4;   // 512 threads x 128 registers
+};
+template <>
+struct SepCfg<1> {
+    static constexpr int WARPS = 8, WCOLS = 2, RT = 4, CT = 8;    // 256 threads x 255 registers
+};
 
 __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b)
 {
@@ -188,15 +204,19 @@ __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, doubl
                  : "d"(a), "d"(b));
 }
 
-template <int NRA, bool MMA>  // NRA = number of row axes (dim - 1), 1..SEP_MAX_ROW_AXES
-__global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepParams prm)
+template <int NRA, int CFG>  // NRA = number of row axes (dim - 1), 1..SEP_MAX_ROW_AXES
+__device__ __forceinline__ void separable_body(const SepParams &prm)
 {
-    constexpr int STAGE_DOUBLES = MMA ? SEP_STAGE_DOUBLES_MMA : SEP_STAGE_DOUBLES;
-    constexpr int NCONS = SEP_CONSUMER_WARPS * 32;
+    using C = SepCfg<CFG>;
+    constexpr int NTHR = C::WARPS * 32;
+    constexpr int RT = C::RT, CT = C::CT;
+    constexpr int GEN = SEP_TM * SEP_KC / NTHR;   // A entries generated per thread per stage
+    static_assert(C::WARPS / C::WCOLS * RT * 8 == SEP_TM && C::WCOLS * CT * 8 == SEP_TN, "tile");
+    static_assert(GEN >= 1 && SEP_TM * SEP_KC % NTHR == 0, "A generation split");
+
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stage_base = reinterpret_cast<double *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + SEP_STAGES * STAGE_DOUBLES);
-    uint64_t *empty = full + SEP_STAGES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + SEP_STAGES * SEP_STAGE_DOUBLES);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -208,57 +228,45 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
     const int n_stages_total = prm.n_modes_pad / SEP_KC;
 
     if (tid == 0) {
-        for (int s = 0; s < SEP_STAGES; ++s) {
-            mbar_init(&full[s], NCONS + 1);            // 256 A-operand writers + the TMA issuer
-            mbar_init(&empty[s], SEP_CONSUMER_WARPS);  // one arrive per consumer warp
-        }
+        for (int s = 0; s < SEP_STAGES; ++s) mbar_init(&full[s], NTHR + 1);  // A writers + TMA issuer
         fence_barrier_init();
     }
     __syncthreads();
 
-    if (warp >= SEP_CONSUMER_WARPS) {
-        // ================== TMA WARPGROUP: one thread feeds the B operand ==================
-        // Registers are handed to the consumers (setmaxnreg); the idle warps retire at once.
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SEP_REGS_PRODUCER));
-        if (tid != NCONS) return;
-        const double *bc = prm.bc + batch * prm.b_bstride + col0;
-        const double *bs = prm.bs + batch * prm.b_bstride + col0;
-        for (int s = 0; s < n_stages_total; ++s) {
-            const int slot = s % SEP_STAGES;
-            const int round = s / SEP_STAGES;
-            if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
-            double *B = stage_base + slot * STAGE_DOUBLES + (MMA ? SEP_TM * SEP_AST : 2 * SEP_KC * SEP_TM);
-            const int64_t j0 = (int64_t)s * SEP_KC;
-            mbar_arrive_expect_tx(&full[slot], 2 * SEP_KC * SEP_TN * sizeof(double));
-#pragma unroll
-            for (int kc = 0; kc < SEP_KC; ++kc) {
-                // MMA: smem row 2*kc + part      DFMA: smem row part*KC + kc      (part 0 cos, 1 sin)
-                double *dc = B + (MMA ? (2 * kc) * SEP_BST : kc * SEP_TN);
-                double *ds = B + (MMA ? (2 * kc + 1) * SEP_BST : (SEP_KC + kc) * SEP_TN);
-                bulk_g2s(dc, bc + (j0 + kc) * prm.lc_pad, SEP_TN * sizeof(double), &full[slot]);
-                bulk_g2s(ds, bs + (j0 + kc) * prm.lc_pad, SEP_TN * sizeof(double), &full[slot]);
-            }
-        }
-        return;
-    }
-
-    // ================================ CONSUMER WARPGROUPS ================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SEP_REGS_CONSUMER));
-    const int wr = warp >> 1;        // 0..3 : 32-row band
-    const int wc = warp & 1;         // 0..1 : 64-column band
+    const int wr = warp / C::WCOLS;      // row band of RT*8 rows
+    const int wc = warp % C::WCOLS;      // column band of CT*8 columns
     double *out = prm.out + (batch * prm.ncomp + comp) * prm.out_fstride;
     const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 
-    // ---- cooperative generation of the A operand: thread -> (tile row, 4 of the KC modes) ----
+    // ---- B operand: thread 0 issues the cp.async.bulk copies (TMA unit) of stage s -------------
+    // 2*KC table-row slices of 1 KB each, completion counted on the stage's mbarrier.
+    const double *bc = prm.bc + batch * prm.b_bstride + col0;
+    const double *bs = prm.bs + batch * prm.b_bstride + col0;
+    auto tma_issue = [&](int s) {
+        const int slot = s % SEP_STAGES;
+        double *B = stage_base + slot * SEP_STAGE_DOUBLES + SEP_TM * SEP_AST;
+        const int64_t j0 = (int64_t)s * SEP_KC;
+        mbar_arrive_expect_tx(&full[slot], 2 * SEP_KC * SEP_TN * sizeof(double));
+#pragma unroll
+        for (int kc = 0; kc < SEP_KC; ++kc) {
+            bulk_g2s(B + (2 * kc) * SEP_BST, bc + (j0 + kc) * prm.lc_pad, SEP_TN * sizeof(double), &full[slot]);
+            bulk_g2s(B + (2 * kc + 1) * SEP_BST, bs + (j0 + kc) * prm.lc_pad, SEP_TN * sizeof(double), &full[slot]);
+        }
+    };
+
+    // ---- A operand: generated cooperatively, thread -> (tile row, GEN of the KC modes) ---------
     // The loads for stage s+LOOKAHEAD are issued before the contraction of stage s and consumed
     // after it, so their L2 latency is hidden; the complex products run on the issuing warp's own
     // FP64 slots (in order with its DMMAs -- a dedicated producer warp starves behind them).
     // LOOKAHEAD = 2 keeps the warps out of lock step: full[s+1] only needs every warp to have
-    // finished stage s-1.  Slot reuse is safe for STAGES >= 2*LOOKAHEAD: a thread writing stage
-    // s+LOOKAHEAD has passed full[s], which all threads arrived on after finishing stage
-    // s-LOOKAHEAD >= s+LOOKAHEAD-STAGES.
+    // finished stage s-1.
+    // Slot reuse needs no "empty" barrier when STAGES >= 2*LOOKAHEAD + 1: a thread that has
+    // passed full[s] knows that ALL threads arrived on it, which each does only after finishing
+    // the contraction of stage s-LOOKAHEAD; the slot of stage s+LOOKAHEAD was last read by stage
+    // s+LOOKAHEAD-STAGES <= s-LOOKAHEAD-1.  Both the A writes and the TMA issue for stage
+    // s+LOOKAHEAD happen after that wait.
     const int grow = tid & (SEP_TM - 1);
-    const int gm0 = (tid >> 7) * (SEP_KC / 2);
+    const int gm0 = (tid / SEP_TM) * GEN;
     const double2 *ep[NRA];
     {
         int64_t r = row0 + grow;
@@ -272,19 +280,19 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
     }
     const double *proj =
         prm.proj ? prm.proj + batch * prm.proj_bstride + (int64_t)comp * prm.n_modes_pad : nullptr;
-    double2 ge[NRA][SEP_KC / 2];
+    double2 ge[NRA][GEN];
     auto gen_load = [&](int s) {
         const int64_t j = (int64_t)s * SEP_KC + gm0;
 #pragma unroll
         for (int t = 0; t < NRA; ++t)
 #pragma unroll
-            for (int u = 0; u < SEP_KC / 2; ++u) ge[t][u] = __ldg(ep[t] + (j + u) * prm.row_stride[t]);
+            for (int u = 0; u < GEN; ++u) ge[t][u] = __ldg(ep[t] + (j + u) * prm.row_stride[t]);
     };
     auto gen_store = [&](int s) {
         const int slot = s % SEP_STAGES;
-        double *A = stage_base + slot * STAGE_DOUBLES;
+        double *A = stage_base + slot * SEP_STAGE_DOUBLES;
 #pragma unroll
-        for (int u = 0; u < SEP_KC / 2; ++u) {
+        for (int u = 0; u < GEN; ++u) {
             double2 e = ge[0][u];
 #pragma unroll
             for (int t = 1; t < NRA; ++t) {
@@ -298,12 +306,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
                 e.x *= pj;
                 e.y *= pj;
             }
-            if (MMA) {
-                *reinterpret_cast<double2 *>(A + grow * SEP_AST + 2 * (gm0 + u)) = make_double2(e.x, -e.y);
-            } else {
-                A[(gm0 + u) * SEP_TM + grow] = e.x;
-                A[(SEP_KC + gm0 + u) * SEP_TM + grow] = -e.y;
-            }
+            *reinterpret_cast<double2 *>(A + grow * SEP_AST + 2 * (gm0 + u)) = make_double2(e.x, -e.y);
         }
         mbar_arrive(&full[slot]);  // release: this thread's part of the A tile is written
     };
@@ -311,161 +314,119 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) separable_kernel(const SepPara
 #pragma unroll
     for (int p = 0; p < SEP_LOOKAHEAD; ++p) {
         if (p < n_stages_total) {
+            if (tid == 0) tma_issue(p);
             gen_load(p);
             gen_store(p);
         }
     }
 
-    if (MMA) {
-        // warp tile 32 x 64 = 4 x 8 DMMA tiles of 8x8; fragment owner: g = lane/4, t = lane%4
-        const int g = lane >> 2;
-        const int t = lane & 3;
-        double acc[4][8][2];
+    // warp tile = RT x CT DMMA tiles of 8x8; fragment owner: g = lane/4, t = lane%4
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    double acc[RT][CT][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RT; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        const int a_off = (wr * 32 + g) * SEP_AST + t;   // + rt*8*SEP_AST + 4*k4
-        const int b_off = t * SEP_BST + wc * 64 + g;     // + 4*k4*SEP_BST + ct*8
+        for (int j = 0; j < CT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int a_off = (wr * RT * 8 + g) * SEP_AST + t;   // + i*8*SEP_AST + 4*k4
+    const int b_off = t * SEP_BST + wc * CT * 8 + g;     // + 4*k4*SEP_BST + j*8
 
-        for (int s = 0; s < n_stages_total; ++s) {
-            const int slot = s % SEP_STAGES;
-            if (s + SEP_LOOKAHEAD < n_stages_total) gen_load(s + SEP_LOOKAHEAD);
-            mbar_wait(&full[slot], (s / SEP_STAGES) & 1);
-            const double *A = stage_base + slot * STAGE_DOUBLES;
-            const double *B = A + SEP_TM * SEP_AST;
+    for (int s = 0; s < n_stages_total; ++s) {
+        const int slot = s % SEP_STAGES;
+        if (s + SEP_LOOKAHEAD < n_stages_total) gen_load(s + SEP_LOOKAHEAD);
+        mbar_wait(&full[slot], (s / SEP_STAGES) & 1);
+        if (tid == 0 && s + SEP_LOOKAHEAD < n_stages_total) tma_issue(s + SEP_LOOKAHEAD);
+        const double *A = stage_base + slot * SEP_STAGE_DOUBLES;
+        const double *B = A + SEP_TM * SEP_AST;
 #pragma unroll
-            for (int k4 = 0; k4 < SEP_KC / 2; ++k4) {   // 4 contraction indices = 2 modes
-                double af[4], bf[8];
+        for (int k4 = 0; k4 < SEP_KC / 2; ++k4) {   // 4 contraction indices = 2 modes
+            double af[RT], bf[CT];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) af[i] = A[a_off + i * 8 * SEP_AST + 4 * k4];
+            for (int i = 0; i < RT; ++i) af[i] = A[a_off + i * 8 * SEP_AST + 4 * k4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) bf[j] = B[b_off + 4 * k4 * SEP_BST + j * 8];
+            for (int j = 0; j < CT; ++j) bf[j] = B[b_off + 4 * k4 * SEP_BST + j * 8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < CT; ++j)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
-            if (s + SEP_LOOKAHEAD < n_stages_total) gen_store(s + SEP_LOOKAHEAD);
+                for (int i = 0; i < RT; ++i) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
-        // epilogue: thread holds C[g][2t], C[g][2t+1] of every 8x8 tile
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t row = row0 + wr * 32 + i * 8 + g;
-            if (row >= prm.n_rows) continue;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
-                double *dst = out + row * prm.lc + col;
-                if (vec2 && col + 1 < prm.lc) {
-                    *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
-                } else {
-                    if (col < prm.lc) dst[0] = acc[i][j][0];
-                    if (col + 1 < prm.lc) dst[1] = acc[i][j][1];
-                }
-            }
-        }
-    } else {
-        const int g = lane >> 3;         // 0..3
-        const int h = lane & 7;          // 0..7
-        // thread rows: wr*32 + 8*i + 2*g + {0,1}, i = 0..3 ; cols: wc*64 + 16*i + 2*h + {0,1}
-        const int arow = wr * 32 + 2 * g;
-        const int bcol = wc * 64 + 2 * h;
-        double acc[8][8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-#pragma unroll
-            for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+        if (s + SEP_LOOKAHEAD < n_stages_total) gen_store(s + SEP_LOOKAHEAD);
+    }
 
-        for (int s = 0; s < n_stages_total; ++s) {
-            const int slot = s % SEP_STAGES;
-            if (s + SEP_LOOKAHEAD < n_stages_total) gen_load(s + SEP_LOOKAHEAD);
-            mbar_wait(&full[slot], (s / SEP_STAGES) & 1);
-            const double *Ar = stage_base + slot * STAGE_DOUBLES;
-            const double *Ai = Ar + SEP_KC * SEP_TM;
-            const double *Bc = Ai + SEP_KC * SEP_TM;
-            const double *Bs = Bc + SEP_KC * SEP_TN;
+    // epilogue: thread holds C[g][2t], C[g][2t+1] of every 8x8 tile
 #pragma unroll
-            for (int kc = 0; kc < SEP_KC; ++kc) {
-                double ar[8], ai[8], bc[8], bs[8];
+    for (int i = 0; i < RT; ++i) {
+        const int64_t row = row0 + wr * RT * 8 + i * 8 + g;
+        if (row >= prm.n_rows) continue;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double2 va = *reinterpret_cast<const double2 *>(Ar + kc * SEP_TM + arow + 8 * i);
-                    const double2 vi = *reinterpret_cast<const double2 *>(Ai + kc * SEP_TM + arow + 8 * i);
-                    const double2 vc = *reinterpret_cast<const double2 *>(Bc + kc * SEP_TN + bcol + 16 * i);
-                    const double2 vs = *reinterpret_cast<const double2 *>(Bs + kc * SEP_TN + bcol + 16 * i);
-                    ar[2 * i] = va.x; ar[2 * i + 1] = va.y;
-                    ai[2 * i] = vi.x; ai[2 * i + 1] = vi.y;
-                    bc[2 * i] = vc.x; bc[2 * i + 1] = vc.y;
-                    bs[2 * i] = vs.x; bs[2 * i + 1] = vs.y;
-                }
-#pragma unroll
-                for (int a = 0; a < 8; ++a)
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) acc[a][b] = fma(ar[a], bc[b], acc[a][b]);
-#pragma unroll
-                for (int a = 0; a < 8; ++a)
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) acc[a][b] = fma(ai[a], bs[b], acc[a][b]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
-            if (s + SEP_LOOKAHEAD < n_stages_total) gen_store(s + SEP_LOOKAHEAD);
-        }
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            const int64_t row = row0 + arow + 8 * (a >> 1) + (a & 1);
-            if (row >= prm.n_rows) continue;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t col = col0 + bcol + 16 * i;
-                double *dst = out + row * prm.lc + col;
-                if (vec2 && col + 1 < prm.lc) {
-                    *reinterpret_cast<double2 *>(dst) = make_double2(acc[a][2 * i], acc[a][2 * i + 1]);
-                } else {
-                    if (col < prm.lc) dst[0] = acc[a][2 * i];
-                    if (col + 1 < prm.lc) dst[1] = acc[a][2 * i + 1];
-                }
+        for (int j = 0; j < CT; ++j) {
+            const int64_t col = col0 + wc * CT * 8 + j * 8 + 2 * t;
+            double *dst = out + row * prm.lc + col;
+            if (vec2 && col + 1 < prm.lc) {
+                *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+            } else {
+                if (col < prm.lc) dst[0] = acc[i][j][0];
+                if (col + 1 < prm.lc) dst[1] = acc[i][j][1];
             }
         }
     }
 }
 
-template <int NRA, bool MMA>
+// CFG 0: 16 warps x 128 registers
+template <int NRA>
+__global__ void __launch_bounds__(512, 1) separable_kernel_w16(const SepParams prm)
+{
+    separable_body<NRA, 0>(prm);
+}
+
+// CFG 1: 8 warps x 255 registers
+template <int NRA>
+__global__ void __launch_bounds__(256, 1) separable_kernel_w8(const SepParams prm)
+{
+    separable_body<NRA, 1>(prm);
+}
+
+template <int NRA, int CFG>
 inline int launch_separable_variant(const SepParams &prm, dim3 grid, cudaStream_t st)
 {
-    const size_t smem = MMA ? SEP_SMEM_BYTES_MMA : SEP_SMEM_BYTES;
-    GSB_CUDA(cudaFuncSetAttribute(separable_kernel<NRA, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    separable_kernel<NRA, MMA><<<grid, SEP_THREADS, smem, st>>>(prm);
+    using C = SepCfg<CFG>;
+    constexpr int threads = C::WARPS * 32;
+    if (CFG == 0) {
+        GSB_CUDA(cudaFuncSetAttribute(separable_kernel_w16<NRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SEP_SMEM_BYTES));
+        separable_kernel_w16<NRA><<<grid, threads, SEP_SMEM_BYTES, st>>>(prm);
+    } else {
+        GSB_CUDA(cudaFuncSetAttribute(separable_kernel_w8<NRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SEP_SMEM_BYTES));
+        separable_kernel_w8<NRA><<<grid, threads, SEP_SMEM_BYTES, st>>>(prm);
+    }
     return GSB_OK;
 }
 
-// variant: 0 = DMMA (default), 1 = DFMA register tile (ablation; dims 2 and 3 only)
+// variant: warp configuration CFG (0 = 16 consumer warps, 1 = 8 consumer warps + setmaxnreg)
 inline int launch_separable(const SepParams &prm, int64_t n_batch, int variant, cudaStream_t st)
 {
     dim3 grid((unsigned)(prm.lc_pad / SEP_TN), (unsigned)((prm.n_rows + SEP_TM - 1) / SEP_TM),
               (unsigned)(n_batch * prm.ncomp));
     if (grid.y > 65535u || grid.z > 65535u)
         return fail(GSB_ERR_ARGUMENT, "structured mesh too large for one launch (rows/128 or batch*ncomp > 65535)");
-    if (variant == 1 && prm.n_row_axes <= 2) {
-        if (prm.n_row_axes == 1) GSB_TRY((launch_separable_variant<1, false>(prm, grid, st)));
-        else GSB_TRY((launch_separable_variant<2, false>(prm, grid, st)));
-    } else {
-        switch (prm.n_row_axes) {
-        case 1: GSB_TRY((launch_separable_variant<1, true>(prm, grid, st))); break;
-        case 2: GSB_TRY((launch_separable_variant<2, true>(prm, grid, st))); break;
-        case 3: GSB_TRY((launch_separable_variant<3, true>(prm, grid, st))); break;
-        case 4: GSB_TRY((launch_separable_variant<4, true>(prm, grid, st))); break;
-        case 5: GSB_TRY((launch_separable_variant<5, true>(prm, grid, st))); break;
-        case 6: GSB_TRY((launch_separable_variant<6, true>(prm, grid, st))); break;
-        case 7: GSB_TRY((launch_separable_variant<7, true>(prm, grid, st))); break;
-        default:
-            return fail(GSB_ERR_ARGUMENT, "structured path needs 2 <= dim <= 8");
-        }
+#define GSB_SEP_CASE(N)                                                                        \
+    case N:                                                                                    \
+        if (variant == 1) GSB_TRY((launch_separable_variant<N, 1>(prm, grid, st)));            \
+        else GSB_TRY((launch_separable_variant<N, 0>(prm, grid, st)));                         \
+        break;
+    switch (prm.n_row_axes) {
+        GSB_SEP_CASE(1)
+        GSB_SEP_CASE(2)
+        GSB_SEP_CASE(3)
+        GSB_SEP_CASE(4)
+        GSB_SEP_CASE(5)
+        GSB_SEP_CASE(6)
+        GSB_SEP_CASE(7)
+    default:
+        return fail(GSB_ERR_ARGUMENT, "structured path needs 2 <= dim <= 8");
     }
+#undef GSB_SEP_CASE
     g_launches.fetch_add(1);
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;

@@ -1,0 +1,76 @@
+"""Multi-GPU path on real devices (NCCL): skipped unless the box has >= 2 GPUs."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tmpdir):
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+
+    import gstools_b200 as gsb
+    from conftest import synth_modes
+    from gstools_b200 import dist as gdist
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        cov, z1, z2 = synth_modes(3, 200, seed=5)
+        tc, t1, t2 = (torch.tensor(a, device=dev) for a in (cov, z1, z2))
+        axes = [torch.arange(float(n), device=dev, dtype=torch.float64) for n in (67, 64, 256)]
+        gsb.set_option("force_path", 2)
+        slab, (lo, hi) = gdist.summate_structured_sharded(tc, t1, t2, axes)
+        assert slab.device == dev and tuple(slab.shape) == (hi - lo, 64, 256)
+        full = gdist.gather_field(slab, 67)                      # NCCL all-gather
+        only0 = gdist.gather_field(slab, 67, dst=0)              # NCCL gather to rank 0
+        single = gsb.summate_structured(tc, t1, t2, axes)        # whole mesh on this GPU
+        assert torch.equal(full, single)
+        assert (only0 is None) == (rank != 0)
+        if rank == 0:
+            assert torch.equal(only0, single)
+        # flat points, host arrays in: every rank uses its own device (LOCAL_RANK)
+        gsb.set_option("force_path", 0)
+        pos = np.random.RandomState(1).uniform(0, 100, (3, 100001))
+        local, (lo, hi) = gdist.summate_sharded(cov, z1, z2, pos)
+        whole = gsb.summate(cov, z1, z2, pos)
+        assert np.array_equal(local, whole[lo:hi])
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_nccl_sharded_structured_and_gather(tmp_path):
+    import torch.multiprocessing as mp
+
+    world = min(_ngpu(), 4)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))

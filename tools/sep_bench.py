@@ -26,9 +26,9 @@ def timeit(fn, reps=5):
 
 peak = gsb.measure_fp64_peak(0, 0, 0.3)
 print(f"DFMA peak {peak/1e12:.3f} TFMA/s")
-for variant in (0, 1):
+for variant in ((0,) if os.environ.get('SEP_ONLY_DMMA') else (0, 1)):
     gsb.set_option("sep_variant", variant)
-    name = "DMMA" if variant == 0 else "DFMA"
+    name = "W16" if variant == 0 else "W8 "
     # correctness on a sample
     cfg = bc.config2(128)
     tc, t1, t2 = (torch.tensor(cfg[k], device=dev) for k in ("cov", "z1", "z2"))
