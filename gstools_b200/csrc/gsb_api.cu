@@ -19,14 +19,30 @@ std::atomic<int64_t> g_launches{0};
 static std::atomic<int64_t> g_opt_structured_min_tiles{64};
 static std::atomic<int64_t> g_opt_force_path{0};
 static std::atomic<int64_t> g_opt_host_chunk_points{1 << 22};
-static std::atomic<int64_t> g_opt_slab_tiles{148 * 6};
-static std::atomic<int64_t> g_opt_sep_variant{0};  // 0 = DMMA, 1 = DFMA register tile
+static std::atomic<int64_t> g_opt_scratch_mb{3072};  // A-operand scratch budget (two buffers)
+static std::atomic<int64_t> g_opt_min_chunks{4};     // so that A generation overlaps the contraction
+static std::atomic<int64_t> g_opt_chunk_growth_pct{140};
 static std::atomic<int64_t> g_cnt_direct{0}, g_cnt_separable{0};
 // optional device-side timing of the dominant kernels (bench.py roofline): events recorded on the
 // launch stream around every direct / separable launch while the option "time_kernels" is 1
 static std::atomic<int64_t> g_opt_time_kernels{0};
 static std::mutex g_time_mutex;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_time_events;
+
+// debugging aid (option "trace" = 1): start/end of every agen / contract kernel relative to the
+// start of the structured call, printed to stderr after a device synchronisation
+static std::atomic<int64_t> g_opt_trace{0};
+struct TraceRec { const char *name; cudaEvent_t e0, e1; };
+static std::vector<TraceRec> g_trace;
+struct TraceScope {
+    cudaEvent_t e0 = nullptr, e1 = nullptr; cudaStream_t st; const char *name;
+    TraceScope(const char *n, cudaStream_t s) : st(s), name(n)
+    {
+        if (!g_opt_trace.load()) return;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st);
+    }
+    ~TraceScope() { if (e0) { cudaEventRecord(e1, st); g_trace.push_back({name, e0, e1}); } }
+};
 
 struct KernelTimer {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -50,10 +66,16 @@ struct KernelTimer {
 // device bookkeeping
 // ---------------------------------------------------------------------------------------------
 struct DeviceState {
+    static constexpr int N_STREAMS = 4;        // 0: host-path main, 1: copies, 2/3: contraction
+    static constexpr int N_EVENTS = 5;
+    static constexpr int N_CHUNK_EVENTS = 8;
     bool ready = false;
     int sm_count = 0;
-    cudaStream_t streams[2] = {nullptr, nullptr};  // library-owned streams for host-memory calls
-    cudaEvent_t events[2] = {nullptr, nullptr};
+    cudaStream_t streams[N_STREAMS] = {};
+    cudaEvent_t events[N_EVENTS] = {};
+    cudaEvent_t chunk_events[N_CHUNK_EVENTS] = {};      // A generation of chunk c done
+    cudaEvent_t contract_events[N_CHUNK_EVENTS] = {};   // contraction of chunk c done
+    std::mutex call_mutex;                     // one structured call at a time per device
 };
 static std::mutex g_dev_mutex;
 static DeviceState g_dev[64];
@@ -86,9 +108,18 @@ static int ensure_device(int device, DeviceState **out)
             return fail(GSB_ERR_NO_DEVICE, std::string("device '") + prop.name +
                                                "' is not sm_100-class; this library is built for sm_100a only");
         d.sm_count = prop.multiProcessorCount;
-        for (int i = 0; i < 2; ++i) {
-            GSB_CUDA(cudaStreamCreateWithFlags(&d.streams[i], cudaStreamNonBlocking));
+        // Stream 2 runs the A generation.  It gets the highest priority: the block scheduler
+        // finishes dispatching one grid before it starts the next of the same priority, so without
+        // this the A generation of chunk c+1 would only start in the tail of contraction c.
+        int prio_lo = 0, prio_hi = 0;
+        GSB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        for (int i = 0; i < DeviceState::N_STREAMS; ++i)
+            GSB_CUDA(cudaStreamCreateWithPriority(&d.streams[i], cudaStreamNonBlocking, i == 2 ? prio_hi : prio_lo));
+        for (int i = 0; i < DeviceState::N_EVENTS; ++i)
             GSB_CUDA(cudaEventCreateWithFlags(&d.events[i], cudaEventDisableTiming));
+        for (int i = 0; i < DeviceState::N_CHUNK_EVENTS; ++i) {
+            GSB_CUDA(cudaEventCreateWithFlags(&d.chunk_events[i], cudaEventDisableTiming));
+            GSB_CUDA(cudaEventCreateWithFlags(&d.contract_events[i], cudaEventDisableTiming));
         }
         // keep freed scratch in the stream-ordered pool instead of returning it to the driver
         cudaMemPool_t pool;
@@ -283,20 +314,24 @@ struct MeshInfo {
     bool identity;
 };
 
-// everything on device: d_cov (B,dim,N), d_z1/d_z2 (B,N), d_axes, d_out (B,ncomp,n)
-// `sync_copy_out`: when non-null, slabs are copied to this host buffer as they finish.
+// everything on device: d_cov (B,dim,N), d_z1/d_z2 (B,N), d_axes, d_out (B,ncomp,n).
+// `h_out`: when non-null, finished chunks are copied to this host buffer as they complete.
+// `st` is the caller's stream: all work is ordered after what `st` holds on entry, and `st` waits
+// for all of it before this function returns (the library's two contraction streams are used
+// in between so that the A generation of one chunk overlaps the contraction of the other).
 static int structured_on_device(const double *d_cov, const double *d_z1, const double *d_z2,
                                 const double *d_axes, const MeshInfo &mesh, int64_t n_modes,
                                 int64_t n_batch, bool vec, double *d_out, double *h_out,
-                                const DeviceState &dev, cudaStream_t st, cudaStream_t copy_st,
-                                cudaEvent_t ev)
+                                DeviceState &dev, cudaStream_t st)
 {
     const int dim = mesh.dim;
     const int ncomp = vec ? dim : 1;
     Scratch scr(st);
     const int64_t force = g_opt_force_path.load();
-    const int64_t tiles = ((mesh.n_rows + SEP_TM - 1) / SEP_TM) * ((mesh.len[dim - 1] + SEP_TN - 1) / SEP_TN) *
-                          n_batch * ncomp;
+    const int64_t lc = mesh.len[dim - 1];
+    const int64_t n_row_tiles_total = (mesh.n_rows + SEP_TM - 1) / SEP_TM;
+    const int n_col_tiles = (int)((lc + SEP_TN - 1) / SEP_TN);
+    const int64_t tiles = n_row_tiles_total * n_col_tiles * n_batch * ncomp;
     bool separable = dim >= 2 && n_modes > 0 && tiles >= g_opt_structured_min_tiles.load();
     if (force == 1) separable = false;
     if (force == 2 && dim >= 2 && n_modes > 0) separable = true;
@@ -334,11 +369,10 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         return GSB_OK;
     }
 
-    // ---- separable path: build the per-axis tables, then the tiled contraction ----
+    // ---- separable path: tables -> (A generation || contraction) per chunk ----
     const int nra = dim - 1;
     const int n_modes_pad = (int)((n_modes + SEP_KC - 1) / SEP_KC * SEP_KC);
-    const int64_t lc = mesh.len[dim - 1];
-    const int64_t lc_pad = (lc + SEP_TN - 1) / SEP_TN * SEP_TN;
+    const int n_stages = n_modes_pad / SEP_KC;
     TableParams tp;
     std::memset(&tp, 0, sizeof tp);
     tp.cov = d_cov;
@@ -349,9 +383,9 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     tp.dim = dim;
     tp.n_modes = n_modes;
     tp.n_modes_pad = n_modes_pad;
-    tp.vec = vec ? 1 : 0;
-    tp.lc_pad = lc_pad;
-    int64_t max_width = lc_pad;
+    tp.ncomp = ncomp;
+    tp.n_col_tiles = n_col_tiles;
+    int64_t max_width = (int64_t)n_col_tiles * SEP_TN;
     for (int t = 0; t < dim; ++t) {
         tp.axis_off[t] = mesh.off[t];
         tp.axis_len[t] = mesh.len[t];
@@ -361,79 +395,155 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
             max_width = std::max(max_width, mesh.len[t]);
         }
     }
-    tp.b_bstride = lc_pad * n_modes_pad;
-    GSB_TRY(scr.alloc(&tp.bc, (size_t)n_batch * tp.b_bstride));
-    GSB_TRY(scr.alloc(&tp.bs, (size_t)n_batch * tp.b_bstride));
-    tp.proj_bstride = (int64_t)dim * n_modes_pad;
-    if (vec) GSB_TRY(scr.alloc(&tp.proj, (size_t)n_batch * tp.proj_bstride));
+    GSB_TRY(scr.alloc(&tp.btile, (size_t)n_batch * ncomp * n_col_tiles * n_stages * SEP_B_TILE));
     {
+        if (n_batch > 65535) return fail(GSB_ERR_ARGUMENT, "n_batch too large");
         const int64_t work = max_width * n_modes_pad;
         dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 4096), (unsigned)dim, (unsigned)n_batch);
-        if (n_batch > 65535) return fail(GSB_ERR_ARGUMENT, "n_batch too large");
         build_tables_kernel<<<grid, 256, 0, st>>>(tp);
         g_launches.fetch_add(1);
         GSB_CUDA(cudaGetLastError());
     }
 
-    SepParams sp;
-    std::memset(&sp, 0, sizeof sp);
-    sp.n_row_axes = nra;
+    // Chunk plan.  A unit is (field, row tile); its A operand takes `unit_bytes`.  Chunks alternate
+    // between two scratch buffers of `cap` units.  The first chunk is small (its A generation is
+    // the only one that is not hidden behind a contraction) and chunks then grow by <= 1.4x, the
+    // ratio at which the co-resident A generation of chunk c+1 still finishes within contraction c.
+    // Chunk sizes are multiples of `q` units = a whole number of waves over the SMs.
+    const size_t unit_bytes = (size_t)n_stages * SEP_A_TILE * sizeof(double);
+    const int64_t total_units = n_batch * n_row_tiles_total;
+    const int64_t tiles_per_unit = (int64_t)n_col_tiles * ncomp;
+    int64_t q = dev.sm_count;
+    {
+        int64_t a2 = tiles_per_unit, b2 = dev.sm_count;
+        while (b2) { const int64_t tmp = a2 % b2; a2 = b2; b2 = tmp; }
+        q = dev.sm_count / a2;     // units per whole wave
+    }
+    int64_t cap = std::max<int64_t>(1, (int64_t)((size_t)g_opt_scratch_mb.load() * (1u << 20) / 2 / unit_bytes));
+    cap = std::min<int64_t>(cap, total_units);
+    if (cap >= 2 * q) cap -= cap % q;
+    const bool whole_fields = n_row_tiles_total <= cap && n_batch > 1;
+    struct Chunk { int64_t f0, nf, r0, nrt; };
+    std::vector<Chunk> chunks;          // a range of row tiles of one field, or whole fields
+    int64_t biggest = 0;
+    {
+        const int64_t min_chunks = std::max<int64_t>(1, g_opt_min_chunks.load());
+        int64_t n = std::max<int64_t>(q, total_units / (4 * min_chunks) / q * q);
+        const double growth = (double)g_opt_chunk_growth_pct.load() / 100.0;
+        int64_t f = 0, r = 0;
+        while (f < n_batch) {
+            Chunk ch;
+            const int64_t want = std::min(n, cap);
+            if (whole_fields) {
+                ch = {f, std::min<int64_t>(std::max<int64_t>(1, want / n_row_tiles_total), n_batch - f), 0,
+                      n_row_tiles_total};
+                f += ch.nf;
+            } else {
+                ch = {f, 1, r, std::min<int64_t>(want, n_row_tiles_total - r)};
+                r += ch.nrt;
+                if (r >= n_row_tiles_total) { r = 0; ++f; }
+            }
+            chunks.push_back(ch);
+            biggest = std::max(biggest, ch.nf * ch.nrt);
+            n = std::max<int64_t>(n, (int64_t)(growth * (double)n) / q * q);
+        }
+    }
+    double *abuf[2] = {nullptr, nullptr};
+    const int nbuf = chunks.size() > 1 ? 2 : 1;
+    for (int i = 0; i < nbuf; ++i) GSB_TRY(scr.alloc(&abuf[i], (size_t)biggest * n_stages * SEP_A_TILE));
+
+    // Software pipeline over chunks: the contractions run in order on the caller's stream `st`;
+    // the A generation of chunk c+1 runs on a helper stream while chunk c is being contracted
+    // (it only needs buffer (c+1)&1, i.e. the contraction of chunk c-1, to be finished).
+    cudaStream_t hs = dev.streams[2];
+    cudaStream_t copy_st = dev.streams[1];
+    constexpr int NE = DeviceState::N_CHUNK_EVENTS;
+    GSB_CUDA(cudaEventRecord(dev.events[1], st));            // tables (and scratch) are ready
+    GSB_CUDA(cudaStreamWaitEvent(hs, dev.events[1], 0));
+
+    AgenParams ap;
+    std::memset(&ap, 0, sizeof ap);
+    ap.n_row_axes = nra;
     for (int t = 0; t < nra; ++t) {
-        sp.erow[t] = tp.erow[t];
-        sp.row_len[t] = mesh.len[t];
-        sp.row_stride[t] = mesh.len[t];
-        sp.erow_bstride[t] = tp.erow_bstride[t];
+        ap.erow[t] = tp.erow[t];
+        ap.erow_bstride[t] = tp.erow_bstride[t];
+        ap.row_len[t] = mesh.len[t];
     }
-    sp.bc = tp.bc;
-    sp.bs = tp.bs;
-    sp.lc = lc;
-    sp.lc_pad = lc_pad;
-    sp.n_modes_pad = n_modes_pad;
-    sp.proj = vec ? tp.proj : nullptr;
-    sp.ncomp = ncomp;
-    sp.b_bstride = tp.b_bstride;
-    sp.proj_bstride = tp.proj_bstride;
-    sp.out_fstride = mesh.n;
+    ap.n_rows = mesh.n_rows;
+    ap.n_modes_pad = n_modes_pad;
+    ContractParams cp;
+    std::memset(&cp, 0, sizeof cp);
+    cp.btile = tp.btile;
+    cp.n_col_tiles = n_col_tiles;
+    cp.n_stages = n_stages;
+    cp.ncomp = ncomp;
+    cp.n_rows = mesh.n_rows;
+    cp.lc = lc;
+    cp.out = d_out;
+    cp.out_fstride = mesh.n;
 
-    // Slabs along axis 0 keep each launch's grid.y in range and let the D2H copy of slab s
-    // overlap the contraction of slab s+1 when the caller's buffers live on the host.
-    const int64_t rows_per_x = mesh.n_rows / mesh.len[0];
-    const int64_t col_tiles = lc_pad / SEP_TN;
-    int64_t slab_x = mesh.len[0];
-    const bool single_field = (n_batch * ncomp == 1);
-    if (h_out && single_field) {
-        // aim for ~slab_tiles tiles per launch (a whole number of waves over the SMs)
-        const int64_t tiles_per_x = ((rows_per_x + SEP_TM - 1) / SEP_TM) * col_tiles;
-        slab_x = std::max<int64_t>(1, g_opt_slab_tiles.load() / std::max<int64_t>(1, tiles_per_x));
-    }
-    // grid.y limit
-    const int64_t max_rows = 65535LL * SEP_TM;
-    if (rows_per_x > max_rows) return fail(GSB_ERR_ARGUMENT, "structured mesh: prod(len[1:-1]) too large");
-    slab_x = std::min(slab_x, std::max<int64_t>(1, max_rows / rows_per_x));
-    slab_x = std::min(slab_x, mesh.len[0]);
-
-    for (int64_t x0 = 0; x0 < mesh.len[0]; x0 += slab_x) {
-        const int64_t nx = std::min(slab_x, mesh.len[0] - x0);
-        SepParams s2 = sp;
-        s2.erow[0] = sp.erow[0] + x0;
-        s2.row_len[0] = nx;
-        s2.n_rows = nx * rows_per_x;
-        s2.out = d_out + x0 * rows_per_x * lc;
+    int64_t c = 0;
+    for (const Chunk &ch : chunks) {
         {
-            KernelTimer timer(st);
-            GSB_TRY(launch_separable(s2, n_batch, (int)g_opt_sep_variant.load(), st));
-        }
-        if (h_out && single_field) {
-            GSB_CUDA(cudaEventRecord(ev, st));
-            GSB_CUDA(cudaStreamWaitEvent(copy_st, ev, 0));
-            GSB_CUDA(cudaMemcpyAsync(h_out + x0 * rows_per_x * lc, s2.out,
-                                     sizeof(double) * nx * rows_per_x * lc, cudaMemcpyDeviceToHost,
-                                     copy_st));
+            const int64_t f0 = ch.f0, nf = ch.nf, r0 = ch.r0, nrt = ch.nrt;
+            const int bi = (int)(c % nbuf);
+            // A generation (helper stream); buffer bi was last read by the contraction of chunk c-nbuf
+            if (c >= nbuf) GSB_CUDA(cudaStreamWaitEvent(hs, dev.contract_events[(c - nbuf) % NE], 0));
+            ap.row_begin = r0 * SEP_TM;
+            ap.n_row_tiles = (int)nrt;
+            ap.batch0 = f0;
+            ap.atile = abuf[bi];
+            {
+                TraceScope ts("agen", hs);
+                GSB_TRY(launch_agen(ap, nf, dev.sm_count, hs));
+            }
+            GSB_CUDA(cudaEventRecord(dev.chunk_events[c % NE], hs));
+            // contraction (caller's stream)
+            GSB_CUDA(cudaStreamWaitEvent(st, dev.chunk_events[c % NE], 0));
+            cp.atile = abuf[bi];
+            cp.n_row_tiles = (int)nrt;
+            cp.batch0 = f0;
+            cp.row_begin = r0 * SEP_TM;
+            {
+                KernelTimer timer(st);
+                TraceScope ts("contract", st);
+                GSB_TRY(launch_contract(cp, nf, dev.sm_count, st));
+            }
+            GSB_CUDA(cudaEventRecord(dev.contract_events[c % NE], st));
+            if (h_out) {
+                // copy the finished chunk to the host while the next one is being computed
+                GSB_CUDA(cudaStreamWaitEvent(copy_st, dev.contract_events[c % NE], 0));
+                const int64_t row_lo = r0 * SEP_TM;
+                const int64_t row_hi = std::min<int64_t>(mesh.n_rows, (r0 + nrt) * SEP_TM);
+                if (whole_fields) {
+                    const size_t off = (size_t)f0 * ncomp * mesh.n;
+                    GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * nf * ncomp * mesh.n,
+                                             cudaMemcpyDeviceToHost, copy_st));
+                } else {
+                    for (int comp = 0; comp < ncomp; ++comp) {
+                        const size_t off = ((size_t)f0 * ncomp + comp) * mesh.n + (size_t)row_lo * lc;
+                        GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * (row_hi - row_lo) * lc,
+                                                 cudaMemcpyDeviceToHost, copy_st));
+                    }
+                }
+            }
+            ++c;
         }
     }
-    if (h_out && !single_field) {
-        GSB_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * n_batch * ncomp * mesh.n,
-                                 cudaMemcpyDeviceToHost, st));
+    if (h_out) {
+        GSB_CUDA(cudaEventRecord(dev.events[4], copy_st));
+        GSB_CUDA(cudaStreamWaitEvent(st, dev.events[4], 0));
+    }
+    if (g_opt_trace.load() && !g_trace.empty()) {
+        cudaDeviceSynchronize();
+        for (auto &r : g_trace) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, g_trace[0].e0, r.e0);
+            cudaEventElapsedTime(&b, g_trace[0].e0, r.e1);
+            fprintf(stderr, "[gsb trace] %-9s %8.3f -> %8.3f ms\n", r.name, a, b);
+        }
+        for (auto &r : g_trace) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        g_trace.clear();
     }
     g_cnt_separable.fetch_add(1);
     return GSB_OK;
@@ -497,9 +607,10 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
 
     if (mem == GSB_MEM_DEVICE) {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        return structured_on_device(cov, z1, z2, axes, mesh, n_modes, n_batch, vec, out, nullptr, *dev,
-                                    st, nullptr, nullptr);
+        std::lock_guard<std::mutex> lock(dev->call_mutex);
+        return structured_on_device(cov, z1, z2, axes, mesh, n_modes, n_batch, vec, out, nullptr, *dev, st);
     }
+    std::lock_guard<std::mutex> lock(dev->call_mutex);
     cudaStream_t s0 = dev->streams[0];
     Scratch scr(s0);
     double *d_cov, *d_z1, *d_z2, *d_axes, *d_out;
@@ -514,10 +625,8 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
         GSB_CUDA(cudaMemcpyAsync(d_z2, z2, sizeof(double) * n_batch * n_modes, cudaMemcpyHostToDevice, s0));
     }
     GSB_CUDA(cudaMemcpyAsync(d_axes, axes, sizeof(double) * mesh.total_axes, cudaMemcpyHostToDevice, s0));
-    GSB_TRY(structured_on_device(d_cov, d_z1, d_z2, d_axes, mesh, n_modes, n_batch, vec, d_out, out, *dev,
-                                 s0, dev->streams[1], dev->events[0]));
+    GSB_TRY(structured_on_device(d_cov, d_z1, d_z2, d_axes, mesh, n_modes, n_batch, vec, d_out, out, *dev, s0));
     GSB_CUDA(cudaStreamSynchronize(s0));
-    GSB_CUDA(cudaStreamSynchronize(dev->streams[1]));
     return GSB_OK;
 }
 
@@ -654,8 +763,10 @@ int gsb_set_option(const char *name, int64_t value)
     if (n == "structured_min_tiles") g_opt_structured_min_tiles = value;
     else if (n == "force_path") g_opt_force_path = value;
     else if (n == "host_chunk_points") g_opt_host_chunk_points = value;
-    else if (n == "slab_tiles") g_opt_slab_tiles = value;
-    else if (n == "sep_variant") g_opt_sep_variant = value;
+    else if (n == "scratch_mb") g_opt_scratch_mb = std::max<int64_t>(value, 1);
+    else if (n == "min_chunks") g_opt_min_chunks = std::max<int64_t>(value, 1);
+    else if (n == "trace") g_opt_trace = value;
+    else if (n == "chunk_growth_pct") g_opt_chunk_growth_pct = std::max<int64_t>(value, 100);
     else if (n == "time_kernels") g_opt_time_kernels = value;
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);
     return GSB_OK;

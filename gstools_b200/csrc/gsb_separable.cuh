@@ -12,22 +12,34 @@
 // ~D+17 of the direct kernel: all sin/cos work moves into per-axis tables of size (len_t x N)
 // built once per call with full-accuracy sincos.
 //
-// Kernel structure (one CTA per 128x128 output tile, 1 CTA/SM, warp specialised):
-//   * warps 8..11 = TMA warpgroup: one elected thread issues, per pipeline stage of KC modes, the
-//     cp.async.bulk copies (TMA unit) of the Cz/Sz table slices into shared memory, signalled on
-//     the stage's "full" mbarrier; the warpgroup gives its registers to the consumers
-//     (setmaxnreg.dec / .inc).
-//   * the A operand is GENERATED on the fly by the consumer threads, one stage ahead: one complex
-//     product per (row, mode) from the L2-resident row-axis tables, written straight to shared
-//     memory.  The 4.2 GB A matrix of config 2 never exists in HBM.
-//   * warps 0..7 = consumers: each warp owns a 32x64 block of the tile as 4x8 DMMA.8x8x4
-//     accumulator tiles (64 fp64 accumulators per thread); per 2 modes it fetches 4 + 8 fragment
-//     doubles with conflict-free LDS.64 and issues 32 DMMA; modes are accumulated in ascending
-//     order (deterministic, no atomics).  They release the stage on its "empty" mbarrier.
-//   * epilogue: registers -> global, 16-byte stores.
-// The incompressible variant (generator.py:479-495) multiplies A by the projector p_t(k_j) and
-// runs one CTA column per vector component (2 d DFMA per pair).
+// Three kernels:
+//   1. build_tables_kernel   per-axis phase tables; the last-axis table is written PRE-TILED in the
+//                            exact shared-memory layout of a pipeline stage (one bulk copy each).
+//                            For the incompressible variant (generator.py:479-495) the projector
+//                            p_t(k_j) is folded into the last-axis table of component t.
+//   2. agen_kernel           A operand: one complex product per (row, mode), written pre-tiled
+//                            (memory bound, ~5 % of the contraction time, runs on a helper stream
+//                            concurrently with the contraction of the previous row chunk).
+//   3. contract_kernel       one CTA of 8 warps per 128x128 output tile, 1 CTA per SM:
+//        TMA                  two cp.async.bulk copies per stage of KC modes (a 20 KB A tile and a
+//                             16.5 KB B tile) completing on the stage's "full" mbarrier, issued
+//                             three stages ahead by lane 0 of a warp that rotates with the stage
+//                             (it first checks the slot's "empty" mbarrier);
+//        every warp           32x64 warp tile = 4x8 DMMA.8x8x4 accumulator tiles (64 fp64
+//                             accumulators per thread); per 2 modes 4 + 8 fragment doubles by
+//                             conflict-free LDS.64 and 32 DMMA; modes in ascending order
+//                             (deterministic, no atomics); registers -> global in the epilogue.
+//      An earlier single-kernel version generated A inside the contraction kernel; ncu and the
+//      bisect microbenchmark (profiles/) showed the FP64 products, their loads and stores costing
+//      ~12 % of the DMMA issue slots however they were placed, while this split reaches 97 %.
+//
+// Why DMMA and not DFMA: B200 runs DMMA.8x8x4 at the same FMA rate as DFMA (measured 18.5 vs
+// 18.4 TFMA/s), but one instruction carries 256 FMAs with 8 register reads.  A register-tiled DFMA
+// version of the contraction topped out at 73 % of the FP64 peak: 3 x 64-bit operands per DFMA
+// exceed what the register file sustains once the operand-reuse cache is lost between warps.
 #pragma once
+
+#include <algorithm>
 
 #include "gsb_common.cuh"
 
@@ -39,46 +51,33 @@ constexpr int SEP_TN = 128;      // columns per CTA tile
 #define GSB_SEP_KC 8
 #endif
 #ifndef GSB_SEP_STAGES
-#define GSB_SEP_STAGES 5
+#define GSB_SEP_STAGES 4
 #endif
-#ifndef GSB_SEP_LOOKAHEAD
-#define GSB_SEP_LOOKAHEAD 2
-#endif
-constexpr int SEP_KC = GSB_SEP_KC;        // modes per pipeline stage (multiple of 4)
+constexpr int SEP_KC = GSB_SEP_KC;        // modes per pipeline stage (multiple of 2)
 constexpr int SEP_STAGES = GSB_SEP_STAGES;
-constexpr int SEP_LOOKAHEAD = GSB_SEP_LOOKAHEAD;   // A operand is generated this many stages ahead (needs STAGES >= 2*LOOKAHEAD)
-static_assert(SEP_KC % 4 == 0 && SEP_STAGES >= 2 * SEP_LOOKAHEAD + 1, "pipeline shape");
+static_assert(SEP_KC % 2 == 0 && SEP_STAGES >= 3, "pipeline shape");
+static_assert((8 & (8 - 1)) == 0, "warp rotation uses a power-of-two mask");
 constexpr int SEP_MAX_ROW_AXES = GSB_MAX_DIM - 1;
+constexpr int SEP_WARPS = 8;
+constexpr int SEP_THREADS = SEP_WARPS * 32;
 
-
-struct SepParams {
-    // row-axis tables: E_t[j * len_t + i] = exp(i k'_{t,j} a_t[i]) as (cos, sin); t = 0 is
-    // pre-multiplied by (z1_j - i z2_j).  Modes j >= n_modes (padding) are zero.
-    const double2 *erow[SEP_MAX_ROW_AXES];
-    int64_t row_len[SEP_MAX_ROW_AXES];     // extent of each row axis in THIS launch (slab)
-    int64_t row_stride[SEP_MAX_ROW_AXES];  // full table width (entries per mode) of each row axis
-    int n_row_axes;
-    int64_t n_rows;        // prod(row_len)
-    // last-axis tables, planes of n_modes_pad x lc_pad doubles
-    const double *bc;
-    const double *bs;
-    int64_t lc;            // length of the last axis
-    int64_t lc_pad;        // padded to a multiple of SEP_TN
-    int n_modes_pad;       // multiple of SEP_KC
-    // incompressible projector p_t[j], (ncomp, n_modes_pad); nullptr for the scalar sum
-    const double *proj;
-    int ncomp;             // 1 (scalar) or dim (vector)
-    // per-batch strides (in elements) of the tables above; batch index = blockIdx.z / ncomp
-    int64_t erow_bstride[SEP_MAX_ROW_AXES];
-    int64_t b_bstride;
-    int64_t proj_bstride;
-    double *out;           // field f = batch*ncomp + comp starts at out + f*out_fstride; (n_rows, lc) inside
-    int64_t out_fstride;
-};
+// Stage layout in shared memory == tile layout in global memory (doubles):
+//   A tile [SEP_TM rows][SEP_AST]   k = 2*kc + part (part 0: Re A, part 1: -Im A); the row stride
+//                                   2*KC+4 makes the 8x4 fragment loads (LDS.64) hit 32 distinct
+//                                   banks per half warp
+//   B tile [2*KC][SEP_BST]          row 2*kc + part (part 0: p*cos, part 1: p*sin), stride 132
+constexpr int SEP_AST = 2 * SEP_KC + 4;
+constexpr int SEP_BST = SEP_TN + 4;
+constexpr int SEP_A_TILE = SEP_TM * SEP_AST;          // doubles
+constexpr int SEP_B_TILE = 2 * SEP_KC * SEP_BST;      // doubles
+constexpr int SEP_STAGE_DOUBLES = SEP_A_TILE + SEP_B_TILE;
+static_assert((SEP_A_TILE * 8) % 16 == 0 && (SEP_B_TILE * 8) % 16 == 0, "bulk copy granularity");
+static_assert((SEP_A_TILE / 2) % SEP_TM == 0, "agen copy-out loop");
+constexpr size_t SEP_SMEM_BYTES =
+    (size_t)SEP_STAGES * SEP_STAGE_DOUBLES * sizeof(double) + 2 * SEP_STAGES * sizeof(uint64_t) + 128;
 
 // ---------------------------------------------------------------------------------------------
-// table builder: one thread per (axis entry, mode).  Full-accuracy sincos (libdevice), cost
-// O((sum_t len_t) N) -- negligible against the O(n N) contraction.
+// 1. table builder.  Full-accuracy sincos (libdevice), cost O((sum_t len_t) N): negligible.
 // ---------------------------------------------------------------------------------------------
 struct TableParams {
     const double *cov;     // (n_batch, dim, n_modes)
@@ -90,16 +89,16 @@ struct TableParams {
     double matrix[GSB_MAX_DIM * GSB_MAX_DIM];  // row-major (dim x dim) isometrisation matrix
     int dim;
     int64_t n_modes;
-    int n_modes_pad;
-    int vec;               // build the projector table
+    int n_modes_pad;       // multiple of SEP_KC; padded modes are zero
+    int ncomp;             // 1 scalar, dim for the incompressible field
+    // row-axis tables: erow[t][b][j * len_t + i] = exp(i k'_{t,j} a_t[i]) as (cos, sin); t = 0 is
+    // pre-multiplied by (z1_j - i z2_j)
     double2 *erow[SEP_MAX_ROW_AXES];
     int64_t erow_bstride[SEP_MAX_ROW_AXES];
-    double *bc;
-    double *bs;
-    int64_t lc_pad;
-    int64_t b_bstride;
-    double *proj;
-    int64_t proj_bstride;
+    // last-axis table, pre-tiled: btile[((b*ncomp + comp)*n_col_tiles + ct)*n_stages + s] is one
+    // SEP_B_TILE block
+    double *btile;
+    int n_col_tiles;
 };
 
 __global__ void build_tables_kernel(const TableParams tp)
@@ -108,8 +107,9 @@ __global__ void build_tables_kernel(const TableParams tp)
     const int64_t b = blockIdx.z;             // batch entry
     const int64_t len = tp.axis_len[t];
     const bool last = (t == tp.dim - 1);
-    const int64_t width = last ? tp.lc_pad : len;
+    const int64_t width = last ? (int64_t)tp.n_col_tiles * SEP_TN : len;
     const int64_t total = width * tp.n_modes_pad;
+    const int n_stages = tp.n_modes_pad / SEP_KC;
     const double *cov = tp.cov + b * tp.dim * tp.n_modes;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
@@ -130,71 +130,123 @@ __global__ void build_tables_kernel(const TableParams tp)
                 s = im;
             }
         }
-        if (last) {
-            tp.bc[b * tp.b_bstride + j * tp.lc_pad + i] = c;
-            tp.bs[b * tp.b_bstride + j * tp.lc_pad + i] = s;
-        } else {
+        if (!last) {
             tp.erow[t][b * tp.erow_bstride[t] + j * len + i] = make_double2(c, s);
+            continue;
         }
-    }
-    // projector table (vector field): p_c[j] = delta_c0 - k_c k_0 / |k|^2 on the ORIGINAL k
-    if (tp.vec && t == 0) {
-        for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < tp.n_modes_pad;
-             j += (int64_t)gridDim.x * blockDim.x) {
-            double k2 = 0.0;
-            if (j < tp.n_modes)
-                for (int s2 = 0; s2 < tp.dim; ++s2) {
-                    const double k = cov[(int64_t)s2 * tp.n_modes + j];
-                    k2 += k * k;
-                }
-            for (int c2 = 0; c2 < tp.dim; ++c2) {
-                double p = 0.0;
-                if (j < tp.n_modes) {
-                    const double e = (c2 == 0) ? 1.0 : 0.0;
-                    p = e - cov[(int64_t)c2 * tp.n_modes + j] * cov[j] / k2;
-                }
-                tp.proj[b * tp.proj_bstride + (int64_t)c2 * tp.n_modes_pad + j] = p;
+        const int ct = (int)(i / SEP_TN), col = (int)(i % SEP_TN);
+        const int st = (int)(j / SEP_KC), kc = (int)(j % SEP_KC);
+        double k2 = 0.0, k0 = 0.0;
+        if (tp.ncomp > 1 && j < tp.n_modes) {
+            for (int s2 = 0; s2 < tp.dim; ++s2) {
+                const double k = cov[(int64_t)s2 * tp.n_modes + j];
+                k2 += k * k;
             }
+            k0 = cov[j];
+        }
+        for (int comp = 0; comp < tp.ncomp; ++comp) {
+            double p = 1.0;
+            if (tp.ncomp > 1) {
+                // incompressible projector on the ORIGINAL wave vector (generator.py:479-495)
+                p = 0.0;
+                if (j < tp.n_modes) {
+                    const double e = (comp == 0) ? 1.0 : 0.0;
+                    p = e - cov[(int64_t)comp * tp.n_modes + j] * k0 / k2;
+                }
+            }
+            double *tile = tp.btile +
+                           ((((b * tp.ncomp + comp) * tp.n_col_tiles + ct) * n_stages + st) * (int64_t)SEP_B_TILE);
+            tile[(2 * kc) * SEP_BST + col] = p * c;
+            tile[(2 * kc + 1) * SEP_BST + col] = p * s;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// the contraction kernel
-//
-// The consumers run DMMA.8x8x4 (mma.sync m8n8k4 f64) on the tensor-core FP64 path.  B200 executes
-// it at the same FMA rate as DFMA (measured 18.5 vs 18.4 TFMA/s), but one instruction carries 256
-// FMAs with 8 register reads, so neither the register file (3 x 64-bit operands per DFMA exceed
-// the 2 reads/clk it sustains once the operand-reuse cache is lost between warps: a register-tiled
-// DFMA version of this kernel measured 73 % of the FP64 peak, profiles/) nor shared-memory
-// fragment traffic limits the pipe.
-// Shared-memory layout per stage:
-//   A[row][SEP_AST]           k = 2*kc + part (part 0: p*Re A, part 1: -p*Im A); rows padded to
-//                             2*KC+4 doubles so the 8x4 fragment loads (LDS.64) hit 32 distinct
-//                             banks per half warp;
-//   B[2*kc + part][SEP_BST]   part 0: cos, part 1: sin; rows padded to 132 doubles likewise.
-// Two warp configurations (template CFG), no warp specialisation (every warp contracts, every
-// thread generates part of A, thread 0 issues the TMA copies):
-//   CFG 0: 16 warps (4 per SM sub-partition), warp tile 32x32 = 4x4 DMMA tiles, 32 accumulators
-//          per thread, 512 threads x 128 registers;
-//   CFG 1:  8 warps (2 per sub-partition), warp tile 32x64 = 4x8 DMMA tiles, 64 accumulators per
-//          thread, 256 threads x 255 registers.
+// 2. A operand generator: atile[((f*n_row_tiles + rt)*n_stages + s)] is one SEP_A_TILE block holding
+//    rows rt*128 .. rt*128+127 of field-batch entry f for modes s*KC .. s*KC+KC-1.
 // ---------------------------------------------------------------------------------------------
-constexpr int SEP_AST = 2 * SEP_KC + 4;   // A row stride (doubles)
-constexpr int SEP_BST = SEP_TN + 4;       // B row stride (doubles)
-constexpr int SEP_STAGE_DOUBLES = SEP_TM * SEP_AST + 2 * SEP_KC * SEP_BST;
-constexpr size_t SEP_SMEM_BYTES =
-    (size_t)SEP_STAGES * SEP_STAGE_DOUBLES * sizeof(double) + SEP_STAGES * sizeof(uint64_t) + 128;
-
-template <int CFG>
-struct SepCfg;
-template <>
-struct SepCfg<0> {
-    static constexpr int WARPS = 16, WCOLS = 4, RT = 4, CT = 4;   // 512 threads x 128 registers
+struct AgenParams {
+    const double2 *erow[SEP_MAX_ROW_AXES];
+    int64_t erow_bstride[SEP_MAX_ROW_AXES];
+    int64_t row_len[SEP_MAX_ROW_AXES];   // full extent of every row axis
+    int n_row_axes;
+    int64_t n_rows;        // prod(row_len)
+    int64_t row_begin;     // first row of this chunk (multiple of SEP_TM)
+    int n_row_tiles;       // row tiles in this chunk
+    int n_modes_pad;
+    int64_t batch0;        // first batch entry of this chunk
+    double *atile;
 };
-template <>
-struct SepCfg<1> {
-    static constexpr int WARPS = 8, WCOLS = 2, RT = 4, CT = 8;    // 256 threads x 255 registers
+
+template <int NRA>
+__global__ void __launch_bounds__(SEP_TM) agen_kernel(const AgenParams ap)
+{
+    __shared__ __align__(16) double tile[SEP_A_TILE];   // staged so the global stores are coalesced
+    const int rt = blockIdx.x;
+    const int64_t f = blockIdx.z;
+    const int n_stages = ap.n_modes_pad / SEP_KC;
+    const int row = threadIdx.x;
+    int64_t r = ap.row_begin + (int64_t)rt * SEP_TM + row;
+    if (r >= ap.n_rows) r = ap.n_rows - 1;   // clamp; those rows are never stored by the contraction
+    const double2 *ep[NRA];
+#pragma unroll
+    for (int t = NRA - 1; t >= 0; --t) {
+        const int64_t it = r % ap.row_len[t];
+        r /= ap.row_len[t];
+        ep[t] = ap.erow[t] + (ap.batch0 + f) * ap.erow_bstride[t] + it;
+    }
+    double *tiles = ap.atile + (((int64_t)f * ap.n_row_tiles + rt) * n_stages) * (int64_t)SEP_A_TILE;
+    // the pad columns 2*KC .. AST-1 are never read by the contraction; keep them defined
+    tile[row * SEP_AST + 2 * SEP_KC + 0] = 0.0;
+    tile[row * SEP_AST + 2 * SEP_KC + 1] = 0.0;
+    tile[row * SEP_AST + 2 * SEP_KC + 2] = 0.0;
+    tile[row * SEP_AST + 2 * SEP_KC + 3] = 0.0;
+    // blockIdx.y strides over the stages so that small meshes still fill the GPU
+    for (int s = blockIdx.y; s < n_stages; s += gridDim.y) {
+        double2 e[SEP_KC];
+#pragma unroll
+        for (int u = 0; u < SEP_KC; ++u) e[u] = __ldg(ep[0] + ((int64_t)s * SEP_KC + u) * ap.row_len[0]);
+#pragma unroll
+        for (int t = 1; t < NRA; ++t) {
+#pragma unroll
+            for (int u = 0; u < SEP_KC; ++u) {
+                const double2 f2 = __ldg(ep[t] + ((int64_t)s * SEP_KC + u) * ap.row_len[t]);
+                const double re = e[u].x * f2.x - e[u].y * f2.y;
+                const double im = e[u].x * f2.y + e[u].y * f2.x;
+                e[u].x = re;
+                e[u].y = im;
+            }
+        }
+        __syncthreads();   // previous stage's copy-out is complete
+        double2 *dst = reinterpret_cast<double2 *>(tile + row * SEP_AST);
+#pragma unroll
+        for (int u = 0; u < SEP_KC; ++u) dst[u] = make_double2(e[u].x, -e[u].y);
+        __syncthreads();
+        const double2 *src = reinterpret_cast<const double2 *>(tile);
+        double2 *gdst = reinterpret_cast<double2 *>(tiles + (int64_t)s * SEP_A_TILE);
+#pragma unroll
+        for (int i = 0; i < SEP_A_TILE / 2 / SEP_TM; ++i) gdst[i * SEP_TM + row] = src[i * SEP_TM + row];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. the contraction
+// ---------------------------------------------------------------------------------------------
+struct ContractParams {
+    const double *atile;   // chunk-local A tiles, see AgenParams
+    const double *btile;   // whole-call B tiles, see TableParams
+    int n_row_tiles;       // row tiles in this chunk (gridDim.y)
+    int n_col_tiles;       // gridDim.x
+    int n_stages;
+    int ncomp;
+    int64_t n_fields;      // (batch entries in this chunk) * ncomp
+    int64_t batch0;        // first batch entry of this chunk
+    int64_t n_rows;        // rows of one field
+    int64_t row_begin;     // first row of this chunk
+    int64_t lc;            // length of the last axis
+    double *out;           // field (batch, comp) starts at out + (batch*ncomp + comp)*out_fstride
+    int64_t out_fstride;
 };
 
 __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b)
@@ -204,229 +256,206 @@ __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, doubl
                  : "d"(a), "d"(b));
 }
 
-template <int NRA, int CFG>  // NRA = number of row axes (dim - 1), 1..SEP_MAX_ROW_AXES
-__device__ __forceinline__ void separable_body(const SepParams &prm)
+__global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const ContractParams prm)
 {
-    using C = SepCfg<CFG>;
-    constexpr int NTHR = C::WARPS * 32;
-    constexpr int RT = C::RT, CT = C::CT;
-    constexpr int GEN = SEP_TM * SEP_KC / NTHR;   // A entries generated per thread per stage
-    static_assert(C::WARPS / C::WCOLS * RT * 8 == SEP_TM && C::WCOLS * CT * 8 == SEP_TN, "tile");
-    static_assert(GEN >= 1 && SEP_TM * SEP_KC % NTHR == 0, "A generation split");
-
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stage_base = reinterpret_cast<double *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + SEP_STAGES * SEP_STAGE_DOUBLES);
+    uint64_t *empty = full + SEP_STAGES;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int64_t col0 = (int64_t)blockIdx.x * SEP_TN;
-    const int64_t row0 = (int64_t)blockIdx.y * SEP_TM;
-    const int comp = blockIdx.z % prm.ncomp;
-    const int64_t batch = blockIdx.z / prm.ncomp;
-    const int n_stages_total = prm.n_modes_pad / SEP_KC;
+    const int n_stages = prm.n_stages;
+    // PERSISTENT: one CTA per SM walks over the output tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+    // (column tile fastest, so the CTAs working side by side share their A tiles through L2).
+    // The CTA never leaves its SM, so the concurrently running A-generation kernel can only take
+    // the resources this kernel leaves free and truly overlaps with it.
+    const int64_t n_tiles = (int64_t)prm.n_col_tiles * prm.n_row_tiles * prm.n_fields;
 
     if (tid == 0) {
-        for (int s = 0; s < SEP_STAGES; ++s) mbar_init(&full[s], NTHR + 1);  // A writers + TMA issuer
+        for (int s = 0; s < SEP_STAGES; ++s) {
+            mbar_init(&full[s], 1);              // the issuing thread's arrive.expect_tx
+            mbar_init(&empty[s], SEP_WARPS);     // one arrive per warp
+        }
         fence_barrier_init();
     }
     __syncthreads();
 
-    const int wr = warp / C::WCOLS;      // row band of RT*8 rows
-    const int wc = warp % C::WCOLS;      // column band of CT*8 columns
-    double *out = prm.out + (batch * prm.ncomp + comp) * prm.out_fstride;
-    const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-
-    // ---- B operand: thread 0 issues the cp.async.bulk copies (TMA unit) of stage s -------------
-    // 2*KC table-row slices of 1 KB each, completion counted on the stage's mbarrier.
-    const double *bc = prm.bc + batch * prm.b_bstride + col0;
-    const double *bs = prm.bs + batch * prm.b_bstride + col0;
-    auto tma_issue = [&](int s) {
-        const int slot = s % SEP_STAGES;
-        double *B = stage_base + slot * SEP_STAGE_DOUBLES + SEP_TM * SEP_AST;
-        const int64_t j0 = (int64_t)s * SEP_KC;
-        mbar_arrive_expect_tx(&full[slot], 2 * SEP_KC * SEP_TN * sizeof(double));
-#pragma unroll
-        for (int kc = 0; kc < SEP_KC; ++kc) {
-            bulk_g2s(B + (2 * kc) * SEP_BST, bc + (j0 + kc) * prm.lc_pad, SEP_TN * sizeof(double), &full[slot]);
-            bulk_g2s(B + (2 * kc + 1) * SEP_BST, bs + (j0 + kc) * prm.lc_pad, SEP_TN * sizeof(double), &full[slot]);
+    // ---- TMA: two bulk copies per pipeline step (A tile 20 KB, B tile 16.5 KB), issued by lane 0
+    // of a warp that rotates with the step.  There is no dedicated producer warp: registers are
+    // allocated to a CTA in units of four warps, so a ninth warp would cost as much as twelve.
+    // Every thread tracks the prefetch cursor (tile, stage) incrementally -- no divisions in the
+    // steady state.
+    constexpr int DEPTH = SEP_STAGES - 2;   // steps in flight ahead of the one being contracted
+    int64_t pf_tile = blockIdx.x;
+    int pf_s = 0;
+    int pf_slot = 0;
+    uint32_t pf_round = 0;                  // how often pf_slot has wrapped
+    const double *pf_a = nullptr, *pf_b = nullptr;
+    auto pf_decode = [&]() {
+        const int ct = (int)(pf_tile % prm.n_col_tiles);
+        const int64_t rest = pf_tile / prm.n_col_tiles;
+        const int rt = (int)(rest % prm.n_row_tiles);
+        const int64_t z = rest / prm.n_row_tiles;          // field-local index * ncomp + comp
+        const int comp = (int)(z % prm.ncomp);
+        const int64_t fl = z / prm.ncomp;
+        pf_a = prm.atile + ((fl * prm.n_row_tiles + rt) * (int64_t)n_stages) * SEP_A_TILE;
+        pf_b = prm.btile +
+               ((((prm.batch0 + fl) * prm.ncomp + comp) * prm.n_col_tiles + ct) * (int64_t)n_stages) * SEP_B_TILE;
+    };
+    auto pf_issue = [&]() {   // one thread
+        double *A = stage_base + pf_slot * SEP_STAGE_DOUBLES;
+        mbar_arrive_expect_tx(&full[pf_slot], SEP_STAGE_DOUBLES * sizeof(double));
+        bulk_g2s(A, pf_a + (int64_t)pf_s * SEP_A_TILE, SEP_A_TILE * sizeof(double), &full[pf_slot]);
+        bulk_g2s(A + SEP_A_TILE, pf_b + (int64_t)pf_s * SEP_B_TILE, SEP_B_TILE * sizeof(double), &full[pf_slot]);
+    };
+    auto pf_advance = [&]() {   // all threads, uniform
+        if (++pf_slot == SEP_STAGES) { pf_slot = 0; ++pf_round; }
+        if (++pf_s == n_stages) {
+            pf_s = 0;
+            pf_tile += gridDim.x;
+            if (pf_tile < n_tiles) pf_decode();
         }
     };
-
-    // ---- A operand: generated cooperatively, thread -> (tile row, GEN of the KC modes) ---------
-    // The loads for stage s+LOOKAHEAD are issued before the contraction of stage s and consumed
-    // after it, so their L2 latency is hidden; the complex products run on the issuing warp's own
-    // FP64 slots (in order with its DMMAs -- a dedicated producer warp starves behind them).
-    // LOOKAHEAD = 2 keeps the warps out of lock step: full[s+1] only needs every warp to have
-    // finished stage s-1.
-    // Slot reuse needs no "empty" barrier when STAGES >= 2*LOOKAHEAD + 1: a thread that has
-    // passed full[s] knows that ALL threads arrived on it, which each does only after finishing
-    // the contraction of stage s-LOOKAHEAD; the slot of stage s+LOOKAHEAD was last read by stage
-    // s+LOOKAHEAD-STAGES <= s-LOOKAHEAD-1.  Both the A writes and the TMA issue for stage
-    // s+LOOKAHEAD happen after that wait.
-    const int grow = tid & (SEP_TM - 1);
-    const int gm0 = (tid / SEP_TM) * GEN;
-    const double2 *ep[NRA];
-    {
-        int64_t r = row0 + grow;
-        if (r >= prm.n_rows) r = prm.n_rows - 1;  // clamp; result is never stored
+    if (pf_tile < n_tiles) pf_decode();
 #pragma unroll
-        for (int t = NRA - 1; t >= 0; --t) {
-            const int64_t it = r % prm.row_len[t];
-            r /= prm.row_len[t];
-            ep[t] = prm.erow[t] + batch * prm.erow_bstride[t] + it;
-        }
-    }
-    const double *proj =
-        prm.proj ? prm.proj + batch * prm.proj_bstride + (int64_t)comp * prm.n_modes_pad : nullptr;
-    double2 ge[NRA][GEN];
-    auto gen_load = [&](int s) {
-        const int64_t j = (int64_t)s * SEP_KC + gm0;
-#pragma unroll
-        for (int t = 0; t < NRA; ++t)
-#pragma unroll
-            for (int u = 0; u < GEN; ++u) ge[t][u] = __ldg(ep[t] + (j + u) * prm.row_stride[t]);
-    };
-    auto gen_store = [&](int s) {
-        const int slot = s % SEP_STAGES;
-        double *A = stage_base + slot * SEP_STAGE_DOUBLES;
-#pragma unroll
-        for (int u = 0; u < GEN; ++u) {
-            double2 e = ge[0][u];
-#pragma unroll
-            for (int t = 1; t < NRA; ++t) {
-                const double re = e.x * ge[t][u].x - e.y * ge[t][u].y;
-                const double im = e.x * ge[t][u].y + e.y * ge[t][u].x;
-                e.x = re;
-                e.y = im;
-            }
-            if (proj) {
-                const double pj = proj[(int64_t)s * SEP_KC + gm0 + u];
-                e.x *= pj;
-                e.y *= pj;
-            }
-            *reinterpret_cast<double2 *>(A + grow * SEP_AST + 2 * (gm0 + u)) = make_double2(e.x, -e.y);
-        }
-        mbar_arrive(&full[slot]);  // release: this thread's part of the A tile is written
-    };
-
-#pragma unroll
-    for (int p = 0; p < SEP_LOOKAHEAD; ++p) {
-        if (p < n_stages_total) {
-            if (tid == 0) tma_issue(p);
-            gen_load(p);
-            gen_store(p);
+    for (int p = 0; p < DEPTH; ++p) {
+        if (pf_tile < n_tiles) {
+            if (tid == 0) pf_issue();
+            pf_advance();
         }
     }
 
-    // warp tile = RT x CT DMMA tiles of 8x8; fragment owner: g = lane/4, t = lane%4
+    // warp tile 32 x 64 = 4 x 8 DMMA tiles of 8x8; fragment owner: g = lane/4, t = lane%4
+    const int wr = warp >> 1;        // 0..3 : 32-row band
+    const int wc = warp & 1;         // 0..1 : 64-column band
     const int g = lane >> 2;
     const int t = lane & 3;
-    double acc[RT][CT][2];
-#pragma unroll
-    for (int i = 0; i < RT; ++i)
-#pragma unroll
-        for (int j = 0; j < CT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const int a_off = (wr * RT * 8 + g) * SEP_AST + t;   // + i*8*SEP_AST + 4*k4
-    const int b_off = t * SEP_BST + wc * CT * 8 + g;     // + 4*k4*SEP_BST + j*8
+    const int a_off = (wr * 32 + g) * SEP_AST + t;               // + i*8*SEP_AST + 4*k4
+    const int b_off = SEP_A_TILE + t * SEP_BST + wc * 64 + g;    // + 4*k4*SEP_BST + j*8
 
-    for (int s = 0; s < n_stages_total; ++s) {
-        const int slot = s % SEP_STAGES;
-        if (s + SEP_LOOKAHEAD < n_stages_total) gen_load(s + SEP_LOOKAHEAD);
-        mbar_wait(&full[slot], (s / SEP_STAGES) & 1);
-        if (tid == 0 && s + SEP_LOOKAHEAD < n_stages_total) tma_issue(s + SEP_LOOKAHEAD);
-        const double *A = stage_base + slot * SEP_STAGE_DOUBLES;
-        const double *B = A + SEP_TM * SEP_AST;
+    int slot = 0;
+    uint32_t round = 0;
+    int turn = 0;                           // warp whose lane 0 issues the next prefetch
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        double acc[4][8][2];
 #pragma unroll
-        for (int k4 = 0; k4 < SEP_KC / 2; ++k4) {   // 4 contraction indices = 2 modes
-            double af[RT], bf[CT];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int i = 0; i < RT; ++i) af[i] = A[a_off + i * 8 * SEP_AST + 4 * k4];
+            for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int s = 0; s < n_stages; ++s) {
+            // prefetch DEPTH steps ahead into the slot of the step before last, which every warp
+            // released long ago (the wait on its "empty" barrier practically never blocks)
+            if (pf_tile < n_tiles) {
+                if (lane == 0 && warp == turn) {
+                    if (pf_round > 0) mbar_wait(&empty[pf_slot], (pf_round - 1) & 1);
+                    pf_issue();
+                }
+                pf_advance();
+            }
+            turn = (turn + 1) & (SEP_WARPS - 1);
+            __syncwarp();
+            mbar_wait(&full[slot], round & 1);
+            const double *S = stage_base + slot * SEP_STAGE_DOUBLES;
 #pragma unroll
-            for (int j = 0; j < CT; ++j) bf[j] = B[b_off + 4 * k4 * SEP_BST + j * 8];
+            for (int k4 = 0; k4 < SEP_KC / 2; ++k4) {   // 4 contraction indices = 2 modes
+                double af[4], bf[8];
 #pragma unroll
-            for (int j = 0; j < CT; ++j)
+                for (int i = 0; i < 4; ++i) af[i] = S[a_off + i * 8 * SEP_AST + 4 * k4];
 #pragma unroll
-                for (int i = 0; i < RT; ++i) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < 8; ++j) bf[j] = S[b_off + 4 * k4 * SEP_BST + j * 8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+            if (++slot == SEP_STAGES) { slot = 0; ++round; }
         }
-        if (s + SEP_LOOKAHEAD < n_stages_total) gen_store(s + SEP_LOOKAHEAD);
-    }
 
-    // epilogue: thread holds C[g][2t], C[g][2t+1] of every 8x8 tile
+        // epilogue: thread holds C[g][2t], C[g][2t+1] of every 8x8 tile
+        const int ct = (int)(tile % prm.n_col_tiles);
+        const int64_t rest = tile / prm.n_col_tiles;
+        const int rt = (int)(rest % prm.n_row_tiles);
+        const int64_t z = rest / prm.n_row_tiles;
+        const int comp = (int)(z % prm.ncomp);
+        const int64_t fl = z / prm.ncomp;
+        double *out = prm.out + ((prm.batch0 + fl) * prm.ncomp + comp) * prm.out_fstride;
+        const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        const int64_t row0 = prm.row_begin + (int64_t)rt * SEP_TM;
+        const int64_t col0 = (int64_t)ct * SEP_TN;
 #pragma unroll
-    for (int i = 0; i < RT; ++i) {
-        const int64_t row = row0 + wr * RT * 8 + i * 8 + g;
-        if (row >= prm.n_rows) continue;
+        for (int i = 0; i < 4; ++i) {
+            const int64_t row = row0 + wr * 32 + i * 8 + g;
+            if (row >= prm.n_rows) continue;
 #pragma unroll
-        for (int j = 0; j < CT; ++j) {
-            const int64_t col = col0 + wc * CT * 8 + j * 8 + 2 * t;
-            double *dst = out + row * prm.lc + col;
-            if (vec2 && col + 1 < prm.lc) {
-                *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
-            } else {
-                if (col < prm.lc) dst[0] = acc[i][j][0];
-                if (col + 1 < prm.lc) dst[1] = acc[i][j][1];
+            for (int j = 0; j < 8; ++j) {
+                const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
+                double *dst = out + row * prm.lc + col;
+                if (vec2 && col + 1 < prm.lc) {
+                    *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+                } else {
+                    if (col < prm.lc) dst[0] = acc[i][j][0];
+                    if (col + 1 < prm.lc) dst[1] = acc[i][j][1];
+                }
             }
         }
     }
 }
 
-// CFG 0: 16 warps x 128 registers
-template <int NRA>
-__global__ void __launch_bounds__(512, 1) separable_kernel_w16(const SepParams prm)
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+inline int launch_agen(const AgenParams &ap, int64_t n_batch_chunk, int sm_count, cudaStream_t st)
 {
-    separable_body<NRA, 0>(prm);
-}
-
-// CFG 1: 8 warps x 255 registers
-template <int NRA>
-__global__ void __launch_bounds__(256, 1) separable_kernel_w8(const SepParams prm)
-{
-    separable_body<NRA, 1>(prm);
-}
-
-template <int NRA, int CFG>
-inline int launch_separable_variant(const SepParams &prm, dim3 grid, cudaStream_t st)
-{
-    using C = SepCfg<CFG>;
-    constexpr int threads = C::WARPS * 32;
-    if (CFG == 0) {
-        GSB_CUDA(cudaFuncSetAttribute(separable_kernel_w16<NRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)SEP_SMEM_BYTES));
-        separable_kernel_w16<NRA><<<grid, threads, SEP_SMEM_BYTES, st>>>(prm);
-    } else {
-        GSB_CUDA(cudaFuncSetAttribute(separable_kernel_w8<NRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)SEP_SMEM_BYTES));
-        separable_kernel_w8<NRA><<<grid, threads, SEP_SMEM_BYTES, st>>>(prm);
+    const int n_stages = ap.n_modes_pad / SEP_KC;
+    // enough CTAs to fill the machine a few times over, never more stage-splits than stages
+    const int64_t ctas = (int64_t)ap.n_row_tiles * n_batch_chunk;
+    const int ysplit = (int)std::min<int64_t>(n_stages, std::max<int64_t>(1, (8LL * sm_count + ctas - 1) / ctas));
+    dim3 grid((unsigned)ap.n_row_tiles, (unsigned)ysplit, (unsigned)n_batch_chunk);
+    // Same shared-memory carve-out as the contraction kernel, otherwise the two kernels cannot
+    // be resident on one SM at the same time and the overlap is lost.
+    static std::atomic<bool> carveout_set{false};
+    if (!carveout_set.load()) {
+#define GSB_AGEN_ATTR(N) GSB_CUDA(cudaFuncSetAttribute(agen_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        GSB_AGEN_ATTR(1) GSB_AGEN_ATTR(2) GSB_AGEN_ATTR(3) GSB_AGEN_ATTR(4) GSB_AGEN_ATTR(5) GSB_AGEN_ATTR(6) GSB_AGEN_ATTR(7)
+#undef GSB_AGEN_ATTR
+        carveout_set.store(true);
     }
-    return GSB_OK;
-}
-
-// variant: warp configuration CFG (0 = 16 consumer warps, 1 = 8 consumer warps + setmaxnreg)
-inline int launch_separable(const SepParams &prm, int64_t n_batch, int variant, cudaStream_t st)
-{
-    dim3 grid((unsigned)(prm.lc_pad / SEP_TN), (unsigned)((prm.n_rows + SEP_TM - 1) / SEP_TM),
-              (unsigned)(n_batch * prm.ncomp));
-    if (grid.y > 65535u || grid.z > 65535u)
-        return fail(GSB_ERR_ARGUMENT, "structured mesh too large for one launch (rows/128 or batch*ncomp > 65535)");
-#define GSB_SEP_CASE(N)                                                                        \
-    case N:                                                                                    \
-        if (variant == 1) GSB_TRY((launch_separable_variant<N, 1>(prm, grid, st)));            \
-        else GSB_TRY((launch_separable_variant<N, 0>(prm, grid, st)));                         \
-        break;
-    switch (prm.n_row_axes) {
-        GSB_SEP_CASE(1)
-        GSB_SEP_CASE(2)
-        GSB_SEP_CASE(3)
-        GSB_SEP_CASE(4)
-        GSB_SEP_CASE(5)
-        GSB_SEP_CASE(6)
-        GSB_SEP_CASE(7)
+    switch (ap.n_row_axes) {
+    case 1: agen_kernel<1><<<grid, SEP_TM, 0, st>>>(ap); break;
+    case 2: agen_kernel<2><<<grid, SEP_TM, 0, st>>>(ap); break;
+    case 3: agen_kernel<3><<<grid, SEP_TM, 0, st>>>(ap); break;
+    case 4: agen_kernel<4><<<grid, SEP_TM, 0, st>>>(ap); break;
+    case 5: agen_kernel<5><<<grid, SEP_TM, 0, st>>>(ap); break;
+    case 6: agen_kernel<6><<<grid, SEP_TM, 0, st>>>(ap); break;
+    case 7: agen_kernel<7><<<grid, SEP_TM, 0, st>>>(ap); break;
     default:
         return fail(GSB_ERR_ARGUMENT, "structured path needs 2 <= dim <= 8");
     }
-#undef GSB_SEP_CASE
+    g_launches.fetch_add(1);
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+inline int launch_contract(ContractParams cp, int64_t n_batch_chunk, int sm_count, cudaStream_t st)
+{
+    cp.n_fields = n_batch_chunk * cp.ncomp;
+    const int64_t n_tiles = (int64_t)cp.n_col_tiles * cp.n_row_tiles * cp.n_fields;
+    dim3 grid((unsigned)std::min<int64_t>(n_tiles, sm_count));
+    static std::atomic<bool> attr_set{false};
+    if (!attr_set.load()) {
+        GSB_CUDA(cudaFuncSetAttribute(contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SEP_SMEM_BYTES));
+        // full 228 KB carve-out: leaves room next to this CTA for one A-generation CTA
+        GSB_CUDA(cudaFuncSetAttribute(contract_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        attr_set.store(true);
+    }
+    contract_kernel<<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
     g_launches.fetch_add(1);
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;

@@ -113,7 +113,8 @@ int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int de
  *   gsb_set_option("structured_min_tiles", v): meshes with fewer 128x128 output tiles than v
  *       are expanded on the device and sent through the direct kernel (default 64).
  *   gsb_set_option("force_path", 0|1|2): 0 auto, 1 always direct, 2 always separable.
- *   gsb_set_option("sep_variant", 0|1): separable consumer, 0 = DMMA.8x8x4 (default), 1 = DFMA tile.
+ *   gsb_set_option("scratch_mb", v): budget (MiB) for the pre-tiled A operand of the structured
+ *       path; larger meshes are processed in row chunks (default 3072).
  *   gsb_set_option("time_kernels", 0|1): see gsb_kernel_times().
  *   gsb_get_counter("launches"): CUDA kernels launched by this library so far (process-wide);
  *   "direct_calls" / "separable_calls": how often each path ran.

@@ -296,12 +296,13 @@ def test_structured_device_tensors_and_slab_consistency(gsb):
                                  [torch.tensor(a, device=dev) for a in axes])
     assert out.is_cuda and tuple(out.shape) == (64, 96, 256)
     assert np.array_equal(out.cpu().numpy(), host)
-    # the host route pipelines slabs along axis 0; a different slab size must not change a bit
-    gsb.set_option("slab_tiles", 40)
+    # the mesh is processed in row chunks bounded by the A-operand scratch budget; a different
+    # chunking must not change a bit
+    gsb.set_option("scratch_mb", 8)
     try:
         assert np.array_equal(gsb.summate_structured(cov, z1, z2, axes), host)
     finally:
-        gsb.set_option("slab_tiles", 148 * 6)
+        gsb.set_option("scratch_mb", 3072)
     # a slab computed alone equals the same rows of the full field (multi-GPU sharding unit);
     # the slab is below the tiled kernel's size threshold, so pin the path for the comparison
     gsb.set_option("force_path", 2)

@@ -26,9 +26,10 @@ def timeit(fn, reps=5):
 
 peak = gsb.measure_fp64_peak(0, 0, 0.3)
 print(f"DFMA peak {peak/1e12:.3f} TFMA/s")
-for variant in ((0,) if os.environ.get('SEP_ONLY_DMMA') else (0, 1)):
-    gsb.set_option("sep_variant", variant)
-    name = "W16" if variant == 0 else "W8 "
+for variant, growth in ((4, 140),):
+    gsb.set_option("min_chunks", variant)
+    gsb.set_option("chunk_growth_pct", growth)
+    name = f"mc={variant} g={growth}"
     # correctness on a sample
     cfg = bc.config2(128)
     tc, t1, t2 = (torch.tensor(cfg[k], device=dev) for k in ("cov", "z1", "z2"))
@@ -55,4 +56,3 @@ for variant in ((0,) if os.environ.get('SEP_ONLY_DMMA') else (0, 1)):
     t = timeit(lambda: gsb.summate_structured(*m5, axes), reps=3)
     pairs = 64 * 128 ** 3 * 1000
     print(f"{name} ensemble 64x128^3: {t*1e3:.2f} ms {pairs/t/1e12:.3f} Tpair/s  {2*pairs/t/peak*100:.1f}% of DFMA peak")
-gsb.set_option("sep_variant", 0)
