@@ -22,6 +22,7 @@ static std::atomic<int64_t> g_opt_host_chunk_points{1 << 22};
 static std::atomic<int64_t> g_opt_scratch_mb{3072};  // A-operand scratch budget (two buffers)
 static std::atomic<int64_t> g_opt_min_chunks{4};     // so that A generation overlaps the contraction
 static std::atomic<int64_t> g_opt_chunk_growth_pct{140};
+static std::atomic<int64_t> g_opt_direct_cfg{-1};   // -1 auto, else force P = 1 / 2 / 4 points per thread (0 / 1 / 2)
 static std::atomic<int64_t> g_cnt_direct{0}, g_cnt_separable{0};
 // optional device-side timing of the dominant kernels (bench.py roofline): events recorded on the
 // launch stream around every direct / separable launch while the option "time_kernels" is 1
@@ -194,6 +195,7 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
             break;
         }
     }
+    if (g_opt_direct_cfg.load() >= 0) cfg = (int)g_opt_direct_cfg.load();
     const int64_t ctas = (n_pts + direct_cfg_points(cfg, dim) - 1) / direct_cfg_points(cfg, dim);
     const int n_tiles = (int)((n_modes_pad + DIRECT_TM - 1) / DIRECT_TM);
     int n_split = 1;
@@ -766,6 +768,7 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "scratch_mb") g_opt_scratch_mb = std::max<int64_t>(value, 1);
     else if (n == "min_chunks") g_opt_min_chunks = std::max<int64_t>(value, 1);
     else if (n == "trace") g_opt_trace = value;
+    else if (n == "direct_cfg") g_opt_direct_cfg = value;
     else if (n == "chunk_growth_pct") g_opt_chunk_growth_pct = std::max<int64_t>(value, 100);
     else if (n == "time_kernels") g_opt_time_kernels = value;
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);

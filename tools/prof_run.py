@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Tiny driver for ncu captures: one separable launch (edge^3 mesh) and one direct launch."""
+"""Tiny driver for ncu captures: structured C2-like call (edge^3 mesh) and direct calls."""
 import os
 import sys
 
@@ -19,15 +19,14 @@ axes = [torch.tensor(a, device=dev) for a in cfg["axes"]]
 for _ in range(2):
     out = gsb.summate_structured(tc, t1, t2, axes)
 torch.cuda.synchronize()
-c4 = bc.config4(64)
-v = gsb.summate_incompr_structured(*(torch.tensor(c4[k], device=dev) for k in ("cov", "z1", "z2")),
-                                   [torch.arange(128.0, device=dev, dtype=torch.float64)] * 3)
 c3 = bc.config3(npts)
 pos = torch.tensor(c3["pos"], device=dev)
-m = [torch.tensor(c3[k][..., :1000], device=dev) for k in ("cov", "z1", "z2")]
+m = [torch.tensor(np.ascontiguousarray(c3[k][..., :2000]), device=dev) for k in ("cov", "z1", "z2")]
 for _ in range(2):
-    o = gsb.summate(m[0].contiguous(), m[1].contiguous(), m[2].contiguous(), pos)
+    o = gsb.summate(m[0], m[1], m[2], pos)
 pos3 = torch.rand((3, npts), device=dev, dtype=torch.float64) * 256
-o = gsb.summate_incompr(tc, t1, t2, pos3)
+c4 = bc.config4(8)
+m4 = [torch.tensor(c4[k], device=dev) for k in ("cov", "z1", "z2")]
+o = gsb.summate_incompr(m4[0], m4[1], m4[2], pos3)
 torch.cuda.synchronize()
 print("done", float(out.sum()), float(o.sum()))
