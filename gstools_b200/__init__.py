@@ -20,6 +20,8 @@ from .backend import (
     scale_shift_,
     set_device,
     summate,
+    summate_fourier,
+    summate_fourier_structured,
     summate_incompr,
     summate_incompr_structured,
     summate_structured,
@@ -33,6 +35,8 @@ __all__ = [
     "summate_incompr",
     "summate_structured",
     "summate_incompr_structured",
+    "summate_fourier",
+    "summate_fourier_structured",
     "scale_shift_",
     "enable",
     "disable",

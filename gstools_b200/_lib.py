@@ -32,6 +32,10 @@ SIGNATURES = {
                                       _int, _int, _vp]),
     "gsb_summate_incompr_structured": (_int, [_vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64,
                                               _i64, _vp, _int, _int, _vp]),
+    "gsb_summate_fourier": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _int, _int,
+                                   _vp]),
+    "gsb_summate_fourier_structured": (_int, [_vp, _vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64,
+                                              _vp, _int, _int, _vp]),
     "gsb_scale_shift": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp]),
     "gsb_set_option": (_int, [ctypes.c_char_p, _i64]),
     "gsb_get_counter": (_i64, [ctypes.c_char_p]),

@@ -29,6 +29,8 @@ __all__ = [
     "summate_incompr",
     "summate_structured",
     "summate_incompr_structured",
+    "summate_fourier",
+    "summate_fourier_structured",
     "scale_shift_",
     "set_device",
     "get_device",
@@ -115,10 +117,10 @@ def _ptr(a):
 # ----------------------------------------------------------------------------------------
 # flat (unstructured) entry points -- the reference signatures
 # ----------------------------------------------------------------------------------------
-def _flat(cov_samples, z_1, z_2, pos, vec):
+def _flat(cov_samples, z_1, z_2, pos, vec, sf=None):
     lib = _lib.load()
     if any(_is_cuda_tensor(x) for x in (cov_samples, z_1, z_2, pos)):
-        return _flat_device(lib, cov_samples, z_1, z_2, pos, vec)
+        return _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf)
     cov = np.ascontiguousarray(_as_f64(cov_samples, "cov_samples"))
     z1 = np.ascontiguousarray(_as_f64(z_1, "z_1"))
     z2 = np.ascontiguousarray(_as_f64(z_2, "z_2"))
@@ -134,6 +136,14 @@ def _flat(cov_samples, z_1, z_2, pos, vec):
         rc = lib.gsb_summate_incompr(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n,
                                      _ptr(out), max(n, 1), _lib.MEM_HOST, get_device(), None)
         _lib.check(rc, "summate_incompr")
+    elif sf is not None:
+        f = np.ascontiguousarray(_as_f64(sf, "spectrum_factor"))
+        if f.shape != z1.shape:
+            raise ValueError("spectrum_factor must have shape (mode_no,)")
+        out = _empty_host((n,))
+        rc = lib.gsb_summate_fourier(_ptr(f), _ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim,
+                                     n_modes, n, _ptr(out), _lib.MEM_HOST, get_device(), None)
+        _lib.check(rc, "summate_fourier")
     else:
         out = _empty_host((n,))
         rc = lib.gsb_summate(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n,
@@ -142,7 +152,7 @@ def _flat(cov_samples, z_1, z_2, pos, vec):
     return out
 
 
-def _flat_device(lib, cov_samples, z_1, z_2, pos, vec):
+def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None):
     torch = _torch()
     dev = next(x.device for x in (pos, cov_samples, z_1, z_2) if _is_cuda_tensor(x))
 
@@ -171,6 +181,15 @@ def _flat_device(lib, cov_samples, z_1, z_2, pos, vec):
                                      ld, dim, n_modes, n, out.data_ptr(), max(n, 1),
                                      _lib.MEM_DEVICE, dev.index, stream)
         _lib.check(rc, "summate_incompr")
+    elif sf is not None:
+        f = prep(sf)
+        if tuple(f.shape) != tuple(z1.shape):
+            raise ValueError("spectrum_factor must have shape (mode_no,)")
+        out = torch.empty((n,), dtype=torch.float64, device=dev)
+        rc = lib.gsb_summate_fourier(f.data_ptr(), cov.data_ptr(), z1.data_ptr(), z2.data_ptr(),
+                                     p.data_ptr(), ld, dim, n_modes, n, out.data_ptr(),
+                                     _lib.MEM_DEVICE, dev.index, stream)
+        _lib.check(rc, "summate_fourier")
     else:
         out = torch.empty((n,), dtype=torch.float64, device=dev)
         rc = lib.gsb_summate(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), ld,
@@ -187,6 +206,39 @@ def summate(cov_samples, z_1, z_2, pos, num_threads=None):
 def summate_incompr(cov_samples, z_1, z_2, pos, num_threads=None):
     """B200 replacement of the native ``summate_incompr`` (generator.py:51-64, math :479-495)."""
     return _flat(cov_samples, z_1, z_2, pos, vec=True)
+
+
+def summate_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads=None):
+    """B200 replacement of the native ``summate_fourier`` (generator.py:67-75, 685-692)."""
+    return _flat(modes, z_1, z_2, pos, vec=False, sf=spectrum_factor)
+
+
+def summate_fourier_structured(spectrum_factor, modes, z_1, z_2, axes, matrix=None):
+    """``summate_fourier`` on the mesh spanned by ``axes`` (host arrays), cf. :func:`summate_structured`."""
+    lib = _lib.load()
+    axes = [np.ascontiguousarray(_as_f64(a, "axes")).reshape(-1) for a in axes]
+    dim = len(axes)
+    cov = np.ascontiguousarray(_as_f64(modes, "modes"))
+    z1 = np.ascontiguousarray(_as_f64(z_1, "z_1"))
+    z2 = np.ascontiguousarray(_as_f64(z_2, "z_2"))
+    f = np.ascontiguousarray(_as_f64(spectrum_factor, "spectrum_factor"))
+    _check_modes(cov, z1, z2)
+    if cov.shape[0] != dim or f.shape != z1.shape:
+        raise ValueError("modes (dim, N), spectrum_factor (N,), len(axes) == dim")
+    lens = np.array([a.shape[0] for a in axes], dtype=np.int64)
+    cat = np.ascontiguousarray(np.concatenate(axes))
+    mat_ptr = None
+    if matrix is not None:
+        mat = np.ascontiguousarray(_as_f64(matrix, "matrix"))
+        if mat.shape != (dim, dim):
+            raise ValueError("matrix must have shape (dim, dim)")
+        mat_ptr = _ptr(mat)
+    out = _empty_host(tuple(int(v) for v in lens))
+    rc = lib.gsb_summate_fourier_structured(_ptr(f), _ptr(cov), _ptr(z1), _ptr(z2), _ptr(cat),
+                                            lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim,
+                                            cov.shape[1], _ptr(out), _lib.MEM_HOST, get_device(), None)
+    _lib.check(rc, "summate_fourier_structured")
+    return out
 
 
 # ----------------------------------------------------------------------------------------

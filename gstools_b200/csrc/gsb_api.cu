@@ -165,15 +165,15 @@ static int check_common(const void *cov, const void *z1, const void *z2, int dim
 // ---------------------------------------------------------------------------------------------
 // direct path on device-resident data
 // ---------------------------------------------------------------------------------------------
-static int pack_modes(const double *d_cov, const double *d_z1, const double *d_z2, int dim,
-                      int64_t n_modes, bool vec, double **d_recs, int64_t *n_modes_pad,
+static int pack_modes(const double *d_cov, const double *d_z1, const double *d_z2, const double *d_sf,
+                      int dim, int64_t n_modes, bool vec, double **d_recs, int64_t *n_modes_pad,
                       Scratch &scr, cudaStream_t st)
 {
     const int64_t pad = std::max<int64_t>(4, (n_modes + 3) / 4 * 4);
     GSB_TRY(scr.alloc(d_recs, (size_t)pad * direct_rec(dim, vec)));
     const int threads = 128;
     const int blocks = (int)std::min<int64_t>((pad + threads - 1) / threads, 1024);
-    pack_modes_kernel<<<blocks, threads, 0, st>>>(d_cov, d_z1, d_z2, dim, n_modes, pad, vec ? 1 : 0,
+    pack_modes_kernel<<<blocks, threads, 0, st>>>(d_cov, d_z1, d_z2, d_sf, dim, n_modes, pad, vec ? 1 : 0,
                                                   *d_recs);
     g_launches.fetch_add(1);
     GSB_CUDA(cudaGetLastError());
@@ -229,9 +229,9 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
     return GSB_OK;
 }
 
-static int summate_impl(const double *cov, const double *z1, const double *z2, const double *pos,
-                        int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts, double *out,
-                        int64_t out_ld, bool vec, int mem, int device, void *stream)
+static int summate_impl(const double *cov, const double *z1, const double *z2, const double *sf,
+                        const double *pos, int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts,
+                        double *out, int64_t out_ld, bool vec, int mem, int device, void *stream)
 {
     DeviceGuard guard;
     GSB_TRY(check_common(cov, z1, z2, dim, n_modes));
@@ -254,24 +254,29 @@ static int summate_impl(const double *cov, const double *z1, const double *z2, c
         Scratch scr(st);
         double *d_recs = nullptr;
         int64_t pad = 0;
-        GSB_TRY(pack_modes(cov, z1, z2, dim, n_modes, vec, &d_recs, &pad, scr, st));
+        GSB_TRY(pack_modes(cov, z1, z2, sf, dim, n_modes, vec, &d_recs, &pad, scr, st));
         return direct_on_device(d_recs, pad, pos, pos_ld, dim, vec, n_pts, out, out_ld, *dev, scr, st);
     }
 
     // ---- host buffers: stage modes once, then pipeline point chunks over two streams ----
     cudaStream_t s0 = dev->streams[0];
     Scratch scr0(s0);
-    double *d_cov, *d_z1, *d_z2, *d_recs;
+    double *d_cov, *d_z1, *d_z2, *d_recs, *d_sf = nullptr;
     GSB_TRY(scr0.alloc(&d_cov, (size_t)dim * n_modes));
     GSB_TRY(scr0.alloc(&d_z1, (size_t)n_modes));
     GSB_TRY(scr0.alloc(&d_z2, (size_t)n_modes));
+    if (sf) {
+        GSB_TRY(scr0.alloc(&d_sf, (size_t)n_modes));
+        if (n_modes > 0)
+            GSB_CUDA(cudaMemcpyAsync(d_sf, sf, sizeof(double) * n_modes, cudaMemcpyHostToDevice, s0));
+    }
     if (n_modes > 0) {
         GSB_CUDA(cudaMemcpyAsync(d_cov, cov, sizeof(double) * dim * n_modes, cudaMemcpyHostToDevice, s0));
         GSB_CUDA(cudaMemcpyAsync(d_z1, z1, sizeof(double) * n_modes, cudaMemcpyHostToDevice, s0));
         GSB_CUDA(cudaMemcpyAsync(d_z2, z2, sizeof(double) * n_modes, cudaMemcpyHostToDevice, s0));
     }
     int64_t pad = 0;
-    GSB_TRY(pack_modes(d_cov, d_z1, d_z2, dim, n_modes, vec, &d_recs, &pad, scr0, s0));
+    GSB_TRY(pack_modes(d_cov, d_z1, d_z2, d_sf, dim, n_modes, vec, &d_recs, &pad, scr0, s0));
     GSB_CUDA(cudaEventRecord(dev->events[0], s0));
 
     const int64_t chunk = std::min<int64_t>(n_pts, std::max<int64_t>(1024, g_opt_host_chunk_points.load()));
@@ -322,7 +327,7 @@ struct MeshInfo {
 // for all of it before this function returns (the library's two contraction streams are used
 // in between so that the A generation of one chunk overlaps the contraction of the other).
 static int structured_on_device(const double *d_cov, const double *d_z1, const double *d_z2,
-                                const double *d_axes, const MeshInfo &mesh, int64_t n_modes,
+                                const double *d_sf, const double *d_axes, const MeshInfo &mesh, int64_t n_modes,
                                 int64_t n_batch, bool vec, double *d_out, double *h_out,
                                 DeviceState &dev, cudaStream_t st)
 {
@@ -359,8 +364,8 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         for (int64_t b = 0; b < n_batch; ++b) {
             double *d_recs = nullptr;
             int64_t pad = 0;
-            GSB_TRY(pack_modes(d_cov + b * dim * n_modes, d_z1 + b * n_modes, d_z2 + b * n_modes, dim,
-                               n_modes, vec, &d_recs, &pad, scr, st));
+            GSB_TRY(pack_modes(d_cov + b * dim * n_modes, d_z1 + b * n_modes, d_z2 + b * n_modes,
+                               d_sf ? d_sf + b * n_modes : nullptr, dim, n_modes, vec, &d_recs, &pad, scr, st));
             GSB_TRY(direct_on_device(d_recs, pad, d_pos, mesh.n, dim, vec, mesh.n,
                                      d_out + b * ncomp * mesh.n, mesh.n, dev, scr, st));
         }
@@ -380,6 +385,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     tp.cov = d_cov;
     tp.z1 = d_z1;
     tp.z2 = d_z2;
+    tp.sf = d_sf;
     tp.axes = d_axes;
     std::memcpy(tp.matrix, mesh.matrix, sizeof tp.matrix);
     tp.dim = dim;
@@ -551,9 +557,10 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     return GSB_OK;
 }
 
-static int structured_impl(const double *cov, const double *z1, const double *z2, const double *axes,
-                           const int64_t *axis_len, const double *matrix, int dim, int64_t n_modes,
-                           int64_t n_batch, double *out, bool vec, int mem, int device, void *stream)
+static int structured_impl(const double *cov, const double *z1, const double *z2, const double *sf,
+                           const double *axes, const int64_t *axis_len, const double *matrix, int dim,
+                           int64_t n_modes, int64_t n_batch, double *out, bool vec, int mem, int device,
+                           void *stream)
 {
     DeviceGuard guard;
     GSB_TRY(check_common(cov, z1, z2, dim, n_modes));
@@ -610,12 +617,17 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
     if (mem == GSB_MEM_DEVICE) {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         std::lock_guard<std::mutex> lock(dev->call_mutex);
-        return structured_on_device(cov, z1, z2, axes, mesh, n_modes, n_batch, vec, out, nullptr, *dev, st);
+        return structured_on_device(cov, z1, z2, sf, axes, mesh, n_modes, n_batch, vec, out, nullptr, *dev, st);
     }
     std::lock_guard<std::mutex> lock(dev->call_mutex);
     cudaStream_t s0 = dev->streams[0];
     Scratch scr(s0);
-    double *d_cov, *d_z1, *d_z2, *d_axes, *d_out;
+    double *d_cov, *d_z1, *d_z2, *d_axes, *d_out, *d_sf = nullptr;
+    if (sf) {
+        GSB_TRY(scr.alloc(&d_sf, (size_t)n_batch * n_modes));
+        if (n_modes > 0)
+            GSB_CUDA(cudaMemcpyAsync(d_sf, sf, sizeof(double) * n_batch * n_modes, cudaMemcpyHostToDevice, s0));
+    }
     GSB_TRY(scr.alloc(&d_cov, (size_t)n_batch * dim * n_modes));
     GSB_TRY(scr.alloc(&d_z1, (size_t)n_batch * n_modes));
     GSB_TRY(scr.alloc(&d_z2, (size_t)n_batch * n_modes));
@@ -627,7 +639,7 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
         GSB_CUDA(cudaMemcpyAsync(d_z2, z2, sizeof(double) * n_batch * n_modes, cudaMemcpyHostToDevice, s0));
     }
     GSB_CUDA(cudaMemcpyAsync(d_axes, axes, sizeof(double) * mesh.total_axes, cudaMemcpyHostToDevice, s0));
-    GSB_TRY(structured_on_device(d_cov, d_z1, d_z2, d_axes, mesh, n_modes, n_batch, vec, d_out, out, *dev, s0));
+    GSB_TRY(structured_on_device(d_cov, d_z1, d_z2, d_sf, d_axes, mesh, n_modes, n_batch, vec, d_out, out, *dev, s0));
     GSB_CUDA(cudaStreamSynchronize(s0));
     return GSB_OK;
 }
@@ -713,16 +725,16 @@ int gsb_summate(const double *cov_samples, const double *z_1, const double *z_2,
                 int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts, double *out, int mem,
                 int device, void *stream)
 {
-    return summate_impl(cov_samples, z_1, z_2, pos, pos_ld, dim, n_modes, n_pts, out, n_pts, false,
-                        mem, device, stream);
+    return summate_impl(cov_samples, z_1, z_2, nullptr, pos, pos_ld, dim, n_modes, n_pts, out, n_pts,
+                        false, mem, device, stream);
 }
 
 int gsb_summate_incompr(const double *cov_samples, const double *z_1, const double *z_2,
                         const double *pos, int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts,
                         double *out, int64_t out_ld, int mem, int device, void *stream)
 {
-    return summate_impl(cov_samples, z_1, z_2, pos, pos_ld, dim, n_modes, n_pts, out, out_ld, true,
-                        mem, device, stream);
+    return summate_impl(cov_samples, z_1, z_2, nullptr, pos, pos_ld, dim, n_modes, n_pts, out, out_ld,
+                        true, mem, device, stream);
 }
 
 int gsb_summate_structured(const double *cov_samples, const double *z_1, const double *z_2,
@@ -730,8 +742,8 @@ int gsb_summate_structured(const double *cov_samples, const double *z_1, const d
                            int64_t n_modes, int64_t n_batch, double *out, int mem, int device,
                            void *stream)
 {
-    return structured_impl(cov_samples, z_1, z_2, axes, axis_len, matrix, dim, n_modes, n_batch, out,
-                           false, mem, device, stream);
+    return structured_impl(cov_samples, z_1, z_2, nullptr, axes, axis_len, matrix, dim, n_modes, n_batch,
+                           out, false, mem, device, stream);
 }
 
 int gsb_summate_incompr_structured(const double *cov_samples, const double *z_1, const double *z_2,
@@ -739,8 +751,27 @@ int gsb_summate_incompr_structured(const double *cov_samples, const double *z_1,
                                    int dim, int64_t n_modes, int64_t n_batch, double *out, int mem,
                                    int device, void *stream)
 {
-    return structured_impl(cov_samples, z_1, z_2, axes, axis_len, matrix, dim, n_modes, n_batch, out,
-                           true, mem, device, stream);
+    return structured_impl(cov_samples, z_1, z_2, nullptr, axes, axis_len, matrix, dim, n_modes, n_batch,
+                           out, true, mem, device, stream);
+}
+
+int gsb_summate_fourier(const double *spectrum_factor, const double *modes, const double *z_1,
+                        const double *z_2, const double *pos, int64_t pos_ld, int dim, int64_t n_modes,
+                        int64_t n_pts, double *out, int mem, int device, void *stream)
+{
+    if (n_modes > 0 && !spectrum_factor) return fail(GSB_ERR_ARGUMENT, "spectrum_factor must not be NULL");
+    return summate_impl(modes, z_1, z_2, spectrum_factor, pos, pos_ld, dim, n_modes, n_pts, out, n_pts,
+                        false, mem, device, stream);
+}
+
+int gsb_summate_fourier_structured(const double *spectrum_factor, const double *modes, const double *z_1,
+                                   const double *z_2, const double *axes, const int64_t *axis_len,
+                                   const double *matrix, int dim, int64_t n_modes, double *out, int mem,
+                                   int device, void *stream)
+{
+    if (n_modes > 0 && !spectrum_factor) return fail(GSB_ERR_ARGUMENT, "spectrum_factor must not be NULL");
+    return structured_impl(modes, z_1, z_2, spectrum_factor, axes, axis_len, matrix, dim, n_modes, 1, out,
+                           false, mem, device, stream);
 }
 
 int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int device, void *stream)

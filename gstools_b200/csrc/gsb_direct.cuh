@@ -42,8 +42,9 @@ __host__ __device__ constexpr int direct_rec(int D, bool vec)
 // Records j >= n_modes (padding up to n_modes_pad) are all-zero and contribute exactly 0.
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_modes_kernel(const double *__restrict__ cov, const double *__restrict__ z1,
-                                  const double *__restrict__ z2, int dim, int64_t n_modes,
-                                  int64_t n_modes_pad, int vec, double *__restrict__ recs)
+                                  const double *__restrict__ z2, const double *__restrict__ sf,
+                                  int dim, int64_t n_modes, int64_t n_modes_pad, int vec,
+                                  double *__restrict__ recs)
 {
     const int koff = direct_koff(dim);
     const int rec = direct_rec(dim, vec != 0);
@@ -61,7 +62,9 @@ __global__ void pack_modes_kernel(const double *__restrict__ cov, const double *
             k2 += k * k;
         }
         for (int t = dim; t < koff; ++t) R[t] = 0.0;
-        const double a = z1[j], b = z2[j];
+        // sf: optional per-mode spectrum factor of the Fourier generator (generator.py:685-692)
+        const double w = sf ? sf[j] : 1.0;
+        const double a = w * z1[j], b = w * z2[j];
         double *W = R + koff;
         W[0] = a;  W[1] = b;     // n & 3 == 0 :  z1 c + z2 s
         W[2] = b;  W[3] = -a;    // n & 3 == 1 :  z2 c - z1 s

@@ -83,6 +83,7 @@ struct TableParams {
     const double *cov;     // (n_batch, dim, n_modes)
     const double *z1;      // (n_batch, n_modes)
     const double *z2;
+    const double *sf;      // optional per-mode spectrum factor (Fourier generator), (n_batch, n_modes)
     const double *axes;    // concatenated axis coordinates
     int64_t axis_off[GSB_MAX_DIM];
     int64_t axis_len[GSB_MAX_DIM];
@@ -123,7 +124,8 @@ __global__ void build_tables_kernel(const TableParams tp)
                 kp = fma(tp.matrix[s2 * tp.dim + t], cov[(int64_t)s2 * tp.n_modes + j], kp);
             sincos(kp * tp.axes[tp.axis_off[t] + i], &s, &c);
             if (t == 0 && !last) {  // fold the complex weight (z1 - i z2) into the first row axis
-                const double a = tp.z1[b * tp.n_modes + j], bb = tp.z2[b * tp.n_modes + j];
+                const double w = tp.sf ? tp.sf[b * tp.n_modes + j] : 1.0;
+                const double a = w * tp.z1[b * tp.n_modes + j], bb = w * tp.z2[b * tp.n_modes + j];
                 const double re = a * c + bb * s;
                 const double im = a * s - bb * c;
                 c = re;

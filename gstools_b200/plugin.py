@@ -10,7 +10,7 @@ at call time (generator.py:266, :554), so rebinding them takes effect for existi
     wrappers to versions that consult it first and otherwise fall through to the originals
     (Cython / Rust) -- zero edits to the reference;
   * optionally (``lazy_grid=True``) wraps ``Field.pre_pos`` (field/base.py:254-297) so that, for
-    ``mesh_type="structured"`` calls of an SRF/CondSRF driven by RandMeth/IncomprRandMeth, the
+    ``mesh_type="structured"`` calls of an SRF/CondSRF driven by RandMeth/IncomprRandMeth/Fourier, the
     mesh is NOT expanded on the host: ``pre_pos`` returns a zero-stride placeholder of the right
     shape ``(dim, n)`` that carries ``(axes, isometrisation matrix)``, and the rebound wrapper
     recognises it and runs the separable structured kernel.  Everything between ``pre_pos`` and
@@ -85,8 +85,10 @@ def enable(lazy_grid: bool = True):
     with _LOCK:
         if not _STATE["enabled"]:
             _STATE.update(orig_summate=gen._summate, orig_summate_incompr=gen._summate_incompr,
+                          orig_summate_fourier=gen._summate_fourier,
                           orig_pre_pos=fbase.Field.pre_pos, gen=gen, fbase=fbase, config=config)
         orig_s, orig_si = _STATE["orig_summate"], _STATE["orig_summate_incompr"]
+        orig_sf = _STATE["orig_summate_fourier"]
         orig_pre_pos = _STATE["orig_pre_pos"]
         config.USE_GSTOOLS_B200 = True
         config._GSTOOLS_B200_AVAIL = True
@@ -111,6 +113,16 @@ def enable(lazy_grid: bool = True):
                 return backend.summate_incompr(cov_samples, z_1, z_2, pos, num_threads)
             return orig_si(cov_samples, z_1, z_2, _materialise(pos), num_threads)
 
+        def _summate_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads=None):
+            """A wrapper function for calling the Fourier algorithms (B200 first)."""
+            if getattr(config, "USE_GSTOOLS_B200", False):
+                lazy = _lookup_lazy(pos)
+                if lazy is not None:
+                    return backend.summate_fourier_structured(spectrum_factor, modes, z_1, z_2,
+                                                              lazy[0], lazy[1]).reshape(-1)
+                return backend.summate_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads)
+            return orig_sf(spectrum_factor, modes, z_1, z_2, _materialise(pos), num_threads)
+
         def _materialise(pos):
             lazy = _lookup_lazy(pos)
             if lazy is None:
@@ -120,9 +132,10 @@ def enable(lazy_grid: bool = True):
 
         gen._summate = _summate
         gen._summate_incompr = _summate_incompr
+        gen._summate_fourier = _summate_fourier
 
         if lazy_grid:
-            exact = (gen.RandMeth, gen.IncomprRandMeth)
+            exact = (gen.RandMeth, gen.IncomprRandMeth, gen.Fourier)
 
             def pre_pos(self, pos=None, mesh_type="unstructured", info=False):
                 generator = getattr(self, "_generator", None)
@@ -166,6 +179,7 @@ def disable():
         gen, fbase, config = _STATE["gen"], _STATE["fbase"], _STATE["config"]
         gen._summate = _STATE["orig_summate"]
         gen._summate_incompr = _STATE["orig_summate_incompr"]
+        gen._summate_fourier = _STATE["orig_summate_fourier"]
         fbase.Field.pre_pos = _STATE["orig_pre_pos"]
         config.USE_GSTOOLS_B200 = False
         _STATE["enabled"] = False

@@ -101,6 +101,25 @@ int gsb_summate_incompr_structured(const double *cov_samples, const double *z_1,
                                    int device, void *stream);
 
 /*
+ * gsb_summate_fourier[_structured] -- replaces gstools_cython.field.summate_fourier /
+ *   gstools_core.summate_fourier (imported generator.py:23,33; called generator.py:67-75 from the
+ *   Fourier generator, generator.py:685-692):
+ *   out[i] = sum_j spectrum_factor[j] (z_1[j] cos(k_j . x_i) + z_2[j] sin(k_j . x_i)),
+ *   `modes` is (dim, n_modes).  Same kernels with the factor folded into the mode weights on the
+ *   device.  
+ */
+int gsb_summate_fourier(const double *spectrum_factor, const double *modes, const double *z_1,
+                        const double *z_2, const double *pos, int64_t pos_ld, int dim,
+                        int64_t n_modes, int64_t n_pts, double *out, int mem, int device,
+                        void *stream);
+
+int gsb_summate_fourier_structured(const double *spectrum_factor, const double *modes,
+                                   const double *z_1, const double *z_2, const double *axes,
+                                   const int64_t *axis_len, const double *matrix, int dim,
+                                   int64_t n_modes, double *out, int mem, int device,
+                                   void *stream);
+
+/*
  * Fused caller epilogue (reference: src/gstools/field/generator.py:269-270):
  *   field[i] = scale * field[i] + shift     in place, device pointers only.
  * Lets a device-resident caller keep the field on the GPU.

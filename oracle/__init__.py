@@ -51,6 +51,9 @@ def _load():
             fn.restype = ctypes.c_int
             fn.argtypes = [dp, dp, dp, dp, ctypes.c_int, ctypes.c_int64,
                            ctypes.c_int64, dp, ctypes.c_int]
+        lib.oracle_summate_fourier.restype = ctypes.c_int
+        lib.oracle_summate_fourier.argtypes = [dp, dp, dp, dp, dp, ctypes.c_int, ctypes.c_int64,
+                                               ctypes.c_int64, dp, ctypes.c_int]
         lib.oracle_max_threads.restype = ctypes.c_int
         _lib = lib
     return _lib
@@ -97,6 +100,21 @@ def summate_incompr(cov_samples, z_1, z_2, pos, num_threads=None):
                                         _ptr(out), int(num_threads or 0))
     if rc:
         raise RuntimeError(f"oracle_summate_incompr failed: {rc}")
+    return out
+
+
+def summate_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads=None):
+    """C/OpenMP oracle of ``summate_fourier`` (generator.py:67-75)."""
+    cov, z1, z2, p = _prep(modes, z_1, z_2, pos)
+    sf = np.ascontiguousarray(spectrum_factor, dtype=np.float64)
+    if sf.shape != z1.shape:
+        raise ValueError("oracle: spectrum_factor must have shape (N,)")
+    out = np.zeros(p.shape[1], dtype=np.float64)
+    rc = _load().oracle_summate_fourier(_ptr(sf), _ptr(cov), _ptr(z1), _ptr(z2), _ptr(p),
+                                        cov.shape[0], cov.shape[1], p.shape[1], _ptr(out),
+                                        int(num_threads or 0))
+    if rc:
+        raise RuntimeError(f"oracle_summate_fourier failed: {rc}")
     return out
 
 

@@ -116,3 +116,26 @@ int oracle_summate_incompr(const double *cov_samples, const double *z1, const do
     }
     return 0;
 }
+
+/* summate_fourier (next row f3): out[i] = sum_j sf[j] (z1[j] cos(phi_ij) + z2[j] sin(phi_ij)),
+ * phi_ij = modes[:,j] . pos[:,i]; call site src/gstools/field/generator.py:67-75, 685-692. */
+int oracle_summate_fourier(const double *spectrum_factor, const double *modes, const double *z1,
+                           const double *z2, const double *pos, int dim, int64_t n_modes,
+                           int64_t n_pts, double *out, int num_threads)
+{
+    if (dim < 1 || n_modes < 0 || n_pts < 0) return 1;
+    int nt = pick_threads(num_threads);
+    (void)nt;
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int64_t i = 0; i < n_pts; ++i) {
+        double acc = 0.0;
+        for (int64_t j = 0; j < n_modes; ++j) {
+            double phase = 0.0;
+            for (int t = 0; t < dim; ++t)
+                phase += modes[(int64_t)t * n_modes + j] * pos[(int64_t)t * n_pts + i];
+            acc += spectrum_factor[j] * (z1[j] * cos(phase) + z2[j] * sin(phase));
+        }
+        out[i] = acc;
+    }
+    return 0;
+}

@@ -46,6 +46,17 @@ def _rec(kind, fn):
 
 gen._summate = _rec("scalar", _orig_summate)
 gen._summate_incompr = _rec("incompr", _orig_summate_incompr)
+_orig_summate_fourier = gen._summate_fourier
+
+
+def _rec_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads=None):
+    out = _orig_summate_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads)
+    RECORD.append(dict(kind="fourier", cov_samples=np.array(modes), z_1=np.array(z_1), z_2=np.array(z_2),
+                       pos=np.array(pos), raw=np.array(out), spectrum_factor=np.array(spectrum_factor)))
+    return out
+
+
+gen._summate_fourier = _rec_fourier
 
 
 def save(name, field, asserts, extra=None, places_default=7):
@@ -63,6 +74,8 @@ def save(name, field, asserts, extra=None, places_default=7):
         meta.update({k: v for k, v in extra.items() if not isinstance(v, np.ndarray)})
     arrays = dict(cov_samples=rec["cov_samples"], z_1=rec["z_1"], z_2=rec["z_2"],
                   pos=rec["pos"], raw=rec["raw"], field=field)
+    if "spectrum_factor" in rec:
+        arrays["spectrum_factor"] = rec["spectrum_factor"]
     if extra:
         arrays.update({k: v for k, v in extra.items() if isinstance(v, np.ndarray)})
     np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), **arrays)
@@ -180,6 +193,25 @@ def main():
     save("condsrf_1d", f, [], extra=dict(var=0.5, mode_no=100, cond_pos=cond_pos[0],
                                           cond_val=cond_val, gridx=gx,
                                           cite="examples/06_conditioned_fields/00_condition_ensemble.py"))
+    # ---- Fourier generator (next row f3): tests/test_fouriergen.py:13-57 -------------------
+    fseed = 19900408
+    L = [80, 30, 91]
+    fx, fy, fz = np.linspace(0, L[0], 11), np.linspace(0, L[1], 31), np.linspace(0, L[2], 13)
+    mode_no = [12, 6, 14]
+    for dim, model, pos, idx, val, cite in [
+        (1, gs.Gaussian(dim=1, var=0.5, len_scale=10.0), (fx,), (0,), 0.6236929351309081,
+         "tests/test_fouriergen.py:48"),
+        (2, gs.Gaussian(dim=2, var=2.0, len_scale=30.0), (fx, fy), (0, 0), -0.1431996611581266,
+         "tests/test_fouriergen.py:52"),
+        (3, gs.Gaussian(dim=3, var=2.1, len_scale=21.0), (fx, fy, fz), (0, 0, 0), -1.0433325279452803,
+         "tests/test_fouriergen.py:56"),
+    ]:
+        srf = gs.SRF(model, generator="Fourier", mode_no=mode_no[:dim], period=L[:dim], seed=fseed)
+        f = srf(pos, mesh_type="structured")
+        extra = dict(var=float(model.var), mode_no=int(np.prod(mode_no[:dim])))
+        for t, a in enumerate(pos):
+            extra[f"axis{t}"] = np.asarray(a, dtype=float)
+        save(f"fourier_{dim}d", f, [(idx, val, cite)], extra=extra)
     print("done:", len(RECORD), "boundary crossings recorded")
 
 

@@ -167,6 +167,32 @@ def test_condsrf_ensemble_through_plugin(gs_b200, gsb):
     assert np.max(np.abs(f_at - cond_val)) < 1e-6
 
 
+def test_fourier_generator_through_plugin(gs_b200, gsb):
+    """Next row f3: tests/test_fouriergen.py:46-74 with the B200 backend (structured, lazy mesh)."""
+    gs = gs_b200
+    seed, L, mode_no = 19900408, [80, 30, 91], [12, 6, 14]
+    x, y, z = np.linspace(0, L[0], 11), np.linspace(0, L[1], 31), np.linspace(0, L[2], 13)
+    launches = gsb.get_counter("launches")
+    srf1 = gs.SRF(gs.Gaussian(dim=1, var=0.5, len_scale=10.0), generator="Fourier", mode_no=mode_no[:1],
+                  period=L[:1], seed=seed)
+    f1 = srf1((x,), mesh_type="structured")
+    assert round(f1[0] - 0.6236929351309081, 7) == 0 and round(f1[0] - f1[-1], 7) == 0
+    srf2 = gs.SRF(gs.Gaussian(dim=2, var=2.0, len_scale=30.0), generator="Fourier", mode_no=mode_no[:2],
+                  period=L[:2], seed=seed)
+    f2 = srf2((x, y), mesh_type="structured")
+    assert round(f2[0, 0] - -0.1431996611581266, 7) == 0
+    assert round(f2[0, len(y) // 2] - f2[-1, len(y) // 2], 7) == 0      # periodicity
+    srf3 = gs.SRF(gs.Gaussian(dim=3, var=2.1, len_scale=21.0), generator="Fourier", mode_no=mode_no,
+                  period=L, seed=seed)
+    f3 = srf3((x, y, z), mesh_type="structured")
+    assert round(f3[0, 0, 0] - -1.0433325279452803, 7) == 0
+    f3u = srf3((x[:5], y[:5], z[:5]), mesh_type="unstructured")
+    assert abs(f3u[0] - f3[0, 0, 0]) < 1e-9
+    assert gsb.get_counter("launches") > launches
+    meta, d = load_golden("fourier_3d")
+    assert np.max(np.abs(f3 - d["field"])) <= TOL * np.sqrt(2.1)
+
+
 def test_backends_agree_and_switch_at_runtime(gs_b200, gsb):
     """config flag is read at call time (docs/source/index.rst:131-132): flipping
     USE_GSTOOLS_B200 switches an EXISTING generator between the GPU and the reference backend."""

@@ -27,6 +27,21 @@ def maxabs(a, b):
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_boundary_arrays(name, gsb):
     meta, d = load_golden(name)
+    if meta["kind"] == "fourier":
+        got = gsb.summate_fourier(d["spectrum_factor"], d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
+        assert maxabs(got, d["raw"]) <= TOL * np.sqrt(meta["var"])   # spectrum factor carries the scale
+        axes = [d[f"axis{t}"] for t in range(d["cov_samples"].shape[0])]
+        for force in (1, 2):
+            gsb.set_option("force_path", force)
+            try:
+                st = gsb.summate_fourier_structured(d["spectrum_factor"], d["cov_samples"], d["z_1"], d["z_2"], axes)
+            finally:
+                gsb.set_option("force_path", 0)
+            assert st.shape == d["field"].shape
+            assert maxabs(st, d["field"]) <= TOL * np.sqrt(meta["var"])
+            for a in meta["asserts"]:
+                assert round(st[tuple(a["index"])] - a["value"], a["places"]) == 0, a["cite"]
+        return
     fn = gsb.summate if meta["kind"] == "scalar" else gsb.summate_incompr
     got = fn(d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
     assert got.shape == d["raw"].shape and got.dtype == np.float64
@@ -326,3 +341,39 @@ def test_separable_and_direct_kernels_agree(gsb):
     finally:
         gsb.set_option("force_path", 0)
     assert maxabs(sep, direct) <= raw_tol(1000)
+
+
+def test_structured_chunking_is_invisible(gsb, oracle_mod):
+    """The A-operand scratch budget splits the mesh into row chunks (and ensembles into field
+    chunks); vector fields, batches, host and device routes must give the same bits whatever the
+    chunking, and ragged last tiles / chunks must be handled."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    cov, z1, z2 = synth_modes(3, 96, seed=21)
+    axes = [np.arange(37.0), np.linspace(0, 50, 53), np.linspace(-3, 40, 150)]   # 1961 rows: ragged
+    grid = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+    gsb.set_option("force_path", 2)
+    try:
+        ref_s = gsb.summate_structured(cov, z1, z2, axes)
+        ref_v = gsb.summate_incompr_structured(cov, z1, z2, axes)
+        assert maxabs(ref_s, oracle_mod.summate(cov, z1, z2, grid).reshape(37, 53, 150)) <= raw_tol(96)
+        assert maxabs(ref_v, oracle_mod.summate_incompr(cov, z1, z2, grid).reshape(3, 37, 53, 150)) <= raw_tol(96)
+        sets = [synth_modes(3, 96, seed=30 + b) for b in range(5)]
+        bc_, b1, b2 = (np.stack([s_[i] for s_ in sets]) for i in range(3))
+        ref_b = gsb.summate_structured(bc_, b1, b2, axes)
+        ref_bv = gsb.summate_incompr_structured(bc_, b1, b2, axes)
+        for mb in (1, 2, 5):          # 1 MiB: a handful of row tiles per chunk
+            gsb.set_option("scratch_mb", mb)
+            assert np.array_equal(gsb.summate_structured(cov, z1, z2, axes), ref_s)
+            assert np.array_equal(gsb.summate_incompr_structured(cov, z1, z2, axes), ref_v)
+            assert np.array_equal(gsb.summate_structured(bc_, b1, b2, axes), ref_b)
+            assert np.array_equal(gsb.summate_incompr_structured(bc_, b1, b2, axes), ref_bv)
+            t = [torch.tensor(a, device=dev) for a in (bc_, b1, b2)]
+            out = gsb.summate_incompr_structured(t[0], t[1], t[2], [torch.tensor(a, device=dev) for a in axes])
+            assert np.array_equal(out.cpu().numpy(), ref_bv)
+        for b in range(5):
+            assert np.array_equal(ref_b[b], gsb.summate_structured(*sets[b], axes))
+    finally:
+        gsb.set_option("scratch_mb", 3072)
+        gsb.set_option("force_path", 0)

@@ -88,6 +88,7 @@ def test_enable_rebinds_and_disable_restores(gsb):
     from gstools.field import generator as gen
 
     o1, o2, o3 = gen._summate, gen._summate_incompr, fbase.Field.pre_pos
+    o4 = gen._summate_fourier
     gsb.enable()
     try:
         assert gsb.is_enabled() and config.USE_GSTOOLS_B200 is True
@@ -97,6 +98,7 @@ def test_enable_rebinds_and_disable_restores(gsb):
     finally:
         gsb.disable()
     assert gen._summate is o1 and gen._summate_incompr is o2 and fbase.Field.pre_pos is o3
+    assert gen._summate_fourier is o4
     assert config.USE_GSTOOLS_B200 is False and not gsb.is_enabled()
 
 

@@ -13,8 +13,11 @@ from conftest import golden_names, load_golden, synth_modes
 @pytest.mark.parametrize("name", golden_names())
 def test_oracle_reproduces_recorded_boundary(name, oracle_mod):
     meta, d = load_golden(name)
-    fn = oracle_mod.summate if meta["kind"] == "scalar" else oracle_mod.summate_incompr
-    got = fn(d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
+    if meta["kind"] == "fourier":
+        got = oracle_mod.summate_fourier(d["spectrum_factor"], d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
+    else:
+        fn = oracle_mod.summate if meta["kind"] == "scalar" else oracle_mod.summate_incompr
+        got = fn(d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
     # same library, same libm: bit-for-bit
     assert np.array_equal(got, d["raw"])
 
@@ -34,6 +37,19 @@ def test_oracle_matches_reference_test_literals(name, oracle_mod):
     for a in meta["asserts"]:
         got = field[tuple(a["index"])]
         assert round(got - a["value"], a["places"]) == 0, (a["cite"], got, a["value"])
+
+
+@pytest.mark.parametrize("name", ["fourier_1d", "fourier_2d", "fourier_3d"])
+def test_oracle_fourier_matches_reference_test_literals(name, oracle_mod):
+    """tests/test_fouriergen.py:46-57: the Fourier generator returns the raw sum (generator.py:693-694)."""
+    meta, d = load_golden(name)
+    raw = oracle_mod.summate_fourier(d["spectrum_factor"], d["cov_samples"], d["z_1"], d["z_2"], d["pos"])
+    field = raw.reshape(d["field"].shape)
+    for a in meta["asserts"]:
+        assert round(field[tuple(a["index"])] - a["value"], a["places"]) == 0, a["cite"]
+    # and equals the modified-weights form used by the GPU kernels
+    assert np.allclose(raw, oracle_mod.summate(d["cov_samples"], d["spectrum_factor"] * d["z_1"],
+                                               d["spectrum_factor"] * d["z_2"], d["pos"]), rtol=0, atol=1e-12)
 
 
 def test_oracle_3d_literals_are_16_digit(oracle_mod):

@@ -21,7 +21,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
                  ::"r"(s32(bar)), "r"(parity) : "memory");
 }
 
-template <int STAGES, int CW>   // CW consumer warps: 8 (32x64 tiles) or 16 (32x32 tiles)
+template <int STAGES, int CW, bool SCALE>   // CW consumer warps: 8 (32x64 tiles) or 16 (32x32 tiles)
 __global__ void __launch_bounds__((CW + 1) * 32, 1) gemm_like(double* sink, int stages, const double* at, const double* bt, int n_at)
 {
     extern __shared__ __align__(128) double sm[];
@@ -70,6 +70,17 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) gemm_like(double* sink, int 
             double af[RT], bf[CT];
 #pragma unroll
             for (int i = 0; i < RT; ++i) af[i] = A[a_off + i * 8 * AST + 4 * k4];
+            if (SCALE) {
+                // frag' = alpha*own + beta*partner, (alpha, beta) per (lane parity, mode): the slow-axis
+                // phase factor applied in the consumer instead of a pre-generated A operand
+                const double2 cc = *reinterpret_cast<const double2*>(B + 2 * KC * BST - 32 + 2 * (2 * k4 + (t >> 1)));
+                const double alpha = (t & 1) ? -cc.x : cc.x, beta = -cc.y;
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    const double partner = __shfl_xor_sync(0xffffffffu, af[i], 1);
+                    af[i] = fma(alpha, af[i], beta * partner);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < CT; ++j) bf[j] = B[b_off + 4 * k4 * BST + j * 8];
 #pragma unroll
@@ -88,17 +99,17 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) gemm_like(double* sink, int 
     if (r == 1.2345) sink[0] = r;
 }
 
-template <int STAGES, int CW>
+template <int STAGES, int CW, bool SCALE>
 int run(const char* name, double* sink, int ctas, const double* at, const double* bt, int n_at)
 {
     const int stages = 125 * 8;
     const size_t smem = STAGES * STAGE_D * sizeof(double) + 2 * STAGES * 8 + 64;
-    CK(cudaFuncSetAttribute(gemm_like<STAGES, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(gemm_like<STAGES, CW, SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0);
-        gemm_like<STAGES, CW><<<ctas, (CW + 1) * 32, smem>>>(sink, stages, at, bt, n_at);
+        gemm_like<STAGES, CW, SCALE><<<ctas, (CW + 1) * 32, smem>>>(sink, stages, at, bt, n_at);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep && ms < best) best = ms;
     }
@@ -118,10 +129,12 @@ int main()
     CK(cudaMalloc(&bt, sizeof(double) * (size_t)B_D * 125)); CK(cudaMemset(bt, 0, sizeof(double) * (size_t)B_D * 125));
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
     const int n = p.multiProcessorCount;
-    run<4, 8>("8 consumer warps, 4 stages, 1 wave", sink, n, at, bt, n_at);
-    run<5, 8>("8 consumer warps, 5 stages, 1 wave", sink, n, at, bt, n_at);
-    run<5, 16>("16 consumer warps, 5 stages, 1 wave", sink, n, at, bt, n_at);
-    run<3, 8>("8 consumer warps, 3 stages, 1 wave", sink, n, at, bt, n_at);
-    run<5, 8>("8 consumer warps, 5 stages, 4 waves", sink, 4 * n, at, bt, n_at);
+    run<4, 8, false>("8 consumer warps, 4 stages, 1 wave", sink, n, at, bt, n_at);
+    run<5, 8, false>("8 consumer warps, 5 stages, 1 wave", sink, n, at, bt, n_at);
+    run<5, 16, false>("16 consumer warps, 5 stages, 1 wave", sink, n, at, bt, n_at);
+    run<5, 8, false>("8 consumer warps, 5 stages, 4 waves", sink, 4 * n, at, bt, n_at);
+    run<4, 8, true>("8 warps, 4 stages, A rescaled in consumer", sink, n, at, bt, n_at);
+    run<5, 8, true>("8 warps, 5 stages, A rescaled in consumer", sink, n, at, bt, n_at);
+    run<5, 16, true>("16 warps, 5 stages, A rescaled in consumer", sink, n, at, bt, n_at);
     return 0;
 }
