@@ -22,6 +22,8 @@ static std::atomic<int64_t> g_opt_host_chunk_points{1 << 22};
 static std::atomic<int64_t> g_opt_scratch_mb{3072};  // A-operand scratch budget (two buffers)
 static std::atomic<int64_t> g_opt_min_chunks{4};     // so that A generation overlaps the contraction
 static std::atomic<int64_t> g_opt_chunk_growth_pct{140};
+static std::atomic<int64_t> g_opt_sep_path{0};      // 0 auto, 1 pre-generated A (agen), 2 scaled in the consumer
+static std::atomic<int64_t> g_cnt_scaled{0};
 static std::atomic<int64_t> g_opt_direct_cfg{-1};   // -1 auto, else force P = 1 / 2 / 4 points per thread (0 / 1 / 2)
 static std::atomic<int64_t> g_cnt_direct{0}, g_cnt_separable{0};
 // optional device-side timing of the dominant kernels (bench.py roofline): events recorded on the
@@ -393,7 +395,28 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     tp.n_modes_pad = n_modes_pad;
     tp.ncomp = ncomp;
     tp.n_col_tiles = n_col_tiles;
+    // Which contraction variant?  "scaled" (no A generation, ~89 % of peak whatever the shape, rows
+    // padded to 128 per slow index) wins when an A tile would feed only one or two output tiles;
+    // pre-generated A (~94 %) wins otherwise.  2-D meshes have no slow axis: A is the table itself.
+    const int64_t ly = mesh.len[dim - 2];
+    const int n_ytiles = (int)((ly + SEP_TM - 1) / SEP_TM);
+    const int64_t n_slow = mesh.n_rows / ly;
+    bool scaled = false;
+    if (nra >= 2) {
+        const int64_t tpu = (int64_t)n_col_tiles * ncomp;
+        const double eff_agen = tpu >= 4 ? 0.93 : (tpu == 3 ? 0.90 : (tpu == 2 ? 0.80 : 0.72));
+        const double eff_scaled = 0.89 * (double)ly / ((double)n_ytiles * SEP_TM);
+        scaled = eff_scaled > eff_agen;
+        const int64_t sp = g_opt_sep_path.load();
+        if (sp == 1) scaled = false;
+        if (sp == 2) scaled = true;
+    }
     int64_t max_width = (int64_t)n_col_tiles * SEP_TN;
+    if (scaled) {
+        tp.n_ytiles = n_ytiles;
+        GSB_TRY(scr.alloc(&tp.ytab, (size_t)n_batch * n_ytiles * n_stages * SEP_A_TILE));
+        max_width = std::max<int64_t>(max_width, (int64_t)n_ytiles * SEP_TM);
+    }
     for (int t = 0; t < dim; ++t) {
         tp.axis_off[t] = mesh.off[t];
         tp.axis_len[t] = mesh.len[t];
@@ -411,6 +434,84 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         build_tables_kernel<<<grid, 256, 0, st>>>(tp);
         g_launches.fetch_add(1);
         GSB_CUDA(cudaGetLastError());
+    }
+
+    if (scaled) {
+        CtabParams ctp;
+        std::memset(&ctp, 0, sizeof ctp);
+        ctp.n_slow_axes = nra - 1;
+        for (int t = 0; t < nra - 1; ++t) {
+            ctp.erow[t] = tp.erow[t];
+            ctp.erow_bstride[t] = tp.erow_bstride[t];
+            ctp.row_len[t] = mesh.len[t];
+        }
+        ctp.n_slow = n_slow;
+        ctp.n_modes_pad = n_modes_pad;
+        GSB_TRY(scr.alloc(&ctp.ctab, (size_t)n_batch * n_slow * n_modes_pad));
+        {
+            const int64_t work = n_slow * n_modes_pad;
+            dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 4096), 1, (unsigned)n_batch);
+            ctab_kernel<<<grid, 256, 0, st>>>(ctp);
+            g_launches.fetch_add(1);
+            GSB_CUDA(cudaGetLastError());
+        }
+        ContractParams cp;
+        std::memset(&cp, 0, sizeof cp);
+        cp.btile = tp.btile;
+        cp.n_col_tiles = n_col_tiles;
+        cp.n_stages = n_stages;
+        cp.ncomp = ncomp;
+        cp.n_rows = mesh.n_rows;
+        cp.lc = lc;
+        cp.out = d_out;
+        cp.out_fstride = mesh.n;
+        cp.ytab = tp.ytab;
+        cp.ctab = ctp.ctab;
+        cp.n_ytiles = n_ytiles;
+        cp.n_slow = n_slow;
+        cp.ly = ly;
+        cp.n_modes_pad = n_modes_pad;
+        // One launch for everything on the device route.  The host route splits the work into ~8
+        // pieces (groups of fields, or ranges of slow indices of a single field) so that the D2H
+        // copy of one piece overlaps the contraction of the next.
+        if (n_slow * n_ytiles > 0x7fffffff) return fail(GSB_ERR_ARGUMENT, "structured mesh too large");
+        const int64_t pieces = h_out ? 8 : 1;
+        const int64_t fgroup = std::max<int64_t>(1, n_batch / pieces);
+        const int64_t splits = (n_batch >= pieces) ? 1 : std::min<int64_t>(n_slow, pieces / n_batch);
+        int64_t c = 0;
+        for (int64_t f0 = 0; f0 < n_batch; f0 += fgroup) {
+            const int64_t nf = std::min(fgroup, n_batch - f0);
+            for (int64_t k = 0; k < splits; ++k, ++c) {
+                const int64_t s_lo = n_slow * k / splits, s_hi = n_slow * (k + 1) / splits;
+                if (s_hi == s_lo) continue;
+                cp.batch0 = f0;
+                cp.rt0 = s_lo * n_ytiles;
+                cp.n_row_tiles = (int)((s_hi - s_lo) * n_ytiles);
+                {
+                    KernelTimer timer(st);
+                    TraceScope ts("contract(scaled)", st);
+                    GSB_TRY(launch_contract(cp, nf, dev.sm_count, true, st));
+                }
+                if (h_out) {
+                    cudaEvent_t ev = dev.contract_events[c % DeviceState::N_CHUNK_EVENTS];
+                    GSB_CUDA(cudaEventRecord(ev, st));
+                    GSB_CUDA(cudaStreamWaitEvent(dev.streams[1], ev, 0));
+                    for (int64_t f = f0; f < f0 + nf; ++f)
+                        for (int comp = 0; comp < ncomp; ++comp) {
+                            const size_t off = ((size_t)f * ncomp + comp) * mesh.n + (size_t)s_lo * ly * lc;
+                            GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * (s_hi - s_lo) * ly * lc,
+                                                     cudaMemcpyDeviceToHost, dev.streams[1]));
+                        }
+                }
+            }
+        }
+        if (h_out) {
+            GSB_CUDA(cudaEventRecord(dev.events[4], dev.streams[1]));
+            GSB_CUDA(cudaStreamWaitEvent(st, dev.events[4], 0));
+        }
+        g_cnt_separable.fetch_add(1);
+        g_cnt_scaled.fetch_add(1);
+        return GSB_OK;
     }
 
     // Chunk plan.  A unit is (field, row tile); its A operand takes `unit_bytes`.  Chunks alternate
@@ -515,7 +616,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
             {
                 KernelTimer timer(st);
                 TraceScope ts("contract", st);
-                GSB_TRY(launch_contract(cp, nf, dev.sm_count, st));
+                GSB_TRY(launch_contract(cp, nf, dev.sm_count, false, st));
             }
             GSB_CUDA(cudaEventRecord(dev.contract_events[c % NE], st));
             if (h_out) {
@@ -800,6 +901,7 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "min_chunks") g_opt_min_chunks = std::max<int64_t>(value, 1);
     else if (n == "trace") g_opt_trace = value;
     else if (n == "direct_cfg") g_opt_direct_cfg = value;
+    else if (n == "sep_path") g_opt_sep_path = value;
     else if (n == "chunk_growth_pct") g_opt_chunk_growth_pct = std::max<int64_t>(value, 100);
     else if (n == "time_kernels") g_opt_time_kernels = value;
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);
@@ -813,6 +915,7 @@ int64_t gsb_get_counter(const char *name)
     if (n == "launches") return g_launches.load();
     if (n == "direct_calls") return g_cnt_direct.load();
     if (n == "separable_calls") return g_cnt_separable.load();
+    if (n == "scaled_calls") return g_cnt_scaled.load();
     return -1;
 }
 

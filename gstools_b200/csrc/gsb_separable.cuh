@@ -70,7 +70,8 @@ constexpr int SEP_AST = 2 * SEP_KC + 4;
 constexpr int SEP_BST = SEP_TN + 4;
 constexpr int SEP_A_TILE = SEP_TM * SEP_AST;          // doubles
 constexpr int SEP_B_TILE = 2 * SEP_KC * SEP_BST;      // doubles
-constexpr int SEP_STAGE_DOUBLES = SEP_A_TILE + SEP_B_TILE;
+constexpr int SEP_C_BLOCK = 2 * SEP_KC;               // doubles: KC complex slow-axis factors (scaled variant)
+constexpr int SEP_STAGE_DOUBLES = SEP_A_TILE + SEP_B_TILE + SEP_C_BLOCK;
 static_assert((SEP_A_TILE * 8) % 16 == 0 && (SEP_B_TILE * 8) % 16 == 0, "bulk copy granularity");
 static_assert((SEP_A_TILE / 2) % SEP_TM == 0, "agen copy-out loop");
 constexpr size_t SEP_SMEM_BYTES =
@@ -100,6 +101,10 @@ struct TableParams {
     // SEP_B_TILE block
     double *btile;
     int n_col_tiles;
+    // scaled variant only: the LAST row axis pre-tiled like an A tile, raw (cos, sin):
+    // ytab[((b*n_ytiles + yt)*n_stages + s)] is one SEP_A_TILE block (rows beyond the axis are zero)
+    double *ytab;
+    int n_ytiles;
 };
 
 __global__ void build_tables_kernel(const TableParams tp)
@@ -108,7 +113,8 @@ __global__ void build_tables_kernel(const TableParams tp)
     const int64_t b = blockIdx.z;             // batch entry
     const int64_t len = tp.axis_len[t];
     const bool last = (t == tp.dim - 1);
-    const int64_t width = last ? (int64_t)tp.n_col_tiles * SEP_TN : len;
+    const bool ytile = (tp.ytab != nullptr && t == tp.dim - 2);
+    const int64_t width = last ? (int64_t)tp.n_col_tiles * SEP_TN : (ytile ? (int64_t)tp.n_ytiles * SEP_TM : len);
     const int64_t total = width * tp.n_modes_pad;
     const int n_stages = tp.n_modes_pad / SEP_KC;
     const double *cov = tp.cov + b * tp.dim * tp.n_modes;
@@ -133,7 +139,12 @@ __global__ void build_tables_kernel(const TableParams tp)
             }
         }
         if (!last) {
-            tp.erow[t][b * tp.erow_bstride[t] + j * len + i] = make_double2(c, s);
+            if (i < len) tp.erow[t][b * tp.erow_bstride[t] + j * len + i] = make_double2(c, s);
+            if (ytile) {
+                const int yt = (int)(i / SEP_TM), r = (int)(i % SEP_TM);
+                double *tile = tp.ytab + (((b * tp.n_ytiles + yt) * n_stages + (j / SEP_KC)) * (int64_t)SEP_A_TILE);
+                *reinterpret_cast<double2 *>(tile + r * SEP_AST + 2 * (j % SEP_KC)) = make_double2(c, s);
+            }
             continue;
         }
         const int ct = (int)(i / SEP_TN), col = (int)(i % SEP_TN);
@@ -232,6 +243,41 @@ __global__ void __launch_bounds__(SEP_TM) agen_kernel(const AgenParams ap)
     }
 }
 
+// Scaled variant: slow-axis phase factors c[b][s][j] = prod_{t < NRA-1} E_t[j][i_t(s)] (weights folded
+// in through axis 0), s = flattened index over all row axes but the last.
+struct CtabParams {
+    const double2 *erow[SEP_MAX_ROW_AXES];
+    int64_t erow_bstride[SEP_MAX_ROW_AXES];
+    int64_t row_len[SEP_MAX_ROW_AXES];
+    int n_slow_axes;       // NRA - 1 >= 1
+    int64_t n_slow;        // prod(row_len[:n_slow_axes])
+    int n_modes_pad;
+    double2 *ctab;         // (n_batch, n_slow, n_modes_pad)
+};
+
+__global__ void ctab_kernel(const CtabParams cp)
+{
+    const int64_t b = blockIdx.z;
+    const int64_t total = cp.n_slow * cp.n_modes_pad;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t sidx = idx / cp.n_modes_pad;
+        const int64_t j = idx - sidx * cp.n_modes_pad;
+        int64_t r = sidx;
+        double2 e = make_double2(1.0, 0.0);
+        for (int t = cp.n_slow_axes - 1; t >= 0; --t) {
+            const int64_t it = r % cp.row_len[t];
+            r /= cp.row_len[t];
+            const double2 f = cp.erow[t][b * cp.erow_bstride[t] + j * cp.row_len[t] + it];
+            const double re = e.x * f.x - e.y * f.y;
+            const double im = e.x * f.y + e.y * f.x;
+            e.x = re;
+            e.y = im;
+        }
+        cp.ctab[(b * cp.n_slow + sidx) * cp.n_modes_pad + j] = e;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // 3. the contraction
 // ---------------------------------------------------------------------------------------------
@@ -249,6 +295,15 @@ struct ContractParams {
     int64_t lc;            // length of the last axis
     double *out;           // field (batch, comp) starts at out + (batch*ncomp + comp)*out_fstride
     int64_t out_fstride;
+    // scaled variant (template SCALED): A tiles come from the pre-tiled last row axis and are
+    // multiplied by the slow-axis phase factor in the consumer; row tile rt = s_slow*n_ytiles + yt
+    const double *ytab;
+    const double2 *ctab;
+    int n_ytiles;
+    int64_t n_slow;
+    int64_t ly;            // length of the last row axis
+    int n_modes_pad;
+    int64_t rt0;           // first (global) row tile of this launch
 };
 
 __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b)
@@ -258,6 +313,14 @@ __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, doubl
                  : "d"(a), "d"(b));
 }
 
+// SCALED = false: A tiles pre-generated by agen_kernel (best when an A tile feeds >= 3 output tiles).
+// SCALED = true : no A generation at all.  The A tile is the pre-tiled table of the LAST row axis
+//                 (shared by all slow indices, L2 resident); the phase factor of the slower axes,
+//                 c_j(s), arrives as a third 128-byte bulk copy per stage and each consumer rescales
+//                 its own A fragments (2 FP64 ops per fragment).  Costs ~9 % of the DMMA rate
+//                 (profiles/r01_microbench_dmma_tma.log) but no scratch, no extra HBM traffic, and
+//                 it does not depend on how often an A tile is reused.
+template <bool SCALED>
 __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const ContractParams prm)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -294,7 +357,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
     int pf_s = 0;
     int pf_slot = 0;
     uint32_t pf_round = 0;                  // how often pf_slot has wrapped
-    const double *pf_a = nullptr, *pf_b = nullptr;
+    const double *pf_a = nullptr, *pf_b = nullptr, *pf_c = nullptr;
     auto pf_decode = [&]() {
         const int ct = (int)(pf_tile % prm.n_col_tiles);
         const int64_t rest = pf_tile / prm.n_col_tiles;
@@ -302,15 +365,26 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
         const int64_t z = rest / prm.n_row_tiles;          // field-local index * ncomp + comp
         const int comp = (int)(z % prm.ncomp);
         const int64_t fl = z / prm.ncomp;
-        pf_a = prm.atile + ((fl * prm.n_row_tiles + rt) * (int64_t)n_stages) * SEP_A_TILE;
+        if (SCALED) {
+            const int64_t sl = (prm.rt0 + rt) / prm.n_ytiles;
+            const int yt = (int)((prm.rt0 + rt) % prm.n_ytiles);
+            pf_a = prm.ytab + (((prm.batch0 + fl) * prm.n_ytiles + yt) * (int64_t)n_stages) * SEP_A_TILE;
+            pf_c = reinterpret_cast<const double *>(prm.ctab + ((prm.batch0 + fl) * prm.n_slow + sl) * prm.n_modes_pad);
+        } else {
+            pf_a = prm.atile + ((fl * prm.n_row_tiles + rt) * (int64_t)n_stages) * SEP_A_TILE;
+        }
         pf_b = prm.btile +
                ((((prm.batch0 + fl) * prm.ncomp + comp) * prm.n_col_tiles + ct) * (int64_t)n_stages) * SEP_B_TILE;
     };
     auto pf_issue = [&]() {   // one thread
         double *A = stage_base + pf_slot * SEP_STAGE_DOUBLES;
-        mbar_arrive_expect_tx(&full[pf_slot], SEP_STAGE_DOUBLES * sizeof(double));
+        constexpr uint32_t bytes = (SEP_A_TILE + SEP_B_TILE + (SCALED ? SEP_C_BLOCK : 0)) * sizeof(double);
+        mbar_arrive_expect_tx(&full[pf_slot], bytes);
         bulk_g2s(A, pf_a + (int64_t)pf_s * SEP_A_TILE, SEP_A_TILE * sizeof(double), &full[pf_slot]);
         bulk_g2s(A + SEP_A_TILE, pf_b + (int64_t)pf_s * SEP_B_TILE, SEP_B_TILE * sizeof(double), &full[pf_slot]);
+        if (SCALED)
+            bulk_g2s(A + SEP_A_TILE + SEP_B_TILE, pf_c + (int64_t)pf_s * SEP_C_BLOCK,
+                     SEP_C_BLOCK * sizeof(double), &full[pf_slot]);
     };
     auto pf_advance = [&]() {   // all threads, uniform
         if (++pf_slot == SEP_STAGES) { pf_slot = 0; ++pf_round; }
@@ -368,6 +442,21 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
                 for (int i = 0; i < 4; ++i) af[i] = S[a_off + i * 8 * SEP_AST + 4 * k4];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) bf[j] = S[b_off + 4 * k4 * SEP_BST + j * 8];
+                if (SCALED) {
+                    // this lane holds part (t & 1) of mode 2*k4 + (t >> 1): (cos, sin) of the last row
+                    // axis.  With c = (cr, ci) the slow-axis factor, the contraction needs
+                    //   part 0:  Re(c e) =  cr*cos - ci*sin       part 1: -Im(c e) = -cr*sin - ci*cos
+                    // i.e. alpha*own + beta*partner with alpha = +-cr, beta = -ci.
+                    const double2 cc = *reinterpret_cast<const double2 *>(
+                        S + SEP_A_TILE + SEP_B_TILE + 2 * (2 * k4 + (t >> 1)));
+                    const double alpha = (t & 1) ? -cc.x : cc.x;
+                    const double beta = -cc.y;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const double partner = __shfl_xor_sync(0xffffffffu, af[i], 1);
+                        af[i] = fma(alpha, af[i], beta * partner);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -387,12 +476,21 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
         const int64_t fl = z / prm.ncomp;
         double *out = prm.out + ((prm.batch0 + fl) * prm.ncomp + comp) * prm.out_fstride;
         const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-        const int64_t row0 = prm.row_begin + (int64_t)rt * SEP_TM;
         const int64_t col0 = (int64_t)ct * SEP_TN;
+        int64_t row0, row_end;                      // first row of the tile, end of its valid rows
+        if (SCALED) {
+            const int64_t sl = (prm.rt0 + rt) / prm.n_ytiles;
+            const int64_t iy0 = (int64_t)((prm.rt0 + rt) % prm.n_ytiles) * SEP_TM;
+            row0 = sl * prm.ly + iy0;
+            row_end = sl * prm.ly + prm.ly;         // rows of one slow index never spill into the next
+        } else {
+            row0 = prm.row_begin + (int64_t)rt * SEP_TM;
+            row_end = prm.n_rows;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int64_t row = row0 + wr * 32 + i * 8 + g;
-            if (row >= prm.n_rows) continue;
+            if (row >= row_end) continue;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
@@ -443,21 +541,22 @@ inline int launch_agen(const AgenParams &ap, int64_t n_batch_chunk, int sm_count
     return GSB_OK;
 }
 
-inline int launch_contract(ContractParams cp, int64_t n_batch_chunk, int sm_count, cudaStream_t st)
+inline int launch_contract(ContractParams cp, int64_t n_batch_chunk, int sm_count, bool scaled, cudaStream_t st)
 {
     cp.n_fields = n_batch_chunk * cp.ncomp;
     const int64_t n_tiles = (int64_t)cp.n_col_tiles * cp.n_row_tiles * cp.n_fields;
     dim3 grid((unsigned)std::min<int64_t>(n_tiles, sm_count));
     static std::atomic<bool> attr_set{false};
     if (!attr_set.load()) {
-        GSB_CUDA(cudaFuncSetAttribute(contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)SEP_SMEM_BYTES));
-        // full 228 KB carve-out: leaves room next to this CTA for one A-generation CTA
-        GSB_CUDA(cudaFuncSetAttribute(contract_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
+        // full 228 KB carve-out: leaves room next to this CTA for A-generation CTAs
+        GSB_CUDA(cudaFuncSetAttribute(contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM_BYTES));
+        GSB_CUDA(cudaFuncSetAttribute(contract_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        GSB_CUDA(cudaFuncSetAttribute(contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM_BYTES));
+        GSB_CUDA(cudaFuncSetAttribute(contract_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set.store(true);
     }
-    contract_kernel<<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
+    if (scaled) contract_kernel<true><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
+    else contract_kernel<false><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
     g_launches.fetch_add(1);
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;

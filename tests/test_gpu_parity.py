@@ -235,7 +235,7 @@ STRUCT_CASES = [
 
 
 @pytest.mark.parametrize("dim,lens,n_modes", STRUCT_CASES)
-@pytest.mark.parametrize("path", ["direct", "separable"])
+@pytest.mark.parametrize("path", ["direct", "separable", "separable-agen", "separable-scaled"])
 def test_structured_vs_oracle(dim, lens, n_modes, path, gsb, oracle_mod):
     cov, z1, z2 = synth_modes(dim, n_modes, seed=7 + dim)
     rs = np.random.RandomState(5)
@@ -245,6 +245,8 @@ def test_structured_vs_oracle(dim, lens, n_modes, path, gsb, oracle_mod):
     pos = mat @ grid
     want = oracle_mod.summate(cov, z1, z2, pos).reshape(lens)
     gsb.set_option("force_path", 1 if path == "direct" else 2)
+    # the two contraction variants: A operand pre-generated (agen) / rescaled in the consumer
+    gsb.set_option("sep_path", {"separable-agen": 1, "separable-scaled": 2}.get(path, 0))
     try:
         got = gsb.summate_structured(cov, z1, z2, axes, mat)
         assert got.shape == tuple(lens)
@@ -256,6 +258,7 @@ def test_structured_vs_oracle(dim, lens, n_modes, path, gsb, oracle_mod):
             assert maxabs(gv, wv) <= raw_tol(n_modes)
     finally:
         gsb.set_option("force_path", 0)
+        gsb.set_option("sep_path", 0)
 
 
 def test_structured_identity_matrix_and_auto_path(gsb, oracle_mod):
@@ -374,6 +377,17 @@ def test_structured_chunking_is_invisible(gsb, oracle_mod):
             assert np.array_equal(out.cpu().numpy(), ref_bv)
         for b in range(5):
             assert np.array_equal(ref_b[b], gsb.summate_structured(*sets[b], axes))
+        # the scaled variant: same fields within tolerance, batching / host splitting invisible
+        gsb.set_option("scratch_mb", 3072)
+        gsb.set_option("sep_path", 2)
+        sc_s = gsb.summate_structured(cov, z1, z2, axes)
+        sc_bv = gsb.summate_incompr_structured(bc_, b1, b2, axes)
+        assert maxabs(sc_s, ref_s) <= raw_tol(96) and maxabs(sc_bv, ref_bv) <= raw_tol(96)
+        t = [torch.tensor(a, device=dev) for a in (bc_, b1, b2)]
+        out = gsb.summate_incompr_structured(t[0], t[1], t[2], [torch.tensor(a, device=dev) for a in axes])
+        assert np.array_equal(out.cpu().numpy(), sc_bv)
+        assert np.array_equal(gsb.summate_structured(*sets[2], axes), gsb.summate_structured(bc_, b1, b2, axes)[2])
     finally:
         gsb.set_option("scratch_mb", 3072)
         gsb.set_option("force_path", 0)
+        gsb.set_option("sep_path", 0)

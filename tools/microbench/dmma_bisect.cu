@@ -59,6 +59,27 @@ __global__ void __launch_bounds__(256, 1) loop(double* sink, int stages, const d
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(s32(B + k * BST)), "l"(btab + (size_t)((s * 16 + k) % 2000) * 512), "r"(1024), "r"(s32(&full[slot])) : "memory");
     };
+    // split phase (F & 16): products are computed at the TOP of a stage from the raw (TMA-loaded)
+    // operands and only stored at the END of the stage, a whole stage of DMMAs later
+    double2 sp[4];
+    auto gen_compute = [&](int s) {
+        const int slot = s % STAGES;
+        const double* raw = sm + slot * STAGE_D;      // stands in for the raw table tile of stage s
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double2 e = *reinterpret_cast<const double2*>(raw + grow * AST + 2 * (gm0 + u));
+            const double2 c = *reinterpret_cast<const double2*>(raw + TM * AST + 2 * (gm0 + u));   // broadcast
+            sp[u].x = e.x * c.x - e.y * c.y;
+            sp[u].y = -(e.x * c.y + e.y * c.x);
+        }
+    };
+    auto gen_commit = [&](int s) {
+        const int slot = s % STAGES;
+        double* A = sm + slot * STAGE_D;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) *reinterpret_cast<double2*>(A + grow * AST + 2 * (gm0 + u)) = sp[u];
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&full[slot])) : "memory");
+    };
     auto gen_store = [&](int s) {
         const int slot = s % STAGES;
         double* A = sm + slot * STAGE_D;
@@ -75,7 +96,9 @@ __global__ void __launch_bounds__(256, 1) loop(double* sink, int stages, const d
         }
         if (F & 4) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&full[slot])) : "memory");
     };
-    if (F & 4) {
+    if (F & 16) {
+        for (int p = 0; p < 2; ++p) { if ((F & 8) && tid == 0) tma(p); gen_compute(p); gen_commit(p); }
+    } else if (F & 4) {
         for (int p = 0; p < 2; ++p) { if ((F & 8) && tid == 0) tma(p); gen_store(p); }
     }
     for (int s = 0; s < stages; ++s) {
@@ -87,6 +110,7 @@ __global__ void __launch_bounds__(256, 1) loop(double* sink, int stages, const d
                 ge[1][u] = __ldg(tab + 512000 + ((size_t)(s * 8 + gm0 + u) % 1000) * 512 + ((grow * 3) & 511));
             }
         }
+        if ((F & 16) && s + 2 < stages) gen_compute(s + 2);
         if (F & 4) {
             mbar_wait(&full[slot], (s / STAGES) & 1);
             if ((F & 8) && tid == 0 && s + 2 < stages) tma(s + 2);
@@ -105,7 +129,8 @@ __global__ void __launch_bounds__(256, 1) loop(double* sink, int stages, const d
 #pragma unroll
                 for (int i = 0; i < 4; ++i) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
-        if (s + 2 < stages) gen_store(s + 2);
+        if (F & 16) { if (s + 2 < stages) gen_commit(s + 2); }
+        else if (s + 2 < stages) gen_store(s + 2);
     }
     double r = 0;
 #pragma unroll
@@ -151,5 +176,6 @@ int main()
     run<7>("+ FP64 + LDG + STS + mbarrier", sink, n, tab, btab);
     run<12>("+ STS + mbarrier + TMA", sink, n, tab, btab);
     run<15>("everything (FP64 + LDG + STS + mbarrier + TMA)", sink, n, tab, btab);
+    run<20>("split phase: FP64 at stage top, STS at stage end", sink, n, tab, btab);
     return 0;
 }

@@ -68,8 +68,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) gemm_like(double* sink, int 
 #pragma unroll
         for (int k4 = 0; k4 < KC / 2; ++k4) {
             double af[RT], bf[CT];
+            if (!SCALE) {
 #pragma unroll
-            for (int i = 0; i < RT; ++i) af[i] = A[a_off + i * 8 * AST + 4 * k4];
+                for (int i = 0; i < RT; ++i) af[i] = A[a_off + i * 8 * AST + 4 * k4];
+            }
             if (SCALE) {
                 // frag' = alpha*own + beta*partner, (alpha, beta) per (lane parity, mode): the slow-axis
                 // phase factor applied in the consumer instead of a pre-generated A operand
@@ -77,8 +79,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) gemm_like(double* sink, int 
                 const double alpha = (t & 1) ? -cc.x : cc.x, beta = -cc.y;
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
-                    const double partner = __shfl_xor_sync(0xffffffffu, af[i], 1);
-                    af[i] = fma(alpha, af[i], beta * partner);
+                    // (re, im) pair of this lane's mode: one 16-byte load instead of LDS.64 + shuffle
+                    const double2 p = *reinterpret_cast<const double2*>(A + a_off - t + 2 * (t >> 1) + i * 8 * AST + 4 * k4);
+                    const double own = (t & 1) ? p.y : p.x, partner = (t & 1) ? p.x : p.y;
+                    af[i] = fma(alpha, own, beta * partner);
                 }
             }
 #pragma unroll

@@ -26,10 +26,9 @@ def timeit(fn, reps=5):
 
 peak = gsb.measure_fp64_peak(0, 0, 0.3)
 print(f"DFMA peak {peak/1e12:.3f} TFMA/s")
-for variant, growth in ((4, 140),):
-    gsb.set_option("min_chunks", variant)
-    gsb.set_option("chunk_growth_pct", growth)
-    name = f"mc={variant} g={growth}"
+for variant in (0, 1, 2):
+    gsb.set_option("sep_path", variant)
+    name = ["auto  ", "agen  ", "scaled"][variant]
     # correctness on a sample
     cfg = bc.config2(128)
     tc, t1, t2 = (torch.tensor(cfg[k], device=dev) for k in ("cov", "z1", "z2"))
