@@ -182,8 +182,19 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
                 const double v = u + RINT_MAGIC;           // rint(u) lands in the low mantissa bits
                 const int q = lo32(v);
                 const double r = u - (v - RINT_MAGIC);     // exact, |r| <= 1/2
+#ifdef GSB_DIRECT_SEL
+                // arithmetic quadrant fix-up (ablation): selects + sign flips instead of the LDS
+                const double z1v = R[KOFF], z2v = R[KOFF + 1];
+                double2 w;
+                w.x = (q & 1) ? z2v : z1v;
+                w.y = (q & 1) ? -z1v : z2v;
+                const int sgn = (q & 2) << 30;
+                w.x = __hiloint2double(__double2hiint(w.x) ^ sgn, __double2loint(w.x));
+                w.y = __hiloint2double(__double2hiint(w.y) ^ sgn, __double2loint(w.y));
+#else
                 const double2 w = *reinterpret_cast<const double2 *>(
                     reinterpret_cast<const char *>(R + KOFF) + ((q & 3) << 4));
+#endif
                 const double z = r * r;
                 double ps, pc;
                 qt_polys(z, ps, pc);
@@ -245,7 +256,10 @@ template <int D, bool VEC>
 inline void launch_direct_dim(const DirectParams &prm, int cfg, cudaStream_t st)
 {
     if constexpr (D <= 4) {
-        if (cfg == 2) return launch_direct_cfg<D, 4, VEC, 256, 2>(prm, st);
+#ifndef GSB_DIRECT_MINB
+#define GSB_DIRECT_MINB 2
+#endif
+        if (cfg == 2) return launch_direct_cfg<D, 4, VEC, 256, GSB_DIRECT_MINB>(prm, st);
     }
     if (cfg >= 1) launch_direct_cfg<D, 2, VEC, 128, 4>(prm, st);
     else launch_direct_cfg<D, 1, VEC, 64, 8>(prm, st);

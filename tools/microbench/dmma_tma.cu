@@ -21,7 +21,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
                  ::"r"(s32(bar)), "r"(parity) : "memory");
 }
 
-template <int STAGES, int CW, bool SCALE>   // CW consumer warps: 8 (32x64 tiles) or 16 (32x32 tiles)
+template <int STAGES, int CW, bool SCALE, int WT = 0>   // CW consumer warps: 8 (32x64 tiles) or 16 (32x32 tiles)
 __global__ void __launch_bounds__((CW + 1) * 32, 1) gemm_like(double* sink, int stages, const double* at, const double* bt, int n_at)
 {
     extern __shared__ __align__(128) double sm[];
@@ -52,9 +52,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) gemm_like(double* sink, int 
         }
         return;
     }
-    constexpr int WCOLS = (CW == 8) ? 2 : 4, CT = (CW == 8) ? 8 : 4, RT = 4;
+    constexpr int WCOLS = WT ? 1 : ((CW == 8) ? 2 : 4), CT = WT ? 16 : ((CW == 8) ? 8 : 4), RT = WT ? 2 : 4;
     const int g = lane >> 2, t = lane & 3, wr = warp / WCOLS, wc = warp % WCOLS;
-    const int a_off = (wr * 32 + g) * AST + t, b_off = t * BST + wc * CT * 8 + g;
+    const int a_off = (wr * RT * 8 + g) * AST + t, b_off = t * BST + wc * CT * 8 + g;
     double acc[RT][CT][2];
 #pragma unroll
     for (int i = 0; i < RT; ++i)
@@ -103,17 +103,17 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) gemm_like(double* sink, int 
     if (r == 1.2345) sink[0] = r;
 }
 
-template <int STAGES, int CW, bool SCALE>
+template <int STAGES, int CW, bool SCALE, int WT = 0>
 int run(const char* name, double* sink, int ctas, const double* at, const double* bt, int n_at)
 {
     const int stages = 125 * 8;
     const size_t smem = STAGES * STAGE_D * sizeof(double) + 2 * STAGES * 8 + 64;
-    CK(cudaFuncSetAttribute(gemm_like<STAGES, CW, SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(gemm_like<STAGES, CW, SCALE, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0);
-        gemm_like<STAGES, CW, SCALE><<<ctas, (CW + 1) * 32, smem>>>(sink, stages, at, bt, n_at);
+        gemm_like<STAGES, CW, SCALE, WT><<<ctas, (CW + 1) * 32, smem>>>(sink, stages, at, bt, n_at);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep && ms < best) best = ms;
     }
@@ -140,5 +140,7 @@ int main()
     run<4, 8, true>("8 warps, 4 stages, A rescaled in consumer", sink, n, at, bt, n_at);
     run<5, 8, true>("8 warps, 5 stages, A rescaled in consumer", sink, n, at, bt, n_at);
     run<5, 16, true>("16 warps, 5 stages, A rescaled in consumer", sink, n, at, bt, n_at);
+    run<4, 8, false, 1>("8 warps, warp tile 16x128, plain", sink, n, at, bt, n_at);
+    run<4, 8, true, 1>("8 warps, warp tile 16x128, A rescaled", sink, n, at, bt, n_at);
     return 0;
 }
