@@ -17,6 +17,7 @@ from ._lib import (GSB200Error, device_count, get_counter, kernel_times, measure
                    set_option)
 from .backend import (
     get_device,
+    make_epilogue,
     scale_shift_,
     set_device,
     summate,
@@ -38,6 +39,7 @@ __all__ = [
     "summate_fourier",
     "summate_fourier_structured",
     "scale_shift_",
+    "make_epilogue",
     "enable",
     "disable",
     "is_enabled",

@@ -20,6 +20,19 @@ _int = ctypes.c_int
 MEM_HOST = 0
 MEM_DEVICE = 1
 
+EPI_MAX_ADD = 4
+EPI_MAX_COMP = 3
+
+
+class Epilogue(ctypes.Structure):
+    """``gsb_epilogue`` of include/gsb200.h: v = scale*sum, then + add[0][c], + add[1][c], ..."""
+
+    _fields_ = [("scale", ctypes.c_double), ("n_add", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("add", (ctypes.c_double * EPI_MAX_COMP) * EPI_MAX_ADD)]
+
+
+_epi_p = ctypes.POINTER(Epilogue)
+
 # every symbol include/gsb200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "gsb_version": (_int, []),
@@ -32,6 +45,14 @@ SIGNATURES = {
                                       _int, _int, _vp]),
     "gsb_summate_incompr_structured": (_int, [_vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64,
                                               _i64, _vp, _int, _int, _vp]),
+    "gsb_summate_ex": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _epi_p, _int, _int,
+                              _vp]),
+    "gsb_summate_incompr_ex": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _i64, _epi_p,
+                                      _int, _int, _vp]),
+    "gsb_summate_structured_ex": (_int, [_vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64, _i64, _vp,
+                                         _epi_p, _int, _int, _vp]),
+    "gsb_summate_incompr_structured_ex": (_int, [_vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64,
+                                                 _i64, _vp, _epi_p, _int, _int, _vp]),
     "gsb_summate_fourier": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _int, _int,
                                    _vp]),
     "gsb_summate_fourier_structured": (_int, [_vp, _vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64,

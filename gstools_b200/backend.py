@@ -18,6 +18,7 @@ Everything runs through ``libgsb200.so``; there is no CPU fallback.
 
 from __future__ import annotations
 
+import ctypes
 import os
 
 import numpy as np
@@ -32,6 +33,7 @@ __all__ = [
     "summate_fourier",
     "summate_fourier_structured",
     "scale_shift_",
+    "make_epilogue",
     "set_device",
     "get_device",
 ]
@@ -114,13 +116,48 @@ def _ptr(a):
     return a.ctypes.data
 
 
+def make_epilogue(scale, adds=()):
+    """Build the fused caller epilogue ``v = scale*sum; v += adds[0]; v += adds[1]; ...``.
+
+    Each entry of ``adds`` is a scalar or a per-component sequence (vector fields).  The kernels
+    round every operation separately, in this order, like the numpy passes of the reference
+    (generator.py:269-270, 561-567; normalizer/tools.py:99-103).  ``None`` means raw sums.
+    """
+    if scale is None:
+        return None
+    adds = list(adds)
+    if len(adds) > _lib.EPI_MAX_ADD:
+        raise ValueError(f"at most {_lib.EPI_MAX_ADD} additive terms can be fused")
+    epi = _lib.Epilogue()
+    epi.scale = float(scale)
+    epi.n_add = len(adds)
+    for k, a in enumerate(adds):
+        vals = np.asarray(a, dtype=np.float64).reshape(-1)
+        if vals.size not in (1, 2, 3):
+            raise ValueError("an additive term is a scalar or one value per field component")
+        for c in range(_lib.EPI_MAX_COMP):
+            epi.add[k][c] = float(vals[c] if vals.size > 1 and c < vals.size else vals[0])
+    return epi
+
+
+def _epi_ref(epilogue):
+    if epilogue is None:
+        return None
+    if not isinstance(epilogue, _lib.Epilogue):
+        epilogue = make_epilogue(*epilogue)
+    return ctypes.byref(epilogue)
+
+
 # ----------------------------------------------------------------------------------------
 # flat (unstructured) entry points -- the reference signatures
 # ----------------------------------------------------------------------------------------
-def _flat(cov_samples, z_1, z_2, pos, vec, sf=None):
+def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None):
     lib = _lib.load()
+    epi = _epi_ref(epilogue)
+    if sf is not None and epi is not None:
+        raise ValueError("summate_fourier has no fused epilogue")
     if any(_is_cuda_tensor(x) for x in (cov_samples, z_1, z_2, pos)):
-        return _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf)
+        return _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf, epi)
     cov = np.ascontiguousarray(_as_f64(cov_samples, "cov_samples"))
     z1 = np.ascontiguousarray(_as_f64(z_1, "z_1"))
     z2 = np.ascontiguousarray(_as_f64(z_2, "z_2"))
@@ -133,8 +170,8 @@ def _flat(cov_samples, z_1, z_2, pos, vec, sf=None):
     p, ld = _rows_contiguous(p)
     if vec:
         out = _empty_host((dim, n))
-        rc = lib.gsb_summate_incompr(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n,
-                                     _ptr(out), max(n, 1), _lib.MEM_HOST, get_device(), None)
+        rc = lib.gsb_summate_incompr_ex(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n,
+                                        _ptr(out), max(n, 1), epi, _lib.MEM_HOST, get_device(), None)
         _lib.check(rc, "summate_incompr")
     elif sf is not None:
         f = np.ascontiguousarray(_as_f64(sf, "spectrum_factor"))
@@ -146,13 +183,13 @@ def _flat(cov_samples, z_1, z_2, pos, vec, sf=None):
         _lib.check(rc, "summate_fourier")
     else:
         out = _empty_host((n,))
-        rc = lib.gsb_summate(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n,
-                             _ptr(out), _lib.MEM_HOST, get_device(), None)
+        rc = lib.gsb_summate_ex(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n,
+                                _ptr(out), epi, _lib.MEM_HOST, get_device(), None)
         _lib.check(rc, "summate")
     return out
 
 
-def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None):
+def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None, epi=None):
     torch = _torch()
     dev = next(x.device for x in (pos, cov_samples, z_1, z_2) if _is_cuda_tensor(x))
 
@@ -177,9 +214,9 @@ def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None):
     stream = torch.cuda.current_stream(dev).cuda_stream
     if vec:
         out = torch.empty((dim, n), dtype=torch.float64, device=dev)
-        rc = lib.gsb_summate_incompr(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(),
-                                     ld, dim, n_modes, n, out.data_ptr(), max(n, 1),
-                                     _lib.MEM_DEVICE, dev.index, stream)
+        rc = lib.gsb_summate_incompr_ex(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(),
+                                        ld, dim, n_modes, n, out.data_ptr(), max(n, 1), epi,
+                                        _lib.MEM_DEVICE, dev.index, stream)
         _lib.check(rc, "summate_incompr")
     elif sf is not None:
         f = prep(sf)
@@ -192,20 +229,24 @@ def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None):
         _lib.check(rc, "summate_fourier")
     else:
         out = torch.empty((n,), dtype=torch.float64, device=dev)
-        rc = lib.gsb_summate(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), ld,
-                             dim, n_modes, n, out.data_ptr(), _lib.MEM_DEVICE, dev.index, stream)
+        rc = lib.gsb_summate_ex(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), ld,
+                                dim, n_modes, n, out.data_ptr(), epi, _lib.MEM_DEVICE, dev.index,
+                                stream)
         _lib.check(rc, "summate")
     return out
 
 
-def summate(cov_samples, z_1, z_2, pos, num_threads=None):
-    """B200 replacement of the native ``summate`` (generator.py:42-48, math :193-199)."""
-    return _flat(cov_samples, z_1, z_2, pos, vec=False)
+def summate(cov_samples, z_1, z_2, pos, num_threads=None, *, epilogue=None):
+    """B200 replacement of the native ``summate`` (generator.py:42-48, math :193-199).
+
+    ``epilogue`` (keyword only, not in the reference): see :func:`make_epilogue`.
+    """
+    return _flat(cov_samples, z_1, z_2, pos, vec=False, epilogue=epilogue)
 
 
-def summate_incompr(cov_samples, z_1, z_2, pos, num_threads=None):
+def summate_incompr(cov_samples, z_1, z_2, pos, num_threads=None, *, epilogue=None):
     """B200 replacement of the native ``summate_incompr`` (generator.py:51-64, math :479-495)."""
-    return _flat(cov_samples, z_1, z_2, pos, vec=True)
+    return _flat(cov_samples, z_1, z_2, pos, vec=True, epilogue=epilogue)
 
 
 def summate_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads=None):
@@ -244,12 +285,13 @@ def summate_fourier_structured(spectrum_factor, modes, z_1, z_2, axes, matrix=No
 # ----------------------------------------------------------------------------------------
 # structured (rectilinear mesh) entry points -- the side channel for mesh_type="structured"
 # ----------------------------------------------------------------------------------------
-def _structured(cov_samples, z_1, z_2, axes, matrix, vec):
+def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None):
     lib = _lib.load()
+    epi = _epi_ref(epilogue)
     axes = list(axes)
     dim = len(axes)
     if any(_is_cuda_tensor(x) for x in (cov_samples, z_1, z_2, *axes)):
-        return _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec)
+        return _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi)
     cov = np.ascontiguousarray(_as_f64(cov_samples, "cov_samples"))
     z1 = np.ascontiguousarray(_as_f64(z_1, "z_1"))
     z2 = np.ascontiguousarray(_as_f64(z_2, "z_2"))
@@ -276,15 +318,15 @@ def _structured(cov_samples, z_1, z_2, axes, matrix, vec):
     n_batch, _, n_modes = cov3.shape
     full = ((n_batch,) if batched else ()) + ((dim,) if vec else ()) + shape
     out = _empty_host(full)
-    fn = lib.gsb_summate_incompr_structured if vec else lib.gsb_summate_structured
+    fn = lib.gsb_summate_incompr_structured_ex if vec else lib.gsb_summate_structured_ex
     rc = fn(_ptr(cov3), _ptr(z1b), _ptr(z2b), _ptr(cat),
-            lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch, _ptr(out),
+            lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch, _ptr(out), epi,
             _lib.MEM_HOST, get_device(), None)
     _lib.check(rc, "summate_incompr_structured" if vec else "summate_structured")
     return out
 
 
-def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec):
+def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi=None):
     torch = _torch()
     dev = next(x.device for x in (cov_samples, z_1, z_2, *axes) if _is_cuda_tensor(x))
 
@@ -315,27 +357,27 @@ def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec):
     full = ((n_batch,) if batched else ()) + ((dim,) if vec else ()) + shape
     out = torch.empty(full, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    fn = lib.gsb_summate_incompr_structured if vec else lib.gsb_summate_structured
+    fn = lib.gsb_summate_incompr_structured_ex if vec else lib.gsb_summate_structured_ex
     rc = fn(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), cat.data_ptr(),
             lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch, out.data_ptr(),
-            _lib.MEM_DEVICE, dev.index, stream)
+            epi, _lib.MEM_DEVICE, dev.index, stream)
     _lib.check(rc, "summate_incompr_structured" if vec else "summate_structured")
     return out
 
 
-def summate_structured(cov_samples, z_1, z_2, axes, matrix=None):
+def summate_structured(cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=None):
     """``summate`` on the mesh spanned by ``axes`` without the flat position array.
 
     Equals ``summate(cov_samples, z_1, z_2, matrix @ generate_grid(axes)).reshape(shape)``
     (reference: field/base.py:289-297, tools/geometric.py:340-356, covmodel/base.py:572-582).
     ``cov_samples`` may carry a leading batch axis (ensembles of mode sets on one mesh).
     """
-    return _structured(cov_samples, z_1, z_2, axes, matrix, vec=False)
+    return _structured(cov_samples, z_1, z_2, axes, matrix, vec=False, epilogue=epilogue)
 
 
-def summate_incompr_structured(cov_samples, z_1, z_2, axes, matrix=None):
+def summate_incompr_structured(cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=None):
     """Vector-field variant of :func:`summate_structured`; returns ``(dim,) + shape``."""
-    return _structured(cov_samples, z_1, z_2, axes, matrix, vec=True)
+    return _structured(cov_samples, z_1, z_2, axes, matrix, vec=True, epilogue=epilogue)
 
 
 def scale_shift_(field, scale, shift=0.0):

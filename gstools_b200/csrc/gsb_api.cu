@@ -155,6 +155,13 @@ struct Scratch {
     }
 };
 
+static int check_epilogue(const gsb_epilogue *e)
+{
+    if (e && (e->n_add < 0 || e->n_add > GSB_EPI_MAX_ADD))
+        return fail(GSB_ERR_ARGUMENT, "epilogue: n_add must be in 0..GSB_EPI_MAX_ADD");
+    return GSB_OK;
+}
+
 static int check_common(const void *cov, const void *z1, const void *z2, int dim, int64_t n_modes)
 {
     if (dim < 1 || dim > GSB_MAX_DIM) return fail(GSB_ERR_ARGUMENT, "dim must be in 1..8");
@@ -186,7 +193,8 @@ static int pack_modes(const double *d_cov, const double *d_z1, const double *d_z
 // d_recs already packed; evaluates n_pts points
 static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const double *d_pos,
                             int64_t pos_ld, int dim, bool vec, int64_t n_pts, double *d_out,
-                            int64_t out_ld, const DeviceState &dev, Scratch &scr, cudaStream_t st)
+                            int64_t out_ld, const Epi &epi, const DeviceState &dev, Scratch &scr,
+                            cudaStream_t st)
 {
     if (n_pts == 0) return GSB_OK;
     const int64_t want = 2LL * dev.sm_count;
@@ -215,6 +223,7 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
     prm.out_ld = out_ld;
     prm.n_split = n_split;
     prm.partial = nullptr;
+    prm.epi = epi;
     const int ncomp = vec ? dim : 1;
     if (n_split > 1) GSB_TRY(scr.alloc(&prm.partial, (size_t)n_split * ncomp * n_pts));
     {
@@ -223,7 +232,7 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
     }
     if (n_split > 1) {
         dim3 grid((unsigned)((n_pts + 255) / 256), (unsigned)ncomp);
-        reduce_partials_kernel<<<grid, 256, 0, st>>>(prm.partial, n_split, ncomp, n_pts, d_out, out_ld);
+        reduce_partials_kernel<<<grid, 256, 0, st>>>(prm.partial, n_split, ncomp, n_pts, d_out, out_ld, epi);
         g_launches.fetch_add(1);
         GSB_CUDA(cudaGetLastError());
     }
@@ -233,10 +242,13 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
 
 static int summate_impl(const double *cov, const double *z1, const double *z2, const double *sf,
                         const double *pos, int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts,
-                        double *out, int64_t out_ld, bool vec, int mem, int device, void *stream)
+                        double *out, int64_t out_ld, bool vec, const gsb_epilogue *epilogue, int mem,
+                        int device, void *stream)
 {
     DeviceGuard guard;
     GSB_TRY(check_common(cov, z1, z2, dim, n_modes));
+    GSB_TRY(check_epilogue(epilogue));
+    const Epi epi = make_epi(epilogue);
     if (n_pts < 0) return fail(GSB_ERR_ARGUMENT, "n_pts must be >= 0");
     if (vec && dim != 2 && dim != 3)
         return fail(GSB_ERR_ARGUMENT,
@@ -257,7 +269,7 @@ static int summate_impl(const double *cov, const double *z1, const double *z2, c
         double *d_recs = nullptr;
         int64_t pad = 0;
         GSB_TRY(pack_modes(cov, z1, z2, sf, dim, n_modes, vec, &d_recs, &pad, scr, st));
-        return direct_on_device(d_recs, pad, pos, pos_ld, dim, vec, n_pts, out, out_ld, *dev, scr, st);
+        return direct_on_device(d_recs, pad, pos, pos_ld, dim, vec, n_pts, out, out_ld, epi, *dev, scr, st);
     }
 
     // ---- host buffers: stage modes once, then pipeline point chunks over two streams ----
@@ -299,7 +311,7 @@ static int summate_impl(const double *cov, const double *z1, const double *z2, c
         const int64_t m = std::min(chunk, n_pts - i0);
         GSB_CUDA(cudaMemcpy2DAsync(d_pos[b], sizeof(double) * chunk, pos + i0, sizeof(double) * pos_ld,
                                    sizeof(double) * m, dim, cudaMemcpyHostToDevice, st));
-        GSB_TRY(direct_on_device(d_recs, pad, d_pos[b], chunk, dim, vec, m, d_out[b], chunk, *dev, s, st));
+        GSB_TRY(direct_on_device(d_recs, pad, d_pos[b], chunk, dim, vec, m, d_out[b], chunk, epi, *dev, s, st));
         GSB_CUDA(cudaMemcpy2DAsync(out + i0, sizeof(double) * (vec ? out_ld : n_pts), d_out[b],
                                    sizeof(double) * chunk, sizeof(double) * m, ncomp,
                                    cudaMemcpyDeviceToHost, st));
@@ -330,7 +342,7 @@ struct MeshInfo {
 // in between so that the A generation of one chunk overlaps the contraction of the other).
 static int structured_on_device(const double *d_cov, const double *d_z1, const double *d_z2,
                                 const double *d_sf, const double *d_axes, const MeshInfo &mesh, int64_t n_modes,
-                                int64_t n_batch, bool vec, double *d_out, double *h_out,
+                                int64_t n_batch, bool vec, const Epi &epi, double *d_out, double *h_out,
                                 DeviceState &dev, cudaStream_t st)
 {
     const int dim = mesh.dim;
@@ -369,7 +381,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
             GSB_TRY(pack_modes(d_cov + b * dim * n_modes, d_z1 + b * n_modes, d_z2 + b * n_modes,
                                d_sf ? d_sf + b * n_modes : nullptr, dim, n_modes, vec, &d_recs, &pad, scr, st));
             GSB_TRY(direct_on_device(d_recs, pad, d_pos, mesh.n, dim, vec, mesh.n,
-                                     d_out + b * ncomp * mesh.n, mesh.n, dev, scr, st));
+                                     d_out + b * ncomp * mesh.n, mesh.n, epi, dev, scr, st));
         }
         if (h_out) {
             GSB_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * n_batch * ncomp * mesh.n,
@@ -465,6 +477,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         cp.lc = lc;
         cp.out = d_out;
         cp.out_fstride = mesh.n;
+        cp.epi = epi;
         cp.ytab = tp.ytab;
         cp.ctab = ctp.ctab;
         cp.n_ytiles = n_ytiles;
@@ -590,6 +603,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     cp.lc = lc;
     cp.out = d_out;
     cp.out_fstride = mesh.n;
+    cp.epi = epi;
 
     int64_t c = 0;
     for (const Chunk &ch : chunks) {
@@ -660,11 +674,13 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
 
 static int structured_impl(const double *cov, const double *z1, const double *z2, const double *sf,
                            const double *axes, const int64_t *axis_len, const double *matrix, int dim,
-                           int64_t n_modes, int64_t n_batch, double *out, bool vec, int mem, int device,
-                           void *stream)
+                           int64_t n_modes, int64_t n_batch, double *out, bool vec,
+                           const gsb_epilogue *epilogue, int mem, int device, void *stream)
 {
     DeviceGuard guard;
     GSB_TRY(check_common(cov, z1, z2, dim, n_modes));
+    GSB_TRY(check_epilogue(epilogue));
+    const Epi epi = make_epi(epilogue);
     if (!axis_len) return fail(GSB_ERR_ARGUMENT, "axis_len must not be NULL");
     if (n_batch < 1) return fail(GSB_ERR_ARGUMENT, "n_batch must be >= 1");
     if (vec && dim != 2 && dim != 3)
@@ -718,7 +734,7 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
     if (mem == GSB_MEM_DEVICE) {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         std::lock_guard<std::mutex> lock(dev->call_mutex);
-        return structured_on_device(cov, z1, z2, sf, axes, mesh, n_modes, n_batch, vec, out, nullptr, *dev, st);
+        return structured_on_device(cov, z1, z2, sf, axes, mesh, n_modes, n_batch, vec, epi, out, nullptr, *dev, st);
     }
     std::lock_guard<std::mutex> lock(dev->call_mutex);
     cudaStream_t s0 = dev->streams[0];
@@ -740,7 +756,7 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
         GSB_CUDA(cudaMemcpyAsync(d_z2, z2, sizeof(double) * n_batch * n_modes, cudaMemcpyHostToDevice, s0));
     }
     GSB_CUDA(cudaMemcpyAsync(d_axes, axes, sizeof(double) * mesh.total_axes, cudaMemcpyHostToDevice, s0));
-    GSB_TRY(structured_on_device(d_cov, d_z1, d_z2, d_sf, d_axes, mesh, n_modes, n_batch, vec, d_out, out, *dev, s0));
+    GSB_TRY(structured_on_device(d_cov, d_z1, d_z2, d_sf, d_axes, mesh, n_modes, n_batch, vec, epi, d_out, out, *dev, s0));
     GSB_CUDA(cudaStreamSynchronize(s0));
     return GSB_OK;
 }
@@ -827,7 +843,42 @@ int gsb_summate(const double *cov_samples, const double *z_1, const double *z_2,
                 int device, void *stream)
 {
     return summate_impl(cov_samples, z_1, z_2, nullptr, pos, pos_ld, dim, n_modes, n_pts, out, n_pts,
-                        false, mem, device, stream);
+                        false, nullptr, mem, device, stream);
+}
+
+int gsb_summate_ex(const double *cov_samples, const double *z_1, const double *z_2, const double *pos,
+                   int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts, double *out,
+                   const gsb_epilogue *epi, int mem, int device, void *stream)
+{
+    return summate_impl(cov_samples, z_1, z_2, nullptr, pos, pos_ld, dim, n_modes, n_pts, out, n_pts,
+                        false, epi, mem, device, stream);
+}
+
+int gsb_summate_incompr_ex(const double *cov_samples, const double *z_1, const double *z_2,
+                           const double *pos, int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts,
+                           double *out, int64_t out_ld, const gsb_epilogue *epi, int mem, int device,
+                           void *stream)
+{
+    return summate_impl(cov_samples, z_1, z_2, nullptr, pos, pos_ld, dim, n_modes, n_pts, out, out_ld,
+                        true, epi, mem, device, stream);
+}
+
+int gsb_summate_structured_ex(const double *cov_samples, const double *z_1, const double *z_2,
+                              const double *axes, const int64_t *axis_len, const double *matrix, int dim,
+                              int64_t n_modes, int64_t n_batch, double *out, const gsb_epilogue *epi,
+                              int mem, int device, void *stream)
+{
+    return structured_impl(cov_samples, z_1, z_2, nullptr, axes, axis_len, matrix, dim, n_modes, n_batch,
+                           out, false, epi, mem, device, stream);
+}
+
+int gsb_summate_incompr_structured_ex(const double *cov_samples, const double *z_1, const double *z_2,
+                                      const double *axes, const int64_t *axis_len, const double *matrix,
+                                      int dim, int64_t n_modes, int64_t n_batch, double *out,
+                                      const gsb_epilogue *epi, int mem, int device, void *stream)
+{
+    return structured_impl(cov_samples, z_1, z_2, nullptr, axes, axis_len, matrix, dim, n_modes, n_batch,
+                           out, true, epi, mem, device, stream);
 }
 
 int gsb_summate_incompr(const double *cov_samples, const double *z_1, const double *z_2,
@@ -835,7 +886,7 @@ int gsb_summate_incompr(const double *cov_samples, const double *z_1, const doub
                         double *out, int64_t out_ld, int mem, int device, void *stream)
 {
     return summate_impl(cov_samples, z_1, z_2, nullptr, pos, pos_ld, dim, n_modes, n_pts, out, out_ld,
-                        true, mem, device, stream);
+                        true, nullptr, mem, device, stream);
 }
 
 int gsb_summate_structured(const double *cov_samples, const double *z_1, const double *z_2,
@@ -844,7 +895,7 @@ int gsb_summate_structured(const double *cov_samples, const double *z_1, const d
                            void *stream)
 {
     return structured_impl(cov_samples, z_1, z_2, nullptr, axes, axis_len, matrix, dim, n_modes, n_batch,
-                           out, false, mem, device, stream);
+                           out, false, nullptr, mem, device, stream);
 }
 
 int gsb_summate_incompr_structured(const double *cov_samples, const double *z_1, const double *z_2,
@@ -853,7 +904,7 @@ int gsb_summate_incompr_structured(const double *cov_samples, const double *z_1,
                                    int device, void *stream)
 {
     return structured_impl(cov_samples, z_1, z_2, nullptr, axes, axis_len, matrix, dim, n_modes, n_batch,
-                           out, true, mem, device, stream);
+                           out, true, nullptr, mem, device, stream);
 }
 
 int gsb_summate_fourier(const double *spectrum_factor, const double *modes, const double *z_1,
@@ -862,7 +913,7 @@ int gsb_summate_fourier(const double *spectrum_factor, const double *modes, cons
 {
     if (n_modes > 0 && !spectrum_factor) return fail(GSB_ERR_ARGUMENT, "spectrum_factor must not be NULL");
     return summate_impl(modes, z_1, z_2, spectrum_factor, pos, pos_ld, dim, n_modes, n_pts, out, n_pts,
-                        false, mem, device, stream);
+                        false, nullptr, mem, device, stream);
 }
 
 int gsb_summate_fourier_structured(const double *spectrum_factor, const double *modes, const double *z_1,
@@ -872,7 +923,7 @@ int gsb_summate_fourier_structured(const double *spectrum_factor, const double *
 {
     if (n_modes > 0 && !spectrum_factor) return fail(GSB_ERR_ARGUMENT, "spectrum_factor must not be NULL");
     return structured_impl(modes, z_1, z_2, spectrum_factor, axes, axis_len, matrix, dim, n_modes, 1, out,
-                           false, mem, device, stream);
+                           false, nullptr, mem, device, stream);
 }
 
 int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int device, void *stream)

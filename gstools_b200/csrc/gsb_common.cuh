@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstring>
 #include <string>
 
 #include "../../include/gsb200.h"
@@ -112,6 +113,39 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         ::"r"(smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused caller epilogue (gsb_epilogue in the C ABI): v = scale*sum, then + add[0][c], + add[1][c] ...
+// Separately rounded multiply and adds (no FMA contraction), so the result has the same bits as the
+// reference's numpy passes (generator.py:269-270, normalizer/tools.py:99-103) applied to the raw sum.
+// ---------------------------------------------------------------------------------------------
+struct Epi {
+    double scale;
+    double add[GSB_EPI_MAX_ADD][GSB_EPI_MAX_COMP];
+    int n_add;
+    int on;        // 0: store the raw sum
+};
+
+__device__ __forceinline__ double epi_apply(const Epi &e, double v, int comp)
+{
+    if (!e.on) return v;
+    v = __dmul_rn(e.scale, v);
+    for (int k = 0; k < e.n_add; ++k) v = __dadd_rn(v, e.add[k][comp]);
+    return v;
+}
+
+inline Epi make_epi(const gsb_epilogue *src)
+{
+    Epi e;
+    std::memset(&e, 0, sizeof e);
+    if (!src) return e;
+    e.on = 1;
+    e.scale = src->scale;
+    e.n_add = src->n_add;
+    for (int k = 0; k < GSB_EPI_MAX_ADD; ++k)
+        for (int c = 0; c < GSB_EPI_MAX_COMP; ++c) e.add[k][c] = src->add[k][c];
+    return e;
 }
 
 __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }

@@ -92,6 +92,7 @@ struct DirectParams {
     int64_t out_ld;
     int n_split;            // mode splits (gridDim.y); >1 writes partials to `partial`
     double *partial;        // (n_split, ncomp, n_pts) when n_split > 1
+    Epi epi;                // fused caller epilogue (off: raw sums)
 };
 
 // residual sin/cos on r in [-1/2, 1/2] quarter turns: returns ps = sin(pi/2 r)/r and pc = cos(pi/2 r)
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
         if (i < prm.n_pts) {
             if (prm.n_split == 1) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) prm.out[c * prm.out_ld + i] = acc[p][c];
+                for (int c = 0; c < NC; ++c) prm.out[c * prm.out_ld + i] = epi_apply(prm.epi, acc[p][c], c);
             } else {
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
@@ -230,14 +231,15 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
 
 // fixed-order reduction of mode-split partial sums (deterministic: split 0, 1, 2, ...)
 __global__ void reduce_partials_kernel(const double *__restrict__ partial, int n_split, int ncomp,
-                                       int64_t n_pts, double *__restrict__ out, int64_t out_ld)
+                                       int64_t n_pts, double *__restrict__ out, int64_t out_ld,
+                                       const Epi epi)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     if (i >= n_pts) return;
     double s = 0.0;
     for (int k = 0; k < n_split; ++k) s += partial[((int64_t)k * ncomp + c) * n_pts + i];
-    out[c * out_ld + i] = s;
+    out[c * out_ld + i] = epi_apply(epi, s, c);
 }
 
 // ---------------------------------------------------------------------------------------------

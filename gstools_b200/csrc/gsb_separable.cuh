@@ -304,6 +304,7 @@ struct ContractParams {
     int64_t ly;            // length of the last row axis
     int n_modes_pad;
     int64_t rt0;           // first (global) row tile of this launch
+    Epi epi;               // fused caller epilogue (off: raw sums)
 };
 
 __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b)
@@ -476,6 +477,15 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
         const int64_t fl = z / prm.ncomp;
         double *out = prm.out + ((prm.batch0 + fl) * prm.ncomp + comp) * prm.out_fstride;
         const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        if (prm.epi.on) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc[i][j][0] = epi_apply(prm.epi, acc[i][j][0], comp);
+                    acc[i][j][1] = epi_apply(prm.epi, acc[i][j][1], comp);
+                }
+        }
         const int64_t col0 = (int64_t)ct * SEP_TN;
         int64_t row0, row_end;                      // first row of the tile, end of its valid rows
         if (SCALED) {

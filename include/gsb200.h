@@ -40,6 +40,27 @@ extern "C" {
 #define GSB_ERR_NO_DEVICE 3
 
 #define GSB_MAX_DIM 8
+#define GSB_EPI_MAX_ADD 4
+#define GSB_EPI_MAX_COMP 3
+
+/*
+ * Fused caller epilogue.  The reference applies, on the host and
+ * one numpy pass each, to the array the native function returns:
+ *     RandMeth.__call__        sqrt(var/N) * summed + nugget          generator.py:269-270
+ *     IncomprRandMeth.__call__ mean_u*e1 + mean_u*sqrt(var/N)*summed + nugget   generator.py:561-567
+ *     apply_mean_norm_trend    field += mean; (identity normalizer); field += trend
+ *                                                                     normalizer/tools.py:99-103
+ * With a gsb_epilogue the kernels store
+ *     v = scale * sum;  v = v + add[0][c];  v = v + add[1][c]; ...  (n_add terms, c = component)
+ * with separately rounded operations in exactly this order, i.e. the bits the numpy passes give
+ * for constant nugget / mean / trend.  NULL means "raw sums" (the reference's native function).
+ */
+typedef struct gsb_epilogue {
+    double scale;
+    int32_t n_add;      /* 0..GSB_EPI_MAX_ADD */
+    int32_t reserved;
+    double add[GSB_EPI_MAX_ADD][GSB_EPI_MAX_COMP];
+} gsb_epilogue;
 
 /* Library version (major*10000 + minor*100 + patch). */
 int gsb_version(void);
@@ -99,6 +120,30 @@ int gsb_summate_incompr_structured(const double *cov_samples, const double *z_1,
                                    const int64_t *axis_len, const double *matrix, int dim,
                                    int64_t n_modes, int64_t n_batch, double *out, int mem,
                                    int device, void *stream);
+
+/*
+ * The same four entry points with the caller epilogue fused into the kernels' stores
+ * (`epi` == NULL: identical to the functions above).
+ */
+int gsb_summate_ex(const double *cov_samples, const double *z_1, const double *z_2,
+                   const double *pos, int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts,
+                   double *out, const gsb_epilogue *epi, int mem, int device, void *stream);
+
+int gsb_summate_incompr_ex(const double *cov_samples, const double *z_1, const double *z_2,
+                           const double *pos, int64_t pos_ld, int dim, int64_t n_modes,
+                           int64_t n_pts, double *out, int64_t out_ld, const gsb_epilogue *epi,
+                           int mem, int device, void *stream);
+
+int gsb_summate_structured_ex(const double *cov_samples, const double *z_1, const double *z_2,
+                              const double *axes, const int64_t *axis_len, const double *matrix,
+                              int dim, int64_t n_modes, int64_t n_batch, double *out,
+                              const gsb_epilogue *epi, int mem, int device, void *stream);
+
+int gsb_summate_incompr_structured_ex(const double *cov_samples, const double *z_1,
+                                      const double *z_2, const double *axes,
+                                      const int64_t *axis_len, const double *matrix, int dim,
+                                      int64_t n_modes, int64_t n_batch, double *out,
+                                      const gsb_epilogue *epi, int mem, int device, void *stream);
 
 /*
  * gsb_summate_fourier[_structured] -- replaces gstools_cython.field.summate_fourier /

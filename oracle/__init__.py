@@ -144,3 +144,17 @@ def summate_incompr_np(cov_samples, z_1, z_2, pos, num_threads=None):
         amp = np.cos(phase) * z1 + np.sin(phase) * z2   # (n, N)
         out[:, a:a + step] = proj @ amp.T
     return out
+
+
+def apply_epilogue(raw, scale, adds=()):
+    """numpy restatement of the caller epilogue the reference applies to the summed modes:
+    ``scale * raw`` (generator.py:269-270, 561-567), then one array pass per additive term
+    (nugget, ``field += mean``, ``field += trend``: normalizer/tools.py:99-103).  Each entry of
+    ``adds`` is a scalar or one value per component of a vector field ``(d, ...)``."""
+    out = np.float64(scale) * np.asarray(raw, dtype=np.float64)
+    for a in adds:
+        a = np.asarray(a, dtype=np.float64).reshape(-1)
+        if a.size > 1:
+            a = a.reshape((a.size,) + (1,) * (out.ndim - 1))
+        out = out + a
+    return out

@@ -176,3 +176,133 @@ def test_lazy_pre_pos_only_for_randmeth_structured(gsb):
         assert not isinstance(iso, LazyGridPos)
     finally:
         gsb.disable()
+
+
+# ---------------------------------------------------------------------------------------------
+# fused SRF call (row f2): the affine epilogue handed to the kernels must reproduce the bits of
+# the reference's numpy passes.  On CPU the backend entry points are replaced by the oracle plus
+# oracle.apply_epilogue, so this checks the plugin's host logic (which constants, which order,
+# which cases fall through), not the kernels -- those are covered by tests/test_gpu_epilogue.py.
+# ---------------------------------------------------------------------------------------------
+def _fake_backend(monkeypatch, oracle_mod, calls):
+    from gstools_b200 import backend
+
+    def unpack(epilogue):
+        if epilogue is None:
+            return None
+        n = epilogue.n_add
+        return epilogue.scale, [tuple(epilogue.add[k]) for k in range(n)]
+
+    def grid(axes, matrix):
+        g = np.array(np.meshgrid(*axes, indexing="ij")).reshape(len(axes), -1)
+        return g if matrix is None else np.dot(matrix, g)
+
+    def finish(raw, epilogue, vec):
+        e = unpack(epilogue)
+        if e is None:
+            return raw
+        d = raw.shape[0] if vec else 1
+        return oracle_mod.apply_epilogue(raw, e[0], [a[:d] if vec else a[0] for a in e[1]])
+
+    def summate(cov, z1, z2, pos, num_threads=None, *, epilogue=None):
+        calls.append(("flat", epilogue is not None))
+        return finish(oracle_mod.summate(cov, z1, z2, pos), epilogue, False)
+
+    def summate_incompr(cov, z1, z2, pos, num_threads=None, *, epilogue=None):
+        calls.append(("flat_vec", epilogue is not None))
+        return finish(oracle_mod.summate_incompr(cov, z1, z2, pos), epilogue, True)
+
+    def summate_structured(cov, z1, z2, axes, matrix=None, *, epilogue=None):
+        calls.append(("struct", epilogue is not None))
+        shape = tuple(len(a) for a in axes)
+        return finish(oracle_mod.summate(cov, z1, z2, grid(axes, matrix)), epilogue, False).reshape(shape)
+
+    def summate_incompr_structured(cov, z1, z2, axes, matrix=None, *, epilogue=None):
+        calls.append(("struct_vec", epilogue is not None))
+        shape = tuple(len(a) for a in axes)
+        raw = oracle_mod.summate_incompr(cov, z1, z2, grid(axes, matrix))
+        return finish(raw, epilogue, True).reshape((len(axes),) + shape)
+
+    for fn in (summate, summate_incompr, summate_structured, summate_incompr_structured):
+        monkeypatch.setattr(backend, fn.__name__, fn)
+
+
+FUSED_CASES = [
+    dict(kw=dict(), srf=dict()),
+    dict(kw=dict(), srf=dict(mean=1.25, trend=-0.3)),
+    dict(kw=dict(post_process=False), srf=dict(mean=1.25)),
+    dict(kw=dict(), srf=dict(generator="VectorField", mean_velocity=0.7)),
+    dict(kw=dict(), srf=dict(generator="VectorField", mean=(0.5, 0.0), mean_velocity=-1.3)),
+    dict(kw=dict(), srf=dict(generator="VectorField", mean=2.0, trend=(1.0, -1.0))),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", FUSED_CASES)
+@pytest.mark.parametrize("mesh", ["structured", "unstructured"])
+def test_fused_srf_call_matches_reference_bits(gsb, oracle_mod, monkeypatch, case, mesh):
+    gs = refharness.import_gstools()
+    model = gs.Gaussian(dim=2, var=1.7, len_scale=[4.0, 2.5], angles=0.3)
+    if mesh == "structured":
+        pos = [np.linspace(0, 10, 9), np.linspace(-5, 5, 16)]
+    else:
+        pos = np.random.RandomState(3).uniform(-5, 5, (2, 57))
+    want = gs.SRF(model, seed=198412031, mode_no=64, **case["srf"])(pos, mesh_type=mesh, **case["kw"])
+    calls = []
+    _fake_backend(monkeypatch, oracle_mod, calls)
+    gsb.enable()
+    try:
+        srf = gs.SRF(model, seed=198412031, mode_no=64, **case["srf"])
+        got = srf(pos, mesh_type=mesh, **case["kw"])
+        assert calls and all(fused for _, fused in calls), calls
+        assert got.shape == want.shape and np.array_equal(got, want)
+        assert srf.field is got and srf.field_names == ["field"]
+        # a new seed passes through the fused call like through the original (srf.py:152)
+        got2 = srf(pos, seed=7, mesh_type=mesh, **case["kw"])
+        want2 = gs.SRF(model, seed=7, mode_no=64, **case["srf"])
+        gsb.disable()
+        assert np.array_equal(got2, want2(pos, mesh_type=mesh, **case["kw"]))
+    finally:
+        gsb.disable()
+
+
+@needs_ref
+def test_fused_srf_call_falls_through_when_not_affine(gsb, oracle_mod, monkeypatch):
+    """Callable mean / trend, non-identity normalizer, nugget, upscaling and zero variance keep
+    the reference's own epilogue (the summation still runs on the backend, unfused)."""
+    gs = refharness.import_gstools()
+    pos = [np.linspace(0, 10, 7), np.linspace(-5, 5, 6)]
+    m = gs.Gaussian(dim=2, var=1.7, len_scale=3.0)
+    variants = [
+        (m, dict(mean=lambda x, y: x + y), dict()),
+        (m, dict(trend=lambda x, y: x * y), dict()),
+        (m, dict(normalizer=gs.normalizer.LogNormal()), dict()),
+        (gs.Gaussian(dim=2, var=1.7, len_scale=3.0, nugget=0.4), dict(), dict()),
+        (m, dict(upscaling="coarse_graining"), dict(point_volumes=2.0)),
+        (gs.Gaussian(dim=2, var=0.0, len_scale=3.0, nugget=0.1), dict(), dict()),
+    ]
+    for model, skw, ckw in variants:
+        want = gs.SRF(model, seed=5, mode_no=32, **skw)(pos, mesh_type="structured", **ckw)
+        calls = []
+        with monkeypatch.context() as mp:
+            _fake_backend(mp, oracle_mod, calls)
+            gsb.enable()
+            try:
+                got = gs.SRF(model, seed=5, mode_no=32, **skw)(pos, mesh_type="structured", **ckw)
+            finally:
+                gsb.disable()
+        assert not any(fused for _, fused in calls), (skw, calls)
+        assert np.array_equal(got, want), skw
+    # fused=False leaves SRF.__call__ alone
+    from gstools.field import srf as fsrf
+
+    orig = fsrf.SRF.__call__
+    gsb.enable(fused=False)
+    try:
+        assert fsrf.SRF.__call__ is orig
+    finally:
+        gsb.disable()
+    gsb.enable()
+    assert fsrf.SRF.__call__ is not orig
+    gsb.disable()
+    assert fsrf.SRF.__call__ is orig
