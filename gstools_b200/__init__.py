@@ -16,6 +16,8 @@ from . import _build, _lib
 from ._lib import (GSB200Error, device_count, get_counter, kernel_times, measure_fp64_peak,
                    set_option)
 from .backend import (
+    calc_field_krige,
+    calc_field_krige_and_variance,
     get_device,
     make_epilogue,
     scale_shift_,
@@ -38,6 +40,8 @@ __all__ = [
     "summate_incompr_structured",
     "summate_fourier",
     "summate_fourier_structured",
+    "calc_field_krige_and_variance",
+    "calc_field_krige",
     "scale_shift_",
     "make_epilogue",
     "enable",

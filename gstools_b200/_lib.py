@@ -57,6 +57,9 @@ SIGNATURES = {
                                    _vp]),
     "gsb_summate_fourier_structured": (_int, [_vp, _vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64,
                                               _vp, _int, _int, _vp]),
+    "gsb_calc_field_krige_and_variance": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _int, _int,
+                                                 _vp]),
+    "gsb_calc_field_krige": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _int, _int, _vp]),
     "gsb_scale_shift": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp]),
     "gsb_set_option": (_int, [ctypes.c_char_p, _i64]),
     "gsb_get_counter": (_i64, [ctypes.c_char_p]),

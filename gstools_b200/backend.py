@@ -32,6 +32,8 @@ __all__ = [
     "summate_incompr_structured",
     "summate_fourier",
     "summate_fourier_structured",
+    "calc_field_krige_and_variance",
+    "calc_field_krige",
     "scale_shift_",
     "make_epilogue",
     "set_device",
@@ -378,6 +380,74 @@ def summate_structured(cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=Non
 def summate_incompr_structured(cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=None):
     """Vector-field variant of :func:`summate_structured`; returns ``(dim,) + shape``."""
     return _structured(cov_samples, z_1, z_2, axes, matrix, vec=True, epilogue=epilogue)
+
+
+# ----------------------------------------------------------------------------------------
+# kriging evaluation -- the reference signatures (krige/base.py:42-61)
+# ----------------------------------------------------------------------------------------
+def _krige(krig_mat, krig_vecs, cond, want_var):
+    lib = _lib.load()
+    name = "calc_field_krige_and_variance" if want_var else "calc_field_krige"
+    if any(_is_cuda_tensor(x) for x in (krig_mat, krig_vecs, cond)):
+        torch = _torch()
+        dev = next(x.device for x in (krig_vecs, krig_mat, cond) if _is_cuda_tensor(x))
+        mat = torch.as_tensor(krig_mat, dtype=torch.float64, device=dev).contiguous()
+        c = torch.as_tensor(cond, dtype=torch.float64, device=dev).contiguous()
+        kv = torch.as_tensor(krig_vecs, dtype=torch.float64, device=dev)
+        if kv.ndim == 2 and kv.shape[1] > 0 and kv.stride(1) == 1 and kv.stride(0) >= kv.shape[1]:
+            ld = kv.stride(0)
+        else:
+            kv = kv.contiguous()
+            ld = max(kv.shape[1], 1) if kv.ndim == 2 else 1
+        if mat.ndim != 2 or mat.shape[0] != mat.shape[1] or kv.ndim != 2 or kv.shape[0] != mat.shape[0] \
+                or tuple(c.shape) != (mat.shape[0],):
+            raise ValueError("krig_mat (K, K), krig_vecs (K, n), cond (K,)")
+        size, n = mat.shape[0], kv.shape[1]
+        field = torch.empty(n, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if want_var:
+            error = torch.empty(n, dtype=torch.float64, device=dev)
+            rc = lib.gsb_calc_field_krige_and_variance(mat.data_ptr(), kv.data_ptr(), ld, c.data_ptr(),
+                                                       size, n, field.data_ptr(), error.data_ptr(),
+                                                       _lib.MEM_DEVICE, dev.index, stream)
+            _lib.check(rc, name)
+            return field, error
+        rc = lib.gsb_calc_field_krige(mat.data_ptr(), kv.data_ptr(), ld, c.data_ptr(), size, n,
+                                      field.data_ptr(), _lib.MEM_DEVICE, dev.index, stream)
+        _lib.check(rc, name)
+        return field
+    mat = np.ascontiguousarray(_as_f64(krig_mat, "krig_mat"))
+    c = np.ascontiguousarray(_as_f64(cond, "cond"))
+    kv = _as_f64(krig_vecs, "krig_vecs")
+    if mat.ndim != 2 or mat.shape[0] != mat.shape[1] or kv.ndim != 2 or kv.shape[0] != mat.shape[0] \
+            or c.shape != (mat.shape[0],):
+        raise ValueError("krig_mat (K, K), krig_vecs (K, n), cond (K,)")
+    size, n = mat.shape[0], kv.shape[1]
+    kv, ld = _rows_contiguous(kv)
+    field = np.empty(n, dtype=np.float64)
+    if want_var:
+        error = np.empty(n, dtype=np.float64)
+        rc = lib.gsb_calc_field_krige_and_variance(_ptr(mat), _ptr(kv), ld, _ptr(c), size, n,
+                                                   _ptr(field), _ptr(error), _lib.MEM_HOST,
+                                                   get_device(), None)
+        _lib.check(rc, name)
+        return field, error
+    rc = lib.gsb_calc_field_krige(_ptr(mat), _ptr(kv), ld, _ptr(c), size, n, _ptr(field),
+                                  _lib.MEM_HOST, get_device(), None)
+    _lib.check(rc, name)
+    return field
+
+
+def calc_field_krige_and_variance(krig_mat, krig_vecs, cond, num_threads=None):
+    """B200 replacement of the native ``calc_field_krige_and_variance`` (krige/base.py:51-61):
+    ``(field, error)`` with ``field = cond @ (krig_mat @ krig_vecs)`` and
+    ``error[k] = krig_vecs[:, k] @ krig_mat @ krig_vecs[:, k]``."""
+    return _krige(krig_mat, krig_vecs, cond, True)
+
+
+def calc_field_krige(krig_mat, krig_vecs, cond, num_threads=None):
+    """B200 replacement of the native ``calc_field_krige`` (krige/base.py:42-49)."""
+    return _krige(krig_mat, krig_vecs, cond, False)
 
 
 def scale_shift_(field, scale, shift=0.0):

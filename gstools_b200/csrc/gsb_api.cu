@@ -12,6 +12,7 @@
 #include "gsb_common.cuh"
 #include "gsb_direct.cuh"
 #include "gsb_separable.cuh"
+#include "gsb_krige.cuh"
 
 namespace gsb {
 
@@ -762,6 +763,183 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
 }
 
 // ---------------------------------------------------------------------------------------------
+// kriging evaluation (row f1)
+// ---------------------------------------------------------------------------------------------
+static std::atomic<int64_t> g_cnt_krige{0};
+static std::atomic<int64_t> g_opt_krige_host_chunk_mb{256};
+
+struct KrigeOperand {
+    double *w = nullptr;       // M^T cond
+    double *atile = nullptr;   // pre-tiled [L; w]
+    double *zeros = nullptr;
+    int K = 0, R = 0;
+};
+
+// d_mat (K,K), d_cond (K,) on the device
+static int krige_prepare(const double *d_mat, const double *d_cond, int K, bool want_var, KrigeOperand *op,
+                         Scratch &scr, cudaStream_t st)
+{
+    op->K = K;
+    op->R = (K + 1 + SEP_TM - 1) / SEP_TM;
+    GSB_TRY(scr.alloc(&op->w, (size_t)K));
+    krige_w_kernel<<<(K + 127) / 128, 128, 0, st>>>(d_mat, d_cond, K, op->w);
+    g_launches.fetch_add(1);
+    GSB_CUDA(cudaGetLastError());
+    if (!want_var) return GSB_OK;
+    const int64_t n_tiles = krige_tile_off(op->R);
+    GSB_TRY(scr.alloc(&op->atile, (size_t)n_tiles * SEP_A_TILE));
+    GSB_TRY(scr.alloc(&op->zeros, (size_t)SEP_TN));
+    GSB_CUDA(cudaMemsetAsync(op->zeros, 0, sizeof(double) * SEP_TN, st));
+    krige_tiles_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(d_mat, op->w, K, op->R, op->atile);
+    g_launches.fetch_add(1);
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+// d_kv (K, n) with row stride ld on the device -> d_field, d_error (n,)
+// `pad_ok`: for odd n the caller guarantees that column n of every row is readable and finite (ld > n).
+static int krige_on_device(const KrigeOperand &op, const double *d_kv, int64_t ld, int64_t n, bool pad_ok,
+                           double *d_field, double *d_error, const DeviceState &dev, Scratch &scr, cudaStream_t st)
+{
+    if (n == 0) return GSB_OK;
+    const int K = op.K;
+    if (!d_error) {
+        krige_field_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op.w, d_kv, ld, K, n, d_field);
+        g_launches.fetch_add(1);
+        GSB_CUDA(cudaGetLastError());
+        g_cnt_krige.fetch_add(1);
+        return GSB_OK;
+    }
+    KrigeParams kp;
+    std::memset(&kp, 0, sizeof kp);
+    kp.atile = op.atile;
+    kp.K = K;
+    kp.R = op.R;
+    kp.n_pairs = (op.R + 1) / 2;
+    kp.n_dstages = (K + KRG_KD - 1) / KRG_KD;
+    kp.zeros = op.zeros;
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_kv) & 15) == 0 && (ld & 1) == 0 &&
+                         ((n & 1) == 0 || (pad_ok && ld > n));
+    // column chunks: bound the partial sums (and the repack buffer when the caller's array cannot be
+    // read by 16-byte bulk copies)
+    int64_t chunk = n;
+    if (!aligned) {
+        chunk = std::max<int64_t>(SEP_TN, ((int64_t)256 << 20) / ((int64_t)K * 8) / SEP_TN * SEP_TN);
+        chunk = std::min<int64_t>(chunk, (n + 1) / 2 * 2);
+    }
+    double *d_pack = nullptr, *d_partial = nullptr;
+    if (!aligned) GSB_TRY(scr.alloc(&d_pack, (size_t)K * chunk));
+    GSB_TRY(scr.alloc(&d_partial, (size_t)kp.n_pairs * std::min<int64_t>(chunk, n)));
+    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+        const int64_t m = std::min(chunk, n - c0);
+        if (aligned) {
+            kp.kv = d_kv + c0;
+            kp.ld = ld;
+            kp.n = m;
+            kp.n_copy = (m + 1) / 2 * 2;
+        } else {
+            const int64_t m_pad = (m + 1) / 2 * 2;
+            const int blocks = (int)std::min<int64_t>(((int64_t)K * m_pad + 255) / 256, 32LL * dev.sm_count);
+            krige_repack_kernel<<<blocks, 256, 0, st>>>(d_kv + c0, ld, K, m, d_pack, m_pad);
+            g_launches.fetch_add(1);
+            GSB_CUDA(cudaGetLastError());
+            kp.kv = d_pack;
+            kp.ld = m_pad;
+            kp.n = m;
+            kp.n_copy = m_pad;   // the bulk copies read m rounded up to even: the zero padding column
+        }
+        kp.n_col_tiles = (m + SEP_TN - 1) / SEP_TN;
+        kp.partial = d_partial;
+        kp.field = d_field + c0;
+        {
+            KernelTimer timer(st);
+            GSB_TRY(launch_krige(kp, dev.sm_count, st));
+        }
+        const int blocks = (int)std::min<int64_t>((m + 255) / 256, 8LL * dev.sm_count);
+        krige_finish_kernel<<<blocks, 256, 0, st>>>(d_partial, kp.n_pairs, m, d_error + c0);
+        g_launches.fetch_add(1);
+        GSB_CUDA(cudaGetLastError());
+    }
+    g_cnt_krige.fetch_add(1);
+    return GSB_OK;
+}
+
+static int krige_impl(const double *mat, const double *kv, int64_t ld, const double *cond, int64_t K64, int64_t n,
+                      double *field, double *error, bool want_var, int mem, int device, void *stream)
+{
+    DeviceGuard guard;
+    if (K64 < 0 || K64 > (1 << 20)) return fail(GSB_ERR_ARGUMENT, "krige: K out of range");
+    if (n < 0) return fail(GSB_ERR_ARGUMENT, "krige: n must be >= 0");
+    if (mem != GSB_MEM_HOST && mem != GSB_MEM_DEVICE)
+        return fail(GSB_ERR_ARGUMENT, "mem must be GSB_MEM_HOST or GSB_MEM_DEVICE");
+    if (n == 0) return GSB_OK;
+    if (!field || (want_var && !error)) return fail(GSB_ERR_ARGUMENT, "krige: output pointers must not be NULL");
+    if (K64 > 0 && (!mat || !kv || !cond)) return fail(GSB_ERR_ARGUMENT, "krige: krig_mat, krig_vecs and cond must not be NULL");
+    if (ld < n) return fail(GSB_ERR_ARGUMENT, "krige: leading dimension smaller than n");
+    const int K = (int)K64;
+    DeviceState *dev = nullptr;
+    GSB_TRY(ensure_device(device, &dev));
+    if (K == 0) {   // empty system: both sums are empty
+        if (mem == GSB_MEM_DEVICE) {
+            cudaStream_t st = static_cast<cudaStream_t>(stream);
+            GSB_CUDA(cudaMemsetAsync(field, 0, sizeof(double) * n, st));
+            if (want_var) GSB_CUDA(cudaMemsetAsync(error, 0, sizeof(double) * n, st));
+        } else {
+            std::memset(field, 0, sizeof(double) * n);
+            if (want_var) std::memset(error, 0, sizeof(double) * n);
+        }
+        return GSB_OK;
+    }
+    if (mem == GSB_MEM_DEVICE) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        Scratch scr(st);
+        KrigeOperand op;
+        GSB_TRY(krige_prepare(mat, cond, K, want_var, &op, scr, st));
+        return krige_on_device(op, kv, ld, n, false, field, want_var ? error : nullptr, *dev, scr, st);
+    }
+    // ---- host buffers: operand once, then column chunks of krig_vecs double buffered over two streams ----
+    cudaStream_t s0 = dev->streams[0];
+    Scratch scr0(s0), scr1(dev->streams[1]);
+    double *d_mat, *d_cond;
+    GSB_TRY(scr0.alloc(&d_mat, (size_t)K * K));
+    GSB_TRY(scr0.alloc(&d_cond, (size_t)K));
+    GSB_CUDA(cudaMemcpyAsync(d_mat, mat, sizeof(double) * K * K, cudaMemcpyHostToDevice, s0));
+    GSB_CUDA(cudaMemcpyAsync(d_cond, cond, sizeof(double) * K, cudaMemcpyHostToDevice, s0));
+    KrigeOperand op;
+    GSB_TRY(krige_prepare(d_mat, d_cond, K, want_var, &op, scr0, s0));
+    GSB_CUDA(cudaEventRecord(dev->events[0], s0));
+    GSB_CUDA(cudaStreamWaitEvent(dev->streams[1], dev->events[0], 0));
+    int64_t chunk = std::max<int64_t>(SEP_TN, (g_opt_krige_host_chunk_mb.load() << 20) / ((int64_t)K * 8) / SEP_TN * SEP_TN);
+    chunk = std::min<int64_t>(chunk, (n + 1) / 2 * 2);
+    const int nbuf = n > chunk ? 2 : 1;
+    double *d_kv[2] = {nullptr, nullptr}, *d_f[2] = {nullptr, nullptr}, *d_e[2] = {nullptr, nullptr};
+    for (int b = 0; b < nbuf; ++b) {
+        Scratch &s = b ? scr1 : scr0;
+        GSB_TRY(s.alloc(&d_kv[b], (size_t)K * chunk));
+        GSB_TRY(s.alloc(&d_f[b], (size_t)chunk));
+        if (want_var) GSB_TRY(s.alloc(&d_e[b], (size_t)chunk));
+    }
+    int64_t c = 0;
+    for (int64_t c0 = 0; c0 < n; c0 += chunk, ++c) {
+        const int b = (int)(c % nbuf);
+        cudaStream_t st = dev->streams[b];
+        Scratch &s = b ? scr1 : scr0;
+        const int64_t m = std::min(chunk, n - c0);
+        if (m & 1)   // the bulk copies read an even number of columns: keep the padding column finite
+            GSB_CUDA(cudaMemset2DAsync(d_kv[b] + m, sizeof(double) * chunk, 0, sizeof(double), K, st));
+        GSB_CUDA(cudaMemcpy2DAsync(d_kv[b], sizeof(double) * chunk, kv + c0, sizeof(double) * ld, sizeof(double) * m, K,
+                                   cudaMemcpyHostToDevice, st));
+        // chunk buffers are aligned with an even row stride; an odd tail is padded with the zero column
+        GSB_TRY(krige_on_device(op, d_kv[b], chunk, m, true, d_f[b], want_var ? d_e[b] : nullptr, *dev, s, st));
+        GSB_CUDA(cudaMemcpyAsync(field + c0, d_f[b], sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+        if (want_var) GSB_CUDA(cudaMemcpyAsync(error + c0, d_e[b], sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    }
+    GSB_CUDA(cudaStreamSynchronize(dev->streams[1]));
+    GSB_CUDA(cudaStreamSynchronize(s0));
+    return GSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // epilogue + microbenchmarks
 // ---------------------------------------------------------------------------------------------
 __global__ void scale_shift_kernel(double *f, int64_t n, double scale, double shift)
@@ -926,6 +1104,19 @@ int gsb_summate_fourier_structured(const double *spectrum_factor, const double *
                            false, nullptr, mem, device, stream);
 }
 
+int gsb_calc_field_krige_and_variance(const double *krig_mat, const double *krig_vecs, int64_t vecs_ld,
+                                      const double *cond, int64_t krige_size, int64_t n_pts, double *field,
+                                      double *error, int mem, int device, void *stream)
+{
+    return krige_impl(krig_mat, krig_vecs, vecs_ld, cond, krige_size, n_pts, field, error, true, mem, device, stream);
+}
+
+int gsb_calc_field_krige(const double *krig_mat, const double *krig_vecs, int64_t vecs_ld, const double *cond,
+                         int64_t krige_size, int64_t n_pts, double *field, int mem, int device, void *stream)
+{
+    return krige_impl(krig_mat, krig_vecs, vecs_ld, cond, krige_size, n_pts, field, nullptr, false, mem, device, stream);
+}
+
 int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int device, void *stream)
 {
     if (n < 0) return fail(GSB_ERR_ARGUMENT, "n must be >= 0");
@@ -955,6 +1146,7 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "sep_path") g_opt_sep_path = value;
     else if (n == "chunk_growth_pct") g_opt_chunk_growth_pct = std::max<int64_t>(value, 100);
     else if (n == "time_kernels") g_opt_time_kernels = value;
+    else if (n == "krige_host_chunk_mb") g_opt_krige_host_chunk_mb = std::max<int64_t>(value, 1);
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);
     return GSB_OK;
 }
@@ -967,6 +1159,7 @@ int64_t gsb_get_counter(const char *name)
     if (n == "direct_calls") return g_cnt_direct.load();
     if (n == "separable_calls") return g_cnt_separable.load();
     if (n == "scaled_calls") return g_cnt_scaled.load();
+    if (n == "krige_calls") return g_cnt_krige.load();
     return -1;
 }
 

@@ -1,0 +1,404 @@
+// gsb_krige.cuh -- kriging evaluation on sm_100a.
+//
+// Replaces the native `calc_field_krige_and_variance` / `calc_field_krige` of gstools-cython /
+// gstools_core (reference: imported src/gstools/krige/base.py:16-19, 30-33; dispatched :42-61; called
+// from Krige._summate :307-317):
+//     field[k] = sum_i cond[i] (M kv)[i,k]        error[k] = sum_i kv[i,k] (M kv)[i,k]
+// with M = krig_mat (K,K), kv = krig_vecs (K,n).  The reference evaluates the full product M kv
+// (K^2 FMAs per point).  Here both results come from exact algebraic regroupings:
+//     field[k] = sum_j w[j] kv[j,k],                 w = M^T cond                       (K FMAs per point)
+//     error[k] = sum_j kv[j,k] sum_{i<=j} L[j,i] kv[i,k],   L[j,j] = M[j,j], L[j,i] = M[i,j] + M[j,i]
+// i.e. the quadratic form through a LOWER-TRIANGULAR operand: about K^2/2 FMAs per point.  The row w
+// rides along as row K of the same operand (a padding row of the last 128-row tile), so the field
+// falls out of the same contraction.  The identities hold for any M (no symmetry assumed); only the
+// rounding differs from the reference's order (tests state the bound).
+//
+// Kernels:
+//   krige_w_kernel       w = M^T cond
+//   krige_tiles_kernel   the operand [L; w] PRE-TILED in the shared-memory layout of a pipeline stage
+//                        ([row tile r][depth stage s <= 8(r+1)] -> 128 x 20 doubles), O(K^2), once per call
+//   krige_kernel         persistent, one CTA of 8 warps per SM.  Work unit = (column tile of 128 points,
+//                        pair of row tiles {R-1-p, p}): every unit costs the same (R+1)*8 depth stages, so
+//                        static striding over units is balanced.  Per stage of 16 depth indices one bulk
+//                        copy of the 20 KB operand tile plus 16 bulk copies of 1 KB -- the rows of kv
+//                        straight from the caller's row-major array into the padded B layout -- land in a
+//                        4-slot mbarrier ring.  Consumers: the DMMA.8x8x4 loop of the separable
+//                        contraction (gsb_separable.cuh).  Epilogue: multiply the accumulators with the
+//                        matching kv entries (L2 hits), reduce over rows in a fixed order (registers ->
+//                        shuffles -> shared memory), one partial per (pair, point); row K is the field.
+//   krige_finish_kernel  error[k] = sum_p partial[p][k] in ascending p (deterministic, no atomics).
+//   krige_field_kernel   `calc_field_krige` (no variance): field = w . kv, one pass over kv (HBM bound).
+#pragma once
+
+#include "gsb_separable.cuh"
+
+namespace gsb {
+
+#ifndef GSB_KRG_STAGES
+#define GSB_KRG_STAGES 5
+#endif
+constexpr int KRG_STAGES = GSB_KRG_STAGES;         // pipeline ring slots
+constexpr int KRG_STAGE_DOUBLES = SEP_A_TILE + SEP_B_TILE;
+constexpr size_t KRG_SMEM_BYTES = (size_t)KRG_STAGES * KRG_STAGE_DOUBLES * sizeof(double) + 2 * KRG_STAGES * sizeof(uint64_t) + 128;
+constexpr int KRG_KD = 2 * SEP_KC;                 // depth indices per pipeline stage (16)
+constexpr int KRG_SPT = SEP_TM / KRG_KD;           // depth stages per 128-row tile (8)
+static_assert(KRG_KD % SEP_WARPS == 0, "kv rows of a stage are split evenly over the warps");
+static_assert(SEP_TM % KRG_KD == 0, "row tile must be a whole number of depth stages");
+
+// first operand tile of row tile r (each row tile r owns KRG_SPT*(r+1) tile slots)
+__host__ __device__ inline int64_t krige_tile_off(int r) { return (int64_t)KRG_SPT * r * (r + 1) / 2; }
+
+struct KrigeParams {
+    const double *atile;    // pre-tiled operand [L; w]
+    const double *kv;       // (K, n), row stride ld; 16-byte aligned base, ld and n even
+    int64_t ld;
+    int64_t n;
+    int64_t n_copy;         // n rounded up to even: columns the bulk copies may read
+    int K;                  // kriging system size
+    int R;                  // 128-row tiles of the operand (covers rows 0..K, row K = w)
+    int n_pairs;            // (R + 1) / 2
+    int n_dstages;          // ceil(K / 16): depth stages holding real rows
+    int64_t n_col_tiles;
+    const double *zeros;    // >= SEP_TN doubles of 0.0 (source for depth rows >= K)
+    double *partial;        // (n_pairs, n)
+    double *field;          // (n,)
+};
+
+__global__ void krige_w_kernel(const double *__restrict__ mat, const double *__restrict__ cond, int K,
+                               double *__restrict__ w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    double s = 0.0;
+    for (int l = 0; l < K; ++l) s = fma(mat[(int64_t)l * K + i], cond[l], s);
+    w[i] = s;
+}
+
+// one CTA per operand tile (r, s)
+__global__ void krige_tiles_kernel(const double *__restrict__ mat, const double *__restrict__ w, int K,
+                                   int R, double *__restrict__ atile)
+{
+    int r = 0;
+    int64_t rem = blockIdx.x;
+    while (rem >= (int64_t)KRG_SPT * (r + 1)) { rem -= (int64_t)KRG_SPT * (r + 1); ++r; }
+    const int s = (int)rem;
+    double *T = atile + (krige_tile_off(r) + s) * SEP_A_TILE;
+    for (int e = threadIdx.x; e < SEP_A_TILE; e += blockDim.x) {
+        const int row = e / SEP_AST, d = e % SEP_AST;
+        const int j = r * SEP_TM + row;      // operand row
+        const int i = s * KRG_KD + d;        // depth index
+        double v = 0.0;
+        if (d < KRG_KD && i < K) {
+            if (j < K) {
+                if (i < j) v = mat[(int64_t)i * K + j] + mat[(int64_t)j * K + i];
+                else if (i == j) v = mat[(int64_t)j * K + j];
+            } else if (j == K) {
+                v = w[i];
+            }
+        }
+        T[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(SEP_THREADS, 1) krige_kernel(const KrigeParams prm)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage_base = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + KRG_STAGES * KRG_STAGE_DOUBLES);
+    uint64_t *empty = full + KRG_STAGES;
+    __shared__ double red[4][SEP_TN];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int64_t n_units = prm.n_col_tiles * prm.n_pairs;
+
+    if (tid == 0) {
+        for (int s = 0; s < KRG_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], SEP_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // cursor over (unit, half, stage); `half` 0 is the heavy row tile R-1-p, half 1 the light one p
+    struct Cursor {
+        int64_t unit;
+        int half, s, r, S;
+        int64_t c;
+    };
+    auto cur_set = [&](Cursor &q) {   // derive (c, r, S) from (unit, half)
+        q.c = q.unit / prm.n_pairs;
+        const int p = (int)(q.unit % prm.n_pairs);
+        q.r = q.half == 0 ? prm.R - 1 - p : p;
+        q.S = min(KRG_SPT * (q.r + 1), prm.n_dstages);
+    };
+    auto cur_advance = [&](Cursor &q, int64_t stride) {   // next stage; uniform over the CTA
+        if (++q.s < q.S) return;
+        q.s = 0;
+        const int p = (int)(q.unit % prm.n_pairs);
+        if (q.half == 0 && p != prm.R - 1 - p) {
+            q.half = 1;
+        } else {
+            q.half = 0;
+            q.unit += stride;
+        }
+        if (q.unit < n_units) cur_set(q);
+    };
+
+    constexpr int DEPTH = KRG_STAGES - 2;
+    Cursor pf{(int64_t)blockIdx.x, 0, 0, 0, 0, 0};
+    int pf_slot = 0;
+    uint32_t pf_round = 0;
+    if (pf.unit < n_units) cur_set(pf);
+#ifndef GSB_KRG_ISSUE
+#define GSB_KRG_ISSUE 1
+#endif
+    // Prefetch of one stage = the 20 KB operand tile + 16 kv rows of 1 KB (a bulk copy is one
+    // uniform-datapath instruction per row).  A complete_tx landing before the arrive.expect_tx is fine:
+    // the phase cannot complete before that one pending arrival.
+    //   GSB_KRG_ISSUE 1: the warp whose turn it is issues everything, one copy per lane (17 lanes)
+    //   GSB_KRG_ISSUE 2: lane 0 of every warp copies two kv rows, the turn warp adds the operand tile
+    //   GSB_KRG_ISSUE 3: lane 0 of the turn warp issues all 17 copies back to back
+    auto pf_issue = [&](bool lead) {
+        double *A = stage_base + pf_slot * KRG_STAGE_DOUBLES;
+        const int64_t col0 = pf.c * SEP_TN;
+        const uint32_t row_bytes = (uint32_t)min((int64_t)SEP_TN, prm.n_copy - col0) * sizeof(double);
+        const uint32_t tx = SEP_A_TILE * sizeof(double) + KRG_KD * row_bytes;
+        const double *asrc = prm.atile + (krige_tile_off(pf.r) + pf.s) * SEP_A_TILE;
+#if GSB_KRG_ISSUE == 1
+        if (!lead) return;
+        if (lane == 0) {
+            if (pf_round > 0) mbar_wait(&empty[pf_slot], (pf_round - 1) & 1);
+            mbar_arrive_expect_tx(&full[pf_slot], tx);
+        }
+        __syncwarp();
+        if (lane < KRG_KD) {
+            const int row = pf.s * KRG_KD + lane;
+            const double *src = row < prm.K ? prm.kv + (int64_t)row * prm.ld + col0 : prm.zeros;
+            bulk_g2s(A + SEP_A_TILE + lane * SEP_BST, src, row_bytes, &full[pf_slot]);
+        } else if (lane == KRG_KD) {
+            bulk_g2s(A, asrc, SEP_A_TILE * sizeof(double), &full[pf_slot]);
+        }
+#elif GSB_KRG_ISSUE == 2
+        if (lane != 0) return;
+        if (pf_round > 0) mbar_wait(&empty[pf_slot], (pf_round - 1) & 1);
+        if (lead) {
+            mbar_arrive_expect_tx(&full[pf_slot], tx);
+            bulk_g2s(A, asrc, SEP_A_TILE * sizeof(double), &full[pf_slot]);
+        }
+#pragma unroll
+        for (int d = 0; d < KRG_KD / SEP_WARPS; ++d) {
+            const int lr = warp * (KRG_KD / SEP_WARPS) + d;
+            const int row = pf.s * KRG_KD + lr;
+            const double *src = row < prm.K ? prm.kv + (int64_t)row * prm.ld + col0 : prm.zeros;
+            bulk_g2s(A + SEP_A_TILE + lr * SEP_BST, src, row_bytes, &full[pf_slot]);
+        }
+#else
+        if (!lead || lane != 0) return;
+        if (pf_round > 0) mbar_wait(&empty[pf_slot], (pf_round - 1) & 1);
+        mbar_arrive_expect_tx(&full[pf_slot], tx);
+        bulk_g2s(A, asrc, SEP_A_TILE * sizeof(double), &full[pf_slot]);
+        const double *src = prm.kv + (int64_t)pf.s * KRG_KD * prm.ld + col0;
+        const int nreal = min(KRG_KD, prm.K - pf.s * KRG_KD);
+#pragma unroll
+        for (int d = 0; d < KRG_KD; ++d)
+            bulk_g2s(A + SEP_A_TILE + d * SEP_BST, d < nreal ? src + (int64_t)d * prm.ld : prm.zeros, row_bytes,
+                     &full[pf_slot]);
+#endif
+    };
+    auto pf_advance = [&]() {
+        if (++pf_slot == KRG_STAGES) { pf_slot = 0; ++pf_round; }
+        cur_advance(pf, gridDim.x);
+    };
+#pragma unroll
+    for (int p = 0; p < DEPTH; ++p) {
+        if (pf.unit < n_units) {
+            pf_issue(warp == 0);
+            pf_advance();
+        }
+    }
+
+    // warp -> (32-row band wr, 64-column half wc).  In the 8 diagonal stages of a row tile the operand
+    // is zero above the diagonal, so band wr only has work in the first 2*wr + 2 of them.  Sub-partition k
+    // hosts warps k and k + 4: pairing bands (0, 3) and (1, 2) there gives every FP64 pipe the same
+    // 10 of 16 band-stages, and the diagonal block costs 5 stage times instead of 8.
+    const int wc = warp & 1;
+    const int wr = ((warp >> 1) & 1) == 0 ? ((warp >> 2) ? 3 : 0) : ((warp >> 2) ? 2 : 1);
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int a_off = (wr * 32 + g) * SEP_AST + t;
+    const int b_off = SEP_A_TILE + t * SEP_BST + wc * 64 + g;
+    const bool vec2 = (prm.ld & 1) == 0 && ((reinterpret_cast<uintptr_t>(prm.kv) & 15) == 0);
+
+    int slot = 0;
+    uint32_t round = 0;
+    int turn = 0;
+    for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int64_t c = unit / prm.n_pairs;
+        const int p = (int)(unit % prm.n_pairs);
+        const int64_t col0 = c * SEP_TN;
+        double esum[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) esum[j][0] = esum[j][1] = 0.0;
+
+        const int n_half = (p == prm.R - 1 - p) ? 1 : 2;
+        for (int half = 0; half < n_half; ++half) {
+            const int r = half == 0 ? prm.R - 1 - p : p;
+            const int S = min(KRG_SPT * (r + 1), prm.n_dstages);
+            double acc[4][8][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+            for (int s = 0; s < S; ++s) {
+                if (pf.unit < n_units) {
+                    pf_issue(warp == turn);
+                    pf_advance();
+                }
+                turn = (turn + 1) & (SEP_WARPS - 1);
+                __syncwarp();
+                mbar_wait(&full[slot], round & 1);   // also for an idle band: keeps the warps within one ring round
+                const double *Sm = stage_base + slot * KRG_STAGE_DOUBLES;
+                if (s < KRG_SPT * r + 2 * wr + 2)
+#pragma unroll
+                for (int k4 = 0; k4 < KRG_KD / 4; ++k4) {
+                    double af[4], bf[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) af[i] = Sm[a_off + i * 8 * SEP_AST + 4 * k4];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bf[j] = Sm[b_off + 4 * k4 * SEP_BST + j * 8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+                if (++slot == KRG_STAGES) { slot = 0; ++round; }
+            }
+
+            // sub-tile epilogue: acc[i][j][e] = Y[row, col] with row = 128r + 32wr + 8i + g,
+            // col = col0 + 64wc + 8j + 2t + e.  error += kv[row, col] * Y (rows < K); row K is the field.
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = r * SEP_TM + wr * 32 + i * 8 + g;
+                if (row < prm.K) {
+                    const double *kr = prm.kv + (int64_t)row * prm.ld;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
+                        double k0 = 0.0, k1 = 0.0;
+                        if (vec2 && col + 1 < prm.n) {
+                            const double2 v = *reinterpret_cast<const double2 *>(kr + col);
+                            k0 = v.x;
+                            k1 = v.y;
+                        } else {
+                            if (col < prm.n) k0 = kr[col];
+                            if (col + 1 < prm.n) k1 = kr[col + 1];
+                        }
+                        esum[j][0] = fma(k0, acc[i][j][0], esum[j][0]);
+                        esum[j][1] = fma(k1, acc[i][j][1], esum[j][1]);
+                    }
+                } else if (row == prm.K) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
+                        if (col < prm.n) prm.field[col] = acc[i][j][0];
+                        if (col + 1 < prm.n) prm.field[col + 1] = acc[i][j][1];
+                    }
+                }
+            }
+        }
+
+        // reduce over the 8 row owners of a warp (lanes with equal t), then over the 4 row bands
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double v = esum[j][e];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                esum[j][e] = v;
+            }
+        __syncthreads();   // red[] of the previous unit has been read
+        if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                red[wr][wc * 64 + j * 8 + 2 * t] = esum[j][0];
+                red[wr][wc * 64 + j * 8 + 2 * t + 1] = esum[j][1];
+            }
+        }
+        __syncthreads();
+        if (tid < SEP_TN && col0 + tid < prm.n)
+            prm.partial[(int64_t)p * prm.n + col0 + tid] = ((red[0][tid] + red[1][tid]) + red[2][tid]) + red[3][tid];
+    }
+}
+
+__global__ void krige_finish_kernel(const double *__restrict__ partial, int n_pairs, int64_t n,
+                                    double *__restrict__ error)
+{
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < n_pairs; ++p) s += partial[(int64_t)p * n + k];
+        error[k] = s;
+    }
+}
+
+// field[k] = sum_j w[j] kv[j,k]: one thread per pair of points, 4 independent row streams, coalesced
+__global__ void __launch_bounds__(256) krige_field_kernel(const double *__restrict__ w, const double *__restrict__ kv,
+                                                          int64_t ld, int K, int64_t n, double *__restrict__ field)
+{
+    __shared__ double ws[1024];
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int j0 = 0; j0 < K; j0 += 1024) {
+        const int cnt = min(1024, K - j0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) ws[e] = w[j0 + e];
+        __syncthreads();
+        if (k < n) {
+            const double *col = kv + (int64_t)j0 * ld + k;
+            int j = 0;
+            for (; j + 4 <= cnt; j += 4) {
+                s0 = fma(ws[j], col[(int64_t)j * ld], s0);
+                s1 = fma(ws[j + 1], col[(int64_t)(j + 1) * ld], s1);
+                s2 = fma(ws[j + 2], col[(int64_t)(j + 2) * ld], s2);
+                s3 = fma(ws[j + 3], col[(int64_t)(j + 3) * ld], s3);
+            }
+            for (; j < cnt; ++j) s0 = fma(ws[j], col[(int64_t)j * ld], s0);
+        }
+    }
+    if (k < n) field[k] = (s0 + s1) + (s2 + s3);
+}
+
+// aligned repack for callers whose kv is not 16-byte aligned / has odd ld or n
+__global__ void krige_repack_kernel(const double *__restrict__ src, int64_t src_ld, int K, int64_t n,
+                                    double *__restrict__ dst, int64_t dst_ld)
+{
+    const int64_t total = (int64_t)K * dst_ld;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = e / dst_ld, k = e % dst_ld;
+        dst[e] = k < n ? src[j * src_ld + k] : 0.0;
+    }
+}
+
+inline int launch_krige(const KrigeParams &kp, int sm_count, cudaStream_t st)
+{
+    static std::atomic<bool> attr_set{false};
+    if (!attr_set.load()) {
+        GSB_CUDA(cudaFuncSetAttribute(krige_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KRG_SMEM_BYTES));
+        attr_set.store(true);
+    }
+    const int64_t n_units = kp.n_col_tiles * kp.n_pairs;
+    dim3 grid((unsigned)std::min<int64_t>(n_units, sm_count));
+    krige_kernel<<<grid, SEP_THREADS, KRG_SMEM_BYTES, st>>>(kp);
+    g_launches.fetch_add(1);
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+}  // namespace gsb

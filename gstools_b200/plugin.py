@@ -103,6 +103,7 @@ def enable(lazy_grid: bool = True, fused: bool = True):
     from gstools.field import base as fbase
     from gstools.field import generator as gen
     from gstools.field import srf as fsrf
+    from gstools.krige import base as kbase
     from gstools.normalizer import Normalizer
     from gstools.tools.geometric import matrix_isometrize
 
@@ -111,7 +112,9 @@ def enable(lazy_grid: bool = True, fused: bool = True):
             _STATE.update(orig_summate=gen._summate, orig_summate_incompr=gen._summate_incompr,
                           orig_summate_fourier=gen._summate_fourier,
                           orig_pre_pos=fbase.Field.pre_pos, orig_srf_call=fsrf.SRF.__call__,
-                          gen=gen, fbase=fbase, fsrf=fsrf, config=config)
+                          orig_krige=kbase._calc_field_krige,
+                          orig_krige_var=kbase._calc_field_krige_and_variance,
+                          gen=gen, fbase=fbase, fsrf=fsrf, kbase=kbase, config=config)
         orig_s, orig_si = _STATE["orig_summate"], _STATE["orig_summate_incompr"]
         orig_sf = _STATE["orig_summate_fourier"]
         orig_pre_pos = _STATE["orig_pre_pos"]
@@ -158,6 +161,25 @@ def enable(lazy_grid: bool = True, fused: bool = True):
         gen._summate = _summate
         gen._summate_incompr = _summate_incompr
         gen._summate_fourier = _summate_fourier
+
+        # kriging evaluation (row f1): same scheme, wrappers at krige/base.py:42-61, looked up as module
+        # globals from Krige._summate (base.py:307-317)
+        orig_k, orig_kv = _STATE["orig_krige"], _STATE["orig_krige_var"]
+
+        def _calc_field_krige(krig_mat, krig_vecs, cond, num_threads=None):
+            """A wrapper function for calling the krige algorithms (B200 first)."""
+            if getattr(config, "USE_GSTOOLS_B200", False):
+                return backend.calc_field_krige(krig_mat, krig_vecs, cond, num_threads)
+            return orig_k(krig_mat, krig_vecs, cond, num_threads)
+
+        def _calc_field_krige_and_variance(krig_mat, krig_vecs, cond, num_threads=None):
+            """A wrapper function for calling the krige algorithms (B200 first)."""
+            if getattr(config, "USE_GSTOOLS_B200", False):
+                return backend.calc_field_krige_and_variance(krig_mat, krig_vecs, cond, num_threads)
+            return orig_kv(krig_mat, krig_vecs, cond, num_threads)
+
+        kbase._calc_field_krige = _calc_field_krige
+        kbase._calc_field_krige_and_variance = _calc_field_krige_and_variance
 
         if lazy_grid:
             exact = (gen.RandMeth, gen.IncomprRandMeth, gen.Fourier)
@@ -262,6 +284,8 @@ def disable():
         gen._summate = _STATE["orig_summate"]
         gen._summate_incompr = _STATE["orig_summate_incompr"]
         gen._summate_fourier = _STATE["orig_summate_fourier"]
+        _STATE["kbase"]._calc_field_krige = _STATE["orig_krige"]
+        _STATE["kbase"]._calc_field_krige_and_variance = _STATE["orig_krige_var"]
         fbase.Field.pre_pos = _STATE["orig_pre_pos"]
         _STATE["fsrf"].SRF.__call__ = _STATE["orig_srf_call"]
         config.USE_GSTOOLS_B200 = False

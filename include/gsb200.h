@@ -165,6 +165,29 @@ int gsb_summate_fourier_structured(const double *spectrum_factor, const double *
                                    void *stream);
 
 /*
+ * gsb_calc_field_krige_and_variance / gsb_calc_field_krige -- replace
+ *   gstools_cython.krige.calc_field_krige_and_variance / calc_field_krige (and the gstools_core
+ *   twins), imported at src/gstools/krige/base.py:16-19, 30-33, dispatched at base.py:42-61 and
+ *   called from Krige._summate (base.py:307-317) as fct(krig_mat, krig_vecs, cond, num_threads):
+ *     field[k] = sum_i cond[i] * (krig_mat @ krig_vecs)[i,k]
+ *     error[k] = sum_i krig_vecs[i,k] * (krig_mat @ krig_vecs)[i,k]
+ *   krig_mat  (krige_size, krige_size) row-major     the inverted kriging matrix, base.py:319-357
+ *   krig_vecs (krige_size, n_pts), row stride vecs_ld right-hand sides of one chunk, base.py:359-388
+ *   cond      (krige_size,)                           base.py:562-565
+ *   field, error (n_pts,)
+ *   Host buffers of any size are streamed through the device
+ * in column chunks (option "krige_host_chunk_mb").
+ */
+int gsb_calc_field_krige_and_variance(const double *krig_mat, const double *krig_vecs,
+                                      int64_t vecs_ld, const double *cond, int64_t krige_size,
+                                      int64_t n_pts, double *field, double *error, int mem,
+                                      int device, void *stream);
+
+int gsb_calc_field_krige(const double *krig_mat, const double *krig_vecs, int64_t vecs_ld,
+                         const double *cond, int64_t krige_size, int64_t n_pts, double *field,
+                         int mem, int device, void *stream);
+
+/*
  * Fused caller epilogue (reference: src/gstools/field/generator.py:269-270):
  *   field[i] = scale * field[i] + shift     in place, device pointers only.
  * Lets a device-resident caller keep the field on the GPU.

@@ -30,11 +30,11 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile ``liboracle.so`` with gcc (``make -C oracle``)."""
-    src = os.path.join(_HERE, "summate_oracle.c")
+    srcs = [os.path.join(_HERE, f) for f in ("summate_oracle.c", "krige_oracle.c", "Makefile")]
     if (
         force
         or not os.path.exists(_LIB_PATH)
-        or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
     ):
         subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
     return _LIB_PATH
@@ -55,6 +55,12 @@ def _load():
         lib.oracle_summate_fourier.argtypes = [dp, dp, dp, dp, dp, ctypes.c_int, ctypes.c_int64,
                                                ctypes.c_int64, dp, ctypes.c_int]
         lib.oracle_max_threads.restype = ctypes.c_int
+        i64 = ctypes.c_int64
+        lib.oracle_calc_field_krige_and_variance.restype = ctypes.c_int
+        lib.oracle_calc_field_krige_and_variance.argtypes = [dp, dp, i64, dp, i64, i64, dp, dp,
+                                                             ctypes.c_int]
+        lib.oracle_calc_field_krige.restype = ctypes.c_int
+        lib.oracle_calc_field_krige.argtypes = [dp, dp, i64, dp, i64, i64, dp, ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -158,3 +164,45 @@ def apply_epilogue(raw, scale, adds=()):
             a = a.reshape((a.size,) + (1,) * (out.ndim - 1))
         out = out + a
     return out
+
+
+def _prep_krige(krig_mat, krig_vecs, cond):
+    mat = np.ascontiguousarray(krig_mat, dtype=np.float64)
+    kv = np.ascontiguousarray(krig_vecs, dtype=np.float64)
+    c = np.ascontiguousarray(cond, dtype=np.float64)
+    if mat.ndim != 2 or mat.shape[0] != mat.shape[1] or kv.ndim != 2 or kv.shape[0] != mat.shape[0] \
+            or c.shape != (mat.shape[0],):
+        raise ValueError("oracle: krig_mat (K,K), krig_vecs (K,n), cond (K,)")
+    return mat, kv, c
+
+
+def calc_field_krige_and_variance(krig_mat, krig_vecs, cond, num_threads=None):
+    """C/OpenMP oracle of ``calc_field_krige_and_variance`` (krige/base.py:42-61, 307-317)."""
+    mat, kv, c = _prep_krige(krig_mat, krig_vecs, cond)
+    n = kv.shape[1]
+    field, error = np.zeros(n), np.zeros(n)
+    rc = _load().oracle_calc_field_krige_and_variance(_ptr(mat), _ptr(kv), max(n, 1), _ptr(c),
+                                                      mat.shape[0], n, _ptr(field), _ptr(error),
+                                                      int(num_threads or 0))
+    if rc:
+        raise RuntimeError(f"oracle_calc_field_krige_and_variance failed: {rc}")
+    return field, error
+
+
+def calc_field_krige(krig_mat, krig_vecs, cond, num_threads=None):
+    """C/OpenMP oracle of ``calc_field_krige`` (krige/base.py:42-49)."""
+    mat, kv, c = _prep_krige(krig_mat, krig_vecs, cond)
+    n = kv.shape[1]
+    field = np.zeros(n)
+    rc = _load().oracle_calc_field_krige(_ptr(mat), _ptr(kv), max(n, 1), _ptr(c), mat.shape[0], n,
+                                         _ptr(field), int(num_threads or 0))
+    if rc:
+        raise RuntimeError(f"oracle_calc_field_krige failed: {rc}")
+    return field
+
+
+def calc_field_krige_and_variance_np(krig_mat, krig_vecs, cond, num_threads=None):
+    """numpy restatement (BLAS order) used to cross-check the C build."""
+    mat, kv, c = _prep_krige(krig_mat, krig_vecs, cond)
+    mk = mat @ kv
+    return c @ mk, np.einsum("ij,ij->j", kv, mk)
