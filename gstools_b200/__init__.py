@@ -18,6 +18,8 @@ from ._lib import (GSB200Error, device_count, get_counter, kernel_times, measure
 from .backend import (
     calc_field_krige,
     calc_field_krige_and_variance,
+    cov_model_spec,
+    krige_evaluate,
     get_device,
     make_epilogue,
     scale_shift_,
@@ -42,6 +44,8 @@ __all__ = [
     "summate_fourier_structured",
     "calc_field_krige_and_variance",
     "calc_field_krige",
+    "krige_evaluate",
+    "cov_model_spec",
     "scale_shift_",
     "make_epilogue",
     "enable",

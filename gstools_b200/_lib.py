@@ -33,6 +33,19 @@ class Epilogue(ctypes.Structure):
 
 _epi_p = ctypes.POINTER(Epilogue)
 
+COV_TYPES = {"Gaussian": 1, "Exponential": 2, "Stable": 3, "Rational": 4, "Cubic": 5, "Linear": 6,
+             "Circular": 7, "Spherical": 8}
+
+
+class CovModelSpec(ctypes.Structure):
+    """``gsb_cov_model`` of include/gsb200.h."""
+
+    _fields_ = [("type", ctypes.c_int32), ("exact", ctypes.c_int32), ("var", ctypes.c_double),
+                ("len_rescaled", ctypes.c_double), ("sill", ctypes.c_double), ("param", ctypes.c_double)]
+
+
+_cov_p = ctypes.POINTER(CovModelSpec)
+
 # every symbol include/gsb200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "gsb_version": (_int, []),
@@ -60,6 +73,10 @@ SIGNATURES = {
     "gsb_calc_field_krige_and_variance": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _int, _int,
                                                  _vp]),
     "gsb_calc_field_krige": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _int, _int, _vp]),
+    "gsb_krige_evaluate": (_int, [_cov_p, _vp, _vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _int, _vp, _i64,
+                                  _vp, _vp, _int, _int, _vp]),
+    "gsb_krige_evaluate_structured": (_int, [_cov_p, _vp, _vp, _i64, _vp, _i64, _int, _vp, _c_int64_p, _vp,
+                                             _int, _vp, _i64, _vp, _vp, _int, _int, _vp]),
     "gsb_scale_shift": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp]),
     "gsb_set_option": (_int, [ctypes.c_char_p, _i64]),
     "gsb_get_counter": (_i64, [ctypes.c_char_p]),

@@ -34,6 +34,8 @@ __all__ = [
     "summate_fourier_structured",
     "calc_field_krige_and_variance",
     "calc_field_krige",
+    "krige_evaluate",
+    "cov_model_spec",
     "scale_shift_",
     "make_epilogue",
     "set_device",
@@ -448,6 +450,94 @@ def calc_field_krige_and_variance(krig_mat, krig_vecs, cond, num_threads=None):
 def calc_field_krige(krig_mat, krig_vecs, cond, num_threads=None):
     """B200 replacement of the native ``calc_field_krige`` (krige/base.py:42-49)."""
     return _krige(krig_mat, krig_vecs, cond, False)
+
+
+def cov_model_spec(kind, var, len_rescaled, sill=None, param=0.0, exact=False):
+    """``gsb_cov_model``: ``var * cor(r / len_rescaled)`` with ``cor`` the closed form of model ``kind``
+    (one of ``_lib.COV_TYPES``; src/gstools/covmodel/models.py), ``sill`` at r ~ 0 when ``exact``."""
+    if kind not in _lib.COV_TYPES:
+        raise ValueError(f"covariance model '{kind}' has no device implementation: {sorted(_lib.COV_TYPES)}")
+    spec = _lib.CovModelSpec()
+    spec.type = _lib.COV_TYPES[kind]
+    spec.exact = int(bool(exact))
+    spec.var = float(var)
+    spec.len_rescaled = float(len_rescaled)
+    spec.sill = float(var if sill is None else sill)
+    spec.param = float(param)
+    return spec
+
+
+def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=None, unbiased=True,
+                   tail_rows=None, return_var=True):
+    """The evaluation loop of ``Krige.__call__`` (krige/base.py:278-294) on the device.
+
+    The right-hand sides of ``Krige._get_krige_vecs`` (base.py:359-388) -- ``model`` evaluated at
+    the distances between ``cond_pos`` (dim, cond_no) and the evaluation points, the row of ones of
+    an unbiased system, then ``tail_rows`` (drift rows, evaluated by the caller) -- are generated
+    on the GPU and contracted with ``krig_mat`` / ``cond`` there.  Evaluation points: ``pos``
+    (dim, n), isometrised, or the mesh ``axes`` (+ isometrisation ``matrix``).  Host arrays in,
+    host arrays out.  Returns ``(field, error)`` or ``field`` (``return_var=False``); for a mesh
+    the results have the mesh shape.
+    """
+    lib = _lib.load()
+    if not isinstance(model, _lib.CovModelSpec):
+        model = cov_model_spec(**model)
+    mat = np.ascontiguousarray(_as_f64(krig_mat, "krig_mat"))
+    c = np.ascontiguousarray(_as_f64(cond, "cond"))
+    cp = np.ascontiguousarray(_as_f64(cond_pos, "cond_pos"))
+    if mat.ndim != 2 or mat.shape[0] != mat.shape[1] or c.shape != (mat.shape[0],) or cp.ndim != 2:
+        raise ValueError("krig_mat (K, K), cond (K,), cond_pos (dim, cond_no)")
+    size, (dim, cond_no) = mat.shape[0], cp.shape
+    n_tail = size - cond_no - int(bool(unbiased))
+    if n_tail < 0:
+        raise ValueError("cond_no + unbiased exceeds the kriging system size")
+    if (pos is None) == (axes is None):
+        raise ValueError("give either pos (dim, n) or axes")
+    if axes is not None:
+        ax = [np.ascontiguousarray(_as_f64(a, "axes")).reshape(-1) for a in axes]
+        if len(ax) != dim:
+            raise ValueError("number of axes must equal the dim of cond_pos")
+        lens = np.array([a.shape[0] for a in ax], dtype=np.int64)
+        shape = tuple(int(v) for v in lens)
+        n = int(np.prod(lens))
+        cat = np.ascontiguousarray(np.concatenate(ax))
+        mat_ptr = None
+        if matrix is not None:
+            m = np.ascontiguousarray(_as_f64(matrix, "matrix"))
+            if m.shape != (dim, dim):
+                raise ValueError("matrix must have shape (dim, dim)")
+            mat_ptr = _ptr(m)
+    else:
+        p = _as_f64(pos, "pos")
+        if p.ndim != 2 or p.shape[0] != dim:
+            raise ValueError("pos must have shape (dim, n) with the dim of cond_pos")
+        n = p.shape[1]
+        shape = (n,)
+        p, ld = _rows_contiguous(p)
+    tail_ptr, tail_ld = None, max(n, 1)
+    if n_tail > 0:
+        if tail_rows is None:
+            raise ValueError(f"{n_tail} drift rows expected in tail_rows")
+        tail = _as_f64(tail_rows, "tail_rows").reshape(n_tail, -1)
+        if tail.shape[1] != n:
+            raise ValueError("tail_rows must have shape (krige_size - cond_no - unbiased, n)")
+        tail, tail_ld = _rows_contiguous(tail)
+        tail_ptr = _ptr(tail)
+    field = np.empty(n, dtype=np.float64)
+    error = np.empty(n, dtype=np.float64) if return_var else None
+    err_ptr = _ptr(error) if return_var else None
+    if axes is not None:
+        rc = lib.gsb_krige_evaluate_structured(ctypes.byref(model), _ptr(mat), _ptr(c), size, _ptr(cp),
+                                               cond_no, dim, _ptr(cat), lens.ctypes.data_as(_lib._c_int64_p),
+                                               mat_ptr, int(bool(unbiased)), tail_ptr, tail_ld, _ptr(field),
+                                               err_ptr, _lib.MEM_HOST, get_device(), None)
+    else:
+        rc = lib.gsb_krige_evaluate(ctypes.byref(model), _ptr(mat), _ptr(c), size, _ptr(cp), cond_no, dim,
+                                    _ptr(p), ld, n, int(bool(unbiased)), tail_ptr, tail_ld, _ptr(field),
+                                    err_ptr, _lib.MEM_HOST, get_device(), None)
+    _lib.check(rc, "krige_evaluate")
+    field = field.reshape(shape)
+    return (field, error.reshape(shape)) if return_var else field
 
 
 def scale_shift_(field, scale, shift=0.0):

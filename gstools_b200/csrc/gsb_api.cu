@@ -853,7 +853,7 @@ static int krige_on_device(const KrigeOperand &op, const double *d_kv, int64_t l
         kp.field = d_field + c0;
         {
             KernelTimer timer(st);
-            GSB_TRY(launch_krige(kp, dev.sm_count, st));
+            GSB_TRY(launch_krige(kp, false, dev.sm_count, st));
         }
         const int blocks = (int)std::min<int64_t>((m + 255) / 256, 8LL * dev.sm_count);
         krige_finish_kernel<<<blocks, 256, 0, st>>>(d_partial, kp.n_pairs, m, d_error + c0);
@@ -935,6 +935,229 @@ static int krige_impl(const double *mat, const double *kv, int64_t ld, const dou
         if (want_var) GSB_CUDA(cudaMemcpyAsync(error + c0, d_e[b], sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     }
     GSB_CUDA(cudaStreamSynchronize(dev->streams[1]));
+    GSB_CUDA(cudaStreamSynchronize(s0));
+    return GSB_OK;
+}
+
+// ---- whole evaluation loop on the device: right-hand sides generated, then contracted ----
+struct KrigeEvalArgs {
+    const gsb_cov_model *model;
+    const double *mat, *cond, *cond_pos;
+    int64_t K, C;
+    int dim;
+    const double *pos;       // flat variant
+    int64_t pos_ld, n;
+    const double *axes;      // structured variant
+    const int64_t *axis_len;
+    const double *matrix;
+    int unbiased;
+    const double *tail;
+    int64_t tail_ld;
+    double *field, *error;
+};
+
+template <int D>
+static void launch_kvgen(const KvgenParams &gp, int n_dstages, int64_t n_ct, cudaStream_t st)
+{
+    dim3 grid((unsigned)n_dstages, (unsigned)n_ct);
+    kvgen_kernel<D><<<grid, 256, 0, st>>>(gp);
+}
+
+template <int D>
+static int launch_field_gen(const KvgenParams &gp, cudaStream_t st)
+{
+    const size_t smem = ((size_t)gp.C * D + gp.K) * sizeof(double);
+    if (smem > 200 * 1024) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: system too large for the field-only kernel");
+    GSB_CUDA(cudaFuncSetAttribute(krige_field_gen_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    krige_field_gen_kernel<D><<<(unsigned)((gp.n + 255) / 256), 256, smem, st>>>(gp);
+    return GSB_OK;
+}
+
+// all pointers on the device except axis_len / matrix (host, tiny)
+static int krige_eval_on_device(const KrigeEvalArgs &a, const MeshInfo *mesh, const DeviceState &dev, cudaStream_t st)
+{
+    const int K = (int)a.K, C = (int)a.C, D = a.dim;
+    Scratch scr(st);
+    KrigeOperand op;
+    GSB_TRY(krige_prepare(a.mat, a.cond, K, a.error != nullptr, &op, scr, st));
+    KvgenParams gp;
+    std::memset(&gp, 0, sizeof gp);
+    gp.cov.type = a.model->type;
+    gp.cov.exact = a.model->exact;
+    gp.cov.var = a.model->var;
+    gp.cov.len_rescaled = a.model->len_rescaled;
+    gp.cov.sill = a.model->sill;
+    gp.cov.param = a.model->param;
+    gp.dim = D;
+    gp.C = C;
+    gp.K = K;
+    gp.unbiased = a.unbiased ? 1 : 0;
+    gp.n_dstages = (K + KRG_KD - 1) / KRG_KD;
+    gp.cond_pos = a.cond_pos;
+    gp.pos = a.pos;
+    gp.pos_ld = a.pos_ld;
+    if (mesh) {
+        gp.axes = a.axes;
+        for (int t = 0; t < D; ++t) {
+            gp.axis_off[t] = mesh->off[t];
+            gp.axis_len[t] = mesh->len[t];
+        }
+        std::memcpy(gp.matrix, mesh->matrix, sizeof gp.matrix);
+    }
+    gp.tail = a.tail;
+    gp.tail_ld = a.tail_ld;
+    gp.w = op.w;
+    const int64_t n = a.n;
+#define GSB_KRG_DIM_SWITCH(CALL)                                                              \
+    switch (D) {                                                                              \
+    case 1: CALL(1); break;                                                                   \
+    case 2: CALL(2); break;                                                                   \
+    case 3: CALL(3); break;                                                                   \
+    case 4: CALL(4); break;                                                                   \
+    default: return fail(GSB_ERR_ARGUMENT, "krige_evaluate: dim must be in 1..4");            \
+    }
+    if (!a.error) {
+        gp.col_begin = 0;
+        gp.n = n;
+        gp.field = a.field;
+#define GSB_CALL(DD) GSB_TRY(launch_field_gen<DD>(gp, st))
+        GSB_KRG_DIM_SWITCH(GSB_CALL)
+#undef GSB_CALL
+        g_launches.fetch_add(1);
+        GSB_CUDA(cudaGetLastError());
+        g_cnt_krige.fetch_add(1);
+        return GSB_OK;
+    }
+    KrigeParams kp;
+    std::memset(&kp, 0, sizeof kp);
+    kp.atile = op.atile;
+    kp.K = K;
+    kp.R = op.R;
+    kp.n_pairs = (op.R + 1) / 2;
+    kp.n_dstages = gp.n_dstages;
+    kp.zeros = op.zeros;
+    // column chunks sized by the scratch budget (half of "scratch_mb" for the tiled right-hand sides)
+    const size_t col_tile_bytes = (size_t)gp.n_dstages * SEP_B_TILE * sizeof(double);
+    int64_t chunk_tiles = std::max<int64_t>(1, (int64_t)((size_t)g_opt_scratch_mb.load() * (1u << 20) / 2 / col_tile_bytes));
+    chunk_tiles = std::min<int64_t>(std::min<int64_t>(chunk_tiles, 65535), (n + SEP_TN - 1) / SEP_TN);
+    double *d_btile = nullptr, *d_partial = nullptr;
+    GSB_TRY(scr.alloc(&d_btile, (size_t)chunk_tiles * gp.n_dstages * SEP_B_TILE));
+    GSB_TRY(scr.alloc(&d_partial, (size_t)kp.n_pairs * chunk_tiles * SEP_TN));
+    gp.btile = d_btile;
+    kp.btile = d_btile;
+    kp.partial = d_partial;
+    for (int64_t c0 = 0; c0 < n; c0 += chunk_tiles * SEP_TN) {
+        const int64_t m = std::min<int64_t>(chunk_tiles * SEP_TN, n - c0);
+        const int64_t n_ct = (m + SEP_TN - 1) / SEP_TN;
+        gp.col_begin = c0;
+        gp.n = m;
+#define GSB_CALL(DD) launch_kvgen<DD>(gp, gp.n_dstages, n_ct, st)
+        GSB_KRG_DIM_SWITCH(GSB_CALL)
+#undef GSB_CALL
+        g_launches.fetch_add(1);
+        GSB_CUDA(cudaGetLastError());
+        kp.n = m;
+        kp.n_copy = m;
+        kp.n_col_tiles = n_ct;
+        kp.field = a.field + c0;
+        {
+            KernelTimer timer(st);
+            GSB_TRY(launch_krige(kp, true, dev.sm_count, st));
+        }
+        const int blocks = (int)std::min<int64_t>((m + 255) / 256, 8LL * dev.sm_count);
+        krige_finish_kernel<<<blocks, 256, 0, st>>>(d_partial, kp.n_pairs, m, a.error + c0);
+        g_launches.fetch_add(1);
+        GSB_CUDA(cudaGetLastError());
+    }
+#undef GSB_KRG_DIM_SWITCH
+    g_cnt_krige.fetch_add(1);
+    return GSB_OK;
+}
+
+static int krige_eval_impl(KrigeEvalArgs a, bool structured, int mem, int device, void *stream)
+{
+    DeviceGuard guard;
+    if (!a.model) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: model must not be NULL");
+    if (a.model->type < GSB_COV_GAUSSIAN || a.model->type > GSB_COV_SPHERICAL)
+        return fail(GSB_ERR_ARGUMENT, "krige_evaluate: unknown covariance model type");
+    if (!(a.model->len_rescaled > 0.0)) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: len_rescaled must be > 0");
+    if (a.dim < 1 || a.dim > 4) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: dim must be in 1..4");
+    if (a.K < 1 || a.K > (1 << 20)) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: krige_size out of range");
+    a.unbiased = a.unbiased ? 1 : 0;
+    if (a.C < 0 || a.C + a.unbiased > a.K) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: cond_no + unbiased exceeds krige_size");
+    const int64_t n_tail = a.K - a.C - a.unbiased;
+    if (!a.mat || !a.cond || (a.C > 0 && !a.cond_pos)) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: NULL input");
+    if (mem != GSB_MEM_HOST && mem != GSB_MEM_DEVICE)
+        return fail(GSB_ERR_ARGUMENT, "mem must be GSB_MEM_HOST or GSB_MEM_DEVICE");
+    MeshInfo mesh;
+    std::memset(&mesh, 0, sizeof mesh);
+    if (structured) {
+        if (!a.axis_len) return fail(GSB_ERR_ARGUMENT, "axis_len must not be NULL");
+        mesh.dim = a.dim;
+        mesh.n = 1;
+        for (int t = 0; t < a.dim; ++t) {
+            if (a.axis_len[t] < 0) return fail(GSB_ERR_ARGUMENT, "axis_len must be >= 0");
+            mesh.len[t] = a.axis_len[t];
+            mesh.off[t] = mesh.total_axes;
+            mesh.total_axes += a.axis_len[t];
+            mesh.n *= a.axis_len[t];
+        }
+        a.n = mesh.n;
+        for (int t = 0; t < a.dim; ++t)
+            for (int u = 0; u < a.dim; ++u)
+                mesh.matrix[t * a.dim + u] = a.matrix ? a.matrix[t * a.dim + u] : (t == u ? 1.0 : 0.0);
+    }
+    if (a.n < 0) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: n_pts must be >= 0");
+    if (a.n == 0) return GSB_OK;
+    if (!a.field) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: field must not be NULL");
+    if (structured ? !a.axes : (!a.pos || a.pos_ld < a.n)) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: bad positions");
+    if (n_tail > 0 && (!a.tail || a.tail_ld < a.n)) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: drift rows missing");
+    DeviceState *dev = nullptr;
+    GSB_TRY(ensure_device(device, &dev));
+    if (mem == GSB_MEM_DEVICE)
+        return krige_eval_on_device(a, structured ? &mesh : nullptr, *dev, static_cast<cudaStream_t>(stream));
+
+    cudaStream_t s0 = dev->streams[0];
+    Scratch scr(s0);
+    KrigeEvalArgs d = a;
+    double *p = nullptr;
+    auto up = [&](const double *src, size_t count, const double **dst) -> int {
+        GSB_TRY(scr.alloc(&p, count));
+        if (count) GSB_CUDA(cudaMemcpyAsync(p, src, sizeof(double) * count, cudaMemcpyHostToDevice, s0));
+        *dst = p;
+        return GSB_OK;
+    };
+    GSB_TRY(up(a.mat, (size_t)a.K * a.K, &d.mat));
+    GSB_TRY(up(a.cond, (size_t)a.K, &d.cond));
+    GSB_TRY(up(a.cond_pos, (size_t)a.dim * a.C, &d.cond_pos));
+    if (structured) {
+        GSB_TRY(up(a.axes, (size_t)mesh.total_axes, &d.axes));
+    } else {
+        double *dp = nullptr;
+        GSB_TRY(scr.alloc(&dp, (size_t)a.dim * a.n));
+        GSB_CUDA(cudaMemcpy2DAsync(dp, sizeof(double) * a.n, a.pos, sizeof(double) * a.pos_ld, sizeof(double) * a.n,
+                                   a.dim, cudaMemcpyHostToDevice, s0));
+        d.pos = dp;
+        d.pos_ld = a.n;
+    }
+    if (n_tail > 0) {
+        double *dt = nullptr;
+        GSB_TRY(scr.alloc(&dt, (size_t)n_tail * a.n));
+        GSB_CUDA(cudaMemcpy2DAsync(dt, sizeof(double) * a.n, a.tail, sizeof(double) * a.tail_ld, sizeof(double) * a.n,
+                                   n_tail, cudaMemcpyHostToDevice, s0));
+        d.tail = dt;
+        d.tail_ld = a.n;
+    }
+    double *df = nullptr, *de = nullptr;
+    GSB_TRY(scr.alloc(&df, (size_t)a.n));
+    d.field = df;
+    if (a.error) {
+        GSB_TRY(scr.alloc(&de, (size_t)a.n));
+        d.error = de;
+    }
+    GSB_TRY(krige_eval_on_device(d, structured ? &mesh : nullptr, *dev, s0));
+    GSB_CUDA(cudaMemcpyAsync(a.field, df, sizeof(double) * a.n, cudaMemcpyDeviceToHost, s0));
+    if (a.error) GSB_CUDA(cudaMemcpyAsync(a.error, de, sizeof(double) * a.n, cudaMemcpyDeviceToHost, s0));
     GSB_CUDA(cudaStreamSynchronize(s0));
     return GSB_OK;
 }
@@ -1115,6 +1338,27 @@ int gsb_calc_field_krige(const double *krig_mat, const double *krig_vecs, int64_
                          int64_t krige_size, int64_t n_pts, double *field, int mem, int device, void *stream)
 {
     return krige_impl(krig_mat, krig_vecs, vecs_ld, cond, krige_size, n_pts, field, nullptr, false, mem, device, stream);
+}
+
+int gsb_krige_evaluate(const gsb_cov_model *model, const double *krig_mat, const double *cond, int64_t krige_size,
+                       const double *cond_pos, int64_t cond_no, int dim, const double *pos, int64_t pos_ld,
+                       int64_t n_pts, int unbiased, const double *tail_rows, int64_t tail_ld, double *field,
+                       double *error, int mem, int device, void *stream)
+{
+    KrigeEvalArgs a{model, krig_mat, cond, cond_pos, krige_size, cond_no, dim, pos, pos_ld, n_pts, nullptr, nullptr,
+                    nullptr, unbiased, tail_rows, tail_ld, field, error};
+    return krige_eval_impl(a, false, mem, device, stream);
+}
+
+int gsb_krige_evaluate_structured(const gsb_cov_model *model, const double *krig_mat, const double *cond,
+                                  int64_t krige_size, const double *cond_pos, int64_t cond_no, int dim,
+                                  const double *axes, const int64_t *axis_len, const double *matrix, int unbiased,
+                                  const double *tail_rows, int64_t tail_ld, double *field, double *error, int mem,
+                                  int device, void *stream)
+{
+    KrigeEvalArgs a{model, krig_mat, cond, cond_pos, krige_size, cond_no, dim, nullptr, 0, 0, axes, axis_len,
+                    matrix, unbiased, tail_rows, tail_ld, field, error};
+    return krige_eval_impl(a, true, mem, device, stream);
 }
 
 int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int device, void *stream)

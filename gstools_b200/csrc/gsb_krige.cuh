@@ -60,6 +60,8 @@ struct KrigeParams {
     int n_dstages;          // ceil(K / 16): depth stages holding real rows
     int64_t n_col_tiles;
     const double *zeros;    // >= SEP_TN doubles of 0.0 (source for depth rows >= K)
+    const double *btile;    // TILED variant: kv pre-tiled by kvgen_kernel, tile (ct, s) = [16][SEP_BST] doubles at
+                            // ((ct * n_dstages + s) * SEP_B_TILE); rows >= K are zero
     double *partial;        // (n_pairs, n)
     double *field;          // (n,)
 };
@@ -100,6 +102,9 @@ __global__ void krige_tiles_kernel(const double *__restrict__ mat, const double 
     }
 }
 
+// TILED = false: kv is the caller's row-major array (16 row copies per stage)
+// TILED = true : kv was generated on the device, pre-tiled in the stage layout (one copy per stage)
+template <bool TILED>
 __global__ void __launch_bounds__(SEP_THREADS, 1) krige_kernel(const KrigeParams prm)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -167,6 +172,15 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) krige_kernel(const KrigeParams
         const uint32_t row_bytes = (uint32_t)min((int64_t)SEP_TN, prm.n_copy - col0) * sizeof(double);
         const uint32_t tx = SEP_A_TILE * sizeof(double) + KRG_KD * row_bytes;
         const double *asrc = prm.atile + (krige_tile_off(pf.r) + pf.s) * SEP_A_TILE;
+        if (TILED) {
+            if (!lead || lane != 0) return;
+            if (pf_round > 0) mbar_wait(&empty[pf_slot], (pf_round - 1) & 1);
+            mbar_arrive_expect_tx(&full[pf_slot], (SEP_A_TILE + SEP_B_TILE) * sizeof(double));
+            bulk_g2s(A, asrc, SEP_A_TILE * sizeof(double), &full[pf_slot]);
+            bulk_g2s(A + SEP_A_TILE, prm.btile + (pf.c * prm.n_dstages + pf.s) * SEP_B_TILE,
+                     SEP_B_TILE * sizeof(double), &full[pf_slot]);
+            return;
+        }
 #if GSB_KRG_ISSUE == 1
         if (!lead) return;
         if (lane == 0) {
@@ -286,12 +300,18 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) krige_kernel(const KrigeParams
             for (int i = 0; i < 4; ++i) {
                 const int row = r * SEP_TM + wr * 32 + i * 8 + g;
                 if (row < prm.K) {
-                    const double *kr = prm.kv + (int64_t)row * prm.ld;
+                    const double *kr = TILED
+                        ? prm.btile + ((c * prm.n_dstages + row / KRG_KD) * KRG_KD + row % KRG_KD) * SEP_BST - col0
+                        : prm.kv + (int64_t)row * prm.ld;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
                         double k0 = 0.0, k1 = 0.0;
-                        if (vec2 && col + 1 < prm.n) {
+                        if (TILED) {   // padded tile rows: always readable, 16-byte aligned
+                            const double2 v = *reinterpret_cast<const double2 *>(kr + col);
+                            k0 = v.x;
+                            k1 = v.y;
+                        } else if (vec2 && col + 1 < prm.n) {
                             const double2 v = *reinterpret_cast<const double2 *>(kr + col);
                             k0 = v.x;
                             k1 = v.y;
@@ -386,19 +406,187 @@ __global__ void krige_repack_kernel(const double *__restrict__ src, int64_t src_
     }
 }
 
-inline int launch_krige(const KrigeParams &kp, int sm_count, cudaStream_t st)
+inline int launch_krige(const KrigeParams &kp, bool tiled, int sm_count, cudaStream_t st)
 {
     static std::atomic<bool> attr_set{false};
     if (!attr_set.load()) {
-        GSB_CUDA(cudaFuncSetAttribute(krige_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KRG_SMEM_BYTES));
+        GSB_CUDA(cudaFuncSetAttribute(krige_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KRG_SMEM_BYTES));
+        GSB_CUDA(cudaFuncSetAttribute(krige_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KRG_SMEM_BYTES));
         attr_set.store(true);
     }
     const int64_t n_units = kp.n_col_tiles * kp.n_pairs;
     dim3 grid((unsigned)std::min<int64_t>(n_units, sm_count));
-    krige_kernel<<<grid, SEP_THREADS, KRG_SMEM_BYTES, st>>>(kp);
+    if (tiled) krige_kernel<true><<<grid, SEP_THREADS, KRG_SMEM_BYTES, st>>>(kp);
+    else krige_kernel<false><<<grid, SEP_THREADS, KRG_SMEM_BYTES, st>>>(kp);
     g_launches.fetch_add(1);
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// right-hand sides on the device (reference: Krige._get_krige_vecs, krige/base.py:359-388):
+//   rows 0..C-1      cov(|x_cond_i - x_k|)  with cdist on the isometrised positions (base.py:430-450) and
+//                    CovModel.covariance / cov_nugget (covmodel/tools.py:65-76, covmodel/base.py:313-320)
+//   row  C           1 when the system is unbiased (base.py:377-378)
+//   rows after that  drift rows supplied by the caller (functional and external drift, base.py:379-387)
+// ---------------------------------------------------------------------------------------------
+struct CovParams {
+    int type;             // GSB_COV_*
+    int exact;            // cov_nugget instead of covariance (Krige.exact)
+    double var, len_rescaled, sill, param;
+};
+
+// normalised correlation cor(h) of the supported models (src/gstools/covmodel/models.py)
+__device__ __forceinline__ double cov_cor(const CovParams &m, double h)
+{
+    switch (m.type) {
+    case GSB_COV_GAUSSIAN: return exp(-(h * h));                                        // models.py:139-141
+    case GSB_COV_EXPONENTIAL: return exp(-h);                                           // models.py:213-215
+    case GSB_COV_STABLE: return exp(-pow(h, m.param));                                  // models.py:343-345
+    case GSB_COV_RATIONAL: return pow(1.0 + h * h / m.param, -m.param);                 // models.py:610-612
+    case GSB_COV_CUBIC: {                                                               // models.py:654-657
+        const double x = fmin(h, 1.0), x2 = x * x, x3 = x2 * x;
+        return (((1.0 - 7.0 * x2) + 8.75 * x3) - 3.5 * (x3 * x2)) + 0.75 * (x3 * x2 * x2);
+    }
+    case GSB_COV_LINEAR: return fmax(1.0 - h, 0.0);                                     // models.py:687-689
+    case GSB_COV_CIRCULAR:                                                              // models.py:728-738
+        return h < 1.0 ? 2.0 / 3.141592653589793 * (acos(h) - h * sqrt(1.0 - h * h)) : 0.0;
+    case GSB_COV_SPHERICAL: {                                                           // models.py:774-777
+        const double x = fmin(h, 1.0);
+        return (1.0 - 1.5 * x) + 0.5 * (x * x * x);
+    }
+    default: return 0.0;
+    }
+}
+
+__device__ __forceinline__ double cov_value(const CovParams &m, double r)
+{
+    // cov_nugget: np.isclose(r, 0) <=> |r| <= 1e-8 -> sill (covmodel/base.py:313-320)
+    if (m.exact && r <= 1e-8) return m.sill;
+    return m.var * cov_cor(m, r / m.len_rescaled);
+}
+
+struct KvgenParams {
+    CovParams cov;
+    int dim;
+    int C;                 // conditioning points (covariance rows)
+    int K;                 // kriging system size
+    int unbiased;
+    int n_dstages;
+    const double *cond_pos;    // (dim, C) isometrised
+    // evaluation points of this column chunk: flat (dim, n) with row stride pos_ld, or a structured mesh
+    const double *pos;
+    int64_t pos_ld;
+    const double *axes;        // structured: concatenated axes + matrix (as ExpandParams)
+    int64_t axis_off[GSB_MAX_DIM];
+    int64_t axis_len[GSB_MAX_DIM];
+    double matrix[GSB_MAX_DIM * GSB_MAX_DIM];
+    int64_t col_begin;         // first point of this chunk (global index)
+    int64_t n;                 // points in this chunk
+    const double *tail;        // (K - C - unbiased, n_total) drift rows, row stride tail_ld; indexed globally
+    int64_t tail_ld;
+    double *btile;             // out: pre-tiled chunk (TILED layout)
+    const double *w;           // field-only kernel: M^T cond
+    double *field;
+};
+
+template <int D>
+__device__ __forceinline__ void kvgen_point(const KvgenParams &prm, int64_t gcol, double (&x)[D])
+{
+    if (prm.pos) {
+#pragma unroll
+        for (int t = 0; t < D; ++t) x[t] = prm.pos[t * prm.pos_ld + gcol];
+    } else {   // generate_grid + isometrize on the fly (geometric.py:340-356, covmodel/base.py:572-582)
+        double gpt[D];
+        int64_t rem = gcol;
+#pragma unroll
+        for (int t = D - 1; t >= 0; --t) {
+            const int64_t it = rem % prm.axis_len[t];
+            rem /= prm.axis_len[t];
+            gpt[t] = prm.axes[prm.axis_off[t] + it];
+        }
+#pragma unroll
+        for (int t = 0; t < D; ++t) {
+            double v = 0.0;
+#pragma unroll
+            for (int u = 0; u < D; ++u) v += prm.matrix[t * D + u] * gpt[u];
+            x[t] = v;
+        }
+    }
+}
+
+template <int D>
+__device__ __forceinline__ double kvgen_entry(const KvgenParams &prm, int row, int64_t gcol, const double (&x)[D],
+                                              const double *cpos /* [D] of this row, or nullptr */)
+{
+    if (row < prm.C) {
+        double s2 = 0.0;
+#pragma unroll
+        for (int t = 0; t < D; ++t) {
+            const double dlt = __dsub_rn(cpos[t], x[t]);
+            s2 = __dadd_rn(s2, __dmul_rn(dlt, dlt));     // scipy cdist: plain sum of squares, then sqrt
+        }
+        return cov_value(prm.cov, sqrt(s2));
+    }
+    if (row < prm.C + prm.unbiased) return 1.0;
+    if (row < prm.K) return prm.tail[(int64_t)(row - prm.C - prm.unbiased) * prm.tail_ld + gcol];
+    return 0.0;
+}
+
+// one CTA per (column tile, depth stage): 16 rows x 128 points, written in the stage layout
+template <int D>
+__global__ void __launch_bounds__(256) kvgen_kernel(const KvgenParams prm)
+{
+    __shared__ double cp[KRG_KD][D];
+    const int s = blockIdx.x;
+    const int64_t ct = blockIdx.y;
+    for (int e = threadIdx.x; e < KRG_KD * D; e += blockDim.x) {
+        const int d = e / D, t = e % D, row = s * KRG_KD + d;
+        cp[d][t] = row < prm.C ? prm.cond_pos[(int64_t)t * prm.C + row] : 0.0;
+    }
+    __syncthreads();
+    const int cl = threadIdx.x % SEP_TN;
+    const int64_t lcol = ct * SEP_TN + cl;
+    double *T = prm.btile + (ct * prm.n_dstages + s) * SEP_B_TILE;
+    double x[D];
+    const bool live = lcol < prm.n;
+    if (live) kvgen_point<D>(prm, prm.col_begin + lcol, x);
+#pragma unroll
+    for (int i = 0; i < KRG_KD / 2; ++i) {
+        const int d = threadIdx.x / SEP_TN + 2 * i;
+        const int row = s * KRG_KD + d;
+        T[d * SEP_BST + cl] = live ? kvgen_entry<D>(prm, row, prm.col_begin + lcol, x, cp[d]) : 0.0;
+    }
+    if (threadIdx.x < KRG_KD * (SEP_BST - SEP_TN)) {   // the 4 padding doubles of every row
+        const int d = threadIdx.x / (SEP_BST - SEP_TN), q = threadIdx.x % (SEP_BST - SEP_TN);
+        T[d * SEP_BST + SEP_TN + q] = 0.0;
+    }
+}
+
+// field only (return_var = False): field[k] = sum_row w[row] kv[row, k] with kv generated on the fly
+template <int D>
+__global__ void __launch_bounds__(256) krige_field_gen_kernel(const KvgenParams prm)
+{
+    extern __shared__ double sm[];     // [C][D] conditioning positions, then w[K]
+    double *cps = sm, *ws = sm + (size_t)prm.C * D;
+    for (int e = threadIdx.x; e < prm.C * D; e += blockDim.x) {
+        const int row = e / D, t = e % D;
+        cps[e] = prm.cond_pos[(int64_t)t * prm.C + row];
+    }
+    for (int e = threadIdx.x; e < prm.K; e += blockDim.x) ws[e] = prm.w[e];
+    __syncthreads();
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= prm.n) return;
+    double x[D];
+    kvgen_point<D>(prm, prm.col_begin + k, x);
+    double s0 = 0.0, s1 = 0.0;
+    int row = 0;
+    for (; row + 2 <= prm.K; row += 2) {
+        s0 = fma(ws[row], kvgen_entry<D>(prm, row, prm.col_begin + k, x, cps + (size_t)row * D), s0);
+        s1 = fma(ws[row + 1], kvgen_entry<D>(prm, row + 1, prm.col_begin + k, x, cps + (size_t)(row + 1) * D), s1);
+    }
+    if (row < prm.K) s0 = fma(ws[row], kvgen_entry<D>(prm, row, prm.col_begin + k, x, cps + (size_t)row * D), s0);
+    prm.field[k] = s0 + s1;
 }
 
 }  // namespace gsb

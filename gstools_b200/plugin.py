@@ -23,7 +23,13 @@ at call time (generator.py:266, :554), so rebinding them takes effect for existi
     accumulators before they are stored, with separately rounded operations in the reference's
     order (same bits as the numpy passes).  The field then crosses PCIe once and no host pass
     touches it: for the 512^3 mesh the reference's epilogue is five passes over 1 GB (~1.7 s)
-    after a 21 ms summation.  Every other case falls through to the reference's own code.
+    after a 21 ms summation.  Every other case falls through to the reference's own code;
+  * rebinds the kriging wrappers ``_calc_field_krige[_and_variance]`` (krige/base.py:42-61) the same
+    way (row f1), and -- with ``fused=True`` -- wraps ``Krige.__call__`` (krige/base.py:220-300): for
+    the covariance models with a device implementation the right-hand sides of every chunk
+    (``Krige._get_krige_vecs``: cdist + covariance, K x n doubles built on the host by the reference)
+    are generated on the GPU and contracted there, so that CondSRF / Krige calls on large meshes no
+    longer build and ship gigabytes of right-hand sides.
 """
 
 from __future__ import annotations
@@ -33,7 +39,7 @@ import weakref
 
 import numpy as np
 
-from . import backend
+from . import _lib, backend
 
 __all__ = ["enable", "disable", "is_enabled", "LazyGridPos"]
 
@@ -112,7 +118,7 @@ def enable(lazy_grid: bool = True, fused: bool = True):
             _STATE.update(orig_summate=gen._summate, orig_summate_incompr=gen._summate_incompr,
                           orig_summate_fourier=gen._summate_fourier,
                           orig_pre_pos=fbase.Field.pre_pos, orig_srf_call=fsrf.SRF.__call__,
-                          orig_krige=kbase._calc_field_krige,
+                          orig_krige=kbase._calc_field_krige, orig_krige_call=kbase.Krige.__call__,
                           orig_krige_var=kbase._calc_field_krige_and_variance,
                           gen=gen, fbase=fbase, fsrf=fsrf, kbase=kbase, config=config)
         orig_s, orig_si = _STATE["orig_summate"], _STATE["orig_summate_incompr"]
@@ -271,6 +277,72 @@ def enable(lazy_grid: bool = True, fused: bool = True):
 
         srf_call.__doc__ = orig_srf_call.__doc__
         fsrf.SRF.__call__ = srf_call if fused else orig_srf_call
+
+        orig_krige_call = _STATE["orig_krige_call"]
+        from gstools.covmodel import models as cmodels
+
+        device_models = {getattr(cmodels, name): name for name in _lib.COV_TYPES if hasattr(cmodels, name)}
+
+        def _cov_spec(krige):
+            """gsb_cov_model of ``krige.model`` (exact class only: a subclass may override cor)."""
+            model = krige.model
+            kind = device_models.get(type(model))
+            if kind is None or model.latlon or getattr(model, "temporal", False) or model.dim > 4:
+                return None
+            param = float(getattr(model, "alpha", 0.0)) if kind in ("Stable", "Rational") else 0.0
+            return backend.cov_model_spec(kind, model.var, model.len_rescaled, model.sill, param, krige.exact)
+
+        def krige_call(self, pos=None, mesh_type="unstructured", ext_drift=None, chunk_size=None,
+                       only_mean=False, return_var=True, post_process=True, store=True):
+            spec = None
+            if getattr(config, "USE_GSTOOLS_B200", False) and not only_mean and self.cond_no > 0:
+                spec = _cov_spec(self)
+            if spec is None:
+                return orig_krige_call(self, pos, mesh_type, ext_drift, chunk_size, only_mean,
+                                       return_var, post_process, store)
+            fld_cnt = 2 if return_var else 1
+            name, save = self.get_store_config(store, None, fld_cnt)       # base.py:264-267
+            # positions: keep a structured mesh as axes + isometrisation matrix (no host expansion)
+            # unless functional drift terms need the expanded positions (base.py:379-383)
+            if pos is not None:
+                self.set_pos(pos, mesh_type)
+            elif self.pos is None:
+                raise ValueError("Field: no position tuple 'pos' present")
+            lazy = self.mesh_type != "unstructured" and self.int_drift_no == 0
+            if lazy:
+                shape = self.field_shape
+                pnt_cnt = int(np.prod(shape))
+                iso_pos = None
+            else:
+                iso_pos, shape = orig_pre_pos(self, None, self.mesh_type)
+                pnt_cnt = len(iso_pos[0])
+            ext_drift = self._pre_ext_drift(pnt_cnt, ext_drift)               # base.py:279
+            tail = []
+            if self.int_drift_no > 0:
+                chunk_pos = self.model.anisometrize(iso_pos)
+                tail += [np.asarray(f(*chunk_pos), dtype=np.double).reshape(-1) for f in self.drift_functions]
+            if self.ext_drift_no > 0:
+                tail += list(np.asarray(ext_drift, dtype=np.double).reshape(self.ext_drift_no, -1))
+            tail_rows = np.ascontiguousarray(tail) if tail else None
+            kwargs = dict(unbiased=self.unbiased, tail_rows=tail_rows, return_var=return_var)
+            if lazy:
+                matrix = matrix_isometrize(self.model.dim, self.model.angles, self.model.anis)
+                out = backend.krige_evaluate(spec, self._krige_mat, self._krige_cond, self._krige_pos,
+                                             axes=self.pos, matrix=matrix, **kwargs)
+            else:
+                out = backend.krige_evaluate(spec, self._krige_mat, self._krige_cond, self._krige_pos,
+                                             pos=iso_pos, **kwargs)
+            field, krige_var = out if return_var else (out, None)
+            field = np.reshape(field, shape)
+            field = self.post_field(field, name[0], post_process, save[0])
+            if return_var:                                                    # base.py:296-300
+                krige_var = np.reshape(np.maximum(self.model.sill - krige_var, 0), shape)
+                krige_var = self.post_field(krige_var, name[1], False, save[1])
+                return field, krige_var
+            return field
+
+        krige_call.__doc__ = orig_krige_call.__doc__
+        kbase.Krige.__call__ = krige_call if fused else orig_krige_call
         _STATE["enabled"] = True
     return gstools
 
@@ -288,5 +360,6 @@ def disable():
         _STATE["kbase"]._calc_field_krige_and_variance = _STATE["orig_krige_var"]
         fbase.Field.pre_pos = _STATE["orig_pre_pos"]
         _STATE["fsrf"].SRF.__call__ = _STATE["orig_srf_call"]
+        _STATE["kbase"].Krige.__call__ = _STATE["orig_krige_call"]
         config.USE_GSTOOLS_B200 = False
         _STATE["enabled"] = False

@@ -188,6 +188,54 @@ int gsb_calc_field_krige(const double *krig_mat, const double *krig_vecs, int64_
                          int mem, int device, void *stream);
 
 /*
+ * gsb_krige_evaluate[_structured] -- the whole evaluation loop of Krige.__call__
+ * (src/gstools/krige/base.py:278-294) on the device: the right-hand sides of
+ * Krige._get_krige_vecs (base.py:359-388) are generated there instead of being built on the host
+ * (cdist + covariance: K x n doubles, 16.8 GB for 1000 conditioning points on a 128^3 mesh) and are
+ * contracted straight away as above.
+ *   model      covariance model: var * cor(r / len_rescaled), or `sill` at r ~ 0 when `exact`
+ *              (CovModel.covariance / cov_nugget, covmodel/tools.py:65-76, covmodel/base.py:313-320);
+ *              `type` selects cor(h) among the closed forms of covmodel/models.py
+ *   cond_pos   (dim, cond_no) isometrised conditioning positions (Krige._krige_pos, base.py:584)
+ *   pos        (dim, n_pts) isometrised evaluation positions, row stride pos_ld    [flat variant]
+ *   axes, axis_len, matrix   structured mesh as in gsb_summate_structured          [structured variant]
+ *   unbiased   1: row cond_no of the right-hand side is all ones (base.py:377-378)
+ *   tail_rows  (krige_size - cond_no - unbiased, n_pts), row stride tail_ld: functional and external
+ *              drift rows evaluated by the caller (base.py:379-387); NULL when there are none
+ *   error      NULL: field only (return_var=False)
+ */
+#define GSB_COV_GAUSSIAN 1
+#define GSB_COV_EXPONENTIAL 2
+#define GSB_COV_STABLE 3      /* param = alpha */
+#define GSB_COV_RATIONAL 4    /* param = alpha */
+#define GSB_COV_CUBIC 5
+#define GSB_COV_LINEAR 6
+#define GSB_COV_CIRCULAR 7
+#define GSB_COV_SPHERICAL 8
+
+typedef struct gsb_cov_model {
+    int32_t type;
+    int32_t exact;
+    double var;
+    double len_rescaled;
+    double sill;
+    double param;
+} gsb_cov_model;
+
+int gsb_krige_evaluate(const gsb_cov_model *model, const double *krig_mat, const double *cond,
+                       int64_t krige_size, const double *cond_pos, int64_t cond_no, int dim,
+                       const double *pos, int64_t pos_ld, int64_t n_pts, int unbiased,
+                       const double *tail_rows, int64_t tail_ld, double *field, double *error,
+                       int mem, int device, void *stream);
+
+int gsb_krige_evaluate_structured(const gsb_cov_model *model, const double *krig_mat,
+                                  const double *cond, int64_t krige_size, const double *cond_pos,
+                                  int64_t cond_no, int dim, const double *axes,
+                                  const int64_t *axis_len, const double *matrix, int unbiased,
+                                  const double *tail_rows, int64_t tail_ld, double *field,
+                                  double *error, int mem, int device, void *stream);
+
+/*
  * Fused caller epilogue (reference: src/gstools/field/generator.py:269-270):
  *   field[i] = scale * field[i] + shift     in place, device pointers only.
  * Lets a device-resident caller keep the field on the GPU.

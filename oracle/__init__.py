@@ -206,3 +206,62 @@ def calc_field_krige_and_variance_np(krig_mat, krig_vecs, cond, num_threads=None
     mat, kv, c = _prep_krige(krig_mat, krig_vecs, cond)
     mk = mat @ kv
     return c @ mk, np.einsum("ij,ij->j", kv, mk)
+
+
+# ---------------------------------------------------------------------------------------------
+# right-hand sides of the kriging system (numpy restatement of Krige._get_krige_vecs)
+# ---------------------------------------------------------------------------------------------
+def cov_cor_np(kind, h, param=0.0):
+    """Normalised correlation ``cor(h)`` of the models with a device implementation, restated from
+    src/gstools/covmodel/models.py (Gaussian :139-141, Exponential :213-215, Stable :343-345,
+    Rational :610-612, Cubic :654-657, Linear :687-689, Circular :728-738, Spherical :774-777)."""
+    h = np.asarray(np.abs(h), dtype=np.float64)
+    if kind == "Gaussian":
+        return np.exp(-(h**2))
+    if kind == "Exponential":
+        return np.exp(-h)
+    if kind == "Stable":
+        return np.exp(-np.power(h, param))
+    if kind == "Rational":
+        return np.power(1 + h**2 / param, -param)
+    if kind == "Cubic":
+        h = np.minimum(h, 1.0)
+        return 1.0 - 7 * h**2 + 8.75 * h**3 - 3.5 * h**5 + 0.75 * h**7
+    if kind == "Linear":
+        return np.maximum(1 - h, 0.0)
+    if kind == "Circular":
+        res = np.zeros_like(h)
+        lo = h < 1.0
+        hl = h[lo]
+        res[lo] = 2 / np.pi * (np.arccos(hl) - hl * np.sqrt(1 - hl**2))
+        return res
+    if kind == "Spherical":
+        h = np.minimum(h, 1.0)
+        return 1.0 - 1.5 * h + 0.5 * h**3
+    raise ValueError(kind)
+
+
+def krige_vecs_np(kind, var, len_rescaled, sill, cond_pos, pos, unbiased=True, tail_rows=None,
+                  param=0.0, exact=False):
+    """``Krige._get_krige_vecs`` (krige/base.py:359-388) for one chunk: covariance rows from the
+    pairwise distances of the isometrised positions (base.py:430-450, scipy ``cdist``), the row of
+    ones of an unbiased system, then the drift rows."""
+    cond_pos, pos = np.asarray(cond_pos, dtype=np.float64), np.asarray(pos, dtype=np.float64)
+    diff = cond_pos[:, :, None] - pos[:, None, :]
+    r = np.sqrt(np.sum(diff * diff, axis=0))
+    cov = var * cov_cor_np(kind, r / len_rescaled, param)            # covmodel/tools.py:65-76
+    if exact:                                                       # cov_nugget, covmodel/base.py:313-320
+        cov[np.isclose(r, 0)] = sill
+    rows = [cov]
+    if unbiased:
+        rows.append(np.ones((1, pos.shape[1])))
+    if tail_rows is not None and np.size(tail_rows):
+        rows.append(np.asarray(tail_rows, dtype=np.float64).reshape(-1, pos.shape[1]))
+    return np.concatenate(rows, axis=0)
+
+
+def krige_evaluate(spec, krig_mat, cond, cond_pos, pos, unbiased=True, tail_rows=None):
+    """Right-hand sides by :func:`krige_vecs_np`, then the C oracle of the native evaluation."""
+    kv = krige_vecs_np(spec["kind"], spec["var"], spec["len_rescaled"], spec.get("sill", spec["var"]),
+                       cond_pos, pos, unbiased, tail_rows, spec.get("param", 0.0), spec.get("exact", False))
+    return calc_field_krige_and_variance(krig_mat, kv, cond)

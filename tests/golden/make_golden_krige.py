@@ -23,6 +23,8 @@ import refharness  # noqa: E402
 gs = refharness.import_gstools()
 from gstools.krige import base as kbase  # noqa: E402
 
+import oracle  # noqa: E402
+
 RECORD = []
 _orig = kbase._calc_field_krige_and_variance
 
@@ -54,14 +56,31 @@ def run(name, krige, dim, cite):
     idx = tuple(np.searchsorted(AXES[t], DATA[:, t]) for t in range(dim))
     at_nodes = field[idx]
     flat = np.ravel_multi_index(idx, field.shape)
-    meta = dict(name=name, kind="krige", cite=cite, var=float(krige.model.var), sill=float(krige.model.sill),
-                cond_val=COND_VAL.tolist(), node_index=[int(i) for i in flat], exact=bool(krige.exact))
+    model = krige.model
+    spec = dict(kind=type(model).__name__, var=float(model.var), len_rescaled=float(model.len_rescaled),
+                sill=float(model.sill), param=float(getattr(model, "alpha", 0.0)), exact=bool(krige.exact))
+    meta = dict(name=name, kind="krige", cite=cite, var=float(model.var), sill=float(model.sill),
+                cond_val=COND_VAL.tolist(), node_index=[int(i) for i in flat], exact=bool(krige.exact),
+                spec=spec, unbiased=bool(krige.unbiased), shape=list(field.shape))
+    # what the device-side right-hand-side generator needs, as the reference holds it
+    iso_pos, _ = krige.pre_pos(pos, "structured")
+    n_tail = krige.krige_size - krige.cond_no - int(krige.unbiased)
+    tail = rec["krig_vecs"][krige.krige_size - n_tail:] if n_tail else np.zeros((0, iso_pos.shape[1]))
+    from gstools.tools.geometric import matrix_isometrize
+    extra = dict(cond_pos_iso=np.array(krige._krige_pos), pos_iso=np.array(iso_pos), tail_rows=np.array(tail),
+                 matrix=matrix_isometrize(model.dim, model.angles, model.anis),
+                 krige_var=np.array(var), **{f"axis{t}": np.array(a) for t, a in enumerate(pos)})
+    # pin the numpy restatement of the covariance formulas on the reference's own right-hand sides
+    kv_np = oracle.krige_vecs_np(spec["kind"], spec["var"], spec["len_rescaled"], spec["sill"],
+                                 extra["cond_pos_iso"], extra["pos_iso"], krige.unbiased, tail,
+                                 spec["param"], spec["exact"])
+    assert np.max(np.abs(kv_np - rec["krig_vecs"])) <= 4e-16 * spec["sill"], (name, np.max(np.abs(kv_np - rec["krig_vecs"])))
     if krige.exact and np.all(np.asarray(krige.cond_err) == 0):
         for got, val in zip(at_nodes, COND_VAL):        # the reference's own assertion (places=2)
             assert round(got - val, 2) == 0, (name, got, val)
     np.savez_compressed(os.path.join(HERE, "krige", name + ".npz"), meta=json.dumps(meta),
                         krig_mat=rec["krig_mat"], krig_vecs=rec["krig_vecs"], cond=rec["cond"],
-                        field=rec["field"], error=rec["error"])
+                        field=rec["field"], error=rec["error"], **extra)
     print(f"{name}: K={rec['krig_mat'].shape[0]} n={rec['krig_vecs'].shape[1]} "
           f"|M|max={np.abs(rec['krig_mat']).max():.3g}")
 
@@ -77,6 +96,13 @@ def main():
             run(f"ordinary_{Model.__name__.lower()}_{dim}d",
                 gs.krige.Ordinary(m, COND_POS[:dim], COND_VAL), dim,
                 "tests/test_krige.py:81-107 (test_ordinary)")
+    for Model, kw in ((gs.Stable, dict(alpha=1.3)), (gs.Rational, dict(alpha=0.8)), (gs.Cubic, {}),
+                      (gs.Linear, {}), (gs.Circular, {})):
+        dim = 1 if Model is gs.Linear else 2
+        m = Model(dim=dim, var=1.5, len_scale=4, nugget=0.1, anis=0.7, angles=0.4, **kw)
+        run(f"ordinary_{Model.__name__.lower()}_{dim}d_exact",
+            gs.krige.Ordinary(m, COND_POS[:dim], COND_VAL, exact=True), dim,
+            "tests/test_krige.py:81-107 (test_ordinary), model list of covmodel/models.py")
     m = gs.Exponential(dim=2, var=2, len_scale=10, anis=[0.9, 0.8], angles=[2, 1, 0.5])
     run("universal_linear_exponential_2d", gs.krige.Universal(m, COND_POS[:2], COND_VAL, "linear"), 2,
         "tests/test_krige.py:109-133 (test_universal)")

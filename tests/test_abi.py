@@ -91,3 +91,18 @@ def test_product_package_never_imports_oracle():
                 text = open(os.path.join(root, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "liboracle" not in text, f
+
+
+def test_krige_argument_errors_need_no_gpu(gsb):
+    lib = gsb._lib.load()
+    a = np.zeros(16)
+    p = a.ctypes.data
+    assert lib.gsb_calc_field_krige_and_variance(p, p, 4, p, -1, 4, p, p, 0, 0, None) == 1
+    assert lib.gsb_calc_field_krige_and_variance(p, p, 4, p, 2, -4, p, p, 0, 0, None) == 1
+    assert lib.gsb_calc_field_krige_and_variance(p, p, 2, p, 2, 4, p, p, 0, 0, None) == 1   # ld < n
+    assert lib.gsb_calc_field_krige_and_variance(p, p, 4, p, 2, 4, p, None, 0, 0, None) == 1
+    assert lib.gsb_calc_field_krige(None, p, 4, p, 2, 4, p, 0, 0, None) == 1
+    assert lib.gsb_calc_field_krige(p, p, 4, p, 2, 4, p, 9, 0, None) == 1
+    # n == 0 returns without touching a device
+    f, e = gsb.calc_field_krige_and_variance(np.zeros((3, 3)), np.zeros((3, 0)), np.zeros(3))
+    assert f.shape == (0,) and e.shape == (0,)

@@ -169,3 +169,111 @@ def test_reference_krige_and_condsrf_on_gpu(gsb):
                 assert round(f1[i] - val, 2) == 0 and round(f2[(i, i, i)] - val, 2) == 0
     finally:
         gsb.disable()
+
+
+# ---------------------------------------------------------------------------------------------
+# krige_evaluate: right-hand sides generated on the device (Krige._get_krige_vecs, base.py:359-388)
+# ---------------------------------------------------------------------------------------------
+def _eval_bounds(mat, kv, cond, unit_f, unit_e):
+    """Rounding bound as above plus the effect of a 4-ulp perturbation of every right-hand-side
+    entry (device exp / pow / acos vs libm), propagated through the same sums."""
+    tf, te = bounds(mat, kv, cond, unit_f, unit_e)
+    am, akv = np.abs(mat), np.abs(kv)
+    return tf + 8 * EPS * (np.abs(cond) @ (am @ akv)), te + 16 * EPS * np.einsum("ij,ij->j", akv, am @ akv)
+
+
+@pytest.mark.parametrize("name", krige_fixtures())
+def test_krige_evaluate_fixtures(name, gsb, oracle_mod):
+    d = np.load(os.path.join(GOLDEN_DIR, "krige", name + ".npz"))
+    meta = json.loads(str(d["meta"]))
+    spec = gsb.cov_model_spec(**meta["spec"])
+    tail = d["tail_rows"] if d["tail_rows"].size else None
+    tf, te = _eval_bounds(d["krig_mat"], d["krig_vecs"], d["cond"], np.sqrt(meta["var"]), meta["var"])
+    f, e = gsb.krige_evaluate(spec, d["krig_mat"], d["cond"], d["cond_pos_iso"], pos=d["pos_iso"],
+                              unbiased=meta["unbiased"], tail_rows=tail)
+    assert np.all(np.abs(f - d["field"]) <= tf) and np.all(np.abs(e - d["error"]) <= te)
+    axes = [d[f"axis{t}"] for t in range(len(meta["shape"]))]
+    fs, es = gsb.krige_evaluate(spec, d["krig_mat"], d["cond"], d["cond_pos_iso"], axes=axes, matrix=d["matrix"],
+                                unbiased=meta["unbiased"], tail_rows=tail)
+    assert fs.shape == tuple(meta["shape"])
+    # the mesh is isometrised on the device: positions differ by rounding from the reference's np.dot
+    slack = 1e-12 * (np.abs(d["cond"]) @ (np.abs(d["krig_mat"]) @ np.abs(d["krig_vecs"])))
+    assert np.all(np.abs(fs.reshape(-1) - d["field"]) <= tf + slack)
+    f_only = gsb.krige_evaluate(spec, d["krig_mat"], d["cond"], d["cond_pos_iso"], pos=d["pos_iso"],
+                                unbiased=meta["unbiased"], tail_rows=tail, return_var=False)
+    assert np.all(np.abs(f_only - d["field"]) <= tf)
+    # the kriging variance the reference forms from it (base.py:296-298)
+    assert np.all(np.abs(np.maximum(meta["sill"] - e, 0).reshape(meta["shape"]) - d["krige_var"]) <= te.reshape(meta["shape"]))
+
+
+@pytest.mark.parametrize("kind,param", [("Gaussian", 0.0), ("Exponential", 0.0), ("Stable", 1.3), ("Rational", 0.8),
+                                        ("Cubic", 0.0), ("Linear", 0.0), ("Circular", 0.0), ("Spherical", 0.0)])
+@pytest.mark.parametrize("dim,C,n,exact", [(3, 300, 5001, False), (2, 129, 640, True), (1, 17, 130, False)])
+def test_krige_evaluate_random_vs_oracle(kind, param, dim, C, n, exact, gsb, oracle_mod):
+    rs = np.random.RandomState(C + n)
+    cond_pos = rs.uniform(0, 50, (dim, C))
+    pos = rs.uniform(0, 50, (dim, n))
+    pos[:, :5] = cond_pos[:, :5]                       # evaluation points ON conditioning points (r = 0)
+    K = C + 1 + 2                                      # unbiased row + two drift rows
+    mat = rs.normal(size=(K, K)) / K
+    cond = np.concatenate([rs.normal(size=C), np.zeros(3)])
+    tail = rs.normal(size=(2, n))
+    spec = dict(kind=kind, var=1.7, len_rescaled=9.0, sill=1.9, param=param, exact=exact)
+    kv = oracle_mod.krige_vecs_np(kind, 1.7, 9.0, 1.9, cond_pos, pos, True, tail, param, exact)
+    wf, we = oracle_mod.calc_field_krige_and_variance(mat, kv, cond)
+    tf, te = _eval_bounds(mat, kv, cond, 1.0, 1.0)
+    f, e = gsb.krige_evaluate(spec, mat, cond, cond_pos, pos=pos, unbiased=True, tail_rows=tail)
+    assert np.all(np.abs(f - wf) <= tf), float(np.max(np.abs(f - wf) / tf))
+    assert np.all(np.abs(e - we) <= te), float(np.max(np.abs(e - we) / te))
+    f2 = gsb.krige_evaluate(spec, mat, cond, cond_pos, pos=pos, unbiased=True, tail_rows=tail, return_var=False)
+    assert np.all(np.abs(f2 - wf) <= tf)
+
+
+def test_krige_evaluate_chunking_is_invisible(gsb):
+    rs = np.random.RandomState(2)
+    C, n = 100, 3000
+    cond_pos, pos = rs.uniform(0, 30, (3, C)), rs.uniform(0, 30, (3, n))
+    mat, cond = rs.normal(size=(C + 1, C + 1)) / C, np.concatenate([rs.normal(size=C), [0.0]])
+    spec = dict(kind="Exponential", var=1.0, len_rescaled=5.0)
+    ref = gsb.krige_evaluate(spec, mat, cond, cond_pos, pos=pos)
+    gsb.set_option("scratch_mb", 1)                   # a few column tiles per chunk
+    try:
+        got = gsb.krige_evaluate(spec, mat, cond, cond_pos, pos=pos)
+    finally:
+        gsb.set_option("scratch_mb", 3072)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    with pytest.raises(ValueError):
+        gsb.krige_evaluate(dict(kind="Matern", var=1.0, len_rescaled=5.0), mat, cond, cond_pos, pos=pos)
+    with pytest.raises(ValueError):
+        gsb.krige_evaluate(spec, mat, cond, cond_pos, pos=pos, unbiased=False)     # a drift row is missing
+
+
+@needs_ref
+@pytest.mark.parametrize("mesh", ["structured", "unstructured"])
+def test_fast_krige_and_condsrf_equal_reference_path(gsb, mesh):
+    """gs.krige.* and gs.CondSRF through the fast Krige.__call__ (device right-hand sides) against
+    the same objects on the reference's own chunk loop (host right-hand sides, CPU oracle)."""
+    gs = refharness.import_gstools()
+    rs = np.random.RandomState(20170519)
+    cond_pos = rs.uniform(0, 31, (3, 60))
+    cond_val = rs.normal(size=60)
+    model = gs.Exponential(dim=3, var=1.3, len_scale=[10, 6, 4], angles=[0.3, 0.2, 0.1])
+    if mesh == "structured":
+        pos = [np.arange(32.0), np.arange(30.0), np.arange(17.0)]
+    else:
+        pos = rs.uniform(0, 31, (3, 4000))
+    ref_k = gs.krige.Ordinary(model, cond_pos, cond_val)
+    want_f, want_v = ref_k(pos, mesh_type=mesh)
+    want_c = gs.CondSRF(gs.krige.Ordinary(model, cond_pos, cond_val), seed=4711, mode_no=128)(pos, mesh_type=mesh)
+    gsb.enable()
+    try:
+        calls = gsb.get_counter("krige_calls")
+        got_f, got_v = gs.krige.Ordinary(model, cond_pos, cond_val)(pos, mesh_type=mesh)
+        got_c = gs.CondSRF(gs.krige.Ordinary(model, cond_pos, cond_val), seed=4711, mode_no=128)(pos, mesh_type=mesh)
+        assert gsb.get_counter("krige_calls") >= calls + 2
+    finally:
+        gsb.disable()
+    assert got_f.shape == want_f.shape
+    assert np.max(np.abs(got_f - want_f)) <= 1e-9 * np.sqrt(model.var)
+    assert np.max(np.abs(got_v - want_v)) <= 1e-9 * model.var
+    assert np.max(np.abs(got_c - want_c)) <= 1e-8 * np.sqrt(model.var)   # sqrt(krige_var) near data amplifies

@@ -306,3 +306,126 @@ def test_fused_srf_call_falls_through_when_not_affine(gsb, oracle_mod, monkeypat
     assert fsrf.SRF.__call__ is not orig
     gsb.disable()
     assert fsrf.SRF.__call__ is orig
+
+
+# ---------------------------------------------------------------------------------------------
+# fast Krige.__call__ (row f1): on CPU the backend entry is replaced by the oracle restatement
+# (numpy right-hand sides + C evaluation), so this checks the plugin's host logic: which model
+# parameters, positions, drift rows and flags reach the device entry, and which cases fall through.
+# ---------------------------------------------------------------------------------------------
+def _fake_krige_backend(monkeypatch, oracle_mod, calls):
+    from gstools_b200 import _lib, backend
+
+    kinds = {v: k for k, v in _lib.COV_TYPES.items()}
+
+    def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=None, unbiased=True,
+                       tail_rows=None, return_var=True):
+        calls.append("eval")
+        spec = dict(kind=kinds[model.type], var=model.var, len_rescaled=model.len_rescaled, sill=model.sill,
+                    param=model.param, exact=bool(model.exact))
+        shape = None
+        if axes is not None:
+            shape = tuple(len(a) for a in axes)
+            pos = np.array(np.meshgrid(*axes, indexing="ij")).reshape(len(axes), -1)
+            if matrix is not None:
+                pos = np.dot(matrix, pos)
+        f, e = oracle_mod.krige_evaluate(spec, krig_mat, cond, cond_pos, pos, unbiased, tail_rows)
+        if shape:
+            f, e = f.reshape(shape), e.reshape(shape)
+        return (f, e) if return_var else f
+
+    monkeypatch.setattr(backend, "krige_evaluate", krige_evaluate)
+    monkeypatch.setattr(backend, "calc_field_krige_and_variance",
+                        lambda *a: (calls.append("native"), oracle_mod.calc_field_krige_and_variance(*a[:3]))[1])
+    monkeypatch.setattr(backend, "calc_field_krige",
+                        lambda *a: (calls.append("native"), oracle_mod.calc_field_krige(*a[:3]))[1])
+
+
+_KDATA = np.array([[0.3, 1.2, 0.5, 0.47], [1.9, 0.6, 1.0, 0.56], [1.1, 3.2, 1.5, 0.74],
+                   [3.3, 4.4, 2.0, 1.47], [4.7, 3.8, 2.5, 1.74]])
+
+
+def _krige_cases(gs):
+    cp, cv = (_KDATA[:, 0], _KDATA[:, 1], _KDATA[:, 2]), _KDATA[:, 3]
+    m3 = gs.Exponential(dim=3, var=2, len_scale=4, anis=[0.9, 0.8], angles=[2, 1, 0.5])
+    m2 = gs.Stable(dim=2, var=1.5, len_scale=4, nugget=0.1, anis=0.7, angles=0.4, alpha=1.3)
+    return [
+        ("simple", lambda: gs.krige.Simple(m3, cp, cv, mean=1.0), 3, {}),
+        ("ordinary", lambda: gs.krige.Ordinary(m3, cp, cv), 3, {}),
+        ("ordinary_exact", lambda: gs.krige.Ordinary(m2, cp[:2], cv, exact=True), 2, {}),
+        ("universal", lambda: gs.krige.Universal(m2, cp[:2], cv, "linear"), 2, {}),
+        ("extdrift", lambda: gs.krige.ExtDrift(m2, cp[:2], cv, ext_drift=np.arange(5.0) ** 2), 2, {"ext": True}),
+        ("novar", lambda: gs.krige.Ordinary(m3, cp, cv, trend=0.5), 3, {"return_var": False}),
+    ]
+
+
+@needs_ref
+@pytest.mark.parametrize("mesh", ["structured", "unstructured"])
+@pytest.mark.parametrize("case", range(6))
+def test_fast_krige_call_matches_reference(gsb, oracle_mod, monkeypatch, case, mesh):
+    gs = refharness.import_gstools()
+    label, make, dim, opt = _krige_cases(gs)[case]
+    axes = [np.linspace(0, 5, 7), np.linspace(0, 6, 5), np.linspace(0, 7, 4)][:dim]
+    if mesh == "structured":
+        pos, n = axes, int(np.prod([len(a) for a in axes]))
+    else:
+        pos = np.random.RandomState(1).uniform(0, 5, (dim, 33))
+        n = 33
+    kw = {k: v for k, v in opt.items() if k != "ext"}
+    if opt.get("ext"):
+        kw["ext_drift"] = np.linspace(0, 3, n)
+    want = make()(pos, mesh_type=mesh, **kw)
+    calls = []
+    _fake_krige_backend(monkeypatch, oracle_mod, calls)
+    gsb.enable()
+    try:
+        krige = make()
+        got = krige(pos, mesh_type=mesh, **kw)
+    finally:
+        gsb.disable()
+    assert calls == ["eval"], (label, calls)
+    want, got = np.atleast_1d(want), np.atleast_1d(got)       # (field, var) pairs or a single field
+    if kw.get("return_var", True):
+        assert np.allclose(got[0], want[0], rtol=0, atol=1e-12) and np.allclose(got[1], want[1], rtol=0, atol=1e-12)
+        assert krige.field is not None and krige.krige_var is not None
+    else:
+        assert np.allclose(got, want, rtol=0, atol=1e-12)
+
+
+@needs_ref
+def test_fast_krige_call_falls_through(gsb, oracle_mod, monkeypatch):
+    """Models without a device implementation, lat-lon models and only_mean keep the reference's
+    chunk loop (whose native evaluation still goes to the backend, through the rebound wrapper)."""
+    gs = refharness.import_gstools()
+    cp, cv = (_KDATA[:, 0], _KDATA[:, 1]), _KDATA[:, 3]
+    pos = [np.linspace(0, 5, 6), np.linspace(0, 6, 5)]
+
+    class MyExp(gs.Exponential):          # a subclass may override cor(): never treated as Exponential
+        pass
+
+    variants = [
+        (gs.Matern(dim=2, var=1, len_scale=3, nu=1.5), {}),
+        (MyExp(dim=2, var=1, len_scale=3), {}),
+        (gs.Exponential(dim=2, var=1, len_scale=3), {"only_mean": True}),
+    ]
+    for model, kw in variants:
+        want = gs.krige.Ordinary(model, cp, cv)(pos, mesh_type="structured", **kw)
+        calls = []
+        with monkeypatch.context() as mp:
+            _fake_krige_backend(mp, oracle_mod, calls)
+            gsb.enable()
+            try:
+                got = gs.krige.Ordinary(model, cp, cv)(pos, mesh_type="structured", **kw)
+            finally:
+                gsb.disable()
+        assert "eval" not in calls, (type(model).__name__, calls)
+        for a, b in zip(np.atleast_1d(want), np.atleast_1d(got)):
+            assert np.allclose(a, b, rtol=0, atol=1e-12)
+    from gstools.krige import base as kbase
+
+    assert kbase.Krige.__call__ is not None
+    orig = kbase.Krige.__call__
+    gsb.enable()
+    assert kbase.Krige.__call__ is not orig
+    gsb.disable()
+    assert kbase.Krige.__call__ is orig

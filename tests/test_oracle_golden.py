@@ -119,3 +119,42 @@ def test_live_reference_matches_fixtures(oracle_mod):
     y = np.linspace(-5.0, 5.0, 10)
     z = np.linspace(-6.0, 8.0, 10)
     assert np.allclose(rm((x, y, z)), d["field"], rtol=0, atol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------
+# kriging evaluation oracle (row f1): fixtures from the reference's Krige classes
+# (tests/golden/make_golden_krige.py) and the known-answer facts of tests/test_krige.py
+# ---------------------------------------------------------------------------------------------
+def _krige_fixtures():
+    import glob
+    import os
+
+    from conftest import GOLDEN_DIR
+
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "krige", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _krige_fixtures(), ids=lambda p: p.split("/")[-1][:-4])
+def test_krige_oracle_reproduces_recorded_boundary(path, oracle_mod):
+    import json
+
+    d = np.load(path)
+    meta = json.loads(str(d["meta"]))
+    field, error = oracle_mod.calc_field_krige_and_variance(d["krig_mat"], d["krig_vecs"], d["cond"])
+    assert np.array_equal(field, d["field"]) and np.array_equal(error, d["error"])
+    assert np.array_equal(oracle_mod.calc_field_krige(d["krig_mat"], d["krig_vecs"], d["cond"]), field)
+    # numpy restatement (BLAS order): agreement to the rounding scale of the system
+    f_np, e_np = oracle_mod.calc_field_krige_and_variance_np(d["krig_mat"], d["krig_vecs"], d["cond"])
+    am, akv = np.abs(d["krig_mat"]), np.abs(d["krig_vecs"])
+    eps = np.finfo(float).eps
+    k = am.shape[0]
+    assert np.all(np.abs(f_np - field) <= 8 * k * eps * (np.abs(d["cond"]) @ (am @ akv)) + 1e-300)
+    assert np.all(np.abs(e_np - error) <= 8 * k * eps * np.einsum("ij,ij->j", akv, am @ akv) + 1e-300)
+    # known answer asserted by the reference (tests/test_krige.py:76-79, 104-107): the kriged field
+    # reproduces the conditioning values at the conditioning nodes, places=2
+    if not meta["name"].startswith("universal"):
+        mean = float(np.mean(meta["cond_val"])) if meta["name"].startswith("simple") else 0.0
+        for idx, val in zip(meta["node_index"], meta["cond_val"]):
+            assert round(field[idx] + mean - val, 2) == 0, meta["cite"]
+        # ... and the error variance vanishes there (sill - error == 0 at exact data, base.py:296-298)
+        assert np.all(np.abs(meta["sill"] - error[meta["node_index"]]) < 1e-6 * max(1.0, np.abs(d["krig_mat"]).max()))

@@ -33,3 +33,22 @@ for want_var in (True, False):
               f"= {100*tri/ms/1e-3/peak:.1f} % of measured DFMA peak {peak/1e12:.2f} TFMA/s")
     else:
         print(f"calc_field_krige K={K} n={n}: {ms:.2f} ms/call, {8.0*K*n/ms/1e6:.0f} GB/s of krig_vecs")
+# the whole evaluation loop with device-generated right-hand sides (BASELINE.json configs[4] kriging step:
+# 1000 conditioning points, ordinary kriging, Exponential(dim=3, var=1, len_scale=10), 128^3 mesh)
+import time
+rs = np.random.RandomState(20170519)
+C = K - 1
+edge = round(n ** (1 / 3))
+if edge ** 3 == n:
+    cond_pos = rs.uniform(0, edge - 1, (3, C))
+    axes = [np.arange(float(edge))] * 3
+    matn, condn = mat.cpu().numpy() / K, cond.cpu().numpy()
+    spec = dict(kind="Exponential", var=1.0, len_rescaled=10.0)
+    for i in range(3):
+        t0 = time.perf_counter()
+        gsb.set_option("time_kernels", 1); gsb.kernel_times()
+        f, e = gsb.krige_evaluate(spec, matn, condn, cond_pos, axes=axes)
+        t = time.perf_counter() - t0
+        kms, kn = gsb.kernel_times(); gsb.set_option("time_kernels", 0)
+        print(f"krige_evaluate (device right-hand sides) K={K} mesh {edge}^3: {1e3*t:.1f} ms wall, "
+              f"contraction kernels {kms:.2f} ms in {kn} launches")
