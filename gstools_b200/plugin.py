@@ -102,7 +102,19 @@ def _const_term(value, value_type, dim):
     return None
 
 
-def enable(lazy_grid: bool = True, fused: bool = True):
+def _same(a, b):
+    """Identity or equal content (None-aware; tuples of arrays element-wise)."""
+    if a is b:
+        return True
+    if a is None or b is None:
+        return False
+    if isinstance(a, (tuple, list)):
+        return isinstance(b, (tuple, list)) and len(a) == len(b) and all(_same(x, y) for x, y in zip(a, b))
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and np.array_equal(a, b)
+
+
+def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True):
     """Route ``RandMeth`` / ``IncomprRandMeth`` summation of ``gstools`` to the B200 backend."""
     import gstools  # the user's (unmodified) installation
     from gstools import config
@@ -222,6 +234,7 @@ def enable(lazy_grid: bool = True, fused: bool = True):
             fbase.Field.pre_pos = orig_pre_pos
 
         orig_srf_call = _STATE["orig_srf_call"]
+        _STATE["cache_krige"] = bool(cache_krige)
 
         def _fused_epilogue(srf, post_process):
             """gsb_epilogue equal to everything SRF.__call__ does after the summation, or None."""
@@ -325,14 +338,31 @@ def enable(lazy_grid: bool = True, fused: bool = True):
                 tail += list(np.asarray(ext_drift, dtype=np.double).reshape(self.ext_drift_no, -1))
             tail_rows = np.ascontiguousarray(tail) if tail else None
             kwargs = dict(unbiased=self.unbiased, tail_rows=tail_rows, return_var=return_var)
-            if lazy:
-                matrix = matrix_isometrize(self.model.dim, self.model.angles, self.model.anis)
-                out = backend.krige_evaluate(spec, self._krige_mat, self._krige_cond, self._krige_pos,
-                                             axes=self.pos, matrix=matrix, **kwargs)
+            matrix = matrix_isometrize(self.model.dim, self.model.angles, self.model.anis) if lazy else None
+            # The evaluation is a pure function of these inputs.  The reference's ensemble idiom
+            # (examples/06_conditioned_fields/01_2D_condition_ensemble.py:32-35, store=[name, False, False])
+            # re-evaluates the same kriging system for every realisation; remember the last result
+            # and hand out copies (post_field below works in place).
+            cond = self._krige_cond
+            key = dict(spec=bytes(spec), flags=(lazy, bool(self.unbiased), bool(return_var)), matrix=matrix,
+                       mat=self._krige_mat, cond=cond, cpos=self._krige_pos,
+                       pos=self.pos if lazy else iso_pos, tail=tail_rows)
+            cached = getattr(self, "_b200_krige_cache", None) if _STATE.get("cache_krige") else None
+            if cached is not None and cached["key"]["spec"] == key["spec"] and cached["key"]["flags"] == key["flags"] \
+                    and all(_same(cached["key"][k], key[k]) for k in ("mat", "cond", "cpos", "matrix", "pos", "tail")):
+                out = tuple(np.copy(o) for o in cached["out"])
+                _STATE["krige_cache_hits"] = _STATE.get("krige_cache_hits", 0) + 1
             else:
-                out = backend.krige_evaluate(spec, self._krige_mat, self._krige_cond, self._krige_pos,
-                                             pos=iso_pos, **kwargs)
-            field, krige_var = out if return_var else (out, None)
+                if lazy:
+                    out = backend.krige_evaluate(spec, self._krige_mat, cond, self._krige_pos,
+                                                 axes=self.pos, matrix=matrix, **kwargs)
+                else:
+                    out = backend.krige_evaluate(spec, self._krige_mat, cond, self._krige_pos,
+                                                 pos=iso_pos, **kwargs)
+                out = out if return_var else (out,)
+                if _STATE.get("cache_krige"):
+                    self._b200_krige_cache = dict(key=key, out=tuple(np.copy(o) for o in out))
+            field, krige_var = out if return_var else (out[0], None)
             field = np.reshape(field, shape)
             field = self.post_field(field, name[0], post_process, save[0])
             if return_var:                                                    # base.py:296-300

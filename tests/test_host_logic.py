@@ -429,3 +429,58 @@ def test_fast_krige_call_falls_through(gsb, oracle_mod, monkeypatch):
     assert kbase.Krige.__call__ is not orig
     gsb.disable()
     assert kbase.Krige.__call__ is orig
+
+
+@needs_ref
+def test_fast_krige_call_memoises_only_identical_systems(gsb, oracle_mod, monkeypatch):
+    gs = refharness.import_gstools()
+    from gstools_b200 import plugin
+
+    cp, cv = (_KDATA[:, 0], _KDATA[:, 1]), _KDATA[:, 3]
+    pos = [np.linspace(0, 5, 6), np.linspace(0, 6, 5)]
+    model = gs.Exponential(dim=2, var=1.2, len_scale=3)
+    calls = []
+    _fake_krige_backend(monkeypatch, oracle_mod, calls)
+    _fake_backend(monkeypatch, oracle_mod, [])          # the CondSRF below also sums modes
+    gsb.enable()
+    try:
+        krige = gs.krige.Ordinary(model, cp, cv)
+        f1, v1 = krige(pos, mesh_type="structured")
+        f1 = f1.copy()
+        f2, v2 = krige(pos, mesh_type="structured")               # same system, same mesh: served from the cache
+        assert calls == ["eval"] and np.array_equal(f1, f2) and np.array_equal(v1, v2)
+        f2 += 1.0                                                   # results are copies: the cache is not aliased
+        f3, _ = krige(mesh_type="structured")
+        assert calls == ["eval"] and np.array_equal(f1, f3)
+        krige(pos, mesh_type="structured", return_var=False)       # different request
+        assert calls == ["eval"] * 2
+        krige([pos[0], pos[1] + 0.5], mesh_type="structured")      # different mesh
+        assert calls == ["eval"] * 3
+        krige.set_condition(cp, cv + 1.0)                           # different data
+        f4, _ = krige(mesh_type="structured")
+        assert calls == ["eval"] * 4 and not np.allclose(f4, f3)
+        krige.model.len_scale = 4.0                                 # model edited in place
+        krige(mesh_type="structured")
+        assert calls == ["eval"] * 5
+        # the ensemble idiom of the reference's example: one evaluation for all realisations
+        crf = gs.CondSRF(gs.krige.Ordinary(model, cp, cv), seed=1, mode_no=16)
+        n0 = len(calls)
+        fields = [crf(pos, seed=s, mesh_type="structured", store=[f"fld{s}", False, False]) for s in (1, 2, 3)]
+        assert len(calls) == n0 + 1 and not np.allclose(fields[0], fields[1])
+    finally:
+        gsb.disable()
+    # cache_krige=False evaluates every time
+    calls.clear()
+    gsb.enable(cache_krige=False)
+    try:
+        krige = gs.krige.Ordinary(model, cp, cv)
+        krige(pos, mesh_type="structured")
+        krige(pos, mesh_type="structured")
+        assert calls == ["eval"] * 2
+    finally:
+        gsb.disable()
+    # reference result for the CondSRF ensemble member (plugin off) agrees
+    # (the shared model object was edited to len_scale = 4 above)
+    want = gs.CondSRF(gs.krige.Ordinary(gs.Exponential(dim=2, var=1.2, len_scale=4.0), cp, cv), seed=2,
+                      mode_no=16)(pos, mesh_type="structured")
+    assert np.allclose(fields[1], want, rtol=0, atol=1e-12)
