@@ -489,7 +489,10 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         // pieces (groups of fields, or ranges of slow indices of a single field) so that the D2H
         // copy of one piece overlaps the contraction of the next.
         if (n_slow * n_ytiles > 0x7fffffff) return fail(GSB_ERR_ARGUMENT, "structured mesh too large");
-        const int64_t pieces = h_out ? 8 : 1;
+        // ... but never pieces of less than two waves of tiles: a 128^3 field is 128 tiles, and eight
+        // launches of 16 CTAs each would leave most of the SMs idle (2.4 ms instead of 0.3 ms).
+        const int64_t tiles_all = n_slow * n_ytiles * n_col_tiles * ncomp * n_batch;
+        const int64_t pieces = h_out ? std::max<int64_t>(1, std::min<int64_t>(8, tiles_all / (2 * (int64_t)dev.sm_count))) : 1;
         const int64_t fgroup = std::max<int64_t>(1, n_batch / pieces);
         const int64_t splits = (n_batch >= pieces) ? 1 : std::min<int64_t>(n_slow, pieces / n_batch);
         int64_t c = 0;

@@ -52,3 +52,14 @@ if edge ** 3 == n:
         kms, kn = gsb.kernel_times(); gsb.set_option("time_kernels", 0)
         print(f"krige_evaluate (device right-hand sides) K={K} mesh {edge}^3: {1e3*t:.1f} ms wall, "
               f"contraction kernels {kms:.2f} ms in {kn} launches")
+# the reference's loop nest on the host cores (C/OpenMP oracle, test infrastructure) on a bounded sample
+import oracle
+ns = 16384
+kvs = np.random.RandomState(0).uniform(0, 1, (K, ns))
+mats, conds = mat.cpu().numpy(), cond.cpu().numpy()
+oracle.calc_field_krige_and_variance(mats, kvs[:, :256], conds)
+t0 = time.perf_counter()
+oracle.calc_field_krige_and_variance(mats, kvs, conds)
+t = time.perf_counter() - t0
+print(f"CPU oracle calc_field_krige_and_variance K={K} on {ns} points, {oracle.max_threads()} threads: {t:.2f} s "
+      f"-> {t / ns * n:.1f} s extrapolated to n={n} ({1.0 * K * K * ns / t / 1e9:.2f} GFMA/s)")

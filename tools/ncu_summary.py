@@ -66,10 +66,23 @@ def main():
             pass
         lines.append("")
     src = page(rep, "source")
-    if len(src) > 2:
-        h = src[1]
+    # the source page holds one block per profiled launch: ["Kernel Name", name], header row, data rows
+    blocks, cur = [], None
+    for r in src:
+        if r and r[0] == "Kernel Name":
+            cur = dict(name=r[1] if len(r) > 1 else "?", header=None, rows=[])
+            blocks.append(cur)
+        elif cur is not None and cur["header"] is None:
+            cur["header"] = r
+        elif cur is not None and len(r) == len(cur["header"]):
+            cur["rows"].append(r)
+    seen = set()
+    for b in blocks:
+        if b["name"] in seen or not b["header"]:
+            continue          # one block per distinct kernel is enough
+        seen.add(b["name"])
+        h, data = b["header"], b["rows"]
         idx = {n: i for i, n in enumerate(h)}
-        data = [r for r in src[2:] if len(r) == len(h)]
         ops = Counter()
         for r in data:
             s = r[idx["Source"]].split()
@@ -81,15 +94,22 @@ def main():
             except ValueError:
                 pass
         tot = sum(ops.values())
-        lines.append("executed warp-instructions by opcode (source page):")
+        lines.append(f"[{b['name']}] executed warp-instructions by opcode (source page):")
         for op, c in ops.most_common(14):
             lines.append(f"  {op:12s} {c:14d}  {100.0 * c / max(tot, 1):5.1f}%")
         lines.append("")
-        lines.append("top sampled instructions (stall samples):")
-        top = sorted(data, key=lambda r: -float(r[idx["# Samples"]] or 0))[:12]
-        for r in top:
+        lines.append(f"[{b['name']}] top sampled instructions (stall samples):")
+
+        def samples(r):
+            try:
+                return float(r[idx["# Samples"]] or 0)
+            except ValueError:
+                return 0.0
+
+        for r in sorted(data, key=lambda r: -samples(r))[:12]:
             lines.append(f"  {r[idx['Source']][:60]:60s} samples {r[idx['# Samples']]:>7s}  long_sb {r[idx['stall_long_sb']]:>6s}"
                          f" math {r[idx['stall_math']]:>6s} wait {r[idx['stall_wait']]:>6s} short_sb {r[idx['stall_short_sb']]:>6s}")
+        lines.append("")
     open(dst, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[:60]))
 
