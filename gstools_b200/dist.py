@@ -24,6 +24,7 @@ __all__ = [
     "summate_sharded",
     "summate_structured_sharded",
     "ensemble_sharded",
+    "krige_evaluate_sharded",
     "gather_field",
 ]
 
@@ -83,6 +84,31 @@ def ensemble_sharded(mode_sets, evaluate, group=None):
     rank, world = _rank_world(group)
     lo, hi = shard_range(len(mode_sets), rank, world)
     return [evaluate(mode_sets[i]) for i in range(lo, hi)], (lo, hi)
+
+
+def krige_evaluate_sharded(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=None,
+                           unbiased=True, tail_rows=None, return_var=True, group=None, compute=None):
+    """This rank's share of :func:`gstools_b200.krige_evaluate` (row f1): points are independent, the
+    kriging system (``krig_mat``, ``cond``, ``cond_pos``) is replicated.  Flat points are split into
+    contiguous ranges, meshes into slabs along axis 0; drift rows follow their points.
+    Returns ``(local_result, (lo, hi))`` with ``local_result`` as ``krige_evaluate`` returns it."""
+    rank, world = _rank_world(group)
+    fn = compute or backend.krige_evaluate
+    if (pos is None) == (axes is None):
+        raise ValueError("give either pos (dim, n) or axes")
+    if axes is not None:
+        axes = [np.asarray(a, dtype=np.float64).reshape(-1) for a in axes]
+        lo, hi = shard_range(len(axes[0]), rank, world)
+        inner = int(np.prod([len(a) for a in axes[1:]])) if len(axes) > 1 else 1
+        tail = None if tail_rows is None else np.asarray(tail_rows)[:, lo * inner:hi * inner]
+        out = fn(model, krig_mat, cond, cond_pos, axes=[axes[0][lo:hi]] + axes[1:], matrix=matrix,
+                 unbiased=unbiased, tail_rows=tail, return_var=return_var)
+    else:
+        lo, hi = shard_range(pos.shape[1], rank, world)
+        tail = None if tail_rows is None else np.asarray(tail_rows)[:, lo:hi]
+        out = fn(model, krig_mat, cond, cond_pos, pos=pos[:, lo:hi], unbiased=unbiased, tail_rows=tail,
+                 return_var=return_var)
+    return out, (lo, hi)
 
 
 def gather_field(local, n_total: int, axis: int = 0, group=None, dst=None):

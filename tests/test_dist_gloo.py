@@ -68,6 +68,33 @@ def _worker(rank, world, port, tmpdir):
         assert len(mine) == hi - lo and (lo, hi) == gdist.shard_range(5, rank, world)
         for f, s in zip(mine, range(lo, hi)):
             assert np.array_equal(f, oracle.summate(*sets[s], pos[:, :50]))
+        # ---- kriging evaluation: points / slabs sharded, system replicated, drift rows follow ----
+        rs = np.random.RandomState(3)
+        cpos, K = rs.uniform(0, 9, (3, 12)), 12 + 1 + 1
+        kmat, kcond = rs.normal(size=(K, K)), np.concatenate([rs.normal(size=12), [0.0, 0.0]])
+        spec = dict(kind="Exponential", var=1.3, len_rescaled=4.0)
+
+        def krige_compute(model, m, c, cp, pos=None, axes=None, matrix=None, unbiased=True, tail_rows=None,
+                          return_var=True):
+            shape = None
+            if axes is not None:
+                shape = tuple(len(a) for a in axes)
+                pos = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+            f, e = oracle.krige_evaluate(model, m, c, cp, pos, unbiased, tail_rows)
+            return (f.reshape(shape), e.reshape(shape)) if shape else (f, e)
+
+        grid = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+        drift = grid[0:1] * 0.5                                            # one drift row on the mesh
+        (lf, le), (lo, hi) = gdist.krige_evaluate_sharded(spec, kmat, kcond, cpos, axes=axes, tail_rows=drift,
+                                                           compute=krige_compute)
+        assert lf.shape == (hi - lo, 5, 4)
+        wf, we = oracle.krige_evaluate(spec, kmat, kcond, cpos, grid, True, drift)
+        assert np.array_equal(gdist.gather_field(lf, 7).reshape(-1), wf)
+        assert np.array_equal(gdist.gather_field(le, 7).reshape(-1), we)
+        (pf, pe), (lo, hi) = gdist.krige_evaluate_sharded(spec, kmat, kcond, cpos, pos=pos[:, :101] * 0.09,
+                                                           tail_rows=pos[0:1, :101], compute=krige_compute)
+        wf, we = oracle.krige_evaluate(spec, kmat, kcond, cpos, pos[:, :101] * 0.09, True, pos[0:1, :101])
+        assert np.array_equal(gdist.gather_field(pf, 101), wf) and np.array_equal(gdist.gather_field(pe, 101), we)
         open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

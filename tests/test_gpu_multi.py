@@ -62,6 +62,17 @@ def _worker(rank, world, port, tmpdir):
         local, (lo, hi) = gdist.summate_sharded(cov, z1, z2, pos)
         whole = gsb.summate(cov, z1, z2, pos)
         assert np.array_equal(local, whole[lo:hi])
+        # kriging evaluation (row f1): slabs along axis 0, the system replicated on every device
+        rs = np.random.RandomState(7)
+        cpos = rs.uniform(0, 30, (3, 40))
+        kmat, kcond = rs.normal(size=(41, 41)) / 40, np.concatenate([rs.normal(size=40), [0.0]])
+        spec = dict(kind="Exponential", var=1.0, len_rescaled=6.0)
+        kaxes = [np.arange(33.0), np.arange(16.0), np.arange(24.0)]
+        (lf, le), (lo, hi) = gdist.krige_evaluate_sharded(spec, kmat, kcond, cpos, axes=kaxes)
+        wf, we = gsb.krige_evaluate(spec, kmat, kcond, cpos, axes=kaxes)
+        assert np.array_equal(lf, wf[lo:hi]) and np.array_equal(le, we[lo:hi])
+        gathered = gdist.gather_field(torch.tensor(lf, device=dev), 33)
+        assert torch.equal(gathered.cpu(), torch.tensor(wf))
         open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
