@@ -20,6 +20,7 @@ from .backend import (
     calc_field_krige_and_variance,
     cov_model_spec,
     krige_evaluate,
+    sample_radii_mcmc,
     get_device,
     make_epilogue,
     scale_shift_,
@@ -46,6 +47,7 @@ __all__ = [
     "calc_field_krige",
     "krige_evaluate",
     "cov_model_spec",
+    "sample_radii_mcmc",
     "scale_shift_",
     "make_epilogue",
     "enable",

@@ -14,12 +14,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("GSB200_LIB") or os.path.join(HERE, "libgsb200.so")
 SOURCES = ["gsb_api.cu"]
-HEADERS = ["gsb_common.cuh", "gsb_direct.cuh", "gsb_separable.cuh", "gsb_krige.cuh",
+HEADERS = ["gsb_common.cuh", "gsb_direct.cuh", "gsb_separable.cuh", "gsb_krige.cuh", "gsb_sampler.cuh",
            "sincos_coeffs.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared",
     "-diag-suppress", "550",
 ]
 

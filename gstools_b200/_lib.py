@@ -37,6 +37,9 @@ COV_TYPES = {"Gaussian": 1, "Exponential": 2, "Stable": 3, "Rational": 4, "Cubic
              "Circular": 7, "Spherical": 8}
 
 
+PDF_KINDS = {"Exponential": 1, "Matern": 2}
+
+
 class CovModelSpec(ctypes.Structure):
     """``gsb_cov_model`` of include/gsb200.h."""
 
@@ -77,6 +80,8 @@ SIGNATURES = {
                                   _vp, _vp, _int, _int, _vp]),
     "gsb_krige_evaluate_structured": (_int, [_cov_p, _vp, _vp, _i64, _vp, _i64, _int, _vp, _c_int64_p, _vp,
                                              _int, _vp, _i64, _vp, _vp, _int, _int, _vp]),
+    "gsb_sample_radii_mcmc": (_int, [_int, _int, ctypes.c_double, ctypes.c_double, _vp, _int, _vp, _int, _vp,
+                                     _int, _int, _int, _vp]),
     "gsb_scale_shift": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp]),
     "gsb_set_option": (_int, [ctypes.c_char_p, _i64]),
     "gsb_get_counter": (_i64, [ctypes.c_char_p]),

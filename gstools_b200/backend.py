@@ -36,6 +36,7 @@ __all__ = [
     "calc_field_krige",
     "krige_evaluate",
     "cov_model_spec",
+    "sample_radii_mcmc",
     "scale_shift_",
     "make_epilogue",
     "set_device",
@@ -538,6 +539,32 @@ def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=
     _lib.check(rc, "krige_evaluate")
     field = field.reshape(shape)
     return (field, error.reshape(shape)) if return_var else field
+
+
+def sample_radii_mcmc(kind, dim, len_rescaled, nu, burn_state, main_state, init, burn_in, n_steps):
+    """Native, stream-compatible ``emcee`` run of ``RNG.sample_ln_pdf`` (random/rng.py:77-101).
+
+    ``burn_state`` / ``main_state`` are the ``numpy.random.RandomState.get_state()`` tuples (legacy
+    MT19937) the reference hands to the burn-in and the production ``run_mcmc`` call, ``init`` the
+    ``nwalkers`` initial positions.  Returns the production chain ``(n_steps, nwalkers)``.  Host only.
+    """
+    if kind not in _lib.PDF_KINDS:
+        raise ValueError(f"no native log-pdf for model '{kind}': {sorted(_lib.PDF_KINDS)}")
+    keys = []
+    for st in (burn_state, main_state):
+        if st[0] != "MT19937":
+            raise ValueError("the legacy MT19937 state of numpy.random.RandomState is required")
+        key = np.ascontiguousarray(st[1], dtype=np.uint32)
+        if key.shape != (624,):
+            raise ValueError("MT19937 key must have 624 words")
+        keys.append(key)
+    x0 = np.ascontiguousarray(_as_f64(init, "init")).reshape(-1)
+    chain = np.empty((int(n_steps), x0.shape[0]), dtype=np.float64)
+    rc = _lib.load().gsb_sample_radii_mcmc(_lib.PDF_KINDS[kind], int(dim), float(len_rescaled), float(nu),
+                                           _ptr(keys[0]), int(burn_state[2]), _ptr(keys[1]), int(main_state[2]),
+                                           _ptr(x0), x0.shape[0], int(burn_in), int(n_steps), _ptr(chain))
+    _lib.check(rc, "sample_radii_mcmc")
+    return chain
 
 
 def scale_shift_(field, scale, shift=0.0):

@@ -236,6 +236,27 @@ int gsb_krige_evaluate_structured(const gsb_cov_model *model, const double *krig
                                   double *error, int mem, int device, void *stream);
 
 /*
+ * gsb_sample_radii_mcmc -- host-side, stream-compatible restatement of RNG.sample_ln_pdf
+ * (src/gstools/random/rng.py:38-104): the emcee ensemble sampler
+ * (stretch move, a = 2) that draws the mode radii of RandMeth for models without an inverse CDF
+ * (generator.py:381-385).  Runs `burn_in` steps from the numpy legacy MT19937 state
+ * (mt_key_burn[624], mt_pos_burn), then `n_steps` production steps from (mt_key_main, mt_pos_main) --
+ * the reference hands each run_mcmc call the state of a fresh RandomState (rng.py:84-99, 193-203) --
+ * and writes the positions of all walkers after every production step to chain[n_steps][nwalkers]
+ * (= get_chain(flat=True)).
+ *   pdf_kind   GSB_PDF_EXPONENTIAL / GSB_PDF_MATERN: CovModel.ln_spectral_rad_pdf of that model
+ *              (covmodel/base.py:553-560, covmodel/tools.py:374-406, models.py:217-224, 434-449)
+ *   init       nwalkers initial positions (rng.py:78-80)
+ * No device is touched.
+ */
+#define GSB_PDF_EXPONENTIAL 1
+#define GSB_PDF_MATERN 2
+int gsb_sample_radii_mcmc(int pdf_kind, int dim, double len_rescaled, double nu,
+                          const uint32_t *mt_key_burn, int mt_pos_burn,
+                          const uint32_t *mt_key_main, int mt_pos_main, const double *init,
+                          int nwalkers, int burn_in, int n_steps, double *chain);
+
+/*
  * Fused caller epilogue (reference: src/gstools/field/generator.py:269-270):
  *   field[i] = scale * field[i] + shift     in place, device pointers only.
  * Lets a device-resident caller keep the field on the GPU.

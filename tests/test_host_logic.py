@@ -484,3 +484,81 @@ def test_fast_krige_call_memoises_only_identical_systems(gsb, oracle_mod, monkey
     want = gs.CondSRF(gs.krige.Ordinary(gs.Exponential(dim=2, var=1.2, len_scale=4.0), cp, cv), seed=2,
                       mode_no=16)(pos, mesh_type="structured")
     assert np.allclose(fields[1], want, rtol=0, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# native mode-radius sampler (row f4): host code, fully testable here.  Bar: BIT-EXACT -- the same
+# seed must give the same radii as the reference's emcee run, so that every field stays the one the
+# reference would have produced.
+# ---------------------------------------------------------------------------------------------
+@needs_ref
+@pytest.mark.parametrize("seed", [20170519, 19031977, 3])
+@pytest.mark.parametrize("make", [
+    lambda gs: gs.Exponential(dim=3, var=1, len_scale=10),
+    lambda gs: gs.Exponential(dim=3, var=2, len_scale=[12.0, 5.0, 3.0], angles=[0.4, -0.3, 0.7]),
+    lambda gs: gs.Matern(dim=2, var=1, len_scale=10, nu=1.0),
+    lambda gs: gs.Matern(dim=3, var=1, len_scale=4, nu=2.5),
+    lambda gs: gs.Matern(dim=1, var=1, len_scale=4, nu=0.5),
+    lambda gs: gs.Matern(dim=2, var=1, len_scale=4, nu=30.0),       # nu > 20: Gaussian-like branch, models.py:438-444
+], ids=["exp3d", "exp3d_aniso", "matern2d", "matern3d", "matern1d", "matern_nu30"])
+def test_native_radius_sampler_is_stream_compatible(gsb, make, seed):
+    gs = refharness.import_gstools()
+    from gstools.field.generator import RandMeth
+
+    ref = RandMeth(make(gs), mode_no=300, seed=seed)
+    gsb.enable()
+    try:
+        got = RandMeth(make(gs), mode_no=300, seed=seed)
+        assert np.array_equal(got._cov_sample, ref._cov_sample)
+        assert np.array_equal(got._z_1, ref._z_1) and np.array_equal(got._z_2, ref._z_2)
+        got.seed = seed + 1                                           # reseeding goes through the same path
+    finally:
+        gsb.disable()
+    ref.seed = seed + 1
+    assert np.array_equal(got._cov_sample, ref._cov_sample)
+
+
+@needs_ref
+def test_native_radius_sampler_reference_literals_and_fallthrough(gsb, monkeypatch):
+    """tests/test_randmeth.py:43-46 (3-D golden) through the native sampler; models without a native
+    log-pdf, overridden densities and the flag switched off keep emcee."""
+    gs = refharness.import_gstools()
+    from gstools import config
+    from gstools.field.generator import RandMeth
+    from gstools.random import rng as grng
+    from gstools_b200 import backend
+
+    meta, d = load_golden("randmeth_3d")
+    calls = []
+    real = backend.sample_radii_mcmc
+    monkeypatch.setattr(backend, "sample_radii_mcmc", lambda *a: (calls.append(a[0]), real(*a))[1])
+    orig = grng.RNG.sample_ln_pdf
+    gsb.enable()
+    try:
+        assert grng.RNG.sample_ln_pdf is not orig
+        rm = RandMeth(gs.Exponential(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=19031977)
+        assert calls == ["Exponential"]
+        # the fixture's model (Gaussian 3-D) has an inverse CDF: no MCMC at all, same modes as recorded
+        rg = RandMeth(gs.Gaussian(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=19031977)
+        assert calls == ["Exponential"] and np.array_equal(rg._cov_sample, d["cov_samples"])
+
+        class MyMatern(gs.Matern):                                  # overridden density: emcee
+            def spectral_density(self, k):
+                return super().spectral_density(k)
+
+        RandMeth(MyMatern(dim=2, var=1, len_scale=3, nu=1.0), mode_no=50, seed=1)
+        assert calls == ["Exponential"]
+        config.USE_GSTOOLS_B200 = False
+        RandMeth(gs.Exponential(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=19031977)
+        assert calls == ["Exponential"]
+    finally:
+        gsb.disable()
+    assert grng.RNG.sample_ln_pdf is orig
+    ref = RandMeth(gs.Exponential(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=19031977)
+    assert np.array_equal(rm._cov_sample, ref._cov_sample)
+    with pytest.raises(ValueError):
+        backend.sample_radii_mcmc("Stable", 3, 1.0, 0.0, ("MT19937", np.zeros(624, np.uint32), 0),
+                                  ("MT19937", np.zeros(624, np.uint32), 0), np.ones(50), 1, 1)
+    with pytest.raises(ValueError):      # odd number of walkers
+        real("Exponential", 3, 1.0, 0.0, ("MT19937", np.zeros(624, np.uint32), 624),
+             ("MT19937", np.zeros(624, np.uint32), 624), np.ones(51), 1, 1)
