@@ -963,7 +963,7 @@ struct KrigeEvalArgs {
 template <int D>
 static void launch_kvgen(const KvgenParams &gp, int n_dstages, int64_t n_ct, cudaStream_t st)
 {
-    dim3 grid((unsigned)n_dstages, (unsigned)n_ct);
+    dim3 grid((unsigned)n_ct, (unsigned)std::min(8, std::max(1, n_dstages / 4)));
     kvgen_kernel<D><<<grid, 256, 0, st>>>(gp);
 }
 
@@ -1043,7 +1043,7 @@ static int krige_eval_on_device(const KrigeEvalArgs &a, const MeshInfo *mesh, co
     // column chunks sized by the scratch budget (half of "scratch_mb" for the tiled right-hand sides)
     const size_t col_tile_bytes = (size_t)gp.n_dstages * SEP_B_TILE * sizeof(double);
     int64_t chunk_tiles = std::max<int64_t>(1, (int64_t)((size_t)g_opt_scratch_mb.load() * (1u << 20) / 2 / col_tile_bytes));
-    chunk_tiles = std::min<int64_t>(std::min<int64_t>(chunk_tiles, 65535), (n + SEP_TN - 1) / SEP_TN);
+    chunk_tiles = std::min<int64_t>(chunk_tiles, (n + SEP_TN - 1) / SEP_TN);
     double *d_btile = nullptr, *d_partial = nullptr;
     GSB_TRY(scr.alloc(&d_btile, (size_t)chunk_tiles * gp.n_dstages * SEP_B_TILE));
     GSB_TRY(scr.alloc(&d_partial, (size_t)kp.n_pairs * chunk_tiles * SEP_TN));

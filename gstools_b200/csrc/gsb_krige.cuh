@@ -533,33 +533,45 @@ __device__ __forceinline__ double kvgen_entry(const KvgenParams &prm, int row, i
     return 0.0;
 }
 
-// one CTA per (column tile, depth stage): 16 rows x 128 points, written in the stage layout
+// one CTA per column tile of 128 points: every thread owns one point and every second row, walks down
+// all depth stages (position and constants set up once) and writes in the stage layout
+constexpr int KVGEN_ROWS = 1024;     // conditioning positions staged in shared memory per pass
 template <int D>
 __global__ void __launch_bounds__(256) kvgen_kernel(const KvgenParams prm)
 {
-    __shared__ double cp[KRG_KD][D];
-    const int s = blockIdx.x;
-    const int64_t ct = blockIdx.y;
-    for (int e = threadIdx.x; e < KRG_KD * D; e += blockDim.x) {
-        const int d = e / D, t = e % D, row = s * KRG_KD + d;
-        cp[d][t] = row < prm.C ? prm.cond_pos[(int64_t)t * prm.C + row] : 0.0;
-    }
-    __syncthreads();
+    __shared__ double cp[KVGEN_ROWS][D];
+    const int64_t ct = blockIdx.x;
     const int cl = threadIdx.x % SEP_TN;
+    const int half = threadIdx.x / SEP_TN;
     const int64_t lcol = ct * SEP_TN + cl;
-    double *T = prm.btile + (ct * prm.n_dstages + s) * SEP_B_TILE;
+    const int64_t gcol = prm.col_begin + lcol;
+    double *T = prm.btile + ct * prm.n_dstages * SEP_B_TILE;
     double x[D];
     const bool live = lcol < prm.n;
-    if (live) kvgen_point<D>(prm, prm.col_begin + lcol, x);
-#pragma unroll
-    for (int i = 0; i < KRG_KD / 2; ++i) {
-        const int d = threadIdx.x / SEP_TN + 2 * i;
-        const int row = s * KRG_KD + d;
-        T[d * SEP_BST + cl] = live ? kvgen_entry<D>(prm, row, prm.col_begin + lcol, x, cp[d]) : 0.0;
+    if (live) kvgen_point<D>(prm, gcol, x);
+    // gridDim.y CTAs share the depth stages of a column tile (finer grain: fewer idle SMs in the last wave)
+    const int st_per = (prm.n_dstages + gridDim.y - 1) / gridDim.y;
+    const int row_lo = min(prm.n_dstages, (int)blockIdx.y * st_per) * KRG_KD;
+    const int n_rows = min(prm.n_dstages, ((int)blockIdx.y + 1) * st_per) * KRG_KD;
+    for (int r0 = row_lo; r0 < n_rows; r0 += KVGEN_ROWS) {
+        const int cnt = min(KVGEN_ROWS, n_rows - r0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * D; e += blockDim.x) {
+            const int rr = e / D, t = e % D, row = r0 + rr;
+            cp[rr][t] = row < prm.C ? prm.cond_pos[(int64_t)t * prm.C + row] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int rr = half; rr < cnt; rr += 2) {
+            const int row = r0 + rr;
+            T[(row / KRG_KD) * SEP_B_TILE + (row % KRG_KD) * SEP_BST + cl] =
+                live ? kvgen_entry<D>(prm, row, gcol, x, cp[rr]) : 0.0;
+        }
     }
-    if (threadIdx.x < KRG_KD * (SEP_BST - SEP_TN)) {   // the 4 padding doubles of every row
-        const int d = threadIdx.x / (SEP_BST - SEP_TN), q = threadIdx.x % (SEP_BST - SEP_TN);
-        T[d * SEP_BST + SEP_TN + q] = 0.0;
+    // the 4 padding doubles of every row
+    for (int e = threadIdx.x; e < (n_rows - row_lo) * (SEP_BST - SEP_TN); e += blockDim.x) {
+        const int row = row_lo + e / (SEP_BST - SEP_TN), q = e % (SEP_BST - SEP_TN);
+        T[(row / KRG_KD) * SEP_B_TILE + (row % KRG_KD) * SEP_BST + SEP_TN + q] = 0.0;
     }
 }
 
