@@ -10,14 +10,15 @@
 //   * the CTA streams tiles of packed mode records through shared memory with
 //     cp.async.bulk + mbarrier (TMA unit), double buffered; every lane of a warp reads the
 //     same record, so the LDS are broadcasts;
-//   * sin/cos: the wave vectors are pre-scaled to quarter turns (k * 2/pi), so that
+//   * sin/cos: the wave vectors are pre-scaled to EIGHTH turns (k * 4/pi), so that
 //     u = k.x, n = rint(u) (magic-number add), r = u - n in [-1/2, 1/2] is an EXACT
-//     reduction with 3 DADD; sin(pi/2 r) and cos(pi/2 r) are degree-11 / degree-10 minimax
-//     polynomials (sincos_coeffs.cuh, abs error < 6e-14);
-//   * the quadrant fix-up costs no FP64 and no select: each record carries the four rotated
-//     weight pairs (z1,z2),(z2,-z1),(-z1,-z2),(-z2,z1) and the lane fetches pair (n & 3) with
-//     one conflict-free 16-byte LDS;
-//   * FP64 instructions per (point, mode): D + 17 (scalar), D + 17 + D (incompressible).
+//     reduction with 3 DADD; sin(pi/4 r) and cos(pi/4 r) are degree-9 / degree-8 polynomials
+//     (sincos_coeffs.cuh, abs error 1.7e-15 / 4.7e-14 -- the same accuracy the quarter-turn
+//     reduction of the first version needed one more coefficient each for);
+//   * the octant fix-up costs no FP64 and no select: each record carries the eight rotated
+//     weight pairs W_q = (z1 c_q + z2 s_q, z2 c_q - z1 s_q), c_q + i s_q = exp(i q pi/4), and the
+//     lane fetches pair (n & 7) with one conflict-free 16-byte LDS;
+//   * FP64 instructions per (point, mode): D + 15 (scalar), D + 15 + D (incompressible).
 #pragma once
 
 #include "gsb_common.cuh"
@@ -25,19 +26,20 @@
 
 namespace gsb {
 
-constexpr int DIRECT_TM = 128;  // modes per shared-memory tile
+constexpr int DIRECT_TM = 96;   // modes per shared-memory tile (2 buffers x 96 x 24 doubles <= 48 KB static)
 constexpr double RINT_MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-constexpr double TWO_OVER_PI = 0.63661977236758134308;
+constexpr double FOUR_OVER_PI = 1.27323954473516268615;
+constexpr int DIRECT_NW = 16;   // doubles of rotated weight pairs per record (8 octants)
 
 __host__ __device__ constexpr int direct_koff(int D) { return (D + 1) & ~1; }
 __host__ __device__ constexpr int direct_rec(int D, bool vec)
 {
-    return direct_koff(D) + 8 + (vec ? direct_koff(D) : 0);
+    return direct_koff(D) + DIRECT_NW + (vec ? direct_koff(D) : 0);
 }
 
 // ---------------------------------------------------------------------------------------------
-// mode packing: (cov_samples, z1, z2) -> records [kq_0..kq_{D-1} pad | W0 W1 W2 W3 | p_0..p_{D-1} pad]
-// kq = k * 2/pi (quarter turns); W_q = weight pair after rotating by q quarter turns;
+// mode packing: (cov_samples, z1, z2) -> records [kq_0..kq_{D-1} pad | W0 .. W7 | p_0..p_{D-1} pad]
+// kq = k * 4/pi (eighth turns); W_q = weight pair after rotating by q eighth turns;
 // p_t = delta_t0 - k_t k_0 / |k|^2 (incompressible projector, generator.py:479-495).
 // Records j >= n_modes (padding up to n_modes_pad) are all-zero and contribute exactly 0.
 // ---------------------------------------------------------------------------------------------
@@ -58,7 +60,7 @@ __global__ void pack_modes_kernel(const double *__restrict__ cov, const double *
         double k2 = 0.0;
         for (int t = 0; t < dim; ++t) {
             double k = cov[(int64_t)t * n_modes + j];
-            R[t] = k * TWO_OVER_PI;
+            R[t] = k * FOUR_OVER_PI;
             k2 += k * k;
         }
         for (int t = dim; t < koff; ++t) R[t] = 0.0;
@@ -66,12 +68,21 @@ __global__ void pack_modes_kernel(const double *__restrict__ cov, const double *
         const double w = sf ? sf[j] : 1.0;
         const double a = w * z1[j], b = w * z2[j];
         double *W = R + koff;
-        W[0] = a;  W[1] = b;     // n & 3 == 0 :  z1 c + z2 s
-        W[2] = b;  W[3] = -a;    // n & 3 == 1 :  z2 c - z1 s
-        W[4] = -a; W[5] = -b;    // n & 3 == 2 : -z1 c - z2 s
-        W[6] = -b; W[7] = a;     // n & 3 == 3 : -z2 c + z1 s
+        // z1 cos(phi) + z2 sin(phi) with phi = (q + r) pi/4:  cos(r pi/4) * W[2q] + sin(r pi/4) * W[2q+1]
+        const double h = 0.70710678118654752440;   // sqrt(1/2)
+        const double cq[8] = {1.0, h, 0.0, -h, -1.0, -h, 0.0, h};
+        const double sq[8] = {0.0, h, 1.0, h, 0.0, -h, -1.0, -h};
+        for (int q = 0; q < 8; ++q) {
+            if (q & 1) {   // (a +- b) / sqrt(2): one rounding for the sum, one for the scale
+                W[2 * q] = (cq[q] > 0 ? a : -a) * h + (sq[q] > 0 ? b : -b) * h;
+                W[2 * q + 1] = (cq[q] > 0 ? b : -b) * h - (sq[q] > 0 ? a : -a) * h;
+            } else {       // exact quarter-turn rotations
+                W[2 * q] = a * cq[q] + b * sq[q];
+                W[2 * q + 1] = b * cq[q] - a * sq[q];
+            }
+        }
         if (vec) {
-            double *Pj = W + 8;
+            double *Pj = W + DIRECT_NW;
             const double k0 = cov[j];
             for (int t = 0; t < dim; ++t) {
                 const double e = (t == 0) ? 1.0 : 0.0;
@@ -95,13 +106,11 @@ struct DirectParams {
     Epi epi;                // fused caller epilogue (off: raw sums)
 };
 
-// residual sin/cos on r in [-1/2, 1/2] quarter turns: returns ps = sin(pi/2 r)/r and pc = cos(pi/2 r)
+// residual sin/cos on r in [-1/2, 1/2] eighth turns: returns ps = sin(pi/4 r)/r and pc = cos(pi/4 r)
 __device__ __forceinline__ void qt_polys(double z, double &ps, double &pc)
 {
-    double s = fma(z, GSB_S5, GSB_S4);
-    double c = fma(z, GSB_C5, GSB_C4);
-    s = fma(z, s, GSB_S3);
-    c = fma(z, c, GSB_C3);
+    double s = fma(z, GSB_S4, GSB_S3);
+    double c = fma(z, GSB_C4, GSB_C3);
     s = fma(z, s, GSB_S2);
     c = fma(z, c, GSB_C2);
     s = fma(z, s, GSB_S1);
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
             double pj[NC];
             if (VEC) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) pj[c] = R[KOFF + 8 + c];
+                for (int c = 0; c < NC; ++c) pj[c] = R[KOFF + DIRECT_NW + c];
             }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
@@ -183,19 +192,8 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
                 const double v = u + RINT_MAGIC;           // rint(u) lands in the low mantissa bits
                 const int q = lo32(v);
                 const double r = u - (v - RINT_MAGIC);     // exact, |r| <= 1/2
-#ifdef GSB_DIRECT_SEL
-                // arithmetic quadrant fix-up (ablation): selects + sign flips instead of the LDS
-                const double z1v = R[KOFF], z2v = R[KOFF + 1];
-                double2 w;
-                w.x = (q & 1) ? z2v : z1v;
-                w.y = (q & 1) ? -z1v : z2v;
-                const int sgn = (q & 2) << 30;
-                w.x = __hiloint2double(__double2hiint(w.x) ^ sgn, __double2loint(w.x));
-                w.y = __hiloint2double(__double2hiint(w.y) ^ sgn, __double2loint(w.y));
-#else
                 const double2 w = *reinterpret_cast<const double2 *>(
-                    reinterpret_cast<const char *>(R + KOFF) + ((q & 3) << 4));
-#endif
+                    reinterpret_cast<const char *>(R + KOFF) + ((q & 7) << 4));
                 const double z = r * r;
                 double ps, pc;
                 qt_polys(z, ps, pc);
