@@ -10,15 +10,17 @@
 //   * the CTA streams tiles of packed mode records through shared memory with
 //     cp.async.bulk + mbarrier (TMA unit), double buffered; every lane of a warp reads the
 //     same record, so the LDS are broadcasts;
-//   * sin/cos: the wave vectors are pre-scaled to EIGHTH turns (k * 4/pi), so that
+//   * sin/cos: the wave vectors are pre-scaled to SIXTEENTH turns (k * 8/pi), so that
 //     u = k.x, n = rint(u) (magic-number add), r = u - n in [-1/2, 1/2] is an EXACT
-//     reduction with 3 DADD; sin(pi/4 r) and cos(pi/4 r) are degree-9 / degree-8 polynomials
-//     (sincos_coeffs.cuh, abs error 1.7e-15 / 4.7e-14 -- the same accuracy the quarter-turn
-//     reduction of the first version needed one more coefficient each for);
-//   * the octant fix-up costs no FP64 and no select: each record carries the eight rotated
-//     weight pairs W_q = (z1 c_q + z2 s_q, z2 c_q - z1 s_q), c_q + i s_q = exp(i q pi/4), and the
-//     lane fetches pair (n & 7) with one conflict-free 16-byte LDS;
-//   * FP64 instructions per (point, mode): D + 15 (scalar), D + 15 + D (incompressible).
+//     reduction with 3 DADD; sin(pi/8 r) and cos(pi/8 r) are degree-7 / degree-6 polynomials
+//     (sincos_coeffs.cuh, abs error 9.3e-15 / 4.3e-13; tools/gen_sincos_coeffs.py lists the
+//     accuracy / table-size trade-off: every halving of the reduced range saves one DFMA per
+//     polynomial and doubles the table below);
+//   * the rotation by n sixteenth turns costs no FP64 and no select: each record carries the 16
+//     rotated weight pairs W_q = (z1 c_q + z2 s_q, z2 c_q - z1 s_q), c_q + i s_q = exp(i q pi/8), as two
+//     arrays of 16 doubles -- each exactly one 128-byte row of shared memory, so the per-lane LDS.64
+//     with index (n & 15) are conflict free;
+//   * FP64 instructions per (point, mode): D + 13 (scalar), D + 13 + D (incompressible).
 #pragma once
 
 #include "gsb_common.cuh"
@@ -26,10 +28,11 @@
 
 namespace gsb {
 
-constexpr int DIRECT_TM = 96;   // modes per shared-memory tile (2 buffers x 96 x 24 doubles <= 48 KB static)
+constexpr int DIRECT_TM = 64;   // modes per shared-memory tile (2 buffers x 64 x 40 doubles <= 48 KB static)
 constexpr double RINT_MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-constexpr double FOUR_OVER_PI = 1.27323954473516268615;
-constexpr int DIRECT_NW = 16;   // doubles of rotated weight pairs per record (8 octants)
+constexpr double EIGHT_OVER_PI = 2.54647908947032537230;
+constexpr int DIRECT_NROT = 16;              // rotations per record (sixteenth turns)
+constexpr int DIRECT_NW = 2 * DIRECT_NROT;   // doubles of rotated weights per record: Wx[16], Wy[16]
 
 __host__ __device__ constexpr int direct_koff(int D) { return (D + 1) & ~1; }
 __host__ __device__ constexpr int direct_rec(int D, bool vec)
@@ -38,8 +41,8 @@ __host__ __device__ constexpr int direct_rec(int D, bool vec)
 }
 
 // ---------------------------------------------------------------------------------------------
-// mode packing: (cov_samples, z1, z2) -> records [kq_0..kq_{D-1} pad | W0 .. W7 | p_0..p_{D-1} pad]
-// kq = k * 4/pi (eighth turns); W_q = weight pair after rotating by q eighth turns;
+// mode packing: (cov_samples, z1, z2) -> records [kq_0..kq_{D-1} pad | Wx[16] | Wy[16] | p_0..p_{D-1} pad]
+// kq = k * 8/pi (sixteenth turns); (Wx[q], Wy[q]) = weight pair after rotating by q sixteenth turns;
 // p_t = delta_t0 - k_t k_0 / |k|^2 (incompressible projector, generator.py:479-495).
 // Records j >= n_modes (padding up to n_modes_pad) are all-zero and contribute exactly 0.
 // ---------------------------------------------------------------------------------------------
@@ -60,7 +63,7 @@ __global__ void pack_modes_kernel(const double *__restrict__ cov, const double *
         double k2 = 0.0;
         for (int t = 0; t < dim; ++t) {
             double k = cov[(int64_t)t * n_modes + j];
-            R[t] = k * FOUR_OVER_PI;
+            R[t] = k * EIGHT_OVER_PI;
             k2 += k * k;
         }
         for (int t = dim; t < koff; ++t) R[t] = 0.0;
@@ -68,18 +71,11 @@ __global__ void pack_modes_kernel(const double *__restrict__ cov, const double *
         const double w = sf ? sf[j] : 1.0;
         const double a = w * z1[j], b = w * z2[j];
         double *W = R + koff;
-        // z1 cos(phi) + z2 sin(phi) with phi = (q + r) pi/4:  cos(r pi/4) * W[2q] + sin(r pi/4) * W[2q+1]
-        const double h = 0.70710678118654752440;   // sqrt(1/2)
-        const double cq[8] = {1.0, h, 0.0, -h, -1.0, -h, 0.0, h};
-        const double sq[8] = {0.0, h, 1.0, h, 0.0, -h, -1.0, -h};
-        for (int q = 0; q < 8; ++q) {
-            if (q & 1) {   // (a +- b) / sqrt(2): one rounding for the sum, one for the scale
-                W[2 * q] = (cq[q] > 0 ? a : -a) * h + (sq[q] > 0 ? b : -b) * h;
-                W[2 * q + 1] = (cq[q] > 0 ? b : -b) * h - (sq[q] > 0 ? a : -a) * h;
-            } else {       // exact quarter-turn rotations
-                W[2 * q] = a * cq[q] + b * sq[q];
-                W[2 * q + 1] = b * cq[q] - a * sq[q];
-            }
+        // z1 cos(phi) + z2 sin(phi) with phi = (q + r) pi/8:  cos(r pi/8) * Wx[q] + sin(r pi/8) * Wy[q]
+        for (int q = 0; q < DIRECT_NROT; ++q) {
+            const double cq = cospi(q / 8.0), sq = sinpi(q / 8.0);   // exact 0, +-1 at the quarter turns
+            W[q] = a * cq + b * sq;
+            W[DIRECT_NROT + q] = b * cq - a * sq;
         }
         if (vec) {
             double *Pj = W + DIRECT_NW;
@@ -106,13 +102,11 @@ struct DirectParams {
     Epi epi;                // fused caller epilogue (off: raw sums)
 };
 
-// residual sin/cos on r in [-1/2, 1/2] eighth turns: returns ps = sin(pi/4 r)/r and pc = cos(pi/4 r)
+// residual sin/cos on r in [-1/2, 1/2] sixteenth turns: returns ps = sin(pi/8 r)/r and pc = cos(pi/8 r)
 __device__ __forceinline__ void qt_polys(double z, double &ps, double &pc)
 {
-    double s = fma(z, GSB_S4, GSB_S3);
-    double c = fma(z, GSB_C4, GSB_C3);
-    s = fma(z, s, GSB_S2);
-    c = fma(z, c, GSB_C2);
+    double s = fma(z, GSB_S3, GSB_S2);
+    double c = fma(z, GSB_C3, GSB_C2);
     s = fma(z, s, GSB_S1);
     c = fma(z, c, GSB_C1);
     ps = fma(z, s, GSB_S0);
@@ -192,8 +186,9 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
                 const double v = u + RINT_MAGIC;           // rint(u) lands in the low mantissa bits
                 const int q = lo32(v);
                 const double r = u - (v - RINT_MAGIC);     // exact, |r| <= 1/2
-                const double2 w = *reinterpret_cast<const double2 *>(
-                    reinterpret_cast<const char *>(R + KOFF) + ((q & 7) << 4));
+                double2 w;
+                w.x = R[KOFF + (q & (DIRECT_NROT - 1))];
+                w.y = R[KOFF + DIRECT_NROT + (q & (DIRECT_NROT - 1))];
                 const double z = r * r;
                 double ps, pc;
                 qt_polys(z, ps, pc);

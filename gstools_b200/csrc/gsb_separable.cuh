@@ -9,7 +9,7 @@
 // with  A_j(row) = (z1_j - i z2_j) prod_{t<d-1} exp(i k'_{t,j} a_t[i_t])   (row = all axes but the last)
 //       E_j(c)   = exp(i k'_{d-1,j} a_{d-1}[c]) = Cz + i Sz               (c = last, contiguous axis).
 // That is a real fp64 contraction of depth 2N costing 2 DFMA per (point, mode) instead of the
-// ~D+15 of the direct kernel: all sin/cos work moves into per-axis tables of size (len_t x N)
+// ~D+13 of the direct kernel: all sin/cos work moves into per-axis tables of size (len_t x N)
 // built once per call with full-accuracy sincos.
 //
 // Three kernels:

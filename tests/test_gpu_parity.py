@@ -108,8 +108,9 @@ def test_edge_cases(gsb, oracle_mod):
     assert np.array_equal(out, np.zeros(5))
     out = gsb.summate_incompr(cov[:, :0], z1[:0], z2[:0], np.ones((2, 5)))
     assert np.array_equal(out, np.zeros((2, 5)))
-    # x = 0 -> sum(z1)
-    assert abs(gsb.summate(cov, z1, z2, np.zeros((2, 1)))[0] - z1.sum()) < 1e-13
+    # x = 0 -> sum(z1), up to the documented abs error of the cos polynomial (4.3e-13 per mode,
+    # gstools_b200/csrc/sincos_coeffs.cuh: the Chebyshev interpolant is not pinned to 1 at r = 0)
+    assert abs(gsb.summate(cov, z1, z2, np.zeros((2, 1)))[0] - z1.sum()) < 5e-13 * np.abs(z1).sum()
     # a zero wave vector gives NaN in the projector, exactly like the reference loop (k2 == 0)
     cov0 = cov.copy()
     cov0[:, 3] = 0.0

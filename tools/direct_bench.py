@@ -23,9 +23,9 @@ for cfg in (2, 1, 0):
     gsb.set_option("direct_cfg", cfg)
     t = timeit(lambda: gsb.summate(m[0], m[1], m[2], pos))
     pr = 8e6 * 2000
-    print(f"cfg {cfg} scalar 2D: {t*1e3:.2f} ms {pr/t/1e12:.3f} Tpair/s pipe {pr*17/t/peak*100:.1f}%")
+    print(f"cfg {cfg} scalar 2D: {t*1e3:.2f} ms {pr/t/1e12:.3f} Tpair/s pipe {pr*15/t/peak*100:.1f}%")
     t = timeit(lambda: gsb.summate(m4[0], m4[1], m4[2], pos3))
     pr = 8e6 * 1000
-    print(f"cfg {cfg} scalar 3D: {t*1e3:.2f} ms {pr/t/1e12:.3f} Tpair/s pipe {pr*18/t/peak*100:.1f}%")
+    print(f"cfg {cfg} scalar 3D: {t*1e3:.2f} ms {pr/t/1e12:.3f} Tpair/s pipe {pr*16/t/peak*100:.1f}%")
     t = timeit(lambda: gsb.summate_incompr(m4[0], m4[1], m4[2], pos3))
-    print(f"cfg {cfg} incompr 3D: {t*1e3:.2f} ms {pr/t/1e12:.3f} Tpair/s pipe {pr*21/t/peak*100:.1f}%")
+    print(f"cfg {cfg} incompr 3D: {t*1e3:.2f} ms {pr/t/1e12:.3f} Tpair/s pipe {pr*19/t/peak*100:.1f}%")
