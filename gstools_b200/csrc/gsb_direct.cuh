@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
                 double u = k[0] * x[p][0];
 #pragma unroll
                 for (int t2 = 1; t2 < D; ++t2) u = fma(k[t2], x[p][t2], u);
+                // (rint on the conversion pipe -- F2I + I2F instead of two of the DADDs -- measured +2 % only:
+                // 64-bit conversions are not cheaper than DADDs here, and they narrow the phase domain)
                 const double v = u + RINT_MAGIC;           // rint(u) lands in the low mantissa bits
                 const int q = lo32(v);
                 const double r = u - (v - RINT_MAGIC);     // exact, |r| <= 1/2
