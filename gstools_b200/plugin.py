@@ -136,6 +136,7 @@ def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True)
                           orig_pre_pos=fbase.Field.pre_pos, orig_srf_call=fsrf.SRF.__call__,
                           orig_krige=kbase._calc_field_krige, orig_krige_call=kbase.Krige.__call__,
                           orig_sample_ln_pdf=grng.RNG.sample_ln_pdf, grng=grng,
+                          orig_apply_mnt=fbase.apply_mean_norm_trend,
                           orig_krige_var=kbase._calc_field_krige_and_variance,
                           gen=gen, fbase=fbase, fsrf=fsrf, kbase=kbase, config=config)
         orig_s, orig_si = _STATE["orig_summate"], _STATE["orig_summate_incompr"]
@@ -379,6 +380,36 @@ def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True)
         krige_call.__doc__ = orig_krige_call.__doc__
         kbase.Krige.__call__ = krige_call if fused else orig_krige_call
 
+        # Field.post_field's epilogue (field/base.py:326-336 -> normalizer/tools.py:83-104) for the common
+        # case -- constant mean and trend, identity normalizer: the reference's `denormalize` alone is
+        # five passes over the field (isnan, not, full_like, two masked copies) to return the same
+        # values; here: add in place (the reference mutates its input the same way), copy, add.
+        orig_apply_mnt = _STATE["orig_apply_mnt"]
+
+        def apply_mean_norm_trend(pos, field, mean=None, normalizer=None, trend=None, mesh_type="unstructured",
+                                  value_type="scalar", check_shape=True, stacked=False):
+            fast = (getattr(config, "USE_GSTOOLS_B200", False) and not check_shape and not stacked
+                    and type(normalizer) is Normalizer and isinstance(field, np.ndarray)
+                    and field.dtype == np.double)
+            consts = []
+            if fast:
+                for value in (mean, trend):
+                    value = 0 if value is None else value
+                    if callable(value) or np.size(value) != 1:
+                        fast = False
+                        break
+                    consts.append(np.asarray(value, dtype=np.double).item())
+            if not fast:
+                return orig_apply_mnt(pos, field, mean, normalizer, trend, mesh_type, value_type, check_shape,
+                                      stacked)
+            field += consts[0]                          # tools.py:99-100, in place like the reference
+            out = np.array(field, dtype=np.double)      # identity denormalize returns a fresh array (base.py:93-108)
+            out += consts[1]                            # tools.py:102-103
+            return out
+
+        apply_mean_norm_trend.__doc__ = orig_apply_mnt.__doc__
+        fbase.apply_mean_norm_trend = apply_mean_norm_trend if fused else orig_apply_mnt
+
         # mode radii (row f4)
         orig_sample_ln_pdf = _STATE["orig_sample_ln_pdf"]
         pdf_models = {getattr(cmodels, name): name for name in _lib.PDF_KINDS if hasattr(cmodels, name)}
@@ -425,5 +456,6 @@ def disable():
         _STATE["fsrf"].SRF.__call__ = _STATE["orig_srf_call"]
         _STATE["kbase"].Krige.__call__ = _STATE["orig_krige_call"]
         _STATE["grng"].RNG.sample_ln_pdf = _STATE["orig_sample_ln_pdf"]
+        fbase.apply_mean_norm_trend = _STATE["orig_apply_mnt"]
         config.USE_GSTOOLS_B200 = False
         _STATE["enabled"] = False

@@ -1,0 +1,53 @@
+"""The reference's OWN test files, rerun on the GPU box with the B200 backend enabled
+(gstools_b200.enable(): summation, Fourier summation, kriging evaluation, fused epilogues, native
+radius sampler).  The files come from baseline/_ref/reference_tests (copied there, git-ignored, by
+__graft_entry__.build() in the build container); the stand-ins of tools/refstubs replace the
+third-party packages that are not installed (emcee, hankel, meshio, pyevtk, gstools_cython)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import refharness
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FILES = ["test_srf.py", "test_randmeth.py", "test_incomprrandmeth.py", "test_fouriergen.py", "test_krige.py",
+         "test_condition.py", "test_field.py", "test_temporal.py", "test_latlon.py", "test_pgs.py",
+         "test_transform.py", "test_rng.py", "test_normalizer.py"]
+# need packages that are not installed here (meshio) or the native variogram estimator (out of scope)
+DESELECT = ["test_srf.py::TestSRF::test_meshio", "test_latlon.py::TestLatLon::test_cond_srf",
+            "test_latlon.py::TestLatLon::test_krige", "test_latlon.py::TestLatLon::test_vario_est",
+            "test_normalizer.py::TestNormalizer::test_auto_fit"]
+
+
+def _suite_dir():
+    for cand in ("/root/reference/tests", os.path.join(REPO, "baseline", "_ref", "reference_tests")):
+        if os.path.isfile(os.path.join(cand, "test_srf.py")):
+            return cand
+    return None
+
+
+@pytest.mark.skipif(_suite_dir() is None or not refharness.have_reference(),
+                    reason="reference test files not present")
+def test_reference_test_files_pass_with_the_backend_enabled(tmp_path):
+    suite = _suite_dir()
+    report = tmp_path / "counters.json"
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(REPO, "tests"), refharness.STUBS, refharness.reference_root(),
+                                         REPO, env.get("PYTHONPATH", "")])
+    env["GSB200_SUITE_REPORT"] = str(report)
+    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p", "b200_enable_plugin",
+           "--rootdir", str(tmp_path)]
+    cmd += [os.path.join(suite, f) for f in FILES]
+    for d in DESELECT:
+        cmd += ["--deselect", os.path.join(suite, d)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=str(tmp_path), timeout=1500)
+    tail = "\n".join(res.stdout.splitlines()[-15:])
+    assert res.returncode == 0, tail + "\n" + res.stderr[-2000:]
+    assert " passed" in tail and "failed" not in tail
+    counters = json.load(open(report))
+    # the tests really ran on the GPU: all three kernel families were used
+    assert counters["launches"] > 500 and counters["direct_calls"] > 50 and counters["krige_calls"] > 20, counters

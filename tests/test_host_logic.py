@@ -562,3 +562,47 @@ def test_native_radius_sampler_reference_literals_and_fallthrough(gsb, monkeypat
     with pytest.raises(ValueError):      # odd number of walkers
         real("Exponential", 3, 1.0, 0.0, ("MT19937", np.zeros(624, np.uint32), 624),
              ("MT19937", np.zeros(624, np.uint32), 624), np.ones(51), 1, 1)
+
+
+@needs_ref
+def test_fast_post_field_epilogue_matches_reference_bits(gsb, oracle_mod, monkeypatch):
+    """The shortcut for Field.post_field's mean / normalizer / trend step (constant terms, identity
+    normalizer) returns the reference's bits, mutates its input like the reference, and steps aside for
+    everything else."""
+    gs = refharness.import_gstools()
+    from gstools.field import base as fbase
+    from gstools.normalizer import LogNormal, Normalizer
+
+    orig = fbase.apply_mean_norm_trend
+    rs = np.random.RandomState(0)
+    base = rs.normal(size=(7, 5))
+    base[2, 3] = np.nan
+    base[0, 0] = -0.0
+    pos = [np.arange(7.0), np.arange(5.0)]
+    cases = [dict(mean=None, trend=None), dict(mean=1.5, trend=None), dict(mean=-0.25, trend=3.0),
+             dict(mean=np.array([2.0]), trend=0.0)]
+    gsb.enable()
+    try:
+        fast = fbase.apply_mean_norm_trend
+        assert fast is not orig
+        for kw in cases:
+            a, b = base.copy(), base.copy()
+            want = orig(pos, a, normalizer=Normalizer(), mesh_type="structured", check_shape=False, **kw)
+            got = fast(pos, b, normalizer=Normalizer(), mesh_type="structured", check_shape=False, **kw)
+            assert np.array_equal(got, want, equal_nan=True) and np.array_equal(np.signbit(got), np.signbit(want))
+            assert np.array_equal(a, b, equal_nan=True)              # same in-place effect on the input
+            assert got is not b
+        # not the shortcut's business: callable mean, other normalizers, shape checks, stacked fields
+        for kw in (dict(mean=lambda x, y: x + y), dict(normalizer=LogNormal()), dict(check_shape=True),
+                   dict(stacked=True)):
+            a, b = np.abs(base.copy()) + 1, np.abs(base.copy()) + 1
+            args = dict(normalizer=Normalizer(), mesh_type="structured", check_shape=False)
+            args.update(kw)
+            if kw.get("stacked"):
+                a, b = a[None], b[None]
+            want = orig(pos, a, **args)
+            got = fast(pos, b, **args)
+            assert np.array_equal(np.asarray(got), np.asarray(want), equal_nan=True)
+    finally:
+        gsb.disable()
+    assert fbase.apply_mean_norm_trend is orig
