@@ -40,11 +40,11 @@ def test_reference_test_files_pass_with_the_backend_enabled(tmp_path):
                                          REPO, env.get("PYTHONPATH", "")])
     env["GSB200_SUITE_REPORT"] = str(report)
     cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p", "b200_enable_plugin",
-           "--rootdir", str(tmp_path)]
-    cmd += [os.path.join(suite, f) for f in FILES]
+           "--rootdir", suite, "-c", os.devnull]
+    cmd += FILES                                   # node ids relative to the suite directory
     for d in DESELECT:
-        cmd += ["--deselect", os.path.join(suite, d)]
-    res = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=str(tmp_path), timeout=1500)
+        cmd += ["--deselect", d]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=suite, timeout=1500)
     tail = "\n".join(res.stdout.splitlines()[-15:])
     assert res.returncode == 0, tail + "\n" + res.stderr[-2000:]
     assert " passed" in tail and "failed" not in tail
