@@ -427,9 +427,9 @@ def _krige(krig_mat, krig_vecs, cond, want_var):
         raise ValueError("krig_mat (K, K), krig_vecs (K, n), cond (K,)")
     size, n = mat.shape[0], kv.shape[1]
     kv, ld = _rows_contiguous(kv)
-    field = np.empty(n, dtype=np.float64)
+    field = _empty_host((n,))
     if want_var:
-        error = np.empty(n, dtype=np.float64)
+        error = _empty_host((n,))
         rc = lib.gsb_calc_field_krige_and_variance(_ptr(mat), _ptr(kv), ld, _ptr(c), size, n,
                                                    _ptr(field), _ptr(error), _lib.MEM_HOST,
                                                    get_device(), None)
@@ -524,8 +524,8 @@ def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=
             raise ValueError("tail_rows must have shape (krige_size - cond_no - unbiased, n)")
         tail, tail_ld = _rows_contiguous(tail)
         tail_ptr = _ptr(tail)
-    field = np.empty(n, dtype=np.float64)
-    error = np.empty(n, dtype=np.float64) if return_var else None
+    field = _empty_host((n,))
+    error = _empty_host((n,)) if return_var else None
     err_ptr = _ptr(error) if return_var else None
     if axes is not None:
         rc = lib.gsb_krige_evaluate_structured(ctypes.byref(model), _ptr(mat), _ptr(c), size, _ptr(cp),
