@@ -80,7 +80,7 @@ struct DeviceState {
     cudaEvent_t events[N_EVENTS] = {};
     cudaEvent_t chunk_events[N_CHUNK_EVENTS] = {};      // A generation of chunk c done
     cudaEvent_t contract_events[N_CHUNK_EVENTS] = {};   // contraction of chunk c done
-    std::mutex call_mutex;                     // one structured call at a time per device
+    std::mutex call_mutex;                     // one structured / host-route call at a time per device
 };
 static std::mutex g_dev_mutex;
 static DeviceState g_dev[64];
@@ -275,6 +275,8 @@ static int summate_impl(const double *cov, const double *z1, const double *z2, c
     }
 
     // ---- host buffers: stage modes once, then pipeline point chunks over two streams ----
+    // (the library's own streams and events are per device: one host-route call at a time)
+    std::lock_guard<std::mutex> lock(dev->call_mutex);
     cudaStream_t s0 = dev->streams[0];
     Scratch scr0(s0);
     double *d_cov, *d_z1, *d_z2, *d_recs, *d_sf = nullptr;
@@ -902,6 +904,7 @@ static int krige_impl(const double *mat, const double *kv, int64_t ld, const dou
         return krige_on_device(op, kv, ld, n, false, field, want_var ? error : nullptr, *dev, scr, st);
     }
     // ---- host buffers: operand once, then column chunks of krig_vecs double buffered over two streams ----
+    std::lock_guard<std::mutex> lock(dev->call_mutex);
     cudaStream_t s0 = dev->streams[0];
     Scratch scr0(s0), scr1(dev->streams[1]);
     double *d_mat, *d_cond;
@@ -1121,6 +1124,7 @@ static int krige_eval_impl(KrigeEvalArgs a, bool structured, int mem, int device
     if (mem == GSB_MEM_DEVICE)
         return krige_eval_on_device(a, structured ? &mesh : nullptr, *dev, static_cast<cudaStream_t>(stream));
 
+    std::lock_guard<std::mutex> lock(dev->call_mutex);
     cudaStream_t s0 = dev->streams[0];
     Scratch scr(s0);
     KrigeEvalArgs d = a;

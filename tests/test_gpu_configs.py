@@ -136,3 +136,39 @@ def test_config5_full_ensemble_256x128cubed(gsb, oracle_mod):
     # one realisation computed alone == the same realisation inside the batch (seed sharding)
     single = gsb.summate_structured(tc[37], t1[37], t2[37], axes)
     assert torch.equal(single, out[37])
+
+
+def test_beyond_the_configs_1024cubed_index_arithmetic(gsb, oracle_mod):
+    """Maximum-size case: 1024^3 nodes (2^30 points, 8.6 GB of output, element offsets beyond 2^31 for
+    the vector field).  Device resident; sampled against the oracle, plus the x-plane symmetry
+    u(axis0 reversed) == u reversed, which touches every row chunk."""
+    import torch
+
+    cfg = bc.config2(512)
+    dev = torch.device("cuda:0")
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~25 GB of device memory")
+    tc, t1, t2 = (torch.tensor(cfg[k][..., :64], device=dev) for k in ("cov", "z1", "z2"))
+    ax = [np.arange(1024.0), np.arange(1024.0) * 0.5, np.arange(1024.0) * 0.25]
+    axes = [torch.tensor(a, device=dev) for a in ax]
+    out = gsb.summate_structured(tc, t1, t2, axes)
+    assert tuple(out.shape) == (1024, 1024, 1024)
+    n = 1024 ** 3
+    rs = np.random.RandomState(5)
+    idx = np.unique(np.concatenate([rs.randint(0, n, 20000), [0, n - 1, n // 2, 2 ** 29 + 12345]]))
+    got = out.reshape(-1)[torch.tensor(idx, device=dev)].cpu().numpy()
+    want = oracle_mod.summate(cfg["cov"][:, :64], cfg["z1"][:64], cfg["z2"][:64], bc.grid_points(ax, None, idx))
+    assert np.max(np.abs(got - want)) * np.sqrt(1.0 / 64) <= TOL
+    rev = gsb.summate_structured(tc, t1, t2, [axes[0].flip(0), axes[1], axes[2]])
+    assert torch.equal(rev, out.flip(0))
+    del rev, out
+    # vector field on 1024 x 1024 x 768: 3 x 0.8e9 elements, component offsets beyond 2^31
+    axes[2] = axes[2][:768]
+    vec = gsb.summate_incompr_structured(tc, t1, t2, axes)
+    assert tuple(vec.shape) == (3, 1024, 1024, 768)
+    nv = 1024 * 1024 * 768
+    idx = np.unique(np.concatenate([rs.randint(0, nv, 5000), [0, nv - 1]]))
+    gotv = vec.reshape(3, -1)[:, torch.tensor(idx, device=dev)].cpu().numpy()
+    wantv = oracle_mod.summate_incompr(cfg["cov"][:, :64], cfg["z1"][:64], cfg["z2"][:64],
+                                       bc.grid_points([ax[0], ax[1], ax[2][:768]], None, idx))
+    assert np.max(np.abs(gotv - wantv)) * np.sqrt(1.0 / 64) <= TOL

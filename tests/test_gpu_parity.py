@@ -392,3 +392,39 @@ def test_structured_chunking_is_invisible(gsb, oracle_mod):
         gsb.set_option("scratch_mb", 3072)
         gsb.set_option("force_path", 0)
         gsb.set_option("sep_path", 0)
+
+
+def test_concurrent_calls_from_python_threads(gsb, oracle_mod):
+    """SURVEY 8(b) threading: the reference's native functions are re-entrant and release the GIL;
+    so does the C ABI (ctypes drops the GIL, per-device work is serialised by a mutex).  Several
+    Python threads calling different entry points at once get the single-threaded bits."""
+    import threading
+
+    cov, z1, z2 = synth_modes(3, 300, seed=9)
+    pos = np.random.RandomState(4).uniform(0, 80, (3, 60001))
+    axes = [np.arange(20.0), np.arange(140.0), np.arange(150.0)]
+    rs = np.random.RandomState(8)
+    kmat, kcond, kv = rs.normal(size=(90, 90)), rs.normal(size=90), rs.uniform(-1, 1, (90, 30000))
+    jobs = {
+        "flat": lambda: gsb.summate(cov, z1, z2, pos),
+        "vec": lambda: gsb.summate_incompr(cov, z1, z2, pos[:, :20000]),
+        "mesh": lambda: gsb.summate_structured(cov, z1, z2, axes),
+        "krige": lambda: np.stack(gsb.calc_field_krige_and_variance(kmat, kv, kcond)),
+    }
+    want = {k: np.array(fn()) for k, fn in jobs.items()}
+    got, errors = {}, []
+
+    def work(name, rep):
+        try:
+            got[(name, rep)] = np.array(jobs[name]())
+        except Exception as exc:  # pragma: no cover
+            errors.append((name, exc))
+
+    threads = [threading.Thread(target=work, args=(n, r)) for r in range(3) for n in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (name, rep), val in got.items():
+        assert np.array_equal(val, want[name]), name
