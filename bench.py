@@ -399,7 +399,12 @@ def run_b200_arm(args, cfg):
             except Exception:
                 traffic = None
         roofline = {
-            "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            # DMMA.8x8x4 issues on the tensor pipe (ncu: sm__pipe_tensor_cycles_active), the direct
+            # kernel's DFMAs on the FP64 pipe; both have the same measured fp64 peak
+            "bound": "tensor" if structured else "fp64",
+            "bound_detail": ("fp64 tensor path (DMMA.8x8x4), FP64-pipe roofline of BASELINE.json" if structured
+                             else "FP64 pipe (DFMA), FP64-pipe roofline of BASELINE.json"),
+            "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": (achieved / peak_tflops) if achieved else None, "traffic": traffic,
             "kernel": "separable_kernel (DMMA.8x8x4)" if structured else "direct_kernel",
             "kernel_ms_per_launch": 1e3 * kern_s, "launches_timed": kern_n,
