@@ -468,6 +468,72 @@ def cov_model_spec(kind, var, len_rescaled, sill=None, param=0.0, exact=False):
     return spec
 
 
+def _krige_evaluate_device(lib, model, krig_mat, cond, cond_pos, pos, axes, matrix, unbiased, tail_rows,
+                           return_var):
+    """Device-resident variant: CUDA tensors in, CUDA tensors out, work enqueued on the current stream."""
+    torch = _torch()
+    cands = [krig_mat, cond, cond_pos, pos, tail_rows] + (list(axes) if axes is not None else [])
+    dev = next(x.device for x in cands if _is_cuda_tensor(x))
+
+    def prep(x):
+        return torch.as_tensor(x, dtype=torch.float64, device=dev).contiguous()
+
+    mat, c, cp = prep(krig_mat), prep(cond), prep(cond_pos)
+    if mat.ndim != 2 or mat.shape[0] != mat.shape[1] or tuple(c.shape) != (mat.shape[0],) or cp.ndim != 2:
+        raise ValueError("krig_mat (K, K), cond (K,), cond_pos (dim, cond_no)")
+    size, (dim, cond_no) = mat.shape[0], cp.shape
+    n_tail = size - cond_no - int(bool(unbiased))
+    if n_tail < 0:
+        raise ValueError("cond_no + unbiased exceeds the kriging system size")
+    if (pos is None) == (axes is None):
+        raise ValueError("give either pos (dim, n) or axes")
+    if axes is not None:
+        ax = [prep(a).reshape(-1) for a in axes]
+        if len(ax) != dim:
+            raise ValueError("number of axes must equal the dim of cond_pos")
+        lens = np.array([int(a.shape[0]) for a in ax], dtype=np.int64)
+        shape, n = tuple(int(v) for v in lens), int(np.prod(lens))
+        cat = torch.cat(ax)
+        mat_ptr = None
+        if matrix is not None:
+            if _is_cuda_tensor(matrix):
+                matrix = matrix.detach().cpu().numpy()
+            m = np.ascontiguousarray(_as_f64(matrix, "matrix"))
+            if m.shape != (dim, dim):
+                raise ValueError("matrix must have shape (dim, dim)")
+            mat_ptr = _ptr(m)            # host pointer: the ABI reads the tiny matrix on the host
+    else:
+        p = prep(pos)
+        if p.ndim != 2 or p.shape[0] != dim:
+            raise ValueError("pos must have shape (dim, n) with the dim of cond_pos")
+        n, shape = p.shape[1], (p.shape[1],)
+    tail_ptr, tail_ld = None, max(n, 1)
+    if n_tail > 0:
+        if tail_rows is None:
+            raise ValueError(f"{n_tail} drift rows expected in tail_rows")
+        tail = prep(tail_rows).reshape(n_tail, -1)
+        if tail.shape[1] != n:
+            raise ValueError("tail_rows must have shape (krige_size - cond_no - unbiased, n)")
+        tail_ptr = tail.data_ptr()
+    field = torch.empty(n, dtype=torch.float64, device=dev)
+    error = torch.empty(n, dtype=torch.float64, device=dev) if return_var else None
+    err_ptr = error.data_ptr() if return_var else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if axes is not None:
+        rc = lib.gsb_krige_evaluate_structured(ctypes.byref(model), mat.data_ptr(), c.data_ptr(), size,
+                                               cp.data_ptr(), cond_no, dim, cat.data_ptr(),
+                                               lens.ctypes.data_as(_lib._c_int64_p), mat_ptr,
+                                               int(bool(unbiased)), tail_ptr, tail_ld, field.data_ptr(), err_ptr,
+                                               _lib.MEM_DEVICE, dev.index, stream)
+    else:
+        rc = lib.gsb_krige_evaluate(ctypes.byref(model), mat.data_ptr(), c.data_ptr(), size, cp.data_ptr(),
+                                    cond_no, dim, p.data_ptr(), max(n, 1), n, int(bool(unbiased)), tail_ptr,
+                                    tail_ld, field.data_ptr(), err_ptr, _lib.MEM_DEVICE, dev.index, stream)
+    _lib.check(rc, "krige_evaluate")
+    field = field.reshape(shape)
+    return (field, error.reshape(shape)) if return_var else field
+
+
 def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=None, unbiased=True,
                    tail_rows=None, return_var=True):
     """The evaluation loop of ``Krige.__call__`` (krige/base.py:278-294) on the device.
@@ -483,6 +549,10 @@ def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=
     lib = _lib.load()
     if not isinstance(model, _lib.CovModelSpec):
         model = cov_model_spec(**model)
+    tensors = [krig_mat, cond, cond_pos, pos, tail_rows] + (list(axes) if axes is not None else [])
+    if any(_is_cuda_tensor(x) for x in tensors):
+        return _krige_evaluate_device(lib, model, krig_mat, cond, cond_pos, pos, axes, matrix, unbiased,
+                                      tail_rows, return_var)
     mat = np.ascontiguousarray(_as_f64(krig_mat, "krig_mat"))
     c = np.ascontiguousarray(_as_f64(cond, "cond"))
     cp = np.ascontiguousarray(_as_f64(cond_pos, "cond_pos"))

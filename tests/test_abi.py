@@ -106,3 +106,29 @@ def test_krige_argument_errors_need_no_gpu(gsb):
     # n == 0 returns without touching a device
     f, e = gsb.calc_field_krige_and_variance(np.zeros((3, 3)), np.zeros((3, 0)), np.zeros(3))
     assert f.shape == (0,) and e.shape == (0,)
+
+
+def _build_c_consumer(tmp_path, gsb):
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    lib = gsb._lib.lib_path()
+    exe = str(tmp_path / "abi_smoke")
+    cmd = [cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(REPO, "include"),
+           os.path.join(REPO, "tests", "c_abi", "abi_smoke.c"), "-o", exe, lib, "-lm",
+           "-Wl,-rpath," + os.path.dirname(lib)]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_header_is_plain_c_and_library_links_from_c(gsb, tmp_path):
+    """include/gsb200.h compiles as strict C99 and a C program can call the library (argument errors
+    need no device)."""
+    import subprocess
+
+    exe = _build_c_consumer(tmp_path, gsb)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "abi ok" in out.stdout, out.stderr

@@ -277,3 +277,31 @@ def test_fast_krige_and_condsrf_equal_reference_path(gsb, mesh):
     assert np.max(np.abs(got_f - want_f)) <= 1e-9 * np.sqrt(model.var)
     assert np.max(np.abs(got_v - want_v)) <= 1e-9 * model.var
     assert np.max(np.abs(got_c - want_c)) <= 1e-8 * np.sqrt(model.var)   # sqrt(krige_var) near data amplifies
+
+
+def test_krige_evaluate_device_tensors(gsb):
+    """CUDA tensors in, CUDA tensors out: the same bits as the host-array call (flat and mesh, with a
+    drift row, field only)."""
+    import torch
+
+    rs = np.random.RandomState(12)
+    C, n = 70, 2600
+    cond_pos, pos = rs.uniform(0, 25, (3, C)), rs.uniform(0, 25, (3, n))
+    K = C + 2
+    mat, cond, tail = rs.normal(size=(K, K)) / K, np.concatenate([rs.normal(size=C), [0.0, 0.0]]), rs.normal(size=(1, n))
+    spec = dict(kind="Spherical", var=1.4, len_rescaled=9.0, sill=1.5, exact=True)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+    hf, he = gsb.krige_evaluate(spec, mat, cond, cond_pos, pos=pos, tail_rows=tail)
+    df, de = gsb.krige_evaluate(spec, t(mat), t(cond), t(cond_pos), pos=t(pos), tail_rows=t(tail))
+    assert df.is_cuda and np.array_equal(df.cpu().numpy(), hf) and np.array_equal(de.cpu().numpy(), he)
+    axes = [np.arange(10.0), np.linspace(0, 20, 13), np.linspace(0, 25, 20)]
+    mtx = np.array([[0.9, 0.1, 0.0], [-0.1, 1.1, 0.0], [0.0, 0.2, 2.0]])
+    mesh_tail = rs.normal(size=(1, 10 * 13 * 20))
+    hf, he = gsb.krige_evaluate(spec, mat, cond, cond_pos, axes=axes, matrix=mtx, tail_rows=mesh_tail)
+    df, de = gsb.krige_evaluate(spec, t(mat), t(cond), t(cond_pos), axes=[t(a) for a in axes], matrix=mtx,
+                                tail_rows=t(mesh_tail))
+    assert tuple(df.shape) == (10, 13, 20)
+    assert np.array_equal(df.cpu().numpy(), hf) and np.array_equal(de.cpu().numpy(), he)
+    f_only = gsb.krige_evaluate(spec, t(mat), t(cond), t(cond_pos), pos=t(pos), tail_rows=t(tail), return_var=False)
+    assert np.array_equal(f_only.cpu().numpy(), gsb.krige_evaluate(spec, mat, cond, cond_pos, pos=pos, tail_rows=tail,
+                                                                   return_var=False))

@@ -428,3 +428,14 @@ def test_concurrent_calls_from_python_threads(gsb, oracle_mod):
     assert not errors, errors
     for (name, rep), val in got.items():
         assert np.array_equal(val, want[name]), name
+
+
+def test_c_program_calls_the_library_on_the_gpu(gsb, tmp_path):
+    """The drop-in boundary from plain C: one summation and one kriging evaluation against closed forms."""
+    import subprocess
+
+    from test_abi import _build_c_consumer
+
+    exe = _build_c_consumer(tmp_path, gsb)
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "gpu ok" in out.stdout, out.stderr + out.stdout
