@@ -543,7 +543,8 @@ def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=
     an unbiased system, then ``tail_rows`` (drift rows, evaluated by the caller) -- are generated
     on the GPU and contracted with ``krig_mat`` / ``cond`` there.  Evaluation points: ``pos``
     (dim, n), isometrised, or the mesh ``axes`` (+ isometrisation ``matrix``).  Host arrays in,
-    host arrays out.  Returns ``(field, error)`` or ``field`` (``return_var=False``); for a mesh
+    host arrays out -- or CUDA tensors in, CUDA tensors out (nothing is copied, work is enqueued on the
+    current torch stream).  Returns ``(field, error)`` or ``field`` (``return_var=False``); for a mesh
     the results have the mesh shape.
     """
     lib = _lib.load()
