@@ -117,345 +117,366 @@ def _same(a, b):
     return a.shape == b.shape and np.array_equal(a, b)
 
 
-def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True):
-    """Route ``RandMeth`` / ``IncomprRandMeth`` summation of ``gstools`` to the B200 backend."""
-    import gstools  # the user's (unmodified) installation
-    from gstools import config
-    from gstools.field import base as fbase
-    from gstools.field import generator as gen
-    from gstools.field import srf as fsrf
-    from gstools.krige import base as kbase
-    from gstools.random import rng as grng
-    from gstools.normalizer import Normalizer
-    from gstools.tools.geometric import matrix_isometrize
+class _Refs:
+    """The reference modules and their original attributes, captured once at the first ``enable()``."""
 
-    with _LOCK:
-        if not _STATE["enabled"]:
-            _STATE.update(orig_summate=gen._summate, orig_summate_incompr=gen._summate_incompr,
-                          orig_summate_fourier=gen._summate_fourier,
-                          orig_pre_pos=fbase.Field.pre_pos, orig_srf_call=fsrf.SRF.__call__,
-                          orig_krige=kbase._calc_field_krige, orig_krige_call=kbase.Krige.__call__,
-                          orig_sample_ln_pdf=grng.RNG.sample_ln_pdf, grng=grng,
-                          orig_apply_mnt=fbase.apply_mean_norm_trend,
-                          orig_krige_var=kbase._calc_field_krige_and_variance,
-                          gen=gen, fbase=fbase, fsrf=fsrf, kbase=kbase, config=config)
-        orig_s, orig_si = _STATE["orig_summate"], _STATE["orig_summate_incompr"]
-        orig_sf = _STATE["orig_summate_fourier"]
-        orig_pre_pos = _STATE["orig_pre_pos"]
-        config.USE_GSTOOLS_B200 = True
-        config._GSTOOLS_B200_AVAIL = True
-
-        def _summate(cov_samples, z_1, z_2, pos, num_threads=None):
-            """A wrapper function for calling the randomization algorithms (B200 first)."""
-            if getattr(config, "USE_GSTOOLS_B200", False):
-                lazy = _lookup_lazy(pos)
-                if lazy is not None:
-                    return backend.summate_structured(cov_samples, z_1, z_2, lazy[0],
-                                                      lazy[1]).reshape(-1)
-                return backend.summate(cov_samples, z_1, z_2, pos, num_threads)
-            return orig_s(cov_samples, z_1, z_2, _materialise(pos), num_threads)
-
-        def _summate_incompr(cov_samples, z_1, z_2, pos, num_threads=None):
-            """A wrapper function for calling the incompr. randomization algorithms (B200 first)."""
-            if getattr(config, "USE_GSTOOLS_B200", False):
-                lazy = _lookup_lazy(pos)
-                if lazy is not None:
-                    out = backend.summate_incompr_structured(cov_samples, z_1, z_2, lazy[0], lazy[1])
-                    return out.reshape(out.shape[0], -1)
-                return backend.summate_incompr(cov_samples, z_1, z_2, pos, num_threads)
-            return orig_si(cov_samples, z_1, z_2, _materialise(pos), num_threads)
-
-        def _summate_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads=None):
-            """A wrapper function for calling the Fourier algorithms (B200 first)."""
-            if getattr(config, "USE_GSTOOLS_B200", False):
-                lazy = _lookup_lazy(pos)
-                if lazy is not None:
-                    return backend.summate_fourier_structured(spectrum_factor, modes, z_1, z_2,
-                                                              lazy[0], lazy[1]).reshape(-1)
-                return backend.summate_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads)
-            return orig_sf(spectrum_factor, modes, z_1, z_2, _materialise(pos), num_threads)
-
-        def _materialise(pos):
-            lazy = _lookup_lazy(pos)
-            if lazy is None:
-                return pos
-            grid = gen.generate_grid(lazy[0])
-            return grid if lazy[1] is None else np.dot(lazy[1], grid)
-
-        gen._summate = _summate
-        gen._summate_incompr = _summate_incompr
-        gen._summate_fourier = _summate_fourier
-
-        # kriging evaluation (row f1): same scheme, wrappers at krige/base.py:42-61, looked up as module
-        # globals from Krige._summate (base.py:307-317)
-        orig_k, orig_kv = _STATE["orig_krige"], _STATE["orig_krige_var"]
-
-        def _calc_field_krige(krig_mat, krig_vecs, cond, num_threads=None):
-            """A wrapper function for calling the krige algorithms (B200 first)."""
-            if getattr(config, "USE_GSTOOLS_B200", False):
-                return backend.calc_field_krige(krig_mat, krig_vecs, cond, num_threads)
-            return orig_k(krig_mat, krig_vecs, cond, num_threads)
-
-        def _calc_field_krige_and_variance(krig_mat, krig_vecs, cond, num_threads=None):
-            """A wrapper function for calling the krige algorithms (B200 first)."""
-            if getattr(config, "USE_GSTOOLS_B200", False):
-                return backend.calc_field_krige_and_variance(krig_mat, krig_vecs, cond, num_threads)
-            return orig_kv(krig_mat, krig_vecs, cond, num_threads)
-
-        kbase._calc_field_krige = _calc_field_krige
-        kbase._calc_field_krige_and_variance = _calc_field_krige_and_variance
-
-        if lazy_grid:
-            exact = (gen.RandMeth, gen.IncomprRandMeth, gen.Fourier)
-
-            def pre_pos(self, pos=None, mesh_type="unstructured", info=False):
-                generator = getattr(self, "_generator", None)
-                model = getattr(self, "model", None)
-                lazy_ok = (
-                    getattr(config, "USE_GSTOOLS_B200", False)
-                    and type(generator) in exact
-                    and model is not None
-                    and not model.latlon
-                    and model.dim >= 2
-                )
-                if not lazy_ok:
-                    return orig_pre_pos(self, pos, mesh_type, info)
-                info_ret = {"deleted": False}
-                if pos is None:
-                    if self.pos is None:
-                        raise ValueError("Field: no position tuple 'pos' present")
-                else:
-                    info_ret = self.set_pos(pos, mesh_type, info=True)
-                if self.mesh_type == "unstructured" or model.field_dim != model.dim \
-                        or getattr(generator, "zero_var", False):
-                    out = orig_pre_pos(self, None, self.mesh_type, False)
-                    return out + info * (info_ret,)
-                matrix = matrix_isometrize(model.dim, model.angles, model.anis)
-                lazy = LazyGridPos(self.pos, matrix)
-                return (lazy, self.field_shape) + info * (info_ret,)
-
-            pre_pos.__doc__ = orig_pre_pos.__doc__
-            fbase.Field.pre_pos = pre_pos
-        else:
-            fbase.Field.pre_pos = orig_pre_pos
-
-        orig_srf_call = _STATE["orig_srf_call"]
-        _STATE["cache_krige"] = bool(cache_krige)
-
-        def _fused_epilogue(srf, post_process):
-            """gsb_epilogue equal to everything SRF.__call__ does after the summation, or None."""
-            generator = srf.generator
-            model = srf.model
-            if type(generator) not in (gen.RandMeth, gen.IncomprRandMeth) or model.nugget > 0:
-                return None
-            vec = type(generator) is gen.IncomprRandMeth
-            if vec and model.dim not in (2, 3):
-                return None
-            root = np.sqrt(model.var / generator._mode_no)
-            if vec:  # mean_u*e1 + mean_u*sqrt(var/N)*summed + nugget     (generator.py:561-567)
-                e1 = [generator.mean_u * 1.0] + [generator.mean_u * 0.0] * (model.dim - 1)
-                scale, adds = generator.mean_u * root, [tuple(e1), 0.0]
-            else:    # sqrt(var/N)*summed + nugget                         (generator.py:269-270)
-                scale, adds = root, [0.0]
-            if post_process:  # field += mean; denormalize; field += trend  (normalizer/tools.py:99-103)
-                if type(srf.normalizer) is not Normalizer:
-                    return None
-                for value in (srf.mean, srf.trend):
-                    term = _const_term(value, srf.value_type, model.dim)
-                    if term is None:
-                        return None
-                    adds.append(term)
-            return backend.make_epilogue(scale, adds)
-
-        def srf_call(self, pos=None, seed=np.nan, point_volumes=0.0, mesh_type="unstructured",
-                     post_process=True, store=True):
-            if not (getattr(config, "USE_GSTOOLS_B200", False) and np.isscalar(point_volumes)
-                    and np.isclose(point_volumes, 0)
-                    and type(getattr(self, "_generator", None)) in (gen.RandMeth, gen.IncomprRandMeth)):
-                return orig_srf_call(self, pos, seed, point_volumes, mesh_type, post_process, store)
-            name, save = self.get_store_config(store)
-            # update the model/seed in the generator if any changes were made   (srf.py:152)
-            self.generator.update(self.model, seed)
-            generator = self.generator
-            epi = None if generator.zero_var else _fused_epilogue(self, post_process)
-            if epi is None:  # seed already applied: keep it
-                return orig_srf_call(self, pos, np.nan, point_volumes, mesh_type, post_process, store)
-            iso_pos, shape = self.pre_pos(pos, mesh_type)
-            vec = type(generator) is gen.IncomprRandMeth
-            lazy = _lookup_lazy(iso_pos)
-            if lazy is not None:
-                fn = backend.summate_incompr_structured if vec else backend.summate_structured
-                field = fn(generator._cov_sample, generator._z_1, generator._z_2, lazy[0], lazy[1],
-                           epilogue=epi)
-            else:
-                fn = backend.summate_incompr if vec else backend.summate
-                field = fn(generator._cov_sample, generator._z_1, generator._z_2,
-                           np.asarray(iso_pos, dtype=np.double), epilogue=epi)
-            field = np.reshape(field, shape)
-            return self.post_field(field, name, False, save)
-
-        srf_call.__doc__ = orig_srf_call.__doc__
-        fsrf.SRF.__call__ = srf_call if fused else orig_srf_call
-
-        orig_krige_call = _STATE["orig_krige_call"]
+    def __init__(self):
+        import gstools  # the user's (unmodified) installation
+        from gstools import config
         from gstools.covmodel import models as cmodels
+        from gstools.field import base as fbase
+        from gstools.field import generator as gen
+        from gstools.field import srf as fsrf
+        from gstools.krige import base as kbase
+        from gstools.normalizer import Normalizer
+        from gstools.random import rng as grng
+        from gstools.tools.geometric import matrix_isometrize
 
-        device_models = {getattr(cmodels, name): name for name in _lib.COV_TYPES if hasattr(cmodels, name)}
+        self.gstools, self.config, self.cmodels = gstools, config, cmodels
+        self.fbase, self.gen, self.fsrf, self.kbase, self.grng = fbase, gen, fsrf, kbase, grng
+        self.Normalizer, self.matrix_isometrize = Normalizer, matrix_isometrize
+        # (owner, attribute) -> original; everything enable() may rebind, restored by disable()
+        self.orig = {(o, a): getattr(o, a) for o, a in (
+            (gen, "_summate"), (gen, "_summate_incompr"), (gen, "_summate_fourier"),
+            (kbase, "_calc_field_krige"), (kbase, "_calc_field_krige_and_variance"),
+            (fbase.Field, "pre_pos"), (fsrf.SRF, "__call__"), (kbase.Krige, "__call__"),
+            (fbase, "apply_mean_norm_trend"), (grng.RNG, "sample_ln_pdf"))}
+        self.cache_krige = True
 
-        def _cov_spec(krige):
-            """gsb_cov_model of ``krige.model`` (exact class only: a subclass may override cor)."""
-            model = krige.model
-            kind = device_models.get(type(model))
-            if kind is None or model.latlon or getattr(model, "temporal", False) or model.dim > 4:
-                return None
-            param = float(getattr(model, "alpha", 0.0)) if kind in ("Stable", "Rational") else 0.0
-            return backend.cov_model_spec(kind, model.var, model.len_rescaled, model.sill, param, krige.exact)
+    def on(self):
+        return getattr(self.config, "USE_GSTOOLS_B200", False)
 
-        def krige_call(self, pos=None, mesh_type="unstructured", ext_drift=None, chunk_size=None,
-                       only_mean=False, return_var=True, post_process=True, store=True):
-            spec = None
-            if getattr(config, "USE_GSTOOLS_B200", False) and not only_mean and self.cond_no > 0:
-                spec = _cov_spec(self)
-            if spec is None:
-                return orig_krige_call(self, pos, mesh_type, ext_drift, chunk_size, only_mean,
-                                       return_var, post_process, store)
-            fld_cnt = 2 if return_var else 1
-            name, save = self.get_store_config(store, None, fld_cnt)       # base.py:264-267
-            # positions: keep a structured mesh as axes + isometrisation matrix (no host expansion)
-            # unless functional drift terms need the expanded positions (base.py:379-383)
-            if pos is not None:
-                self.set_pos(pos, mesh_type)
-            elif self.pos is None:
+
+def _like(new, orig):
+    new.__doc__ = orig.__doc__
+    return new
+
+
+# ---- native wrappers: generator.py:42-75 and krige/base.py:42-61 ------------------------------------
+def _build_native_wrappers(r):
+    gen, kbase = r.gen, r.kbase
+    orig_s, orig_si, orig_sf = (r.orig[(gen, n)] for n in ("_summate", "_summate_incompr", "_summate_fourier"))
+    orig_k, orig_kv = (r.orig[(kbase, n)] for n in ("_calc_field_krige", "_calc_field_krige_and_variance"))
+
+    def _materialise(pos):
+        lazy = _lookup_lazy(pos)
+        if lazy is None:
+            return pos
+        grid = gen.generate_grid(lazy[0])
+        return grid if lazy[1] is None else np.dot(lazy[1], grid)
+
+    def _summate(cov_samples, z_1, z_2, pos, num_threads=None):
+        """A wrapper function for calling the randomization algorithms (B200 first)."""
+        if r.on():
+            lazy = _lookup_lazy(pos)
+            if lazy is not None:
+                return backend.summate_structured(cov_samples, z_1, z_2, lazy[0], lazy[1]).reshape(-1)
+            return backend.summate(cov_samples, z_1, z_2, pos, num_threads)
+        return orig_s(cov_samples, z_1, z_2, _materialise(pos), num_threads)
+
+    def _summate_incompr(cov_samples, z_1, z_2, pos, num_threads=None):
+        """A wrapper function for calling the incompr. randomization algorithms (B200 first)."""
+        if r.on():
+            lazy = _lookup_lazy(pos)
+            if lazy is not None:
+                out = backend.summate_incompr_structured(cov_samples, z_1, z_2, lazy[0], lazy[1])
+                return out.reshape(out.shape[0], -1)
+            return backend.summate_incompr(cov_samples, z_1, z_2, pos, num_threads)
+        return orig_si(cov_samples, z_1, z_2, _materialise(pos), num_threads)
+
+    def _summate_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads=None):
+        """A wrapper function for calling the Fourier algorithms (B200 first)."""
+        if r.on():
+            lazy = _lookup_lazy(pos)
+            if lazy is not None:
+                return backend.summate_fourier_structured(spectrum_factor, modes, z_1, z_2,
+                                                          lazy[0], lazy[1]).reshape(-1)
+            return backend.summate_fourier(spectrum_factor, modes, z_1, z_2, pos, num_threads)
+        return orig_sf(spectrum_factor, modes, z_1, z_2, _materialise(pos), num_threads)
+
+    # looked up as module globals from Krige._summate (krige/base.py:307-317)
+    def _calc_field_krige(krig_mat, krig_vecs, cond, num_threads=None):
+        """A wrapper function for calling the krige algorithms (B200 first)."""
+        if r.on():
+            return backend.calc_field_krige(krig_mat, krig_vecs, cond, num_threads)
+        return orig_k(krig_mat, krig_vecs, cond, num_threads)
+
+    def _calc_field_krige_and_variance(krig_mat, krig_vecs, cond, num_threads=None):
+        """A wrapper function for calling the krige algorithms (B200 first)."""
+        if r.on():
+            return backend.calc_field_krige_and_variance(krig_mat, krig_vecs, cond, num_threads)
+        return orig_kv(krig_mat, krig_vecs, cond, num_threads)
+
+    return {(gen, "_summate"): _summate, (gen, "_summate_incompr"): _summate_incompr,
+            (gen, "_summate_fourier"): _summate_fourier, (kbase, "_calc_field_krige"): _calc_field_krige,
+            (kbase, "_calc_field_krige_and_variance"): _calc_field_krige_and_variance}
+
+
+# ---- Field.pre_pos: keep a structured mesh as (axes, isometrisation matrix) -------------------------
+def _build_pre_pos(r):
+    gen = r.gen
+    orig_pre_pos = r.orig[(r.fbase.Field, "pre_pos")]
+    exact = (gen.RandMeth, gen.IncomprRandMeth, gen.Fourier)
+
+    def pre_pos(self, pos=None, mesh_type="unstructured", info=False):
+        generator = getattr(self, "_generator", None)
+        model = getattr(self, "model", None)
+        lazy_ok = (r.on() and type(generator) in exact and model is not None and not model.latlon
+                   and model.dim >= 2)
+        if not lazy_ok:
+            return orig_pre_pos(self, pos, mesh_type, info)
+        info_ret = {"deleted": False}
+        if pos is None:
+            if self.pos is None:
                 raise ValueError("Field: no position tuple 'pos' present")
-            lazy = self.mesh_type != "unstructured" and self.int_drift_no == 0
-            if lazy:
-                shape = self.field_shape
-                pnt_cnt = int(np.prod(shape))
-                iso_pos = None
-            else:
-                iso_pos, shape = orig_pre_pos(self, None, self.mesh_type)
-                pnt_cnt = len(iso_pos[0])
-            ext_drift = self._pre_ext_drift(pnt_cnt, ext_drift)               # base.py:279
-            tail = []
-            if self.int_drift_no > 0:
-                chunk_pos = self.model.anisometrize(iso_pos)
-                tail += [np.asarray(f(*chunk_pos), dtype=np.double).reshape(-1) for f in self.drift_functions]
-            if self.ext_drift_no > 0:
-                tail += list(np.asarray(ext_drift, dtype=np.double).reshape(self.ext_drift_no, -1))
-            tail_rows = np.ascontiguousarray(tail) if tail else None
-            kwargs = dict(unbiased=self.unbiased, tail_rows=tail_rows, return_var=return_var)
-            matrix = matrix_isometrize(self.model.dim, self.model.angles, self.model.anis) if lazy else None
-            # The evaluation is a pure function of these inputs.  The reference's ensemble idiom
-            # (examples/06_conditioned_fields/01_2D_condition_ensemble.py:32-35, store=[name, False, False])
-            # re-evaluates the same kriging system for every realisation; remember the last result
-            # and hand out copies (post_field below works in place).
-            cond = self._krige_cond
-            key = dict(spec=bytes(spec), flags=(lazy, bool(self.unbiased), bool(return_var)), matrix=matrix,
-                       mat=self._krige_mat, cond=cond, cpos=self._krige_pos,
-                       pos=self.pos if lazy else iso_pos, tail=tail_rows)
-            cached = getattr(self, "_b200_krige_cache", None) if _STATE.get("cache_krige") else None
-            if cached is not None and cached["key"]["spec"] == key["spec"] and cached["key"]["flags"] == key["flags"] \
-                    and all(_same(cached["key"][k], key[k]) for k in ("mat", "cond", "cpos", "matrix", "pos", "tail")):
-                out = tuple(np.copy(o) for o in cached["out"])
-                _STATE["krige_cache_hits"] = _STATE.get("krige_cache_hits", 0) + 1
-            else:
-                if lazy:
-                    out = backend.krige_evaluate(spec, self._krige_mat, cond, self._krige_pos,
-                                                 axes=self.pos, matrix=matrix, **kwargs)
-                else:
-                    out = backend.krige_evaluate(spec, self._krige_mat, cond, self._krige_pos,
-                                                 pos=iso_pos, **kwargs)
-                out = out if return_var else (out,)
-                if _STATE.get("cache_krige"):
-                    self._b200_krige_cache = dict(key=key, out=tuple(np.copy(o) for o in out))
-            field, krige_var = out if return_var else (out[0], None)
-            field = np.reshape(field, shape)
-            field = self.post_field(field, name[0], post_process, save[0])
-            if return_var:                                                    # base.py:296-300
-                krige_var = np.reshape(np.maximum(self.model.sill - krige_var, 0), shape)
-                krige_var = self.post_field(krige_var, name[1], False, save[1])
-                return field, krige_var
-            return field
+        else:
+            info_ret = self.set_pos(pos, mesh_type, info=True)
+        if self.mesh_type == "unstructured" or model.field_dim != model.dim \
+                or getattr(generator, "zero_var", False):
+            out = orig_pre_pos(self, None, self.mesh_type, False)
+            return out + info * (info_ret,)
+        matrix = r.matrix_isometrize(model.dim, model.angles, model.anis)
+        lazy = LazyGridPos(self.pos, matrix)
+        return (lazy, self.field_shape) + info * (info_ret,)
 
-        krige_call.__doc__ = orig_krige_call.__doc__
-        kbase.Krige.__call__ = krige_call if fused else orig_krige_call
+    return _like(pre_pos, orig_pre_pos)
 
-        # Field.post_field's epilogue (field/base.py:326-336 -> normalizer/tools.py:83-104) for the common
-        # case -- constant mean and trend, identity normalizer: the reference's `denormalize` alone is
-        # five passes over the field (isnan, not, full_like, two masked copies) to return the same
-        # values; here: add in place (the reference mutates its input the same way), copy, add.
-        orig_apply_mnt = _STATE["orig_apply_mnt"]
 
-        def apply_mean_norm_trend(pos, field, mean=None, normalizer=None, trend=None, mesh_type="unstructured",
-                                  value_type="scalar", check_shape=True, stacked=False):
-            fast = (getattr(config, "USE_GSTOOLS_B200", False) and not check_shape and not stacked
-                    and type(normalizer) is Normalizer and isinstance(field, np.ndarray)
-                    and field.dtype == np.double)
-            consts = []
-            if fast:
-                for value in (mean, trend):
-                    value = 0 if value is None else value
-                    if callable(value) or np.size(value) != 1:
-                        fast = False
-                        break
-                    consts.append(np.asarray(value, dtype=np.double).item())
-            if not fast:
-                return orig_apply_mnt(pos, field, mean, normalizer, trend, mesh_type, value_type, check_shape,
-                                      stacked)
-            field += consts[0]                          # tools.py:99-100, in place like the reference
-            out = np.array(field, dtype=np.double)      # identity denormalize returns a fresh array (base.py:93-108)
-            out += consts[1]                            # tools.py:102-103
-            return out
+# ---- SRF.__call__ with the caller epilogue fused into the kernels (row f2) --------------------------
+def _build_srf_call(r):
+    gen = r.gen
+    orig_srf_call = r.orig[(r.fsrf.SRF, "__call__")]
 
-        apply_mean_norm_trend.__doc__ = orig_apply_mnt.__doc__
-        fbase.apply_mean_norm_trend = apply_mean_norm_trend if fused else orig_apply_mnt
+    def _fused_epilogue(srf, post_process):
+        """gsb_epilogue equal to everything SRF.__call__ does after the summation, or None."""
+        generator = srf.generator
+        model = srf.model
+        if type(generator) not in (gen.RandMeth, gen.IncomprRandMeth) or model.nugget > 0:
+            return None
+        vec = type(generator) is gen.IncomprRandMeth
+        if vec and model.dim not in (2, 3):
+            return None
+        root = np.sqrt(model.var / generator._mode_no)
+        if vec:  # mean_u*e1 + mean_u*sqrt(var/N)*summed + nugget     (generator.py:561-567)
+            e1 = [generator.mean_u * 1.0] + [generator.mean_u * 0.0] * (model.dim - 1)
+            scale, adds = generator.mean_u * root, [tuple(e1), 0.0]
+        else:    # sqrt(var/N)*summed + nugget                         (generator.py:269-270)
+            scale, adds = root, [0.0]
+        if post_process:  # field += mean; denormalize; field += trend  (normalizer/tools.py:99-103)
+            if type(srf.normalizer) is not r.Normalizer:
+                return None
+            for value in (srf.mean, srf.trend):
+                term = _const_term(value, srf.value_type, model.dim)
+                if term is None:
+                    return None
+                adds.append(term)
+        return backend.make_epilogue(scale, adds)
 
-        # mode radii (row f4)
-        orig_sample_ln_pdf = _STATE["orig_sample_ln_pdf"]
-        pdf_models = {getattr(cmodels, name): name for name in _lib.PDF_KINDS if hasattr(cmodels, name)}
-        base_ln_pdf = cmodels.CovModel.ln_spectral_rad_pdf
+    def srf_call(self, pos=None, seed=np.nan, point_volumes=0.0, mesh_type="unstructured",
+                 post_process=True, store=True):
+        if not (r.on() and np.isscalar(point_volumes) and np.isclose(point_volumes, 0)
+                and type(getattr(self, "_generator", None)) in (gen.RandMeth, gen.IncomprRandMeth)):
+            return orig_srf_call(self, pos, seed, point_volumes, mesh_type, post_process, store)
+        name, save = self.get_store_config(store)
+        # update the model/seed in the generator if any changes were made   (srf.py:152)
+        self.generator.update(self.model, seed)
+        generator = self.generator
+        epi = None if generator.zero_var else _fused_epilogue(self, post_process)
+        if epi is None:  # seed already applied: keep it
+            return orig_srf_call(self, pos, np.nan, point_volumes, mesh_type, post_process, store)
+        iso_pos, shape = self.pre_pos(pos, mesh_type)
+        vec = type(generator) is gen.IncomprRandMeth
+        lazy = _lookup_lazy(iso_pos)
+        if lazy is not None:
+            fn = backend.summate_incompr_structured if vec else backend.summate_structured
+            field = fn(generator._cov_sample, generator._z_1, generator._z_2, lazy[0], lazy[1],
+                       epilogue=epi)
+        else:
+            fn = backend.summate_incompr if vec else backend.summate
+            field = fn(generator._cov_sample, generator._z_1, generator._z_2,
+                       np.asarray(iso_pos, dtype=np.double), epilogue=epi)
+        field = np.reshape(field, shape)
+        return self.post_field(field, name, False, save)
 
-        def sample_ln_pdf(self, ln_pdf, size=None, sample_around=1.0, nwalkers=50, burn_in=20,
-                          oversampling_factor=10):
-            model = getattr(ln_pdf, "__self__", None)
-            kind = pdf_models.get(type(model))
-            native = (getattr(config, "USE_GSTOOLS_B200", False) and kind is not None
-                      and getattr(ln_pdf, "__func__", None) is base_ln_pdf
-                      and type(model).spectral_density is getattr(cmodels, kind).spectral_density
-                      and nwalkers >= 2 and nwalkers % 2 == 0)
-            if not native:
-                return orig_sample_ln_pdf(self, ln_pdf, size, sample_around, nwalkers, burn_in, oversampling_factor)
-            # same draws from the master generator, in the same order, as rng.py:72-104
-            sample_size = burn_in if size is None else max(burn_in, (size / nwalkers) * oversampling_factor)
-            sample_size = int(sample_size)
-            init_guess = self.random.rand(nwalkers).reshape((nwalkers, 1)) * sample_around
-            burn_state = self.random.get_state()
-            main_state = self.random.get_state()
-            chain = backend.sample_radii_mcmc(kind, model.dim, model.len_rescaled, getattr(model, "nu", 0.0),
-                                              burn_state, main_state, init_guess[:, 0], burn_in, sample_size)
-            return self.random.choice(chain.reshape(-1), size)
+    return _like(srf_call, orig_srf_call)
 
-        sample_ln_pdf.__doc__ = orig_sample_ln_pdf.__doc__
-        grng.RNG.sample_ln_pdf = sample_ln_pdf
+
+# ---- Krige.__call__ with the right-hand sides generated on the device (row f1) ----------------------
+def _build_krige_call(r):
+    kbase, cmodels = r.kbase, r.cmodels
+    orig_krige_call = r.orig[(kbase.Krige, "__call__")]
+    orig_pre_pos = r.orig[(r.fbase.Field, "pre_pos")]
+    device_models = {getattr(cmodels, name): name for name in _lib.COV_TYPES if hasattr(cmodels, name)}
+
+    def _cov_spec(krige):
+        """gsb_cov_model of ``krige.model`` (exact class only: a subclass may override cor)."""
+        model = krige.model
+        kind = device_models.get(type(model))
+        if kind is None or model.latlon or getattr(model, "temporal", False) or model.dim > 4:
+            return None
+        param = float(getattr(model, "alpha", 0.0)) if kind in ("Stable", "Rational") else 0.0
+        return backend.cov_model_spec(kind, model.var, model.len_rescaled, model.sill, param, krige.exact)
+
+    def krige_call(self, pos=None, mesh_type="unstructured", ext_drift=None, chunk_size=None,
+                   only_mean=False, return_var=True, post_process=True, store=True):
+        spec = None
+        if r.on() and not only_mean and self.cond_no > 0:
+            spec = _cov_spec(self)
+        if spec is None:
+            return orig_krige_call(self, pos, mesh_type, ext_drift, chunk_size, only_mean,
+                                   return_var, post_process, store)
+        fld_cnt = 2 if return_var else 1
+        name, save = self.get_store_config(store, None, fld_cnt)       # base.py:264-267
+        # positions: keep a structured mesh as axes + isometrisation matrix (no host expansion)
+        # unless functional drift terms need the expanded positions (base.py:379-383)
+        if pos is not None:
+            self.set_pos(pos, mesh_type)
+        elif self.pos is None:
+            raise ValueError("Field: no position tuple 'pos' present")
+        lazy = self.mesh_type != "unstructured" and self.int_drift_no == 0
+        if lazy:
+            shape = self.field_shape
+            pnt_cnt = int(np.prod(shape))
+            iso_pos = None
+        else:
+            iso_pos, shape = orig_pre_pos(self, None, self.mesh_type)
+            pnt_cnt = len(iso_pos[0])
+        ext_drift = self._pre_ext_drift(pnt_cnt, ext_drift)               # base.py:279
+        tail = []
+        if self.int_drift_no > 0:
+            chunk_pos = self.model.anisometrize(iso_pos)
+            tail += [np.asarray(f(*chunk_pos), dtype=np.double).reshape(-1) for f in self.drift_functions]
+        if self.ext_drift_no > 0:
+            tail += list(np.asarray(ext_drift, dtype=np.double).reshape(self.ext_drift_no, -1))
+        tail_rows = np.ascontiguousarray(tail) if tail else None
+        kwargs = dict(unbiased=self.unbiased, tail_rows=tail_rows, return_var=return_var)
+        matrix = r.matrix_isometrize(self.model.dim, self.model.angles, self.model.anis) if lazy else None
+        # The evaluation is a pure function of these inputs.  The reference's ensemble idiom
+        # (examples/06_conditioned_fields/01_2D_condition_ensemble.py:32-35, store=[name, False, False])
+        # re-evaluates the same kriging system for every realisation; remember the last result
+        # and hand out copies (post_field below works in place).
+        cond = self._krige_cond
+        key = dict(spec=bytes(spec), flags=(lazy, bool(self.unbiased), bool(return_var)), matrix=matrix,
+                   mat=self._krige_mat, cond=cond, cpos=self._krige_pos,
+                   pos=self.pos if lazy else iso_pos, tail=tail_rows)
+        cached = getattr(self, "_b200_krige_cache", None) if r.cache_krige else None
+        if cached is not None and cached["key"]["spec"] == key["spec"] and cached["key"]["flags"] == key["flags"] \
+                and all(_same(cached["key"][k], key[k]) for k in ("mat", "cond", "cpos", "matrix", "pos", "tail")):
+            out = tuple(np.copy(o) for o in cached["out"])
+        else:
+            where = dict(axes=self.pos, matrix=matrix) if lazy else dict(pos=iso_pos)
+            out = backend.krige_evaluate(spec, self._krige_mat, cond, self._krige_pos, **where, **kwargs)
+            out = out if return_var else (out,)
+            if r.cache_krige:
+                self._b200_krige_cache = dict(key=key, out=tuple(np.copy(o) for o in out))
+        field, krige_var = out if return_var else (out[0], None)
+        field = np.reshape(field, shape)
+        field = self.post_field(field, name[0], post_process, save[0])
+        if return_var:                                                    # base.py:296-300
+            krige_var = np.reshape(np.maximum(self.model.sill - krige_var, 0), shape)
+            krige_var = self.post_field(krige_var, name[1], False, save[1])
+            return field, krige_var
+        return field
+
+    return _like(krige_call, orig_krige_call)
+
+
+# ---- Field.post_field's mean / normalizer / trend step for constant terms ---------------------------
+def _build_apply_mean_norm_trend(r):
+    """field/base.py:326-336 -> normalizer/tools.py:83-104.  With constant mean and trend and the identity
+    normalizer the reference's `denormalize` alone is five passes over the field (isnan, not, full_like,
+    two masked copies) to return the same values; here: add in place (the reference mutates its input the
+    same way), copy, add."""
+    orig = r.orig[(r.fbase, "apply_mean_norm_trend")]
+
+    def apply_mean_norm_trend(pos, field, mean=None, normalizer=None, trend=None, mesh_type="unstructured",
+                              value_type="scalar", check_shape=True, stacked=False):
+        fast = (r.on() and not check_shape and not stacked and type(normalizer) is r.Normalizer
+                and isinstance(field, np.ndarray) and field.dtype == np.double)
+        consts = []
+        if fast:
+            for value in (mean, trend):
+                value = 0 if value is None else value
+                if callable(value) or np.size(value) != 1:
+                    fast = False
+                    break
+                consts.append(np.asarray(value, dtype=np.double).item())
+        if not fast:
+            return orig(pos, field, mean, normalizer, trend, mesh_type, value_type, check_shape, stacked)
+        field += consts[0]                          # tools.py:99-100, in place like the reference
+        out = np.array(field, dtype=np.double)      # identity denormalize returns a fresh array (base.py:93-108)
+        out += consts[1]                            # tools.py:102-103
+        return out
+
+    return _like(apply_mean_norm_trend, orig)
+
+
+# ---- RNG.sample_ln_pdf through the native stream-compatible sampler (row f4) ------------------------
+def _build_sample_ln_pdf(r):
+    cmodels = r.cmodels
+    orig = r.orig[(r.grng.RNG, "sample_ln_pdf")]
+    pdf_models = {getattr(cmodels, name): name for name in _lib.PDF_KINDS if hasattr(cmodels, name)}
+    base_ln_pdf = cmodels.CovModel.ln_spectral_rad_pdf
+
+    def sample_ln_pdf(self, ln_pdf, size=None, sample_around=1.0, nwalkers=50, burn_in=20,
+                      oversampling_factor=10):
+        model = getattr(ln_pdf, "__self__", None)
+        kind = pdf_models.get(type(model))
+        native = (r.on() and kind is not None and getattr(ln_pdf, "__func__", None) is base_ln_pdf
+                  and type(model).spectral_density is getattr(cmodels, kind).spectral_density
+                  and nwalkers >= 2 and nwalkers % 2 == 0)
+        if not native:
+            return orig(self, ln_pdf, size, sample_around, nwalkers, burn_in, oversampling_factor)
+        # same draws from the master generator, in the same order, as rng.py:72-104
+        sample_size = burn_in if size is None else max(burn_in, (size / nwalkers) * oversampling_factor)
+        sample_size = int(sample_size)
+        init_guess = self.random.rand(nwalkers).reshape((nwalkers, 1)) * sample_around
+        burn_state = self.random.get_state()
+        main_state = self.random.get_state()
+        chain = backend.sample_radii_mcmc(kind, model.dim, model.len_rescaled, getattr(model, "nu", 0.0),
+                                          burn_state, main_state, init_guess[:, 0], burn_in, sample_size)
+        return self.random.choice(chain.reshape(-1), size)
+
+    return _like(sample_ln_pdf, orig)
+
+
+def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True):
+    """Route an unmodified ``gstools`` to the B200 backend (see the module docstring).
+
+    ``lazy_grid=False`` keeps the reference's host mesh expansion; ``fused=False`` rebinds only the
+    native wrappers (and the radius sampler) and leaves ``SRF.__call__`` / ``Krige.__call__`` /
+    ``post_field`` alone; ``cache_krige=False`` re-evaluates an unchanged kriging system on every call.
+    Idempotent; :func:`disable` restores everything.
+    """
+    with _LOCK:
+        r = _STATE.get("refs")
+        if r is None:
+            r = _STATE["refs"] = _Refs()
+        r.cache_krige = bool(cache_krige)
+        r.config.USE_GSTOOLS_B200 = True
+        r.config._GSTOOLS_B200_AVAIL = True
+        patches = dict(r.orig)                                    # start from the originals
+        patches.update(_build_native_wrappers(r))
+        patches[(r.grng.RNG, "sample_ln_pdf")] = _build_sample_ln_pdf(r)
+        if lazy_grid:
+            patches[(r.fbase.Field, "pre_pos")] = _build_pre_pos(r)
+        if fused:
+            patches[(r.fsrf.SRF, "__call__")] = _build_srf_call(r)
+            patches[(r.kbase.Krige, "__call__")] = _build_krige_call(r)
+            patches[(r.fbase, "apply_mean_norm_trend")] = _build_apply_mean_norm_trend(r)
+        for (owner, attr), value in patches.items():
+            setattr(owner, attr, value)
         _STATE["enabled"] = True
-    return gstools
+    return r.gstools
 
 
 def disable():
-    """Restore the reference's own wrappers and ``Field.pre_pos``."""
+    """Restore everything :func:`enable` rebound and switch the flag off."""
     with _LOCK:
         if not _STATE["enabled"]:
             return
-        gen, fbase, config = _STATE["gen"], _STATE["fbase"], _STATE["config"]
-        gen._summate = _STATE["orig_summate"]
-        gen._summate_incompr = _STATE["orig_summate_incompr"]
-        gen._summate_fourier = _STATE["orig_summate_fourier"]
-        _STATE["kbase"]._calc_field_krige = _STATE["orig_krige"]
-        _STATE["kbase"]._calc_field_krige_and_variance = _STATE["orig_krige_var"]
-        fbase.Field.pre_pos = _STATE["orig_pre_pos"]
-        _STATE["fsrf"].SRF.__call__ = _STATE["orig_srf_call"]
-        _STATE["kbase"].Krige.__call__ = _STATE["orig_krige_call"]
-        _STATE["grng"].RNG.sample_ln_pdf = _STATE["orig_sample_ln_pdf"]
-        fbase.apply_mean_norm_trend = _STATE["orig_apply_mnt"]
-        config.USE_GSTOOLS_B200 = False
+        r = _STATE["refs"]
+        for (owner, attr), value in r.orig.items():
+            setattr(owner, attr, value)
+        r.config.USE_GSTOOLS_B200 = False
         _STATE["enabled"] = False
