@@ -3,6 +3,9 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2]
 
+(`--workload c1|c3|c4|c5` run the other BASELINE configs, `--workload krige` the widened row f1: the
+kriging evaluation of config 5 in points/s, same JSON contract.)
+
 Workload (default, the config BASELINE.json's metric is quoted on): configs[1] -- SRF Exponential
 3D on a structured 512^3 mesh (134 217 728 points), mode_no = 1000; the mode set is the one the
 unmodified reference draws for seed 20170519 (tests/golden/config_modes.npz).  A "step" is one
@@ -434,15 +437,212 @@ def run_b200_arm(args, cfg):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# widened row f1: the kriging evaluation of BASELINE.json configs[4] (--workload krige)
+# ----------------------------------------------------------------------------------------------
+KRIGE_METRIC = "Krige evaluation points/s (fp64, 1000 conditioning points, field + variance)"
+
+
+def make_krige_workload(edge=128, n_cond=1000):
+    """Ordinary kriging of config 5: 1000 synthetic conditioning points, Exponential(dim=3,
+    var=1, len_scale=10), structured edge^3 mesh.  The kriging matrix is assembled and pseudo-inverted on
+    the host exactly as Krige._get_krige_mat does (src/gstools/krige/base.py:330-357)."""
+    rs = np.random.RandomState(20170519)
+    cond_pos = rs.uniform(0, edge - 1, (3, n_cond))
+    cond_val = rs.normal(size=n_cond)
+    diff = cond_pos[:, :, None] - cond_pos[:, None, :]
+    size = n_cond + 1
+    mat = np.ones((size, size))
+    mat[:n_cond, :n_cond] = np.exp(-np.sqrt((diff * diff).sum(axis=0)) / 10.0)
+    mat[n_cond, n_cond] = 0.0
+    return dict(spec=dict(kind="Exponential", var=1.0, len_rescaled=10.0), mat=np.linalg.pinv(mat),
+                cond=np.concatenate([cond_val, [0.0]]), cond_pos=cond_pos, axes=[np.arange(float(edge))] * 3,
+                size=size, n=edge ** 3, name=f"C5 kriging step: Ordinary kriging, {n_cond} points, "
+                                              f"Exponential 3D, {edge}^3 structured mesh")
+
+
+def krige_cpu(w, n_pts, offset=0):
+    """The reference's chunk step on the host: right-hand sides (numpy) + native loop nest (oracle port)."""
+    import oracle
+
+    idx = (np.arange(n_pts) + offset) % w["n"]
+    pos = bc.grid_points(w["axes"], None, idx)
+    t0 = time.perf_counter()
+    oracle.krige_evaluate(w["spec"], w["mat"], w["cond"], w["cond_pos"], pos)
+    return time.perf_counter() - t0
+
+
+def krige_config(w, world):
+    return {"workload": w["name"], "baseline_config": "C5 (kriging step, SURVEY.md 8f row f1)",
+            "path": "krige_evaluate (device-generated right-hand sides, triangular DMMA contraction)",
+            "krige_size": int(w["size"]), "dim": 3, "sharding": f"axis-0 slabs over {world} GPU(s), no collective",
+            "l2": "256 MiB flush buffer written between timed steps, outside the event brackets"}
+
+
+def run_krige_reference_arm(args, w):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle
+
+    oracle.build()
+    t = krige_cpu(w, 512)
+    budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
+    m = int(max(512, min(65536, 512 * budget / max(t, 1e-9))))
+    for k in range(args.warmup):
+        krige_cpu(w, m, offset=k * m)
+    total = sum(krige_cpu(w, m, offset=(args.warmup + k) * m) for k in range(args.steps))
+    value = args.steps * m / total
+    sample = (f"each step = {m} contiguous mesh nodes on the host CPU: numpy right-hand sides "
+              f"(Krige._get_krige_vecs) + C/OpenMP port of the native loop nest; linear in the number of points")
+    print(json.dumps({
+        "impl": "reference", "metric": KRIGE_METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": krige_config(w, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": oracle.max_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def run_krige_arm(args, w):
+    import torch
+    import torch.distributed as dist
+
+    import gstools_b200 as gsb
+    from gstools_b200.dist import shard_range
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 backend has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    gsb.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lo, hi = shard_range(len(w["axes"][0]), rank, world)
+    h_axes = [np.ascontiguousarray(w["axes"][0][lo:hi])] + [np.ascontiguousarray(a) for a in w["axes"][1:]]
+    n_local = int(np.prod([len(a) for a in h_axes]))
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), device=dev)
+    d_mat, d_cond, d_cpos, d_axes = t(w["mat"]), t(w["cond"]), t(w["cond_pos"]), [t(a) for a in h_axes]
+
+    def step_device():
+        return gsb.krige_evaluate(w["spec"], d_mat, d_cond, d_cpos, axes=d_axes)
+
+    def step_host():
+        return gsb.krige_evaluate(w["spec"], w["mat"], w["cond"], w["cond_pos"], axes=h_axes)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    peak_dfma = gsb.measure_fp64_peak(local, 0, 0.4)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    gsb.set_option("time_kernels", 1)
+    gsb.kernel_times()
+    launches0 = gsb.get_counter("launches")
+    events = []
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = step_device()
+            e1.record()
+            events.append((e0, e1))
+            del out
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = gsb.get_counter("launches") - launches0
+    kern_ms, kern_n = gsb.kernel_times()
+    gsb.set_option("time_kernels", 0)
+    dev_s = sum(a.elapsed_time(b) for a, b in events) * 1e-3
+    red = torch.tensor([dev_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    dev_s = float(red.item())
+    value = args.steps * w["n"] / dev_s
+    for _ in range(3):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    red = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    e2e_s = float(red.item())
+    if rank == 0:
+        K = w["size"]
+        fma_per_point = 0.5 * K * (K + 1) + K              # triangular quadratic form + the field row
+        kern_s = kern_ms * 1e-3 / max(kern_n, 1)
+        pts_per_launch = n_local * args.steps / max(kern_n, 1)
+        achieved = pts_per_launch * 2.0 * fma_per_point / kern_s / 1e12 if kern_n else None
+        peak_tflops = 2.0 * peak_dfma / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(REPO, "profiles", "dominant_kernel_traffic.json"))).get("krige")
+        except Exception:
+            pass
+        roofline = {
+            "bound": "tensor", "bound_detail": "fp64 tensor path (DMMA.8x8x4), FP64-pipe roofline",
+            "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": (achieved / peak_tflops) if achieved else None, "traffic": traffic,
+            "kernel": "krige_kernel<TILED> (DMMA.8x8x4)", "kernel_ms_per_launch": 1e3 * kern_s,
+            "launches_timed": kern_n, "kernel_share_of_step": (kern_ms * 1e-3) / dev_s * (1 if world == 1 else 1),
+            "algorithmic_flop_per_point": 2.0 * fma_per_point,
+            "reference_loop_flop_per_point": 2.0 * K * K,
+            "peak_source": "DFMA microbenchmark run in this process (gsb_measure_fp64_peak); "
+                           "MEASURED_PEAKS.json has no fp64 entry"}
+        line = {
+            "metric": KRIGE_METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": krige_config(w, world),
+            "e2e": {"value": args.steps * w["n"] / e2e_s, "unit": "points/s",
+                    "h2d_bytes_per_step": int(w["mat"].nbytes + w["cond"].nbytes + w["cond_pos"].nbytes
+                                              + sum(a.nbytes for a in h_axes)),
+                    "d2h_bytes_per_step": int(2 * out[0].nbytes), "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "api": "gstools_b200.krige_evaluate(numpy...) -> (field, error) numpy"},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks.summary(),
+            "wall_s_timed_region": t_wall}
+        if world == 1:
+            import oracle
+
+            oracle.build()
+            tp = krige_cpu(w, 256)
+            m = int(max(256, min(16384, 256 * 10.0 / max(tp, 1e-9))))
+            tc = krige_cpu(w, m, offset=m)
+            line["cpu_baseline"] = {"value": m / tc, "unit": "points/s", "cores": oracle.max_threads(), "kind": "port",
+                                    "sample": f"{m} contiguous mesh nodes ({tc:.1f} s): numpy right-hand sides + "
+                                              f"C/OpenMP port of the native loop nest"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "krige"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload == "krige":
+        w = make_krige_workload()
+        return run_krige_reference_arm(args, w) if args.impl == "reference" else run_krige_arm(args, w)
     cfg = make_workload(args.workload)
     if args.impl == "reference":
         run_reference_arm(args, cfg)
