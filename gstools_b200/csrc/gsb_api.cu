@@ -558,7 +558,11 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     {
         const int64_t min_chunks = std::max<int64_t>(1, g_opt_min_chunks.load());
         int64_t n = std::max<int64_t>(q, total_units / (4 * min_chunks) / q * q);
-        const double growth = (double)g_opt_chunk_growth_pct.load() / 100.0;
+        // Host route: the D2H copy of a chunk (PCIe: ~1.26x its contraction time for C2) runs while the
+        // next chunk is contracted.  Growing chunks would make that next contraction longer than the
+        // copy and leave the copy engine -- the bottleneck of the whole call -- idle in between, so
+        // chunks stay equal there.
+        const double growth = h_out ? 1.0 : (double)g_opt_chunk_growth_pct.load() / 100.0;
         int64_t f = 0, r = 0;
         while (f < n_batch) {
             Chunk ch;
