@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 
 import numpy as np
 
@@ -77,14 +78,42 @@ def _torch():
     return torch
 
 
+_PINNED = {"bytes": 0, "limit": None}
+
+
+def _pinned_limit():
+    """Cap on the pinned host memory held by arrays this module handed out (they stay pinned for as long
+    as the caller keeps them): ``GSB200_PINNED_LIMIT_MB``, default a quarter of the physical memory."""
+    if _PINNED["limit"] is None:
+        env = os.environ.get("GSB200_PINNED_LIMIT_MB")
+        if env is not None:
+            _PINNED["limit"] = int(float(env) * (1 << 20))
+        else:
+            try:
+                total = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
+            except (ValueError, OSError):
+                total = 64 << 30
+            _PINNED["limit"] = total // 4
+    return _PINNED["limit"]
+
+
+def _release_pinned(nbytes):
+    _PINNED["bytes"] -= nbytes
+
+
 def _empty_host(shape):
     """Uninitialised float64 host array; pinned when large so D2H runs at full PCIe speed."""
     n = int(np.prod(shape)) if len(shape) else 1
-    if n >= _PIN_THRESHOLD:
+    nbytes = 8 * n
+    if n >= _PIN_THRESHOLD and _PINNED["bytes"] + nbytes <= _pinned_limit():
         try:
             torch = _torch()
             if torch.cuda.is_available():
-                return torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True).numpy()
+                tensor = torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True)
+                arr = tensor.numpy()
+                _PINNED["bytes"] += nbytes
+                weakref.finalize(tensor, _release_pinned, nbytes)   # the array keeps the tensor alive
+                return arr
         except Exception:  # pinned allocation is an optimisation only
             pass
     return np.empty(shape, dtype=np.float64)

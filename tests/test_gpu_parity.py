@@ -439,3 +439,10 @@ def test_c_program_calls_the_library_on_the_gpu(gsb, tmp_path):
     exe = _build_c_consumer(tmp_path, gsb)
     out = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "gpu ok" in out.stdout, out.stderr + out.stdout
+
+
+def test_pinned_output_budget_on_the_gpu(gsb, monkeypatch):
+    """Same accounting test as on CPU, here with real pinned allocations."""
+    from test_host_logic import test_pinned_output_budget
+
+    test_pinned_output_budget(gsb, monkeypatch)

@@ -606,3 +606,30 @@ def test_fast_post_field_epilogue_matches_reference_bits(gsb, oracle_mod, monkey
     finally:
         gsb.disable()
     assert fbase.apply_mean_norm_trend is orig
+
+
+def test_pinned_output_budget(gsb, monkeypatch):
+    """Outputs are pinned only while the outstanding pinned bytes stay under the cap; the accounting
+    follows the lifetime of the arrays handed out."""
+    import gc
+
+    from gstools_b200 import backend
+
+    monkeypatch.setattr(backend, "_PINNED", {"bytes": 0, "limit": None})
+    monkeypatch.setenv("GSB200_PINNED_LIMIT_MB", "3")
+    assert backend._pinned_limit() == 3 << 20
+    # without a CUDA device the arrays are pageable and nothing is accounted
+    a = backend._empty_host((1 << 17,))
+    import torch
+
+    if not torch.cuda.is_available():
+        assert backend._PINNED["bytes"] == 0 and a.shape == (1 << 17,)
+        return
+    assert backend._PINNED["bytes"] == 1 << 20
+    b = backend._empty_host((1 << 18,))                # 2 MiB more: exactly at the cap
+    assert backend._PINNED["bytes"] == 3 << 20
+    c = backend._empty_host((1 << 17,))                # over the cap: pageable, not accounted
+    assert backend._PINNED["bytes"] == 3 << 20 and c.shape == (1 << 17,)
+    del a, b
+    gc.collect()
+    assert backend._PINNED["bytes"] == 0
