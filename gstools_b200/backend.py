@@ -112,7 +112,7 @@ def _empty_host(shape):
                 tensor = torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True)
                 arr = tensor.numpy()
                 _PINNED["bytes"] += nbytes
-                weakref.finalize(tensor, _release_pinned, nbytes)   # the array keeps the tensor alive
+                weakref.finalize(arr, _release_pinned, nbytes)   # views keep `arr` alive through .base
                 return arr
         except Exception:  # pinned allocation is an optimisation only
             pass
