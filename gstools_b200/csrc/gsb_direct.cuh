@@ -256,7 +256,12 @@ inline void launch_direct_dim(const DirectParams &prm, int cfg, cudaStream_t st)
 #ifndef GSB_DIRECT_MINB
 #define GSB_DIRECT_MINB 2
 #endif
-        if (cfg == 2) return launch_direct_cfg<D, 4, VEC, 256, GSB_DIRECT_MINB>(prm, st);
+        // 8 points per thread, 8 warps per SM: fewer warps with more independent chains keep the FP64
+        // pipe fuller than 4 points x 16 warps (+3 % 2-D, +4 % 3-D, +8 % incompressible; tools/direct_cfg_sweep.py)
+        if constexpr (D <= 3) {
+            if (cfg >= 2) return launch_direct_cfg<D, 8, VEC, 128, 2>(prm, st);
+        }
+        if (cfg >= 2) return launch_direct_cfg<D, 4, VEC, 256, GSB_DIRECT_MINB>(prm, st);
     }
     if (cfg >= 1) launch_direct_cfg<D, 2, VEC, 128, 4>(prm, st);
     else launch_direct_cfg<D, 1, VEC, 64, 8>(prm, st);
@@ -265,8 +270,8 @@ inline void launch_direct_dim(const DirectParams &prm, int cfg, cudaStream_t st)
 // points per CTA of configuration cfg
 inline int64_t direct_cfg_points(int cfg, int dim)
 {
-    if (cfg == 2 && dim > 4) cfg = 1;
-    return cfg == 2 ? 1024 : (cfg == 1 ? 256 : 64);
+    if (cfg >= 2 && dim > 4) cfg = 1;
+    return cfg >= 2 ? 1024 : (cfg == 1 ? 256 : 64);
 }
 
 inline int launch_direct(int dim, bool vec, const DirectParams &prm, int cfg, cudaStream_t st)
