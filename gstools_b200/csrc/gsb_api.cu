@@ -199,7 +199,7 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
                             cudaStream_t st)
 {
     if (n_pts == 0) return GSB_OK;
-    // Launch configuration by a small cost model: time ~ waves x points per CTA / relative speed.  The
+    // Launch configuration by a small cost model: time ~ waves x points per SM and wave / relative speed.  The
     // big-CTA configuration is the fastest per point (measured 1.05 vs 0.84 vs 0.74 Tpair/s, 2-D) but
     // quantises into waves of 2 x 1024 points per SM; mid-sized point sets are better off with smaller CTAs.
     // (A point's bits do not depend on the configuration: the per-point instruction sequence is the same.)
@@ -213,7 +213,7 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
             const int64_t ppc = direct_cfg_points(c, dim);
             const int64_t nc = (n_pts + ppc - 1) / ppc;
             const int64_t slots = (int64_t)resident[c] * dev.sm_count;
-            const double t = (double)((nc + slots - 1) / slots) * (double)ppc / speed[c];
+            const double t = (double)((nc + slots - 1) / slots) * (double)(resident[c] * ppc) / speed[c];
             if (t < best * 0.999) {
                 best = t;
                 cfg = c;
