@@ -200,13 +200,13 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
 {
     if (n_pts == 0) return GSB_OK;
     // Launch configuration by a small cost model: time ~ waves x points per SM and wave / relative speed.  The
-    // big-CTA configuration is the fastest per point (measured 1.05 vs 0.84 vs 0.74 Tpair/s, 2-D) but
+    // big-CTA configuration is the fastest per point (measured 1.02 vs 0.93 vs 0.77 Tpair/s, 2-D) but
     // quantises into waves of 2 x 1024 points per SM; mid-sized point sets are better off with smaller CTAs.
     // (A point's bits do not depend on the configuration: the per-point instruction sequence is the same.)
     const int64_t want = 2LL * dev.sm_count;
     int cfg = 0;
     {
-        static const double speed[3] = {0.70, 0.80, 1.00};
+        static const double speed[3] = {0.756, 0.906, 1.00};   // tools/direct_size_sweep.py
         static const int resident[3] = {8, 4, 2};
         double best = 1e300;
         for (int c = 0; c < 3; ++c) {
