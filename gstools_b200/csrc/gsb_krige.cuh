@@ -23,9 +23,10 @@
 //                        copy of the 20 KB operand tile plus 16 bulk copies of 1 KB -- the rows of kv
 //                        straight from the caller's row-major array into the padded B layout -- land in a
 //                        4-slot mbarrier ring.  Consumers: the DMMA.8x8x4 loop of the separable
-//                        contraction (gsb_separable.cuh).  Epilogue: multiply the accumulators with the
-//                        matching kv entries (L2 hits), reduce over rows in a fixed order (registers ->
-//                        shuffles -> shared memory), one partial per (pair, point); row K is the field.
+//                        contraction (gsb_separable.cuh).  Epilogue: the accumulators times the matching kv
+//                        entries -- read from the stage buffers of the diagonal stages, where they pass through
+//                        shared memory anyway -- reduced over rows in a fixed order (registers -> shuffles ->
+//                        shared memory), one partial per (pair, point); row K is the field.
 //   krige_finish_kernel  error[k] = sum_p partial[p][k] in ascending p (deterministic, no atomics).
 //   krige_field_kernel   `calc_field_krige` (no variance): field = w . kv, one pass over kv (HBM bound).
 #pragma once
@@ -244,7 +245,6 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) krige_kernel(const KrigeParams
     const int t = lane & 3;
     const int a_off = (wr * 32 + g) * SEP_AST + t;
     const int b_off = SEP_A_TILE + t * SEP_BST + wc * 64 + g;
-    const bool vec2 = (prm.ld & 1) == 0 && ((reinterpret_cast<uintptr_t>(prm.kv) & 15) == 0);
 
     int slot = 0;
     uint32_t round = 0;
@@ -289,40 +289,45 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) krige_kernel(const KrigeParams
 #pragma unroll
                         for (int i = 0; i < 4; ++i) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
                 }
+                // Epilogue folded into the diagonal stages.  acc[i][j][e] = Y[row, col] with row = 128r + 32wr +
+                // 8i + g, col = col0 + 64wc + 8j + 2t + e.  Diagonal stage sd = s - 8r holds the depth rows
+                // 128r + 16sd .. +15 in shared memory: for band wr = sd / 2 these are exactly the kv rows of its
+                // accumulator rows i = 2(sd & 1), 2(sd & 1) + 1, which are final after this stage's DMMAs
+                // (the operand is zero beyond the diagonal).  error += kv[row, col] * Y[row, col] straight from
+                // the stage buffer: no global loads, and the other bands keep the DMMA pipe busy meanwhile.
+                if (s >= KRG_SPT * r && ((s - KRG_SPT * r) >> 1) == wr) {
+                    const double *Bt = Sm + SEP_A_TILE + g * SEP_BST + wc * 64 + 2 * t;
+                    if (((s - KRG_SPT * r) & 1) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const double2 v0 = *reinterpret_cast<const double2 *>(Bt + j * 8);
+                            const double2 v1 = *reinterpret_cast<const double2 *>(Bt + 8 * SEP_BST + j * 8);
+                            esum[j][0] = fma(v0.x, acc[0][j][0], esum[j][0]);
+                            esum[j][1] = fma(v0.y, acc[0][j][1], esum[j][1]);
+                            esum[j][0] = fma(v1.x, acc[1][j][0], esum[j][0]);
+                            esum[j][1] = fma(v1.y, acc[1][j][1], esum[j][1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const double2 v0 = *reinterpret_cast<const double2 *>(Bt + j * 8);
+                            const double2 v1 = *reinterpret_cast<const double2 *>(Bt + 8 * SEP_BST + j * 8);
+                            esum[j][0] = fma(v0.x, acc[2][j][0], esum[j][0]);
+                            esum[j][1] = fma(v0.y, acc[2][j][1], esum[j][1]);
+                            esum[j][0] = fma(v1.x, acc[3][j][0], esum[j][0]);
+                            esum[j][1] = fma(v1.y, acc[3][j][1], esum[j][1]);
+                        }
+                    }
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[slot]);
                 if (++slot == KRG_STAGES) { slot = 0; ++round; }
             }
 
-            // sub-tile epilogue: acc[i][j][e] = Y[row, col] with row = 128r + 32wr + 8i + g,
-            // col = col0 + 64wc + 8j + 2t + e.  error += kv[row, col] * Y (rows < K); row K is the field.
+            // what is left for the end of the sub-tile: row K of the operand is w = M^T cond, i.e. the field
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int row = r * SEP_TM + wr * 32 + i * 8 + g;
-                if (row < prm.K) {
-                    const double *kr = TILED
-                        ? prm.btile + ((c * prm.n_dstages + row / KRG_KD) * KRG_KD + row % KRG_KD) * SEP_BST - col0
-                        : prm.kv + (int64_t)row * prm.ld;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
-                        double k0 = 0.0, k1 = 0.0;
-                        if (TILED) {   // padded tile rows: always readable, 16-byte aligned
-                            const double2 v = *reinterpret_cast<const double2 *>(kr + col);
-                            k0 = v.x;
-                            k1 = v.y;
-                        } else if (vec2 && col + 1 < prm.n) {
-                            const double2 v = *reinterpret_cast<const double2 *>(kr + col);
-                            k0 = v.x;
-                            k1 = v.y;
-                        } else {
-                            if (col < prm.n) k0 = kr[col];
-                            if (col + 1 < prm.n) k1 = kr[col + 1];
-                        }
-                        esum[j][0] = fma(k0, acc[i][j][0], esum[j][0]);
-                        esum[j][1] = fma(k1, acc[i][j][1], esum[j][1]);
-                    }
-                } else if (row == prm.K) {
+                if (r * SEP_TM + wr * 32 + i * 8 + g == prm.K) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
