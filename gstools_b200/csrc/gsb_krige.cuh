@@ -295,7 +295,9 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) krige_kernel(const KrigeParams
                 // accumulator rows i = 2(sd & 1), 2(sd & 1) + 1, which are final after this stage's DMMAs
                 // (the operand is zero beyond the diagonal).  error += kv[row, col] * Y[row, col] straight from
                 // the stage buffer: no global loads, and the other bands keep the DMMA pipe busy meanwhile.
-                if (s >= KRG_SPT * r && ((s - KRG_SPT * r) >> 1) == wr) {
+                // (Row-major variant only: 72.4 -> 68.1 ms for K = 1001, n = 128^3.  With pre-tiled right-hand
+                // sides the end-of-sub-tile loads below hit L2 in one burst and measured 1.5 % faster.)
+                if (!TILED && s >= KRG_SPT * r && ((s - KRG_SPT * r) >> 1) == wr) {
                     const double *Bt = Sm + SEP_A_TILE + g * SEP_BST + wc * 64 + 2 * t;
                     if (((s - KRG_SPT * r) & 1) == 0) {
 #pragma unroll
@@ -324,10 +326,22 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) krige_kernel(const KrigeParams
                 if (++slot == KRG_STAGES) { slot = 0; ++round; }
             }
 
-            // what is left for the end of the sub-tile: row K of the operand is w = M^T cond, i.e. the field
+            // end of the sub-tile.  TILED: error += kv[row, col] * Y[row, col] with kv from the pre-tiled chunk
+            // (L2 hits).  Both: row K of the operand is w = M^T cond, i.e. the field.
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (r * SEP_TM + wr * 32 + i * 8 + g == prm.K) {
+                const int row = r * SEP_TM + wr * 32 + i * 8 + g;
+                if (TILED && row < prm.K) {
+                    const double *kr = prm.btile + ((c * prm.n_dstages + row / KRG_KD) * KRG_KD + row % KRG_KD) * SEP_BST +
+                                       wc * 64 + 2 * t;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double2 v = *reinterpret_cast<const double2 *>(kr + j * 8);
+                        esum[j][0] = fma(v.x, acc[i][j][0], esum[j][0]);
+                        esum[j][1] = fma(v.y, acc[i][j][1], esum[j][1]);
+                    }
+                }
+                if (row == prm.K) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
