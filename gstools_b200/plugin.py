@@ -140,7 +140,8 @@ class _Refs:
             (gen, "_summate"), (gen, "_summate_incompr"), (gen, "_summate_fourier"),
             (kbase, "_calc_field_krige"), (kbase, "_calc_field_krige_and_variance"),
             (fbase.Field, "pre_pos"), (fsrf.SRF, "__call__"), (kbase.Krige, "__call__"),
-            (fbase, "apply_mean_norm_trend"), (grng.RNG, "sample_ln_pdf"))}
+            (fbase, "apply_mean_norm_trend"), (grng.RNG, "sample_ln_pdf"),
+            (gen.RandMeth, "__call__"), (gen.IncomprRandMeth, "__call__"))}
         self.cache_krige = True
 
     def on(self):
@@ -299,6 +300,48 @@ def _build_srf_call(r):
         return self.post_field(field, name, False, save)
 
     return _like(srf_call, orig_srf_call)
+
+
+# ---- RandMeth.__call__ / IncomprRandMeth.__call__ with the scale fused (CondSRF and direct users) ---
+def _build_generator_calls(r):
+    """generator.py:243-270 and 529-567 for the case without a nugget draw: the `sqrt(var/N) * summed + 0.0`
+    passes become the kernels' epilogue.  CondSRF calls the generator with add_nugget=False
+    (cond_srf.py:122), so every conditioned realisation takes this path."""
+    gen = r.gen
+    orig_rm = r.orig[(gen.RandMeth, "__call__")]
+    orig_irm = r.orig[(gen.IncomprRandMeth, "__call__")]
+
+    def _eligible(self, cls, add_nugget):
+        return (r.on() and type(self) is cls and not self.zero_var
+                and not (add_nugget and self.model.nugget > 0))
+
+    def _sum(self, pos, vec, epi):
+        lazy = _lookup_lazy(pos)
+        if lazy is not None:
+            fn = backend.summate_incompr_structured if vec else backend.summate_structured
+            out = fn(self._cov_sample, self._z_1, self._z_2, lazy[0], lazy[1], epilogue=epi)
+            return out.reshape(out.shape[0], -1) if vec else out.reshape(-1)
+        fn = backend.summate_incompr if vec else backend.summate
+        return fn(self._cov_sample, self._z_1, self._z_2, pos, epilogue=epi)
+
+    def randmeth_call(self, pos, add_nugget=True):
+        pos = np.asarray(pos, dtype=np.double)
+        if not _eligible(self, gen.RandMeth, add_nugget) or pos.ndim != 2:
+            return orig_rm(self, pos, add_nugget)
+        # np.sqrt(var / N) * summed_modes + nugget, nugget == 0.0          (generator.py:269-270)
+        return _sum(self, pos, False, backend.make_epilogue(np.sqrt(self.model.var / self._mode_no), [0.0]))
+
+    def incompr_call(self, pos, add_nugget=True):
+        pos = np.asarray(pos, dtype=np.double)
+        if not _eligible(self, gen.IncomprRandMeth, add_nugget) or pos.ndim != 2 or self.model.dim not in (2, 3):
+            return orig_irm(self, pos, add_nugget)
+        # mean_u * e1 + mean_u * sqrt(var / N) * summed_modes + nugget      (generator.py:561-567)
+        e1 = tuple([self.mean_u * 1.0] + [self.mean_u * 0.0] * (self.model.dim - 1))
+        scale = self.mean_u * np.sqrt(self.model.var / self._mode_no)
+        return _sum(self, pos, True, backend.make_epilogue(scale, [e1, 0.0]))
+
+    return {(gen.RandMeth, "__call__"): _like(randmeth_call, orig_rm),
+            (gen.IncomprRandMeth, "__call__"): _like(incompr_call, orig_irm)}
 
 
 # ---- Krige.__call__ with the right-hand sides generated on the device (row f1) ----------------------
@@ -464,6 +507,7 @@ def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True)
             patches[(r.fsrf.SRF, "__call__")] = _build_srf_call(r)
             patches[(r.kbase.Krige, "__call__")] = _build_krige_call(r)
             patches[(r.fbase, "apply_mean_norm_trend")] = _build_apply_mean_norm_trend(r)
+            patches.update(_build_generator_calls(r))
         for (owner, attr), value in patches.items():
             setattr(owner, attr, value)
         _STATE["enabled"] = True

@@ -273,15 +273,16 @@ def test_fused_srf_call_falls_through_when_not_affine(gsb, oracle_mod, monkeypat
     gs = refharness.import_gstools()
     pos = [np.linspace(0, 10, 7), np.linspace(-5, 5, 6)]
     m = gs.Gaussian(dim=2, var=1.7, len_scale=3.0)
+    # last column: may the generator's own sqrt(var/N) scale still be fused (generator.py:269-270)?
     variants = [
-        (m, dict(mean=lambda x, y: x + y), dict()),
-        (m, dict(trend=lambda x, y: x * y), dict()),
-        (m, dict(normalizer=gs.normalizer.LogNormal()), dict()),
-        (gs.Gaussian(dim=2, var=1.7, len_scale=3.0, nugget=0.4), dict(), dict()),
-        (m, dict(upscaling="coarse_graining"), dict(point_volumes=2.0)),
-        (gs.Gaussian(dim=2, var=0.0, len_scale=3.0, nugget=0.1), dict(), dict()),
+        (m, dict(mean=lambda x, y: x + y), dict(), True),
+        (m, dict(trend=lambda x, y: x * y), dict(), True),
+        (m, dict(normalizer=gs.normalizer.LogNormal()), dict(), True),
+        (gs.Gaussian(dim=2, var=1.7, len_scale=3.0, nugget=0.4), dict(), dict(), False),      # nugget draw
+        (m, dict(upscaling="coarse_graining"), dict(point_volumes=2.0), True),
+        (gs.Gaussian(dim=2, var=0.0, len_scale=3.0, nugget=0.1), dict(), dict(), False),      # no summation at all
     ]
-    for model, skw, ckw in variants:
+    for model, skw, ckw, scale_fused in variants:
         want = gs.SRF(model, seed=5, mode_no=32, **skw)(pos, mesh_type="structured", **ckw)
         calls = []
         with monkeypatch.context() as mp:
@@ -291,7 +292,9 @@ def test_fused_srf_call_falls_through_when_not_affine(gsb, oracle_mod, monkeypat
                 got = gs.SRF(model, seed=5, mode_no=32, **skw)(pos, mesh_type="structured", **ckw)
             finally:
                 gsb.disable()
-        assert not any(fused for _, fused in calls), (skw, calls)
+        # never the SRF-level terms (mean, trend, normalizer, upscaling stay on the host) ...
+        assert all(fused == scale_fused for _, fused in calls), (skw, calls)
+        # ... and the reference's bits either way
         assert np.array_equal(got, want), skw
     # fused=False leaves SRF.__call__ alone
     from gstools.field import srf as fsrf
@@ -633,3 +636,42 @@ def test_pinned_output_budget(gsb, monkeypatch):
     del a, b
     gc.collect()
     assert backend._PINNED["bytes"] == 0
+
+
+@needs_ref
+def test_fused_generator_calls_match_reference_bits(gsb, oracle_mod, monkeypatch):
+    """RandMeth / IncomprRandMeth called directly (as CondSRF and the reference's own tests do): with
+    the scale in the kernels' epilogue the result has the reference's bits; a nugget draw keeps the
+    reference's own code."""
+    gs = refharness.import_gstools()
+    from gstools.field.generator import IncomprRandMeth, RandMeth
+
+    x, y = np.linspace(0.0, 10.0, 10), np.linspace(-5.0, 5.0, 10)
+    m2 = gs.Gaussian(dim=2, var=1.5, len_scale=3.5)
+    mn = gs.Gaussian(dim=2, var=1.5, len_scale=3.5, nugget=0.3)
+    want = {
+        "rm": RandMeth(m2, mode_no=100, seed=19031977)((x, y)),
+        "rm_nonug": RandMeth(mn, mode_no=100, seed=19031977)((x, y), add_nugget=False),
+        "rm_nug": RandMeth(mn, mode_no=100, seed=19031977)((x, y)),
+        "irm": IncomprRandMeth(gs.Gaussian(dim=2, var=1.5, len_scale=2.5), mode_no=100, seed=19031977,
+                               mean_velocity=-0.7)((x, y)),
+    }
+    calls = []
+    _fake_backend(monkeypatch, oracle_mod, calls)
+    gsb.enable()
+    try:
+        got = {"rm": RandMeth(m2, mode_no=100, seed=19031977)((x, y))}
+        assert calls[-1] == ("flat", True)
+        got["rm_nonug"] = RandMeth(mn, mode_no=100, seed=19031977)((x, y), add_nugget=False)
+        assert calls[-1] == ("flat", True)
+        got["rm_nug"] = RandMeth(mn, mode_no=100, seed=19031977)((x, y))
+        assert calls[-1] == ("flat", False)                        # nugget draw: unfused
+        got["irm"] = IncomprRandMeth(gs.Gaussian(dim=2, var=1.5, len_scale=2.5), mode_no=100, seed=19031977,
+                                     mean_velocity=-0.7)((x, y))
+        assert calls[-1] == ("flat_vec", True)
+    finally:
+        gsb.disable()
+    for k in want:
+        assert got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k
+    # the literals of tests/test_randmeth.py:38-41
+    assert round(got["rm"][0] - 1.67318010, 7) == 0 and round(got["rm"][1] - 2.12310269, 7) == 0
