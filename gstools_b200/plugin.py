@@ -405,18 +405,24 @@ def _build_krige_call(r):
         cached = getattr(self, "_b200_krige_cache", None) if r.cache_krige else None
         if cached is not None and cached["key"]["spec"] == key["spec"] and cached["key"]["flags"] == key["flags"] \
                 and all(_same(cached["key"][k], key[k]) for k in ("mat", "cond", "cpos", "matrix", "pos", "tail")):
-            out = tuple(np.copy(o) for o in cached["out"])
+            out = (np.copy(cached["out"][0]),) + tuple(cached["out"][1:])   # the field is post-processed in place
         else:
             where = dict(axes=self.pos, matrix=matrix) if lazy else dict(pos=iso_pos)
             out = backend.krige_evaluate(spec, self._krige_mat, cond, self._krige_pos, **where, **kwargs)
             out = out if return_var else (out,)
+            cached = None
             if r.cache_krige:
-                self._b200_krige_cache = dict(key=key, out=tuple(np.copy(o) for o in out))
-        field, krige_var = out if return_var else (out[0], None)
+                cached = self._b200_krige_cache = dict(key=key, out=tuple(np.copy(o) for o in out))
+        field, error = out if return_var else (out[0], None)
         field = np.reshape(field, shape)
         field = self.post_field(field, name[0], post_process, save[0])
         if return_var:                                                    # base.py:296-300
-            krige_var = np.reshape(np.maximum(self.model.sill - krige_var, 0), shape)
+            if cached is not None:      # sill is part of the key: the variance is a pure function of it too
+                if "krige_var" not in cached:
+                    cached["krige_var"] = np.maximum(self.model.sill - cached["out"][1], 0)
+                krige_var = np.reshape(np.copy(cached["krige_var"]), shape)
+            else:
+                krige_var = np.reshape(np.maximum(self.model.sill - error, 0), shape)
             krige_var = self.post_field(krige_var, name[1], False, save[1])
             return field, krige_var
         return field
