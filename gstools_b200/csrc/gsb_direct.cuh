@@ -28,7 +28,14 @@
 
 namespace gsb {
 
-constexpr int DIRECT_TM = 64;   // modes per shared-memory tile (2 buffers x 64 x 40 doubles <= 48 KB static)
+#ifndef GSB_DIRECT_TM
+#define GSB_DIRECT_TM 64
+#endif
+constexpr int DIRECT_TM = GSB_DIRECT_TM;
+#ifndef GSB_DIRECT_UNROLL
+#define GSB_DIRECT_UNROLL 2
+#endif
+constexpr int DIRECT_UNROLL = GSB_DIRECT_UNROLL;   // modes per unrolled iteration of the inner loop   // modes per shared-memory tile (2 buffers x 64 x 40 doubles <= 48 KB static)
 constexpr double RINT_MAGIC = 6755399441055744.0;  // 1.5 * 2^52
 constexpr double EIGHT_OVER_PI = 2.54647908947032537230;
 constexpr int DIRECT_NROT = 16;              // rotations per record (sixteenth turns)
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
 
         const int cnt = (int)min((int64_t)TM, prm.n_modes_pad - (int64_t)t * TM);
         const char *T = reinterpret_cast<const char *>(&tile[b][0]);
-#pragma unroll 2
+#pragma unroll DIRECT_UNROLL
         for (int j = 0; j < cnt; ++j) {
             const double *R = reinterpret_cast<const double *>(T + j * (REC * 8));
             double k[D];
