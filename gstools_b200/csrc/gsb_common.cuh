@@ -47,6 +47,16 @@ inline int fail(int code, const std::string &msg)
 
 extern std::atomic<int64_t> g_launches;  // kernels launched by this library (gsb_get_counter)
 
+// Function attributes (dynamic shared-memory size, carve-out) are per device: set them the first time a
+// kernel family is launched on each device of the process, not once per process.
+inline bool first_launch_on_device(std::atomic<uint64_t> &seen)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const uint64_t bit = 1ull << (dev & 63);
+    return (seen.fetch_or(bit) & bit) == 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + bulk async copy (TMA unit, SASS UBLKCP) on sm_100a
 // ---------------------------------------------------------------------------------------------

@@ -427,11 +427,10 @@ __global__ void krige_repack_kernel(const double *__restrict__ src, int64_t src_
 
 inline int launch_krige(const KrigeParams &kp, bool tiled, int sm_count, cudaStream_t st)
 {
-    static std::atomic<bool> attr_set{false};
-    if (!attr_set.load()) {
+    static std::atomic<uint64_t> attr_set{0};
+    if (first_launch_on_device(attr_set)) {
         GSB_CUDA(cudaFuncSetAttribute(krige_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KRG_SMEM_BYTES));
         GSB_CUDA(cudaFuncSetAttribute(krige_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KRG_SMEM_BYTES));
-        attr_set.store(true);
     }
     const int64_t n_units = kp.n_col_tiles * kp.n_pairs;
     dim3 grid((unsigned)std::min<int64_t>(n_units, sm_count));

@@ -528,12 +528,11 @@ inline int launch_agen(const AgenParams &ap, int64_t n_batch_chunk, int sm_count
     dim3 grid((unsigned)ap.n_row_tiles, (unsigned)ysplit, (unsigned)n_batch_chunk);
     // Same shared-memory carve-out as the contraction kernel, otherwise the two kernels cannot
     // be resident on one SM at the same time and the overlap is lost.
-    static std::atomic<bool> carveout_set{false};
-    if (!carveout_set.load()) {
+    static std::atomic<uint64_t> carveout_set{0};
+    if (first_launch_on_device(carveout_set)) {
 #define GSB_AGEN_ATTR(N) GSB_CUDA(cudaFuncSetAttribute(agen_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         GSB_AGEN_ATTR(1) GSB_AGEN_ATTR(2) GSB_AGEN_ATTR(3) GSB_AGEN_ATTR(4) GSB_AGEN_ATTR(5) GSB_AGEN_ATTR(6) GSB_AGEN_ATTR(7)
 #undef GSB_AGEN_ATTR
-        carveout_set.store(true);
     }
     switch (ap.n_row_axes) {
     case 1: agen_kernel<1><<<grid, SEP_TM, 0, st>>>(ap); break;
@@ -556,14 +555,13 @@ inline int launch_contract(ContractParams cp, int64_t n_batch_chunk, int sm_coun
     cp.n_fields = n_batch_chunk * cp.ncomp;
     const int64_t n_tiles = (int64_t)cp.n_col_tiles * cp.n_row_tiles * cp.n_fields;
     dim3 grid((unsigned)std::min<int64_t>(n_tiles, sm_count));
-    static std::atomic<bool> attr_set{false};
-    if (!attr_set.load()) {
+    static std::atomic<uint64_t> attr_set{0};
+    if (first_launch_on_device(attr_set)) {
         // full 228 KB carve-out: leaves room next to this CTA for A-generation CTAs
         GSB_CUDA(cudaFuncSetAttribute(contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM_BYTES));
         GSB_CUDA(cudaFuncSetAttribute(contract_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         GSB_CUDA(cudaFuncSetAttribute(contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM_BYTES));
         GSB_CUDA(cudaFuncSetAttribute(contract_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set.store(true);
     }
     if (scaled) contract_kernel<true><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
     else contract_kernel<false><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);

@@ -85,3 +85,38 @@ def test_nccl_sharded_structured_and_gather(tmp_path):
     world = min(_ngpu(), 4)
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_one_process_uses_several_devices():
+    """Kernel attributes (dynamic shared memory, carve-out) are per device: the same process must be
+    able to run every kernel family on device 0 and then on device 1, with identical bits."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import gstools_b200 as gsb
+    from conftest import synth_modes
+
+    cov, z1, z2 = synth_modes(3, 200, seed=5)
+    axes = [np.arange(20.0), np.arange(140.0), np.arange(150.0)]
+    rs = np.random.RandomState(3)
+    kmat, kcond, kv = rs.normal(size=(90, 90)), rs.normal(size=90), rs.uniform(-1, 1, (90, 3000))
+    cpos = rs.uniform(0, 20, (3, 89))
+    spec = dict(kind="Exponential", var=1.0, len_rescaled=5.0)
+    results = []
+    try:
+        for dev in (0, 1):
+            gsb.set_device(dev)
+            gsb.set_option("sep_path", 1)
+            a = gsb.summate_structured(cov, z1, z2, axes)
+            gsb.set_option("sep_path", 2)
+            b = gsb.summate_structured(cov, z1, z2, axes)
+            gsb.set_option("sep_path", 0)
+            c = np.stack(gsb.calc_field_krige_and_variance(kmat, kv, kcond))
+            d = np.stack(gsb.krige_evaluate(spec, kmat, kcond, cpos, axes=[a_[:12] for a_ in axes]))
+            e = gsb.summate(cov, z1, z2, rs.uniform(0, 50, (3, 0)) if False else np.ones((3, 5000)))
+            results.append((a, b, c, d, e))
+    finally:
+        gsb.set_option("sep_path", 0)
+        gsb.set_device(0)
+    for x, y in zip(*results):
+        assert np.array_equal(x, y)
