@@ -14,7 +14,7 @@ The compute lives in ``libgsb200.so`` (C ABI in ``include/gsb200.h``); there is 
 
 from . import _build, _lib
 from ._lib import (GSB200Error, device_count, get_counter, kernel_times, measure_fp64_peak,
-                   set_option)
+                   release_memory, set_option)
 from .backend import (
     calc_field_krige,
     calc_field_krige_and_variance,
@@ -58,6 +58,7 @@ __all__ = [
     "device_count",
     "get_counter",
     "set_option",
+    "release_memory",
     "measure_fp64_peak",
     "kernel_times",
     "GSB200Error",

@@ -84,6 +84,7 @@ SIGNATURES = {
                                      _int, _int, _int, _vp]),
     "gsb_scale_shift": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp]),
     "gsb_set_option": (_int, [ctypes.c_char_p, _i64]),
+    "gsb_release_memory": (_int, [_int]),
     "gsb_get_counter": (_i64, [ctypes.c_char_p]),
     "gsb_kernel_times": (_int, [_c_double_p, _c_int64_p]),
     "gsb_measure_fp64_peak": (_int, [_int, _int, ctypes.c_double, _c_double_p]),
@@ -141,6 +142,15 @@ def device_count() -> int:
 
 def set_option(name: str, value: int):
     check(load().gsb_set_option(name.encode(), int(value)), "gsb_set_option")
+
+
+def release_memory(device=None):
+    """Return the scratch memory the library keeps cached in the device's memory pool to the driver."""
+    if device is None:
+        from . import backend
+
+        device = backend.get_device()
+    check(load().gsb_release_memory(int(device)), "gsb_release_memory")
 
 
 def get_counter(name: str) -> int:

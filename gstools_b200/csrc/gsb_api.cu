@@ -1435,6 +1435,19 @@ int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int de
     return GSB_OK;
 }
 
+int gsb_release_memory(int device)
+{
+    DeviceGuard guard;
+    DeviceState *dev = nullptr;
+    GSB_TRY(ensure_device(device, &dev));
+    std::lock_guard<std::mutex> lock(dev->call_mutex);
+    GSB_CUDA(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    GSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    GSB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return GSB_OK;
+}
+
 int gsb_set_option(const char *name, int64_t value)
 {
     if (!name) return fail(GSB_ERR_ARGUMENT, "option name must not be NULL");

@@ -276,6 +276,14 @@ int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int de
  *   "direct_calls" / "separable_calls": how often each path ran.
  */
 int gsb_set_option(const char *name, int64_t value);
+
+/*
+ * Scratch (mode records, phase tables, the pre-tiled operands, staging buffers of the host routes)
+ * comes from the device's stream-ordered memory pool and is kept there between calls so that steady-state
+ * calls allocate nothing.  gsb_release_memory() waits for the device and returns the cached memory to the
+ * driver (e.g. before handing the GPU to another library in the same process).
+ */
+int gsb_release_memory(int device);
 int64_t gsb_get_counter(const char *name);
 
 /*

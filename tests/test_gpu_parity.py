@@ -446,3 +446,18 @@ def test_pinned_output_budget_on_the_gpu(gsb, monkeypatch):
     from test_host_logic import test_pinned_output_budget
 
     test_pinned_output_budget(gsb, monkeypatch)
+
+
+def test_release_memory_returns_the_cached_scratch(gsb):
+    import torch
+
+    cov, z1, z2 = synth_modes(3, 100, seed=2)
+    axes = [np.arange(64.0), np.arange(256.0), np.arange(256.0)]
+    ref = gsb.summate_structured(cov, z1, z2, axes)                  # host route: device output + scratch cached
+    torch.cuda.synchronize()
+    free_cached, _ = torch.cuda.mem_get_info()
+    gsb.release_memory()
+    free_released, _ = torch.cuda.mem_get_info()
+    assert free_released >= free_cached + 30 * 1024 * 1024           # at least the 33 MB field came back
+    again = gsb.summate_structured(cov, z1, z2, axes)                # and everything still works
+    assert np.array_equal(again, ref)
