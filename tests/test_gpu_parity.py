@@ -461,3 +461,20 @@ def test_release_memory_returns_the_cached_scratch(gsb):
     assert free_released >= free_cached + 30 * 1024 * 1024           # at least the 33 MB field came back
     again = gsb.summate_structured(cov, z1, z2, axes)                # and everything still works
     assert np.array_equal(again, ref)
+
+
+@pytest.mark.parametrize("scale", [1e3, 1e5, 1e7, 1e9])
+def test_large_phases_degrade_like_the_reference(scale, gsb, oracle_mod):
+    """|phase| up to ~1e10 rad: the exact range reduction keeps the kernel's own error at the
+    polynomial level; what grows is the rounding of the phase itself, |phase| * eps, which the
+    reference's libm path carries as well.  Bound: sum_j (|z1_j| + |z2_j|) * (4 eps |phase|_max + 1e-12)."""
+    cov, z1, z2 = synth_modes(3, 200, seed=17)
+    pos = np.random.RandomState(5).uniform(-scale, scale, (3, 20000))
+    got = gsb.summate(cov, z1, z2, pos)
+    want = oracle_mod.summate(cov, z1, z2, pos)
+    phase_max = float(np.max(np.abs(cov.T @ pos[:, :2000])))
+    bound = (np.abs(z1).sum() + np.abs(z2).sum()) * (4 * np.finfo(float).eps * phase_max * 3 + 1e-12)
+    assert maxabs(got, want) <= bound, (maxabs(got, want), bound, phase_max)
+    gv = gsb.summate_incompr(cov, z1, z2, pos)
+    wv = oracle_mod.summate_incompr(cov, z1, z2, pos)
+    assert maxabs(gv, wv) <= 2 * bound
