@@ -478,3 +478,23 @@ def test_large_phases_degrade_like_the_reference(scale, gsb, oracle_mod):
     gv = gsb.summate_incompr(cov, z1, z2, pos)
     wv = oracle_mod.summate_incompr(cov, z1, z2, pos)
     assert maxabs(gv, wv) <= 2 * bound
+
+
+@pytest.mark.parametrize("offset", [0.0, 1e4, 1e7])
+def test_structured_mesh_far_from_the_origin(offset, gsb, oracle_mod):
+    """Meshes with large coordinates (e.g. UTM eastings ~ 1e6..1e7): the per-axis phase tables use
+    full-range sincos, so the separable path degrades only by the rounding of the phases, like the
+    reference."""
+    cov, z1, z2 = synth_modes(3, 150, seed=23)
+    axes = [offset + np.arange(24.0), 2 * offset + np.linspace(0, 70, 130), -offset + np.arange(260.0)]
+    grid = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+    want = oracle_mod.summate(cov, z1, z2, grid).reshape(24, 130, 260)
+    phase_max = float(np.max(np.abs(cov.T @ grid[:, ::997])))
+    bound = (np.abs(z1).sum() + np.abs(z2).sum()) * (4 * np.finfo(float).eps * phase_max * 3 + 1e-12)
+    for force in (1, 2):
+        gsb.set_option("force_path", force)
+        try:
+            got = gsb.summate_structured(cov, z1, z2, axes)
+        finally:
+            gsb.set_option("force_path", 0)
+        assert maxabs(got, want) <= bound, (force, maxabs(got, want), bound)
