@@ -26,7 +26,7 @@ static std::atomic<int64_t> g_opt_min_chunks{4};     // so that A generation ove
 static std::atomic<int64_t> g_opt_chunk_growth_pct{140};
 static std::atomic<int64_t> g_opt_sep_path{0};      // 0 auto, 1 pre-generated A (agen), 2 scaled in the consumer
 static std::atomic<int64_t> g_cnt_scaled{0};
-static std::atomic<int64_t> g_opt_direct_cfg{-1};   // -1 auto, else force P = 1 / 2 / 4 points per thread (0 / 1 / 2)
+static std::atomic<int64_t> g_opt_direct_cfg{-1};   // -1 auto, else force P = 1 / 2 / 8 points per thread (0 / 1 / 2)
 static std::atomic<int64_t> g_cnt_direct{0}, g_cnt_separable{0};
 // optional device-side timing of the dominant kernels (bench.py roofline): events recorded on the
 // launch stream around every direct / separable launch while the option "time_kernels" is 1

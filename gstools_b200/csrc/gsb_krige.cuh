@@ -22,7 +22,7 @@
 //                        static striding over units is balanced.  Per stage of 16 depth indices one bulk
 //                        copy of the 20 KB operand tile plus 16 bulk copies of 1 KB -- the rows of kv
 //                        straight from the caller's row-major array into the padded B layout -- land in a
-//                        4-slot mbarrier ring.  Consumers: the DMMA.8x8x4 loop of the separable
+//                        5-slot mbarrier ring.  Consumers: the DMMA.8x8x4 loop of the separable
 //                        contraction (gsb_separable.cuh).  Epilogue: the accumulators times the matching kv
 //                        entries -- read from the stage buffers of the diagonal stages, where they pass through
 //                        shared memory anyway -- reduced over rows in a fixed order (registers -> shuffles ->
