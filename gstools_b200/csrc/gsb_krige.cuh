@@ -551,6 +551,40 @@ __device__ __forceinline__ double kvgen_entry(const KvgenParams &prm, int row, i
     return 0.0;
 }
 
+// cor(h) with the model fixed at compile time (same expressions as cov_cor)
+template <int KIND>
+__device__ __forceinline__ double cov_cor_t(double param, double h)
+{
+    CovParams m;
+    m.type = KIND;
+    m.param = param;
+    return cov_cor(m, h);     // the switch folds away: KIND is a constant
+}
+
+// covariance rows rr = half, half + 2, ... < n_cov of the staged block (rows r0 + rr < C)
+template <int D, int KIND>
+__device__ __forceinline__ void kvgen_cov_rows(const KvgenParams &prm, const double (&x)[D], const double *cp,
+                                               int half, int n_cov, int r0, int cl, double *T)
+{
+    const double var = prm.cov.var, len = prm.cov.len_rescaled, sill = prm.cov.sill, param = prm.cov.param;
+    const bool exact = prm.cov.exact != 0;
+#pragma unroll 1
+    for (int rr = half; rr < n_cov; rr += 2) {
+        const double *c = cp + rr * D;
+        double s2 = 0.0;
+#pragma unroll
+        for (int t = 0; t < D; ++t) {
+            const double dlt = __dsub_rn(c[t], x[t]);
+            s2 = __dadd_rn(s2, __dmul_rn(dlt, dlt));     // scipy cdist: plain sum of squares, then sqrt
+        }
+        const double r = sqrt(s2);
+        double v = var * cov_cor_t<KIND>(param, r / len);
+        if (exact && r <= 1e-8) v = sill;                  // cov_nugget (covmodel/base.py:313-320)
+        const int row = r0 + rr;
+        T[(row / KRG_KD) * SEP_B_TILE + (row % KRG_KD) * SEP_BST + cl] = v;
+    }
+}
+
 // one CTA per column tile of 128 points: every thread owns one point and every second row, walks down
 // all depth stages (position and constants set up once) and writes in the stage layout
 constexpr int KVGEN_ROWS = 1024;     // conditioning positions staged in shared memory per pass
@@ -579,8 +613,20 @@ __global__ void __launch_bounds__(256) kvgen_kernel(const KvgenParams prm)
             cp[rr][t] = row < prm.C ? prm.cond_pos[(int64_t)t * prm.C + row] : 0.0;
         }
         __syncthreads();
-#pragma unroll 1
-        for (int rr = half; rr < cnt; rr += 2) {
+        // covariance rows first, with the model's cor(h) resolved at compile time (no per-element
+        // switch, no per-element row classification), then the few non-covariance rows generically
+        const int n_cov = live ? max(0, min(cnt, prm.C - r0)) : 0;
+        switch (prm.cov.type) {
+#define GSB_KVGEN_CASE(KIND) \
+        case KIND: kvgen_cov_rows<D, KIND>(prm, x, &cp[0][0], half, n_cov, r0, cl, T); break;
+            GSB_KVGEN_CASE(GSB_COV_GAUSSIAN) GSB_KVGEN_CASE(GSB_COV_EXPONENTIAL) GSB_KVGEN_CASE(GSB_COV_STABLE)
+            GSB_KVGEN_CASE(GSB_COV_RATIONAL) GSB_KVGEN_CASE(GSB_COV_CUBIC) GSB_KVGEN_CASE(GSB_COV_LINEAR)
+            GSB_KVGEN_CASE(GSB_COV_CIRCULAR) GSB_KVGEN_CASE(GSB_COV_SPHERICAL)
+#undef GSB_KVGEN_CASE
+        default: break;
+        }
+        // first row of this thread's parity at or after n_cov
+        for (int rr = n_cov + ((n_cov ^ half) & 1); rr < cnt; rr += 2) {
             const int row = r0 + rr;
             T[(row / KRG_KD) * SEP_B_TILE + (row % KRG_KD) * SEP_BST + cl] =
                 live ? kvgen_entry<D>(prm, row, gcol, x, cp[rr]) : 0.0;
