@@ -26,6 +26,8 @@ static std::atomic<int64_t> g_opt_min_chunks{4};     // so that A generation ove
 static std::atomic<int64_t> g_opt_chunk_growth_pct{140};
 static std::atomic<int64_t> g_opt_sep_path{0};      // 0 auto, 1 pre-generated A (agen), 2 scaled in the consumer
 static std::atomic<int64_t> g_cnt_scaled{0};
+static std::atomic<int64_t> g_opt_fold_axes{1};     // 0 never, 1 when it improves the tile utilisation, 2 whenever it fits
+static std::atomic<int64_t> g_cnt_folded{0};
 static std::atomic<int64_t> g_opt_direct_cfg{-1};   // -1 auto, else force P = 1 / 2 / 8 points per thread (0 / 1 / 2)
 static std::atomic<int64_t> g_cnt_direct{0}, g_cnt_separable{0};
 // optional device-side timing of the dominant kernels (bench.py roofline): events recorded on the
@@ -366,8 +368,31 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     const int ncomp = vec ? dim : 1;
     Scratch scr(st);
     const int64_t force = g_opt_force_path.load();
-    const int64_t lc = mesh.len[dim - 1];
-    const int64_t n_row_tiles_total = (mesh.n_rows + SEP_TM - 1) / SEP_TM;
+    // Virtual mesh of the separable path.  Output tiles are 128 wide along the last (contiguous) axis; a
+    // thin mesh (1000 x 1000 x 10: reservoir layers) would use 10 of the 128 columns of every tile.  The
+    // phase still splits if the last TWO axes are treated as one axis of len_y * len_z entries (its table
+    // holds exp(i (k'_y y + k'_z z))), and C order makes that folded axis contiguous in the output.
+    MeshInfo vm = mesh;
+    if (dim >= 3 && g_opt_fold_axes.load() != 0) {
+        auto util = [](int64_t rows, int64_t cols) {
+            const double ru = (double)rows / (double)((rows + SEP_TM - 1) / SEP_TM * SEP_TM);
+            const double cu = (double)cols / (double)((cols + SEP_TN - 1) / SEP_TN * SEP_TN);
+            return ru * cu;
+        };
+        const int64_t wc2 = mesh.len[dim - 2] * mesh.len[dim - 1];
+        const int64_t n_pad = (n_modes + SEP_KC - 1) / SEP_KC * SEP_KC;
+        const bool fits = wc2 > 0 && wc2 * n_pad * ncomp * n_batch <= ((int64_t)1 << 26);   // <= 1 GiB of tables
+        const bool better = util(mesh.n / std::max<int64_t>(wc2, 1), wc2) > 1.15 * util(mesh.n_rows, mesh.len[dim - 1]);
+        if (fits && (better || g_opt_fold_axes.load() == 2)) {
+            vm.dim = dim - 1;
+            vm.len[dim - 2] = wc2;
+            vm.n_rows = mesh.n / wc2;
+        }
+    }
+    const bool folded = vm.dim != dim;
+    const int vdim = vm.dim;
+    const int64_t lc = vm.len[vdim - 1];
+    const int64_t n_row_tiles_total = (vm.n_rows + SEP_TM - 1) / SEP_TM;
     const int n_col_tiles = (int)((lc + SEP_TN - 1) / SEP_TN);
     const int64_t tiles = n_row_tiles_total * n_col_tiles * n_batch * ncomp;
     bool separable = dim >= 2 && n_modes > 0 && tiles >= g_opt_structured_min_tiles.load();
@@ -408,7 +433,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     }
 
     // ---- separable path: tables -> (A generation || contraction) per chunk ----
-    const int nra = dim - 1;
+    const int nra = vdim - 1;
     const int n_modes_pad = (int)((n_modes + SEP_KC - 1) / SEP_KC * SEP_KC);
     const int n_stages = n_modes_pad / SEP_KC;
     TableParams tp;
@@ -420,6 +445,9 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     tp.axes = d_axes;
     std::memcpy(tp.matrix, mesh.matrix, sizeof tp.matrix);
     tp.dim = dim;
+    tp.n_axes = vdim;
+    tp.fold_len = folded ? mesh.len[dim - 1] : 0;
+    tp.fold_off = folded ? mesh.off[dim - 1] : 0;
     tp.n_modes = n_modes;
     tp.n_modes_pad = n_modes_pad;
     tp.ncomp = ncomp;
@@ -427,9 +455,9 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     // Which contraction variant?  "scaled" (no A generation, ~89 % of peak whatever the shape, rows
     // padded to 128 per slow index) wins when an A tile would feed only one or two output tiles;
     // pre-generated A (~94 %) wins otherwise.  2-D meshes have no slow axis: A is the table itself.
-    const int64_t ly = mesh.len[dim - 2];
+    const int64_t ly = vm.len[vdim - 2];
     const int n_ytiles = (int)((ly + SEP_TM - 1) / SEP_TM);
-    const int64_t n_slow = mesh.n_rows / ly;
+    const int64_t n_slow = vm.n_rows / ly;
     bool scaled = false;
     if (nra >= 2) {
         const int64_t tpu = (int64_t)n_col_tiles * ncomp;
@@ -446,20 +474,20 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         GSB_TRY(scr.alloc(&tp.ytab, (size_t)n_batch * n_ytiles * n_stages * SEP_A_TILE));
         max_width = std::max<int64_t>(max_width, (int64_t)n_ytiles * SEP_TM);
     }
-    for (int t = 0; t < dim; ++t) {
+    for (int t = 0; t < vdim; ++t) {
         tp.axis_off[t] = mesh.off[t];
-        tp.axis_len[t] = mesh.len[t];
+        tp.axis_len[t] = vm.len[t];
         if (t < nra) {
-            tp.erow_bstride[t] = mesh.len[t] * n_modes_pad;
+            tp.erow_bstride[t] = vm.len[t] * n_modes_pad;
             GSB_TRY(scr.alloc(&tp.erow[t], (size_t)n_batch * tp.erow_bstride[t]));
-            max_width = std::max(max_width, mesh.len[t]);
+            max_width = std::max(max_width, vm.len[t]);
         }
     }
     GSB_TRY(scr.alloc(&tp.btile, (size_t)n_batch * ncomp * n_col_tiles * n_stages * SEP_B_TILE));
     {
         if (n_batch > 65535) return fail(GSB_ERR_ARGUMENT, "n_batch too large");
         const int64_t work = max_width * n_modes_pad;
-        dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 4096), (unsigned)dim, (unsigned)n_batch);
+        dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 4096), (unsigned)vdim, (unsigned)n_batch);
         build_tables_kernel<<<grid, 256, 0, st>>>(tp);
         g_launches.fetch_add(1);
         GSB_CUDA(cudaGetLastError());
@@ -472,7 +500,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         for (int t = 0; t < nra - 1; ++t) {
             ctp.erow[t] = tp.erow[t];
             ctp.erow_bstride[t] = tp.erow_bstride[t];
-            ctp.row_len[t] = mesh.len[t];
+            ctp.row_len[t] = vm.len[t];
         }
         ctp.n_slow = n_slow;
         ctp.n_modes_pad = n_modes_pad;
@@ -490,7 +518,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         cp.n_col_tiles = n_col_tiles;
         cp.n_stages = n_stages;
         cp.ncomp = ncomp;
-        cp.n_rows = mesh.n_rows;
+        cp.n_rows = vm.n_rows;
         cp.lc = lc;
         cp.out = d_out;
         cp.out_fstride = mesh.n;
@@ -544,6 +572,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         }
         g_cnt_separable.fetch_add(1);
         g_cnt_scaled.fetch_add(1);
+        if (folded) g_cnt_folded.fetch_add(1);
         return GSB_OK;
     }
 
@@ -613,9 +642,9 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     for (int t = 0; t < nra; ++t) {
         ap.erow[t] = tp.erow[t];
         ap.erow_bstride[t] = tp.erow_bstride[t];
-        ap.row_len[t] = mesh.len[t];
+        ap.row_len[t] = vm.len[t];
     }
-    ap.n_rows = mesh.n_rows;
+    ap.n_rows = vm.n_rows;
     ap.n_modes_pad = n_modes_pad;
     ContractParams cp;
     std::memset(&cp, 0, sizeof cp);
@@ -623,7 +652,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     cp.n_col_tiles = n_col_tiles;
     cp.n_stages = n_stages;
     cp.ncomp = ncomp;
-    cp.n_rows = mesh.n_rows;
+    cp.n_rows = vm.n_rows;
     cp.lc = lc;
     cp.out = d_out;
     cp.out_fstride = mesh.n;
@@ -661,7 +690,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
                 // copy the finished chunk to the host while the next one is being computed
                 GSB_CUDA(cudaStreamWaitEvent(copy_st, dev.contract_events[c % NE], 0));
                 const int64_t row_lo = r0 * SEP_TM;
-                const int64_t row_hi = std::min<int64_t>(mesh.n_rows, (r0 + nrt) * SEP_TM);
+                const int64_t row_hi = std::min<int64_t>(vm.n_rows, (r0 + nrt) * SEP_TM);
                 if (whole_fields) {
                     const size_t off = (size_t)f0 * ncomp * mesh.n;
                     GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * nf * ncomp * mesh.n,
@@ -693,6 +722,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         g_trace.clear();
     }
     g_cnt_separable.fetch_add(1);
+    if (folded) g_cnt_folded.fetch_add(1);
     return GSB_OK;
 }
 
@@ -1462,6 +1492,7 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "sep_path") g_opt_sep_path = value;
     else if (n == "chunk_growth_pct") g_opt_chunk_growth_pct = std::max<int64_t>(value, 100);
     else if (n == "time_kernels") g_opt_time_kernels = value;
+    else if (n == "fold_axes") g_opt_fold_axes = value;
     else if (n == "krige_host_chunk_mb") g_opt_krige_host_chunk_mb = std::max<int64_t>(value, 1);
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);
     return GSB_OK;
@@ -1476,6 +1507,7 @@ int64_t gsb_get_counter(const char *name)
     if (n == "separable_calls") return g_cnt_separable.load();
     if (n == "scaled_calls") return g_cnt_scaled.load();
     if (n == "krige_calls") return g_cnt_krige.load();
+    if (n == "folded_calls") return g_cnt_folded.load();
     return -1;
 }
 

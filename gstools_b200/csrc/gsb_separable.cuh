@@ -89,7 +89,10 @@ struct TableParams {
     int64_t axis_off[GSB_MAX_DIM];
     int64_t axis_len[GSB_MAX_DIM];
     double matrix[GSB_MAX_DIM * GSB_MAX_DIM];  // row-major (dim x dim) isometrisation matrix
-    int dim;
+    int dim;               // dimension of the wave vectors / the matrix
+    int n_axes;            // table axes: dim, or dim - 1 when the last two mesh axes are folded into one
+    int64_t fold_len;      // folded: length of the real last axis (0 = not folded); table entry i of the
+    int64_t fold_off;      //   last table axis is node (i / fold_len, i % fold_len) of the last two axes
     int64_t n_modes;
     int n_modes_pad;       // multiple of SEP_KC; padded modes are zero
     int ncomp;             // 1 scalar, dim for the incompressible field
@@ -112,8 +115,8 @@ __global__ void build_tables_kernel(const TableParams tp)
     const int t = blockIdx.y;                 // axis
     const int64_t b = blockIdx.z;             // batch entry
     const int64_t len = tp.axis_len[t];
-    const bool last = (t == tp.dim - 1);
-    const bool ytile = (tp.ytab != nullptr && t == tp.dim - 2);
+    const bool last = (t == tp.n_axes - 1);
+    const bool ytile = (tp.ytab != nullptr && t == tp.n_axes - 2);
     const int64_t width = last ? (int64_t)tp.n_col_tiles * SEP_TN : (ytile ? (int64_t)tp.n_ytiles * SEP_TM : len);
     const int64_t total = width * tp.n_modes_pad;
     const int n_stages = tp.n_modes_pad / SEP_KC;
@@ -128,7 +131,16 @@ __global__ void build_tables_kernel(const TableParams tp)
             double kp = 0.0;
             for (int s2 = 0; s2 < tp.dim; ++s2)
                 kp = fma(tp.matrix[s2 * tp.dim + t], cov[(int64_t)s2 * tp.n_modes + j], kp);
-            sincos(kp * tp.axes[tp.axis_off[t] + i], &s, &c);
+            double phase;
+            if (last && tp.fold_len > 0) {   // folded trailing axes: k'_y y + k'_z z
+                double kz = 0.0;
+                for (int s2 = 0; s2 < tp.dim; ++s2)
+                    kz = fma(tp.matrix[s2 * tp.dim + t + 1], cov[(int64_t)s2 * tp.n_modes + j], kz);
+                phase = fma(kp, tp.axes[tp.axis_off[t] + i / tp.fold_len], kz * tp.axes[tp.fold_off + i % tp.fold_len]);
+            } else {
+                phase = kp * tp.axes[tp.axis_off[t] + i];
+            }
+            sincos(phase, &s, &c);
             if (t == 0 && !last) {  // fold the complex weight (z1 - i z2) into the first row axis
                 const double w = tp.sf ? tp.sf[b * tp.n_modes + j] : 1.0;
                 const double a = w * tp.z1[b * tp.n_modes + j], bb = w * tp.z2[b * tp.n_modes + j];

@@ -498,3 +498,46 @@ def test_structured_mesh_far_from_the_origin(offset, gsb, oracle_mod):
         finally:
             gsb.set_option("force_path", 0)
         assert maxabs(got, want) <= bound, (force, maxabs(got, want), bound)
+
+
+@pytest.mark.parametrize("shape", [(300, 260, 10), (129, 33, 5), (40, 50, 70), (6, 20, 9, 14)])
+def test_thin_meshes_fold_the_last_two_axes(shape, gsb, oracle_mod):
+    """Meshes whose last axis is short (layered models: nz = 5..50) would use a fraction of every
+    128-wide output tile; the separable path then treats the last two axes as one.  Scalar and
+    vector fields, with an isometrisation matrix, against the oracle and against the unfolded path."""
+    dim = len(shape)
+    cov, z1, z2 = synth_modes(dim, 130, seed=sum(shape))
+    axes = [np.sort(np.random.RandomState(t).uniform(-5, 60, s)) for t, s in enumerate(shape)]
+    mat = np.random.RandomState(9).normal(size=(dim, dim))
+    grid = mat @ np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+    want = oracle_mod.summate(cov, z1, z2, grid).reshape(shape)
+    gsb.set_option("structured_min_tiles", 1)
+    try:
+        out = {}
+        for fold in (0, 2):
+            gsb.set_option("fold_axes", fold)
+            before = gsb.get_counter("folded_calls")
+            out[fold] = gsb.summate_structured(cov, z1, z2, axes, mat)
+            assert (gsb.get_counter("folded_calls") > before) == (fold == 2)
+            assert maxabs(out[fold], want) <= raw_tol(130)
+        if dim == 3:
+            wantv = oracle_mod.summate_incompr(cov, z1, z2, grid).reshape((3,) + shape)
+            gotv = gsb.summate_incompr_structured(cov, z1, z2, axes, mat)
+            assert maxabs(gotv, wantv) <= raw_tol(130)
+        # automatic choice: folds only where it improves the tile utilisation
+        gsb.set_option("fold_axes", 1)
+        before = gsb.get_counter("folded_calls")
+        auto = gsb.summate_structured(cov, z1, z2, axes, mat)
+        assert maxabs(auto, want) <= raw_tol(130)
+        assert (gsb.get_counter("folded_calls") > before) == (shape[-1] < 64)
+        # fused epilogue and batches go through the folded path unchanged
+        gsb.set_option("fold_axes", 2)
+        covb = np.stack([cov, 0.5 * cov])
+        rawb = gsb.summate_structured(covb, np.stack([z1, z2]), np.stack([z2, z1]), axes, mat)
+        gotb = gsb.summate_structured(covb, np.stack([z1, z2]), np.stack([z2, z1]), axes, mat,
+                                      epilogue=(0.25, [0.0, 1.5]))
+        assert maxabs(rawb[0], want) <= raw_tol(130)
+        assert np.array_equal(gotb, oracle_mod.apply_epilogue(rawb, 0.25, [0.0, 1.5]))
+    finally:
+        gsb.set_option("fold_axes", 1)
+        gsb.set_option("structured_min_tiles", 64)
