@@ -271,6 +271,8 @@ int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int de
  *   gsb_set_option("force_path", 0|1|2): 0 auto, 1 always direct, 2 always separable.
  *   gsb_set_option("scratch_mb", v): budget (MiB) for the pre-tiled A operand of the structured
  *       path; larger meshes are processed in row chunks (default 3072).
+ *   gsb_set_option("fold_axes", 0|1|2): fold the last two axes of a thin mesh into one column axis of the
+ *       structured path: 0 never, 1 when it improves the tile utilisation (default), 2 whenever it fits.
  *   gsb_set_option("time_kernels", 0|1): see gsb_kernel_times().
  *   gsb_get_counter("launches"): CUDA kernels launched by this library so far (process-wide);
  *   "direct_calls" / "separable_calls": how often each path ran.
