@@ -396,6 +396,14 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     const int n_col_tiles = (int)((lc + SEP_TN - 1) / SEP_TN);
     const int64_t tiles = n_row_tiles_total * n_col_tiles * n_batch * ncomp;
     bool separable = dim >= 2 && n_modes > 0 && tiles >= g_opt_structured_min_tiles.load();
+    {
+        // Tiles are 128 x 128: when the (virtual) mesh fills only a small part of them -- e.g. a 2-D mesh with
+        // a very short last axis, which cannot be folded -- the direct kernel (D + 13 instructions per pair
+        // at ~86 % of the pipe) beats the contraction (2 per pair at ~94 %, but on padded tiles).
+        const double ru = (double)vm.n_rows / (double)(n_row_tiles_total * SEP_TM);
+        const double cu = (double)lc / (double)((int64_t)n_col_tiles * SEP_TN);
+        if (ru * cu * (double)(dim + 13) / 0.86 < 2.0 / 0.94) separable = false;
+    }
     if (force == 1) separable = false;
     if (force == 2 && dim >= 2 && n_modes > 0) separable = true;
 

@@ -541,3 +541,15 @@ def test_thin_meshes_fold_the_last_two_axes(shape, gsb, oracle_mod):
     finally:
         gsb.set_option("fold_axes", 1)
         gsb.set_option("structured_min_tiles", 64)
+
+
+def test_badly_filled_tiles_go_to_the_direct_kernel(gsb, oracle_mod):
+    """A 2-D mesh with a very short last axis fills 5 % of every 128-wide tile and cannot be folded:
+    the structured entry then expands it on the device and uses the direct kernel."""
+    cov, z1, z2 = synth_modes(2, 64, seed=4)
+    axes = [np.arange(30000.0) * 0.01, np.arange(6.0)]
+    before = (gsb.get_counter("direct_calls"), gsb.get_counter("separable_calls"))
+    got = gsb.summate_structured(cov, z1, z2, axes)
+    assert gsb.get_counter("direct_calls") == before[0] + 1 and gsb.get_counter("separable_calls") == before[1]
+    grid = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+    assert maxabs(got.reshape(-1), oracle_mod.summate(cov, z1, z2, grid)) <= raw_tol(64)
