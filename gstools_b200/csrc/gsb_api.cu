@@ -381,7 +381,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         };
         const int64_t wc2 = mesh.len[dim - 2] * mesh.len[dim - 1];
         const int64_t n_pad = (n_modes + SEP_KC - 1) / SEP_KC * SEP_KC;
-        const bool fits = wc2 > 0 && wc2 * n_pad * ncomp * n_batch <= ((int64_t)1 << 26);   // <= 1 GiB of tables
+        const bool fits = wc2 > 0 && wc2 * n_pad * ncomp * n_batch <= ((int64_t)1 << 28);   // <= 4 GiB of tables
         const bool better = util(mesh.n / std::max<int64_t>(wc2, 1), wc2) > 1.15 * util(mesh.n_rows, mesh.len[dim - 1]);
         if (fits && (better || g_opt_fold_axes.load() == 2)) {
             vm.dim = dim - 1;
