@@ -28,6 +28,7 @@ static std::atomic<int64_t> g_opt_sep_path{0};      // 0 auto, 1 pre-generated A
 static std::atomic<int64_t> g_cnt_scaled{0};
 static std::atomic<int64_t> g_opt_fold_axes{1};     // 0 never, 1 when it improves the tile utilisation, 2 whenever it fits
 static std::atomic<int64_t> g_cnt_folded{0};
+static std::atomic<int64_t> g_opt_partial_tiles{1};  // 0: full-tile contraction kernel even for partial column tiles
 static std::atomic<int64_t> g_opt_direct_cfg{-1};   // -1 auto, else force P = 1 / 2 / 8 points per thread (0 / 1 / 2)
 static std::atomic<int64_t> g_cnt_direct{0}, g_cnt_separable{0};
 // optional device-side timing of the dominant kernels (bench.py roofline): events recorded on the
@@ -531,6 +532,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         cp.out = d_out;
         cp.out_fstride = mesh.n;
         cp.epi = epi;
+        cp.no_partial = g_opt_partial_tiles.load() ? 0 : 1;
         cp.ytab = tp.ytab;
         cp.ctab = ctp.ctab;
         cp.n_ytiles = n_ytiles;
@@ -665,6 +667,7 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     cp.out = d_out;
     cp.out_fstride = mesh.n;
     cp.epi = epi;
+    cp.no_partial = g_opt_partial_tiles.load() ? 0 : 1;
 
     int64_t c = 0;
     for (const Chunk &ch : chunks) {
@@ -1501,6 +1504,7 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "chunk_growth_pct") g_opt_chunk_growth_pct = std::max<int64_t>(value, 100);
     else if (n == "time_kernels") g_opt_time_kernels = value;
     else if (n == "fold_axes") g_opt_fold_axes = value;
+    else if (n == "partial_tiles") g_opt_partial_tiles = value;
     else if (n == "krige_host_chunk_mb") g_opt_krige_host_chunk_mb = std::max<int64_t>(value, 1);
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);
     return GSB_OK;

@@ -40,6 +40,7 @@
 #pragma once
 
 #include <algorithm>
+#include <type_traits>
 
 #include "gsb_common.cuh"
 
@@ -317,6 +318,7 @@ struct ContractParams {
     int n_modes_pad;
     int64_t rt0;           // first (global) row tile of this launch
     Epi epi;               // fused caller epilogue (off: raw sums)
+    int no_partial;        // tuning: 1 = always the full-tile kernel (option "partial_tiles" = 0)
 };
 
 __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b)
@@ -333,7 +335,11 @@ __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, doubl
 //                 its own A fragments (2 FP64 ops per fragment).  Costs ~9 % of the DMMA rate
 //                 (profiles/r01_microbench_dmma_tma.log) but no scratch, no extra HBM traffic, and
 //                 it does not depend on how often an A tile is reused.
-template <bool SCALED>
+//
+// PARTIAL = true : the last column tile of every row is narrower than 128 (last axis not a multiple of 128):
+//                  warps skip the 8-column groups beyond the mesh.  A separate instantiation, so that the
+//                  full-tile kernel keeps its code and register count.
+template <bool SCALED, bool PARTIAL = false>
 __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const ContractParams prm)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -417,8 +423,11 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
     }
 
     // warp tile 32 x 64 = 4 x 8 DMMA tiles of 8x8; fragment owner: g = lane/4, t = lane%4
-    const int wr = warp >> 1;        // 0..3 : 32-row band
-    const int wc = warp & 1;         // 0..1 : 64-column band
+    // Sub-partition k hosts warps k and k + 4: it gets BOTH 64-column halves of band k.  In a partial
+    // column tile (last axis not a multiple of 128) the right half has fewer valid 8-column groups than the
+    // left; with both on the same FP64 pipe the tile costs ceil(width / 8) / 16 of a full one.
+    const int wr = warp & 3;                        // 0..3 : 32-row band
+    const int wc = ((warp >> 2) ^ warp) & 1;        // 0..1 : 64-column half
     const int g = lane >> 2;
     const int t = lane & 3;
     const int a_off = (wr * 32 + g) * SEP_AST + t;               // + i*8*SEP_AST + 4*k4
@@ -434,6 +443,13 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+        // valid 8-column groups of this warp's half in this column tile (8 everywhere but in the last one)
+        int jv = 8;
+        if (PARTIAL) {
+            const int cw_tile = (int)min((int64_t)SEP_TN, prm.lc - (tile % prm.n_col_tiles) * SEP_TN);
+            jv = max(0, min(8, (cw_tile - 64 * wc + 7) >> 3));
+        }
+
         for (int s = 0; s < n_stages; ++s) {
             // prefetch DEPTH steps ahead into the slot of the step before last, which every warp
             // released long ago (the wait on its "empty" barrier practically never blocks)
@@ -448,33 +464,41 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
             __syncwarp();
             mbar_wait(&full[slot], round & 1);
             const double *S = stage_base + slot * SEP_STAGE_DOUBLES;
+            auto contract_stage = [&](auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-            for (int k4 = 0; k4 < SEP_KC / 2; ++k4) {   // 4 contraction indices = 2 modes
-                double af[4], bf[8];
+                for (int k4 = 0; k4 < SEP_KC / 2; ++k4) {   // 4 contraction indices = 2 modes
+                    double af[4], bf[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) af[i] = S[a_off + i * 8 * SEP_AST + 4 * k4];
+                    for (int i = 0; i < 4; ++i) af[i] = S[a_off + i * 8 * SEP_AST + 4 * k4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) bf[j] = S[b_off + 4 * k4 * SEP_BST + j * 8];
-                if (SCALED) {
-                    // this lane holds part (t & 1) of mode 2*k4 + (t >> 1): (cos, sin) of the last row
-                    // axis.  With c = (cr, ci) the slow-axis factor, the contraction needs
-                    //   part 0:  Re(c e) =  cr*cos - ci*sin       part 1: -Im(c e) = -cr*sin - ci*cos
-                    // i.e. alpha*own + beta*partner with alpha = +-cr, beta = -ci.
-                    const double2 cc = *reinterpret_cast<const double2 *>(
-                        S + SEP_A_TILE + SEP_B_TILE + 2 * (2 * k4 + (t >> 1)));
-                    const double alpha = (t & 1) ? -cc.x : cc.x;
-                    const double beta = -cc.y;
+                    for (int j = 0; j < 8; ++j)
+                        if (FULL || j < jv) bf[j] = S[b_off + 4 * k4 * SEP_BST + j * 8];
+                    if (SCALED) {
+                        // this lane holds part (t & 1) of mode 2*k4 + (t >> 1): (cos, sin) of the last row
+                        // axis.  With c = (cr, ci) the slow-axis factor, the contraction needs
+                        //   part 0:  Re(c e) =  cr*cos - ci*sin       part 1: -Im(c e) = -cr*sin - ci*cos
+                        // i.e. alpha*own + beta*partner with alpha = +-cr, beta = -ci.
+                        const double2 cc = *reinterpret_cast<const double2 *>(
+                            S + SEP_A_TILE + SEP_B_TILE + 2 * (2 * k4 + (t >> 1)));
+                        const double alpha = (t & 1) ? -cc.x : cc.x;
+                        const double beta = -cc.y;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const double partner = __shfl_xor_sync(0xffffffffu, af[i], 1);
-                        af[i] = fma(alpha, af[i], beta * partner);
+                        for (int i = 0; i < 4; ++i) {
+                            const double partner = __shfl_xor_sync(0xffffffffu, af[i], 1);
+                            af[i] = fma(alpha, af[i], beta * partner);
+                        }
                     }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (FULL || j < jv) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                        }
                 }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-            }
+            };
+            if (!PARTIAL || jv == 8) contract_stage(std::true_type{});
+            else if (jv > 0) contract_stage(std::false_type{});
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
             if (++slot == SEP_STAGES) { slot = 0; ++round; }
@@ -570,13 +594,21 @@ inline int launch_contract(ContractParams cp, int64_t n_batch_chunk, int sm_coun
     static std::atomic<uint64_t> attr_set{0};
     if (first_launch_on_device(attr_set)) {
         // full 228 KB carve-out: leaves room next to this CTA for A-generation CTAs
-        GSB_CUDA(cudaFuncSetAttribute(contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM_BYTES));
-        GSB_CUDA(cudaFuncSetAttribute(contract_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        GSB_CUDA(cudaFuncSetAttribute(contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM_BYTES));
-        GSB_CUDA(cudaFuncSetAttribute(contract_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#define GSB_CONTRACT_ATTR(K)                                                                                         \
+        GSB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM_BYTES));           \
+        GSB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        GSB_CONTRACT_ATTR((contract_kernel<false, false>)) GSB_CONTRACT_ATTR((contract_kernel<false, true>))
+        GSB_CONTRACT_ATTR((contract_kernel<true, false>)) GSB_CONTRACT_ATTR((contract_kernel<true, true>))
+#undef GSB_CONTRACT_ATTR
     }
-    if (scaled) contract_kernel<true><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
-    else contract_kernel<false><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
+    const bool partial = (cp.lc % SEP_TN) != 0 && !cp.no_partial;
+    if (scaled) {
+        if (partial) contract_kernel<true, true><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
+        else contract_kernel<true, false><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
+    } else {
+        if (partial) contract_kernel<false, true><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
+        else contract_kernel<false, false><<<grid, SEP_THREADS, SEP_SMEM_BYTES, st>>>(cp);
+    }
     g_launches.fetch_add(1);
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;
