@@ -371,6 +371,15 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
     // allocated to a CTA in units of four warps, so a ninth warp would cost as much as twelve.
     // Every thread tracks the prefetch cursor (tile, stage) incrementally -- no divisions in the
     // steady state.
+    // tile -> column tile.  Column tile fastest, so that the CTAs working side by side share their A tiles.
+    // With partial last column tiles the tiles of a row differ in cost; when the number of column tiles
+    // divides the grid size every CTA would always get the same column tile (148 CTAs, 2 column tiles: half
+    // of the CTAs only ever see the cheap partial tile), so the column index is rotated by the CTA's round.
+    const bool skew = PARTIAL && (gridDim.x % prm.n_col_tiles) == 0;
+    auto col_tile_of = [&](int64_t tile_idx) {
+        const int64_t c0 = tile_idx % prm.n_col_tiles;
+        return (int)(skew ? (c0 + tile_idx / gridDim.x) % prm.n_col_tiles : c0);
+    };
     constexpr int DEPTH = SEP_STAGES - 2;   // steps in flight ahead of the one being contracted
     int64_t pf_tile = blockIdx.x;
     int pf_s = 0;
@@ -378,7 +387,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
     uint32_t pf_round = 0;                  // how often pf_slot has wrapped
     const double *pf_a = nullptr, *pf_b = nullptr, *pf_c = nullptr;
     auto pf_decode = [&]() {
-        const int ct = (int)(pf_tile % prm.n_col_tiles);
+        const int ct = col_tile_of(pf_tile);
         const int64_t rest = pf_tile / prm.n_col_tiles;
         const int rt = (int)(rest % prm.n_row_tiles);
         const int64_t z = rest / prm.n_row_tiles;          // field-local index * ncomp + comp
@@ -446,7 +455,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
         // valid 8-column groups of this warp's half in this column tile (8 everywhere but in the last one)
         int jv = 8;
         if (PARTIAL) {
-            const int cw_tile = (int)min((int64_t)SEP_TN, prm.lc - (tile % prm.n_col_tiles) * SEP_TN);
+            const int cw_tile = (int)min((int64_t)SEP_TN, prm.lc - (int64_t)col_tile_of(tile) * SEP_TN);
             jv = max(0, min(8, (cw_tile - 64 * wc + 7) >> 3));
         }
 
@@ -505,7 +514,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
         }
 
         // epilogue: thread holds C[g][2t], C[g][2t+1] of every 8x8 tile
-        const int ct = (int)(tile % prm.n_col_tiles);
+        const int ct = col_tile_of(tile);
         const int64_t rest = tile / prm.n_col_tiles;
         const int rt = (int)(rest % prm.n_row_tiles);
         const int64_t z = rest / prm.n_row_tiles;
