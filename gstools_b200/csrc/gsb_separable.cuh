@@ -432,16 +432,15 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
     }
 
     // warp tile 32 x 64 = 4 x 8 DMMA tiles of 8x8; fragment owner: g = lane/4, t = lane%4
-    // Sub-partition k hosts warps k and k + 4: they share band k, and the 16 groups of 8 columns are dealt
-    // out alternately (warp wc owns groups wc, wc + 2, ...).  In a partial column tile (last axis not a
-    // multiple of 128) both warps then lose the same number of groups and keep the FP64 pipe of their
-    // sub-partition full together (one warp alone cannot), so the tile costs ~ceil(width / 8) / 16 of a full one.
+    // Sub-partition k hosts warps k and k + 4: it gets BOTH 64-column halves of band k.  In a partial
+    // column tile (last axis not a multiple of 128) the right half has fewer valid 8-column groups than the
+    // left; with both on the same FP64 pipe the tile costs ceil(width / 8) / 16 of a full one.
     const int wr = warp & 3;                        // 0..3 : 32-row band
-    const int wc = ((warp >> 2) ^ warp) & 1;        // 0..1 : parity of the 8-column groups
+    const int wc = ((warp >> 2) ^ warp) & 1;        // 0..1 : 64-column half
     const int g = lane >> 2;
     const int t = lane & 3;
     const int a_off = (wr * 32 + g) * SEP_AST + t;               // + i*8*SEP_AST + 4*k4
-    const int b_off = SEP_A_TILE + t * SEP_BST + wc * 8 + g;     // + 4*k4*SEP_BST + j*16
+    const int b_off = SEP_A_TILE + t * SEP_BST + wc * 64 + g;    // + 4*k4*SEP_BST + j*8
 
     int slot = 0;
     uint32_t round = 0;
@@ -457,7 +456,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
         int jv = 8;
         if (PARTIAL) {
             const int cw_tile = (int)min((int64_t)SEP_TN, prm.lc - (int64_t)col_tile_of(tile) * SEP_TN);
-            jv = max(0, min(8, (((cw_tile + 7) >> 3) - wc + 1) >> 1));   // groups wc, wc + 2, ... below ceil(width / 8)
+            jv = max(0, min(8, (cw_tile - 64 * wc + 7) >> 3));
         }
 
         for (int s = 0; s < n_stages; ++s) {
@@ -483,7 +482,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
                     for (int i = 0; i < 4; ++i) af[i] = S[a_off + i * 8 * SEP_AST + 4 * k4];
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (FULL || j < jv) bf[j] = S[b_off + 4 * k4 * SEP_BST + j * 16];
+                        if (FULL || j < jv) bf[j] = S[b_off + 4 * k4 * SEP_BST + j * 8];
                     if (SCALED) {
                         // this lane holds part (t & 1) of mode 2*k4 + (t >> 1): (cos, sin) of the last row
                         // axis.  With c = (cr, ci) the slow-axis factor, the contraction needs
@@ -549,7 +548,7 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
             if (row >= row_end) continue;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int64_t col = col0 + (2 * j + wc) * 8 + 2 * t;
+                const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
                 double *dst = out + row * prm.lc + col;
                 if (vec2 && col + 1 < prm.lc) {
                     *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
