@@ -599,12 +599,6 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         int64_t a2 = tiles_per_unit, b2 = dev.sm_count;
         while (b2) { const int64_t tmp = a2 % b2; a2 = b2; b2 = tmp; }
         q = dev.sm_count / a2;     // units per whole wave
-        // Partial last column tiles are cheaper than full ones.  A one-wave launch gives every CTA exactly
-        // one tile, cheap or not, and takes as long as a full tile; with as many waves as there are column
-        // tiles every CTA gets each kind once (the kernel rotates the column index with the CTA's round).
-        if ((lc % SEP_TN) != 0 && g_opt_partial_tiles.load() && dev.sm_count % n_col_tiles == 0 &&
-            q * n_col_tiles <= std::max<int64_t>(q, total_units / 2))
-            q *= n_col_tiles;
     }
     int64_t cap = std::max<int64_t>(1, (int64_t)((size_t)g_opt_scratch_mb.load() * (1u << 20) / 2 / unit_bytes));
     cap = std::min<int64_t>(cap, total_units);
