@@ -675,3 +675,56 @@ def test_fused_generator_calls_match_reference_bits(gsb, oracle_mod, monkeypatch
         assert got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k
     # the literals of tests/test_randmeth.py:38-41
     assert round(got["rm"][0] - 1.67318010, 7) == 0 and round(got["rm"][1] - 2.12310269, 7) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# property tests (hypothesis) of small host-side pieces
+# ---------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=200, deadline=None)
+@given(n=st.integers(0, 10**12), world=st.integers(1, 64))
+def test_shard_range_properties(n, world):
+    from gstools_b200.dist import shard_range
+
+    prev = 0
+    for r in range(world):
+        lo, hi = shard_range(n, r, world)
+        assert lo == prev and hi >= lo and hi - lo in (n // world, n // world + 1)
+        prev = hi
+    assert prev == n
+
+
+@settings(max_examples=100, deadline=None)
+@given(scale=st.floats(-1e6, 1e6, allow_nan=False), adds=st.lists(
+    st.one_of(st.floats(-1e3, 1e3, allow_nan=False),
+              st.tuples(*[st.floats(-1e3, 1e3, allow_nan=False)] * 3)), max_size=4))
+def test_make_epilogue_round_trips(gsb_mod, scale, adds):
+    epi = gsb_mod.make_epilogue(scale, adds)
+    assert epi.scale == scale and epi.n_add == len(adds)
+    for k, a in enumerate(adds):
+        want = list(a) if isinstance(a, tuple) else [a] * 3
+        assert [epi.add[k][c] for c in range(3)] == want
+
+
+@pytest.fixture(scope="module")
+def gsb_mod():
+    import gstools_b200
+
+    return gstools_b200
+
+
+@settings(max_examples=50, deadline=None)
+@given(lens=st.lists(st.integers(1, 7), min_size=2, max_size=4), seed=st.integers(0, 2**16))
+def test_oracle_apply_epilogue_matches_sequential_numpy(lens, seed):
+    """oracle.apply_epilogue is the sequence of separately rounded numpy passes it claims to be."""
+    import oracle
+
+    rs = np.random.RandomState(seed)
+    raw = rs.normal(size=(3,) + tuple(lens))
+    scale, a0, a1 = rs.normal(), rs.normal(), rs.normal(size=3)
+    want = scale * raw
+    want = want + a0
+    want = want + a1.reshape((3,) + (1,) * len(lens))
+    assert np.array_equal(oracle.apply_epilogue(raw, scale, [a0, tuple(a1)]), want)
