@@ -185,6 +185,16 @@ def cpu_sample_points(cfg, n_pts, offset=0):
     return bc.grid_points(cfg["axes"], cfg.get("matrix"), idx)
 
 
+def host_threads():
+    """Threads of the CPU arm: every core this process may run on, set EXPLICITLY.  The reference uses all
+    cores (src/gstools/config.py:8, NUM_THREADS = None -> all); torchrun exports OMP_NUM_THREADS=1, which
+    must not silently turn the N > 1 reference arm into a single-threaded run."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_run(cfg, pos):
     import oracle
 
@@ -193,7 +203,7 @@ def cpu_run(cfg, pos):
         cov, z1, z2 = cov[0], z1[0], z2[0]
     fn = oracle.summate_incompr if cfg["kind"] == "incompr" else oracle.summate
     t0 = time.perf_counter()
-    fn(cov, z1, z2, pos)
+    fn(cov, z1, z2, pos, num_threads=host_threads())
     return time.perf_counter() - t0
 
 
@@ -207,7 +217,7 @@ def cpu_baseline(cfg, target_seconds=12.0):
     rate = probe * n_modes / max(t, 1e-9)
     m = int(min(max(probe, rate * target_seconds / n_modes), 4_000_000))
     t = cpu_run(cfg, cpu_sample_points(cfg, m))
-    return {"value": m * n_modes / t, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
+    return {"value": m * n_modes / t, "unit": UNIT, "cores": host_threads(), "kind": "port",
             "sample": f"{m} contiguous points of the workload x {n_modes} modes "
                       f"({m * n_modes:.3g} pairs, {t:.1f} s, C/OpenMP oracle, glibc libm)"}
 
@@ -237,7 +247,7 @@ def run_reference_arm(args, cfg):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(cfg, args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -468,7 +478,7 @@ def krige_cpu(w, n_pts, offset=0):
     idx = (np.arange(n_pts) + offset) % w["n"]
     pos = bc.grid_points(w["axes"], None, idx)
     t0 = time.perf_counter()
-    oracle.krige_evaluate(w["spec"], w["mat"], w["cond"], w["cond_pos"], pos)
+    oracle.krige_evaluate(w["spec"], w["mat"], w["cond"], w["cond_pos"], pos, num_threads=host_threads())
     return time.perf_counter() - t0
 
 
@@ -499,7 +509,7 @@ def run_krige_reference_arm(args, w):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": krige_config(w, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": oracle.max_threads(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": host_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
@@ -623,7 +633,7 @@ def run_krige_arm(args, w):
             tp = krige_cpu(w, 256)
             m = int(max(256, min(16384, 256 * 10.0 / max(tp, 1e-9))))
             tc = krige_cpu(w, m, offset=m)
-            line["cpu_baseline"] = {"value": m / tc, "unit": "points/s", "cores": oracle.max_threads(), "kind": "port",
+            line["cpu_baseline"] = {"value": m / tc, "unit": "points/s", "cores": host_threads(), "kind": "port",
                                     "sample": f"{m} contiguous mesh nodes ({tc:.1f} s): numpy right-hand sides + "
                                               f"C/OpenMP port of the native loop nest"}
         print(json.dumps(line), flush=True)

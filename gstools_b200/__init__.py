@@ -22,7 +22,9 @@ from .backend import (
     krige_evaluate,
     sample_radii_mcmc,
     get_device,
+    cond_scaling,
     make_epilogue,
+    make_point_epilogue,
     scale_shift_,
     set_device,
     summate,
@@ -50,6 +52,8 @@ __all__ = [
     "sample_radii_mcmc",
     "scale_shift_",
     "make_epilogue",
+    "make_point_epilogue",
+    "cond_scaling",
     "enable",
     "disable",
     "is_enabled",

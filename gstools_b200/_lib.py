@@ -33,6 +33,16 @@ class Epilogue(ctypes.Structure):
 
 _epi_p = ctypes.POINTER(Epilogue)
 
+
+class PointEpilogue(ctypes.Structure):
+    """``gsb_point_epilogue`` of include/gsb200.h: v = gain[i]*v; v = offset[i] + v; then + add[0], ..."""
+
+    _fields_ = [("gain", ctypes.c_void_p), ("offset", ctypes.c_void_p), ("n_add", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("add", ctypes.c_double * EPI_MAX_ADD)]
+
+
+_pepi_p = ctypes.POINTER(PointEpilogue)
+
 COV_TYPES = {"Gaussian": 1, "Exponential": 2, "Stable": 3, "Rational": 4, "Cubic": 5, "Linear": 6,
              "Circular": 7, "Spherical": 8}
 
@@ -69,6 +79,11 @@ SIGNATURES = {
                                          _epi_p, _int, _int, _vp]),
     "gsb_summate_incompr_structured_ex": (_int, [_vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64,
                                                  _i64, _vp, _epi_p, _int, _int, _vp]),
+    "gsb_summate_pp": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _epi_p, _pepi_p, _int, _int,
+                              _vp]),
+    "gsb_summate_structured_pp": (_int, [_vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64, _i64, _vp,
+                                         _epi_p, _pepi_p, _int, _int, _vp]),
+    "gsb_cond_scaling": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _vp, _vp, _int, _vp]),
     "gsb_summate_fourier": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _int, _int,
                                    _vp]),
     "gsb_summate_fourier_structured": (_int, [_vp, _vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64,

@@ -40,6 +40,10 @@ __all__ = [
     "sample_radii_mcmc",
     "scale_shift_",
     "make_epilogue",
+    "make_point_epilogue",
+    "cond_scaling",
+    "to_device",
+    "to_host",
     "set_device",
     "get_device",
 ]
@@ -61,7 +65,14 @@ def get_device() -> int:
     if env is not None:
         return int(env)
     if "LOCAL_RANK" in os.environ:  # one process per GPU under torchrun
-        return int(os.environ["LOCAL_RANK"])
+        # launchers that narrow CUDA_VISIBLE_DEVICES per rank (SLURM, one visible GPU per process)
+        # leave fewer visible devices than local ranks: wrap instead of failing with "invalid device"
+        rank = int(os.environ["LOCAL_RANK"])
+        try:
+            count = _lib.device_count()
+        except Exception:
+            count = 0
+        return rank % count if count > 0 else rank
     return 0
 
 
@@ -119,6 +130,24 @@ def _empty_host(shape):
     return np.empty(shape, dtype=np.float64)
 
 
+def to_device(a, device=None):
+    """Contiguous float64 CUDA tensor holding a copy of the host array ``a`` (None passes through)."""
+    if a is None:
+        return None
+    torch = _torch()
+    dev = torch.device("cuda", get_device() if device is None else int(device))
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=dev)
+
+
+def to_host(t):
+    """Fresh host array (pinned when large, so the copy runs at PCIe speed) with the contents of CUDA tensor ``t``."""
+    torch = _torch()
+    out = _empty_host(tuple(t.shape))
+    if out.size:
+        torch.from_numpy(out).copy_(t)
+    return out
+
+
 def _as_f64(a, name):
     try:
         arr = np.asarray(a, dtype=np.float64)
@@ -174,6 +203,70 @@ def make_epilogue(scale, adds=()):
     return epi
 
 
+class _PointEpi:
+    """A ``gsb_point_epilogue`` together with the CUDA tensors it points into (kept alive with it)."""
+
+    def __init__(self, gain, offset, adds):
+        adds = [float(a) for a in adds]
+        if len(adds) > _lib.EPI_MAX_ADD:
+            raise ValueError(f"at most {_lib.EPI_MAX_ADD} additive terms can be fused")
+        torch = _torch()
+        self.tensors = []
+        self.n = None
+        self.device = None
+        ptrs = []
+        for name, t in (("gain", gain), ("offset", offset)):
+            if t is None:
+                ptrs.append(None)
+                continue
+            if not _is_cuda_tensor(t) or t.dtype != torch.float64 or not t.is_contiguous():
+                raise TypeError(f"point epilogue: {name} must be a contiguous float64 CUDA tensor "
+                                "(the device-resident result of a kriging evaluation)")
+            if self.n is not None and t.numel() != self.n:
+                raise ValueError("point epilogue: gain and offset must have the same number of points")
+            if self.device is not None and t.device != self.device:
+                raise ValueError("point epilogue: gain and offset must live on the same device")
+            self.n, self.device = t.numel(), t.device
+            self.tensors.append(t)
+            ptrs.append(t.data_ptr())
+        self.struct = _lib.PointEpilogue()
+        self.struct.gain, self.struct.offset = ptrs
+        self.struct.n_add = len(adds)
+        for k, a in enumerate(adds):
+            self.struct.add[k] = a
+
+    def ref(self, n, device_index):
+        if self.n is not None and self.n != n:
+            raise ValueError(f"point epilogue: arrays hold {self.n} points, the field has {n}")
+        if self.device is not None and self.device.index != device_index:
+            raise ValueError("point epilogue: arrays live on another device than the call runs on")
+        return ctypes.byref(self.struct)
+
+
+def make_point_epilogue(gain=None, offset=None, adds=()):
+    """Per-point step of a conditioned field (``gsb_point_epilogue``): after the terms of
+    :func:`make_epilogue`, ``v = gain[i]*v; v = offset[i] + v; v += adds[0]; ...`` -- CondSRF's
+    ``rawkrige + var_scale * rawfield + nugget`` (cond_srf.py:145-150) plus constant mean / trend, with
+    separately rounded operations in that order.  ``gain`` / ``offset`` are contiguous float64 CUDA
+    tensors with one entry per point of the field (device-resident kriging results), or None."""
+    return _PointEpi(gain, offset, adds)
+
+
+def cond_scaling(error, sill, var):
+    """``(krige_var, gain)`` on the device from the kriging error sums (CUDA tensor in, CUDA tensors out):
+    ``krige_var = max(sill - error, 0)`` (krige/base.py:296-298), ``gain = sqrt(krige_var / var)``
+    (CondSRF.get_scaling without nugget, cond_srf.py:175-177), numpy's bits."""
+    torch = _torch()
+    if not _is_cuda_tensor(error) or error.dtype != torch.float64 or not error.is_contiguous():
+        raise TypeError("cond_scaling works on contiguous float64 CUDA tensors")
+    krige_var, gain = torch.empty_like(error), torch.empty_like(error)
+    stream = torch.cuda.current_stream(error.device).cuda_stream
+    rc = _lib.load().gsb_cond_scaling(error.data_ptr(), error.numel(), float(sill), float(var),
+                                      krige_var.data_ptr(), gain.data_ptr(), error.device.index, stream)
+    _lib.check(rc, "cond_scaling")
+    return krige_var, gain
+
+
 def _epi_ref(epilogue):
     if epilogue is None:
         return None
@@ -185,13 +278,15 @@ def _epi_ref(epilogue):
 # ----------------------------------------------------------------------------------------
 # flat (unstructured) entry points -- the reference signatures
 # ----------------------------------------------------------------------------------------
-def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None):
+def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None, point_epilogue=None):
     lib = _lib.load()
     epi = _epi_ref(epilogue)
     if sf is not None and epi is not None:
         raise ValueError("summate_fourier has no fused epilogue")
+    if point_epilogue is not None and (vec or sf is not None):
+        raise ValueError("the per-point epilogue applies to scalar fields only")
     if any(_is_cuda_tensor(x) for x in (cov_samples, z_1, z_2, pos)):
-        return _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf, epi)
+        return _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf, epi, point_epilogue)
     cov = np.ascontiguousarray(_as_f64(cov_samples, "cov_samples"))
     z1 = np.ascontiguousarray(_as_f64(z_1, "z_1"))
     z2 = np.ascontiguousarray(_as_f64(z_2, "z_2"))
@@ -215,6 +310,12 @@ def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None):
         rc = lib.gsb_summate_fourier(_ptr(f), _ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim,
                                      n_modes, n, _ptr(out), _lib.MEM_HOST, get_device(), None)
         _lib.check(rc, "summate_fourier")
+    elif point_epilogue is not None:
+        device = point_epilogue.device.index if point_epilogue.device is not None else get_device()
+        out = _empty_host((n,))
+        rc = lib.gsb_summate_pp(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n, _ptr(out), epi,
+                                point_epilogue.ref(n, device), _lib.MEM_HOST, device, None)
+        _lib.check(rc, "summate")
     else:
         out = _empty_host((n,))
         rc = lib.gsb_summate_ex(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n,
@@ -223,7 +324,7 @@ def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None):
     return out
 
 
-def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None, epi=None):
+def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None, epi=None, pepi=None):
     torch = _torch()
     dev = next(x.device for x in (pos, cov_samples, z_1, z_2) if _is_cuda_tensor(x))
 
@@ -261,6 +362,11 @@ def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None, epi=None):
                                      p.data_ptr(), ld, dim, n_modes, n, out.data_ptr(),
                                      _lib.MEM_DEVICE, dev.index, stream)
         _lib.check(rc, "summate_fourier")
+    elif pepi is not None:
+        out = torch.empty((n,), dtype=torch.float64, device=dev)
+        rc = lib.gsb_summate_pp(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), ld, dim, n_modes, n,
+                                out.data_ptr(), epi, pepi.ref(n, dev.index), _lib.MEM_DEVICE, dev.index, stream)
+        _lib.check(rc, "summate")
     else:
         out = torch.empty((n,), dtype=torch.float64, device=dev)
         rc = lib.gsb_summate_ex(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), ld,
@@ -270,12 +376,13 @@ def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None, epi=None):
     return out
 
 
-def summate(cov_samples, z_1, z_2, pos, num_threads=None, *, epilogue=None):
+def summate(cov_samples, z_1, z_2, pos, num_threads=None, *, epilogue=None, point_epilogue=None):
     """B200 replacement of the native ``summate`` (generator.py:42-48, math :193-199).
 
-    ``epilogue`` (keyword only, not in the reference): see :func:`make_epilogue`.
+    ``epilogue`` / ``point_epilogue`` (keyword only, not in the reference): see :func:`make_epilogue`
+    and :func:`make_point_epilogue`.
     """
-    return _flat(cov_samples, z_1, z_2, pos, vec=False, epilogue=epilogue)
+    return _flat(cov_samples, z_1, z_2, pos, vec=False, epilogue=epilogue, point_epilogue=point_epilogue)
 
 
 def summate_incompr(cov_samples, z_1, z_2, pos, num_threads=None, *, epilogue=None):
@@ -319,13 +426,15 @@ def summate_fourier_structured(spectrum_factor, modes, z_1, z_2, axes, matrix=No
 # ----------------------------------------------------------------------------------------
 # structured (rectilinear mesh) entry points -- the side channel for mesh_type="structured"
 # ----------------------------------------------------------------------------------------
-def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None):
+def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None, point_epilogue=None):
     lib = _lib.load()
     epi = _epi_ref(epilogue)
     axes = list(axes)
     dim = len(axes)
+    if point_epilogue is not None and vec:
+        raise ValueError("the per-point epilogue applies to scalar fields only")
     if any(_is_cuda_tensor(x) for x in (cov_samples, z_1, z_2, *axes)):
-        return _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi)
+        return _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi, point_epilogue)
     cov = np.ascontiguousarray(_as_f64(cov_samples, "cov_samples"))
     z1 = np.ascontiguousarray(_as_f64(z_1, "z_1"))
     z2 = np.ascontiguousarray(_as_f64(z_2, "z_2"))
@@ -352,6 +461,14 @@ def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None):
     n_batch, _, n_modes = cov3.shape
     full = ((n_batch,) if batched else ()) + ((dim,) if vec else ()) + shape
     out = _empty_host(full)
+    if point_epilogue is not None:
+        device = point_epilogue.device.index if point_epilogue.device is not None else get_device()
+        rc = lib.gsb_summate_structured_pp(_ptr(cov3), _ptr(z1b), _ptr(z2b), _ptr(cat),
+                                           lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch,
+                                           _ptr(out), epi, point_epilogue.ref(int(np.prod(lens)), device),
+                                           _lib.MEM_HOST, device, None)
+        _lib.check(rc, "summate_structured")
+        return out
     fn = lib.gsb_summate_incompr_structured_ex if vec else lib.gsb_summate_structured_ex
     rc = fn(_ptr(cov3), _ptr(z1b), _ptr(z2b), _ptr(cat),
             lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch, _ptr(out), epi,
@@ -360,7 +477,7 @@ def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None):
     return out
 
 
-def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi=None):
+def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi=None, pepi=None):
     torch = _torch()
     dev = next(x.device for x in (cov_samples, z_1, z_2, *axes) if _is_cuda_tensor(x))
 
@@ -391,6 +508,13 @@ def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi=None):
     full = ((n_batch,) if batched else ()) + ((dim,) if vec else ()) + shape
     out = torch.empty(full, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
+    if pepi is not None:
+        rc = lib.gsb_summate_structured_pp(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), cat.data_ptr(),
+                                           lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch,
+                                           out.data_ptr(), epi, pepi.ref(int(np.prod(lens)), dev.index),
+                                           _lib.MEM_DEVICE, dev.index, stream)
+        _lib.check(rc, "summate_structured")
+        return out
     fn = lib.gsb_summate_incompr_structured_ex if vec else lib.gsb_summate_structured_ex
     rc = fn(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), cat.data_ptr(),
             lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch, out.data_ptr(),
@@ -399,14 +523,15 @@ def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi=None):
     return out
 
 
-def summate_structured(cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=None):
+def summate_structured(cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=None, point_epilogue=None):
     """``summate`` on the mesh spanned by ``axes`` without the flat position array.
 
     Equals ``summate(cov_samples, z_1, z_2, matrix @ generate_grid(axes)).reshape(shape)``
     (reference: field/base.py:289-297, tools/geometric.py:340-356, covmodel/base.py:572-582).
     ``cov_samples`` may carry a leading batch axis (ensembles of mode sets on one mesh).
     """
-    return _structured(cov_samples, z_1, z_2, axes, matrix, vec=False, epilogue=epilogue)
+    return _structured(cov_samples, z_1, z_2, axes, matrix, vec=False, epilogue=epilogue,
+                       point_epilogue=point_epilogue)
 
 
 def summate_incompr_structured(cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=None):

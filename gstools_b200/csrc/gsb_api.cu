@@ -167,6 +167,15 @@ static int check_epilogue(const gsb_epilogue *e)
     return GSB_OK;
 }
 
+static int check_point_epilogue(const gsb_point_epilogue *e, bool vec)
+{
+    if (!e) return GSB_OK;
+    if (vec) return fail(GSB_ERR_ARGUMENT, "point epilogue: scalar fields only (cond_srf.py:56)");
+    if (e->n_add < 0 || e->n_add > GSB_EPI_MAX_ADD)
+        return fail(GSB_ERR_ARGUMENT, "point epilogue: n_add must be in 0..GSB_EPI_MAX_ADD");
+    return GSB_OK;
+}
+
 static int check_common(const void *cov, const void *z1, const void *z2, int dim, int64_t n_modes)
 {
     if (dim < 1 || dim > GSB_MAX_DIM) return fail(GSB_ERR_ARGUMENT, "dim must be in 1..8");
@@ -261,12 +270,13 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
 static int summate_impl(const double *cov, const double *z1, const double *z2, const double *sf,
                         const double *pos, int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts,
                         double *out, int64_t out_ld, bool vec, const gsb_epilogue *epilogue, int mem,
-                        int device, void *stream)
+                        int device, void *stream, const gsb_point_epilogue *pepi = nullptr)
 {
     DeviceGuard guard;
     GSB_TRY(check_common(cov, z1, z2, dim, n_modes));
     GSB_TRY(check_epilogue(epilogue));
-    const Epi epi = make_epi(epilogue);
+    GSB_TRY(check_point_epilogue(pepi, vec));
+    const Epi epi = make_epi(epilogue, pepi);
     if (n_pts < 0) return fail(GSB_ERR_ARGUMENT, "n_pts must be >= 0");
     if (vec && dim != 2 && dim != 3)
         return fail(GSB_ERR_ARGUMENT,
@@ -331,7 +341,8 @@ static int summate_impl(const double *cov, const double *z1, const double *z2, c
         const int64_t m = std::min(chunk, n_pts - i0);
         GSB_CUDA(cudaMemcpy2DAsync(d_pos[b], sizeof(double) * chunk, pos + i0, sizeof(double) * pos_ld,
                                    sizeof(double) * m, dim, cudaMemcpyHostToDevice, st));
-        GSB_TRY(direct_on_device(d_recs, pad, d_pos[b], chunk, dim, vec, m, d_out[b], chunk, epi, *dev, s, st));
+        GSB_TRY(direct_on_device(d_recs, pad, d_pos[b], chunk, dim, vec, m, d_out[b], chunk, epi_shift(epi, i0), *dev,
+                                 s, st));
         GSB_CUDA(cudaMemcpy2DAsync(out + i0, sizeof(double) * (vec ? out_ld : n_pts), d_out[b],
                                    sizeof(double) * chunk, sizeof(double) * m, ncomp,
                                    cudaMemcpyDeviceToHost, st));
@@ -740,12 +751,14 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
 static int structured_impl(const double *cov, const double *z1, const double *z2, const double *sf,
                            const double *axes, const int64_t *axis_len, const double *matrix, int dim,
                            int64_t n_modes, int64_t n_batch, double *out, bool vec,
-                           const gsb_epilogue *epilogue, int mem, int device, void *stream)
+                           const gsb_epilogue *epilogue, int mem, int device, void *stream,
+                           const gsb_point_epilogue *pepi = nullptr)
 {
     DeviceGuard guard;
     GSB_TRY(check_common(cov, z1, z2, dim, n_modes));
     GSB_TRY(check_epilogue(epilogue));
-    const Epi epi = make_epi(epilogue);
+    GSB_TRY(check_point_epilogue(pepi, vec));
+    const Epi epi = make_epi(epilogue, pepi);
     if (!axis_len) return fail(GSB_ERR_ARGUMENT, "axis_len must not be NULL");
     if (n_batch < 1) return fail(GSB_ERR_ARGUMENT, "n_batch must be >= 1");
     if (vec && dim != 2 && dim != 3)
@@ -1031,10 +1044,7 @@ static void launch_kvgen(const KvgenParams &gp, int n_dstages, int64_t n_ct, cud
 template <int D>
 static int launch_field_gen(const KvgenParams &gp, cudaStream_t st)
 {
-    const size_t smem = ((size_t)gp.C * D + gp.K) * sizeof(double);
-    if (smem > 200 * 1024) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: system too large for the field-only kernel");
-    GSB_CUDA(cudaFuncSetAttribute(krige_field_gen_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    krige_field_gen_kernel<D><<<(unsigned)((gp.n + 255) / 256), 256, smem, st>>>(gp);
+    krige_field_gen_kernel<D><<<(unsigned)((gp.n + 255) / 256), 256, 0, st>>>(gp);
     return GSB_OK;
 }
 
@@ -1238,6 +1248,20 @@ __global__ void scale_shift_kernel(double *f, int64_t n, double scale, double sh
         f[i] = fma(scale, f[i], shift);
 }
 
+// CondSRF.get_scaling without nugget (cond_srf.py:175-177) after the clamp of krige/base.py:296-298.
+// numpy's maximum(x, 0) keeps x when x >= 0 or x is NaN; IEEE sub / div / sqrt give numpy's bits.
+__global__ void cond_scaling_kernel(const double *__restrict__ error, int64_t n, double sill, double var,
+                                    double *krige_var, double *__restrict__ gain)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double d = __dsub_rn(sill, error[i]);
+        const double kv = (d >= 0.0 || d != d) ? d : 0.0;
+        if (krige_var) krige_var[i] = kv;
+        gain[i] = __dsqrt_rn(__ddiv_rn(kv, var));
+    }
+}
+
 // 8 independent DFMA chains per thread, register resident
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double *sink, int iters, double seed)
 {
@@ -1372,6 +1396,39 @@ int gsb_summate_incompr_structured(const double *cov_samples, const double *z_1,
 {
     return structured_impl(cov_samples, z_1, z_2, nullptr, axes, axis_len, matrix, dim, n_modes, n_batch,
                            out, true, nullptr, mem, device, stream);
+}
+
+int gsb_summate_pp(const double *cov_samples, const double *z_1, const double *z_2, const double *pos,
+                   int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts, double *out, const gsb_epilogue *epi,
+                   const gsb_point_epilogue *pepi, int mem, int device, void *stream)
+{
+    return summate_impl(cov_samples, z_1, z_2, nullptr, pos, pos_ld, dim, n_modes, n_pts, out, n_pts, false, epi, mem,
+                        device, stream, pepi);
+}
+
+int gsb_summate_structured_pp(const double *cov_samples, const double *z_1, const double *z_2, const double *axes,
+                              const int64_t *axis_len, const double *matrix, int dim, int64_t n_modes,
+                              int64_t n_batch, double *out, const gsb_epilogue *epi,
+                              const gsb_point_epilogue *pepi, int mem, int device, void *stream)
+{
+    return structured_impl(cov_samples, z_1, z_2, nullptr, axes, axis_len, matrix, dim, n_modes, n_batch, out, false,
+                           epi, mem, device, stream, pepi);
+}
+
+int gsb_cond_scaling(const double *error, int64_t n, double sill, double var, double *krige_var, double *gain,
+                     int device, void *stream)
+{
+    if (n < 0) return fail(GSB_ERR_ARGUMENT, "n must be >= 0");
+    if (n == 0) return GSB_OK;
+    if (!error || !gain) return fail(GSB_ERR_ARGUMENT, "error and gain must not be NULL");
+    DeviceGuard guard;
+    DeviceState *dev = nullptr;
+    GSB_TRY(ensure_device(device, &dev));
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 16LL * dev->sm_count);
+    cond_scaling_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(error, n, sill, var, krige_var, gain);
+    g_launches.fetch_add(1);
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
 }
 
 int gsb_summate_fourier(const double *spectrum_factor, const double *modes, const double *z_1,

@@ -135,26 +135,56 @@ struct Epi {
     double add[GSB_EPI_MAX_ADD][GSB_EPI_MAX_COMP];
     int n_add;
     int on;        // 0: store the raw sum
+    // per-point step (gsb_point_epilogue; CondSRF.__call__, cond_srf.py:145-150), applied after the terms above:
+    //   v = gain[i]*v;  v = offset[i] + v;  v = v + post[0]; ...     i = index of the point in its field
+    const double *gain;
+    const double *offset;
+    double post[GSB_EPI_MAX_ADD];
+    int n_post;
+    int pp;        // 0: no per-point step
 };
 
-__device__ __forceinline__ double epi_apply(const Epi &e, double v, int comp)
+__device__ __forceinline__ double epi_apply(const Epi &e, double v, int comp, int64_t idx)
 {
     if (!e.on) return v;
     v = __dmul_rn(e.scale, v);
     for (int k = 0; k < e.n_add; ++k) v = __dadd_rn(v, e.add[k][comp]);
+    if (e.pp) {
+        if (e.gain) v = __dmul_rn(__ldg(e.gain + idx), v);
+        if (e.offset) v = __dadd_rn(__ldg(e.offset + idx), v);
+        for (int k = 0; k < e.n_post; ++k) v = __dadd_rn(v, e.post[k]);
+    }
     return v;
 }
 
-inline Epi make_epi(const gsb_epilogue *src)
+inline Epi make_epi(const gsb_epilogue *src, const gsb_point_epilogue *pp = nullptr)
 {
     Epi e;
     std::memset(&e, 0, sizeof e);
-    if (!src) return e;
+    if (!src && !pp) return e;
     e.on = 1;
-    e.scale = src->scale;
-    e.n_add = src->n_add;
-    for (int k = 0; k < GSB_EPI_MAX_ADD; ++k)
-        for (int c = 0; c < GSB_EPI_MAX_COMP; ++c) e.add[k][c] = src->add[k][c];
+    e.scale = 1.0;
+    if (src) {
+        e.scale = src->scale;
+        e.n_add = src->n_add;
+        for (int k = 0; k < GSB_EPI_MAX_ADD; ++k)
+            for (int c = 0; c < GSB_EPI_MAX_COMP; ++c) e.add[k][c] = src->add[k][c];
+    }
+    if (pp) {
+        e.pp = 1;
+        e.gain = pp->gain;
+        e.offset = pp->offset;
+        e.n_post = pp->n_add;
+        for (int k = 0; k < GSB_EPI_MAX_ADD; ++k) e.post[k] = pp->add[k];
+    }
+    return e;
+}
+
+// the same epilogue for the points [first, ...) of the field (host route: point chunks)
+inline Epi epi_shift(Epi e, int64_t first)
+{
+    if (e.gain) e.gain += first;
+    if (e.offset) e.offset += first;
     return e;
 }
 

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
         if (i < prm.n_pts) {
             if (prm.n_split == 1) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) prm.out[c * prm.out_ld + i] = epi_apply(prm.epi, acc[p][c], c);
+                for (int c = 0; c < NC; ++c) prm.out[c * prm.out_ld + i] = epi_apply(prm.epi, acc[p][c], c, i);
             } else {
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
@@ -241,7 +241,7 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, int n
     if (i >= n_pts) return;
     double s = 0.0;
     for (int k = 0; k < n_split; ++k) s += partial[((int64_t)k * ncomp + c) * n_pts + i];
-    out[c * out_ld + i] = epi_apply(epi, s, c);
+    out[c * out_ld + i] = epi_apply(epi, s, c, i);
 }
 
 // ---------------------------------------------------------------------------------------------

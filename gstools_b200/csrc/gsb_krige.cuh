@@ -639,30 +639,40 @@ __global__ void __launch_bounds__(256) kvgen_kernel(const KvgenParams prm)
     }
 }
 
-// field only (return_var = False): field[k] = sum_row w[row] kv[row, k] with kv generated on the fly
+// field only (return_var = False): field[k] = sum_row w[row] kv[row, k] with kv generated on the fly.
+// The conditioning positions and w are staged through shared memory in passes of FIELD_GEN_ROWS rows
+// (an even number, so the even / odd partial sums see the same rows whatever the system size): no limit
+// on the size of the kriging system.
+constexpr int FIELD_GEN_ROWS = 1024;
+
 template <int D>
 __global__ void __launch_bounds__(256) krige_field_gen_kernel(const KvgenParams prm)
 {
-    extern __shared__ double sm[];     // [C][D] conditioning positions, then w[K]
-    double *cps = sm, *ws = sm + (size_t)prm.C * D;
-    for (int e = threadIdx.x; e < prm.C * D; e += blockDim.x) {
-        const int row = e / D, t = e % D;
-        cps[e] = prm.cond_pos[(int64_t)t * prm.C + row];
-    }
-    for (int e = threadIdx.x; e < prm.K; e += blockDim.x) ws[e] = prm.w[e];
-    __syncthreads();
+    __shared__ double cps[FIELD_GEN_ROWS * D];   // [row][D] conditioning positions of this pass
+    __shared__ double ws[FIELD_GEN_ROWS];
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= prm.n) return;
+    const bool live = k < prm.n;
     double x[D];
-    kvgen_point<D>(prm, prm.col_begin + k, x);
+    if (live) kvgen_point<D>(prm, prm.col_begin + k, x);
     double s0 = 0.0, s1 = 0.0;
-    int row = 0;
-    for (; row + 2 <= prm.K; row += 2) {
-        s0 = fma(ws[row], kvgen_entry<D>(prm, row, prm.col_begin + k, x, cps + (size_t)row * D), s0);
-        s1 = fma(ws[row + 1], kvgen_entry<D>(prm, row + 1, prm.col_begin + k, x, cps + (size_t)(row + 1) * D), s1);
+    for (int r0 = 0; r0 < prm.K; r0 += FIELD_GEN_ROWS) {
+        const int cnt = min(FIELD_GEN_ROWS, prm.K - r0);
+        __syncthreads();   // the previous pass has been consumed
+        for (int e = threadIdx.x; e < cnt * D; e += blockDim.x) {
+            const int rr = e / D, t = e % D, row = r0 + rr;
+            cps[e] = row < prm.C ? prm.cond_pos[(int64_t)t * prm.C + row] : 0.0;
+        }
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) ws[e] = prm.w[r0 + e];
+        __syncthreads();
+        if (!live) continue;
+        int rr = 0;
+        for (; rr + 2 <= cnt; rr += 2) {
+            s0 = fma(ws[rr], kvgen_entry<D>(prm, r0 + rr, prm.col_begin + k, x, cps + (size_t)rr * D), s0);
+            s1 = fma(ws[rr + 1], kvgen_entry<D>(prm, r0 + rr + 1, prm.col_begin + k, x, cps + (size_t)(rr + 1) * D), s1);
+        }
+        if (rr < cnt) s0 = fma(ws[rr], kvgen_entry<D>(prm, r0 + rr, prm.col_begin + k, x, cps + (size_t)rr * D), s0);
     }
-    if (row < prm.K) s0 = fma(ws[row], kvgen_entry<D>(prm, row, prm.col_begin + k, x, cps + (size_t)row * D), s0);
-    prm.field[k] = s0 + s1;
+    if (live) prm.field[k] = s0 + s1;
 }
 
 }  // namespace gsb

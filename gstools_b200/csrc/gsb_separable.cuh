@@ -522,15 +522,6 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
         const int64_t fl = z / prm.ncomp;
         double *out = prm.out + ((prm.batch0 + fl) * prm.ncomp + comp) * prm.out_fstride;
         const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-        if (prm.epi.on) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    acc[i][j][0] = epi_apply(prm.epi, acc[i][j][0], comp);
-                    acc[i][j][1] = epi_apply(prm.epi, acc[i][j][1], comp);
-                }
-        }
         const int64_t col0 = (int64_t)ct * SEP_TN;
         int64_t row0, row_end;                      // first row of the tile, end of its valid rows
         if (SCALED) {
@@ -550,6 +541,12 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) contract_kernel(const Contract
             for (int j = 0; j < 8; ++j) {
                 const int64_t col = col0 + wc * 64 + j * 8 + 2 * t;
                 double *dst = out + row * prm.lc + col;
+                if (prm.epi.on) {
+                    // (the per-point arrays are only read for columns inside the mesh)
+                    const int64_t idx = row * prm.lc + col;
+                    if (col < prm.lc) acc[i][j][0] = epi_apply(prm.epi, acc[i][j][0], comp, idx);
+                    if (col + 1 < prm.lc) acc[i][j][1] = epi_apply(prm.epi, acc[i][j][1], comp, idx + 1);
+                }
                 if (vec2 && col + 1 < prm.lc) {
                     *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
                 } else {

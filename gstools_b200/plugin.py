@@ -125,6 +125,7 @@ class _Refs:
         from gstools import config
         from gstools.covmodel import models as cmodels
         from gstools.field import base as fbase
+        from gstools.field import cond_srf as fcond
         from gstools.field import generator as gen
         from gstools.field import srf as fsrf
         from gstools.krige import base as kbase
@@ -135,14 +136,18 @@ class _Refs:
         self.gstools, self.config, self.cmodels = gstools, config, cmodels
         self.fbase, self.gen, self.fsrf, self.kbase, self.grng = fbase, gen, fsrf, kbase, grng
         self.Normalizer, self.matrix_isometrize = Normalizer, matrix_isometrize
+        self.cond_cls = fcond.CondSRF
         # (owner, attribute) -> original; everything enable() may rebind, restored by disable()
         self.orig = {(o, a): getattr(o, a) for o, a in (
             (gen, "_summate"), (gen, "_summate_incompr"), (gen, "_summate_fourier"),
             (kbase, "_calc_field_krige"), (kbase, "_calc_field_krige_and_variance"),
             (fbase.Field, "pre_pos"), (fsrf.SRF, "__call__"), (kbase.Krige, "__call__"),
             (fbase, "apply_mean_norm_trend"), (grng.RNG, "sample_ln_pdf"),
-            (gen.RandMeth, "__call__"), (gen.IncomprRandMeth, "__call__"))}
+            (gen.RandMeth, "__call__"), (gen.IncomprRandMeth, "__call__"), (fcond.CondSRF, "__call__"))}
         self.cache_krige = True
+        self.cache_krige_mb = 2048
+        self.fused_cond = True
+        self.krige_eval = _KrigeEval(self)
 
     def on(self):
         return getattr(self.config, "USE_GSTOOLS_B200", False)
@@ -345,26 +350,135 @@ def _build_generator_calls(r):
 
 
 # ---- Krige.__call__ with the right-hand sides generated on the device (row f1) ----------------------
-def _build_krige_call(r):
-    kbase, cmodels = r.kbase, r.cmodels
-    orig_krige_call = r.orig[(kbase.Krige, "__call__")]
-    orig_pre_pos = r.orig[(r.fbase.Field, "pre_pos")]
-    device_models = {getattr(cmodels, name): name for name in _lib.COV_TYPES if hasattr(cmodels, name)}
+def _key_same(a, b):
+    """Content equality for the key entries that may alias user memory (stored as private copies)."""
+    if a is None or b is None:
+        return a is b
+    if isinstance(a, tuple):
+        return isinstance(b, tuple) and len(a) == len(b) and all(_key_same(x, y) for x, y in zip(a, b))
+    return a.shape == b.shape and np.array_equal(a, b)
 
-    def _cov_spec(krige):
+
+def _key_copy(a):
+    if a is None:
+        return None
+    if isinstance(a, (tuple, list)):
+        return tuple(_key_copy(x) for x in a)
+    return np.array(a, dtype=np.double, copy=True)
+
+
+class _KrigeEval:
+    """One kriging evaluation per (system, mesh): shared by the wrapped ``Krige.__call__`` and ``CondSRF.__call__``.
+
+    The evaluation is a pure function of the kriging system, the model and the positions.  The reference's
+    ensemble idiom (examples/06_conditioned_fields/01_2D_condition_ensemble.py:32-35) re-evaluates the
+    same system for every realisation; the last result is remembered on the Krige object.  Key entries the
+    Krige object builds itself (``_krige_mat`` / ``_krige_cond`` / ``_krige_pos``: fresh arrays from every
+    ``set_condition``) are compared by identity; entries that can alias user memory (mesh axes -- views of the
+    caller's arrays, field/base.py:577 --, positions, drift rows) are stored as private COPIES and compared by
+    content, so mutating an axis in place between two calls is seen.
+    """
+
+    def __init__(self, r):
+        self.r = r
+        cmodels = r.cmodels
+        self.device_models = {getattr(cmodels, n): n for n in _lib.COV_TYPES if hasattr(cmodels, n)}
+        self.orig_pre_pos = r.orig[(r.fbase.Field, "pre_pos")]
+
+    def cov_spec(self, krige):
         """gsb_cov_model of ``krige.model`` (exact class only: a subclass may override cor)."""
         model = krige.model
-        kind = device_models.get(type(model))
+        kind = self.device_models.get(type(model))
         if kind is None or model.latlon or getattr(model, "temporal", False) or model.dim > 4:
             return None
         param = float(getattr(model, "alpha", 0.0)) if kind in ("Stable", "Rational") else 0.0
         return backend.cov_model_spec(kind, model.var, model.len_rescaled, model.sill, param, krige.exact)
 
+    def evaluate(self, krige, spec, ext_drift, return_var, want_device=False):
+        """Cache entry ``{"out": (field, error|None), "shape", ...}`` for ``krige`` on its current positions
+        (``krige.pos`` must be set).  ``want_device`` also keeps ``field`` / ``krige_var`` / ``gain``
+        (cond_srf.py:175-177) as CUDA tensors under ``entry["dev"]``."""
+        r = self.r
+        lazy = krige.mesh_type != "unstructured" and krige.int_drift_no == 0
+        if lazy:
+            shape = krige.field_shape
+            pnt_cnt = int(np.prod(shape))
+            iso_pos = None
+        else:
+            iso_pos, shape = self.orig_pre_pos(krige, None, krige.mesh_type)
+            pnt_cnt = len(iso_pos[0])
+        ext_drift = krige._pre_ext_drift(pnt_cnt, ext_drift)               # base.py:279
+        tail = []
+        if krige.int_drift_no > 0:
+            chunk_pos = krige.model.anisometrize(iso_pos)
+            tail += [np.asarray(f(*chunk_pos), dtype=np.double).reshape(-1) for f in krige.drift_functions]
+        if krige.ext_drift_no > 0:
+            tail += list(np.asarray(ext_drift, dtype=np.double).reshape(krige.ext_drift_no, -1))
+        tail_rows = np.ascontiguousarray(tail) if tail else None
+        matrix = r.matrix_isometrize(krige.model.dim, krige.model.angles, krige.model.anis) if lazy else None
+        cond = krige._krige_cond          # a property: rebuilt from cond_val / normalizer / trend / mean per access
+        ident = (krige._krige_mat, krige._krige_pos)
+        flags = (bytes(spec), lazy, bool(krige.unbiased), tuple(shape))
+        where = tuple(krige.pos) if lazy else iso_pos
+        cached = getattr(krige, "_b200_krige_cache", None) if r.cache_krige else None
+        hit = (cached is not None and cached["flags"] == flags
+               and all(a is b for a, b in zip(cached["ident"], ident))
+               and _key_same(cached["matrix"], matrix) and _key_same(cached["where"], where)
+               and _key_same(cached["tail"], tail_rows) and _key_same(cached["cond"], cond)
+               and (cached["out"][1] is not None or not return_var))
+        if not hit:
+            kwargs = dict(unbiased=krige.unbiased, tail_rows=tail_rows, return_var=return_var)
+            pos_kw = dict(axes=krige.pos, matrix=matrix) if lazy else dict(pos=iso_pos)
+            dev = None
+            if want_device:
+                # device-resident evaluation: inputs uploaded once, results stay on the GPU and are
+                # copied to the host for the callers that want arrays
+                up = backend.to_device
+                pos_dev = dict(axes=[up(a) for a in krige.pos], matrix=matrix) if lazy else dict(pos=up(iso_pos))
+                res = backend.krige_evaluate(spec, up(krige._krige_mat), up(cond), up(krige._krige_pos),
+                                             unbiased=krige.unbiased, tail_rows=up(tail_rows), return_var=return_var,
+                                             **pos_dev)
+                res = res if return_var else (res,)
+                dev = {"field": res[0].reshape(-1), "error": res[1].reshape(-1) if return_var else None}
+                out = tuple(backend.to_host(t) for t in res)
+            else:
+                out = backend.krige_evaluate(spec, krige._krige_mat, cond, krige._krige_pos,
+                                             **pos_kw, **kwargs)
+                out = out if return_var else (out,)
+            out = tuple(np.reshape(o, -1) for o in out) + ((None,) if not return_var else ())
+            cached = dict(flags=flags, ident=ident, matrix=_key_copy(matrix), where=_key_copy(where),
+                          tail=_key_copy(tail_rows), cond=_key_copy(cond), out=out, shape=tuple(shape), dev=dev, sill=None)
+            limit = r.cache_krige_mb * (1 << 20)
+            if r.cache_krige and 8 * pnt_cnt * 3 <= limit:
+                krige._b200_krige_cache = cached
+            elif hasattr(krige, "_b200_krige_cache"):
+                del krige._b200_krige_cache
+        if return_var and (cached.get("krige_var") is None or cached["sill"] != krige.model.sill):
+            cached["krige_var"] = np.maximum(krige.model.sill - cached["out"][1], 0)      # base.py:296-298
+            cached["sill"] = krige.model.sill
+            if cached["dev"] is not None:
+                cached["dev"].pop("gain", None)
+        if want_device and return_var:
+            dev = cached["dev"]
+            if dev is None:
+                dev = cached["dev"] = {"field": backend.to_device(cached["out"][0]),
+                                       "error": backend.to_device(cached["out"][1])}
+            if "gain" not in dev or dev["var"] != krige.model.var:
+                dev["krige_var"], dev["gain"] = backend.cond_scaling(dev["error"], krige.model.sill, krige.model.var)
+                dev["var"] = krige.model.var
+        return cached
+
+
+def _build_krige_call(r):
+    kbase = r.kbase
+    orig_krige_call = r.orig[(kbase.Krige, "__call__")]
+    ke = r.krige_eval
+
     def krige_call(self, pos=None, mesh_type="unstructured", ext_drift=None, chunk_size=None,
                    only_mean=False, return_var=True, post_process=True, store=True):
         spec = None
         if r.on() and not only_mean and self.cond_no > 0:
-            spec = _cov_spec(self)
+            spec = ke.cov_spec(self)
         if spec is None:
             return orig_krige_call(self, pos, mesh_type, ext_drift, chunk_size, only_mean,
                                    return_var, post_process, store)
@@ -376,58 +490,96 @@ def _build_krige_call(r):
             self.set_pos(pos, mesh_type)
         elif self.pos is None:
             raise ValueError("Field: no position tuple 'pos' present")
-        lazy = self.mesh_type != "unstructured" and self.int_drift_no == 0
-        if lazy:
-            shape = self.field_shape
-            pnt_cnt = int(np.prod(shape))
-            iso_pos = None
-        else:
-            iso_pos, shape = orig_pre_pos(self, None, self.mesh_type)
-            pnt_cnt = len(iso_pos[0])
-        ext_drift = self._pre_ext_drift(pnt_cnt, ext_drift)               # base.py:279
-        tail = []
-        if self.int_drift_no > 0:
-            chunk_pos = self.model.anisometrize(iso_pos)
-            tail += [np.asarray(f(*chunk_pos), dtype=np.double).reshape(-1) for f in self.drift_functions]
-        if self.ext_drift_no > 0:
-            tail += list(np.asarray(ext_drift, dtype=np.double).reshape(self.ext_drift_no, -1))
-        tail_rows = np.ascontiguousarray(tail) if tail else None
-        kwargs = dict(unbiased=self.unbiased, tail_rows=tail_rows, return_var=return_var)
-        matrix = r.matrix_isometrize(self.model.dim, self.model.angles, self.model.anis) if lazy else None
-        # The evaluation is a pure function of these inputs.  The reference's ensemble idiom
-        # (examples/06_conditioned_fields/01_2D_condition_ensemble.py:32-35, store=[name, False, False])
-        # re-evaluates the same kriging system for every realisation; remember the last result
-        # and hand out copies (post_field below works in place).
-        cond = self._krige_cond
-        key = dict(spec=bytes(spec), flags=(lazy, bool(self.unbiased), bool(return_var)), matrix=matrix,
-                   mat=self._krige_mat, cond=cond, cpos=self._krige_pos,
-                   pos=self.pos if lazy else iso_pos, tail=tail_rows)
-        cached = getattr(self, "_b200_krige_cache", None) if r.cache_krige else None
-        if cached is not None and cached["key"]["spec"] == key["spec"] and cached["key"]["flags"] == key["flags"] \
-                and all(_same(cached["key"][k], key[k]) for k in ("mat", "cond", "cpos", "matrix", "pos", "tail")):
-            out = (np.copy(cached["out"][0]),) + tuple(cached["out"][1:])   # the field is post-processed in place
-        else:
-            where = dict(axes=self.pos, matrix=matrix) if lazy else dict(pos=iso_pos)
-            out = backend.krige_evaluate(spec, self._krige_mat, cond, self._krige_pos, **where, **kwargs)
-            out = out if return_var else (out,)
-            cached = None
-            if r.cache_krige:
-                cached = self._b200_krige_cache = dict(key=key, out=tuple(np.copy(o) for o in out))
-        field, error = out if return_var else (out[0], None)
-        field = np.reshape(field, shape)
+        entry = ke.evaluate(self, spec, ext_drift, return_var)
+        shape = entry["shape"]
+        # the callers get fresh arrays (post_field works in place, and the reference returns new ones)
+        field = np.reshape(np.copy(entry["out"][0]), shape)
         field = self.post_field(field, name[0], post_process, save[0])
         if return_var:                                                    # base.py:296-300
-            if cached is not None:      # sill is part of the key: the variance is a pure function of it too
-                if "krige_var" not in cached:
-                    cached["krige_var"] = np.maximum(self.model.sill - cached["out"][1], 0)
-                krige_var = np.reshape(np.copy(cached["krige_var"]), shape)
-            else:
-                krige_var = np.reshape(np.maximum(self.model.sill - error, 0), shape)
+            krige_var = np.reshape(np.copy(entry["krige_var"]), shape)
             krige_var = self.post_field(krige_var, name[1], False, save[1])
             return field, krige_var
         return field
 
     return _like(krige_call, orig_krige_call)
+
+
+# ---- CondSRF.__call__ with the combination fused into the kernels' stores (row f2, second half) -----
+def _build_cond_call(r):
+    """cond_srf.py:107-150 for the ensemble idiom (only the conditioned field is stored): the kriging
+    system is evaluated once and stays on the device (`rawkrige`, `var_scale`); every realisation is one
+    summation whose epilogue stores  rawkrige + var_scale * (sqrt(var/N) * sum + 0.0) + 0 [+ mean + trend]
+    with separately rounded operations in the reference's order -- the same bits as the numpy passes of
+    cond_srf.py:145-150, 175-177 -- and crosses PCIe once."""
+    gen = r.gen
+    cond_cls = r.cond_cls
+    orig_cond_call = r.orig[(cond_cls, "__call__")]
+    ke = r.krige_eval
+    allowed_kwargs = {"ext_drift", "chunk_size", "only_mean", "return_var", "post_process", "store"}
+
+    def _post_terms(self, post_process):
+        """Constant [mean, trend] that post_field adds (normalizer/tools.py:99-103), [] without
+        post-processing, or None when it is not a constant affine map."""
+        if not post_process:
+            return []
+        if type(self.normalizer) is not r.Normalizer:
+            return None
+        terms = []
+        for value in (self.mean, self.trend):
+            term = _const_term(value, "scalar", self.model.dim)
+            if term is None or isinstance(term, tuple):
+                return None
+            terms.append(term)
+        return terms
+
+    def cond_call(self, pos=None, seed=np.nan, mesh_type="unstructured", post_process=True, store=True,
+                  krige_store=True, **kwargs):
+        def fallback():
+            return orig_cond_call(self, pos, seed, mesh_type, post_process, store, krige_store, **kwargs)
+
+        if not (r.on() and r.fused_cond and type(self) is cond_cls and type(self.generator) is gen.RandMeth
+                and set(kwargs) <= allowed_kwargs):
+            return fallback()
+        model, krige = self.model, self.krige
+        if model.nugget > 0 or not model.var > 0 or krige.cond_no == 0 or model.latlon:
+            return fallback()
+        name, save = self.get_store_config(store=store, fld_cnt=3)
+        krige_name, krige_save = krige.get_store_config(store=krige_store, fld_cnt=2)
+        # fused only when neither raw field is wanted on the host and nothing stored is to be reused
+        # (cond_srf.py:124-132); everything else runs the reference's own body on the rebound wrappers
+        if save[1] or save[2] or name[2] in self.field_names:
+            return fallback()
+        spec = ke.cov_spec(krige)
+        terms = _post_terms(self, post_process)
+        if spec is None or terms is None:
+            return fallback()
+        # update the model/seed in the generator if any changes were made   (cond_srf.py:116)
+        self.generator.update(model, seed)
+        generator = self.generator
+        if generator.zero_var:
+            return orig_cond_call(self, pos, np.nan, mesh_type, post_process, store, krige_store, **kwargs)
+        iso_pos, shape, info = self.pre_pos(pos, mesh_type, info=True)                 # cond_srf.py:118
+        entry = ke.evaluate(krige, spec, kwargs.get("ext_drift"), True, want_device=True)
+        dev = entry["dev"]
+        # what self.krige(**kwargs) and the two krige-side post_field calls leave behind (cond_srf.py:133-141)
+        if krige_save[1]:
+            krige.post_field(backend.to_host(dev["krige_var"]), krige_name[1], False, True)
+        if krige_save[0]:
+            krige.post_field(backend.to_host(dev["field"]), krige_name[0], post_process, True)
+        # sqrt(var/N) * summed + 0.0 (generator.py:269-270, add_nugget=False); var_scale * rawfield;
+        # rawkrige + ...; + nugget (int 0); then post_field's constant mean and trend
+        epi = backend.make_epilogue(np.sqrt(model.var / generator._mode_no), [0.0])
+        pepi = backend.make_point_epilogue(dev["gain"], dev["field"], [0.0] + terms)
+        lazy = _lookup_lazy(iso_pos)
+        if lazy is not None:
+            field = backend.summate_structured(generator._cov_sample, generator._z_1, generator._z_2,
+                                               lazy[0], lazy[1], epilogue=epi, point_epilogue=pepi)
+        else:
+            field = backend.summate(generator._cov_sample, generator._z_1, generator._z_2,
+                                    np.asarray(iso_pos, dtype=np.double), epilogue=epi, point_epilogue=pepi)
+        return self.post_field(np.reshape(field, shape), name[0], False, save[0])        # cond_srf.py:145-150
+
+    return _like(cond_call, orig_cond_call)
 
 
 # ---- Field.post_field's mean / normalizer / trend step for constant terms ---------------------------
@@ -512,6 +664,7 @@ def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True)
         if fused:
             patches[(r.fsrf.SRF, "__call__")] = _build_srf_call(r)
             patches[(r.kbase.Krige, "__call__")] = _build_krige_call(r)
+            patches[(r.cond_cls, "__call__")] = _build_cond_call(r)
             patches[(r.fbase, "apply_mean_norm_trend")] = _build_apply_mean_norm_trend(r)
             patches.update(_build_generator_calls(r))
         for (owner, attr), value in patches.items():

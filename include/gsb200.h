@@ -146,6 +146,52 @@ int gsb_summate_incompr_structured_ex(const double *cov_samples, const double *z
                                       const gsb_epilogue *epi, int mem, int device, void *stream);
 
 /*
+ * Per-point affine epilogue for CONDITIONED fields (second half).
+ * CondSRF.__call__ combines the random field with the kriging results on the host, one numpy pass
+ * each over the whole mesh (src/gstools/field/cond_srf.py:133-150, get_scaling :152-178):
+ *     var_scale = sqrt(krige_var / var)                                   cond_srf.py:176
+ *     field     = rawkrige + var_scale * rawfield + nugget                cond_srf.py:146
+ * followed by post_field's constant mean / trend (normalizer/tools.py:99-103).  With a
+ * gsb_point_epilogue the kernels store, after the terms of gsb_epilogue (which yield `rawfield`),
+ *     v = gain[i] * v;  v = offset[i] + v;  v = v + add[0];  v = v + add[1]; ...
+ * with separately rounded operations in this order (gain = var_scale, offset = rawkrige; i = index
+ * of the point in its field, C order for meshes), i.e. the bits of the numpy passes.  `gain` and
+ * `offset` are ALWAYS device pointers on `device` (they are the device-resident results of one
+ * kriging evaluation, reused by every realisation of an ensemble), whatever `mem` says about the
+ * other arguments; either may be NULL (gain 1 / offset 0: the step is skipped).  Scalar fields only
+ * (CondSRF.valid_value_types, cond_srf.py:56).  With n_batch > 1 every field of the batch uses the same arrays.
+ */
+typedef struct gsb_point_epilogue {
+    const double *gain;     /* (n_pts,) device memory, or NULL */
+    const double *offset;   /* (n_pts,) device memory, or NULL */
+    int32_t n_add;          /* 0..GSB_EPI_MAX_ADD */
+    int32_t reserved;
+    double add[GSB_EPI_MAX_ADD];
+} gsb_point_epilogue;
+
+int gsb_summate_pp(const double *cov_samples, const double *z_1, const double *z_2,
+                   const double *pos, int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts,
+                   double *out, const gsb_epilogue *epi, const gsb_point_epilogue *pepi, int mem,
+                   int device, void *stream);
+
+int gsb_summate_structured_pp(const double *cov_samples, const double *z_1, const double *z_2,
+                              const double *axes, const int64_t *axis_len, const double *matrix,
+                              int dim, int64_t n_modes, int64_t n_batch, double *out,
+                              const gsb_epilogue *epi, const gsb_point_epilogue *pepi, int mem,
+                              int device, void *stream);
+
+/*
+ * gsb_cond_scaling -- CondSRF.get_scaling for a model without nugget (cond_srf.py:175-177) plus the
+ * variance clamp of Krige.__call__ (krige/base.py:296-298), on the device:
+ *     krige_var[i] = max(sill - error[i], 0);   gain[i] = sqrt(krige_var[i] / var)
+ * `error` is the second output of gsb_krige_evaluate / gsb_calc_field_krige_and_variance.  All pointers
+ * are device pointers; krige_var may be NULL or alias `error`.  IEEE subtraction, division and square
+ * root: the same bits as numpy.
+ */
+int gsb_cond_scaling(const double *error, int64_t n, double sill, double var, double *krige_var,
+                     double *gain, int device, void *stream);
+
+/*
  * gsb_summate_fourier[_structured] -- replaces gstools_cython.field.summate_fourier /
  *   gstools_core.summate_fourier (imported generator.py:23,33; called generator.py:67-75 from the
  *   Fourier generator, generator.py:685-692):

@@ -166,6 +166,27 @@ def apply_epilogue(raw, scale, adds=()):
     return out
 
 
+def apply_point_epilogue(field, gain=None, offset=None, adds=()):
+    """numpy restatement of the per-point step of a conditioned field, one array pass per operation in
+    the reference's order: ``var_scale * rawfield``, ``rawkrige + ...``, ``+ nugget`` (cond_srf.py:145-150),
+    then the constant mean / trend of ``post_field`` (normalizer/tools.py:99-103)."""
+    out = np.asarray(field, dtype=np.float64)
+    if gain is not None:
+        out = np.asarray(gain, dtype=np.float64).reshape(out.shape) * out
+    if offset is not None:
+        out = np.asarray(offset, dtype=np.float64).reshape(out.shape) + out
+    for a in adds:
+        out = out + np.float64(a)
+    return out
+
+
+def cond_scaling_np(error, sill, var):
+    """``(krige_var, var_scale)``: the clamp of krige/base.py:296-298 and CondSRF.get_scaling without
+    nugget (cond_srf.py:175-177)."""
+    krige_var = np.maximum(sill - np.asarray(error, dtype=np.float64), 0)
+    return krige_var, np.sqrt(krige_var / var)
+
+
 def _prep_krige(krig_mat, krig_vecs, cond):
     mat = np.ascontiguousarray(krig_mat, dtype=np.float64)
     kv = np.ascontiguousarray(krig_vecs, dtype=np.float64)
@@ -260,8 +281,8 @@ def krige_vecs_np(kind, var, len_rescaled, sill, cond_pos, pos, unbiased=True, t
     return np.concatenate(rows, axis=0)
 
 
-def krige_evaluate(spec, krig_mat, cond, cond_pos, pos, unbiased=True, tail_rows=None):
+def krige_evaluate(spec, krig_mat, cond, cond_pos, pos, unbiased=True, tail_rows=None, num_threads=None):
     """Right-hand sides by :func:`krige_vecs_np`, then the C oracle of the native evaluation."""
     kv = krige_vecs_np(spec["kind"], spec["var"], spec["len_rescaled"], spec.get("sill", spec["var"]),
                        cond_pos, pos, unbiased, tail_rows, spec.get("param", 0.0), spec.get("exact", False))
-    return calc_field_krige_and_variance(krig_mat, kv, cond)
+    return calc_field_krige_and_variance(krig_mat, kv, cond, num_threads)

@@ -204,18 +204,42 @@ def _fake_backend(monkeypatch, oracle_mod, calls):
         d = raw.shape[0] if vec else 1
         return oracle_mod.apply_epilogue(raw, e[0], [a[:d] if vec else a[0] for a in e[1]])
 
-    def summate(cov, z1, z2, pos, num_threads=None, *, epilogue=None):
-        calls.append(("flat", epilogue is not None))
-        return finish(oracle_mod.summate(cov, z1, z2, pos), epilogue, False)
+    def pp(field, point_epilogue):
+        if point_epilogue is None:
+            return field
+        g, o, adds = point_epilogue
+        return oracle_mod.apply_point_epilogue(field, None if g is None else g.numpy().reshape(field.shape),
+                                               None if o is None else o.numpy().reshape(field.shape), adds)
+
+    def summate(cov, z1, z2, pos, num_threads=None, *, epilogue=None, point_epilogue=None):
+        calls.append(("flat", epilogue is not None) + (("pp",) if point_epilogue is not None else ()))
+        return pp(finish(oracle_mod.summate(cov, z1, z2, pos), epilogue, False), point_epilogue)
 
     def summate_incompr(cov, z1, z2, pos, num_threads=None, *, epilogue=None):
         calls.append(("flat_vec", epilogue is not None))
         return finish(oracle_mod.summate_incompr(cov, z1, z2, pos), epilogue, True)
 
-    def summate_structured(cov, z1, z2, axes, matrix=None, *, epilogue=None):
-        calls.append(("struct", epilogue is not None))
+    def summate_structured(cov, z1, z2, axes, matrix=None, *, epilogue=None, point_epilogue=None):
+        calls.append(("struct", epilogue is not None) + (("pp",) if point_epilogue is not None else ()))
         shape = tuple(len(a) for a in axes)
-        return finish(oracle_mod.summate(cov, z1, z2, grid(axes, matrix)), epilogue, False).reshape(shape)
+        out = finish(oracle_mod.summate(cov, z1, z2, grid(axes, matrix)), epilogue, False).reshape(shape)
+        return pp(out, point_epilogue)
+
+    # stand-ins for the device-resident pieces of the fused CondSRF path: torch CPU tensors play the
+    # CUDA tensors, numpy restatements play the kernels
+    import torch
+
+    def to_device(a, device=None):
+        return None if a is None else torch.from_numpy(np.array(a, dtype=np.float64))
+
+    def cond_scaling(error, sill, var):
+        kv, gain = oracle_mod.cond_scaling_np(error.numpy(), sill, var)
+        return torch.from_numpy(kv), torch.from_numpy(gain)
+
+    monkeypatch.setattr(backend, "to_device", to_device)
+    monkeypatch.setattr(backend, "to_host", lambda t: t.numpy().copy())
+    monkeypatch.setattr(backend, "cond_scaling", cond_scaling)
+    monkeypatch.setattr(backend, "make_point_epilogue", lambda gain=None, offset=None, adds=(): (gain, offset, list(adds)))
 
     def summate_incompr_structured(cov, z1, z2, axes, matrix=None, *, epilogue=None):
         calls.append(("struct_vec", epilogue is not None))
@@ -324,6 +348,14 @@ def _fake_krige_backend(monkeypatch, oracle_mod, calls):
     def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=None, unbiased=True,
                        tail_rows=None, return_var=True):
         calls.append("eval")
+        import torch
+
+        tens = any(isinstance(x, torch.Tensor) for x in (krig_mat, cond, cond_pos, pos))
+        host = lambda x: x.numpy() if isinstance(x, torch.Tensor) else x
+        krig_mat, cond, cond_pos, pos, tail_rows = (host(x) for x in (krig_mat, cond, cond_pos, pos, tail_rows))
+        if axes is not None:
+            tens = tens or any(isinstance(a, torch.Tensor) for a in axes)
+            axes = [host(a) for a in axes]
         spec = dict(kind=kinds[model.type], var=model.var, len_rescaled=model.len_rescaled, sill=model.sill,
                     param=model.param, exact=bool(model.exact))
         shape = None
@@ -335,6 +367,8 @@ def _fake_krige_backend(monkeypatch, oracle_mod, calls):
         f, e = oracle_mod.krige_evaluate(spec, krig_mat, cond, cond_pos, pos, unbiased, tail_rows)
         if shape:
             f, e = f.reshape(shape), e.reshape(shape)
+        if tens:
+            f, e = torch.from_numpy(f), torch.from_numpy(e)
         return (f, e) if return_var else f
 
     monkeypatch.setattr(backend, "krige_evaluate", krige_evaluate)
@@ -455,16 +489,31 @@ def test_fast_krige_call_memoises_only_identical_systems(gsb, oracle_mod, monkey
         f2 += 1.0                                                   # results are copies: the cache is not aliased
         f3, _ = krige(mesh_type="structured")
         assert calls == ["eval"] and np.array_equal(f1, f3)
-        krige(pos, mesh_type="structured", return_var=False)       # different request
-        assert calls == ["eval"] * 2
+        f5 = krige(pos, mesh_type="structured", return_var=False)  # field only: the cached evaluation has it
+        assert calls == ["eval"] and np.array_equal(f1, f5)
         krige([pos[0], pos[1] + 0.5], mesh_type="structured")      # different mesh
+        assert calls == ["eval"] * 2
+        # the axes in the key must not alias the caller's arrays -- mutate one IN PLACE
+        ax = [pos[0].copy(), pos[1].copy()]
+        g1, _ = krige(ax, mesh_type="structured")
         assert calls == ["eval"] * 3
+        ax[0] += 10.0
+        g2, _ = krige(ax, mesh_type="structured")
+        assert calls == ["eval"] * 4 and not np.allclose(g1, g2)
+        krige(pos, mesh_type="structured")
+        assert calls == ["eval"] * 5
         krige.set_condition(cp, cv + 1.0)                           # different data
         f4, _ = krige(mesh_type="structured")
-        assert calls == ["eval"] * 4 and not np.allclose(f4, f3)
+        assert calls == ["eval"] * 6 and not np.allclose(f4, f3)
         krige.model.len_scale = 4.0                                 # model edited in place
         krige(mesh_type="structured")
-        assert calls == ["eval"] * 5
+        assert calls == ["eval"] * 7
+        krige(mesh_type="structured", return_var=False)
+        krige.set_condition(cp, cv + 2.0)
+        krige(mesh_type="structured", return_var=False)             # field-only entry ...
+        assert calls == ["eval"] * 8
+        krige(mesh_type="structured")                               # ... cannot serve a variance request
+        assert calls == ["eval"] * 9
         # the ensemble idiom of the reference's example: one evaluation for all realisations
         crf = gs.CondSRF(gs.krige.Ordinary(model, cp, cv), seed=1, mode_no=16)
         n0 = len(calls)
@@ -728,3 +777,101 @@ def test_oracle_apply_epilogue_matches_sequential_numpy(lens, seed):
     want = want + a0
     want = want + a1.reshape((3,) + (1,) * len(lens))
     assert np.array_equal(oracle.apply_epilogue(raw, scale, [a0, tuple(a1)]), want)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused CondSRF.__call__ (row f2, second half): host logic against the reference's own body.  On CPU
+# the device pieces are numpy restatements (see _fake_backend), so this pins WHICH arrays, constants
+# and orders the plugin hands to the kernels -- bit for bit against cond_srf.py:107-150.
+# ---------------------------------------------------------------------------------------------
+def _cond_cases(gs):
+    cp2, cv = (_KDATA[:, 0], _KDATA[:, 1]), _KDATA[:, 3]
+    cp3 = (_KDATA[:, 0], _KDATA[:, 1], _KDATA[:, 2])
+    return {
+        "ordinary2d": lambda: gs.krige.Ordinary(gs.Exponential(dim=2, var=1.3, len_scale=3), cp2, cv),
+        "simple2d_mean": lambda: gs.krige.Simple(gs.Gaussian(dim=2, var=0.5, len_scale=5, anis=0.5, angles=-0.5),
+                                                 cp2, cv, mean=1.0),
+        "ordinary3d_trend": lambda: gs.krige.Ordinary(gs.Exponential(dim=3, var=2.0, len_scale=[4.0, 2.0, 1.0],
+                                                                     angles=[0.3, 0.1, -0.2]), cp3, cv, trend=0.25),
+        "universal2d": lambda: gs.krige.Universal(gs.Gaussian(dim=2, var=1.0, len_scale=6), cp2, cv, "linear"),
+    }
+
+
+@needs_ref
+@pytest.mark.parametrize("case", ["ordinary2d", "simple2d_mean", "ordinary3d_trend", "universal2d"])
+@pytest.mark.parametrize("mesh", ["structured", "unstructured"])
+@pytest.mark.parametrize("post_process", [True, False])
+def test_fused_cond_call_matches_reference_bits(gsb, oracle_mod, monkeypatch, case, mesh, post_process):
+    gs = refharness.import_gstools()
+    make = _cond_cases(gs)[case]
+    dim = 3 if "3d" in case else 2
+    rs = np.random.RandomState(5)
+    if mesh == "structured":
+        pos = [np.linspace(0, 5, 7), np.linspace(0, 6, 5), np.linspace(0, 2, 4)][:dim]
+    else:
+        pos = [rs.uniform(0, 5, 33) for _ in range(dim)]
+    seeds = (11, 12, 13)
+    want, want_state = [], None
+    crf = gs.CondSRF(make(), mode_no=24)
+    for s in seeds:
+        want.append(crf(pos, seed=s, mesh_type=mesh, post_process=post_process, store=[f"f{s}", False, False]))
+    want_state = (crf.krige.field.copy(), crf.krige.krige_var.copy(), list(crf.field_names),
+                  list(crf.krige.field_names))
+    calls, kcalls = [], []
+    _fake_backend(monkeypatch, oracle_mod, calls)
+    _fake_krige_backend(monkeypatch, oracle_mod, kcalls)
+    gsb.enable()
+    try:
+        crf = gs.CondSRF(make(), mode_no=24)
+        got = [crf(pos, seed=s, mesh_type=mesh, post_process=post_process, store=[f"f{s}", False, False])
+               for s in seeds]
+        got_state = (crf.krige.field.copy(), crf.krige.krige_var.copy(), list(crf.field_names),
+                     list(crf.krige.field_names))
+        for s in seeds:
+            assert np.array_equal(getattr(crf, f"f{s}"), got[seeds.index(s)])
+    finally:
+        gsb.disable()
+    assert kcalls == ["eval"], "the kriging system must be evaluated exactly once for the ensemble"
+    assert all(c[-1] == "pp" for c in calls), calls
+    assert calls[0][0] == ("struct" if mesh == "structured" else "flat")
+    # the kriging evaluation itself differs from the reference's native loop only by the oracle-vs-oracle
+    # route (identical here), so the conditioned fields must agree bit for bit
+    for w, g in zip(want, got):
+        assert g.shape == w.shape and np.array_equal(w, g)
+    assert np.array_equal(want_state[0], got_state[0]) and np.array_equal(want_state[1], got_state[1])
+    assert want_state[2:] == got_state[2:]
+
+
+@needs_ref
+def test_fused_cond_call_falls_through(gsb, oracle_mod, monkeypatch):
+    """Default store (raw fields wanted), a model with nugget, a non-identity normalizer and reuse of stored
+    raw fields keep the reference's own body (running on the rebound wrappers)."""
+    gs = refharness.import_gstools()
+    cp, cv = (_KDATA[:, 0], _KDATA[:, 1]), _KDATA[:, 3]
+    pos = [np.linspace(0, 5, 6), np.linspace(0, 6, 5)]
+    variants = [
+        (lambda: gs.krige.Ordinary(gs.Exponential(dim=2, var=1.2, len_scale=3), cp, cv), dict()),
+        (lambda: gs.krige.Ordinary(gs.Exponential(dim=2, var=1.2, len_scale=3, nugget=0.1), cp, cv),
+         dict(store=["a", False, False])),
+        (lambda: gs.krige.Ordinary(gs.Exponential(dim=2, var=1.2, len_scale=3), cp, cv,
+                                   normalizer=gs.normalizer.LogNormal()), dict(store=["a", False, False])),
+        (lambda: gs.krige.Ordinary(gs.Exponential(dim=2, var=1.2, len_scale=3), cp, cv),
+         dict(store=["a", False, True])),
+    ]
+    for make, kw in variants:
+        ref = gs.CondSRF(make(), mode_no=16)
+        want = ref(pos, seed=3, mesh_type="structured", **kw)
+        want2 = ref(seed=3, mesh_type="structured", **kw)
+        calls = []
+        with monkeypatch.context() as mp:
+            _fake_backend(mp, oracle_mod, calls)
+            _fake_krige_backend(mp, oracle_mod, [])
+            gsb.enable()
+            try:
+                crf = gs.CondSRF(make(), mode_no=16)
+                got = crf(pos, seed=3, mesh_type="structured", **kw)
+                got2 = crf(seed=3, mesh_type="structured", **kw)        # second call: reuse branch where stored
+            finally:
+                gsb.disable()
+        assert not any(c[-1] == "pp" for c in calls), (kw, calls)
+        assert np.allclose(want, got, rtol=0, atol=1e-12) and np.allclose(want2, got2, rtol=0, atol=1e-12)
