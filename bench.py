@@ -641,18 +641,107 @@ def run_krige_arm(args, w):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json configs[4] through the drop-in path: gs.CondSRF realisations with the plugin (--workload c5cond)
+# ----------------------------------------------------------------------------------------------
+def run_c5cond_arm(args, edge=128, n_cond=1000):
+    """A "step" is ONE conditioned realisation through the unmodified reference's ``gs.CondSRF.__call__`` with
+    ``gstools_b200.enable()`` -- seed -> mode set (host) -> summation with the kriging results fused into the
+    kernel's stores (device) -> conditioned field as a host array.  Host in, host out: ``value`` and ``e2e``
+    are the same wall-clock measurement here (there is no device-resident variant of this call).  The
+    kriging system (ordinary kriging, 1000 points, Exponential 3D) is evaluated once, in the first warm-up
+    step, and reported separately."""
+    import torch
+
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import refharness
+
+    if not refharness.have_reference():
+        raise SystemExit("bench.py --workload c5cond needs the reference gstools (baseline/_ref; run "
+                         "__graft_entry__.build() in the build container)")
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    gs = refharness.import_gstools()
+    import gstools_b200 as gsb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 backend has no CPU fallback)")
+    gsb.set_device(0)
+    gsb.enable()
+    rs = np.random.RandomState(20170519)
+    cond_pos = rs.uniform(0, edge - 1, (3, n_cond))
+    cond_val = rs.normal(size=n_cond)
+    model = gs.Exponential(dim=3, var=1, len_scale=10)
+    t0 = time.perf_counter()
+    krige = gs.krige.Ordinary(model, cond_pos, cond_val)
+    t_setup = time.perf_counter() - t0
+    crf = gs.CondSRF(krige)
+    crf.set_pos([np.arange(float(edge))] * 3, "structured")
+    seeds = gs.random.MasterRNG(20170519)
+    n_modes = 1000
+    t0 = time.perf_counter()
+    crf(seed=seeds(), store=["fld", False, False])           # evaluates the kriging system
+    t_first = time.perf_counter() - t0
+    for _ in range(max(args.warmup, 3) - 1):
+        crf(seed=seeds(), store=["fld", False, False])
+    torch.cuda.synchronize()
+    launches0 = gsb.get_counter("launches")
+    k0 = gsb.get_counter("krige_calls")
+    t_modes = 0.0
+    with ClockSampler(0) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            f = crf(seed=seeds(), store=["fld", False, False])
+        torch.cuda.synchronize()
+        total = time.perf_counter() - t0
+    launches = gsb.get_counter("launches") - launches0
+    assert gsb.get_counter("krige_calls") == k0, "the kriging system must not be re-evaluated per realisation"
+    # share of the host-side mode sampling (RandMeth.reset_seed with the native radius sampler)
+    t0 = time.perf_counter()
+    for _ in range(8):
+        crf.generator.update(model, seeds())
+    t_modes = (time.perf_counter() - t0) / 8
+    pairs = edge ** 3 * n_modes
+    value = args.steps * pairs / total
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5 as configured: gs.CondSRF realisations, Ordinary kriging on {n_cond} points, "
+                               f"Exponential 3D, {edge}^3 structured mesh, mode_no={n_modes}, plugin enabled",
+                   "baseline_config": "C5", "path": "CondSRF.__call__ -> fused per-point epilogue (scaled contraction)",
+                   "mode_no": n_modes, "dim": 3, "step": "one conditioned realisation, seed in -> host field out",
+                   "l2": "every realisation writes a fresh 16.8 MB field and reads 33.6 MB of kriging results; "
+                         "inputs are re-sampled per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(8 * (5 * n_modes + 3 * edge)),
+                "d2h_bytes_per_step": int(3 * 8 * edge ** 3), "ms_per_step": 1e3 * total / args.steps,
+                "api": "gs.CondSRF(krige)(seed=s, store=[name, False, False]) with gstools_b200.enable()"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "breakdown_ms": {"kriging_setup_pinv_host": 1e3 * t_setup, "first_call_incl_kriging_evaluation": 1e3 * t_first,
+                         "mode_sampling_host_per_realisation": 1e3 * t_modes,
+                         "ensemble_of_256_extrapolated_s": t_first + 255 * total / args.steps},
+        "roofline": None, "wall_s_timed_region": total,
+    }
+    print(json.dumps(line), flush=True)
+    gsb.disable()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "krige"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5cond", "krige"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload == "krige":
         w = make_krige_workload()
         return run_krige_reference_arm(args, w) if args.impl == "reference" else run_krige_arm(args, w)
+    if args.workload == "c5cond":
+        if args.impl == "reference":
+            return run_reference_arm(args, make_workload("c5"))
+        return run_c5cond_arm(args)
     cfg = make_workload(args.workload)
     if args.impl == "reference":
         run_reference_arm(args, cfg)

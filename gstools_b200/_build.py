@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("GSB200_LIB") or os.path.join(HERE, "libgsb200.so")
 SOURCES = ["gsb_api.cu"]
-HEADERS = ["gsb_common.cuh", "gsb_direct.cuh", "gsb_separable.cuh", "gsb_krige.cuh", "gsb_sampler.cuh",
+HEADERS = ["gsb_common.cuh", "gsb_direct.cuh", "gsb_separable.cuh", "gsb_sepk.cuh", "gsb_krige.cuh", "gsb_sampler.cuh",
            "sincos_coeffs.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

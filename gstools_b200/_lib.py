@@ -101,6 +101,8 @@ SIGNATURES = {
     "gsb_set_option": (_int, [ctypes.c_char_p, _i64]),
     "gsb_release_memory": (_int, [_int]),
     "gsb_get_counter": (_i64, [ctypes.c_char_p]),
+    "gsb_streamk_plan": (_int, [_i64, _i64, _i64, _i64, _int, _int, _c_int64_p, ctypes.POINTER(ctypes.c_int32),
+                                ctypes.POINTER(_int)]),
     "gsb_kernel_times": (_int, [_c_double_p, _c_int64_p]),
     "gsb_measure_fp64_peak": (_int, [_int, _int, ctypes.c_double, _c_double_p]),
 }
@@ -178,6 +180,16 @@ def kernel_times():
     n = ctypes.c_int64(0)
     check(load().gsb_kernel_times(ctypes.byref(ms), ctypes.byref(n)), "gsb_kernel_times")
     return float(ms.value), int(n.value)
+
+
+def streamk_plan(tile_begin, tile_end, ly, lc, n_stages, max_grid):
+    """Share boundaries ``[(tile, stage), ...]`` (grid + 1 entries) of the stream-K contraction (host only)."""
+    tiles = (ctypes.c_int64 * (max_grid + 1))()
+    stages = (ctypes.c_int32 * (max_grid + 1))()
+    grid = _int(0)
+    check(load().gsb_streamk_plan(int(tile_begin), int(tile_end), int(ly), int(lc), int(n_stages), int(max_grid),
+                                  tiles, stages, ctypes.byref(grid)), "gsb_streamk_plan")
+    return [(int(tiles[c]), int(stages[c])) for c in range(grid.value + 1)]
 
 
 def measure_fp64_peak(device: int = 0, kind: int = 0, seconds: float = 0.3) -> float:

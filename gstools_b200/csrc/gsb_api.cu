@@ -12,6 +12,7 @@
 #include "gsb_common.cuh"
 #include "gsb_direct.cuh"
 #include "gsb_separable.cuh"
+#include "gsb_sepk.cuh"
 #include "gsb_krige.cuh"
 #include "gsb_sampler.cuh"
 
@@ -366,6 +367,183 @@ struct MeshInfo {
     bool identity;
 };
 
+// ---- second-generation separable path (gsb_sepk.cuh): tables -> ONE stream-K contraction launch per piece ----
+static std::atomic<int64_t> g_cnt_sk{0};
+static std::atomic<int64_t> g_opt_sk_table_mb{256};     // cap on the tile-axis table (all batch entries)
+static std::atomic<int64_t> g_opt_sk_grid{0};           // 0: one CTA per SM; else a fixed grid (tests)
+
+// The virtual mesh of the contraction: [outer slow axes | tile axes (folded: ly rows) | inner slow axes |
+// column axes (folded: lc columns)]
+struct SkLayout {
+    int n_prefix, n_tile_axes, n_inner, n_col_axes;
+    int64_t n_slow, n_in, ly, lc;
+    int n_ytiles, n_col_tiles;
+};
+
+// Which contiguous group of row axes becomes the tile axis?  Estimated time = contraction (cost units of sk_plan:
+// 64 units = one full 128 x 128 tile stage = 4096 SM cycles at 64 DFMA / clk) + building the tile-axis table
+// (one sincos and 24 bytes per entry).  E.g. 100^3: the middle axis alone (78 % of a tile) beats folding both row
+// axes (99 %, but a 237 MB table for a 8 MB field); 512 x 16 x 512: axis 0 alone; 40 x 50 x 130: both folded.
+static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int64_t n_batch, int ncomp, bool fold_cols,
+                                 int sm_count)
+{
+    const int dim = mesh.dim;
+    SkLayout L;
+    L.n_col_axes = fold_cols ? 2 : 1;
+    L.lc = fold_cols ? mesh.len[dim - 2] * mesh.len[dim - 1] : mesh.len[dim - 1];
+    L.n_col_tiles = (int)((L.lc + SK_TN - 1) / SK_TN);
+    const int n_row = dim - L.n_col_axes;                   // >= 1
+    const int64_t n_stages = n_modes_pad / SK_KC;
+    const int64_t cap = g_opt_sk_table_mb.load() << 20;
+    int64_t n_rows = 1, colg = 0;
+    for (int t = 0; t < n_row; ++t) n_rows *= mesh.len[t];
+    for (int ct = 0; ct < L.n_col_tiles; ++ct) colg += sk_colg(L.lc, ct);
+    double best = 1e300;
+    int best_a = n_row - 1, best_b = n_row;
+    for (int a = 0; a < n_row; ++a) {
+        int64_t P = 1;
+        for (int b = a + 1; b <= n_row; ++b) {
+            P *= mesh.len[b - 1];
+            const int64_t n_yt = (P + SK_TM - 1) / SK_TM;
+            const int64_t bytes = n_batch * n_yt * n_stages * SK_A_TILE * (int64_t)sizeof(double);
+            const bool single = (b == a + 1);
+            if (n_yt > (1 << 20) || (!single && bytes > cap)) break;
+            int64_t rq = (n_yt - 1) * 4 + sk_rowq(P, (int)(n_yt - 1));
+            const double units = (double)(n_rows / P) * (double)rq * (double)colg * (double)n_stages *
+                                 (double)(n_batch * ncomp);
+            const bool no_slow = (P == n_rows);
+            const double t_contract = units * 64.0 / ((double)sm_count * 1.9e9 * (no_slow ? 0.96 : 0.93));
+            const double t_table = (double)bytes / 1.0e12;
+            // ties: prefer the trailing axes (rows of a tile then are neighbours in memory)
+            const double t = (t_contract + t_table) * (1.0 + 1e-6 * (n_row - b));
+            if (t < best) { best = t; best_a = a; best_b = b; }
+        }
+    }
+    L.n_prefix = best_a;
+    L.n_tile_axes = best_b - best_a;
+    L.n_inner = n_row - best_b;
+    L.ly = 1;
+    for (int t = best_a; t < best_b; ++t) L.ly *= mesh.len[t];
+    L.n_in = 1;
+    for (int t = best_b; t < n_row; ++t) L.n_in *= mesh.len[t];
+    L.n_slow = n_rows / L.ly;
+    L.n_ytiles = (int)((L.ly + SK_TM - 1) / SK_TM);
+    return L;
+}
+
+static int sk_on_device(const double *d_cov, const double *d_z1, const double *d_z2, const double *d_sf,
+                        const double *d_axes, const MeshInfo &mesh, bool fold_cols, int64_t n_modes, int64_t n_batch,
+                        bool vec, const Epi &epi, double *d_out, double *h_out, DeviceState &dev, cudaStream_t st)
+{
+    const int dim = mesh.dim;
+    const int ncomp = vec ? dim : 1;
+    if (n_batch > 65535) return fail(GSB_ERR_ARGUMENT, "n_batch too large");
+    Scratch scr(st);
+    const int n_modes_pad = (int)((n_modes + SK_KC - 1) / SK_KC * SK_KC);
+    const int n_stages = n_modes_pad / SK_KC;
+    const SkLayout L = sk_choose_layout(mesh, n_modes_pad, n_batch, ncomp, fold_cols, dev.sm_count);
+    const bool scale = (L.n_prefix + L.n_inner) > 0;     // slow axes exist (even of length 1: their phase counts)
+
+    const int64_t gopt = g_opt_sk_grid.load();
+    const int max_grid = gopt > 0 ? (int)std::min<int64_t>(gopt, SK_MAX_GRID) : std::min(dev.sm_count, SK_MAX_GRID);
+    // One launch for everything on the device route.  The host route cuts the (field, slow index) units into
+    // up to 8 pieces of at least two "waves" so that the D2H copy of a piece overlaps the contraction of the next;
+    // unit u = z * n_slow + slow covers the output elements [u, u + 1) * ly * lc, so a piece is ONE contiguous copy.
+    const int64_t units = n_batch * ncomp * L.n_slow;
+    const int64_t tiles_per_unit = (int64_t)L.n_ytiles * L.n_col_tiles;
+    const int64_t tiles_all = units * tiles_per_unit;
+    // (with inner slow axes a unit is not contiguous: pieces then are whole fields)
+    const int64_t cut_units = L.n_in == 1 ? units : n_batch * ncomp;
+    const int64_t unit_mult = units / cut_units;
+    const int64_t pieces = h_out ? std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, cut_units),
+                                                                            tiles_all / (2 * (int64_t)max_grid))) : 1;
+    SkTableParams tp;
+    std::memset(&tp, 0, sizeof tp);
+    tp.cov = d_cov; tp.z1 = d_z1; tp.z2 = d_z2; tp.sf = d_sf; tp.axes = d_axes;
+    for (int t = 0; t < dim; ++t) {
+        tp.axis_off[t] = mesh.off[t];
+        tp.axis_len[t] = mesh.len[t];
+    }
+    std::memcpy(tp.matrix, mesh.matrix, sizeof tp.matrix);
+    tp.dim = dim;
+    tp.n_prefix = L.n_prefix;
+    tp.n_tile_axes = L.n_tile_axes;
+    tp.n_inner = L.n_inner;
+    tp.n_col_axes = L.n_col_axes;
+    tp.ly = L.ly;
+    tp.lc = L.lc;
+    tp.n_slow = L.n_slow;
+    tp.n_in = L.n_in;
+    tp.n_modes = n_modes;
+    tp.n_modes_pad = n_modes_pad;
+    tp.ncomp = ncomp;
+    tp.n_ytiles = L.n_ytiles;
+    tp.n_col_tiles = L.n_col_tiles;
+    GSB_TRY(scr.alloc(&tp.ttab, (size_t)n_batch * L.n_ytiles * n_stages * SK_A_TILE));
+    GSB_TRY(scr.alloc(&tp.btile, (size_t)n_batch * ncomp * L.n_col_tiles * n_stages * SK_B_TILE));
+    if (scale) GSB_TRY(scr.alloc(&tp.ctab, (size_t)n_batch * L.n_slow * n_modes_pad));
+    tp.n_flags = (int)(pieces * max_grid);
+    GSB_TRY(scr.alloc(&tp.flags, (size_t)tp.n_flags));
+    {
+        const int64_t max_width = std::max<int64_t>(std::max<int64_t>((int64_t)L.n_ytiles * SK_TM,
+                                                                       (int64_t)L.n_col_tiles * SK_TN),
+                                                    scale ? L.n_slow : 1);
+        const int64_t work = max_width * n_modes_pad;
+        dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 4096), scale ? 3u : 2u, (unsigned)n_batch);
+        sk_tables_kernel<<<grid, 256, 0, st>>>(tp);
+        g_launches.fetch_add(1);
+        GSB_CUDA(cudaGetLastError());
+    }
+    SkParams sp;
+    std::memset(&sp, 0, sizeof sp);
+    sp.ctab = tp.ctab;
+    sp.ttab = tp.ttab;
+    sp.btile = tp.btile;
+    sp.n_ytiles = L.n_ytiles;
+    sp.n_col_tiles = L.n_col_tiles;
+    sp.n_stages = n_stages;
+    sp.ncomp = ncomp;
+    sp.n_slow = L.n_slow;
+    sp.n_in = L.n_in;
+    sp.ly = L.ly;
+    sp.lc = L.lc;
+    sp.n_modes_pad = n_modes_pad;
+    sp.out = d_out;
+    sp.out_fstride = mesh.n;
+    sp.epi = epi;
+    const bool partial = (L.ly % SK_TM) != 0 || (L.lc % SK_TN) != 0;
+    GSB_TRY(scr.alloc(&sp.slots, (size_t)max_grid * SK_TM * SK_TN));
+    unsigned *d_flags = tp.flags;
+    std::vector<SkBound> bnd;
+    for (int64_t k = 0; k < pieces; ++k) {
+        const int64_t u0 = cut_units * k / pieces * unit_mult, u1 = cut_units * (k + 1) / pieces * unit_mult;
+        if (u1 == u0) continue;
+        const int grid = sk_plan(u0 * tiles_per_unit, u1 * tiles_per_unit, L.n_ytiles, L.n_col_tiles, n_stages, L.ly,
+                                 L.lc, max_grid, bnd);
+        for (int c = 0; c <= grid; ++c) sp.bnd[c] = bnd[(size_t)c];
+        sp.flags = d_flags + k * max_grid;
+        {
+            KernelTimer timer(st);
+            TraceScope ts("contract(sk)", st);
+            GSB_TRY(sk_launch(sp, grid, scale, partial, st));
+        }
+        if (h_out) {
+            cudaEvent_t ev = dev.contract_events[k % DeviceState::N_CHUNK_EVENTS];
+            GSB_CUDA(cudaEventRecord(ev, st));
+            GSB_CUDA(cudaStreamWaitEvent(dev.streams[1], ev, 0));
+            const size_t off = (size_t)u0 * L.ly * L.lc;
+            GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * (size_t)(u1 - u0) * L.ly * L.lc,
+                                     cudaMemcpyDeviceToHost, dev.streams[1]));
+        }
+    }
+    if (h_out) {
+        GSB_CUDA(cudaEventRecord(dev.events[4], dev.streams[1]));
+        GSB_CUDA(cudaStreamWaitEvent(st, dev.events[4], 0));
+    }
+    g_cnt_sk.fetch_add(1);
+    return GSB_OK;
+}
+
 // everything on device: d_cov (B,dim,N), d_z1/d_z2 (B,N), d_axes, d_out (B,ncomp,n).
 // `h_out`: when non-null, finished chunks are copied to this host buffer as they complete.
 // `st` is the caller's stream: all work is ordered after what `st` holds on entry, and `st` waits
@@ -452,6 +630,12 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         return GSB_OK;
     }
 
+    if (g_opt_sep_path.load() == 3) {
+        GSB_TRY(sk_on_device(d_cov, d_z1, d_z2, d_sf, d_axes, mesh, folded, n_modes, n_batch, vec, epi, d_out, h_out, dev, st));
+        g_cnt_separable.fetch_add(1);
+        if (folded) g_cnt_folded.fetch_add(1);
+        return GSB_OK;
+    }
     // ---- separable path: tables -> (A generation || contraction) per chunk ----
     const int nra = vdim - 1;
     const int n_modes_pad = (int)((n_modes + SEP_KC - 1) / SEP_KC * SEP_KC);
@@ -1563,6 +1747,8 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "fold_axes") g_opt_fold_axes = value;
     else if (n == "partial_tiles") g_opt_partial_tiles = value;
     else if (n == "krige_host_chunk_mb") g_opt_krige_host_chunk_mb = std::max<int64_t>(value, 1);
+    else if (n == "sk_table_mb") g_opt_sk_table_mb = std::max<int64_t>(value, 1);
+    else if (n == "sk_grid") g_opt_sk_grid = std::max<int64_t>(value, 0);
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);
     return GSB_OK;
 }
@@ -1577,7 +1763,25 @@ int64_t gsb_get_counter(const char *name)
     if (n == "scaled_calls") return g_cnt_scaled.load();
     if (n == "krige_calls") return g_cnt_krige.load();
     if (n == "folded_calls") return g_cnt_folded.load();
+    if (n == "sk_calls") return g_cnt_sk.load();
     return -1;
+}
+
+int gsb_streamk_plan(int64_t tile_begin, int64_t tile_end, int64_t ly, int64_t lc, int n_stages, int max_grid,
+                     int64_t *tiles, int32_t *stages, int *grid)
+{
+    if (!tiles || !stages || !grid) return fail(GSB_ERR_ARGUMENT, "NULL output pointer");
+    if (tile_begin < 0 || tile_end < tile_begin || ly < 1 || lc < 1 || n_stages < 1 || max_grid < 1)
+        return fail(GSB_ERR_ARGUMENT, "streamk_plan: bad geometry");
+    std::vector<SkBound> bnd;
+    const int n_yt = (int)((ly + SK_TM - 1) / SK_TM), n_ct = (int)((lc + SK_TN - 1) / SK_TN);
+    const int g = sk_plan(tile_begin, tile_end, n_yt, n_ct, n_stages, ly, lc, max_grid, bnd);
+    for (int c = 0; c <= g; ++c) {
+        tiles[c] = bnd[(size_t)c].tile;
+        stages[c] = bnd[(size_t)c].stage;
+    }
+    *grid = g;
+    return GSB_OK;
 }
 
 int gsb_kernel_times(double *total_ms, int64_t *n_launches)

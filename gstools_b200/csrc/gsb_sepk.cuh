@@ -1,0 +1,574 @@
+// gsb_sepk.cuh -- separable summation on structured meshes, second generation ("stream-K" contraction).
+//
+// Same mathematics as gsb_separable.cuh (reference: src/gstools/field/generator.py:193-199 on the mesh of
+// src/gstools/tools/geometric.py:340-356): with k' = M^T k the phase splits per axis and
+//     u[row, c] = sum_j Re( A_j(row) E_j(c) ),   A_j(row) = c_j(slow) T_j(iy),   E_j(c) = exp(i k'_last a_last[c])
+// where the row index is split as row = slow * ly + iy:
+//     T_j(iy)   = exp(i sum_{t in tile axes} k'_t a_t[i_t])   the TILE-AXIS table: the trailing row axes folded into
+//                                                              one axis of ly entries (pre-tiled, L2 resident)
+//     c_j(slow) = (z1_j - i z2_j) sf_j prod_{t in prefix axes} exp(i k'_t a_t[i_t])   one complex factor per
+//                                                              (slow index, mode): 128 bytes per pipeline stage
+// What changed against the first generation, and why:
+//   * NO pre-generated A operand.  The first generation wrote A = c T to HBM (5.2 GB for the 512^3 field) from a
+//     second kernel and re-read it; here every warp rescales the T fragments of ITS OWN rows right after
+//     loading them.  Two layout changes make that cheap: (1) a warp owns 16 rows x 128 columns (2 x 16 DMMA
+//     tiles) instead of 32 x 64, so no two warps rescale the same rows -- half the FP64 work; (2) within a
+//     stage the contraction index is ordered [4 modes: real parts][the same 4 modes: imaginary parts], so the lane
+//     that feeds k-slot t of the DMMA holds BOTH cos and sin of mode t (one LDS.128) and needs no shuffle.
+//     Cost: 2 DMUL + 2 DFMA per 32 DMMA.8x8x4 per warp (1.6 % of the FP64 issue slots).
+//   * STREAM-K.  The first generation walked whole 128x128 output tiles (tile t, t + grid, ...): a 128^3 field is
+//     128 tiles on 148 SMs (one partial wave), 200^3 pads 200 -> 256 columns, and every row chunk was a separate
+//     launch with its own pipeline fill and drain.  Here ONE persistent launch splits the (tile, stage) iteration
+//     space -- weighted by what a tile really costs when it hangs over the mesh edge -- into equal contiguous
+//     shares, one per SM.  A tile that straddles two shares is finished by the CTA that started it: the later
+//     CTA(s) write their partial accumulators to a scratch slot and raise a flag, the owner adds them in a fixed
+//     order (deterministic, no atomics on data).
+#pragma once
+
+#include <algorithm>
+#include <type_traits>
+#include <vector>
+
+#include "gsb_common.cuh"
+
+namespace gsb {
+
+constexpr int SK_TM = 128;                 // rows per tile
+constexpr int SK_TN = 128;                 // columns per tile
+constexpr int SK_KC = 8;                   // modes per pipeline stage (multiple of 4)
+constexpr int SK_STAGES = 4;
+constexpr int SK_WARPS = 8;
+constexpr int SK_THREADS = SK_WARPS * 32;
+static_assert(SK_KC % 4 == 0, "a stage holds whole quads of modes");
+// shared-memory / global tile layouts (doubles)
+//   T tile [128 rows][SK_AST]: (cos, sin) -- or (Re A, -Im A) when nothing is rescaled -- of mode kc at 2*kc;
+//                              row stride 24 makes the LDS.128 of a quarter warp hit 8 distinct 16-byte banks
+//   B tile [2*KC rows][SK_BST]: row 8*(kc/4) + 4*part + kc%4 (part 0: p cos, part 1: p sin), stride 132
+//   C block [KC] complex slow-axis factors
+constexpr int SK_AST = 2 * SK_KC + 8;
+constexpr int SK_BST = SK_TN + 4;
+constexpr int SK_A_TILE = SK_TM * SK_AST;
+constexpr int SK_B_TILE = 2 * SK_KC * SK_BST;
+constexpr int SK_C_BLOCK = 2 * SK_KC;
+constexpr int SK_STAGE_DOUBLES = SK_A_TILE + SK_B_TILE + SK_C_BLOCK;
+constexpr size_t SK_SMEM_BYTES =
+    (size_t)SK_STAGES * SK_STAGE_DOUBLES * sizeof(double) + 2 * SK_STAGES * sizeof(uint64_t) + 128;
+constexpr int SK_MAX_AXES = GSB_MAX_DIM;
+constexpr int SK_MAX_GRID = 160;           // CTAs of the persistent grid (one per SM; B200: 148)
+
+// ---------------------------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------------------------
+struct SkTableParams {
+    const double *cov, *z1, *z2, *sf;   // (n_batch, dim, n_modes), (n_batch, n_modes) x 3 (sf optional)
+    const double *axes;                 // concatenated axis coordinates
+    int64_t axis_off[SK_MAX_AXES];      // per MESH axis
+    int64_t axis_len[SK_MAX_AXES];
+    double matrix[GSB_MAX_DIM * GSB_MAX_DIM];
+    int dim;                            // mesh axes = dimension of the wave vectors
+    // mesh axes, in order: [outer slow axes | tile axes | inner slow axes | column axes]
+    int n_prefix;                       // outer slow axes
+    int n_tile_axes;                    // folded into the tile axis (ly entries)
+    int n_inner;                        // inner slow axes (n_in entries); slow = outer * n_in + inner
+    int n_col_axes;                     // trailing axes (1 or 2) folded into the column axis (lc entries)
+    int64_t ly, lc, n_slow, n_in;
+    int64_t n_modes;
+    int n_modes_pad, ncomp;
+    int n_ytiles, n_col_tiles;
+    double *ttab;                       // [b][ytile][stage] blocks of SK_A_TILE
+    double *btile;                      // [b][comp][col tile][stage] blocks of SK_B_TILE
+    double2 *ctab;                      // [b][slow][mode] slow-axis factors; NULL: no prefix axes, the T table
+                                        //   carries (z1 - i z2) sf itself and stores (Re A, -Im A)
+    unsigned *flags;                    // stream-K flags, zeroed here (n_flags entries)
+    int n_flags;
+};
+
+__device__ __forceinline__ double sk_kprime(const SkTableParams &tp, const double *cov, int t, int64_t j)
+{
+    // k'_t = sum_s M[s][t] k_s   (phase = k . (M a) = (M^T k) . a)
+    double kp = 0.0;
+    for (int s = 0; s < tp.dim; ++s) kp = fma(tp.matrix[s * tp.dim + t], cov[(int64_t)s * tp.n_modes + j], kp);
+    return kp;
+}
+
+// phase of mode j at entry i of the axis obtained by folding mesh axes [t0, t0 + nt) (last fastest)
+__device__ __forceinline__ double sk_folded_phase(const SkTableParams &tp, const double *cov, int t0, int nt,
+                                                  int64_t i, int64_t j)
+{
+    double phase = 0.0;
+    int64_t rem = i;
+    for (int t = t0 + nt - 1; t >= t0; --t) {
+        const int64_t it = rem % tp.axis_len[t];
+        rem /= tp.axis_len[t];
+        phase = fma(sk_kprime(tp, cov, t, j), tp.axes[tp.axis_off[t] + it], phase);
+    }
+    return phase;
+}
+
+// All tables of a call in one launch.  blockIdx.y: 0 = T table (tile axis), 1 = B table (column axis),
+// 2 = slow-axis factors;  blockIdx.z = batch entry.  Full-accuracy sincos (libdevice), O((ly + lc + n_slow) N).
+// The padding columns of the pre-tiled blocks travel with the bulk copies: they are written (zero) here too.
+__global__ void sk_tables_kernel(const SkTableParams tp)
+{
+    const int which = blockIdx.y;
+    const int64_t b = blockIdx.z;
+    const double *cov = tp.cov + b * tp.dim * tp.n_modes;
+    const int n_stages = tp.n_modes_pad / SK_KC;
+    if (which == 0 && b == 0 && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < tp.n_flags; i += blockDim.x) tp.flags[i] = 0u;
+    int64_t width;
+    if (which == 0) width = (int64_t)tp.n_ytiles * SK_TM;
+    else if (which == 1) width = (int64_t)tp.n_col_tiles * SK_TN;
+    else width = tp.n_slow;
+    const int64_t total = width * tp.n_modes_pad;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const bool mode_major = which != 2;     // T / B: consecutive threads walk along the axis; C: along the modes
+        const int64_t j = mode_major ? idx / width : idx % tp.n_modes_pad;
+        const int64_t i = mode_major ? idx - j * width : idx / tp.n_modes_pad;
+        const bool live = j < tp.n_modes;
+        if (which == 0) {
+            double c = 0.0, s = 0.0;
+            if (live && i < tp.ly) {
+                sincos(sk_folded_phase(tp, cov, tp.n_prefix, tp.n_tile_axes, i, j), &s, &c);
+                if (!tp.ctab) {
+                    const double w = tp.sf ? tp.sf[b * tp.n_modes + j] : 1.0;
+                    const double a = w * tp.z1[b * tp.n_modes + j], bb = w * tp.z2[b * tp.n_modes + j];
+                    const double re = a * c + bb * s;      // (a - i bb)(c + i s)
+                    const double im = a * s - bb * c;
+                    c = re;
+                    s = -im;
+                }
+            }
+            const int yt = (int)(i / SK_TM), r = (int)(i % SK_TM);
+            const int kc = (int)(j % SK_KC);
+            double *row = tp.ttab + ((b * tp.n_ytiles + yt) * n_stages + j / SK_KC) * (int64_t)SK_A_TILE + r * SK_AST;
+            *reinterpret_cast<double2 *>(row + 2 * kc) = make_double2(c, s);
+            if (kc == 0) {
+#pragma unroll
+                for (int u = 2 * SK_KC; u < SK_AST; u += 2)
+                    *reinterpret_cast<double2 *>(row + u) = make_double2(0.0, 0.0);
+            }
+        } else if (which == 1) {
+            double c = 0.0, s = 0.0;
+            if (live && i < tp.lc)
+                sincos(sk_folded_phase(tp, cov, tp.n_prefix + tp.n_tile_axes + tp.n_inner, tp.n_col_axes, i, j), &s, &c);
+            double k2 = 0.0, k0 = 0.0;
+            if (tp.ncomp > 1 && live) {
+                for (int s2 = 0; s2 < tp.dim; ++s2) {
+                    const double k = cov[(int64_t)s2 * tp.n_modes + j];
+                    k2 += k * k;
+                }
+                k0 = cov[j];
+            }
+            const int ct = (int)(i / SK_TN), col = (int)(i % SK_TN);
+            const int st = (int)(j / SK_KC), kc = (int)(j % SK_KC);
+            const int row = 8 * (kc / 4) + (kc % 4);
+            for (int comp = 0; comp < tp.ncomp; ++comp) {
+                double p = 1.0;
+                if (tp.ncomp > 1) {
+                    // incompressible projector on the ORIGINAL wave vector (generator.py:479-495)
+                    p = 0.0;
+                    if (live) p = ((comp == 0) ? 1.0 : 0.0) - cov[(int64_t)comp * tp.n_modes + j] * k0 / k2;
+                }
+                double *tile = tp.btile +
+                               (((b * tp.ncomp + comp) * tp.n_col_tiles + ct) * n_stages + st) * (int64_t)SK_B_TILE;
+                tile[row * SK_BST + col] = p * c;
+                tile[(row + 4) * SK_BST + col] = p * s;
+                if (col < SK_BST - SK_TN) {
+                    tile[row * SK_BST + SK_TN + col] = 0.0;
+                    tile[(row + 4) * SK_BST + SK_TN + col] = 0.0;
+                }
+            }
+        } else {
+            // c[b][slow][j] = (z1_j - i z2_j) sf_j exp(i sum_{slow axes} k'_t a_t[i_t(slow)])
+            double2 e = make_double2(0.0, 0.0);
+            if (live) {
+                double c, s;
+                const double phase = sk_folded_phase(tp, cov, 0, tp.n_prefix, i / tp.n_in, j) +
+                                     sk_folded_phase(tp, cov, tp.n_prefix + tp.n_tile_axes, tp.n_inner, i % tp.n_in, j);
+                sincos(phase, &s, &c);
+                const double w = tp.sf ? tp.sf[b * tp.n_modes + j] : 1.0;
+                const double a = w * tp.z1[b * tp.n_modes + j], bb = w * tp.z2[b * tp.n_modes + j];
+                e = make_double2(a * c + bb * s, a * s - bb * c);
+            }
+            tp.ctab[(b * tp.n_slow + i) * tp.n_modes_pad + j] = e;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stream-K plan (host).  Tiles are numbered  tile = ((z * n_slow + slow) * n_ytiles + yt) * n_col_tiles + ct
+// (z = field * ncomp + comp).  A pipeline stage of a tile costs rowq(yt) * colg(ct) units: rowq in 1..4 counts
+// the passes of 8-row groups each of the 4 FP64 pipes makes (row groups are dealt round-robin to the pipes),
+// colg in {4, 8, 12, 16} the 8-column groups computed (inside the mesh, rounded up to 4).  Boundaries of the equal-cost shares are snapped to stages.
+// ---------------------------------------------------------------------------------------------
+struct SkBound { int64_t tile; int32_t stage; int32_t pad; };
+
+inline int sk_rowq(int64_t ly, int yt)
+{
+    const int64_t rows = std::min<int64_t>(SK_TM, ly - (int64_t)yt * SK_TM);
+    const int groups = (int)((rows + 7) / 8);
+    return (groups + 3) / 4;
+}
+inline int sk_colg(int64_t lc, int ct)
+{
+    const int64_t cols = std::min<int64_t>(SK_TN, lc - (int64_t)ct * SK_TN);
+    return 4 * (int)((cols + 31) / 32);      // the kernel has compile-time variants for 4, 8, 12, 16 column groups
+}
+
+// Shares of the tiles [tile_begin, tile_end) for `grid` CTAs: bnd[0..grid], bnd[c] <= bnd[c+1],
+// bnd[0] = (tile_begin, 0), bnd[grid] = (tile_end, 0).  Returns the grid size actually used (<= max_grid).
+inline int sk_plan(int64_t tile_begin, int64_t tile_end, int n_ytiles, int n_col_tiles, int n_stages, int64_t ly,
+                   int64_t lc, int max_grid, std::vector<SkBound> &bnd)
+{
+    max_grid = std::max(1, std::min(max_grid, SK_MAX_GRID));
+    const int period = n_ytiles * n_col_tiles;
+    std::vector<int64_t> prefix((size_t)period + 1, 0);     // cost of the first p tiles of a period
+    std::vector<int> w((size_t)period);
+    for (int p = 0; p < period; ++p) {
+        w[p] = sk_rowq(ly, p / n_col_tiles) * sk_colg(lc, p % n_col_tiles);
+        prefix[p + 1] = prefix[p] + (int64_t)w[p] * n_stages;
+    }
+    const int64_t P = prefix[period];
+    auto cum = [&](int64_t tile) { return (tile / period) * P + prefix[(size_t)(tile % period)]; };
+    const int64_t c0 = cum(tile_begin), c1 = cum(tile_end);
+    const int64_t n_units = (tile_end - tile_begin) * (int64_t)n_stages;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, n_units));
+    bnd.assign((size_t)grid + 1, SkBound{tile_end, 0, 0});
+    bnd[0] = SkBound{tile_begin, 0, 0};
+    for (int c = 1; c < grid; ++c) {
+        // target cost from the start of the numbering; (c1 - c0) * c fits: cost < 2^50, c < 2^10
+        const int64_t target = c0 + (c1 - c0) / grid * c + (c1 - c0) % grid * c / grid;
+        const int64_t per = target / P, rem = target % P;
+        const int p = (int)(std::upper_bound(prefix.begin(), prefix.end(), rem) - prefix.begin()) - 1;   // prefix[p] <= rem
+        const int64_t tile = per * period + p;
+        const int stage = (int)((rem - prefix[(size_t)p]) / w[(size_t)p]);
+        bnd[(size_t)c] = SkBound{tile, stage, 0};
+        if (bnd[(size_t)c].tile >= tile_end) bnd[(size_t)c] = SkBound{tile_end, 0, 0};
+    }
+    return grid;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the contraction
+// ---------------------------------------------------------------------------------------------
+struct SkParams {
+    const double *ttab, *btile;
+    const double2 *ctab;
+    int n_ytiles, n_col_tiles, n_stages, ncomp;
+    int64_t n_slow, n_in;     // slow = outer * n_in + inner: row of (slow, iy) = (outer * ly + iy) * n_in + inner
+    int64_t ly, lc;
+    int n_modes_pad;
+    double *out;              // field (batch, comp) at out + (batch*ncomp + comp)*out_fstride; row r at + r*lc
+    int64_t out_fstride;
+    SkBound bnd[SK_MAX_GRID + 1];   // shares of the gridDim.x CTAs (kernel parameter: constant bank, no upload)
+    double *slots;            // [gridDim.x][SK_TM*SK_TN] partial accumulators of a CTA's leading (non-owned) segment
+    unsigned *flags;          // [gridDim.x], zeroed before the launch
+    Epi epi;
+};
+
+__device__ __forceinline__ void sk_dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ unsigned sk_ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sk_st_release(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One pipeline stage of a warp: NI row groups (1 or 2) x JV column groups (4, 8, 12 or 16), all compile-time, so
+// that partial tiles run the same straight-line, software-pipelined code as full ones (a first version predicated
+// every column group at run time: each LDS was followed by its dependent DMMA, 2x slower on partial tiles).
+template <bool SCALE, int JV, int NI>
+__device__ __forceinline__ void sk_stage(const double *S, double (&acc)[2][16][2], int a_off0, int a_off1, int b_off,
+                                         int c_off)
+{
+#pragma unroll
+    for (int q = 0; q < SK_KC / 4; ++q) {
+        // (cos, sin) of mode 4q + t for this lane's rows; rescaled by the slow-axis factor
+        double ar[2], ai[2];
+        const double2 e0 = *reinterpret_cast<const double2 *>(S + a_off0 + 8 * q);
+        double2 e1 = make_double2(0.0, 0.0);
+        if (NI > 1) e1 = *reinterpret_cast<const double2 *>(S + a_off1 + 8 * q);
+        if (SCALE) {
+            const double2 cc = *reinterpret_cast<const double2 *>(S + c_off + 8 * q);
+            //  Re(c e) = cr cos - ci sin        -Im(c e) = -(cr sin + ci cos)
+            ar[0] = fma(cc.x, e0.x, -(cc.y * e0.y));
+            ai[0] = fma(-cc.x, e0.y, -(cc.y * e0.x));
+            if (NI > 1) {
+                ar[1] = fma(cc.x, e1.x, -(cc.y * e1.y));
+                ai[1] = fma(-cc.x, e1.y, -(cc.y * e1.x));
+            }
+        } else {
+            ar[0] = e0.x; ai[0] = e0.y;
+            ar[1] = e1.x; ai[1] = e1.y;
+        }
+        const double *Bq = S + b_off + 8 * q * SK_BST;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+#pragma unroll
+            for (int j = 0; j < JV; ++j) {
+                const double bf = Bq[4 * part * SK_BST + 8 * j];
+                sk_dmma(acc[0][j][0], acc[0][j][1], part ? ai[0] : ar[0], bf);
+                if (NI > 1) sk_dmma(acc[1][j][0], acc[1][j][1], part ? ai[1] : ar[1], bf);
+            }
+        }
+    }
+}
+
+// SCALE   : rescale the T fragments by the slow-axis factor (meshes with prefix axes); false: the T table is A itself
+// PARTIAL : tiles may hang over the mesh edge (ly % 128 or lc % 128 != 0): skip the row / column groups outside
+template <bool SCALE, bool PARTIAL>
+__global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid_constant__ SkParams prm)
+{
+    extern __shared__ __align__(128) unsigned char sk_smem_raw[];
+    double *stage_base = reinterpret_cast<double *>(sk_smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + SK_STAGES * SK_STAGE_DOUBLES);
+    uint64_t *empty = full + SK_STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int n_stages = prm.n_stages;
+    const int cta = blockIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < SK_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], SK_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // this CTA's share: (tile, stage) from lo (inclusive) to hi (exclusive)
+    const SkBound lo = prm.bnd[cta], hi = prm.bnd[cta + 1];
+    const int64_t last_tile = (hi.stage > 0) ? hi.tile : hi.tile - 1;      // last tile touched
+    const bool has_work = (lo.tile < hi.tile) || (lo.tile == hi.tile && lo.stage < hi.stage);
+
+    // ---- prefetch cursor: walks the same (tile, stage) sequence DEPTH steps ahead ----
+    constexpr int DEPTH = SK_STAGES - 2;
+    int64_t pf_tile = lo.tile;
+    int pf_s = lo.stage, pf_send = 0;
+    bool pf_live = has_work;
+    int pf_slot = 0;
+    uint32_t pf_round = 0;
+    const double *pf_a = nullptr, *pf_b = nullptr, *pf_c = nullptr;
+    auto pf_decode = [&]() {
+        const int ct = (int)(pf_tile % prm.n_col_tiles);
+        int64_t rest = pf_tile / prm.n_col_tiles;
+        const int yt = (int)(rest % prm.n_ytiles);
+        rest /= prm.n_ytiles;
+        const int64_t slow = rest % prm.n_slow;
+        const int64_t z = rest / prm.n_slow;
+        const int comp = (int)(z % prm.ncomp);
+        const int64_t b = z / prm.ncomp;
+        pf_a = prm.ttab + ((b * prm.n_ytiles + yt) * (int64_t)n_stages) * SK_A_TILE;
+        pf_b = prm.btile + (((b * prm.ncomp + comp) * prm.n_col_tiles + ct) * (int64_t)n_stages) * SK_B_TILE;
+        if (SCALE) pf_c = reinterpret_cast<const double *>(prm.ctab + (b * prm.n_slow + slow) * prm.n_modes_pad);
+        pf_send = (pf_tile == hi.tile) ? hi.stage : n_stages;
+    };
+    auto pf_issue = [&]() {   // one thread
+        double *A = stage_base + pf_slot * SK_STAGE_DOUBLES;
+        constexpr uint32_t bytes = (SK_A_TILE + SK_B_TILE + (SCALE ? SK_C_BLOCK : 0)) * sizeof(double);
+        mbar_arrive_expect_tx(&full[pf_slot], bytes);
+        bulk_g2s(A, pf_a + (int64_t)pf_s * SK_A_TILE, SK_A_TILE * sizeof(double), &full[pf_slot]);
+        bulk_g2s(A + SK_A_TILE, pf_b + (int64_t)pf_s * SK_B_TILE, SK_B_TILE * sizeof(double), &full[pf_slot]);
+        if (SCALE)
+            bulk_g2s(A + SK_A_TILE + SK_B_TILE, pf_c + (int64_t)pf_s * SK_C_BLOCK, SK_C_BLOCK * sizeof(double),
+                     &full[pf_slot]);
+    };
+    auto pf_advance = [&]() {   // all threads, uniform
+        if (++pf_slot == SK_STAGES) { pf_slot = 0; ++pf_round; }
+        if (++pf_s == pf_send) {
+            pf_s = 0;
+            ++pf_tile;
+            if (pf_tile > last_tile) pf_live = false;
+            else pf_decode();
+        }
+    };
+    if (pf_live) pf_decode();
+#pragma unroll
+    for (int p = 0; p < DEPTH; ++p) {
+        if (pf_live) {
+            if (tid == 0) pf_issue();
+            pf_advance();
+        }
+    }
+
+    // fragment owner: g = lane / 4 (row within an 8-row group / column within an 8-column group), t = lane % 4
+    // (k slot).  Warp w owns row groups w and w + 8: rows 8w .. 8w+7 and 64+8w .. 64+8w+7, all 128 columns.
+    // Sub-partition s hosts warps s and s + 4, i.e. row groups s, s+4, s+8, s+12: the row groups of a tile that
+    // hangs over the mesh edge are spread evenly over the four FP64 pipes.
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int a_off0 = (8 * warp + g) * SK_AST + 2 * t;            // + q * 8   (q = quad of modes)
+    const int a_off1 = (8 * (warp + 8) + g) * SK_AST + 2 * t;
+    const int b_off = SK_A_TILE + t * SK_BST + g;                  // + (8q + 4 part) * SK_BST + 8 j
+    const int c_off = SK_A_TILE + SK_B_TILE + 2 * t;               // + q * 8
+
+    int slot = 0;
+    uint32_t round = 0;
+    int turn = 0;
+    for (int64_t tile = lo.tile; has_work && tile <= last_tile; ++tile) {
+        const int s_begin = (tile == lo.tile) ? lo.stage : 0;
+        const int s_end = (tile == hi.tile) ? hi.stage : n_stages;
+        const int ct = (int)(tile % prm.n_col_tiles);
+        int64_t rest = tile / prm.n_col_tiles;
+        const int yt = (int)(rest % prm.n_ytiles);
+        rest /= prm.n_ytiles;
+        const int64_t slow = rest % prm.n_slow;
+        const int64_t z = rest / prm.n_slow;
+
+        double acc[2][16][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        // compile-time variants of the stage: column groups rounded up to 4 (the B tile is zero beyond the mesh),
+        // row groups of this warp inside the mesh; variant = 2 * (jv4 - 1) + (ni - 1), 7 = the full tile, -1 = idle
+        int variant = 7;
+        if (PARTIAL) {
+            const int cols = (int)min((int64_t)SK_TN, prm.lc - (int64_t)ct * SK_TN);
+            const int rows = (int)min((int64_t)SK_TM, prm.ly - (int64_t)yt * SK_TM);
+            const int jv4 = (cols + 31) >> 5;
+            const int ni = (8 * warp < rows ? 1 : 0) + (8 * (warp + 8) < rows ? 1 : 0);
+            variant = ni > 0 ? 2 * (jv4 - 1) + (ni - 1) : -1;
+        }
+
+        for (int s = s_begin; s < s_end; ++s) {
+            if (pf_live) {
+                if (lane == 0 && warp == turn) {
+                    if (pf_round > 0) mbar_wait(&empty[pf_slot], (pf_round - 1) & 1);
+                    pf_issue();
+                }
+                pf_advance();
+            }
+            turn = (turn + 1) & (SK_WARPS - 1);
+            __syncwarp();
+            mbar_wait(&full[slot], round & 1);
+            const double *S = stage_base + slot * SK_STAGE_DOUBLES;
+            if (!PARTIAL || variant == 7) {
+                sk_stage<SCALE, 16, 2>(S, acc, a_off0, a_off1, b_off, c_off);
+            } else {
+                switch (variant) {       // warp-uniform
+                case 0: sk_stage<SCALE, 4, 1>(S, acc, a_off0, a_off1, b_off, c_off); break;
+                case 1: sk_stage<SCALE, 4, 2>(S, acc, a_off0, a_off1, b_off, c_off); break;
+                case 2: sk_stage<SCALE, 8, 1>(S, acc, a_off0, a_off1, b_off, c_off); break;
+                case 3: sk_stage<SCALE, 8, 2>(S, acc, a_off0, a_off1, b_off, c_off); break;
+                case 4: sk_stage<SCALE, 12, 1>(S, acc, a_off0, a_off1, b_off, c_off); break;
+                case 5: sk_stage<SCALE, 12, 2>(S, acc, a_off0, a_off1, b_off, c_off); break;
+                case 6: sk_stage<SCALE, 16, 1>(S, acc, a_off0, a_off1, b_off, c_off); break;
+                default: break;          // no row group of this warp inside the mesh
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+            if (++slot == SK_STAGES) { slot = 0; ++round; }
+        }
+
+        // ---- segment bookkeeping: an owned tile starts at stage 0 in this CTA ----
+        if (s_begin > 0) {
+            // leading, non-owned segment: hand the partial accumulators to the owner
+            double *dst = prm.slots + (int64_t)cta * (SK_TM * SK_TN) + tid;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    __stcg(dst + ((i * 16 + j) * 2 + 0) * SK_THREADS, acc[i][j][0]);
+                    __stcg(dst + ((i * 16 + j) * 2 + 1) * SK_THREADS, acc[i][j][1]);
+                }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) sk_st_release(prm.flags + cta, 1u);
+            continue;
+        }
+        if (s_end < n_stages) {
+            // owned tile that continues in the following CTA(s): add their partials in CTA order
+            for (int m = cta + 1; m < (int)gridDim.x; ++m) {
+                const SkBound bm = prm.bnd[m], bn = prm.bnd[m + 1];
+                if (bm.tile > tile) break;                                     // CTA m starts after this tile
+                const bool empty_share = (bm.tile == bn.tile && bm.stage == bn.stage);
+                if (!empty_share) {
+                    if (tid == 0) {
+                        while (sk_ld_acquire(prm.flags + m) == 0u) __nanosleep(64);
+                    }
+                    __syncthreads();
+                    const double *src = prm.slots + (int64_t)m * (SK_TM * SK_TN) + tid;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            acc[i][j][0] += __ldcg(src + ((i * 16 + j) * 2 + 0) * SK_THREADS);
+                            acc[i][j][1] += __ldcg(src + ((i * 16 + j) * 2 + 1) * SK_THREADS);
+                        }
+                }
+                if (bn.tile > tile) break;                                     // CTA m finished the tile
+            }
+        }
+
+        // ---- epilogue: thread holds C[g][2t], C[g][2t+1] of every 8x8 tile ----
+        const int comp = (int)(z % prm.ncomp);
+        double *out = prm.out + z * prm.out_fstride;
+        const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        const int64_t col0 = (int64_t)ct * SK_TN;
+        const int64_t iy0 = (int64_t)yt * SK_TM;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int64_t iy = iy0 + 8 * (warp + 8 * i) + g;
+            if (iy >= prm.ly) continue;
+            const int64_t row = ((slow / prm.n_in) * prm.ly + iy) * prm.n_in + slow % prm.n_in;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int64_t col = col0 + j * 8 + 2 * t;
+                const int64_t idx = row * prm.lc + col;
+                double *dst = out + idx;
+                if (prm.epi.on) {
+                    if (col < prm.lc) acc[i][j][0] = epi_apply(prm.epi, acc[i][j][0], comp, idx);
+                    if (col + 1 < prm.lc) acc[i][j][1] = epi_apply(prm.epi, acc[i][j][1], comp, idx + 1);
+                }
+                if (vec2 && col + 1 < prm.lc) {
+                    *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+                } else {
+                    if (col < prm.lc) dst[0] = acc[i][j][0];
+                    if (col + 1 < prm.lc) dst[1] = acc[i][j][1];
+                }
+            }
+        }
+    }
+}
+
+inline int sk_launch(const SkParams &prm, int grid, bool scale, bool partial, cudaStream_t st)
+{
+    static std::atomic<uint64_t> attr_set{0};
+    if (first_launch_on_device(attr_set)) {
+#define GSB_SK_ATTR(K)                                                                                               \
+        GSB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM_BYTES));
+        GSB_SK_ATTR((sk_contract_kernel<false, false>)) GSB_SK_ATTR((sk_contract_kernel<false, true>))
+        GSB_SK_ATTR((sk_contract_kernel<true, false>)) GSB_SK_ATTR((sk_contract_kernel<true, true>))
+#undef GSB_SK_ATTR
+    }
+    if (scale) {
+        if (partial) sk_contract_kernel<true, true><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
+        else sk_contract_kernel<true, false><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
+    } else {
+        if (partial) sk_contract_kernel<false, true><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
+        else sk_contract_kernel<false, false><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
+    }
+    g_launches.fetch_add(1);
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+}  // namespace gsb

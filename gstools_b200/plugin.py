@@ -565,7 +565,13 @@ def _build_cond_call(r):
         if krige_save[1]:
             krige.post_field(backend.to_host(dev["krige_var"]), krige_name[1], False, True)
         if krige_save[0]:
-            krige.post_field(backend.to_host(dev["field"]), krige_name[0], post_process, True)
+            # the post-processed kriging field is a pure function of the constants in `terms`: the reference's
+            # arithmetic runs once (field/base.py:325-336), the result stays on the device next to the raw one
+            pkey = (bool(post_process), tuple(terms))
+            if dev.get("pp_key") != pkey:
+                done = krige.post_field(backend.to_host(dev["field"]), krige_name[0], post_process, False)
+                dev["pp_field"], dev["pp_key"] = backend.to_device(done), pkey
+            krige.post_field(backend.to_host(dev["pp_field"]), krige_name[0], False, True)
         # sqrt(var/N) * summed + 0.0 (generator.py:269-270, add_nugget=False); var_scale * rawfield;
         # rawkrige + ...; + nugget (int 0); then post_field's constant mean and trend
         epi = backend.make_epilogue(np.sqrt(model.var / generator._mode_no), [0.0])

@@ -335,6 +335,18 @@ int gsb_release_memory(int device);
 int64_t gsb_get_counter(const char *name);
 
 /*
+ * Introspection of the structured path's work split (host only, no device needed): the separable contraction
+ * is ONE persistent launch whose CTAs take equal-cost contiguous shares of the (output tile, pipeline stage)
+ * iteration space ("stream-K", gstools_b200/csrc/gsb_sepk.cuh).  For the tiles [tile_begin, tile_end) of a mesh
+ * with `ly` tile-axis rows and `lc` columns (tile = ((field * n_slow + slow) * ceil(ly/128) + row tile) *
+ * ceil(lc/128) + column tile) and `n_stages` stages per tile, writes the share boundaries of `max_grid` CTAs:
+ * CTA c works on (tiles[c], stages[c]) inclusive .. (tiles[c+1], stages[c+1]) exclusive.  tiles / stages hold
+ * max_grid + 1 entries; *grid receives the number of CTAs actually used.
+ */
+int gsb_streamk_plan(int64_t tile_begin, int64_t tile_end, int64_t ly, int64_t lc, int n_stages,
+                     int max_grid, int64_t *tiles, int32_t *stages, int *grid);
+
+/*
  * Device-side timing of the dominant kernels (roofline evidence).  While the option
  * "time_kernels" is 1, CUDA events are recorded on the launch stream around every direct /
  * separable kernel launch.  gsb_kernel_times() waits for them, returns the summed duration and

@@ -172,3 +172,59 @@ def test_beyond_the_configs_1024cubed_index_arithmetic(gsb, oracle_mod):
     wantv = oracle_mod.summate_incompr(cfg["cov"][:, :64], cfg["z1"][:64], cfg["z2"][:64],
                                        bc.grid_points([ax[0], ax[1], ax[2][:768]], None, idx))
     assert np.max(np.abs(gotv - wantv)) * np.sqrt(1.0 / 64) <= TOL
+
+
+def test_config2_faces_rows_and_full_grid(gsb, oracle_mod):
+    """SURVEY.md 8(d) "Parity check" for C2: all six faces and a random 1 % of the rows of the 512^3 field
+    against the CPU oracle, and the FULL grid once against the direct kernel (independent arithmetic:
+    per-point polynomial sincos instead of per-axis tables)."""
+    import torch
+
+    cfg = bc.config2(512)
+    edge = 512
+    dev = torch.device("cuda:0")
+    tc, t1, t2 = (torch.tensor(cfg[k], device=dev) for k in ("cov", "z1", "z2"))
+    axes = [torch.tensor(a, device=dev) for a in cfg["axes"]]
+    out = gsb.summate_structured(tc, t1, t2, axes)
+    scale = np.sqrt(1.0 / 1000)
+    ax = cfg["axes"]
+    worst = 0.0
+
+    def oracle_at(i0, i1, i2):
+        pos = np.stack([ax[0][i0], ax[1][i1], ax[2][i2]]).astype(np.float64)
+        return oracle_mod.summate(cfg["cov"], cfg["z1"], cfg["z2"], pos)
+
+    # six faces, 512 x 512 nodes each
+    a, b = np.meshgrid(np.arange(edge), np.arange(edge), indexing="ij")
+    a, b = a.reshape(-1), b.reshape(-1)
+    for axis in range(3):
+        for side in (0, edge - 1):
+            ijk = [a, b]
+            ijk.insert(axis, np.full(a.size, side))
+            got = out[tuple(torch.tensor(v, device=dev) for v in ijk)].cpu().numpy()
+            d = float(np.max(np.abs(got - oracle_at(*ijk)))) * scale
+            assert d <= TOL, (axis, side, d)
+            worst = max(worst, d)
+    # a random 1 % of the 262 144 rows (a row = all 512 nodes along the last axis)
+    rs = np.random.RandomState(2)
+    rows = np.unique(rs.randint(0, edge * edge, edge * edge // 100))
+    i0, i1 = np.repeat(rows // edge, edge), np.repeat(rows % edge, edge)
+    i2 = np.tile(np.arange(edge), rows.size)
+    got = out.reshape(edge * edge, edge)[torch.tensor(rows, device=dev)].reshape(-1).cpu().numpy()
+    d = float(np.max(np.abs(got - oracle_at(i0, i1, i2)))) * scale
+    assert d <= TOL, d
+    worst = max(worst, d)
+    # the full grid against the direct kernel, slab by slab (134 217 728 nodes)
+    worst_direct = 0.0
+    yy, zz = torch.meshgrid(axes[1], axes[2], indexing="ij")
+    yy, zz = yy.reshape(-1), zz.reshape(-1)
+    planes = 32
+    for x0 in range(0, edge, planes):
+        xs = axes[0][x0:x0 + planes]
+        pos = torch.stack([xs.repeat_interleave(edge * edge), yy.repeat(planes), zz.repeat(planes)])
+        direct = gsb.summate(tc, t1, t2, pos).reshape(planes, edge, edge)
+        worst_direct = max(worst_direct, float((direct - out[x0:x0 + planes]).abs().max()) * scale)
+        del pos, direct
+    assert worst_direct <= TOL, worst_direct
+    print(f"C2 512^3: faces + 1% rows vs oracle max|d|/sqrt(var) = {worst:.2e}; "
+          f"full grid vs direct kernel = {worst_direct:.2e}")

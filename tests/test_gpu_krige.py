@@ -305,3 +305,22 @@ def test_krige_evaluate_device_tensors(gsb):
     f_only = gsb.krige_evaluate(spec, t(mat), t(cond), t(cond_pos), pos=t(pos), tail_rows=t(tail), return_var=False)
     assert np.array_equal(f_only.cpu().numpy(), gsb.krige_evaluate(spec, mat, cond, cond_pos, pos=pos, tail_rows=tail,
                                                                    return_var=False))
+
+
+def test_field_only_evaluation_of_a_large_system(gsb, oracle_mod):
+    """Krige.__call__(return_var=False) with more conditioning points than the field-only kernel
+    could stage in shared memory at once (C*D + K doubles > 200 KB) used to fail; the rows are now staged in
+    passes.  7000 conditioning points in 3-D, synthetic (well-scaled) weights."""
+    rs = np.random.RandomState(4)
+    C, D, n = 7000, 3, 3000
+    K = C + 1
+    cond_pos = rs.uniform(0, 50, (D, C))
+    pos = rs.uniform(0, 50, (D, n))
+    mat = rs.normal(size=(K, K)) / K
+    cond = rs.normal(size=K)
+    spec = dict(kind="Exponential", var=1.3, len_rescaled=7.0)
+    f = gsb.krige_evaluate(spec, mat, cond, cond_pos, pos=pos, return_var=False)
+    kv = oracle_mod.krige_vecs_np("Exponential", 1.3, 7.0, 1.3, cond_pos, pos)
+    want = oracle_mod.calc_field_krige(mat, kv, cond)
+    s = np.abs(cond) @ (np.abs(mat) @ np.abs(kv))
+    assert np.all(np.abs(f - want) <= np.maximum(1e-9, 8 * K * EPS * s))

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Meshes whose last axis is not a multiple of 128: contraction with and without partial-tile skipping."""
+"""Meshes off the 512^3 sweet spot: first-generation contraction (auto: pre-generated A / scaled) against the
+second generation (stream-K, gsb_sepk.cuh).  Prints Tpair/s and the fraction of the FP64 peak (2 DFMA per pair)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,19 +9,32 @@ import gstools_b200 as gsb
 dev = torch.device("cuda:0")
 cfg = bc.config2(512)
 tc, t1, t2 = (torch.tensor(cfg[k], device=dev) for k in ("cov", "z1", "z2"))
-def timeit(fn, reps=7):
-    fn(); torch.cuda.synchronize(); ts = []
+peak = gsb.measure_fp64_peak(0, 0, 0.3)
+def timeit(fn, reps=9):
+    fn(); fn(); torch.cuda.synchronize(); ts = []
     for _ in range(reps):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return float(np.median(ts))
-for shape in [(512, 512, 512), (200, 200, 200), (300, 300, 300), (256, 256, 130), (100, 100, 100), (128, 128, 128), (400, 400, 72)]:
+shapes = [(512, 512, 512), (64, 512, 512), (200, 200, 200), (300, 300, 300), (256, 256, 130), (100, 100, 100),
+          (128, 128, 128), (400, 400, 72), (512, 16, 512), (2048, 2048), (1000, 1000, 10)]
+if len(sys.argv) > 1:
+    shapes = [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
+print(f"DFMA peak {peak / 1e12:.2f} TFMA/s")
+for shape in shapes:
     axes = [torch.arange(float(s), device=dev, dtype=torch.float64) for s in shape]
+    c = tc[:len(shape)].contiguous()
     pairs = np.prod(shape) * 1000
     res = []
-    for name, v in (("full-tile kernel", 0), ("partial-tile kernel", 1)):
-        gsb.set_option("partial_tiles", v)
-        t = timeit(lambda: gsb.summate_structured(tc, t1, t2, axes))
-        res.append(f"{name} {t:.3f} ms ({pairs / t / 1e9:.2f} Tpair/s)")
-    gsb.set_option("partial_tiles", 1)
-    print(shape, " | ".join(res))
+    for name, v in (("gen1", 0), ("gen2 stream-K", 3)):
+        gsb.set_option("sep_path", v)
+        gsb.set_option("force_path", 2)
+        t = timeit(lambda: gsb.summate_structured(c, t1, t2, axes))
+        gsb.set_option("time_kernels", 1); gsb.kernel_times()
+        for _ in range(5): gsb.summate_structured(c, t1, t2, axes)
+        torch.cuda.synchronize(); km, kn = gsb.kernel_times(); gsb.set_option("time_kernels", 0)
+        res.append(f"{name} {t:.3f} ms ({km / 5:.3f} in {kn // 5} contraction launches) {pairs / t / 1e9:.2f} Tpair/s "
+                   f"{2 * pairs / (t * 1e-3) / peak * 100:.1f}% (kernel {2 * pairs / (km / 5 * 1e-3) / peak * 100:.1f}%)")
+    gsb.set_option("sep_path", 0)
+    gsb.set_option("force_path", 0)
+    print("x".join(str(v) for v in shape), " | ".join(res), flush=True)
