@@ -19,17 +19,12 @@
 namespace gsb {
 
 std::atomic<int64_t> g_launches{0};
-static std::atomic<int64_t> g_opt_structured_min_tiles{64};
+static std::atomic<int64_t> g_opt_structured_min_tiles{0};   // meshes with fewer 128 x 128 tiles go to the direct kernel
 static std::atomic<int64_t> g_opt_force_path{0};
 static std::atomic<int64_t> g_opt_host_chunk_points{1 << 22};
-static std::atomic<int64_t> g_opt_scratch_mb{3072};  // A-operand scratch budget (two buffers)
-static std::atomic<int64_t> g_opt_min_chunks{4};     // so that A generation overlaps the contraction
-static std::atomic<int64_t> g_opt_chunk_growth_pct{140};
-static std::atomic<int64_t> g_opt_sep_path{0};      // 0 auto, 1 pre-generated A (agen), 2 scaled in the consumer
-static std::atomic<int64_t> g_cnt_scaled{0};
+static std::atomic<int64_t> g_opt_scratch_mb{3072};  // scratch budget of the kriging right-hand sides (two buffers)
 static std::atomic<int64_t> g_opt_fold_axes{1};     // 0 never, 1 when it improves the tile utilisation, 2 whenever it fits
 static std::atomic<int64_t> g_cnt_folded{0};
-static std::atomic<int64_t> g_opt_partial_tiles{1};  // 0: full-tile contraction kernel even for partial column tiles
 static std::atomic<int64_t> g_opt_direct_cfg{-1};   // -1 auto, else force P = 1 / 2 / 8 points per thread (0 / 1 / 2)
 static std::atomic<int64_t> g_cnt_direct{0}, g_cnt_separable{0};
 // optional device-side timing of the dominant kernels (bench.py roofline): events recorded on the
@@ -385,7 +380,7 @@ struct SkLayout {
 // (one sincos and 24 bytes per entry).  E.g. 100^3: the middle axis alone (78 % of a tile) beats folding both row
 // axes (99 %, but a 237 MB table for a 8 MB field); 512 x 16 x 512: axis 0 alone; 40 x 50 x 130: both folded.
 static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int64_t n_batch, int ncomp, bool fold_cols,
-                                 int sm_count)
+                                 int sm_count, double *est_seconds = nullptr)
 {
     const int dim = mesh.dim;
     SkLayout L;
@@ -395,9 +390,8 @@ static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int6
     const int n_row = dim - L.n_col_axes;                   // >= 1
     const int64_t n_stages = n_modes_pad / SK_KC;
     const int64_t cap = g_opt_sk_table_mb.load() << 20;
-    int64_t n_rows = 1, colg = 0;
+    int64_t n_rows = 1;
     for (int t = 0; t < n_row; ++t) n_rows *= mesh.len[t];
-    for (int ct = 0; ct < L.n_col_tiles; ++ct) colg += sk_colg(L.lc, ct);
     double best = 1e300;
     int best_a = n_row - 1, best_b = n_row;
     for (int a = 0; a < n_row; ++a) {
@@ -408,10 +402,12 @@ static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int6
             const int64_t bytes = n_batch * n_yt * n_stages * SK_A_TILE * (int64_t)sizeof(double);
             const bool single = (b == a + 1);
             if (n_yt > (1 << 20) || (!single && bytes > cap)) break;
-            int64_t rq = (n_yt - 1) * 4 + sk_rowq(P, (int)(n_yt - 1));
-            const double units = (double)(n_rows / P) * (double)rq * (double)colg * (double)n_stages *
-                                 (double)(n_batch * ncomp);
-            const bool no_slow = (P == n_rows);
+            // cost of one (field, slow index) period: full row tiles + the last one, over all column tiles
+            int64_t per = 0;
+            for (int ct = 0; ct < L.n_col_tiles; ++ct)
+                per += (n_yt - 1) * sk_tile_cost(P, L.lc, 0, ct) + sk_tile_cost(P, L.lc, (int)(n_yt - 1), ct);
+            const double units = (double)(n_rows / P) * (double)per * (double)n_stages * (double)(n_batch * ncomp);
+            const bool no_slow = (b - a == n_row);
             const double t_contract = units * 64.0 / ((double)sm_count * 1.9e9 * (no_slow ? 0.96 : 0.93));
             const double t_table = (double)bytes / 1.0e12;
             // ties: prefer the trailing axes (rows of a tile then are neighbours in memory)
@@ -428,11 +424,15 @@ static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int6
     for (int t = best_b; t < n_row; ++t) L.n_in *= mesh.len[t];
     L.n_slow = n_rows / L.ly;
     L.n_ytiles = (int)((L.ly + SK_TM - 1) / SK_TM);
+    if (est_seconds) {
+        const double b_bytes = (double)n_batch * ncomp * L.n_col_tiles * (double)n_stages * SK_B_TILE * sizeof(double);
+        *est_seconds = best + b_bytes / 1.0e12 + 8e-6;      // + two launches
+    }
     return L;
 }
 
 static int sk_on_device(const double *d_cov, const double *d_z1, const double *d_z2, const double *d_sf,
-                        const double *d_axes, const MeshInfo &mesh, bool fold_cols, int64_t n_modes, int64_t n_batch,
+                        const double *d_axes, const MeshInfo &mesh, const SkLayout &L, int64_t n_modes, int64_t n_batch,
                         bool vec, const Epi &epi, double *d_out, double *h_out, DeviceState &dev, cudaStream_t st)
 {
     const int dim = mesh.dim;
@@ -441,22 +441,33 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
     Scratch scr(st);
     const int n_modes_pad = (int)((n_modes + SK_KC - 1) / SK_KC * SK_KC);
     const int n_stages = n_modes_pad / SK_KC;
-    const SkLayout L = sk_choose_layout(mesh, n_modes_pad, n_batch, ncomp, fold_cols, dev.sm_count);
     const bool scale = (L.n_prefix + L.n_inner) > 0;     // slow axes exist (even of length 1: their phase counts)
 
     const int64_t gopt = g_opt_sk_grid.load();
     const int max_grid = gopt > 0 ? (int)std::min<int64_t>(gopt, SK_MAX_GRID) : std::min(dev.sm_count, SK_MAX_GRID);
     // One launch for everything on the device route.  The host route cuts the (field, slow index) units into
-    // up to 8 pieces of at least two "waves" so that the D2H copy of a piece overlaps the contraction of the next;
-    // unit u = z * n_slow + slow covers the output elements [u, u + 1) * ly * lc, so a piece is ONE contiguous copy.
+    // pieces so that the D2H copy of a piece overlaps the contraction of the next.  PCIe is the slower side (the
+    // 512^3 field: 15.6 ms of contraction, 20 ms of copy at 53 GB/s), so the first piece is small -- the copy
+    // engine starts early -- and the pieces grow by 1.25x, the ratio at which the next contraction still finishes
+    // before the previous copy does.  Unit u = z * n_slow + slow covers the output elements [u, u + 1) * ly * lc,
+    // so a piece is ONE contiguous copy (with inner slow axes a unit is not contiguous: pieces then are whole fields).
     const int64_t units = n_batch * ncomp * L.n_slow;
     const int64_t tiles_per_unit = (int64_t)L.n_ytiles * L.n_col_tiles;
-    const int64_t tiles_all = units * tiles_per_unit;
-    // (with inner slow axes a unit is not contiguous: pieces then are whole fields)
     const int64_t cut_units = L.n_in == 1 ? units : n_batch * ncomp;
     const int64_t unit_mult = units / cut_units;
-    const int64_t pieces = h_out ? std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, cut_units),
-                                                                            tiles_all / (2 * (int64_t)max_grid))) : 1;
+    std::vector<int64_t> cuts{0};      // piece k = cut units [cuts[k], cuts[k+1])
+    if (h_out) {
+        const int64_t tiles_per_cut = tiles_per_unit * unit_mult;
+        const int64_t min_cut = std::max<int64_t>(1, ((int64_t)max_grid + tiles_per_cut - 1) / tiles_per_cut);   // >= one wave
+        double want = std::max<double>((double)min_cut, (double)cut_units / 64.0);
+        while (cuts.back() < cut_units && cuts.size() < 32) {
+            cuts.push_back(std::min<int64_t>(cut_units, cuts.back() + std::max<int64_t>(min_cut, (int64_t)want)));
+            want *= 1.25;
+        }
+    }
+    cuts.back() = cut_units;
+    if (cuts.size() == 1) cuts.push_back(cut_units);
+    const int64_t pieces = (int64_t)cuts.size() - 1;
     SkTableParams tp;
     std::memset(&tp, 0, sizeof tp);
     tp.cov = d_cov; tp.z1 = d_z1; tp.z2 = d_z2; tp.sf = d_sf; tp.axes = d_axes;
@@ -479,11 +490,21 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
     tp.ncomp = ncomp;
     tp.n_ytiles = L.n_ytiles;
     tp.n_col_tiles = L.n_col_tiles;
-    GSB_TRY(scr.alloc(&tp.ttab, (size_t)n_batch * L.n_ytiles * n_stages * SK_A_TILE));
-    GSB_TRY(scr.alloc(&tp.btile, (size_t)n_batch * ncomp * L.n_col_tiles * n_stages * SK_B_TILE));
-    if (scale) GSB_TRY(scr.alloc(&tp.ctab, (size_t)n_batch * L.n_slow * n_modes_pad));
+    // one scratch block per call (every stream-ordered allocation costs host time, which is what a small mesh sees)
+    auto pad16 = [](size_t doubles) { return (doubles + 15) / 16 * 16; };
+    const size_t n_t = pad16((size_t)n_batch * L.n_ytiles * n_stages * SK_A_TILE);
+    const size_t n_b = pad16((size_t)n_batch * ncomp * L.n_col_tiles * n_stages * SK_B_TILE);
+    const size_t n_c = scale ? pad16((size_t)n_batch * L.n_slow * n_modes_pad * 2) : 0;
+    const size_t n_s = pad16((size_t)max_grid * SK_TM * SK_TN);
     tp.n_flags = (int)(pieces * max_grid);
-    GSB_TRY(scr.alloc(&tp.flags, (size_t)tp.n_flags));
+    const size_t n_f = pad16(((size_t)tp.n_flags + 1) / 2);
+    double *block = nullptr;
+    GSB_TRY(scr.alloc(&block, n_t + n_b + n_c + n_s + n_f));
+    tp.ttab = block;
+    tp.btile = block + n_t;
+    tp.ctab = scale ? reinterpret_cast<double2 *>(block + n_t + n_b) : nullptr;
+    double *slots = block + n_t + n_b + n_c;
+    tp.flags = reinterpret_cast<unsigned *>(block + n_t + n_b + n_c + n_s);
     {
         const int64_t max_width = std::max<int64_t>(std::max<int64_t>((int64_t)L.n_ytiles * SK_TM,
                                                                        (int64_t)L.n_col_tiles * SK_TN),
@@ -512,11 +533,11 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
     sp.out_fstride = mesh.n;
     sp.epi = epi;
     const bool partial = (L.ly % SK_TM) != 0 || (L.lc % SK_TN) != 0;
-    GSB_TRY(scr.alloc(&sp.slots, (size_t)max_grid * SK_TM * SK_TN));
+    sp.slots = slots;
     unsigned *d_flags = tp.flags;
     std::vector<SkBound> bnd;
     for (int64_t k = 0; k < pieces; ++k) {
-        const int64_t u0 = cut_units * k / pieces * unit_mult, u1 = cut_units * (k + 1) / pieces * unit_mult;
+        const int64_t u0 = cuts[(size_t)k] * unit_mult, u1 = cuts[(size_t)k + 1] * unit_mult;
         if (u1 == u0) continue;
         const int grid = sk_plan(u0 * tiles_per_unit, u1 * tiles_per_unit, L.n_ytiles, L.n_col_tiles, n_stages, L.ly,
                                  L.lc, max_grid, bnd);
@@ -545,10 +566,9 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
 }
 
 // everything on device: d_cov (B,dim,N), d_z1/d_z2 (B,N), d_axes, d_out (B,ncomp,n).
-// `h_out`: when non-null, finished chunks are copied to this host buffer as they complete.
+// `h_out`: when non-null, finished pieces are copied to this host buffer as they complete.
 // `st` is the caller's stream: all work is ordered after what `st` holds on entry, and `st` waits
-// for all of it before this function returns (the library's two contraction streams are used
-// in between so that the A generation of one chunk overlaps the contraction of the other).
+// for all of it before this function returns.
 static int structured_on_device(const double *d_cov, const double *d_z1, const double *d_z2,
                                 const double *d_sf, const double *d_axes, const MeshInfo &mesh, int64_t n_modes,
                                 int64_t n_batch, bool vec, const Epi &epi, double *d_out, double *h_out,
@@ -558,47 +578,44 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
     const int ncomp = vec ? dim : 1;
     Scratch scr(st);
     const int64_t force = g_opt_force_path.load();
-    // Virtual mesh of the separable path.  Output tiles are 128 wide along the last (contiguous) axis; a
-    // thin mesh (1000 x 1000 x 10: reservoir layers) would use 10 of the 128 columns of every tile.  The
-    // phase still splits if the last TWO axes are treated as one axis of len_y * len_z entries (its table
-    // holds exp(i (k'_y y + k'_z z))), and C order makes that folded axis contiguous in the output.
-    MeshInfo vm = mesh;
-    if (dim >= 3 && g_opt_fold_axes.load() != 0) {
-        auto util = [](int64_t rows, int64_t cols) {
-            const double ru = (double)rows / (double)((rows + SEP_TM - 1) / SEP_TM * SEP_TM);
-            const double cu = (double)cols / (double)((cols + SEP_TN - 1) / SEP_TN * SEP_TN);
-            return ru * cu;
-        };
-        const int64_t wc2 = mesh.len[dim - 2] * mesh.len[dim - 1];
-        const int64_t n_pad = (n_modes + SEP_KC - 1) / SEP_KC * SEP_KC;
-        const bool fits = wc2 > 0 && wc2 * n_pad * ncomp * n_batch <= ((int64_t)1 << 28);   // <= 4 GiB of tables
-        const bool better = util(mesh.n / std::max<int64_t>(wc2, 1), wc2) > 1.15 * util(mesh.n_rows, mesh.len[dim - 1]);
-        if (fits && (better || g_opt_fold_axes.load() == 2)) {
-            vm.dim = dim - 1;
-            vm.len[dim - 2] = wc2;
-            vm.n_rows = mesh.n / wc2;
+    // Which path?  Estimated times from the same cost model that balances the stream-K shares:
+    //   separable  contraction of the padded tiles + table building, with the last axis alone as column axis or
+    //              -- thin meshes (1000 x 1000 x 10: reservoir layers) -- the last TWO axes folded into one
+    //              column axis of len_y * len_z entries (its table holds exp(i (k'_y y + k'_z z)); C order
+    //              makes the folded axis contiguous in the output);
+    //   direct     expand the mesh on the device, D + 13 FP64 instructions per pair at ~86 % of the pipe.
+    const int64_t n_modes_pad = (n_modes + SK_KC - 1) / SK_KC * SK_KC;
+    bool separable = false;
+    SkLayout layout;
+    std::memset(&layout, 0, sizeof layout);
+    if (dim >= 2 && n_modes > 0) {
+        double t_best = 1e300;
+        const int64_t fold_opt = g_opt_fold_axes.load();
+        for (int fold = 0; fold < 2; ++fold) {
+            if (fold == 1) {
+                const int64_t wc2 = mesh.len[dim - 2] * mesh.len[dim - 1];
+                const bool fits = dim >= 3 && wc2 * n_modes_pad * ncomp * n_batch <= ((int64_t)1 << 28);   // <= 4 GiB
+                if (!fits || fold_opt == 0) continue;
+            } else if (fold_opt == 2 && dim >= 3 &&
+                       mesh.len[dim - 2] * mesh.len[dim - 1] * n_modes_pad * ncomp * n_batch <= ((int64_t)1 << 28)) {
+                continue;     // forced folding
+            }
+            double t = 0.0;
+            const SkLayout cand = sk_choose_layout(mesh, n_modes_pad, n_batch, ncomp, fold == 1, dev.sm_count, &t);
+            if (t < t_best) { t_best = t; layout = cand; }
         }
+        const double instr = (double)(dim + 13 + (vec ? dim : 0));
+        const double t_direct = (double)mesh.n * (double)n_modes * (double)n_batch * instr /
+                                    ((double)dev.sm_count * 64.0 * 1.9e9 * 0.86) + 12e-6 * (double)n_batch;
+        separable = t_best < t_direct;
+        const int64_t tiles = ((mesh.n_rows + SK_TM - 1) / SK_TM) * ((mesh.len[dim - 1] + SK_TN - 1) / SK_TN) * n_batch * ncomp;
+        if (tiles < g_opt_structured_min_tiles.load()) separable = false;
+        if (force == 1) separable = false;
+        if (force == 2) separable = true;
     }
-    const bool folded = vm.dim != dim;
-    const int vdim = vm.dim;
-    const int64_t lc = vm.len[vdim - 1];
-    const int64_t n_row_tiles_total = (vm.n_rows + SEP_TM - 1) / SEP_TM;
-    const int n_col_tiles = (int)((lc + SEP_TN - 1) / SEP_TN);
-    const int64_t tiles = n_row_tiles_total * n_col_tiles * n_batch * ncomp;
-    bool separable = dim >= 2 && n_modes > 0 && tiles >= g_opt_structured_min_tiles.load();
-    {
-        // Tiles are 128 x 128: when the (virtual) mesh fills only a small part of them -- e.g. a 2-D mesh with
-        // a very short last axis, which cannot be folded -- the direct kernel (D + 13 instructions per pair
-        // at ~86 % of the pipe) beats the contraction (2 per pair at ~94 %, but on padded tiles).
-        const double ru = (double)vm.n_rows / (double)(n_row_tiles_total * SEP_TM);
-        const double cu = (double)lc / (double)((int64_t)n_col_tiles * SEP_TN);
-        if (ru * cu * (double)(dim + 13) / 0.86 < 2.0 / 0.94) separable = false;
-    }
-    if (force == 1) separable = false;
-    if (force == 2 && dim >= 2 && n_modes > 0) separable = true;
 
     if (!separable) {
-        // small mesh: expand on the device, then the direct kernel per batch entry
+        // expand on the device, then the direct kernel per batch entry
         ExpandParams ep;
         double *d_pos = nullptr;
         GSB_TRY(scr.alloc(&d_pos, (size_t)dim * mesh.n));
@@ -630,305 +647,20 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
         return GSB_OK;
     }
 
-    if (g_opt_sep_path.load() == 3) {
-        GSB_TRY(sk_on_device(d_cov, d_z1, d_z2, d_sf, d_axes, mesh, folded, n_modes, n_batch, vec, epi, d_out, h_out, dev, st));
-        g_cnt_separable.fetch_add(1);
-        if (folded) g_cnt_folded.fetch_add(1);
-        return GSB_OK;
-    }
-    // ---- separable path: tables -> (A generation || contraction) per chunk ----
-    const int nra = vdim - 1;
-    const int n_modes_pad = (int)((n_modes + SEP_KC - 1) / SEP_KC * SEP_KC);
-    const int n_stages = n_modes_pad / SEP_KC;
-    TableParams tp;
-    std::memset(&tp, 0, sizeof tp);
-    tp.cov = d_cov;
-    tp.z1 = d_z1;
-    tp.z2 = d_z2;
-    tp.sf = d_sf;
-    tp.axes = d_axes;
-    std::memcpy(tp.matrix, mesh.matrix, sizeof tp.matrix);
-    tp.dim = dim;
-    tp.n_axes = vdim;
-    tp.fold_len = folded ? mesh.len[dim - 1] : 0;
-    tp.fold_off = folded ? mesh.off[dim - 1] : 0;
-    tp.n_modes = n_modes;
-    tp.n_modes_pad = n_modes_pad;
-    tp.ncomp = ncomp;
-    tp.n_col_tiles = n_col_tiles;
-    // Which contraction variant?  "scaled" (no A generation, ~89 % of peak whatever the shape, rows
-    // padded to 128 per slow index) wins when an A tile would feed only one or two output tiles;
-    // pre-generated A (~94 %) wins otherwise.  2-D meshes have no slow axis: A is the table itself.
-    const int64_t ly = vm.len[vdim - 2];
-    const int n_ytiles = (int)((ly + SEP_TM - 1) / SEP_TM);
-    const int64_t n_slow = vm.n_rows / ly;
-    bool scaled = false;
-    if (nra >= 2) {
-        const int64_t tpu = (int64_t)n_col_tiles * ncomp;
-        const double eff_agen = tpu >= 4 ? 0.93 : (tpu == 3 ? 0.90 : (tpu == 2 ? 0.80 : 0.72));
-        const double eff_scaled = 0.89 * (double)ly / ((double)n_ytiles * SEP_TM);
-        scaled = eff_scaled > eff_agen;
-        const int64_t sp = g_opt_sep_path.load();
-        if (sp == 1) scaled = false;
-        if (sp == 2) scaled = true;
-    }
-    int64_t max_width = (int64_t)n_col_tiles * SEP_TN;
-    if (scaled) {
-        tp.n_ytiles = n_ytiles;
-        GSB_TRY(scr.alloc(&tp.ytab, (size_t)n_batch * n_ytiles * n_stages * SEP_A_TILE));
-        max_width = std::max<int64_t>(max_width, (int64_t)n_ytiles * SEP_TM);
-    }
-    for (int t = 0; t < vdim; ++t) {
-        tp.axis_off[t] = mesh.off[t];
-        tp.axis_len[t] = vm.len[t];
-        if (t < nra) {
-            tp.erow_bstride[t] = vm.len[t] * n_modes_pad;
-            GSB_TRY(scr.alloc(&tp.erow[t], (size_t)n_batch * tp.erow_bstride[t]));
-            max_width = std::max(max_width, vm.len[t]);
-        }
-    }
-    GSB_TRY(scr.alloc(&tp.btile, (size_t)n_batch * ncomp * n_col_tiles * n_stages * SEP_B_TILE));
-    {
-        if (n_batch > 65535) return fail(GSB_ERR_ARGUMENT, "n_batch too large");
-        const int64_t work = max_width * n_modes_pad;
-        dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 4096), (unsigned)vdim, (unsigned)n_batch);
-        build_tables_kernel<<<grid, 256, 0, st>>>(tp);
-        g_launches.fetch_add(1);
-        GSB_CUDA(cudaGetLastError());
-    }
-
-    if (scaled) {
-        CtabParams ctp;
-        std::memset(&ctp, 0, sizeof ctp);
-        ctp.n_slow_axes = nra - 1;
-        for (int t = 0; t < nra - 1; ++t) {
-            ctp.erow[t] = tp.erow[t];
-            ctp.erow_bstride[t] = tp.erow_bstride[t];
-            ctp.row_len[t] = vm.len[t];
-        }
-        ctp.n_slow = n_slow;
-        ctp.n_modes_pad = n_modes_pad;
-        GSB_TRY(scr.alloc(&ctp.ctab, (size_t)n_batch * n_slow * n_modes_pad));
-        {
-            const int64_t work = n_slow * n_modes_pad;
-            dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 4096), 1, (unsigned)n_batch);
-            ctab_kernel<<<grid, 256, 0, st>>>(ctp);
-            g_launches.fetch_add(1);
-            GSB_CUDA(cudaGetLastError());
-        }
-        ContractParams cp;
-        std::memset(&cp, 0, sizeof cp);
-        cp.btile = tp.btile;
-        cp.n_col_tiles = n_col_tiles;
-        cp.n_stages = n_stages;
-        cp.ncomp = ncomp;
-        cp.n_rows = vm.n_rows;
-        cp.lc = lc;
-        cp.out = d_out;
-        cp.out_fstride = mesh.n;
-        cp.epi = epi;
-        cp.no_partial = g_opt_partial_tiles.load() ? 0 : 1;
-        cp.ytab = tp.ytab;
-        cp.ctab = ctp.ctab;
-        cp.n_ytiles = n_ytiles;
-        cp.n_slow = n_slow;
-        cp.ly = ly;
-        cp.n_modes_pad = n_modes_pad;
-        // One launch for everything on the device route.  The host route splits the work into ~8
-        // pieces (groups of fields, or ranges of slow indices of a single field) so that the D2H
-        // copy of one piece overlaps the contraction of the next.
-        if (n_slow * n_ytiles > 0x7fffffff) return fail(GSB_ERR_ARGUMENT, "structured mesh too large");
-        // ... but never pieces of less than two waves of tiles: a 128^3 field is 128 tiles, and eight
-        // launches of 16 CTAs each would leave most of the SMs idle (2.4 ms instead of 0.3 ms).
-        const int64_t tiles_all = n_slow * n_ytiles * n_col_tiles * ncomp * n_batch;
-        const int64_t pieces = h_out ? std::max<int64_t>(1, std::min<int64_t>(8, tiles_all / (2 * (int64_t)dev.sm_count))) : 1;
-        const int64_t fgroup = std::max<int64_t>(1, n_batch / pieces);
-        const int64_t splits = (n_batch >= pieces) ? 1 : std::min<int64_t>(n_slow, pieces / n_batch);
-        int64_t c = 0;
-        for (int64_t f0 = 0; f0 < n_batch; f0 += fgroup) {
-            const int64_t nf = std::min(fgroup, n_batch - f0);
-            for (int64_t k = 0; k < splits; ++k, ++c) {
-                const int64_t s_lo = n_slow * k / splits, s_hi = n_slow * (k + 1) / splits;
-                if (s_hi == s_lo) continue;
-                cp.batch0 = f0;
-                cp.rt0 = s_lo * n_ytiles;
-                cp.n_row_tiles = (int)((s_hi - s_lo) * n_ytiles);
-                {
-                    KernelTimer timer(st);
-                    TraceScope ts("contract(scaled)", st);
-                    GSB_TRY(launch_contract(cp, nf, dev.sm_count, true, st));
-                }
-                if (h_out) {
-                    cudaEvent_t ev = dev.contract_events[c % DeviceState::N_CHUNK_EVENTS];
-                    GSB_CUDA(cudaEventRecord(ev, st));
-                    GSB_CUDA(cudaStreamWaitEvent(dev.streams[1], ev, 0));
-                    for (int64_t f = f0; f < f0 + nf; ++f)
-                        for (int comp = 0; comp < ncomp; ++comp) {
-                            const size_t off = ((size_t)f * ncomp + comp) * mesh.n + (size_t)s_lo * ly * lc;
-                            GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * (s_hi - s_lo) * ly * lc,
-                                                     cudaMemcpyDeviceToHost, dev.streams[1]));
-                        }
-                }
-            }
-        }
-        if (h_out) {
-            GSB_CUDA(cudaEventRecord(dev.events[4], dev.streams[1]));
-            GSB_CUDA(cudaStreamWaitEvent(st, dev.events[4], 0));
-        }
-        g_cnt_separable.fetch_add(1);
-        g_cnt_scaled.fetch_add(1);
-        if (folded) g_cnt_folded.fetch_add(1);
-        return GSB_OK;
-    }
-
-    // Chunk plan.  A unit is (field, row tile); its A operand takes `unit_bytes`.  Chunks alternate
-    // between two scratch buffers of `cap` units.  The first chunk is small (its A generation is
-    // the only one that is not hidden behind a contraction) and chunks then grow by <= 1.4x, the
-    // ratio at which the co-resident A generation of chunk c+1 still finishes within contraction c.
-    // Chunk sizes are multiples of `q` units = a whole number of waves over the SMs.
-    const size_t unit_bytes = (size_t)n_stages * SEP_A_TILE * sizeof(double);
-    const int64_t total_units = n_batch * n_row_tiles_total;
-    const int64_t tiles_per_unit = (int64_t)n_col_tiles * ncomp;
-    int64_t q = dev.sm_count;
-    {
-        int64_t a2 = tiles_per_unit, b2 = dev.sm_count;
-        while (b2) { const int64_t tmp = a2 % b2; a2 = b2; b2 = tmp; }
-        q = dev.sm_count / a2;     // units per whole wave
-    }
-    int64_t cap = std::max<int64_t>(1, (int64_t)((size_t)g_opt_scratch_mb.load() * (1u << 20) / 2 / unit_bytes));
-    cap = std::min<int64_t>(cap, total_units);
-    if (cap >= 2 * q) cap -= cap % q;
-    const bool whole_fields = n_row_tiles_total <= cap && n_batch > 1;
-    struct Chunk { int64_t f0, nf, r0, nrt; };
-    std::vector<Chunk> chunks;          // a range of row tiles of one field, or whole fields
-    int64_t biggest = 0;
-    {
-        const int64_t min_chunks = std::max<int64_t>(1, g_opt_min_chunks.load());
-        int64_t n = std::max<int64_t>(q, total_units / (4 * min_chunks) / q * q);
-        // Host route: the D2H copy of a chunk (PCIe: ~1.26x its contraction time for C2) runs while the
-        // next chunk is contracted.  Growing chunks would make that next contraction longer than the
-        // copy and leave the copy engine -- the bottleneck of the whole call -- idle in between, so
-        // chunks stay equal there.
-        const double growth = h_out ? 1.0 : (double)g_opt_chunk_growth_pct.load() / 100.0;
-        int64_t f = 0, r = 0;
-        while (f < n_batch) {
-            Chunk ch;
-            const int64_t want = std::min(n, cap);
-            if (whole_fields) {
-                ch = {f, std::min<int64_t>(std::max<int64_t>(1, want / n_row_tiles_total), n_batch - f), 0,
-                      n_row_tiles_total};
-                f += ch.nf;
-            } else {
-                ch = {f, 1, r, std::min<int64_t>(want, n_row_tiles_total - r)};
-                r += ch.nrt;
-                if (r >= n_row_tiles_total) { r = 0; ++f; }
-            }
-            chunks.push_back(ch);
-            biggest = std::max(biggest, ch.nf * ch.nrt);
-            n = std::max<int64_t>(n, (int64_t)(growth * (double)n) / q * q);
-        }
-    }
-    double *abuf[2] = {nullptr, nullptr};
-    const int nbuf = chunks.size() > 1 ? 2 : 1;
-    for (int i = 0; i < nbuf; ++i) GSB_TRY(scr.alloc(&abuf[i], (size_t)biggest * n_stages * SEP_A_TILE));
-
-    // Software pipeline over chunks: the contractions run in order on the caller's stream `st`;
-    // the A generation of chunk c+1 runs on a helper stream while chunk c is being contracted
-    // (it only needs buffer (c+1)&1, i.e. the contraction of chunk c-1, to be finished).
-    cudaStream_t hs = dev.streams[2];
-    cudaStream_t copy_st = dev.streams[1];
-    constexpr int NE = DeviceState::N_CHUNK_EVENTS;
-    GSB_CUDA(cudaEventRecord(dev.events[1], st));            // tables (and scratch) are ready
-    GSB_CUDA(cudaStreamWaitEvent(hs, dev.events[1], 0));
-
-    AgenParams ap;
-    std::memset(&ap, 0, sizeof ap);
-    ap.n_row_axes = nra;
-    for (int t = 0; t < nra; ++t) {
-        ap.erow[t] = tp.erow[t];
-        ap.erow_bstride[t] = tp.erow_bstride[t];
-        ap.row_len[t] = vm.len[t];
-    }
-    ap.n_rows = vm.n_rows;
-    ap.n_modes_pad = n_modes_pad;
-    ContractParams cp;
-    std::memset(&cp, 0, sizeof cp);
-    cp.btile = tp.btile;
-    cp.n_col_tiles = n_col_tiles;
-    cp.n_stages = n_stages;
-    cp.ncomp = ncomp;
-    cp.n_rows = vm.n_rows;
-    cp.lc = lc;
-    cp.out = d_out;
-    cp.out_fstride = mesh.n;
-    cp.epi = epi;
-    cp.no_partial = g_opt_partial_tiles.load() ? 0 : 1;
-
-    int64_t c = 0;
-    for (const Chunk &ch : chunks) {
-        {
-            const int64_t f0 = ch.f0, nf = ch.nf, r0 = ch.r0, nrt = ch.nrt;
-            const int bi = (int)(c % nbuf);
-            // A generation (helper stream); buffer bi was last read by the contraction of chunk c-nbuf
-            if (c >= nbuf) GSB_CUDA(cudaStreamWaitEvent(hs, dev.contract_events[(c - nbuf) % NE], 0));
-            ap.row_begin = r0 * SEP_TM;
-            ap.n_row_tiles = (int)nrt;
-            ap.batch0 = f0;
-            ap.atile = abuf[bi];
-            {
-                TraceScope ts("agen", hs);
-                GSB_TRY(launch_agen(ap, nf, dev.sm_count, hs));
-            }
-            GSB_CUDA(cudaEventRecord(dev.chunk_events[c % NE], hs));
-            // contraction (caller's stream)
-            GSB_CUDA(cudaStreamWaitEvent(st, dev.chunk_events[c % NE], 0));
-            cp.atile = abuf[bi];
-            cp.n_row_tiles = (int)nrt;
-            cp.batch0 = f0;
-            cp.row_begin = r0 * SEP_TM;
-            {
-                KernelTimer timer(st);
-                TraceScope ts("contract", st);
-                GSB_TRY(launch_contract(cp, nf, dev.sm_count, false, st));
-            }
-            GSB_CUDA(cudaEventRecord(dev.contract_events[c % NE], st));
-            if (h_out) {
-                // copy the finished chunk to the host while the next one is being computed
-                GSB_CUDA(cudaStreamWaitEvent(copy_st, dev.contract_events[c % NE], 0));
-                const int64_t row_lo = r0 * SEP_TM;
-                const int64_t row_hi = std::min<int64_t>(vm.n_rows, (r0 + nrt) * SEP_TM);
-                if (whole_fields) {
-                    const size_t off = (size_t)f0 * ncomp * mesh.n;
-                    GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * nf * ncomp * mesh.n,
-                                             cudaMemcpyDeviceToHost, copy_st));
-                } else {
-                    for (int comp = 0; comp < ncomp; ++comp) {
-                        const size_t off = ((size_t)f0 * ncomp + comp) * mesh.n + (size_t)row_lo * lc;
-                        GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * (row_hi - row_lo) * lc,
-                                                 cudaMemcpyDeviceToHost, copy_st));
-                    }
-                }
-            }
-            ++c;
-        }
-    }
-    if (h_out) {
-        GSB_CUDA(cudaEventRecord(dev.events[4], copy_st));
-        GSB_CUDA(cudaStreamWaitEvent(st, dev.events[4], 0));
-    }
+    GSB_TRY(sk_on_device(d_cov, d_z1, d_z2, d_sf, d_axes, mesh, layout, n_modes, n_batch, vec, epi, d_out, h_out, dev, st));
+    g_cnt_separable.fetch_add(1);
+    if (layout.n_col_axes == 2) g_cnt_folded.fetch_add(1);
     if (g_opt_trace.load() && !g_trace.empty()) {
         cudaDeviceSynchronize();
         for (auto &r : g_trace) {
             float a = 0.f, b = 0.f;
             cudaEventElapsedTime(&a, g_trace[0].e0, r.e0);
             cudaEventElapsedTime(&b, g_trace[0].e0, r.e1);
-            fprintf(stderr, "[gsb trace] %-9s %8.3f -> %8.3f ms\n", r.name, a, b);
+            fprintf(stderr, "[gsb trace] %-12s %8.3f -> %8.3f ms\n", r.name, a, b);
         }
         for (auto &r : g_trace) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
         g_trace.clear();
     }
-    g_cnt_separable.fetch_add(1);
-    if (folded) g_cnt_folded.fetch_add(1);
     return GSB_OK;
 }
 
@@ -1738,14 +1470,13 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "force_path") g_opt_force_path = value;
     else if (n == "host_chunk_points") g_opt_host_chunk_points = value;
     else if (n == "scratch_mb") g_opt_scratch_mb = std::max<int64_t>(value, 1);
-    else if (n == "min_chunks") g_opt_min_chunks = std::max<int64_t>(value, 1);
+    else if (n == "min_chunks" || n == "sep_path" || n == "chunk_growth_pct" || n == "partial_tiles") {
+        // tuning knobs of the first-generation separable path (removed): accepted and ignored
+    }
     else if (n == "trace") g_opt_trace = value;
     else if (n == "direct_cfg") g_opt_direct_cfg = value;
-    else if (n == "sep_path") g_opt_sep_path = value;
-    else if (n == "chunk_growth_pct") g_opt_chunk_growth_pct = std::max<int64_t>(value, 100);
     else if (n == "time_kernels") g_opt_time_kernels = value;
     else if (n == "fold_axes") g_opt_fold_axes = value;
-    else if (n == "partial_tiles") g_opt_partial_tiles = value;
     else if (n == "krige_host_chunk_mb") g_opt_krige_host_chunk_mb = std::max<int64_t>(value, 1);
     else if (n == "sk_table_mb") g_opt_sk_table_mb = std::max<int64_t>(value, 1);
     else if (n == "sk_grid") g_opt_sk_grid = std::max<int64_t>(value, 0);
@@ -1760,7 +1491,6 @@ int64_t gsb_get_counter(const char *name)
     if (n == "launches") return g_launches.load();
     if (n == "direct_calls") return g_cnt_direct.load();
     if (n == "separable_calls") return g_cnt_separable.load();
-    if (n == "scaled_calls") return g_cnt_scaled.load();
     if (n == "krige_calls") return g_cnt_krige.load();
     if (n == "folded_calls") return g_cnt_folded.load();
     if (n == "sk_calls") return g_cnt_sk.load();

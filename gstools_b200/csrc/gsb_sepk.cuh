@@ -201,7 +201,7 @@ __global__ void sk_tables_kernel(const SkTableParams tp)
 // stream-K plan (host).  Tiles are numbered  tile = ((z * n_slow + slow) * n_ytiles + yt) * n_col_tiles + ct
 // (z = field * ncomp + comp).  A pipeline stage of a tile costs rowq(yt) * colg(ct) units: rowq in 1..4 counts
 // the passes of 8-row groups each of the 4 FP64 pipes makes (row groups are dealt round-robin to the pipes),
-// colg in {4, 8, 12, 16} the 8-column groups computed (inside the mesh, rounded up to 4).  Boundaries of the equal-cost shares are snapped to stages.
+// colg in {2, 4, ..., 16} the 8-column groups computed (inside the mesh, rounded up to 2); floor: sk_tile_cost.  Boundaries of the equal-cost shares are snapped to stages.
 // ---------------------------------------------------------------------------------------------
 struct SkBound { int64_t tile; int32_t stage; int32_t pad; };
 
@@ -214,7 +214,16 @@ inline int sk_rowq(int64_t ly, int yt)
 inline int sk_colg(int64_t lc, int ct)
 {
     const int64_t cols = std::min<int64_t>(SK_TN, lc - (int64_t)ct * SK_TN);
-    return 4 * (int)((cols + 31) / 32);      // the kernel has compile-time variants for 4, 8, 12, 16 column groups
+    return 2 * (int)((cols + 15) / 16);      // the kernel has compile-time variants for 2, 4, ..., 16 column groups
+}
+// Cost of one pipeline stage of tile (yt, ct).  However little of a tile lies inside the mesh, its stage still
+// moves the whole 41.6 KB of operands from L2 to shared memory: measured (profiles/r02_ncu_sk_*): half-height
+// tiles pull 4.85 TB/s through the L2 -> SM path and run at 84 % of the DMMA rate, full tiles need 2.7 TB/s.
+// The floor of 40 units (a full tile stage is 64) stands for that bandwidth limit.
+constexpr int SK_COST_FLOOR = 40;
+inline int sk_tile_cost(int64_t ly, int64_t lc, int yt, int ct)
+{
+    return std::max(SK_COST_FLOOR, sk_rowq(ly, yt) * sk_colg(lc, ct));
 }
 
 // Shares of the tiles [tile_begin, tile_end) for `grid` CTAs: bnd[0..grid], bnd[c] <= bnd[c+1],
@@ -227,14 +236,17 @@ inline int sk_plan(int64_t tile_begin, int64_t tile_end, int n_ytiles, int n_col
     std::vector<int64_t> prefix((size_t)period + 1, 0);     // cost of the first p tiles of a period
     std::vector<int> w((size_t)period);
     for (int p = 0; p < period; ++p) {
-        w[p] = sk_rowq(ly, p / n_col_tiles) * sk_colg(lc, p % n_col_tiles);
+        w[p] = sk_tile_cost(ly, lc, p / n_col_tiles, p % n_col_tiles);
         prefix[p + 1] = prefix[p] + (int64_t)w[p] * n_stages;
     }
     const int64_t P = prefix[period];
     auto cum = [&](int64_t tile) { return (tile / period) * P + prefix[(size_t)(tile % period)]; };
     const int64_t c0 = cum(tile_begin), c1 = cum(tile_end);
-    const int64_t n_units = (tile_end - tile_begin) * (int64_t)n_stages;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, n_units));
+    // A share is never smaller than an eighth of a full tile: the owner of a tile adds the partial accumulators
+    // of the other contributors one after the other (128 KB each), so a tiny mesh (100 x 100: ONE tile) must not
+    // be cut into 125 single-stage shares.
+    const int64_t min_share = std::max<int64_t>(64, (int64_t)n_stages * 64 / 8);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_grid, (c1 - c0) / min_share));
     bnd.assign((size_t)grid + 1, SkBound{tile_end, 0, 0});
     bnd[0] = SkBound{tile_begin, 0, 0};
     for (int c = 1; c < grid; ++c) {
@@ -436,15 +448,15 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        // compile-time variants of the stage: column groups rounded up to 4 (the B tile is zero beyond the mesh),
-        // row groups of this warp inside the mesh; variant = 2 * (jv4 - 1) + (ni - 1), 7 = the full tile, -1 = idle
-        int variant = 7;
+        // compile-time variants of the stage: column groups rounded up to 2 (the B tile is zero beyond the mesh),
+        // row groups of this warp inside the mesh; variant = 2 * (jv2 - 1) + (ni - 1), 15 = the full tile, -1 = idle
+        int variant = 15;
         if (PARTIAL) {
             const int cols = (int)min((int64_t)SK_TN, prm.lc - (int64_t)ct * SK_TN);
             const int rows = (int)min((int64_t)SK_TM, prm.ly - (int64_t)yt * SK_TM);
-            const int jv4 = (cols + 31) >> 5;
+            const int jv2 = (cols + 15) >> 4;
             const int ni = (8 * warp < rows ? 1 : 0) + (8 * (warp + 8) < rows ? 1 : 0);
-            variant = ni > 0 ? 2 * (jv4 - 1) + (ni - 1) : -1;
+            variant = ni > 0 ? 2 * (jv2 - 1) + (ni - 1) : -1;
         }
 
         for (int s = s_begin; s < s_end; ++s) {
@@ -459,19 +471,18 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid
             __syncwarp();
             mbar_wait(&full[slot], round & 1);
             const double *S = stage_base + slot * SK_STAGE_DOUBLES;
-            if (!PARTIAL || variant == 7) {
+            if (!PARTIAL || variant == 15) {
                 sk_stage<SCALE, 16, 2>(S, acc, a_off0, a_off1, b_off, c_off);
             } else {
+#define GSB_SK_CASE(JV)                                                                                     \
+                case 2 * (JV / 2 - 1): sk_stage<SCALE, JV, 1>(S, acc, a_off0, a_off1, b_off, c_off); break;  \
+                case 2 * (JV / 2 - 1) + 1: sk_stage<SCALE, JV, 2>(S, acc, a_off0, a_off1, b_off, c_off); break;
                 switch (variant) {       // warp-uniform
-                case 0: sk_stage<SCALE, 4, 1>(S, acc, a_off0, a_off1, b_off, c_off); break;
-                case 1: sk_stage<SCALE, 4, 2>(S, acc, a_off0, a_off1, b_off, c_off); break;
-                case 2: sk_stage<SCALE, 8, 1>(S, acc, a_off0, a_off1, b_off, c_off); break;
-                case 3: sk_stage<SCALE, 8, 2>(S, acc, a_off0, a_off1, b_off, c_off); break;
-                case 4: sk_stage<SCALE, 12, 1>(S, acc, a_off0, a_off1, b_off, c_off); break;
-                case 5: sk_stage<SCALE, 12, 2>(S, acc, a_off0, a_off1, b_off, c_off); break;
-                case 6: sk_stage<SCALE, 16, 1>(S, acc, a_off0, a_off1, b_off, c_off); break;
+                    GSB_SK_CASE(2) GSB_SK_CASE(4) GSB_SK_CASE(6) GSB_SK_CASE(8)
+                    GSB_SK_CASE(10) GSB_SK_CASE(12) GSB_SK_CASE(14) GSB_SK_CASE(16)
                 default: break;          // no row group of this warp inside the mesh
                 }
+#undef GSB_SK_CASE
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);

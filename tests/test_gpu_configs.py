@@ -67,9 +67,10 @@ def test_config2_full_512cubed(gsb, oracle_mod):
         pos = np.stack([np.full(yy.size, cfg["axes"][0][ix]), yy.reshape(-1), zz.reshape(-1)])
         plane = gsb.summate(tc, t1, t2, torch.tensor(pos, device=dev)).reshape(512, 512)
         assert float((plane - out[ix]).abs().max()) * np.sqrt(1.0 / 1000) <= TOL
-    # host-buffer route (slab pipeline, D2H) returns the same bits
+    # host-buffer route (8 pieces with overlapped D2H: other stream-K shares than the single device launch)
     host = gsb.summate_structured(cfg["cov"], cfg["z1"], cfg["z2"], cfg["axes"])
-    assert np.array_equal(host[::37], out[::37].cpu().numpy())
+    assert np.max(np.abs(host[::37] - out[::37].cpu().numpy())) * np.sqrt(1.0 / 1000) <= 1e-3 * TOL
+    assert np.array_equal(host[::37], gsb.summate_structured(cfg["cov"], cfg["z1"], cfg["z2"], cfg["axes"])[::37])
 
 
 def test_config3_full_20m_points(gsb, oracle_mod):
@@ -133,9 +134,9 @@ def test_config5_full_ensemble_256x128cubed(gsb, oracle_mod):
         want = oracle_mod.summate(cfg["cov"][b], cfg["z1"][b], cfg["z2"][b], pos)
         got = out[b].reshape(-1)[tidx].cpu().numpy()
         assert np.max(np.abs(got - want)) * np.sqrt(1.0 / 1000) <= TOL
-    # one realisation computed alone == the same realisation inside the batch (seed sharding)
+    # one realisation computed alone == the same realisation inside the batch up to rounding (seed sharding)
     single = gsb.summate_structured(tc[37], t1[37], t2[37], axes)
-    assert torch.equal(single, out[37])
+    assert float((single - out[37]).abs().max()) * np.sqrt(1.0 / 1000) <= 1e-3 * TOL
 
 
 def test_beyond_the_configs_1024cubed_index_arithmetic(gsb, oracle_mod):
@@ -160,7 +161,7 @@ def test_beyond_the_configs_1024cubed_index_arithmetic(gsb, oracle_mod):
     want = oracle_mod.summate(cfg["cov"][:, :64], cfg["z1"][:64], cfg["z2"][:64], bc.grid_points(ax, None, idx))
     assert np.max(np.abs(got - want)) * np.sqrt(1.0 / 64) <= TOL
     rev = gsb.summate_structured(tc, t1, t2, [axes[0].flip(0), axes[1], axes[2]])
-    assert torch.equal(rev, out.flip(0))
+    assert float((rev - out.flip(0)).abs().max()) * np.sqrt(1.0 / 64) <= 1e-3 * TOL
     del rev, out
     # vector field on 1024 x 1024 x 768: 3 x 0.8e9 elements, component offsets beyond 2^31
     axes[2] = axes[2][:768]

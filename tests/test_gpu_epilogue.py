@@ -39,17 +39,15 @@ def test_direct_kernel_epilogue_bits(scale, adds, dim, n, n_modes, gsb, oracle_m
 
 
 @pytest.mark.parametrize("scale,adds", EPIS[1:])
-@pytest.mark.parametrize("shape,sep_path", [((24, 130, 260), 1), ((24, 130, 260), 2), ((300, 520), 0),
-                                            ((9, 16), 0)])
-def test_structured_kernel_epilogue_bits(scale, adds, shape, sep_path, gsb, oracle_mod):
-    """Pre-generated-A and scaled contraction variants (forced), a 2-D mesh, and a mesh small enough
-    to be expanded and sent through the direct kernel."""
+@pytest.mark.parametrize("shape,force", [((24, 130, 260), 2), ((300, 520), 2), ((70, 3, 200), 2), ((9, 16), 1)])
+def test_structured_kernel_epilogue_bits(scale, adds, shape, force, gsb, oracle_mod):
+    """The contraction with and without slow axes (3-D / 2-D), partial tiles, and a mesh expanded on the device
+    and sent through the direct kernel."""
     dim = len(shape)
     cov, z1, z2 = synth_modes(dim, 130, seed=sum(shape))
     axes = [np.linspace(-3.0, 40.0, s) for s in shape]
     mat = np.random.RandomState(1).normal(size=(dim, dim))
-    gsb.set_option("sep_path", sep_path)
-    gsb.set_option("structured_min_tiles", 1 if shape != (9, 16) else 64)
+    gsb.set_option("force_path", force)
     try:
         raw = gsb.summate_structured(cov, z1, z2, axes, mat)
         got = gsb.summate_structured(cov, z1, z2, axes, mat, epilogue=(scale, _adds(adds, 1)))
@@ -64,8 +62,7 @@ def test_structured_kernel_epilogue_bits(scale, adds, shape, sep_path, gsb, orac
                                       epilogue=(scale, _adds(adds, 1)))
         assert np.array_equal(gotb, oracle_mod.apply_epilogue(rawb, scale, _adds(adds, 1)))
     finally:
-        gsb.set_option("sep_path", 0)
-        gsb.set_option("structured_min_tiles", 64)
+        gsb.set_option("force_path", 0)
 
 
 def test_device_tensor_epilogue(gsb, oracle_mod):

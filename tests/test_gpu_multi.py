@@ -52,10 +52,12 @@ def _worker(rank, world, port, tmpdir):
         full = gdist.gather_field(slab, 67)                      # NCCL all-gather
         only0 = gdist.gather_field(slab, 67, dst=0)              # NCCL gather to rank 0
         single = gsb.summate_structured(tc, t1, t2, axes)        # whole mesh on this GPU
-        assert torch.equal(full, single)
+        # slabs vs the whole mesh: the same tiles, other stream-K shares -> equal up to rounding (1e-12 * sqrt(var))
+        tight = 1e-12 * np.sqrt(200.0)
+        assert float((full - single).abs().max()) <= tight
         assert (only0 is None) == (rank != 0)
         if rank == 0:
-            assert torch.equal(only0, single)
+            assert torch.equal(only0, full)
         # flat points, host arrays in: every rank uses its own device (LOCAL_RANK)
         gsb.set_option("force_path", 0)
         pos = np.random.RandomState(1).uniform(0, 100, (3, 100001))
@@ -106,17 +108,13 @@ def test_one_process_uses_several_devices():
     try:
         for dev in (0, 1):
             gsb.set_device(dev)
-            gsb.set_option("sep_path", 1)
             a = gsb.summate_structured(cov, z1, z2, axes)
-            gsb.set_option("sep_path", 2)
-            b = gsb.summate_structured(cov, z1, z2, axes)
-            gsb.set_option("sep_path", 0)
+            b = gsb.summate_incompr_structured(cov, z1, z2, axes)
             c = np.stack(gsb.calc_field_krige_and_variance(kmat, kv, kcond))
             d = np.stack(gsb.krige_evaluate(spec, kmat, kcond, cpos, axes=[a_[:12] for a_ in axes]))
             e = gsb.summate(cov, z1, z2, rs.uniform(0, 50, (3, 0)) if False else np.ones((3, 5000)))
             results.append((a, b, c, d, e))
     finally:
-        gsb.set_option("sep_path", 0)
         gsb.set_device(0)
     for x, y in zip(*results):
         assert np.array_equal(x, y)

@@ -236,7 +236,7 @@ STRUCT_CASES = [
 
 
 @pytest.mark.parametrize("dim,lens,n_modes", STRUCT_CASES)
-@pytest.mark.parametrize("path", ["direct", "separable", "separable-agen", "separable-scaled"])
+@pytest.mark.parametrize("path", ["direct", "separable"])
 def test_structured_vs_oracle(dim, lens, n_modes, path, gsb, oracle_mod):
     cov, z1, z2 = synth_modes(dim, n_modes, seed=7 + dim)
     rs = np.random.RandomState(5)
@@ -246,8 +246,6 @@ def test_structured_vs_oracle(dim, lens, n_modes, path, gsb, oracle_mod):
     pos = mat @ grid
     want = oracle_mod.summate(cov, z1, z2, pos).reshape(lens)
     gsb.set_option("force_path", 1 if path == "direct" else 2)
-    # the two contraction variants: A operand pre-generated (agen) / rescaled in the consumer
-    gsb.set_option("sep_path", {"separable-agen": 1, "separable-scaled": 2}.get(path, 0))
     try:
         got = gsb.summate_structured(cov, z1, z2, axes, mat)
         assert got.shape == tuple(lens)
@@ -259,7 +257,6 @@ def test_structured_vs_oracle(dim, lens, n_modes, path, gsb, oracle_mod):
             assert maxabs(gv, wv) <= raw_tol(n_modes)
     finally:
         gsb.set_option("force_path", 0)
-        gsb.set_option("sep_path", 0)
 
 
 def test_structured_identity_matrix_and_auto_path(gsb, oracle_mod):
@@ -273,10 +270,10 @@ def test_structured_identity_matrix_and_auto_path(gsb, oracle_mod):
     assert maxabs(got, want) <= raw_tol(100)
     got_eye = gsb.summate_structured(cov, z1, z2, axes, np.eye(3))
     assert np.array_equal(got, got_eye)
-    # tiny mesh -> expanded on the device, direct kernel
-    before = gsb.get_counter("direct_calls")
+    # tiny mesh: whichever path the cost model picks (a single stream-K share, or expanded + direct kernel)
+    before = gsb.get_counter("direct_calls") + gsb.get_counter("separable_calls")
     small = gsb.summate_structured(cov, z1, z2, [np.arange(4.0), np.arange(5.0), np.arange(6.0)])
-    assert gsb.get_counter("direct_calls") == before + 1
+    assert gsb.get_counter("direct_calls") + gsb.get_counter("separable_calls") == before + 1
     assert maxabs(small, want[:4, :5, :6]) <= raw_tol(100)
 
 
@@ -296,9 +293,12 @@ def test_structured_batched_ensemble(gsb, oracle_mod):
             for b in range(n_batch):
                 want = oracle_mod.summate(cov[b], z1[b], z2[b], grid).reshape(lens)
                 assert maxabs(got[b], want) <= raw_tol(n_modes)
-                # batching changes nothing bitwise
+                # batching changes nothing beyond rounding (direct kernel: not a bit; the stream-K shares of
+                # the separable contraction cut the mode sums of a tile at geometry-dependent stages)
                 single = gsb.summate_structured(cov[b], z1[b], z2[b], axes)
-                assert np.array_equal(single, got[b])
+                if force == 1:
+                    assert np.array_equal(single, got[b])
+                assert maxabs(single, got[b]) <= 1e-3 * raw_tol(n_modes)
         finally:
             gsb.set_option("force_path", 0)
 
@@ -315,21 +315,16 @@ def test_structured_device_tensors_and_slab_consistency(gsb):
                                  [torch.tensor(a, device=dev) for a in axes])
     assert out.is_cuda and tuple(out.shape) == (64, 96, 256)
     assert np.array_equal(out.cpu().numpy(), host)
-    # the mesh is processed in row chunks bounded by the A-operand scratch budget; a different
-    # chunking must not change a bit
-    gsb.set_option("scratch_mb", 8)
-    try:
-        assert np.array_equal(gsb.summate_structured(cov, z1, z2, axes), host)
-    finally:
-        gsb.set_option("scratch_mb", 3072)
-    # a slab computed alone equals the same rows of the full field (multi-GPU sharding unit);
-    # the slab is below the tiled kernel's size threshold, so pin the path for the comparison
+    # a slab computed alone equals the same rows of the full field up to rounding (multi-GPU sharding unit:
+    # the tiles are the same, the stream-K shares cut their mode sums at other stages)
     gsb.set_option("force_path", 2)
     try:
         part = gsb.summate_structured(cov, z1, z2, [axes[0][16:48], axes[1], axes[2]])
+        again = gsb.summate_structured(cov, z1, z2, [axes[0][16:48], axes[1], axes[2]])
     finally:
         gsb.set_option("force_path", 0)
-    assert np.array_equal(part, host[16:48])
+    assert np.array_equal(part, again)
+    assert maxabs(part, host[16:48]) <= 1e-3 * raw_tol(128)
 
 
 def test_separable_and_direct_kernels_agree(gsb):
@@ -347,51 +342,41 @@ def test_separable_and_direct_kernels_agree(gsb):
     assert maxabs(sep, direct) <= raw_tol(1000)
 
 
-def test_structured_chunking_is_invisible(gsb, oracle_mod):
-    """The A-operand scratch budget splits the mesh into row chunks (and ensembles into field
-    chunks); vector fields, batches, host and device routes must give the same bits whatever the
-    chunking, and ragged last tiles / chunks must be handled."""
+def test_structured_routes_and_batches_agree(gsb, oracle_mod):
+    """Vector fields, batches, host and device routes on a ragged mesh (1961 rows): all within rounding of each
+    other and of the oracle; identical calls are bit-identical (fixed split, fixed summation order)."""
     import torch
 
     dev = torch.device("cuda:0")
     cov, z1, z2 = synth_modes(3, 96, seed=21)
-    axes = [np.arange(37.0), np.linspace(0, 50, 53), np.linspace(-3, 40, 150)]   # 1961 rows: ragged
+    axes = [np.arange(37.0), np.linspace(0, 50, 53), np.linspace(-3, 40, 150)]
     grid = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+    tight = 1e-3 * raw_tol(96)
     gsb.set_option("force_path", 2)
     try:
         ref_s = gsb.summate_structured(cov, z1, z2, axes)
         ref_v = gsb.summate_incompr_structured(cov, z1, z2, axes)
         assert maxabs(ref_s, oracle_mod.summate(cov, z1, z2, grid).reshape(37, 53, 150)) <= raw_tol(96)
         assert maxabs(ref_v, oracle_mod.summate_incompr(cov, z1, z2, grid).reshape(3, 37, 53, 150)) <= raw_tol(96)
+        assert np.array_equal(gsb.summate_structured(cov, z1, z2, axes), ref_s)
         sets = [synth_modes(3, 96, seed=30 + b) for b in range(5)]
         bc_, b1, b2 = (np.stack([s_[i] for s_ in sets]) for i in range(3))
         ref_b = gsb.summate_structured(bc_, b1, b2, axes)
         ref_bv = gsb.summate_incompr_structured(bc_, b1, b2, axes)
-        for mb in (1, 2, 5):          # 1 MiB: a handful of row tiles per chunk
-            gsb.set_option("scratch_mb", mb)
-            assert np.array_equal(gsb.summate_structured(cov, z1, z2, axes), ref_s)
-            assert np.array_equal(gsb.summate_incompr_structured(cov, z1, z2, axes), ref_v)
-            assert np.array_equal(gsb.summate_structured(bc_, b1, b2, axes), ref_b)
-            assert np.array_equal(gsb.summate_incompr_structured(bc_, b1, b2, axes), ref_bv)
-            t = [torch.tensor(a, device=dev) for a in (bc_, b1, b2)]
-            out = gsb.summate_incompr_structured(t[0], t[1], t[2], [torch.tensor(a, device=dev) for a in axes])
-            assert np.array_equal(out.cpu().numpy(), ref_bv)
-        for b in range(5):
-            assert np.array_equal(ref_b[b], gsb.summate_structured(*sets[b], axes))
-        # the scaled variant: same fields within tolerance, batching / host splitting invisible
-        gsb.set_option("scratch_mb", 3072)
-        gsb.set_option("sep_path", 2)
-        sc_s = gsb.summate_structured(cov, z1, z2, axes)
-        sc_bv = gsb.summate_incompr_structured(bc_, b1, b2, axes)
-        assert maxabs(sc_s, ref_s) <= raw_tol(96) and maxabs(sc_bv, ref_bv) <= raw_tol(96)
+        assert np.array_equal(gsb.summate_incompr_structured(bc_, b1, b2, axes), ref_bv)
         t = [torch.tensor(a, device=dev) for a in (bc_, b1, b2)]
         out = gsb.summate_incompr_structured(t[0], t[1], t[2], [torch.tensor(a, device=dev) for a in axes])
-        assert np.array_equal(out.cpu().numpy(), sc_bv)
-        assert np.array_equal(gsb.summate_structured(*sets[2], axes), gsb.summate_structured(bc_, b1, b2, axes)[2])
+        assert maxabs(out.cpu().numpy(), ref_bv) <= tight
+        for b in range(5):
+            assert maxabs(ref_b[b], gsb.summate_structured(*sets[b], axes)) <= tight
+            want = oracle_mod.summate_incompr(*sets[b], grid).reshape(3, 37, 53, 150)
+            assert maxabs(ref_bv[b], want) <= raw_tol(96)
+        # a forced odd grid (other shares) moves nothing beyond rounding
+        gsb.set_option("sk_grid", 37)
+        assert maxabs(gsb.summate_structured(cov, z1, z2, axes), ref_s) <= tight
     finally:
-        gsb.set_option("scratch_mb", 3072)
+        gsb.set_option("sk_grid", 0)
         gsb.set_option("force_path", 0)
-        gsb.set_option("sep_path", 0)
 
 
 def test_concurrent_calls_from_python_threads(gsb, oracle_mod):
@@ -511,7 +496,7 @@ def test_thin_meshes_fold_the_last_two_axes(shape, gsb, oracle_mod):
     mat = np.random.RandomState(9).normal(size=(dim, dim))
     grid = mat @ np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
     want = oracle_mod.summate(cov, z1, z2, grid).reshape(shape)
-    gsb.set_option("structured_min_tiles", 1)
+    gsb.set_option("force_path", 2)
     try:
         out = {}
         for fold in (0, 2):
@@ -524,12 +509,10 @@ def test_thin_meshes_fold_the_last_two_axes(shape, gsb, oracle_mod):
             wantv = oracle_mod.summate_incompr(cov, z1, z2, grid).reshape((3,) + shape)
             gotv = gsb.summate_incompr_structured(cov, z1, z2, axes, mat)
             assert maxabs(gotv, wantv) <= raw_tol(130)
-        # automatic choice: folds only where it improves the tile utilisation
+        # automatic choice (cost model: padded-tile contraction + table building, either way)
         gsb.set_option("fold_axes", 1)
-        before = gsb.get_counter("folded_calls")
         auto = gsb.summate_structured(cov, z1, z2, axes, mat)
         assert maxabs(auto, want) <= raw_tol(130)
-        assert (gsb.get_counter("folded_calls") > before) == (shape[-1] < 64)
         # fused epilogue and batches go through the folded path unchanged
         gsb.set_option("fold_axes", 2)
         covb = np.stack([cov, 0.5 * cov])
@@ -540,7 +523,7 @@ def test_thin_meshes_fold_the_last_two_axes(shape, gsb, oracle_mod):
         assert np.array_equal(gotb, oracle_mod.apply_epilogue(rawb, 0.25, [0.0, 1.5]))
     finally:
         gsb.set_option("fold_axes", 1)
-        gsb.set_option("structured_min_tiles", 64)
+        gsb.set_option("force_path", 0)
 
 
 def test_badly_filled_tiles_go_to_the_direct_kernel(gsb, oracle_mod):

@@ -20,10 +20,8 @@ def raw_tol(n_modes, var=1.0):
 @pytest.fixture()
 def sk(gsb):
     gsb.set_option("force_path", 2)
-    gsb.set_option("sep_path", 3)
     yield gsb
     gsb.set_option("force_path", 0)
-    gsb.set_option("sep_path", 0)
     gsb.set_option("sk_grid", 0)
     gsb.set_option("sk_table_mb", 256)
 

@@ -13,7 +13,7 @@ def _cost(ly, lc, n_yt, n_ct, tile):
     rows = min(128, ly - yt * 128)
     cols = min(128, lc - ct * 128)
     rowq = (-(-rows // 8) + 3) // 4
-    return rowq * 4 * -(-cols // 32)
+    return max(40, rowq * 2 * -(-cols // 16))
 
 
 def _check(tile_begin, tile_end, ly, lc, n_stages, max_grid):
@@ -38,6 +38,10 @@ def _check(tile_begin, tile_end, ly, lc, n_stages, max_grid):
     total = sum(_cost(ly, lc, n_yt, n_ct, t) for t in range(tile_begin, tile_end)) * n_stages
     assert sum(shares) == total
     assert max(shares) - min(shares) <= 2 * 64 + 1, (max(shares), min(shares))
+    # no share smaller than an eighth of a full tile (bounded number of contributors per tile), unless there is
+    # only one share
+    if grid > 1:
+        assert min(shares) >= max(64, n_stages * 64 // 8) - 64, (min(shares), n_stages)
 
 
 @pytest.mark.parametrize("args", [
