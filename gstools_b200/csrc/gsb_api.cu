@@ -408,7 +408,10 @@ static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int6
                 per += (n_yt - 1) * sk_tile_cost(P, L.lc, 0, ct) + sk_tile_cost(P, L.lc, (int)(n_yt - 1), ct);
             const double units = (double)(n_rows / P) * (double)per * (double)n_stages * (double)(n_batch * ncomp);
             const bool no_slow = (b - a == n_row);
-            const double t_contract = units * 64.0 / ((double)sm_count * 1.9e9 * (no_slow ? 0.96 : 0.93));
+            // (a tile is cut into at most ~8 shares, sk_plan: a tiny mesh cannot use every SM)
+            const double min_share = std::max<double>(64.0, (double)n_stages * 64.0 / 8.0);
+            const double ctas = std::max(1.0, std::min((double)sm_count, std::floor(units / min_share)));
+            const double t_contract = units * 64.0 / (ctas * 1.9e9 * (no_slow ? 0.96 : 0.93));
             const double t_table = (double)bytes / 1.0e12;
             // ties: prefer the trailing axes (rows of a tile then are neighbours in memory)
             const double t = (t_contract + t_table) * (1.0 + 1e-6 * (n_row - b));
@@ -465,8 +468,8 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
             want *= 1.25;
         }
     }
+    if (cuts.size() == 1) cuts.push_back(cut_units);      // device route: one piece
     cuts.back() = cut_units;
-    if (cuts.size() == 1) cuts.push_back(cut_units);
     const int64_t pieces = (int64_t)cuts.size() - 1;
     SkTableParams tp;
     std::memset(&tp, 0, sizeof tp);
