@@ -63,7 +63,9 @@ def make_workload(tag):
         cfg.update(path="separable_batched", work_per_pair_dfma=2, tag="C5")
     elif tag == "c3":
         cfg = bc.config3(20_000_000)
-        cfg.update(path="direct", work_per_pair_dfma=2 + 2 + 20, tag="C3")
+        # executed FP64-pipe instructions per pair (DFMA 9 + DMUL 3 + DADD 3, verified in the ncu opcode
+        # histogram); SURVEY.md 8(d)'s contract budget is d + 2 + 20 = 24 (libdevice-class sincos)
+        cfg.update(path="direct", work_per_pair_dfma=2 + 13, contract_per_pair_dfma=2 + 2 + 20, tag="C3")
     elif tag == "c1":
         cfg = bc.config1()
         cfg.update(path="separable", work_per_pair_dfma=2, tag="C1")
@@ -342,6 +344,7 @@ def run_b200_arm(args, cfg):
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     peak_dfma = gsb.measure_fp64_peak(local, 0, 0.4)
+    peak_dmma = gsb.measure_fp64_peak(local, 1, 0.3)
 
     # ---- device-resident throughput ----
     for _ in range(args.warmup):
@@ -404,11 +407,12 @@ def run_b200_arm(args, cfg):
         kern_s = kern_ms * 1e-3 / max(kern_n, 1)
         achieved = pairs_per_launch * flop_per_pair / kern_s / 1e12 if kern_n else None
         peak_tflops = 2.0 * peak_dfma / 1e12
-        traffic = None
+        traffic, ncu_clock = None, None
         prof = os.path.join(REPO, "profiles", "dominant_kernel_traffic.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get(cfg["tag"])
+                pj = json.load(open(prof))
+                traffic, ncu_clock = pj.get(cfg["tag"]), pj.get("sm__cycles_elapsed.avg.per_second")
             except Exception:
                 traffic = None
         roofline = {
@@ -419,14 +423,26 @@ def run_b200_arm(args, cfg):
                              else "FP64 pipe (DFMA), FP64-pipe roofline of BASELINE.json"),
             "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": (achieved / peak_tflops) if achieved else None, "traffic": traffic,
-            "kernel": "separable_kernel (DMMA.8x8x4)" if structured else "direct_kernel",
+            "kernel": "sk_contract_kernel (DMMA.8x8x4, stream-K, one launch per step)" if structured
+                      else "direct_kernel",
             "kernel_ms_per_launch": 1e3 * kern_s, "launches_timed": kern_n,
             "kernel_share_of_step": (kern_ms * 1e-3) / dev_s if dev_s else None,
             "algorithmic_flop_per_pair": flop_per_pair,
             "peak_source": "DFMA microbenchmark run in this process (gsb_measure_fp64_peak); "
                            "MEASURED_PEAKS.json has no fp64 entry",
             "frac_of_nominal_37.2_TFLOPs": (achieved / (2 * NOMINAL_DFMA_PER_S / 1e12)) if achieved else None,
+            # both fp64 paths, measured in this process: register-resident DFMA chains and DMMA.8x8x4 tiles, each at
+            # 64 warps per SM (8 CTAs x 8 warps).  tools/microbench/fp64_pipe.cu tops out at 91.8 % with DFMA chains
+            # because it runs at the contraction's occupancy (1-3 warps per sub-partition): a DFMA can only issue
+            # every other cycle per warp, so few warps cannot fill the pipe; 16 warps per sub-partition can (99 %).
+            "peaks_tflops": {"dfma": 2.0 * peak_dfma / 1e12, "dmma_8x8x4": 2.0 * peak_dmma / 1e12,
+                             "nominal_148x64x1.965GHz": 2 * NOMINAL_DFMA_PER_S / 1e12},
+            "ncu_sm_clock_hz": ncu_clock,
         }
+        if "contract_per_pair_dfma" in cfg and achieved:
+            # the same throughput against SURVEY 8(d)'s instruction BUDGET (a note, not the headline: the kernel
+            # does the budgeted work in fewer instructions, it does not skip any)
+            roofline["frac_vs_survey_contract_budget"] = roofline["frac"] * cfg["contract_per_pair_dfma"] / cfg["work_per_pair_dfma"]
         cpu = cpu_baseline(cfg) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -435,6 +451,7 @@ def run_b200_arm(args, cfg):
             "config": workload_config(cfg, args),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "d2h_gbs_per_gpu": d2h * args.steps / e2e_s / 1e9,
                     "api": "gstools_b200.summate_structured(numpy...) -> numpy (pinned)"
                            if structured else "gstools_b200.summate(numpy...) -> numpy"},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks.summary(),
