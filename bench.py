@@ -317,10 +317,20 @@ def run_b200_arm(args, cfg):
 
     h_cov, h_z1, h_z2 = pin(h_cov), pin(h_z1), pin(h_z2)
     d_cov, d_z1, d_z2 = (torch.tensor(a, device=dev) for a in (h_cov, h_z1, h_z2))
+    # --plan G: ONE process drives G GPUs (gsb_plan_*): the library cuts the call into slabs / point ranges /
+    # batch entries itself; device route = every GPU stores its share into the result tensor on GPU 0 (compute and
+    # gather are one kernel), host route = every GPU copies its share into its slice of the one pinned array
+    plan = None
+    if args.plan > 1:
+        if world != 1:
+            raise SystemExit("--plan is the single-process mode: do not combine it with torchrun")
+        plan = gsb.Plan(list(range(args.plan)))
     if structured:
         h_axes = [pin(a) for a in h_axes]
         d_axes = [torch.tensor(a, device=dev) for a in h_axes]
         fn = gsb.summate_incompr_structured if vec else gsb.summate_structured
+        if plan is not None:
+            fn = plan.summate_incompr_structured if vec else plan.summate_structured
 
         def step_device():
             return fn(d_cov, d_z1, d_z2, d_axes, cfg.get("matrix"))
@@ -333,6 +343,8 @@ def run_b200_arm(args, cfg):
         h_pos = pin(h_pos)
         d_pos = torch.tensor(h_pos, device=dev)
         fn = gsb.summate_incompr if vec else gsb.summate
+        if plan is not None:
+            fn = plan.summate_incompr if vec else plan.summate
 
         def step_device():
             return fn(d_cov, d_z1, d_z2, d_pos)
@@ -377,6 +389,53 @@ def run_b200_arm(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s = float(t.item())
     value = args.steps * total_pairs / dev_s
+
+    # ---- --gather: the same step delivered as ONE device array on rank 0 (sum + gather) ----
+    gather = None
+    if args.gather != "none" and world > 1 and structured and not batched:
+        from gstools_b200 import dist as gdist
+
+        g_axes = [torch.tensor(np.ascontiguousarray(a), device=dev) for a in cfg["axes"]]
+
+        def step_gather():
+            return gdist.summate_structured_gathered(d_cov, d_z1, d_z2, g_axes, cfg.get("matrix"), dst=0,
+                                                     incompr=vec, mode=args.gather, pieces=args.pieces)
+
+        for _ in range(args.warmup):
+            out = step_gather()
+            del out
+        barrier()
+        gpairs = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = step_gather()
+            e1.record()
+            gpairs.append((e0, e1))
+            del out
+        barrier()
+        g_s = sum(a.elapsed_time(b) for a, b in gpairs) * 1e-3
+        t = torch.tensor([g_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        g_s = float(t.item())
+        n_full = int(np.prod([len(a) for a in cfg["axes"]])) * (cfg["dim"] if vec else 1)
+        gather = {"mode": args.gather, "pieces": args.pieces if args.gather == "nccl" else 1,
+                  "ms_per_step": 1e3 * g_s / args.steps, "compute_only_ms_per_step": 1e3 * dev_s / args.steps,
+                  "exposed_ms": 1e3 * (g_s - dev_s) / args.steps,
+                  "bytes_into_rank0_per_step": int(8 * n_full * (world - 1) / world),
+                  "value_no_gather": value,
+                  "what": "rank 0 ends the step holding the whole field as one CUDA tensor; "
+                          + ("row pieces sent with grouped NCCL send/recv on a side stream while the next piece contracts"
+                             if args.gather == "nccl" else
+                             "every rank's contraction kernel stores its slab into rank 0's tensor over NVLink (CUDA IPC "
+                             "mapping), a one-element all-reduce orders the step")}
+        value = args.steps * total_pairs / g_s
+        dev_s_for_line = g_s
+        gdist.close_peer_fields()
+    else:
+        dev_s_for_line = dev_s
 
     # ---- end to end through the public numpy API (host in, host out) ----
     out = None
@@ -443,15 +502,17 @@ def run_b200_arm(args, cfg):
             # the same throughput against SURVEY 8(d)'s instruction BUDGET (a note, not the headline: the kernel
             # does the budgeted work in fewer instructions, it does not skip any)
             roofline["frac_vs_survey_contract_budget"] = roofline["frac"] * cfg["contract_per_pair_dfma"] / cfg["work_per_pair_dfma"]
-        cpu = cpu_baseline(cfg) if world == 1 else None
+        cpu = cpu_baseline(cfg) if (world == 1 and not args.no_cpu) else None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world if plan is None else len(plan),
+            "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_for_line / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(cfg, args),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "d2h_gbs_per_gpu": d2h * args.steps / e2e_s / 1e9,
+                    "d2h_gbs_per_gpu": d2h * args.steps / e2e_s / 1e9 / (1 if plan is None else len(plan)),
+                    "d2h_gbs_all_gpus": d2h * args.steps / e2e_s / 1e9 * (world if plan is None else 1),
                     "api": "gstools_b200.summate_structured(numpy...) -> numpy (pinned)"
                            if structured else "gstools_b200.summate(numpy...) -> numpy"},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks.summary(),
@@ -459,7 +520,16 @@ def run_b200_arm(args, cfg):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if gather is not None:
+            line["gather"] = gather
+        if plan is not None:
+            line["config"]["sharding"] = (f"ONE process, gsb_plan over {len(plan)} GPUs: device route stores every GPU's "
+                                          "share into the result tensor on GPU 0 through peer memory, host route copies "
+                                          "every share into its slice of one pinned array")
+            line["config"]["peer_access"] = plan.peer_access
         print(json.dumps(line), flush=True)
+    if plan is not None:
+        plan.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -750,6 +820,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5cond", "krige"])
+    ap.add_argument("--gather", default="none", choices=["none", "nccl", "p2p"],
+                    help="N > 1, structured workloads: deliver the field as one device array on rank 0; `value` then "
+                         "is compute + gather")
+    ap.add_argument("--pieces", type=int, default=4, help="row pieces per rank of --gather nccl")
+    ap.add_argument("--plan", type=int, default=0, help="single-process mode: drive this many GPUs through gsb_plan")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (builder's table runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload == "krige":

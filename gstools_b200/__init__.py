@@ -33,6 +33,9 @@ from .backend import (
     summate_incompr,
     summate_incompr_structured,
     summate_structured,
+    Plan,
+    use_devices,
+    current_plan,
 )
 from .plugin import disable, enable, is_enabled
 
@@ -59,6 +62,9 @@ __all__ = [
     "is_enabled",
     "set_device",
     "get_device",
+    "Plan",
+    "use_devices",
+    "current_plan",
     "device_count",
     "get_counter",
     "set_option",

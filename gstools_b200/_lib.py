@@ -98,6 +98,19 @@ SIGNATURES = {
     "gsb_sample_radii_mcmc": (_int, [_int, _int, ctypes.c_double, ctypes.c_double, _vp, _int, _vp, _int, _vp,
                                      _int, _int, _int, _vp]),
     "gsb_scale_shift": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp]),
+    "gsb_plan_create": (_int, [ctypes.POINTER(_int), _int, ctypes.POINTER(_vp)]),
+    "gsb_plan_destroy": (_int, [_vp]),
+    "gsb_plan_info": (_int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)]),
+    "gsb_plan_share": (_int, [_i64, _int, _int, _c_int64_p, _c_int64_p]),
+    "gsb_plan_summate": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _i64, _i64, _vp, _i64, _int, _epi_p, _vp, _int,
+                                _int, _vp]),
+    "gsb_plan_summate_structured": (_int, [_vp, _vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64, _i64, _vp, _int,
+                                           _epi_p, _vp, _int, _int, _vp]),
+    "gsb_summate_structured_slab": (_int, [_vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64, _i64, _i64, _i64, _vp, _int,
+                                           _epi_p, _vp, _int, _int, _vp]),
+    "gsb_ipc_export": (_int, [_vp, _int, _vp, _c_int64_p]),
+    "gsb_ipc_open": (_int, [_vp, _int, ctypes.POINTER(_vp)]),
+    "gsb_ipc_close": (_int, [_vp, _int]),
     "gsb_set_option": (_int, [ctypes.c_char_p, _i64]),
     "gsb_release_memory": (_int, [_int]),
     "gsb_get_counter": (_i64, [ctypes.c_char_p]),
@@ -180,6 +193,13 @@ def kernel_times():
     n = ctypes.c_int64(0)
     check(load().gsb_kernel_times(ctypes.byref(ms), ctypes.byref(n)), "gsb_kernel_times")
     return float(ms.value), int(n.value)
+
+
+def plan_share(n: int, parts: int, part: int):
+    """``[lo, hi)`` of part ``part`` of ``parts`` over ``n`` units, as the multi-GPU plan cuts them (host only)."""
+    lo, hi = ctypes.c_int64(0), ctypes.c_int64(0)
+    check(load().gsb_plan_share(int(n), int(parts), int(part), ctypes.byref(lo), ctypes.byref(hi)), "gsb_plan_share")
+    return int(lo.value), int(hi.value)
 
 
 def streamk_plan(tile_begin, tile_end, ly, lc, n_stages, max_grid):

@@ -46,6 +46,10 @@ __all__ = [
     "to_host",
     "set_device",
     "get_device",
+    "Plan",
+    "use_devices",
+    "current_plan",
+    "structured_slab_into",
 ]
 
 _DEVICE = None
@@ -276,9 +280,152 @@ def _epi_ref(epilogue):
 
 
 # ----------------------------------------------------------------------------------------
+# multi-GPU plan: one process, several GPUs (gsb_plan_* of include/gsb200.h)
+# ----------------------------------------------------------------------------------------
+_PLAN = {"plan": None, "min_pairs": 4e9}
+
+
+class _PlanPointEpi:
+    """Per-device ``gsb_point_epilogue`` array of a :class:`Plan`: ``gain`` / ``offset`` replicated on every device."""
+
+    def __init__(self, plan, gain, offset, adds):
+        torch = _torch()
+        self.plan = plan
+        self.entries = []
+        for d in plan.devices:
+            dev = torch.device("cuda", d)
+            rep = [None if t is None else torch.as_tensor(t, dtype=torch.float64).to(dev).contiguous().reshape(-1)
+                   for t in (gain, offset)]
+            self.entries.append(_PointEpi(rep[0], rep[1], adds))
+        self.n = self.entries[0].n
+        self.array = (_lib.PointEpilogue * len(self.entries))()
+        for g, e in enumerate(self.entries):
+            self.array[g] = e.struct
+
+    def ref(self, n):
+        if self.n is not None and self.n != n:
+            raise ValueError(f"point epilogue: arrays hold {self.n} points, the field has {n}")
+        return ctypes.cast(self.array, ctypes.c_void_p)
+
+
+class Plan:
+    """Several GPUs driven from ONE process (``gsb_plan_create``): a call is cut into independent shares --
+    point ranges, slabs along axis 0 of a mesh, or batch entries (ensemble seeds) when there are at least as many
+    as devices -- with no inter-GPU traffic during the sum.  Host arrays: every GPU copies its share straight
+    into its slice of the one (pinned) result array.  CUDA tensors: the other GPUs store their share directly into
+    the result tensor on the inputs' device through NVLink peer memory, from the kernels' epilogue.
+
+    ``devices``: list of CUDA device indices, or None / "all" for every visible device.
+    """
+
+    def __init__(self, devices=None):
+        lib = _lib.load()
+        handle = ctypes.c_void_p()
+        if devices is None or (isinstance(devices, str) and devices == "all"):
+            arr, n = None, 0
+        else:
+            ids = [int(d) for d in devices]
+            if not ids:
+                raise ValueError("Plan: empty device list")
+            arr, n = (ctypes.c_int * len(ids))(*ids), len(ids)
+        _lib.check(lib.gsb_plan_create(arr, n, ctypes.byref(handle)), "plan_create")
+        self._handle = handle
+        cnt, peer = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(lib.gsb_plan_info(handle, ctypes.byref(cnt), None, None), "plan_info")
+        devs = (ctypes.c_int * max(cnt.value, 1))()
+        _lib.check(lib.gsb_plan_info(handle, ctypes.byref(cnt), devs, ctypes.byref(peer)), "plan_info")
+        self.devices = [int(devs[i]) for i in range(cnt.value)]
+        self.peer_access = bool(peer.value)
+        self._finalizer = weakref.finalize(self, lib.gsb_plan_destroy, handle)
+
+    def close(self):
+        """Stop the plan's host threads (idempotent; also done when the object is collected)."""
+        if _PLAN["plan"] is self:
+            _PLAN["plan"] = None
+        self._finalizer()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __len__(self):
+        return len(self.devices)
+
+    def share(self, n, part):
+        """``[lo, hi)`` of the units device number ``part`` of the plan gets out of ``n``."""
+        return _lib.plan_share(n, len(self.devices), part)
+
+    def make_point_epilogue(self, gain=None, offset=None, adds=()):
+        """:func:`make_point_epilogue` with ``gain`` / ``offset`` (host arrays or tensors covering all points of a
+        field) replicated on every device of the plan."""
+        return _PlanPointEpi(self, gain, offset, adds)
+
+    def summate(self, cov_samples, z_1, z_2, pos, *, epilogue=None, point_epilogue=None):
+        return _flat(cov_samples, z_1, z_2, pos, vec=False, epilogue=epilogue, point_epilogue=point_epilogue, plan=self)
+
+    def summate_incompr(self, cov_samples, z_1, z_2, pos, *, epilogue=None):
+        return _flat(cov_samples, z_1, z_2, pos, vec=True, epilogue=epilogue, plan=self)
+
+    def summate_structured(self, cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=None, point_epilogue=None):
+        return _structured(cov_samples, z_1, z_2, axes, matrix, vec=False, epilogue=epilogue,
+                           point_epilogue=point_epilogue, plan=self)
+
+    def summate_incompr_structured(self, cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=None):
+        return _structured(cov_samples, z_1, z_2, axes, matrix, vec=True, epilogue=epilogue, plan=self)
+
+
+def use_devices(devices="all", min_pairs=None):
+    """Route the host-array entry points of this module (and with them ``gs.SRF`` / ``gs.CondSRF`` under
+    :func:`gstools_b200.enable`) through a :class:`Plan` over ``devices`` whenever a call has at least
+    ``min_pairs`` (point, mode) pairs (default 4e9: below that one GPU finishes before the fan-out pays).
+    ``devices=None`` switches back to one device.  Returns the plan (or None)."""
+    old = _PLAN["plan"]
+    if min_pairs is not None:
+        _PLAN["min_pairs"] = float(min_pairs)
+    if devices is None:
+        _PLAN["plan"] = None
+        if old is not None:
+            old.close()
+        return None
+    plan = Plan(devices)
+    if len(plan.devices) < 2:
+        plan.close()
+        plan = None
+    _PLAN["plan"] = plan
+    if old is not None and old is not plan:
+        old._finalizer()
+    return plan
+
+
+def current_plan():
+    return _PLAN["plan"]
+
+
+def _pick_plan(plan, pairs, point_epilogue, device_index=None):
+    """The plan a call runs on: the explicit one, the one its point epilogue was built for, the process-wide one
+    (big calls only), or None (one device)."""
+    if isinstance(point_epilogue, _PlanPointEpi):
+        if plan is not None and plan is not point_epilogue.plan:
+            raise ValueError("point epilogue was built for another plan")
+        return point_epilogue.plan
+    if plan is not None:
+        if point_epilogue is not None:
+            raise ValueError("a plan call needs a point epilogue made by Plan.make_point_epilogue")
+        return plan
+    auto = _PLAN["plan"]
+    if auto is None or point_epilogue is not None or pairs < _PLAN["min_pairs"]:
+        return None
+    if device_index is not None and (device_index not in auto.devices or not auto.peer_access):
+        return None
+    return auto
+
+
+# ----------------------------------------------------------------------------------------
 # flat (unstructured) entry points -- the reference signatures
 # ----------------------------------------------------------------------------------------
-def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None, point_epilogue=None):
+def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None, point_epilogue=None, plan=None):
     lib = _lib.load()
     epi = _epi_ref(epilogue)
     if sf is not None and epi is not None:
@@ -286,7 +433,7 @@ def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None, point_epilogu
     if point_epilogue is not None and (vec or sf is not None):
         raise ValueError("the per-point epilogue applies to scalar fields only")
     if any(_is_cuda_tensor(x) for x in (cov_samples, z_1, z_2, pos)):
-        return _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf, epi, point_epilogue)
+        return _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf, epi, point_epilogue, plan)
     cov = np.ascontiguousarray(_as_f64(cov_samples, "cov_samples"))
     z1 = np.ascontiguousarray(_as_f64(z_1, "z_1"))
     z2 = np.ascontiguousarray(_as_f64(z_2, "z_2"))
@@ -297,6 +444,14 @@ def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None, point_epilogu
     dim, n_modes = cov.shape
     n = p.shape[1]
     p, ld = _rows_contiguous(p)
+    plan = None if sf is not None else _pick_plan(plan, float(n) * n_modes, point_epilogue)
+    if plan is not None:
+        out = _empty_host((dim, n) if vec else (n,))
+        pe = point_epilogue.ref(n) if point_epilogue is not None else None
+        rc = lib.gsb_plan_summate(plan._handle, _ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n, _ptr(out),
+                                  max(n, 1), int(vec), epi, pe, _lib.MEM_HOST, 0, None)
+        _lib.check(rc, "plan_summate")
+        return out
     if vec:
         out = _empty_host((dim, n))
         rc = lib.gsb_summate_incompr_ex(_ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n,
@@ -324,7 +479,7 @@ def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None, point_epilogu
     return out
 
 
-def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None, epi=None, pepi=None):
+def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None, epi=None, pepi=None, plan=None):
     torch = _torch()
     dev = next(x.device for x in (pos, cov_samples, z_1, z_2) if _is_cuda_tensor(x))
 
@@ -347,6 +502,15 @@ def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None, epi=None, pepi=N
     n = p.shape[1]
     ld = ld or max(n, 1)
     stream = torch.cuda.current_stream(dev).cuda_stream
+    plan = None if sf is not None else _pick_plan(plan, float(n) * n_modes, pepi, dev.index)
+    if plan is not None:
+        out = torch.empty((dim, n) if vec else (n,), dtype=torch.float64, device=dev)
+        pe = pepi.ref(n) if pepi is not None else None
+        rc = lib.gsb_plan_summate(plan._handle, cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), ld, dim,
+                                  n_modes, n, out.data_ptr(), max(n, 1), int(vec), epi, pe, _lib.MEM_DEVICE, dev.index,
+                                  stream)
+        _lib.check(rc, "plan_summate")
+        return out
     if vec:
         out = torch.empty((dim, n), dtype=torch.float64, device=dev)
         rc = lib.gsb_summate_incompr_ex(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(),
@@ -426,7 +590,7 @@ def summate_fourier_structured(spectrum_factor, modes, z_1, z_2, axes, matrix=No
 # ----------------------------------------------------------------------------------------
 # structured (rectilinear mesh) entry points -- the side channel for mesh_type="structured"
 # ----------------------------------------------------------------------------------------
-def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None, point_epilogue=None):
+def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None, point_epilogue=None, plan=None):
     lib = _lib.load()
     epi = _epi_ref(epilogue)
     axes = list(axes)
@@ -434,7 +598,7 @@ def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None, point_e
     if point_epilogue is not None and vec:
         raise ValueError("the per-point epilogue applies to scalar fields only")
     if any(_is_cuda_tensor(x) for x in (cov_samples, z_1, z_2, *axes)):
-        return _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi, point_epilogue)
+        return _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi, point_epilogue, plan)
     cov = np.ascontiguousarray(_as_f64(cov_samples, "cov_samples"))
     z1 = np.ascontiguousarray(_as_f64(z_1, "z_1"))
     z2 = np.ascontiguousarray(_as_f64(z_2, "z_2"))
@@ -461,6 +625,15 @@ def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None, point_e
     n_batch, _, n_modes = cov3.shape
     full = ((n_batch,) if batched else ()) + ((dim,) if vec else ()) + shape
     out = _empty_host(full)
+    n_pts = int(np.prod(lens)) if dim else 0
+    plan = _pick_plan(plan, float(n_pts) * n_modes * n_batch, point_epilogue)
+    if plan is not None:
+        pe = point_epilogue.ref(n_pts) if point_epilogue is not None else None
+        rc = lib.gsb_plan_summate_structured(plan._handle, _ptr(cov3), _ptr(z1b), _ptr(z2b), _ptr(cat),
+                                             lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch,
+                                             _ptr(out), int(vec), epi, pe, _lib.MEM_HOST, 0, None)
+        _lib.check(rc, "plan_summate_structured")
+        return out
     if point_epilogue is not None:
         device = point_epilogue.device.index if point_epilogue.device is not None else get_device()
         rc = lib.gsb_summate_structured_pp(_ptr(cov3), _ptr(z1b), _ptr(z2b), _ptr(cat),
@@ -477,7 +650,7 @@ def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None, point_e
     return out
 
 
-def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi=None, pepi=None):
+def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi=None, pepi=None, plan=None):
     torch = _torch()
     dev = next(x.device for x in (cov_samples, z_1, z_2, *axes) if _is_cuda_tensor(x))
 
@@ -508,6 +681,15 @@ def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi=None, 
     full = ((n_batch,) if batched else ()) + ((dim,) if vec else ()) + shape
     out = torch.empty(full, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
+    n_pts = int(np.prod(lens)) if dim else 0
+    plan = _pick_plan(plan, float(n_pts) * n_modes * n_batch, pepi, dev.index)
+    if plan is not None:
+        pe = pepi.ref(n_pts) if pepi is not None else None
+        rc = lib.gsb_plan_summate_structured(plan._handle, cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), cat.data_ptr(),
+                                             lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch,
+                                             out.data_ptr(), int(vec), epi, pe, _lib.MEM_DEVICE, dev.index, stream)
+        _lib.check(rc, "plan_summate_structured")
+        return out
     if pepi is not None:
         rc = lib.gsb_summate_structured_pp(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), cat.data_ptr(),
                                            lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch,
@@ -521,6 +703,42 @@ def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi=None, 
             epi, _lib.MEM_DEVICE, dev.index, stream)
     _lib.check(rc, "summate_incompr_structured" if vec else "summate_structured")
     return out
+
+
+def structured_slab_into(cov_samples, z_1, z_2, axes, matrix, lo, hi, out_ptr, *, incompr=False, epilogue=None):
+    """Evaluate the entries ``[lo, hi)`` of axis 0 of the mesh ``axes`` and store them in place into the FULL
+    field at the raw device address ``out_ptr`` (``gsb_summate_structured_slab``, device route).  Inputs are CUDA
+    tensors on the calling rank's device; ``out_ptr`` may be memory of another GPU mapped into this process (peer
+    access / :func:`gstools_b200.dist.open_peer_field`): the kernel then stores over NVLink and the sum needs no
+    gather afterwards.  Work is enqueued on the current torch stream; nothing is returned."""
+    lib = _lib.load()
+    torch = _torch()
+    dev = next(x.device for x in (cov_samples, z_1, z_2, *axes) if _is_cuda_tensor(x))
+
+    def prep(x):
+        return torch.as_tensor(x, dtype=torch.float64, device=dev).contiguous()
+
+    cov, z1, z2 = prep(cov_samples), prep(z_1), prep(z_2)
+    if cov.ndim == 2:
+        cov, z1, z2 = cov[None], z1[None], z2[None]
+    ax = [prep(a).reshape(-1) for a in axes]
+    dim = len(ax)
+    if cov.ndim != 3 or cov.shape[1] != dim or tuple(z1.shape) != (cov.shape[0], cov.shape[2]) or z2.shape != z1.shape:
+        raise ValueError("cov_samples (B, dim, N) / (dim, N); z_1, z_2 (B, N) / (N,); len(axes) == dim")
+    lens = np.array([int(a.shape[0]) for a in ax], dtype=np.int64)
+    cat = torch.cat(ax)
+    mat_ptr = None
+    if matrix is not None:
+        mat = np.ascontiguousarray(_as_f64(matrix, "matrix"))
+        if mat.shape != (dim, dim):
+            raise ValueError("matrix must have shape (dim, dim)")
+        mat_ptr = _ptr(mat)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rc = lib.gsb_summate_structured_slab(cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), cat.data_ptr(),
+                                         lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, cov.shape[2], cov.shape[0],
+                                         int(lo), int(hi), int(out_ptr), int(bool(incompr)), _epi_ref(epilogue), None,
+                                         _lib.MEM_DEVICE, dev.index, stream)
+    _lib.check(rc, "summate_structured_slab")
 
 
 def summate_structured(cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=None, point_epilogue=None):

@@ -5,9 +5,15 @@
 // there is no fallback: without a CUDA device every compute entry returns GSB_ERR_NO_DEVICE.
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
+
+#include <cuda.h>
 
 #include "gsb_common.cuh"
 #include "gsb_direct.cuh"
@@ -266,13 +272,15 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
 static int summate_impl(const double *cov, const double *z1, const double *z2, const double *sf,
                         const double *pos, int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts,
                         double *out, int64_t out_ld, bool vec, const gsb_epilogue *epilogue, int mem,
-                        int device, void *stream, const gsb_point_epilogue *pepi = nullptr)
+                        int device, void *stream, const gsb_point_epilogue *pepi = nullptr, int64_t epi_first = 0)
 {
     DeviceGuard guard;
     GSB_TRY(check_common(cov, z1, z2, dim, n_modes));
     GSB_TRY(check_epilogue(epilogue));
     GSB_TRY(check_point_epilogue(pepi, vec));
-    const Epi epi = make_epi(epilogue, pepi);
+    // epi_first: the call evaluates the points [epi_first, epi_first + n_pts) of a bigger field (multi-GPU plan);
+    // the per-point arrays of `pepi` describe the whole field
+    const Epi epi = epi_shift(make_epi(epilogue, pepi), epi_first);
     if (n_pts < 0) return fail(GSB_ERR_ARGUMENT, "n_pts must be >= 0");
     if (vec && dim != 2 && dim != 3)
         return fail(GSB_ERR_ARGUMENT,
@@ -351,6 +359,8 @@ static int summate_impl(const double *cov, const double *z1, const double *z2, c
 // ---------------------------------------------------------------------------------------------
 // structured path
 // ---------------------------------------------------------------------------------------------
+struct SlabOpt { int64_t lo, hi; };     // range of axis 0 evaluated by one device of a multi-GPU plan
+
 struct MeshInfo {
     int dim;
     int64_t len[GSB_MAX_DIM];
@@ -436,7 +446,8 @@ static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int6
 
 static int sk_on_device(const double *d_cov, const double *d_z1, const double *d_z2, const double *d_sf,
                         const double *d_axes, const MeshInfo &mesh, const SkLayout &L, int64_t n_modes, int64_t n_batch,
-                        bool vec, const Epi &epi, double *d_out, double *h_out, DeviceState &dev, cudaStream_t st)
+                        bool vec, const Epi &epi, double *d_out, int64_t d_fstride, double *h_out, int64_t h_fstride,
+                        DeviceState &dev, cudaStream_t st)
 {
     const int dim = mesh.dim;
     const int ncomp = vec ? dim : 1;
@@ -533,7 +544,7 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
     sp.lc = L.lc;
     sp.n_modes_pad = n_modes_pad;
     sp.out = d_out;
-    sp.out_fstride = mesh.n;
+    sp.out_fstride = d_fstride;
     sp.epi = epi;
     const bool partial = (L.ly % SK_TM) != 0 || (L.lc % SK_TN) != 0;
     sp.slots = slots;
@@ -555,9 +566,22 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
             cudaEvent_t ev = dev.contract_events[k % DeviceState::N_CHUNK_EVENTS];
             GSB_CUDA(cudaEventRecord(ev, st));
             GSB_CUDA(cudaStreamWaitEvent(dev.streams[1], ev, 0));
-            const size_t off = (size_t)u0 * L.ly * L.lc;
-            GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * (size_t)(u1 - u0) * L.ly * L.lc,
-                                     cudaMemcpyDeviceToHost, dev.streams[1]));
+            // units [u0, u1): unit u = z * n_slow + slow lies at field z, offset slow * ly * lc (pieces of a mesh with
+            // inner slow axes are whole fields).  One copy when both sides use the same field stride, else one per field
+            const int64_t unit_elems = L.ly * L.lc;
+            if (d_fstride == h_fstride && d_fstride == mesh.n) {
+                const size_t off = (size_t)u0 * unit_elems;
+                GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * (size_t)(u1 - u0) * unit_elems,
+                                         cudaMemcpyDeviceToHost, dev.streams[1]));
+            } else {
+                for (int64_t z = u0 / L.n_slow; z * L.n_slow < u1; ++z) {
+                    const int64_t a = std::max(u0, z * L.n_slow) - z * L.n_slow;
+                    const int64_t b = std::min(u1, (z + 1) * L.n_slow) - z * L.n_slow;
+                    GSB_CUDA(cudaMemcpyAsync(h_out + z * h_fstride + a * unit_elems, d_out + z * d_fstride + a * unit_elems,
+                                             sizeof(double) * (size_t)(b - a) * unit_elems, cudaMemcpyDeviceToHost,
+                                             dev.streams[1]));
+                }
+            }
         }
     }
     if (h_out) {
@@ -574,8 +598,8 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
 // for all of it before this function returns.
 static int structured_on_device(const double *d_cov, const double *d_z1, const double *d_z2,
                                 const double *d_sf, const double *d_axes, const MeshInfo &mesh, int64_t n_modes,
-                                int64_t n_batch, bool vec, const Epi &epi, double *d_out, double *h_out,
-                                DeviceState &dev, cudaStream_t st)
+                                int64_t n_batch, bool vec, const Epi &epi, double *d_out, int64_t d_fstride,
+                                double *h_out, int64_t h_fstride, DeviceState &dev, cudaStream_t st)
 {
     const int dim = mesh.dim;
     const int ncomp = vec ? dim : 1;
@@ -641,16 +665,17 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
             GSB_TRY(pack_modes(d_cov + b * dim * n_modes, d_z1 + b * n_modes, d_z2 + b * n_modes,
                                d_sf ? d_sf + b * n_modes : nullptr, dim, n_modes, vec, &d_recs, &pad, scr, st));
             GSB_TRY(direct_on_device(d_recs, pad, d_pos, mesh.n, dim, vec, mesh.n,
-                                     d_out + b * ncomp * mesh.n, mesh.n, epi, dev, scr, st));
+                                     d_out + b * ncomp * d_fstride, d_fstride, epi, dev, scr, st));
         }
         if (h_out) {
-            GSB_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * n_batch * ncomp * mesh.n,
-                                     cudaMemcpyDeviceToHost, st));
+            GSB_CUDA(cudaMemcpy2DAsync(h_out, sizeof(double) * h_fstride, d_out, sizeof(double) * d_fstride,
+                                       sizeof(double) * mesh.n, (size_t)(n_batch * ncomp), cudaMemcpyDeviceToHost, st));
         }
         return GSB_OK;
     }
 
-    GSB_TRY(sk_on_device(d_cov, d_z1, d_z2, d_sf, d_axes, mesh, layout, n_modes, n_batch, vec, epi, d_out, h_out, dev, st));
+    GSB_TRY(sk_on_device(d_cov, d_z1, d_z2, d_sf, d_axes, mesh, layout, n_modes, n_batch, vec, epi, d_out, d_fstride,
+                         h_out, h_fstride, dev, st));
     g_cnt_separable.fetch_add(1);
     if (layout.n_col_axes == 2) g_cnt_folded.fetch_add(1);
     if (g_opt_trace.load() && !g_trace.empty()) {
@@ -671,13 +696,13 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
                            const double *axes, const int64_t *axis_len, const double *matrix, int dim,
                            int64_t n_modes, int64_t n_batch, double *out, bool vec,
                            const gsb_epilogue *epilogue, int mem, int device, void *stream,
-                           const gsb_point_epilogue *pepi = nullptr)
+                           const gsb_point_epilogue *pepi = nullptr, const SlabOpt *slab = nullptr)
 {
     DeviceGuard guard;
     GSB_TRY(check_common(cov, z1, z2, dim, n_modes));
     GSB_TRY(check_epilogue(epilogue));
     GSB_TRY(check_point_epilogue(pepi, vec));
-    const Epi epi = make_epi(epilogue, pepi);
+    Epi epi = make_epi(epilogue, pepi);
     if (!axis_len) return fail(GSB_ERR_ARGUMENT, "axis_len must not be NULL");
     if (n_batch < 1) return fail(GSB_ERR_ARGUMENT, "n_batch must be >= 1");
     if (vec && dim != 2 && dim != 3)
@@ -697,6 +722,19 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
     }
     if (mesh.n == 0) return GSB_OK;
     if (!axes || !out) return fail(GSB_ERR_ARGUMENT, "axes and out must not be NULL");
+    // a slab evaluates the entries [lo, hi) of axis 0; `out` and the per-point arrays still describe the FULL mesh
+    const int64_t fstride = mesh.n;
+    if (slab) {
+        if (slab->lo < 0 || slab->hi < slab->lo || slab->hi > mesh.len[0])
+            return fail(GSB_ERR_ARGUMENT, "slab outside axis 0");
+        const int64_t rest = mesh.n / mesh.len[0];
+        mesh.off[0] += slab->lo;
+        mesh.len[0] = slab->hi - slab->lo;
+        mesh.n = mesh.len[0] * rest;
+        if (mesh.n == 0) return GSB_OK;
+        out += slab->lo * rest;
+        epi = epi_shift(epi, slab->lo * rest);
+    }
     mesh.n_rows = mesh.n / mesh.len[dim - 1];
     std::memset(mesh.matrix, 0, sizeof mesh.matrix);
     mesh.identity = (matrix == nullptr);
@@ -731,7 +769,8 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
     if (mem == GSB_MEM_DEVICE) {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         std::lock_guard<std::mutex> lock(dev->call_mutex);
-        return structured_on_device(cov, z1, z2, sf, axes, mesh, n_modes, n_batch, vec, epi, out, nullptr, *dev, st);
+        return structured_on_device(cov, z1, z2, sf, axes, mesh, n_modes, n_batch, vec, epi, out, fstride, nullptr, 0,
+                                    *dev, st);
     }
     std::lock_guard<std::mutex> lock(dev->call_mutex);
     cudaStream_t s0 = dev->streams[0];
@@ -753,7 +792,8 @@ static int structured_impl(const double *cov, const double *z1, const double *z2
         GSB_CUDA(cudaMemcpyAsync(d_z2, z2, sizeof(double) * n_batch * n_modes, cudaMemcpyHostToDevice, s0));
     }
     GSB_CUDA(cudaMemcpyAsync(d_axes, axes, sizeof(double) * mesh.total_axes, cudaMemcpyHostToDevice, s0));
-    GSB_TRY(structured_on_device(d_cov, d_z1, d_z2, d_sf, d_axes, mesh, n_modes, n_batch, vec, epi, d_out, out, *dev, s0));
+    GSB_TRY(structured_on_device(d_cov, d_z1, d_z2, d_sf, d_axes, mesh, n_modes, n_batch, vec, epi, d_out, mesh.n, out,
+                                 fstride, *dev, s0));
     GSB_CUDA(cudaStreamSynchronize(s0));
     return GSB_OK;
 }
@@ -1223,6 +1263,250 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double *sink, int iters,
     if (s == 12345.678) sink[0] = s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU plan: one host thread per device; a call is cut into independent
+// shares (point ranges, axis-0 slabs, batch entries) -- no inter-GPU traffic during the sum
+// ---------------------------------------------------------------------------------------------
+struct PlanWorker {
+    int device = 0;
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool pending = false, finished = true, quit = false;
+    int rc = GSB_OK;
+    std::string err;
+    cudaEvent_t begin_ev = nullptr;   // recorded on the caller's stream when this device is the home device
+    cudaEvent_t done_ev = nullptr;    // device route: this device's share is enqueued up to here
+
+    void loop()
+    {
+        cudaSetDevice(device);
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return pending || quit; });
+            if (quit) return;
+            std::function<int()> j = std::move(job);
+            pending = false;
+            lk.unlock();
+            const int r = j();
+            std::string e = (r != GSB_OK) ? last_error_ref() : std::string();
+            lk.lock();
+            rc = r;
+            err = std::move(e);
+            finished = true;
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<int()> j)
+    {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(j);
+        pending = true;
+        finished = false;
+        cv.notify_all();
+    }
+    int wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return finished; });
+        return rc;
+    }
+};
+
+inline void plan_share(int64_t n, int parts, int part, int64_t *lo, int64_t *hi)
+{
+    const int64_t base = n / parts, rem = n % parts;
+    *lo = part * base + std::min<int64_t>(part, rem);
+    *hi = *lo + base + (part < rem ? 1 : 0);
+}
+
+}  // namespace gsb
+
+struct gsb_plan {
+    std::vector<std::unique_ptr<gsb::PlanWorker>> workers;
+    std::mutex call_mutex;
+    bool peer_ok = true;
+};
+
+namespace gsb {
+
+// hand every device its job, wait for all, report the first failure on the calling thread
+static int plan_run(gsb_plan *plan, const std::vector<std::function<int()>> &jobs)
+{
+    const size_t n = plan->workers.size();
+    for (size_t g = 0; g < n; ++g)
+        if (jobs[g]) plan->workers[g]->submit(jobs[g]);
+    int rc = GSB_OK;
+    std::string err;
+    for (size_t g = 0; g < n; ++g) {
+        if (!jobs[g]) continue;
+        const int r = plan->workers[g]->wait();
+        if (r != GSB_OK && rc == GSB_OK) {
+            rc = r;
+            err = "device " + std::to_string(plan->workers[g]->device) + ": " + plan->workers[g]->err;
+        }
+    }
+    return rc == GSB_OK ? GSB_OK : fail(rc, err);
+}
+
+static int plan_home(const gsb_plan *plan, int mem, int home_device, int *home_idx)
+{
+    *home_idx = -1;
+    if (mem != GSB_MEM_HOST && mem != GSB_MEM_DEVICE)
+        return fail(GSB_ERR_ARGUMENT, "mem must be GSB_MEM_HOST or GSB_MEM_DEVICE");
+    if (mem == GSB_MEM_HOST) return GSB_OK;
+    for (size_t g = 0; g < plan->workers.size(); ++g)
+        if (plan->workers[g]->device == home_device) *home_idx = (int)g;
+    if (*home_idx < 0) return fail(GSB_ERR_ARGUMENT, "plan: home_device is not a device of the plan");
+    if (!plan->peer_ok && plan->workers.size() > 1)
+        return fail(GSB_ERR_ARGUMENT, "plan: no peer access between the plan's devices; use GSB_MEM_HOST");
+    return GSB_OK;
+}
+
+// Device route of a plan call.  `share(g, st, scr)` enqueues device g's share on its stream `st` (scr: scratch that
+// lives until the share has run).  The shares are ordered after everything `stream` (home device) holds on entry, and
+// `stream` waits for all of them.
+static int plan_run_device(gsb_plan *plan, int home_idx, void *stream,
+                           const std::function<int(int, cudaStream_t, Scratch &)> &share)
+{
+    DeviceGuard guard;
+    PlanWorker &home = *plan->workers[(size_t)home_idx];
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    GSB_CUDA(cudaSetDevice(home.device));
+    GSB_CUDA(cudaEventRecord(home.begin_ev, user));
+    std::vector<std::function<int()>> jobs(plan->workers.size());
+    for (size_t g = 0; g < plan->workers.size(); ++g) {
+        PlanWorker *w = plan->workers[g].get();
+        cudaEvent_t begin = home.begin_ev;
+        jobs[g] = [w, g, begin, &share]() -> int {
+            DeviceState *dev = nullptr;
+            GSB_TRY(ensure_device(w->device, &dev));
+            cudaStream_t st = dev->streams[2];
+            GSB_CUDA(cudaStreamWaitEvent(st, begin, 0));
+            {
+                Scratch scr(st);
+                GSB_TRY(share((int)g, st, scr));
+            }
+            GSB_CUDA(cudaEventRecord(w->done_ev, st));
+            return GSB_OK;
+        };
+    }
+    GSB_TRY(plan_run(plan, jobs));
+    for (auto &w : plan->workers) GSB_CUDA(cudaStreamWaitEvent(user, w->done_ev, 0));
+    return GSB_OK;
+}
+
+// a private copy of a small input array of the home device on the current device (peer reads of the mode set from
+// every table entry would cross NVLink once per entry)
+static int plan_stage(const double *src, size_t count, bool local, const double **dst, Scratch &scr, cudaStream_t st)
+{
+    if (local || !src || count == 0) {
+        *dst = src;
+        return GSB_OK;
+    }
+    double *p = nullptr;
+    GSB_TRY(scr.alloc(&p, count));
+    GSB_CUDA(cudaMemcpyAsync(p, src, sizeof(double) * count, cudaMemcpyDefault, st));
+    *dst = p;
+    return GSB_OK;
+}
+
+static int plan_summate_impl(gsb_plan *plan, const double *cov, const double *z1, const double *z2, const double *pos,
+                             int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts, double *out, int64_t out_ld,
+                             bool vec, const gsb_epilogue *epi, const gsb_point_epilogue *pepi, int mem,
+                             int home_device, void *stream)
+{
+    if (!plan) return fail(GSB_ERR_ARGUMENT, "plan must not be NULL");
+    std::lock_guard<std::mutex> lock(plan->call_mutex);
+    const int G = (int)plan->workers.size();
+    int home_idx = -1;
+    GSB_TRY(plan_home(plan, mem, home_device, &home_idx));
+    if (n_pts < 0) return fail(GSB_ERR_ARGUMENT, "n_pts must be >= 0");
+    if (!vec) out_ld = n_pts;
+    auto share_call = [=](int g, const double *c, const double *a, const double *b, int device, void *st) -> int {
+        int64_t lo, hi;
+        plan_share(n_pts, G, g, &lo, &hi);
+        if (hi == lo) return GSB_OK;
+        return summate_impl(c, a, b, nullptr, pos + lo, pos_ld, dim, n_modes, hi - lo, out + lo, out_ld, vec, epi, mem,
+                            device, st, pepi ? pepi + g : nullptr, lo);
+    };
+    if (mem == GSB_MEM_HOST) {
+        std::vector<std::function<int()>> jobs((size_t)G);
+        for (int g = 0; g < G; ++g) {
+            const int device = plan->workers[(size_t)g]->device;
+            jobs[(size_t)g] = [=]() { return share_call(g, cov, z1, z2, device, nullptr); };
+        }
+        return plan_run(plan, jobs);
+    }
+    return plan_run_device(plan, home_idx, stream, [&](int g, cudaStream_t st, Scratch &scr) -> int {
+        const bool local = (g == home_idx);
+        const double *c, *a, *b;
+        GSB_TRY(plan_stage(cov, (size_t)dim * n_modes, local, &c, scr, st));
+        GSB_TRY(plan_stage(z1, (size_t)n_modes, local, &a, scr, st));
+        GSB_TRY(plan_stage(z2, (size_t)n_modes, local, &b, scr, st));
+        return share_call(g, c, a, b, plan->workers[(size_t)g]->device, st);
+    });
+}
+
+static int plan_structured_impl(gsb_plan *plan, const double *cov, const double *z1, const double *z2,
+                                const double *axes, const int64_t *axis_len, const double *matrix, int dim,
+                                int64_t n_modes, int64_t n_batch, double *out, bool vec, const gsb_epilogue *epi,
+                                const gsb_point_epilogue *pepi, int mem, int home_device, void *stream)
+{
+    if (!plan) return fail(GSB_ERR_ARGUMENT, "plan must not be NULL");
+    std::lock_guard<std::mutex> lock(plan->call_mutex);
+    const int G = (int)plan->workers.size();
+    int home_idx = -1;
+    GSB_TRY(plan_home(plan, mem, home_device, &home_idx));
+    if (dim < 1 || dim > GSB_MAX_DIM) return fail(GSB_ERR_ARGUMENT, "dim must be in 1..8");
+    if (!axis_len) return fail(GSB_ERR_ARGUMENT, "axis_len must not be NULL");
+    if (n_batch < 1) return fail(GSB_ERR_ARGUMENT, "n_batch must be >= 1");
+    int64_t n = 1, total_axes = 0;
+    for (int t = 0; t < dim; ++t) {
+        if (axis_len[t] < 0) return fail(GSB_ERR_ARGUMENT, "axis_len must be >= 0");
+        n *= axis_len[t];
+        total_axes += axis_len[t];
+    }
+    const int ncomp = vec ? dim : 1;
+    const bool by_batch = n_batch >= G;      // ensembles: whole fields per device; else slabs of every field
+    const int64_t len0 = axis_len[0];
+    std::vector<int64_t> lens(axis_len, axis_len + dim);
+    auto share_call = [=](int g, const double *c, const double *a, const double *b, const double *ax, int device,
+                          void *st) -> int {
+        int64_t lo, hi;
+        const gsb_point_epilogue *pe = pepi ? pepi + g : nullptr;
+        if (by_batch) {
+            plan_share(n_batch, G, g, &lo, &hi);
+            if (hi == lo) return GSB_OK;
+            return structured_impl(c + lo * dim * n_modes, a + lo * n_modes, b + lo * n_modes, nullptr, ax, lens.data(),
+                                   matrix, dim, n_modes, hi - lo, out + lo * ncomp * n, vec, epi, mem, device, st, pe);
+        }
+        plan_share(len0, G, g, &lo, &hi);
+        if (hi == lo) return GSB_OK;
+        const SlabOpt slab{lo, hi};
+        return structured_impl(c, a, b, nullptr, ax, lens.data(), matrix, dim, n_modes, n_batch, out, vec, epi, mem, device,
+                               st, pe, &slab);
+    };
+    if (mem == GSB_MEM_HOST) {
+        std::vector<std::function<int()>> jobs((size_t)G);
+        for (int g = 0; g < G; ++g) {
+            const int device = plan->workers[(size_t)g]->device;
+            jobs[(size_t)g] = [=]() { return share_call(g, cov, z1, z2, axes, device, nullptr); };
+        }
+        return plan_run(plan, jobs);
+    }
+    return plan_run_device(plan, home_idx, stream, [&](int g, cudaStream_t st, Scratch &scr) -> int {
+        const bool local = (g == home_idx);
+        const double *c, *a, *b, *ax;
+        GSB_TRY(plan_stage(cov, (size_t)n_batch * dim * n_modes, local, &c, scr, st));
+        GSB_TRY(plan_stage(z1, (size_t)n_batch * n_modes, local, &a, scr, st));
+        GSB_TRY(plan_stage(z2, (size_t)n_batch * n_modes, local, &b, scr, st));
+        GSB_TRY(plan_stage(axes, (size_t)total_axes, local, &ax, scr, st));
+        return share_call(g, c, a, b, ax, plan->workers[(size_t)g]->device, st);
+    });
+}
+
 }  // namespace gsb
 
 // =============================================================================================
@@ -1450,6 +1734,177 @@ int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int de
     g_launches.fetch_add(1);
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;
+}
+
+int gsb_summate_structured_slab(const double *cov_samples, const double *z_1, const double *z_2, const double *axes,
+                                const int64_t *axis_len, const double *matrix, int dim, int64_t n_modes,
+                                int64_t n_batch, int64_t slab_lo, int64_t slab_hi, double *out, int incompr,
+                                const gsb_epilogue *epi, const gsb_point_epilogue *pepi, int mem, int device,
+                                void *stream)
+{
+    const SlabOpt slab{slab_lo, slab_hi};
+    return structured_impl(cov_samples, z_1, z_2, nullptr, axes, axis_len, matrix, dim, n_modes, n_batch, out,
+                           incompr != 0, epi, mem, device, stream, pepi, &slab);
+}
+
+int gsb_ipc_export(const void *dev_ptr, int device, unsigned char *handle, int64_t *offset)
+{
+    if (!dev_ptr || !handle || !offset) return fail(GSB_ERR_ARGUMENT, "ipc_export: NULL pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == GSB_IPC_HANDLE_BYTES, "handle size");
+    DeviceGuard guard;
+    DeviceState *dev = nullptr;
+    GSB_TRY(ensure_device(device, &dev));
+    cudaIpcMemHandle_t h;
+    GSB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    // the handle names the whole allocation: report where dev_ptr lies inside it
+    // (driver entry point through the runtime: the library does not link libcuda, so it still loads on a machine
+    // without a driver -- where every compute entry fails loudly instead)
+    typedef CUresult (*range_fn)(CUdeviceptr *, size_t *, CUdeviceptr);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GSB_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (!fn || qres != cudaDriverEntryPointSuccess ||
+        reinterpret_cast<range_fn>(fn)(&base, &size, reinterpret_cast<CUdeviceptr>(dev_ptr)) != CUDA_SUCCESS)
+        return fail(GSB_ERR_CUDA, "ipc_export: cuMemGetAddressRange failed");
+    std::memcpy(handle, &h, sizeof h);
+    *offset = (int64_t)(reinterpret_cast<CUdeviceptr>(dev_ptr) - base);
+    return GSB_OK;
+}
+
+int gsb_ipc_open(const unsigned char *handle, int device, void **base)
+{
+    if (!handle || !base) return fail(GSB_ERR_ARGUMENT, "ipc_open: NULL pointer");
+    DeviceGuard guard;
+    DeviceState *dev = nullptr;
+    GSB_TRY(ensure_device(device, &dev));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    GSB_CUDA(cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess));
+    return GSB_OK;
+}
+
+int gsb_ipc_close(void *base, int device)
+{
+    if (!base) return GSB_OK;
+    DeviceGuard guard;
+    DeviceState *dev = nullptr;
+    GSB_TRY(ensure_device(device, &dev));
+    GSB_CUDA(cudaIpcCloseMemHandle(base));
+    return GSB_OK;
+}
+
+int gsb_plan_share(int64_t n, int parts, int part, int64_t *lo, int64_t *hi)
+{
+    if (!lo || !hi) return fail(GSB_ERR_ARGUMENT, "NULL output pointer");
+    if (n < 0 || parts < 1 || part < 0 || part >= parts) return fail(GSB_ERR_ARGUMENT, "plan_share: invalid part / parts");
+    plan_share(n, parts, part, lo, hi);
+    return GSB_OK;
+}
+
+int gsb_plan_create(const int *devices, int n_devices, gsb_plan **plan)
+{
+    if (!plan) return fail(GSB_ERR_ARGUMENT, "plan must not be NULL");
+    *plan = nullptr;
+    DeviceGuard guard;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(GSB_ERR_NO_DEVICE, "no CUDA device available: the B200 backend has no CPU fallback");
+    }
+    std::vector<int> devs;
+    if (!devices || n_devices <= 0) {
+        for (int d = 0; d < count && d < 64; ++d) devs.push_back(d);
+    } else {
+        devs.assign(devices, devices + n_devices);
+    }
+    // (a device may be listed more than once: its shares then run one after the other -- this is how the share
+    // logic is tested on a one-GPU box)
+    if (devs.size() > 64) return fail(GSB_ERR_ARGUMENT, "plan: too many devices");
+    for (size_t i = 0; i < devs.size(); ++i)
+        if (devs[i] < 0 || devs[i] >= count || devs[i] >= 64) return fail(GSB_ERR_ARGUMENT, "plan: invalid device index");
+    std::unique_ptr<gsb_plan> p(new gsb_plan);
+    for (int d : devs) {
+        DeviceState *dev = nullptr;
+        GSB_TRY(ensure_device(d, &dev));        // streams, pool settings; leaves d current
+        std::unique_ptr<PlanWorker> w(new PlanWorker);
+        w->device = d;
+        GSB_CUDA(cudaEventCreateWithFlags(&w->begin_ev, cudaEventDisableTiming));
+        GSB_CUDA(cudaEventCreateWithFlags(&w->done_ev, cudaEventDisableTiming));
+        // peer access to every other device of the plan (the device route stores into the home device's memory)
+        for (int o : devs) {
+            if (o == d) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, d, o) != cudaSuccess || !can) {
+                cudaGetLastError();
+                p->peer_ok = false;
+                continue;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(o, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) p->peer_ok = false;
+            cudaGetLastError();
+        }
+        p->workers.push_back(std::move(w));
+    }
+    for (auto &w : p->workers) {
+        PlanWorker *raw = w.get();
+        raw->th = std::thread([raw]() { raw->loop(); });
+    }
+    *plan = p.release();
+    return GSB_OK;
+}
+
+int gsb_plan_destroy(gsb_plan *plan)
+{
+    if (!plan) return GSB_OK;
+    DeviceGuard guard;
+    {
+        std::lock_guard<std::mutex> lock(plan->call_mutex);
+        for (auto &w : plan->workers) {
+            {
+                std::lock_guard<std::mutex> lk(w->m);
+                w->quit = true;
+                w->cv.notify_all();
+            }
+            if (w->th.joinable()) w->th.join();
+            if (cudaSetDevice(w->device) == cudaSuccess) {
+                cudaStreamSynchronize(g_dev[w->device].streams[2]);
+                cudaEventDestroy(w->begin_ev);
+                cudaEventDestroy(w->done_ev);
+            }
+            cudaGetLastError();
+        }
+    }
+    delete plan;
+    return GSB_OK;
+}
+
+int gsb_plan_info(const gsb_plan *plan, int *n_devices, int *devices, int *peer_access)
+{
+    if (!plan || !n_devices) return fail(GSB_ERR_ARGUMENT, "plan and n_devices must not be NULL");
+    *n_devices = (int)plan->workers.size();
+    if (devices)
+        for (size_t g = 0; g < plan->workers.size(); ++g) devices[g] = plan->workers[g]->device;
+    if (peer_access) *peer_access = plan->peer_ok ? 1 : 0;
+    return GSB_OK;
+}
+
+int gsb_plan_summate(gsb_plan *plan, const double *cov_samples, const double *z_1, const double *z_2, const double *pos,
+                     int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts, double *out, int64_t out_ld, int incompr,
+                     const gsb_epilogue *epi, const gsb_point_epilogue *pepi, int mem, int home_device, void *stream)
+{
+    return plan_summate_impl(plan, cov_samples, z_1, z_2, pos, pos_ld, dim, n_modes, n_pts, out, out_ld, incompr != 0, epi,
+                             pepi, mem, home_device, stream);
+}
+
+int gsb_plan_summate_structured(gsb_plan *plan, const double *cov_samples, const double *z_1, const double *z_2,
+                                const double *axes, const int64_t *axis_len, const double *matrix, int dim,
+                                int64_t n_modes, int64_t n_batch, double *out, int incompr, const gsb_epilogue *epi,
+                                const gsb_point_epilogue *pepi, int mem, int home_device, void *stream)
+{
+    return plan_structured_impl(plan, cov_samples, z_1, z_2, axes, axis_len, matrix, dim, n_modes, n_batch, out,
+                                incompr != 0, epi, pepi, mem, home_device, stream);
 }
 
 int gsb_release_memory(int device)

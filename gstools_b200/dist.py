@@ -9,8 +9,12 @@ so the path shards into independent units:
 * ensembles of seeds    -> contiguous ranges of realisations (README.md:255-257 idiom).
 
 NCCL (``torch.distributed``) is used only when the caller asks for the field as ONE array:
-:func:`gather_field` all-gathers or gathers the per-rank slabs.  The compute functions are
-injectable so the partition + gather logic is testable on CPU with the gloo backend.
+:func:`gather_field` all-gathers or gathers finished per-rank slabs straight into the destination
+array; :func:`summate_structured_gathered` overlaps that gather with the sum -- either NCCL
+send/recv of row pieces on a side stream while the next piece contracts (``mode="nccl"``), or no
+collective at all: the destination field of rank ``dst`` is mapped into every rank (CUDA IPC) and
+each rank's contraction kernel stores its slab there over NVLink (``mode="p2p"``).  The compute
+functions are injectable so the partition + gather logic is testable on CPU with the gloo backend.
 """
 
 from __future__ import annotations
@@ -26,6 +30,9 @@ __all__ = [
     "ensemble_sharded",
     "krige_evaluate_sharded",
     "gather_field",
+    "piece_bounds",
+    "summate_structured_gathered",
+    "open_peer_field",
 ]
 
 
@@ -116,7 +123,8 @@ def gather_field(local, n_total: int, axis: int = 0, group=None, dst=None):
 
     ``local`` is this rank's block (torch tensor on the rank's device, or numpy for gloo/CPU),
     split along ``axis`` according to :func:`shard_range`.  ``dst=None`` -> every rank gets the
-    field (all-gather); ``dst=r`` -> only rank r does, others get ``None``.
+    field (all-gather); ``dst=r`` -> only rank r does, others get ``None``.  Every slab travels
+    straight into its place of the destination array (grouped send/recv, no padding, no concatenation).
     """
     import torch
 
@@ -127,23 +135,225 @@ def gather_field(local, n_total: int, axis: int = 0, group=None, dst=None):
     if world == 1:
         return local
     t = t.movedim(axis, 0).contiguous()
-    sizes = [hi - lo for lo, hi in (shard_range(n_total, r, world) for r in range(world))]
-    if t.shape[0] != sizes[rank]:
+    ranges = [shard_range(n_total, r, world) for r in range(world)]
+    if t.shape[0] != ranges[rank][1] - ranges[rank][0]:
         raise ValueError("local block does not match shard_range(n_total, rank, world)")
-    # collectives want equal shapes on every rank: pad the short slabs by one row, trim after
-    m = max(sizes)
-    if t.shape[0] < m:
-        pad = torch.zeros((m - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        t = torch.cat([t, pad], dim=0)
+    receiver = dst is None or rank == dst
     full = None
-    if dst is None:
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t, group=group)
+    ops = []
+    if receiver:
+        full = torch.empty((n_total,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        full[ranges[rank][0]:ranges[rank][1]].copy_(t)
+        for r, (lo, hi) in enumerate(ranges):
+            if r != rank and hi > lo:
+                ops.append(dist.P2POp(dist.irecv, full[lo:hi], _global_rank(r, group), group))
+    if t.shape[0] > 0:
+        for q in (range(world) if dst is None else [dst]):
+            if q != rank:
+                ops.append(dist.P2POp(dist.isend, t, _global_rank(q, group), group))
+    for req in (dist.batch_isend_irecv(ops) if ops else []):
+        req.wait()
+    if full is None:
+        return None
+    full = full.movedim(0, axis)
+    return full.numpy() if was_numpy else full
+
+
+def _global_rank(r, group):
+    dist = _dist()
+    return r if group is None else dist.get_global_rank(group, r)
+
+
+def piece_bounds(n: int, pieces: int):
+    """Cut ``n`` rows into at most ``pieces`` pieces of DECREASING size (1/2, 1/4, ..., the last two equal): the
+    transfer of a piece hides behind the contraction of the next, and what stays exposed after the last
+    contraction is only the smallest piece.  Returns the cut positions ``[0, ..., n]``."""
+    n, pieces = int(n), max(1, min(int(pieces), int(n)))
+    cuts, rem = [0], n
+    for k in range(pieces - 1):
+        take = min(max(1, rem // 2), rem - (pieces - 1 - k))
+        cuts.append(cuts[-1] + take)
+        rem -= take
+    if n > 0 or not cuts[1:]:
+        cuts.append(n)
+    return cuts
+
+
+_PEER = {}      # (shape, dst, group id) -> dict(full=tensor on dst | None, ptr=mapped address, base=..., device=...)
+
+
+def open_peer_field(shape, dst=0, group=None, device=None):
+    """The gathered field of rank ``dst`` -- a float64 CUDA tensor of ``shape`` -- mapped into EVERY rank of the
+    group (``gsb_ipc_export`` / ``gsb_ipc_open``: CUDA IPC + peer access over NVLink; one node).  Returns
+    ``(tensor or None, address)``: the tensor on ``dst``, and on every rank the address under which this rank's
+    kernels can store into it.  Collective (handles are exchanged once per shape and cached; the buffer is REUSED by
+    later calls with the same shape)."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+
+    dist = _dist()
+    rank, world = _rank_world(group)
+    key = (tuple(int(v) for v in shape), int(dst), id(group))
+    hit = _PEER.get(key)
+    if hit is not None:
+        return hit["full"], hit["ptr"]
+    lib = _lib.load()
+    dev_index = torch.cuda.current_device() if device is None else int(device)
+    payload = [None]
+    full = None
+    if rank == dst:
+        full = torch.empty(key[0], dtype=torch.float64, device=torch.device("cuda", dev_index))
+        handle = (ctypes.c_ubyte * 64)()
+        off = ctypes.c_int64(0)
+        _lib.check(lib.gsb_ipc_export(full.data_ptr(), dev_index, handle, ctypes.byref(off)), "ipc_export")
+        payload = [(bytes(handle), int(off.value))]
+    if world > 1:
+        dist.broadcast_object_list(payload, src=_global_rank(dst, group), group=group)
+    if rank == dst:
+        entry = dict(full=full, ptr=full.data_ptr(), base=None, device=dev_index)
     else:
-        parts = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
-        dist.gather(t, parts, dst=dst, group=group)
-    if parts is not None:
-        full = torch.cat([p[:k] for p, k in zip(parts, sizes)], dim=0).movedim(0, axis)
-    if full is not None and was_numpy:
-        return full.numpy()
+        raw, off = payload[0]
+        base = ctypes.c_void_p()
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(raw)
+        _lib.check(lib.gsb_ipc_open(buf, dev_index, ctypes.byref(base)), "ipc_open")
+        entry = dict(full=None, ptr=int(base.value) + off, base=int(base.value), device=dev_index)
+    _PEER[key] = entry
+    return entry["full"], entry["ptr"]
+
+
+def close_peer_fields():
+    """Unmap every field opened by :func:`open_peer_field` (call before the owner frees its tensors)."""
+    from . import _lib
+
+    lib = _lib.load()
+    for entry in _PEER.values():
+        if entry["base"] is not None:
+            lib.gsb_ipc_close(entry["base"], entry["device"])
+    _PEER.clear()
+
+
+def summate_structured_gathered(cov_samples, z_1, z_2, axes, matrix=None, group=None, dst=0, incompr=False,
+                                mode="nccl", pieces=4, compute=None):
+    """The structured sum, sharded into slabs along axis 0 over the ranks of ``group``, delivered as ONE array on
+    rank ``dst`` (``dst=None``: on every rank; ``mode="nccl"`` only).  Other ranks get ``None``.
+
+    ``mode="nccl"``: every rank cuts its slab into ``pieces`` row pieces of decreasing size (:func:`piece_bounds`);
+    piece k travels (grouped NCCL send/recv, straight into its rows of the destination) on a side stream while
+    piece k+1 contracts, so only the last, smallest piece's transfer is exposed.
+    ``mode="p2p"``: no collective on the data path at all -- :func:`open_peer_field` maps the destination into every
+    rank and each rank's ONE contraction launch stores its slab there from the kernel's epilogue; a barrier
+    (stream-ordered) tells ``dst`` that the field is complete.  CUDA tensors in, CUDA tensor out.
+    ``compute(cov, z1, z2, local_axes, matrix)`` replaces the kernels (CPU tests with gloo; ``mode="nccl"``).
+    """
+    import torch
+
+    dist = _dist()
+    rank, world = _rank_world(group)
+    axes = list(axes)
+    n0 = len(axes[0])
+    dim = len(axes)
+    fn = compute or (backend.summate_incompr_structured if incompr else backend.summate_structured)
+    if world == 1:
+        return fn(cov_samples, z_1, z_2, axes, matrix)
+    rest = tuple(len(a) for a in axes[1:])
+    lead = (dim,) if incompr else ()
+    ranges = [shard_range(n0, r, world) for r in range(world)]
+    lo, hi = ranges[rank]
+
+    if mode == "p2p":
+        if dst is None or compute is not None:
+            raise ValueError('mode="p2p" gathers onto one rank and runs the CUDA kernels only')
+        full, ptr = open_peer_field(lead + (n0,) + rest, dst, group)
+        # Stream-ordered rendezvous (a one-element all-reduce; the host is not blocked): nobody stores into the
+        # (reused) buffer before its previous consumer on `dst` is done, and `dst` continues only after every
+        # rank's kernel -- enqueued before that rank's contribution -- has finished
+        token = _token(torch.cuda.current_device())
+        dist.all_reduce(token, group=group)
+        if hi > lo:
+            backend.structured_slab_into(cov_samples, z_1, z_2, axes, matrix, lo, hi, ptr, incompr=incompr)
+        dist.all_reduce(token, group=group)
+        return full
+
+    if mode != "nccl":
+        raise ValueError('mode must be "nccl" or "p2p"')
+    receivers = list(range(world)) if dst is None else [dst]
+    receiver = rank in receivers
+    on_gpu = any(backend._is_cuda_tensor(x) for x in (cov_samples, z_1, z_2, *axes))
+    cuts = {r: [a + ranges[r][0] for a in piece_bounds(ranges[r][1] - ranges[r][0], pieces)] for r in range(world)}
+    n_pieces = max(len(c) - 1 for c in cuts.values())
+    full = None
+    keep, reqs = [], []
+    main = side = None
+    if on_gpu:
+        dev = next(x.device for x in (cov_samples, z_1, z_2, *axes) if backend._is_cuda_tensor(x))
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(main)
+    for k in range(n_pieces):
+        mine = None
+        if k + 1 < len(cuts[rank]) and cuts[rank][k + 1] > cuts[rank][k]:
+            a, b = cuts[rank][k], cuts[rank][k + 1]
+            mine = fn(cov_samples, z_1, z_2, [axes[0][a:b]] + axes[1:], matrix)
+            if isinstance(mine, np.ndarray):
+                mine = torch.from_numpy(np.ascontiguousarray(mine))
+            mine = mine.reshape(lead + (b - a,) + rest)
+            keep.append(mine)
+        if receiver and full is None:
+            like = mine if mine is not None else torch.empty(0, dtype=torch.float64)
+            full = torch.empty(lead + (n0,) + rest, dtype=torch.float64, device=like.device)
+        if receiver and mine is not None:
+            full[(slice(None),) * len(lead) + (slice(cuts[rank][k], cuts[rank][k + 1]),)].copy_(mine)
+        ops = []
+        # (several messages between one pair of ranks -- the components of a vector field -- keep their order)
+        comps = [(c,) for c in range(dim)] if incompr else [()]
+        if receiver:
+            for r in range(world):
+                if r != rank and k + 1 < len(cuts[r]) and cuts[r][k + 1] > cuts[r][k]:
+                    for c in comps:
+                        ops.append(dist.P2POp(dist.irecv, full[c + (slice(cuts[r][k], cuts[r][k + 1]),)],
+                                              _global_rank(r, group), group))
+        if mine is not None:
+            for q in receivers:
+                if q != rank:
+                    for c in comps:
+                        ops.append(dist.P2POp(dist.isend, mine[c], _global_rank(q, group), group))
+        if not ops:
+            continue
+        if on_gpu:
+            side.wait_stream(main)                     # the piece is complete on the compute stream
+            with torch.cuda.stream(side):
+                reqs += dist.batch_isend_irecv(ops)    # travels while the next piece contracts on `main`
+        else:
+            reqs += dist.batch_isend_irecv(ops)
+    for req in reqs:
+        req.wait()
+    if on_gpu:
+        main.wait_stream(side)
+    del keep
+    if full is None:
+        return None
     return full
+
+
+_SIDE = {}
+_TOKEN = {}
+
+
+def _token(index):
+    import torch
+
+    if index not in _TOKEN:
+        _TOKEN[index] = torch.zeros(1, dtype=torch.float32, device=torch.device("cuda", index))
+    return _TOKEN[index]
+
+
+def _side_stream(dev):
+    import torch
+
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]

@@ -647,8 +647,13 @@ def _build_sample_ln_pdf(r):
     return _like(sample_ln_pdf, orig)
 
 
-def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True):
+def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True, devices=None):
     """Route an unmodified ``gstools`` to the B200 backend (see the module docstring).
+
+    ``devices="all"`` (or a list of CUDA device indices) drives several GPUs from this one process: big calls
+    -- ``gs.SRF(model)(512^3 mesh)`` -- are cut into slabs along axis 0, one per GPU, each GPU copying its slab
+    straight into its slice of the one result array (:func:`gstools_b200.use_devices`); ``None`` leaves the
+    device selection as it is.
 
     ``lazy_grid=False`` keeps the reference's host mesh expansion; ``fused=False`` rebinds only the
     native wrappers (and the radius sampler) and leaves ``SRF.__call__`` / ``Krige.__call__`` /
@@ -676,6 +681,8 @@ def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True)
         for (owner, attr), value in patches.items():
             setattr(owner, attr, value)
         _STATE["enabled"] = True
+    if devices is not None:
+        backend.use_devices(devices)
     return r.gstools
 
 

@@ -311,6 +311,79 @@ int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int de
                     void *stream);
 
 /*
+ * Multi-GPU plan: ONE process drives several GPUs of a box (SURVEY.md section 8b "gsb_plan_create/destroy",
+ * section 8e; the reference's callers are single-process: src/gstools/field/srf.py:150-163 calls the generator
+ * once per field, examples/06_conditioned_fields/01_2D_condition_ensemble.py:32-35 loops over seeds).
+ * Every output element depends only on its own position and the (tiny, replicated) mode set, so a call is cut
+ * into independent shares with NO inter-GPU traffic during the sum:
+ *     flat point sets          contiguous point ranges                              (gsb_plan_summate)
+ *     meshes, n_batch <  n_dev slabs along axis 0 -- each device's output is one contiguous block of
+ *                              every C-ordered field (tools/geometric.py:340-356)   (gsb_plan_summate_structured)
+ *     meshes, n_batch >= n_dev contiguous ranges of batch entries (ensemble seeds)
+ * Share g of n units over G devices is [lo, hi) with lo = g*(n/G) + min(g, n%G) (gsb_plan_share).
+ * The plan owns one host thread per device; a call hands every device its share and returns when all are done.
+ *   mem == GSB_MEM_HOST   : every device copies its share of the result straight into its slice of the caller's ONE
+ *                           host array (pinned memory recommended), overlapped with its own compute.
+ *   mem == GSB_MEM_DEVICE : all pointers live on `home_device` (a device of the plan).  The other devices read the
+ *                           small inputs and STORE THEIR SHARE OF THE FIELD DIRECTLY INTO `out` on the home device
+ *                           through NVLink peer memory from the contraction kernel's epilogue -- compute and
+ *                           gather are one kernel, nothing is copied afterwards.  Work is ordered after `stream`
+ *                           (a stream of the home device) and `stream` waits for all devices before later work.
+ *                           Needs peer access between the plan's devices (gsb_plan_create enables it; the call
+ *                           fails with GSB_ERR_ARGUMENT when the topology does not allow it).
+ * `incompr` != 0 selects summate_incompr.  `epi` as in the *_ex entries.  `pepi` (scalar fields only): NULL, or an
+ * array of n_devices per-device epilogues -- entry g holds gain / offset arrays resident on devices[g], each
+ * covering ALL points of the field (device g reads its own share of them).
+ * A plan is not re-entrant: one call at a time (calls from several threads are serialised).
+ */
+typedef struct gsb_plan gsb_plan;
+
+/* devices == NULL or n_devices <= 0: all visible devices.  (A device may be listed more than once; its shares then
+ * run one after the other.) */
+int gsb_plan_create(const int *devices, int n_devices, gsb_plan **plan);
+int gsb_plan_destroy(gsb_plan *plan);
+/* Number of devices; devices (may be NULL) receives their indices; *peer_access: 1 when every pair has it. */
+int gsb_plan_info(const gsb_plan *plan, int *n_devices, int *devices, int *peer_access);
+/* The share [lo, hi) of part `part` of `parts` over n units (host only, no plan needed). */
+int gsb_plan_share(int64_t n, int parts, int part, int64_t *lo, int64_t *hi);
+
+int gsb_plan_summate(gsb_plan *plan, const double *cov_samples, const double *z_1, const double *z_2,
+                     const double *pos, int64_t pos_ld, int dim, int64_t n_modes, int64_t n_pts, double *out,
+                     int64_t out_ld, int incompr, const gsb_epilogue *epi, const gsb_point_epilogue *pepi,
+                     int mem, int home_device, void *stream);
+
+int gsb_plan_summate_structured(gsb_plan *plan, const double *cov_samples, const double *z_1, const double *z_2,
+                                const double *axes, const int64_t *axis_len, const double *matrix, int dim,
+                                int64_t n_modes, int64_t n_batch, double *out, int incompr,
+                                const gsb_epilogue *epi, const gsb_point_epilogue *pepi, int mem,
+                                int home_device, void *stream);
+
+/*
+ * gsb_summate_structured_slab -- one share of a mesh for callers that do their own fan-out (one process per GPU,
+ * gstools_b200/dist.py): evaluates the entries [slab_lo, slab_hi) of axis 0 only, while `out` (and the per-point
+ * arrays of `pepi`) describe the FULL mesh: the slab of field z lands at out + z*n + slab_lo*(n/axis_len[0]).
+ * With GSB_MEM_DEVICE `out` may be memory of ANOTHER device mapped into this process (peer access or
+ * gsb_ipc_open): the contraction kernel then stores its slab straight into the gathered field over NVLink, so
+ * "sum, then gather onto rank 0"  is one kernel and no copy.
+ */
+int gsb_summate_structured_slab(const double *cov_samples, const double *z_1, const double *z_2, const double *axes,
+                                const int64_t *axis_len, const double *matrix, int dim, int64_t n_modes,
+                                int64_t n_batch, int64_t slab_lo, int64_t slab_hi, double *out, int incompr,
+                                const gsb_epilogue *epi, const gsb_point_epilogue *pepi, int mem, int device,
+                                void *stream);
+
+/*
+ * Device memory shared between the processes of one box (one process per GPU): the owner exports the allocation
+ * that contains `dev_ptr` (64-byte handle + the pointer's offset inside the allocation), another process maps it
+ * with gsb_ipc_open on its own `device` (peer access is enabled on demand) and gets the allocation's base address
+ * in its address space; gsb_ipc_close unmaps.  Thin wrappers of cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle.
+ */
+#define GSB_IPC_HANDLE_BYTES 64
+int gsb_ipc_export(const void *dev_ptr, int device, unsigned char *handle, int64_t *offset);
+int gsb_ipc_open(const unsigned char *handle, int device, void **base);
+int gsb_ipc_close(void *base, int device);
+
+/*
  * Tuning / introspection.
  *   gsb_set_option("structured_min_tiles", v): meshes with fewer 128x128 output tiles than v
  *       are expanded on the device and sent through the direct kernel (default 64).

@@ -132,3 +132,30 @@ def test_header_is_plain_c_and_library_links_from_c(gsb, tmp_path):
     exe = _build_c_consumer(tmp_path, gsb)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "abi ok" in out.stdout, out.stderr
+
+
+def test_plan_share_is_the_sharding_rule_of_dist(gsb):
+    """gsb_plan_share (single-process multi-GPU plan) cuts exactly like dist.shard_range (one process per GPU)."""
+    from gstools_b200 import dist
+
+    for n in (0, 1, 7, 512, 1000003):
+        for parts in (1, 2, 3, 8):
+            got = [gsb._lib.plan_share(n, parts, g) for g in range(parts)]
+            assert got == [dist.shard_range(n, g, parts) for g in range(parts)]
+            assert got[0][0] == 0 and got[-1][1] == n
+    lib = gsb._lib.load()
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.gsb_plan_share(10, 0, 0, ctypes.byref(lo), ctypes.byref(hi)) == 1
+    assert lib.gsb_plan_share(10, 2, 2, ctypes.byref(lo), ctypes.byref(hi)) == 1
+
+
+def test_plan_needs_a_gpu(gsb):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(gsb.GSB200Error, match="no CPU fallback"):
+        gsb.Plan()
+    lib = gsb._lib.load()
+    assert lib.gsb_plan_destroy(None) == 0
+    assert lib.gsb_plan_summate(None, None, None, None, None, 0, 1, 0, 0, None, 0, 0, None, None, 0, 0, None) == 1

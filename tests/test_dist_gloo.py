@@ -62,6 +62,28 @@ def _worker(rank, world, port, tmpdir):
         field = gdist.gather_field(slab, 7)
         assert np.array_equal(field, struct_compute(cov, z1, z2, axes, None))
 
+        # ---- sum and gather pipelined: row pieces of decreasing size, each sent while the next is computed ----
+        def struct_vec(c, a, b, ax, matrix):
+            grid = np.stack([g.reshape(-1) for g in np.meshgrid(*ax, indexing="ij")])
+            return oracle.summate_incompr(c, a, b, grid).reshape([3] + [len(x) for x in ax])
+
+        for pieces in (1, 3, 8):
+            g0 = gdist.summate_structured_gathered(cov, z1, z2, axes, dst=0, pieces=pieces, compute=struct_compute)
+            assert (g0 is None) == (rank != 0)
+            if rank == 0:
+                assert np.array_equal(g0.numpy(), struct_compute(cov, z1, z2, axes, None))
+            g1 = gdist.summate_structured_gathered(cov, z1, z2, axes, dst=1, pieces=pieces, incompr=True,
+                                                   compute=struct_vec)
+            if rank == 1:
+                assert np.array_equal(g1.numpy(), struct_vec(cov, z1, z2, axes, None))
+            ga = gdist.summate_structured_gathered(cov, z1, z2, axes, dst=None, pieces=pieces, compute=struct_compute)
+            assert np.array_equal(ga.numpy(), struct_compute(cov, z1, z2, axes, None))
+        # one rank without rows (axis 0 shorter than the world)
+        short = [axes[0][:1]] + axes[1:]
+        gs = gdist.summate_structured_gathered(cov, z1, z2, short, dst=1, pieces=4, compute=struct_compute)
+        if rank == 1:
+            assert np.array_equal(gs.numpy(), struct_compute(cov, z1, z2, short, None))
+
         # ---- ensemble: seeds sharded, no collective ----
         sets = [synth_modes(3, 16, seed=s) for s in range(5)]
         mine, (lo, hi) = gdist.ensemble_sharded(sets, lambda m: oracle.summate(*m, pos[:, :50]))

@@ -58,6 +58,24 @@ def _worker(rank, world, port, tmpdir):
         assert (only0 is None) == (rank != 0)
         if rank == 0:
             assert torch.equal(only0, full)
+        # sum + gather onto rank 0 as one operation: NCCL pieces on a side stream / stores into rank 0's memory
+        for mode, kw in (("nccl", dict(pieces=1)), ("nccl", dict(pieces=4)), ("p2p", {})):
+            got = gdist.summate_structured_gathered(tc, t1, t2, axes, dst=0, mode=mode, **kw)
+            assert (got is None) == (rank != 0)
+            if rank == 0:
+                torch.cuda.synchronize()
+                assert tuple(got.shape) == (67, 64, 256)
+                assert float((got - single).abs().max()) <= tight, mode
+            gv = gdist.summate_structured_gathered(tc, t1, t2, axes, dst=world - 1, mode=mode, incompr=True, **kw)
+            if rank == world - 1:
+                torch.cuda.synchronize()
+                vec = gsb.summate_incompr_structured(tc, t1, t2, axes)
+                assert tuple(gv.shape) == (3, 67, 64, 256)
+                assert float((gv - vec).abs().max()) <= tight, mode
+        everywhere = gdist.summate_structured_gathered(tc, t1, t2, axes, dst=None, mode="nccl", pieces=3)
+        assert float((everywhere - single).abs().max()) <= tight
+        dist.barrier()
+        gdist.close_peer_fields()
         # flat points, host arrays in: every rank uses its own device (LOCAL_RANK)
         gsb.set_option("force_path", 0)
         pos = np.random.RandomState(1).uniform(0, 100, (3, 100001))
