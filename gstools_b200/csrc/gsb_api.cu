@@ -376,6 +376,7 @@ struct MeshInfo {
 static std::atomic<int64_t> g_cnt_sk{0};
 static std::atomic<int64_t> g_opt_sk_table_mb{256};     // cap on the tile-axis table (all batch entries)
 static std::atomic<int64_t> g_opt_sk_grid{0};           // 0: one CTA per SM; else a fixed grid (tests)
+static std::atomic<int64_t> g_opt_host_pieces{0};       // host route: 0 = growing pieces (default), n = n equal pieces
 
 // The virtual mesh of the contraction: [outer slow axes | tile axes (folded: ly rows) | inner slow axes |
 // column axes (folded: lc columns)]
@@ -390,7 +391,7 @@ struct SkLayout {
 // (one sincos and 24 bytes per entry).  E.g. 100^3: the middle axis alone (78 % of a tile) beats folding both row
 // axes (99 %, but a 237 MB table for a 8 MB field); 512 x 16 x 512: axis 0 alone; 40 x 50 x 130: both folded.
 static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int64_t n_batch, int ncomp, bool fold_cols,
-                                 int sm_count, double *est_seconds = nullptr)
+                                 int sm_count, bool host_route, double *est_seconds = nullptr)
 {
     const int dim = mesh.dim;
     SkLayout L;
@@ -423,8 +424,18 @@ static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int6
             const double ctas = std::max(1.0, std::min((double)sm_count, std::floor(units / min_share)));
             const double t_contract = units * 64.0 / (ctas * 1.9e9 * (no_slow ? 0.96 : 0.93));
             const double t_table = (double)bytes / 1.0e12;
+            // Host route: the result leaves in contiguous pieces while the next piece contracts (sk_on_device).  With
+            // slow axes INSIDE the tile axis a (field, slow index) unit is not contiguous in the output, pieces are
+            // whole fields, and the copy of the last field (PCIe, ~50 GB/s) is exposed instead of ~1/10 of it.
+            // (256 x 512 x 512 on one device of a 2-GPU plan: axis 0 as tile axis has the smaller table, but
+            // its ONE piece cost 7.8 ms + 9.4 ms instead of 10 ms overlapped.)
+            double t_copy = 0.0;
+            if (host_route) {
+                const double field_bytes = (double)n_rows * (double)L.lc * sizeof(double);
+                t_copy = field_bytes / 50e9 * ((b < n_row) ? 1.0 : 0.1);
+            }
             // ties: prefer the trailing axes (rows of a tile then are neighbours in memory)
-            const double t = (t_contract + t_table) * (1.0 + 1e-6 * (n_row - b));
+            const double t = (t_contract + t_table + t_copy) * (1.0 + 1e-6 * (n_row - b));
             if (t < best) { best = t; best_a = a; best_b = b; }
         }
     }
@@ -474,7 +485,9 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
         const int64_t tiles_per_cut = tiles_per_unit * unit_mult;
         const int64_t min_cut = std::max<int64_t>(1, ((int64_t)max_grid + tiles_per_cut - 1) / tiles_per_cut);   // >= one wave
         double want = std::max<double>((double)min_cut, (double)cut_units / 64.0);
-        while (cuts.back() < cut_units && cuts.size() < 32) {
+        const int64_t fixed = g_opt_host_pieces.load();
+        for (int64_t k = 1; fixed > 0 && k <= fixed; ++k) cuts.push_back(cut_units * k / fixed);
+        while (fixed <= 0 && cuts.back() < cut_units && cuts.size() < 32) {
             cuts.push_back(std::min<int64_t>(cut_units, cuts.back() + std::max<int64_t>(min_cut, (int64_t)want)));
             want *= 1.25;
         }
@@ -569,6 +582,7 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
             // units [u0, u1): unit u = z * n_slow + slow lies at field z, offset slow * ly * lc (pieces of a mesh with
             // inner slow axes are whole fields).  One copy when both sides use the same field stride, else one per field
             const int64_t unit_elems = L.ly * L.lc;
+            TraceScope tc("d2h piece", dev.streams[1]);
             if (d_fstride == h_fstride && d_fstride == mesh.n) {
                 const size_t off = (size_t)u0 * unit_elems;
                 GSB_CUDA(cudaMemcpyAsync(h_out + off, d_out + off, sizeof(double) * (size_t)(u1 - u0) * unit_elems,
@@ -628,12 +642,14 @@ static int structured_on_device(const double *d_cov, const double *d_z1, const d
                 continue;     // forced folding
             }
             double t = 0.0;
-            const SkLayout cand = sk_choose_layout(mesh, n_modes_pad, n_batch, ncomp, fold == 1, dev.sm_count, &t);
+            const SkLayout cand = sk_choose_layout(mesh, n_modes_pad, n_batch, ncomp, fold == 1, dev.sm_count,
+                                                   h_out != nullptr, &t);
             if (t < t_best) { t_best = t; layout = cand; }
         }
         const double instr = (double)(dim + 13 + (vec ? dim : 0));
         const double t_direct = (double)mesh.n * (double)n_modes * (double)n_batch * instr /
-                                    ((double)dev.sm_count * 64.0 * 1.9e9 * 0.86) + 12e-6 * (double)n_batch;
+                                    ((double)dev.sm_count * 64.0 * 1.9e9 * 0.86) + 12e-6 * (double)n_batch +
+                                (h_out ? (double)mesh.n * (double)(n_batch * ncomp) * sizeof(double) / 50e9 : 0.0);
         separable = t_best < t_direct;
         const int64_t tiles = ((mesh.n_rows + SK_TM - 1) / SK_TM) * ((mesh.len[dim - 1] + SK_TN - 1) / SK_TN) * n_batch * ncomp;
         if (tiles < g_opt_structured_min_tiles.load()) separable = false;
@@ -1938,6 +1954,7 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "krige_host_chunk_mb") g_opt_krige_host_chunk_mb = std::max<int64_t>(value, 1);
     else if (n == "sk_table_mb") g_opt_sk_table_mb = std::max<int64_t>(value, 1);
     else if (n == "sk_grid") g_opt_sk_grid = std::max<int64_t>(value, 0);
+    else if (n == "host_pieces") g_opt_host_pieces = std::max<int64_t>(value, 0);
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);
     return GSB_OK;
 }

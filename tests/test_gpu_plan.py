@@ -117,7 +117,7 @@ def test_plan_point_epilogue(plan, gsb):
     # flat points with the same arrays
     pos = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
     flat = plan.summate(cov, z1, z2, pos, epilogue=epi, point_epilogue=pe)
-    assert maxabs(flat, want) <= 1e-12
+    assert maxabs(flat, want) <= 1e-10          # direct kernel against the separable one: 1e-9 * sqrt(var) class
 
 
 def test_plan_device_route_stores_into_home_tensor(plan, gsb):
