@@ -37,7 +37,7 @@ from .backend import (
     use_devices,
     current_plan,
 )
-from .plugin import disable, enable, is_enabled
+from .plugin import disable, enable, is_enabled, prewarm, unfused_methods
 
 __version__ = "0.1.0"
 
@@ -60,6 +60,8 @@ __all__ = [
     "enable",
     "disable",
     "is_enabled",
+    "prewarm",
+    "unfused_methods",
     "set_device",
     "get_device",
     "Plan",

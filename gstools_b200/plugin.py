@@ -37,14 +37,22 @@ at call time (generator.py:266, :554), so rebinding them takes effect for existi
 
 from __future__ import annotations
 
+import ast
+import hashlib
+import inspect
+import io
+import textwrap
 import threading
+import tokenize
+import warnings
 import weakref
 
 import numpy as np
 
 from . import _lib, backend
 
-__all__ = ["enable", "disable", "is_enabled", "LazyGridPos"]
+__all__ = ["enable", "disable", "is_enabled", "LazyGridPos", "prewarm", "unfused_methods", "source_fingerprint",
+           "KNOWN_SOURCES"]
 
 _STATE = {"enabled": False}
 _LOCK = threading.Lock()
@@ -156,6 +164,56 @@ class _Refs:
 def _like(new, orig):
     new.__doc__ = orig.__doc__
     return new
+
+
+# ---- which upstream bodies the fused wrappers restate ------------------------------------------------
+# The fused wrappers (SRF.__call__, Krige.__call__, CondSRF.__call__, Field.pre_pos, RandMeth.__call__,
+# IncomprRandMeth.__call__, apply_mean_norm_trend, RNG.sample_ln_pdf) re-implement the control flow of the reference
+# methods they replace, so an upstream change to one of those methods would silently diverge.  Each wrapper is
+# therefore installed only when the installed method's source -- tokens without comments, docstring and layout --
+# has a fingerprint listed here; otherwise the original method stays (the rebound native wrappers below it still
+# route the arithmetic to the GPU) and a warning names the method.
+KNOWN_SOURCES = {
+    # GSTools 1.7.0 + unreleased changes up to PR #391 (the reference checkout this backend was written against)
+    "SRF.__call__": {"850f4f02ec032086"},                  # src/gstools/field/srf.py:109-163
+    "Krige.__call__": {"092539814c39d035"},                # src/gstools/krige/base.py:220-300
+    "CondSRF.__call__": {"a3315d7cbfa707fb"},              # src/gstools/field/cond_srf.py:82-150
+    "Field.pre_pos": {"61e1ab1140b02bd1"},                 # src/gstools/field/base.py:254-297
+    "RandMeth.__call__": {"3bdd81d12ed562db"},             # src/gstools/field/generator.py:243-270
+    "IncomprRandMeth.__call__": {"5599293d8be13a83"},      # src/gstools/field/generator.py:529-567
+    "apply_mean_norm_trend": {"f7c892dfe9c5d2fb"},         # src/gstools/normalizer/tools.py:35-104
+    "RNG.sample_ln_pdf": {"d7e2ea3b1a27327b"},             # src/gstools/random/rng.py:38-104
+    "CondSRF.get_scaling": {"21606b5f2cae2334"},           # src/gstools/field/cond_srf.py:152-178 (gsb_cond_scaling)
+    "Krige._get_krige_vecs": {"ffaa6a1d9a32909e"},         # src/gstools/krige/base.py:359-388 (kvgen_kernel)
+}
+
+
+def source_fingerprint(fn):
+    """sha256 (16 hex digits) of the function's token stream without comments, docstring and layout; None when
+    the source is not available."""
+    try:
+        src = textwrap.dedent(inspect.getsource(fn))
+        node = ast.parse(src).body[0]
+    except (OSError, TypeError, SyntaxError, IndexError):
+        return None
+    lines = src.splitlines(keepends=True)
+    first = node.body[0] if getattr(node, "body", None) else None
+    if isinstance(first, ast.Expr) and isinstance(getattr(first, "value", None), ast.Constant) \
+            and isinstance(first.value.value, str):
+        for i in range(first.lineno - 1, first.end_lineno):
+            lines[i] = "\n"
+    skip = {tokenize.COMMENT, tokenize.NL, tokenize.NEWLINE, tokenize.INDENT, tokenize.DEDENT, tokenize.ENDMARKER}
+    toks = [t.string for t in tokenize.generate_tokens(io.StringIO("".join(lines)).readline) if t.type not in skip]
+    return hashlib.sha256(" ".join(toks).encode()).hexdigest()[:16]
+
+
+def _known(name, fn, report):
+    """True when the installed ``fn`` is a body the wrapper ``name`` was written against."""
+    got = source_fingerprint(fn)
+    ok = got in KNOWN_SOURCES.get(name, ())
+    if not ok:
+        report.append(f"{name} ({got})")
+    return ok
 
 
 # ---- native wrappers: generator.py:42-75 and krige/base.py:42-61 ------------------------------------
@@ -625,15 +683,9 @@ def _build_sample_ln_pdf(r):
     pdf_models = {getattr(cmodels, name): name for name in _lib.PDF_KINDS if hasattr(cmodels, name)}
     base_ln_pdf = cmodels.CovModel.ln_spectral_rad_pdf
 
-    def sample_ln_pdf(self, ln_pdf, size=None, sample_around=1.0, nwalkers=50, burn_in=20,
-                      oversampling_factor=10):
-        model = getattr(ln_pdf, "__self__", None)
-        kind = pdf_models.get(type(model))
-        native = (r.on() and kind is not None and getattr(ln_pdf, "__func__", None) is base_ln_pdf
-                  and type(model).spectral_density is getattr(cmodels, kind).spectral_density
-                  and nwalkers >= 2 and nwalkers % 2 == 0)
-        if not native:
-            return orig(self, ln_pdf, size, sample_around, nwalkers, burn_in, oversampling_factor)
+    verdicts = {}     # kind -> does the native run reproduce the installed emcee / numpy, bit for bit?
+
+    def _native(self, kind, model, size, sample_around, nwalkers, burn_in, oversampling_factor):
         # same draws from the master generator, in the same order, as rng.py:72-104
         sample_size = burn_in if size is None else max(burn_in, (size / nwalkers) * oversampling_factor)
         sample_size = int(sample_size)
@@ -643,6 +695,38 @@ def _build_sample_ln_pdf(r):
         chain = backend.sample_radii_mcmc(kind, model.dim, model.len_rescaled, getattr(model, "nu", 0.0),
                                           burn_state, main_state, init_guess[:, 0], burn_in, sample_size)
         return self.random.choice(chain.reshape(-1), size)
+
+    def _stream_compatible(kind, model):
+        """One short chain through the ORIGINAL sample_ln_pdf (the installed emcee and numpy) and through the native
+        restatement, from the same seed: the native sampler hard-codes how emcee's stretch move consumes the
+        generator (choice, shuffled red/blue split, rand, randint, rand) and numpy's pow / log / exp, so any other
+        emcee or numpy must be DETECTED, not assumed.  Once per model class and process (a few ms)."""
+        if kind not in verdicts:
+            ok = False
+            try:
+                ln_pdf = model.ln_spectral_rad_pdf
+                args = (24, 1.0 / model.len_rescaled, 6, 3, 3)
+                want = orig(r.grng.RNG(271828), ln_pdf, *args)
+                got = _native(r.grng.RNG(271828), kind, model, *args)
+                ok = np.array_equal(want, got)
+            except Exception:  # no usable emcee to compare with: keep the reference's own path
+                ok = False
+            if not ok:
+                warnings.warn(f"gstools_b200: the native radius sampler does not reproduce the installed emcee/numpy for "
+                              f"{kind}; RNG.sample_ln_pdf keeps the reference's sampler", RuntimeWarning, stacklevel=3)
+            verdicts[kind] = ok
+        return verdicts[kind]
+
+    def sample_ln_pdf(self, ln_pdf, size=None, sample_around=1.0, nwalkers=50, burn_in=20,
+                      oversampling_factor=10):
+        model = getattr(ln_pdf, "__self__", None)
+        kind = pdf_models.get(type(model))
+        native = (r.on() and kind is not None and getattr(ln_pdf, "__func__", None) is base_ln_pdf
+                  and type(model).spectral_density is getattr(cmodels, kind).spectral_density
+                  and nwalkers >= 2 and nwalkers % 2 == 0 and _stream_compatible(kind, model))
+        if not native:
+            return orig(self, ln_pdf, size, sample_around, nwalkers, burn_in, oversampling_factor)
+        return _native(self, kind, model, size, sample_around, nwalkers, burn_in, oversampling_factor)
 
     return _like(sample_ln_pdf, orig)
 
@@ -669,21 +753,73 @@ def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True,
         r.config._GSTOOLS_B200_AVAIL = True
         patches = dict(r.orig)                                    # start from the originals
         patches.update(_build_native_wrappers(r))
-        patches[(r.grng.RNG, "sample_ln_pdf")] = _build_sample_ln_pdf(r)
-        if lazy_grid:
+        # the wrappers below restate upstream method bodies: install each only over a body it was written against
+        unknown = []
+
+        def known(name, owner, attr):
+            return _known(name, r.orig[(owner, attr)], unknown)
+
+        if known("RNG.sample_ln_pdf", r.grng.RNG, "sample_ln_pdf"):
+            patches[(r.grng.RNG, "sample_ln_pdf")] = _build_sample_ln_pdf(r)
+        if lazy_grid and known("Field.pre_pos", r.fbase.Field, "pre_pos"):
             patches[(r.fbase.Field, "pre_pos")] = _build_pre_pos(r)
         if fused:
-            patches[(r.fsrf.SRF, "__call__")] = _build_srf_call(r)
-            patches[(r.kbase.Krige, "__call__")] = _build_krige_call(r)
-            patches[(r.cond_cls, "__call__")] = _build_cond_call(r)
-            patches[(r.fbase, "apply_mean_norm_trend")] = _build_apply_mean_norm_trend(r)
-            patches.update(_build_generator_calls(r))
+            if known("SRF.__call__", r.fsrf.SRF, "__call__"):
+                patches[(r.fsrf.SRF, "__call__")] = _build_srf_call(r)
+            if known("Krige.__call__", r.kbase.Krige, "__call__") and \
+                    _known("Krige._get_krige_vecs", r.kbase.Krige._get_krige_vecs, unknown):
+                patches[(r.kbase.Krige, "__call__")] = _build_krige_call(r)
+                # (shares the kriging evaluation above)
+                if known("CondSRF.__call__", r.cond_cls, "__call__") and \
+                        _known("CondSRF.get_scaling", r.cond_cls.get_scaling, unknown):
+                    patches[(r.cond_cls, "__call__")] = _build_cond_call(r)
+            if known("apply_mean_norm_trend", r.fbase, "apply_mean_norm_trend"):
+                patches[(r.fbase, "apply_mean_norm_trend")] = _build_apply_mean_norm_trend(r)
+            gen_calls = _build_generator_calls(r)
+            for name, key in (("RandMeth.__call__", (r.gen.RandMeth, "__call__")),
+                              ("IncomprRandMeth.__call__", (r.gen.IncomprRandMeth, "__call__"))):
+                if known(name, *key):
+                    patches[key] = gen_calls[key]
+        _STATE["unfused"] = list(unknown)
+        if unknown:
+            warnings.warn("gstools_b200: the installed gstools differs from the version the fused wrappers were "
+                          "written against in " + ", ".join(unknown) + "; these methods keep the reference's own "
+                          "code (the summation and kriging arithmetic still runs on the GPU through the rebound "
+                          "native wrappers).  See gstools_b200.plugin.KNOWN_SOURCES.", RuntimeWarning, stacklevel=2)
         for (owner, attr), value in patches.items():
             setattr(owner, attr, value)
         _STATE["enabled"] = True
     if devices is not None:
         backend.use_devices(devices)
     return r.gstools
+
+
+def unfused_methods():
+    """Methods whose fused wrapper was NOT installed by the last :func:`enable` because the installed gstools'
+    source differs from the known versions (``"name (fingerprint)"`` strings; empty when everything matched)."""
+    return list(_STATE.get("unfused", []))
+
+
+def prewarm(shape, mode_no=1000, incompr=False, devices=None):
+    """Pay the one-time costs of a structured call of this ``shape`` now instead of in the first real call: CUDA
+    context and kernel-attribute setup, the device memory pool (scratch tables + the device copy of the field)
+    and the PINNED host allocation of the result (cudaHostAlloc of 1 GB alone is ~0.4 s; the first
+    ``srf.structured(512^3)`` of a process took 3.6 s, the third 21 ms).  Runs one summation of zero-weight modes
+    on the mesh ``shape`` and keeps the pinned block in the allocator's cache."""
+    shape = tuple(int(v) for v in shape)
+    dim = len(shape)
+    if devices is not None:
+        backend.use_devices(devices)
+    cov = np.zeros((dim, int(mode_no)))
+    z = np.zeros(int(mode_no))
+    axes = [np.arange(float(n)) for n in shape]
+    for _ in range(2):        # second pass: stream-ordered pool and pinned cache are now warm
+        if dim >= 2:
+            fn = backend.summate_incompr_structured if incompr else backend.summate_structured
+            out = fn(cov, z, z, axes)
+        else:
+            out = backend.summate(cov, z, z, np.asarray(axes))
+        del out
 
 
 def disable():

@@ -571,6 +571,83 @@ def test_native_radius_sampler_is_stream_compatible(gsb, make, seed):
 
 
 @needs_ref
+def test_native_sampler_falls_back_when_emcee_differs(gsb, monkeypatch):
+    """the native sampler assumes how emcee consumes the generator.  With an emcee whose stretch move
+    draws differently the self-check must notice and keep the reference's sampler (same radii as without the plugin)."""
+    gs = refharness.import_gstools()
+    import emcee
+    from gstools.field.generator import RandMeth
+
+    ref = RandMeth(gs.Matern(dim=3, var=1.0, len_scale=4.0, nu=1.5), mode_no=64, seed=5)
+
+    class OtherSampler(emcee.EnsembleSampler):
+        def run_mcmc(self, initial_state, nsteps, **kwargs):
+            # one extra draw before the moves: another stream than the native restatement assumes
+            rs = np.random.RandomState()
+            rs.set_state(initial_state.random_state)
+            rs.rand()
+            initial_state.random_state = rs.get_state()
+            return super().run_mcmc(initial_state, nsteps, **kwargs)
+
+    monkeypatch.setattr(emcee, "EnsembleSampler", OtherSampler)
+    other = RandMeth(gs.Matern(dim=3, var=1.0, len_scale=4.0, nu=1.5), mode_no=64, seed=5)
+    assert not np.array_equal(other._cov_sample, ref._cov_sample)
+    gsb.disable()
+    from gstools_b200 import plugin
+    plugin._STATE.pop("refs", None)                      # fresh wrapper state: the verdict is per process
+    with pytest.warns(RuntimeWarning, match="does not reproduce the installed emcee"):
+        gsb.enable()
+        try:
+            got = RandMeth(gs.Matern(dim=3, var=1.0, len_scale=4.0, nu=1.5), mode_no=64, seed=5)
+        finally:
+            gsb.disable()
+            plugin._STATE.pop("refs", None)
+    assert np.array_equal(got._cov_sample, other._cov_sample)
+
+
+@needs_ref
+def test_fused_wrappers_only_over_known_upstream_bodies(gsb, monkeypatch):
+    """a wrapper that restates an upstream method is installed only over a body it was written
+    against; any other body keeps the reference's code and is reported."""
+    gs = refharness.import_gstools()
+    from gstools.field import srf as fsrf
+    from gstools_b200 import plugin
+
+    gsb.enable()
+    assert gsb.unfused_methods() == []
+    assert fsrf.SRF.__call__ is not plugin._STATE["refs"].orig[(fsrf.SRF, "__call__")]
+    gsb.disable()
+    monkeypatch.setitem(plugin.KNOWN_SOURCES, "SRF.__call__", {"0" * 16})
+    with pytest.warns(RuntimeWarning, match="SRF.__call__"):
+        gsb.enable()
+    try:
+        assert fsrf.SRF.__call__ is plugin._STATE["refs"].orig[(fsrf.SRF, "__call__")]
+        assert [m.split()[0] for m in gsb.unfused_methods()] == ["SRF.__call__"]
+        assert gs.krige.Krige.__call__ is not plugin._STATE["refs"].orig[(gs.krige.Krige, "__call__")]
+    finally:
+        gsb.disable()
+    # layout, comments and docstrings do not change a fingerprint; code does
+    def one():
+        def f(a, b):
+            """doc"""
+            return a + b  # comment
+        return f
+
+    def two():
+        def f(a,   b):
+
+            return a   +   b
+        return f
+
+    def three():
+        def f(a, b):
+            return a - b
+        return f
+
+    assert plugin.source_fingerprint(one()) == plugin.source_fingerprint(two()) != plugin.source_fingerprint(three())
+
+
+@needs_ref
 def test_native_radius_sampler_reference_literals_and_fallthrough(gsb, monkeypatch):
     """tests/test_randmeth.py:43-46 (3-D golden) through the native sampler; models without a native
     log-pdf, overridden densities and the flag switched off keep emcee."""
@@ -589,7 +666,11 @@ def test_native_radius_sampler_reference_literals_and_fallthrough(gsb, monkeypat
     try:
         assert grng.RNG.sample_ln_pdf is not orig
         rm = RandMeth(gs.Exponential(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=19031977)
-        assert calls == ["Exponential"]
+        # the first use of a model class runs one short self-check chain against the installed emcee, then the real one
+        assert calls == ["Exponential"] * 2
+        RandMeth(gs.Exponential(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=3)
+        assert calls == ["Exponential"] * 3
+        del calls[1:]
         # the fixture's model (Gaussian 3-D) has an inverse CDF: no MCMC at all, same modes as recorded
         rg = RandMeth(gs.Gaussian(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=19031977)
         assert calls == ["Exponential"] and np.array_equal(rg._cov_sample, d["cov_samples"])
