@@ -485,7 +485,8 @@ def run_b200_arm(args, cfg):
             "kernel": "sk_contract_kernel (DMMA.8x8x4, stream-K, one launch per step)" if structured
                       else "direct_kernel",
             "kernel_ms_per_launch": 1e3 * kern_s, "launches_timed": kern_n,
-            "kernel_share_of_step": (kern_ms * 1e-3) / dev_s if dev_s else None,
+            # (plan mode: the launches of all devices are summed, they run side by side)
+            "kernel_share_of_step": (kern_ms * 1e-3) / dev_s / (1 if plan is None else len(plan)) if dev_s else None,
             "algorithmic_flop_per_pair": flop_per_pair,
             "peak_source": "DFMA microbenchmark run in this process (gsb_measure_fp64_peak); "
                            "MEASURED_PEAKS.json has no fp64 entry",
