@@ -399,7 +399,8 @@ def run_b200_arm(args, cfg):
 
         def step_gather():
             return gdist.summate_structured_gathered(d_cov, d_z1, d_z2, g_axes, cfg.get("matrix"), dst=0,
-                                                     incompr=vec, mode=args.gather, pieces=args.pieces)
+                                                     incompr=vec, mode=args.gather, pieces=args.pieces,
+                                                     reserve_sms=args.reserve_sms)
 
         for _ in range(args.warmup):
             out = step_gather()
@@ -422,6 +423,7 @@ def run_b200_arm(args, cfg):
         g_s = float(t.item())
         n_full = int(np.prod([len(a) for a in cfg["axes"]])) * (cfg["dim"] if vec else 1)
         gather = {"mode": args.gather, "pieces": args.pieces if args.gather == "nccl" else 1,
+                  "reserve_sms": args.reserve_sms if args.gather == "nccl" else 0,
                   "ms_per_step": 1e3 * g_s / args.steps, "compute_only_ms_per_step": 1e3 * dev_s / args.steps,
                   "exposed_ms": 1e3 * (g_s - dev_s) / args.steps,
                   "bytes_into_rank0_per_step": int(8 * n_full * (world - 1) / world),
@@ -824,7 +826,8 @@ def main():
     ap.add_argument("--gather", default="none", choices=["none", "nccl", "p2p"],
                     help="N > 1, structured workloads: deliver the field as one device array on rank 0; `value` then "
                          "is compute + gather")
-    ap.add_argument("--pieces", type=int, default=4, help="row pieces per rank of --gather nccl")
+    ap.add_argument("--pieces", type=int, default=1, help="row pieces per rank of --gather nccl")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left to NCCL while pieces travel (--gather nccl)")
     ap.add_argument("--plan", type=int, default=0, help="single-process mode: drive this many GPUs through gsb_plan")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (builder's table runs)")
     args = ap.parse_args()

@@ -236,7 +236,7 @@ def close_peer_fields():
 
 
 def summate_structured_gathered(cov_samples, z_1, z_2, axes, matrix=None, group=None, dst=0, incompr=False,
-                                mode="nccl", pieces=4, compute=None):
+                                mode="nccl", pieces=1, compute=None, reserve_sms=0):
     """The structured sum, sharded into slabs along axis 0 over the ranks of ``group``, delivered as ONE array on
     rank ``dst`` (``dst=None``: on every rank; ``mode="nccl"`` only).  Other ranks get ``None``.
 
@@ -247,6 +247,9 @@ def summate_structured_gathered(cov_samples, z_1, z_2, axes, matrix=None, group=
     rank and each rank's ONE contraction launch stores its slab there from the kernel's epilogue; a barrier
     (stream-ordered) tells ``dst`` that the field is complete.  CUDA tensors in, CUDA tensor out.
     ``compute(cov, z1, z2, local_axes, matrix)`` replaces the kernels (CPU tests with gloo; ``mode="nccl"``).
+    ``reserve_sms`` (``mode="nccl"``, more than one piece): the persistent contraction normally holds EVERY SM with
+    213 KB of shared memory per CTA, so NCCL's send/recv kernels could not start before it ends and nothing would
+    overlap; while pieces are in flight the contraction runs on ``sm_count - reserve_sms`` CTAs instead.
     """
     import torch
 
@@ -292,7 +295,15 @@ def summate_structured_gathered(cov_samples, z_1, z_2, axes, matrix=None, group=
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
         side.wait_stream(main)
+    shrink = on_gpu and compute is None and n_pieces > 1 and reserve_sms > 0
+    if shrink:
+        from . import _lib
+
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        _lib.set_option("sk_grid", max(1, sms - int(reserve_sms)))
     for k in range(n_pieces):
+        if shrink and k == n_pieces - 1:
+            _lib.set_option("sk_grid", 0)      # nothing travels behind the last piece: all SMs again
         mine = None
         if k + 1 < len(cuts[rank]) and cuts[rank][k + 1] > cuts[rank][k]:
             a, b = cuts[rank][k], cuts[rank][k + 1]
@@ -328,6 +339,8 @@ def summate_structured_gathered(cov_samples, z_1, z_2, axes, matrix=None, group=
                 reqs += dist.batch_isend_irecv(ops)    # travels while the next piece contracts on `main`
         else:
             reqs += dist.batch_isend_irecv(ops)
+    if shrink:
+        _lib.set_option("sk_grid", 0)
     for req in reqs:
         req.wait()
     if on_gpu:

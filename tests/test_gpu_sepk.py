@@ -113,12 +113,10 @@ def test_sk_odd_and_thin_meshes(shape, sk, oracle_mod):
     if dim == 3:
         gv = sk.summate_incompr_structured(cov, z1, z2, axes, mat)
         assert maxabs(gv[(slice(None),) + sub], oracle_mod.summate_incompr(cov, z1, z2, pos)) <= raw_tol(130)
-    # host route (pieces + overlapped D2H) == device route, bit for bit (same shares)
+    # host route (pieces + overlapped D2H) against the device route: the same tiles; the host route may pick another
+    # tile axis (it wants pieces that leave as contiguous copies) and other stream-K shares -> equal up to rounding
     import torch
 
     dev = sk.summate_structured(*(torch.tensor(a, device="cuda:0") for a in (cov, z1, z2)),
                                 [torch.tensor(a, device="cuda:0") for a in axes], mat)
-    if n < 148 * 2 * 128 * 128:       # one piece: the same launch geometry
-        assert np.array_equal(dev.cpu().numpy(), got)
-    else:
-        assert maxabs(dev.cpu().numpy(), got) <= 1e-3 * raw_tol(130)
+    assert maxabs(dev.cpu().numpy(), got) <= 1e-3 * raw_tol(130)
