@@ -749,14 +749,24 @@ def run_c5cond_arm(args, edge=128, n_cond=1000):
     if not refharness.have_reference():
         raise SystemExit("bench.py --workload c5cond needs the reference gstools (baseline/_ref; run "
                          "__graft_entry__.build() in the build container)")
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
     gs = refharness.import_gstools()
     import gstools_b200 as gsb
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 backend has no CPU fallback)")
-    gsb.set_device(0)
+    # N > 1 (torchrun): the ensemble's seeds are sharded over the ranks, one process per GPU (BASELINE.json
+    # configs[4]: "seeds sharded over 8 GPUs"); every rank sets up the (replicated) kriging system itself and runs
+    # `steps` realisations of ITS seeds -- nothing is exchanged.  Weak scaling: the work per GPU is fixed.
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    gsb.set_device(local)
     gsb.enable()
     rs = np.random.RandomState(20170519)
     cond_pos = rs.uniform(0, edge - 1, (3, n_cond))
@@ -767,7 +777,13 @@ def run_c5cond_arm(args, edge=128, n_cond=1000):
     t_setup = time.perf_counter() - t0
     crf = gs.CondSRF(krige)
     crf.set_pos([np.arange(float(edge))] * 3, "structured")
-    seeds = gs.random.MasterRNG(20170519)
+    master = gs.random.MasterRNG(20170519)
+    all_seeds = [master() for _ in range((max(args.warmup, 3) + args.steps + 8) * world)]
+    my_seeds = iter(all_seeds[rank::world])                  # this rank's share of the ensemble's seeds
+
+    def seeds():
+        return next(my_seeds)
+
     n_modes = 1000
     t0 = time.perf_counter()
     crf(seed=seeds(), store=["fld", False, False])           # evaluates the kriging system
@@ -775,15 +791,21 @@ def run_c5cond_arm(args, edge=128, n_cond=1000):
     for _ in range(max(args.warmup, 3) - 1):
         crf(seed=seeds(), store=["fld", False, False])
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     launches0 = gsb.get_counter("launches")
     k0 = gsb.get_counter("krige_calls")
     t_modes = 0.0
-    with ClockSampler(0) as clocks:
+    with ClockSampler(local) as clocks:
         t0 = time.perf_counter()
         for _ in range(args.steps):
             f = crf(seed=seeds(), store=["fld", False, False])
         torch.cuda.synchronize()
         total = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([total], dtype=torch.float64, device=torch.device("cuda", local))
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total = float(tt.item())
     launches = gsb.get_counter("launches") - launches0
     assert gsb.get_counter("krige_calls") == k0, "the kriging system must not be re-evaluated per realisation"
     # share of the host-side mode sampling (RandMeth.reset_seed with the native radius sampler)
@@ -792,15 +814,22 @@ def run_c5cond_arm(args, edge=128, n_cond=1000):
         crf.generator.update(model, seeds())
     t_modes = (time.perf_counter() - t0) / 8
     pairs = edge ** 3 * n_modes
-    value = args.steps * pairs / total
+    value = world * args.steps * pairs / total
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        gsb.disable()
+        return
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C5 as configured: gs.CondSRF realisations, Ordinary kriging on {n_cond} points, "
                                f"Exponential 3D, {edge}^3 structured mesh, mode_no={n_modes}, plugin enabled",
                    "baseline_config": "C5", "path": "CondSRF.__call__ -> fused per-point epilogue (scaled contraction)",
-                   "mode_no": n_modes, "dim": 3, "step": "one conditioned realisation, seed in -> host field out",
+                   "mode_no": n_modes, "dim": 3,
+                   "step": "one conditioned realisation per GPU, seed in -> host field out",
+                   "sharding": f"seeds of the ensemble dealt out to {world} process(es), one per GPU, no collective",
                    "l2": "every realisation writes a fresh 16.8 MB field and reads 33.6 MB of kriging results; "
                          "inputs are re-sampled per step"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(8 * (5 * n_modes + 3 * edge)),
@@ -809,7 +838,7 @@ def run_c5cond_arm(args, edge=128, n_cond=1000):
         "gpu_launches": int(launches), "clocks": clocks.summary(),
         "breakdown_ms": {"kriging_setup_pinv_host": 1e3 * t_setup, "first_call_incl_kriging_evaluation": 1e3 * t_first,
                          "mode_sampling_host_per_realisation": 1e3 * t_modes,
-                         "ensemble_of_256_extrapolated_s": t_first + 255 * total / args.steps},
+                         "ensemble_of_256_extrapolated_s": t_first + (256 / world - 1) * total / args.steps},
         "roofline": None, "wall_s_timed_region": total,
     }
     print(json.dumps(line), flush=True)

@@ -47,7 +47,7 @@ COV_TYPES = {"Gaussian": 1, "Exponential": 2, "Stable": 3, "Rational": 4, "Cubic
              "Circular": 7, "Spherical": 8}
 
 
-PDF_KINDS = {"Exponential": 1, "Matern": 2}
+PDF_KINDS = {"Exponential": 1, "Matern": 2, "Gaussian": 3}
 
 
 class CovModelSpec(ctypes.Structure):
@@ -97,6 +97,7 @@ SIGNATURES = {
                                              _int, _vp, _i64, _vp, _vp, _int, _int, _vp]),
     "gsb_sample_radii_mcmc": (_int, [_int, _int, ctypes.c_double, ctypes.c_double, _vp, _int, _vp, _int, _vp,
                                      _int, _int, _int, _vp]),
+    "gsb_sample_radii_mcmc_cb": (_int, [_vp, _vp, _vp, _int, _vp, _int, _vp, _int, _int, _int, _vp]),
     "gsb_scale_shift": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp]),
     "gsb_plan_create": (_int, [ctypes.POINTER(_int), _int, ctypes.POINTER(_vp)]),
     "gsb_plan_destroy": (_int, [_vp]),
@@ -119,6 +120,8 @@ SIGNATURES = {
     "gsb_kernel_times": (_int, [_c_double_p, _c_int64_p]),
     "gsb_measure_fp64_peak": (_int, [_int, _int, ctypes.c_double, _c_double_p]),
 }
+
+LN_PDF_FN = ctypes.CFUNCTYPE(_int, _c_double_p, _int, _c_double_p, _vp)
 
 _lib = None
 

@@ -984,15 +984,7 @@ def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=
     return (field, error.reshape(shape)) if return_var else field
 
 
-def sample_radii_mcmc(kind, dim, len_rescaled, nu, burn_state, main_state, init, burn_in, n_steps):
-    """Native, stream-compatible ``emcee`` run of ``RNG.sample_ln_pdf`` (random/rng.py:77-101).
-
-    ``burn_state`` / ``main_state`` are the ``numpy.random.RandomState.get_state()`` tuples (legacy
-    MT19937) the reference hands to the burn-in and the production ``run_mcmc`` call, ``init`` the
-    ``nwalkers`` initial positions.  Returns the production chain ``(n_steps, nwalkers)``.  Host only.
-    """
-    if kind not in _lib.PDF_KINDS:
-        raise ValueError(f"no native log-pdf for model '{kind}': {sorted(_lib.PDF_KINDS)}")
+def _mt_keys(burn_state, main_state):
     keys = []
     for st in (burn_state, main_state):
         if st[0] != "MT19937":
@@ -1001,11 +993,51 @@ def sample_radii_mcmc(kind, dim, len_rescaled, nu, burn_state, main_state, init,
         if key.shape != (624,):
             raise ValueError("MT19937 key must have 624 words")
         keys.append(key)
+    return keys
+
+
+def sample_radii_mcmc(kind, dim, len_rescaled, nu, burn_state, main_state, init, burn_in, n_steps):
+    """Native, stream-compatible ``emcee`` run of ``RNG.sample_ln_pdf`` (random/rng.py:77-101).
+
+    ``burn_state`` / ``main_state`` are the ``numpy.random.RandomState.get_state()`` tuples (legacy
+    MT19937) the reference hands to the burn-in and the production ``run_mcmc`` call, ``init`` the
+    ``nwalkers`` initial positions.  Returns the production chain ``(n_steps, nwalkers)``.  Host only.
+    ``kind``: a model name with a native log-pdf (``_lib.PDF_KINDS``), or a callable ``ln_pdf(r)`` -- the
+    model's own vectorised ``ln_spectral_rad_pdf``, called with an ``(n, 1)`` array like emcee does -- for
+    every other model (``gsb_sample_radii_mcmc_cb``).
+    """
+    keys = _mt_keys(burn_state, main_state)
     x0 = np.ascontiguousarray(_as_f64(init, "init")).reshape(-1)
     chain = np.empty((int(n_steps), x0.shape[0]), dtype=np.float64)
-    rc = _lib.load().gsb_sample_radii_mcmc(_lib.PDF_KINDS[kind], int(dim), float(len_rescaled), float(nu),
-                                           _ptr(keys[0]), int(burn_state[2]), _ptr(keys[1]), int(main_state[2]),
-                                           _ptr(x0), x0.shape[0], int(burn_in), int(n_steps), _ptr(chain))
+    lib = _lib.load()
+    if callable(kind):
+        ln_pdf, failure = kind, []
+
+        def trampoline(r_ptr, n, out_ptr, _user):
+            try:      # no exception may cross the C frames: remember it, abort the chain, re-raise below
+                r = np.ctypeslib.as_array(r_ptr, shape=(n,))
+                vals = np.asarray(ln_pdf(np.array(r).reshape(n, 1)), dtype=np.float64).reshape(-1)
+                if vals.shape[0] != n:
+                    raise ValueError("ln_pdf must return one value per radius")
+                np.ctypeslib.as_array(out_ptr, shape=(n,))[:] = vals
+                return 0
+            except BaseException as exc:  # noqa: BLE001
+                failure.append(exc)
+                return 1
+
+        cb = _lib.LN_PDF_FN(trampoline)
+        rc = lib.gsb_sample_radii_mcmc_cb(cb, None, _ptr(keys[0]), int(burn_state[2]), _ptr(keys[1]),
+                                          int(main_state[2]), _ptr(x0), x0.shape[0], int(burn_in), int(n_steps),
+                                          _ptr(chain))
+        if failure:
+            raise failure[0]
+        _lib.check(rc, "sample_radii_mcmc")
+        return chain
+    if kind not in _lib.PDF_KINDS:
+        raise ValueError(f"no native log-pdf for model '{kind}': {sorted(_lib.PDF_KINDS)}")
+    rc = lib.gsb_sample_radii_mcmc(_lib.PDF_KINDS[kind], int(dim), float(len_rescaled), float(nu),
+                                   _ptr(keys[0]), int(burn_state[2]), _ptr(keys[1]), int(main_state[2]),
+                                   _ptr(x0), x0.shape[0], int(burn_in), int(n_steps), _ptr(chain))
     _lib.check(rc, "sample_radii_mcmc")
     return chain
 

@@ -1525,6 +1525,42 @@ static int plan_structured_impl(gsb_plan *plan, const double *cov, const double 
 
 }  // namespace gsb
 
+namespace gsb {
+
+// both entry points: the chain itself (rng.py:77-101); `eval` is the log-pdf of a batch of radii
+template <typename Eval>
+static int sample_radii_impl(Eval &&eval, const uint32_t *mt_key_burn, int mt_pos_burn, const uint32_t *mt_key_main,
+                             int mt_pos_main, const double *init, int nwalkers, int burn_in, int n_steps, double *chain)
+{
+    if (!mt_key_burn || !mt_key_main || mt_pos_burn < 0 || mt_pos_burn > 624 || mt_pos_main < 0 || mt_pos_main > 624 ||
+        !init || !chain)
+        return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: NULL pointer or bad generator position");
+    if (nwalkers < 2 || (nwalkers & 1) || burn_in < 0 || n_steps < 0)
+        return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: nwalkers must be even and >= 2, step counts >= 0");
+    std::vector<double> coords(init, init + nwalkers), logp(nwalkers);
+    for (int i = 0; i < nwalkers; ++i)
+        if (!std::isfinite(coords[i])) return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: initial guess not finite");
+    if (eval(coords.data(), nwalkers, logp.data()))
+        return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: the log-pdf callback failed");
+    for (int i = 0; i < nwalkers; ++i)
+        if (std::isnan(logp[i])) return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: initial log-pdf is NaN");
+    Mt19937 rng;
+    // each run_mcmc call of RNG.sample_ln_pdf gets its own generator state: rng.py:84-99 copies
+    // self.random.get_state() into the sampler, and RNG.random is a fresh RandomState per access
+    // (rng.py:193-203), seeded from the master generator
+    for (int pass = 0; pass < 2; ++pass) {
+        std::memcpy(rng.key, pass == 0 ? mt_key_burn : mt_key_main, sizeof rng.key);
+        rng.pos = pass == 0 ? mt_pos_burn : mt_pos_main;
+        const int rc = stretch_run(eval, rng, nwalkers, pass == 0 ? burn_in : n_steps, coords.data(), logp.data(),
+                                   pass == 0 ? nullptr : chain);
+        if (rc == 2) return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: the log-pdf callback failed");
+        if (rc) return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: proposal or log-pdf not finite");
+    }
+    return GSB_OK;
+}
+
+}  // namespace gsb
+
 // =============================================================================================
 // C ABI
 // =============================================================================================
@@ -1707,34 +1743,27 @@ int gsb_sample_radii_mcmc(int pdf_kind, int dim, double len_rescaled, double nu,
                           int mt_pos_burn, const uint32_t *mt_key_main, int mt_pos_main, const double *init,
                           int nwalkers, int burn_in, int n_steps, double *chain)
 {
-    if (pdf_kind != GSB_PDF_EXPONENTIAL && pdf_kind != GSB_PDF_MATERN)
+    if (pdf_kind != GSB_PDF_EXPONENTIAL && pdf_kind != GSB_PDF_MATERN && pdf_kind != GSB_PDF_GAUSSIAN)
         return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: unknown pdf kind");
     if (dim < 1 || !(len_rescaled > 0.0) || (pdf_kind == GSB_PDF_MATERN && !(nu > 0.0)))
         return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: bad model parameters");
-    if (!mt_key_burn || !mt_key_main || mt_pos_burn < 0 || mt_pos_burn > 624 || mt_pos_main < 0 || mt_pos_main > 624 ||
-        !init || !chain)
-        return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: NULL pointer or bad generator position");
-    if (nwalkers < 2 || (nwalkers & 1) || burn_in < 0 || n_steps < 0)
-        return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: nwalkers must be even and >= 2, step counts >= 0");
-    RadPdf pdf{pdf_kind, dim, len_rescaled, nu};
-    std::vector<double> coords(init, init + nwalkers), logp(nwalkers);
-    for (int i = 0; i < nwalkers; ++i) {
-        if (!std::isfinite(coords[i])) return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: initial guess not finite");
-        logp[i] = pdf.ln_pdf(coords[i]);
-        if (std::isnan(logp[i])) return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: initial log-pdf is NaN");
-    }
-    Mt19937 rng;
-    // each run_mcmc call of RNG.sample_ln_pdf gets its own generator state: rng.py:84-99 copies
-    // self.random.get_state() into the sampler, and RNG.random is a fresh RandomState per access
-    // (rng.py:193-203), seeded from the master generator
-    for (int pass = 0; pass < 2; ++pass) {
-        std::memcpy(rng.key, pass == 0 ? mt_key_burn : mt_key_main, sizeof rng.key);
-        rng.pos = pass == 0 ? mt_pos_burn : mt_pos_main;
-        if (stretch_run(pdf, rng, nwalkers, pass == 0 ? burn_in : n_steps, coords.data(), logp.data(),
-                        pass == 0 ? nullptr : chain))
-            return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: proposal or log-pdf not finite");
-    }
-    return GSB_OK;
+    const RadPdf pdf{pdf_kind, dim, len_rescaled, nu};
+    auto eval = [&pdf](const double *q, int n, double *out) -> int {
+        for (int k = 0; k < n; ++k) out[k] = pdf.ln_pdf(q[k]);
+        return 0;
+    };
+    return sample_radii_impl(eval, mt_key_burn, mt_pos_burn, mt_key_main, mt_pos_main, init, nwalkers, burn_in, n_steps,
+                             chain);
+}
+
+int gsb_sample_radii_mcmc_cb(gsb_ln_pdf_fn ln_pdf, void *user, const uint32_t *mt_key_burn, int mt_pos_burn,
+                             const uint32_t *mt_key_main, int mt_pos_main, const double *init, int nwalkers,
+                             int burn_in, int n_steps, double *chain)
+{
+    if (!ln_pdf) return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc_cb: ln_pdf must not be NULL");
+    auto eval = [ln_pdf, user](const double *q, int n, double *out) -> int { return ln_pdf(q, n, out, user); };
+    return sample_radii_impl(eval, mt_key_burn, mt_pos_burn, mt_key_main, mt_pos_main, init, nwalkers, burn_in, n_steps,
+                             chain);
 }
 
 int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int device, void *stream)

@@ -17,8 +17,9 @@
 //   randint(n)    : masked rejection on 32 bits
 //   choice(p=[1]) : one random_sample
 // The log-pdf is the reference's `CovModel.ln_spectral_rad_pdf` (covmodel/base.py:553-560,
-// covmodel/tools.py:374-406) for the two model families that need it in the BASELINE configs:
-// Exponential (covmodel/models.py:217-224) and Matern (models.py:434-449).
+// covmodel/tools.py:374-406) with a native closed form for Exponential (covmodel/models.py:217-224), Matern
+// (models.py:434-449) and Gaussian (models.py:147-151; 3-D has no inverse CDF); every other model's own Python
+// log-pdf is called back per half ensemble (gsb_sample_radii_mcmc_cb).
 #pragma once
 
 #include <cmath>
@@ -93,7 +94,7 @@ static inline double np_pow(double x, double e)
 }
 
 struct RadPdf {
-    int kind;   // GSB_PDF_EXPONENTIAL / GSB_PDF_MATERN
+    int kind;   // GSB_PDF_EXPONENTIAL / GSB_PDF_MATERN / GSB_PDF_GAUSSIAN
     int dim;
     double len_rescaled, nu;
 
@@ -107,6 +108,10 @@ struct RadPdf {
     double spectral_density(double k) const
     {
         const double l = len_rescaled;
+        if (kind == GSB_PDF_GAUSSIAN) {    // models.py:147-151
+            const double h = k * l / 2.0;
+            return std::pow(l / 2.0 / std::sqrt(M_PI), dim) * std::exp(-(h * h));
+        }
         if (kind == GSB_PDF_EXPONENTIAL)   // models.py:217-224
             return std::pow(l, dim) * std::tgamma((dim + 1) / 2.0) /
                    np_pow(M_PI * (1.0 + (k * l) * (k * l)), (dim + 1) / 2.0);
@@ -133,8 +138,12 @@ struct RadPdf {
 
 // One EnsembleSampler.run_mcmc(state, nsteps) with the default StretchMove; coords / logp are updated in
 // place, `chain` (nsteps x nwalkers) receives the positions after every step when non-null.
-// Returns 0, or 1 when a proposal or its log-pdf is not finite (emcee raises ValueError there).
-static inline int stretch_run(const RadPdf &pdf, Mt19937 &rng, int nwalkers, int nsteps, double *coords, double *logp,
+// Returns 0, 1 when a proposal or its log-pdf is not finite (emcee raises ValueError there), 2 when `eval` aborted.
+//
+// `eval(q, n, out)` evaluates the log-pdf of n proposals at once (emcee runs the reference's sampler with
+// vectorize=True: one call per half ensemble); it returns non-zero to abort.
+template <typename Eval>
+static inline int stretch_run(Eval &&eval, Mt19937 &rng, int nwalkers, int nsteps, double *coords, double *logp,
                               double *chain)
 {
     std::vector<int> inds(nwalkers), S, C;
@@ -167,11 +176,11 @@ static inline int stretch_run(const RadPdf &pdf, Mt19937 &rng, int nwalkers, int
                 const double c = coords[C[r]];
                 q[k] = c - (c - coords[S[k]]) * zz[k];
             }
-            for (int k = 0; k < ns; ++k) {
+            for (int k = 0; k < ns; ++k)
                 if (!std::isfinite(q[k])) return 1;
-                nlp[k] = pdf.ln_pdf(q[k]);
+            if (ns > 0 && eval(q.data(), ns, nlp.data())) return 2;
+            for (int k = 0; k < ns; ++k)
                 if (std::isnan(nlp[k])) return 1;
-            }
             for (int k = 0; k < ns; ++k) {                          // ndim = 1: factors = 0 * log(zz)
                 const double lnpdiff = 0.0 * std::log(zz[k]) + nlp[k] - logp[S[k]];
                 if (lnpdiff > std::log(rng.next_double())) accepted[S[k]] = 1;

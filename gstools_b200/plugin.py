@@ -685,35 +685,41 @@ def _build_sample_ln_pdf(r):
 
     verdicts = {}     # kind -> does the native run reproduce the installed emcee / numpy, bit for bit?
 
-    def _native(self, kind, model, size, sample_around, nwalkers, burn_in, oversampling_factor):
+    def _native(self, kind, model, ln_pdf, size, sample_around, nwalkers, burn_in, oversampling_factor):
         # same draws from the master generator, in the same order, as rng.py:72-104
         sample_size = burn_in if size is None else max(burn_in, (size / nwalkers) * oversampling_factor)
         sample_size = int(sample_size)
         init_guess = self.random.rand(nwalkers).reshape((nwalkers, 1)) * sample_around
         burn_state = self.random.get_state()
         main_state = self.random.get_state()
-        chain = backend.sample_radii_mcmc(kind, model.dim, model.len_rescaled, getattr(model, "nu", 0.0),
-                                          burn_state, main_state, init_guess[:, 0], burn_in, sample_size)
+        if kind == "callback":       # the model's own log-pdf, evaluated per half ensemble like emcee does
+            chain = backend.sample_radii_mcmc(ln_pdf, 0, 0.0, 0.0, burn_state, main_state, init_guess[:, 0], burn_in,
+                                              sample_size)
+        else:
+            chain = backend.sample_radii_mcmc(kind, model.dim, model.len_rescaled, getattr(model, "nu", 0.0),
+                                              burn_state, main_state, init_guess[:, 0], burn_in, sample_size)
         return self.random.choice(chain.reshape(-1), size)
 
-    def _stream_compatible(kind, model):
+    def _stream_compatible(kind, ln_pdf):
         """One short chain through the ORIGINAL sample_ln_pdf (the installed emcee and numpy) and through the native
         restatement, from the same seed: the native sampler hard-codes how emcee's stretch move consumes the
-        generator (choice, shuffled red/blue split, rand, randint, rand) and numpy's pow / log / exp, so any other
-        emcee or numpy must be DETECTED, not assumed.  Once per model class and process (a few ms)."""
+        generator (choice, shuffled red/blue split, rand, randint, rand) and -- for the native log-pdfs -- numpy's
+        pow / log / exp, so any other emcee or numpy must be DETECTED, not assumed.  Once per kind and process."""
         if kind not in verdicts:
             ok = False
             try:
-                ln_pdf = model.ln_spectral_rad_pdf
-                args = (24, 1.0 / model.len_rescaled, 6, 3, 3)
+                model = getattr(ln_pdf, "__self__", None)
+                around = 1.0 / model.len_rescaled if model is not None else 1.0
+                args = (24, around, 6, 3, 3)
                 want = orig(r.grng.RNG(271828), ln_pdf, *args)
-                got = _native(r.grng.RNG(271828), kind, model, *args)
+                got = _native(r.grng.RNG(271828), kind, model, ln_pdf, *args)
                 ok = np.array_equal(want, got)
             except Exception:  # no usable emcee to compare with: keep the reference's own path
                 ok = False
             if not ok:
-                warnings.warn(f"gstools_b200: the native radius sampler does not reproduce the installed emcee/numpy for "
-                              f"{kind}; RNG.sample_ln_pdf keeps the reference's sampler", RuntimeWarning, stacklevel=3)
+                warnings.warn(f"gstools_b200: the native radius sampler ({kind}) does not reproduce the installed "
+                              f"emcee/numpy; RNG.sample_ln_pdf keeps the reference's sampler", RuntimeWarning,
+                              stacklevel=3)
             verdicts[kind] = ok
         return verdicts[kind]
 
@@ -721,12 +727,15 @@ def _build_sample_ln_pdf(r):
                       oversampling_factor=10):
         model = getattr(ln_pdf, "__self__", None)
         kind = pdf_models.get(type(model))
-        native = (r.on() and kind is not None and getattr(ln_pdf, "__func__", None) is base_ln_pdf
-                  and type(model).spectral_density is getattr(cmodels, kind).spectral_density
-                  and nwalkers >= 2 and nwalkers % 2 == 0 and _stream_compatible(kind, model))
+        closed_form = (kind is not None and getattr(ln_pdf, "__func__", None) is base_ln_pdf
+                       and type(model).spectral_density is getattr(cmodels, kind).spectral_density)
+        if not closed_form:
+            kind = "callback"        # any other model / density: native stretch move around the caller's log-pdf
+        native = (r.on() and callable(ln_pdf) and nwalkers >= 2 and nwalkers % 2 == 0
+                  and _stream_compatible(kind, ln_pdf))
         if not native:
             return orig(self, ln_pdf, size, sample_around, nwalkers, burn_in, oversampling_factor)
-        return _native(self, kind, model, size, sample_around, nwalkers, burn_in, oversampling_factor)
+        return _native(self, kind, model, ln_pdf, size, sample_around, nwalkers, burn_in, oversampling_factor)
 
     return _like(sample_ln_pdf, orig)
 

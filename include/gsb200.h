@@ -290,17 +290,31 @@ int gsb_krige_evaluate_structured(const gsb_cov_model *model, const double *krig
  * the reference hands each run_mcmc call the state of a fresh RandomState (rng.py:84-99, 193-203) --
  * and writes the positions of all walkers after every production step to chain[n_steps][nwalkers]
  * (= get_chain(flat=True)).
- *   pdf_kind   GSB_PDF_EXPONENTIAL / GSB_PDF_MATERN: CovModel.ln_spectral_rad_pdf of that model
+ *   pdf_kind   GSB_PDF_EXPONENTIAL / GSB_PDF_MATERN / GSB_PDF_GAUSSIAN: CovModel.ln_spectral_rad_pdf of that model
  *              (covmodel/base.py:553-560, covmodel/tools.py:374-406, models.py:217-224, 434-449)
  *   init       nwalkers initial positions (rng.py:78-80)
  * No device is touched.
  */
 #define GSB_PDF_EXPONENTIAL 1
 #define GSB_PDF_MATERN 2
+#define GSB_PDF_GAUSSIAN 3
 int gsb_sample_radii_mcmc(int pdf_kind, int dim, double len_rescaled, double nu,
                           const uint32_t *mt_key_burn, int mt_pos_burn,
                           const uint32_t *mt_key_main, int mt_pos_main, const double *init,
                           int nwalkers, int burn_in, int n_steps, double *chain);
+
+/*
+ * The same chain for ANY model: the log-pdf is the caller's -- `ln_pdf(r, n, out, user)` writes the log of the radial
+ * spectral density of n radii (the reference hands emcee `model.ln_spectral_rad_pdf` with vectorize=True: one
+ * evaluation per half ensemble, src/gstools/random/rng.py:88, covmodel/base.py:557-560) and returns 0, or non-zero to
+ * abort.  The stretch move, the red/blue split and the consumption of the MT19937 stream are native; models without
+ * a native closed form (Integral, HyperSpherical, JBessel, the TPL family, and every model whose spectral density is
+ * a numerical Hankel transform) keep their own Python density and still lose emcee's per-step Python overhead.
+ */
+typedef int (*gsb_ln_pdf_fn)(const double *r, int n, double *ln_pdf, void *user);
+int gsb_sample_radii_mcmc_cb(gsb_ln_pdf_fn ln_pdf, void *user, const uint32_t *mt_key_burn, int mt_pos_burn,
+                             const uint32_t *mt_key_main, int mt_pos_main, const double *init, int nwalkers,
+                             int burn_in, int n_steps, double *chain);
 
 /*
  * Fused caller epilogue (reference: src/gstools/field/generator.py:269-270):

@@ -606,6 +606,63 @@ def test_native_sampler_falls_back_when_emcee_differs(gsb, monkeypatch):
 
 
 @needs_ref
+@pytest.mark.parametrize("make", [
+    lambda gs: gs.Gaussian(dim=3, var=2.0, len_scale=4.0),
+    lambda gs: gs.Integral(dim=3, var=1.0, len_scale=5.0, nu=1.5),
+    lambda gs: gs.JBessel(dim=2, var=1.0, len_scale=3.0, nu=1.0),
+    lambda gs: gs.HyperSpherical(dim=3, var=1.0, len_scale=6.0),
+    lambda gs: gs.TPLGaussian(dim=3, var=1.0, len_scale=6.0),
+    lambda gs: gs.TPLExponential(dim=2, var=1.0, len_scale=6.0),
+], ids=["Gaussian3d", "Integral", "JBessel", "HyperSpherical", "TPLGaussian", "TPLExponential"])
+def test_native_stretch_move_around_any_models_log_pdf(gsb, make):
+    """Row f4 for every model: no native closed form -> the native sampler calls the model's own
+    ln_spectral_rad_pdf per half ensemble (gsb_sample_radii_mcmc_cb); same seed -> the same modes, bit for bit.
+    (Models whose spectral density is a numerical Hankel transform -- Stable, Spherical, ... -- take the same
+    path; they cannot run in this container: the `hankel` package is not installed.)"""
+    gs = refharness.import_gstools()
+    from gstools.field.generator import RandMeth
+    from gstools_b200 import backend
+
+    ref = RandMeth(make(gs), mode_no=120, seed=77)
+    used = []
+    real = backend.sample_radii_mcmc
+    gsb.enable()
+    backend.sample_radii_mcmc = lambda *a: (used.append(a[0]), real(*a))[1]
+    try:
+        got = RandMeth(make(gs), mode_no=120, seed=77)
+    finally:
+        backend.sample_radii_mcmc = real
+        gsb.disable()
+    if getattr(ref.model, "has_ppf", False):
+        assert not used
+    elif type(ref.model).__name__ == "Gaussian":
+        assert used and used[-1] == "Gaussian"          # native closed form (models.py:147-151)
+    else:
+        assert used and callable(used[-1])
+    assert np.array_equal(got._cov_sample, ref._cov_sample)
+    assert np.array_equal(got._z_1, ref._z_1) and np.array_equal(got._z_2, ref._z_2)
+
+
+@needs_ref
+def test_log_pdf_errors_surface_from_the_callback(gsb):
+    """An exception inside the caller's log-pdf aborts the native chain and is re-raised; NaN is emcee's ValueError."""
+    from gstools_b200 import backend
+
+    st = np.random.RandomState(3).get_state()
+    init = np.linspace(0.1, 1.0, 6)
+
+    def boom(r):
+        raise KeyError("inside ln_pdf")
+
+    with pytest.raises(KeyError, match="inside ln_pdf"):
+        backend.sample_radii_mcmc(boom, 0, 0.0, 0.0, st, st, init, 2, 3)
+    with pytest.raises(ValueError, match="NaN"):
+        backend.sample_radii_mcmc(lambda r: np.full(len(r), np.nan), 0, 0.0, 0.0, st, st, init, 2, 3)
+    chain = backend.sample_radii_mcmc(lambda r: -0.5 * np.asarray(r)[:, 0] ** 2, 0, 0.0, 0.0, st, st, init, 2, 5)
+    assert chain.shape == (5, 6) and np.all(np.isfinite(chain))
+
+
+@needs_ref
 def test_fused_wrappers_only_over_known_upstream_bodies(gsb, monkeypatch):
     """a wrapper that restates an upstream method is installed only over a body it was written
     against; any other body keeps the reference's code and is reported."""
@@ -671,16 +728,20 @@ def test_native_radius_sampler_reference_literals_and_fallthrough(gsb, monkeypat
         RandMeth(gs.Exponential(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=3)
         assert calls == ["Exponential"] * 3
         del calls[1:]
-        # the fixture's model (Gaussian 3-D) has an inverse CDF: no MCMC at all, same modes as recorded
+        # the fixture's model (Gaussian 3-D: no inverse CDF in 3-D, models.py:185-186): native closed form, reproduces
+        # the modes recorded from the reference (16-digit literals of tests/test_randmeth.py:43-46 hang on them)
         rg = RandMeth(gs.Gaussian(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=19031977)
-        assert calls == ["Exponential"] and np.array_equal(rg._cov_sample, d["cov_samples"])
+        assert calls == ["Exponential", "Gaussian", "Gaussian"]          # self-check chain, then the real one
+        assert np.array_equal(rg._cov_sample, d["cov_samples"])
+        del calls[1:]
 
-        class MyMatern(gs.Matern):                                  # overridden density: emcee
+        class MyMatern(gs.Matern):                                  # overridden density: the callback variant too
             def spectral_density(self, k):
                 return super().spectral_density(k)
 
         RandMeth(MyMatern(dim=2, var=1, len_scale=3, nu=1.0), mode_no=50, seed=1)
-        assert calls == ["Exponential"]
+        assert len(calls) == 3 and all(callable(c) for c in calls[1:])     # self-check of the callback variant + the run
+        del calls[1:]
         config.USE_GSTOOLS_B200 = False
         RandMeth(gs.Exponential(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=19031977)
         assert calls == ["Exponential"]
