@@ -376,6 +376,8 @@ struct MeshInfo {
 static std::atomic<int64_t> g_cnt_sk{0};
 static std::atomic<int64_t> g_opt_sk_table_mb{256};     // cap on the tile-axis table (all batch entries)
 static std::atomic<int64_t> g_opt_sk_grid{0};           // 0: one CTA per SM; else a fixed grid (tests)
+static std::atomic<int64_t> g_opt_sk_pack{0};           // row packing across slow indices: 0 auto, 1 never, 2 whenever possible
+static std::atomic<int64_t> g_cnt_packed{0};
 static std::atomic<int64_t> g_opt_host_pieces{0};       // host route: 0 = growing pieces (default), n = n equal pieces
 
 // The virtual mesh of the contraction: [outer slow axes | tile axes (folded: ly rows) | inner slow axes |
@@ -384,7 +386,21 @@ struct SkLayout {
     int n_prefix, n_tile_axes, n_inner, n_col_axes;
     int64_t n_slow, n_in, ly, lc;
     int n_ytiles, n_col_tiles;
+    // virtual row space of a field (gsb_sepk.cuh): lyp rows per slow index, n_vt row tiles per field
+    bool pack;
+    int64_t lyp, n_vt;
 };
+
+// Cost of a field's row tiles when they are packed across the slow indices: all tiles full except the last one.
+static int64_t sk_packed_cost(int64_t n_slow, int64_t ly, int64_t lc, int n_col_tiles, int64_t *n_vt_out)
+{
+    const int64_t lyp = (ly + 7) / 8 * 8, vrows = n_slow * lyp, n_vt = (vrows + SK_TM - 1) / SK_TM;
+    int64_t per = 0;
+    for (int ct = 0; ct < n_col_tiles; ++ct)
+        per += (n_vt - 1) * sk_tile_cost(vrows, lc, 0, ct) + sk_tile_cost(vrows, lc, (int)(n_vt - 1), ct);
+    if (n_vt_out) *n_vt_out = n_vt;
+    return per;
+}
 
 // Which contiguous group of row axes becomes the tile axis?  Estimated time = contraction (cost units of sk_plan:
 // 64 units = one full 128 x 128 tile stage = 4096 SM cycles at 64 DFMA / clk) + building the tile-axis table
@@ -405,6 +421,8 @@ static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int6
     for (int t = 0; t < n_row; ++t) n_rows *= mesh.len[t];
     double best = 1e300;
     int best_a = n_row - 1, best_b = n_row;
+    bool best_pack = false;
+    const int64_t pack_opt = g_opt_sk_pack.load();
     for (int a = 0; a < n_row; ++a) {
         int64_t P = 1;
         for (int b = a + 1; b <= n_row; ++b) {
@@ -417,8 +435,25 @@ static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int6
             int64_t per = 0;
             for (int ct = 0; ct < L.n_col_tiles; ++ct)
                 per += (n_yt - 1) * sk_tile_cost(P, L.lc, 0, ct) + sk_tile_cost(P, L.lc, (int)(n_yt - 1), ct);
-            const double units = (double)(n_rows / P) * (double)per * (double)n_stages * (double)(n_batch * ncomp);
+            double units = (double)(n_rows / P) * (double)per * (double)n_stages * (double)(n_batch * ncomp);
             const bool no_slow = (b - a == n_row);
+            // Row tiles packed across the slow indices (200^3: 200 rows per plane instead of 256): possible when
+            // slow axes exist (the per-slow factors are what a tile then has several of), P is not a multiple of 128
+            // anyway, and a 128-row tile touches at most SK_MAXSEG slow indices
+            bool pack = false;
+            if (!no_slow && n_rows / P > 1 && P % SK_TM != 0 && (P + 7) / 8 * 8 >= SK_PACK_MIN_ROWS && pack_opt != 1) {
+                int64_t n_vt = 0;
+                const int64_t pper = sk_packed_cost(n_rows / P, P, L.lc, L.n_col_tiles, &n_vt);
+                const double punits = (double)pper * (double)n_stages * (double)(n_batch * ncomp);
+                // (a packed tile costs a little more than a plain one -- one bulk copy and one block of factors per
+                // slow index it touches, one more LDS per quad of modes: 64 x 512 x 512 with axis 0 packed measured
+                // 4 % slower than axis 1 as plain tile axis, which the table sizes alone would not have chosen)
+                const double penalty = 1.05;
+                if (n_vt * L.n_col_tiles < (1 << 26) && (punits * penalty < units || pack_opt == 2)) {
+                    pack = true;
+                    units = punits * penalty;
+                }
+            }
             // (a tile is cut into at most ~8 shares, sk_plan: a tiny mesh cannot use every SM)
             const double min_share = std::max<double>(64.0, (double)n_stages * 64.0 / 8.0);
             const double ctas = std::max(1.0, std::min((double)sm_count, std::floor(units / min_share)));
@@ -436,7 +471,7 @@ static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int6
             }
             // ties: prefer the trailing axes (rows of a tile then are neighbours in memory)
             const double t = (t_contract + t_table + t_copy) * (1.0 + 1e-6 * (n_row - b));
-            if (t < best) { best = t; best_a = a; best_b = b; }
+            if (t < best) { best = t; best_a = a; best_b = b; best_pack = pack; }
         }
     }
     L.n_prefix = best_a;
@@ -448,6 +483,9 @@ static SkLayout sk_choose_layout(const MeshInfo &mesh, int64_t n_modes_pad, int6
     for (int t = best_b; t < n_row; ++t) L.n_in *= mesh.len[t];
     L.n_slow = n_rows / L.ly;
     L.n_ytiles = (int)((L.ly + SK_TM - 1) / SK_TM);
+    L.pack = best_pack;
+    L.lyp = best_pack ? (L.ly + 7) / 8 * 8 : (int64_t)L.n_ytiles * SK_TM;
+    L.n_vt = (L.n_slow * L.lyp + SK_TM - 1) / SK_TM;
     if (est_seconds) {
         const double b_bytes = (double)n_batch * ncomp * L.n_col_tiles * (double)n_stages * SK_B_TILE * sizeof(double);
         *est_seconds = best + b_bytes / 1.0e12 + 8e-6;      // + two launches
@@ -476,24 +514,34 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
     // engine starts early -- and the pieces grow by 1.25x, the ratio at which the next contraction still finishes
     // before the previous copy does.  Unit u = z * n_slow + slow covers the output elements [u, u + 1) * ly * lc,
     // so a piece is ONE contiguous copy (with inner slow axes a unit is not contiguous: pieces then are whole fields).
-    const int64_t units = n_batch * ncomp * L.n_slow;
-    const int64_t tiles_per_unit = (int64_t)L.n_ytiles * L.n_col_tiles;
-    const int64_t cut_units = L.n_in == 1 ? units : n_batch * ncomp;
-    const int64_t unit_mult = units / cut_units;
-    std::vector<int64_t> cuts{0};      // piece k = cut units [cuts[k], cuts[k+1])
+    // Work is numbered in ROW TILES: field z = (batch, component) owns the row tiles [z * n_vt, (z + 1) * n_vt), each
+    // of n_col_tiles tiles.  A piece is a range of row tiles [g0, g1); after it, the (field, slow index) units
+    // [done(g0), done(g1)) are complete -- unit u covers the output elements [u, u + 1) * ly * lc, so a piece leaves
+    // as ONE contiguous copy per field (with inner slow axes a unit is not contiguous: pieces then are whole fields).
+    const int64_t n_z = n_batch * ncomp;
+    const int64_t total_vt = n_z * L.n_vt;
+    // cut granularity: whole fields with inner slow axes; whole slow indices when nothing is packed
+    const int64_t quantum = L.n_in > 1 ? L.n_vt : (L.pack ? 1 : (int64_t)L.n_ytiles);
+    auto done_units = [&](int64_t g) -> int64_t {
+        const int64_t z = g / L.n_vt, vt = g % L.n_vt;
+        if (L.n_in > 1) return z * L.n_slow;
+        return z * L.n_slow + std::min<int64_t>(L.n_slow, vt * SK_TM / L.lyp);
+    };
+    std::vector<int64_t> cuts{0};      // piece k = row tiles [cuts[k], cuts[k+1])
     if (h_out) {
-        const int64_t tiles_per_cut = tiles_per_unit * unit_mult;
-        const int64_t min_cut = std::max<int64_t>(1, ((int64_t)max_grid + tiles_per_cut - 1) / tiles_per_cut);   // >= one wave
-        double want = std::max<double>((double)min_cut, (double)cut_units / 64.0);
+        const int64_t n_q = total_vt / quantum;                                       // cut positions available
+        const int64_t tiles_per_q = quantum * L.n_col_tiles;
+        const int64_t min_cut = std::max<int64_t>(1, ((int64_t)max_grid + tiles_per_q - 1) / tiles_per_q);   // >= one wave
+        double want = std::max<double>((double)min_cut, (double)n_q / 64.0);
         const int64_t fixed = g_opt_host_pieces.load();
-        for (int64_t k = 1; fixed > 0 && k <= fixed; ++k) cuts.push_back(cut_units * k / fixed);
-        while (fixed <= 0 && cuts.back() < cut_units && cuts.size() < 32) {
-            cuts.push_back(std::min<int64_t>(cut_units, cuts.back() + std::max<int64_t>(min_cut, (int64_t)want)));
+        for (int64_t k = 1; fixed > 0 && k <= fixed; ++k) cuts.push_back(n_q * k / fixed * quantum);
+        while (fixed <= 0 && cuts.back() < total_vt && cuts.size() < 32) {
+            cuts.push_back(std::min<int64_t>(total_vt, cuts.back() + std::max<int64_t>(min_cut, (int64_t)want) * quantum));
             want *= 1.25;
         }
     }
-    if (cuts.size() == 1) cuts.push_back(cut_units);      // device route: one piece
-    cuts.back() = cut_units;
+    if (cuts.size() == 1) cuts.push_back(total_vt);      // device route: one piece
+    cuts.back() = total_vt;
     const int64_t pieces = (int64_t)cuts.size() - 1;
     SkTableParams tp;
     std::memset(&tp, 0, sizeof tp);
@@ -548,6 +596,9 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
     sp.ttab = tp.ttab;
     sp.btile = tp.btile;
     sp.n_ytiles = L.n_ytiles;
+    sp.lyp = L.lyp;
+    sp.vrows = L.n_slow * L.lyp;
+    sp.n_vt = L.n_vt;
     sp.n_col_tiles = L.n_col_tiles;
     sp.n_stages = n_stages;
     sp.ncomp = ncomp;
@@ -564,18 +615,23 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
     unsigned *d_flags = tp.flags;
     std::vector<SkBound> bnd;
     for (int64_t k = 0; k < pieces; ++k) {
-        const int64_t u0 = cuts[(size_t)k] * unit_mult, u1 = cuts[(size_t)k + 1] * unit_mult;
-        if (u1 == u0) continue;
-        const int grid = sk_plan(u0 * tiles_per_unit, u1 * tiles_per_unit, L.n_ytiles, L.n_col_tiles, n_stages, L.ly,
-                                 L.lc, max_grid, bnd);
+        const int64_t g0 = cuts[(size_t)k], g1 = cuts[(size_t)k + 1];
+        if (g1 == g0) continue;
+        // equal-cost shares of the tiles of this piece; the cost period is one slow index (nothing packed: every slow
+        // index has the same row tiles) or one field (packed: all row tiles full except the last)
+        const int grid = L.pack ? sk_plan(g0 * L.n_col_tiles, g1 * L.n_col_tiles, (int)L.n_vt, L.n_col_tiles, n_stages,
+                                          L.n_slow * L.lyp, L.lc, max_grid, bnd)
+                                : sk_plan(g0 * L.n_col_tiles, g1 * L.n_col_tiles, L.n_ytiles, L.n_col_tiles, n_stages, L.ly,
+                                          L.lc, max_grid, bnd);
         for (int c = 0; c <= grid; ++c) sp.bnd[c] = bnd[(size_t)c];
         sp.flags = d_flags + k * max_grid;
         {
             KernelTimer timer(st);
             TraceScope ts("contract(sk)", st);
-            GSB_TRY(sk_launch(sp, grid, scale, partial, st));
+            GSB_TRY(sk_launch(sp, grid, scale, partial, L.pack, st));
         }
-        if (h_out) {
+        const int64_t u0 = done_units(g0), u1 = (g1 == total_vt) ? n_z * L.n_slow : done_units(g1);
+        if (h_out && u1 > u0) {
             cudaEvent_t ev = dev.contract_events[k % DeviceState::N_CHUNK_EVENTS];
             GSB_CUDA(cudaEventRecord(ev, st));
             GSB_CUDA(cudaStreamWaitEvent(dev.streams[1], ev, 0));
@@ -603,6 +659,7 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
         GSB_CUDA(cudaStreamWaitEvent(st, dev.events[4], 0));
     }
     g_cnt_sk.fetch_add(1);
+    if (L.pack) g_cnt_packed.fetch_add(1);
     return GSB_OK;
 }
 
@@ -1984,6 +2041,7 @@ int gsb_set_option(const char *name, int64_t value)
     else if (n == "sk_table_mb") g_opt_sk_table_mb = std::max<int64_t>(value, 1);
     else if (n == "sk_grid") g_opt_sk_grid = std::max<int64_t>(value, 0);
     else if (n == "host_pieces") g_opt_host_pieces = std::max<int64_t>(value, 0);
+    else if (n == "sk_pack") g_opt_sk_pack = std::max<int64_t>(value, 0);
     else return fail(GSB_ERR_ARGUMENT, "unknown option: " + n);
     return GSB_OK;
 }
@@ -1998,6 +2056,7 @@ int64_t gsb_get_counter(const char *name)
     if (n == "krige_calls") return g_cnt_krige.load();
     if (n == "folded_calls") return g_cnt_folded.load();
     if (n == "sk_calls") return g_cnt_sk.load();
+    if (n == "packed_calls") return g_cnt_packed.load();
     return -1;
 }
 

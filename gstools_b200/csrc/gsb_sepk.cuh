@@ -23,6 +23,13 @@
 //     shares, one per SM.  A tile that straddles two shares is finished by the CTA that started it: the later
 //     CTA(s) write their partial accumulators to a scratch slot and raise a flag, the owner adds them in a fixed
 //     order (deterministic, no atomics on data).
+//   * ROW PACKING (round 2, second step).  Row tiles used to restart at every slow index: a 200^3 mesh computed
+//     256 rows per plane for 200 (78 %), 300^3 384 for 300.  Now the rows of a field live in ONE virtual row space,
+//     `lyp` rows per slow index (ly rounded up to 8, the height of a DMMA row group; or to 128 when nothing is
+//     packed), cut into 128-row tiles regardless of the slow boundaries.  A tile that spans several slow indices
+//     gets its T rows as several bulk copies (one per slow index, the rows are contiguous in the table) and one
+//     128-byte block of slow-axis factors per slow index; every 8-row group rescales with the factors of ITS slow
+//     index.  Costs one more LDS.128 per quad of modes; saves the padding rows.
 #pragma once
 
 #include <algorithm>
@@ -50,7 +57,9 @@ constexpr int SK_BST = SK_TN + 4;
 constexpr int SK_A_TILE = SK_TM * SK_AST;
 constexpr int SK_B_TILE = 2 * SK_KC * SK_BST;
 constexpr int SK_C_BLOCK = 2 * SK_KC;
-constexpr int SK_STAGE_DOUBLES = SK_A_TILE + SK_B_TILE + SK_C_BLOCK;
+constexpr int SK_MAXSEG = 4;               // slow indices a packed row tile may touch (rows per slow index >= 48)
+constexpr int SK_PACK_MIN_ROWS = 48;
+constexpr int SK_STAGE_DOUBLES = SK_A_TILE + SK_B_TILE + SK_MAXSEG * SK_C_BLOCK;
 constexpr size_t SK_SMEM_BYTES =
     (size_t)SK_STAGES * SK_STAGE_DOUBLES * sizeof(double) + 2 * SK_STAGES * sizeof(uint64_t) + 128;
 constexpr int SK_MAX_AXES = GSB_MAX_DIM;
@@ -75,7 +84,7 @@ struct SkTableParams {
     int64_t n_modes;
     int n_modes_pad, ncomp;
     int n_ytiles, n_col_tiles;
-    double *ttab;                       // [b][ytile][stage] blocks of SK_A_TILE
+    double *ttab;                       // [b][stage][n_ytiles * 128 rows][SK_AST]: all rows of a stage are contiguous
     double *btile;                      // [b][comp][col tile][stage] blocks of SK_B_TILE
     double2 *ctab;                      // [b][slow][mode] slow-axis factors; NULL: no prefix axes, the T table
                                         //   carries (z1 - i z2) sf itself and stores (Re A, -Im A)
@@ -142,7 +151,7 @@ __global__ void sk_tables_kernel(const SkTableParams tp)
             }
             const int yt = (int)(i / SK_TM), r = (int)(i % SK_TM);
             const int kc = (int)(j % SK_KC);
-            double *row = tp.ttab + ((b * tp.n_ytiles + yt) * n_stages + j / SK_KC) * (int64_t)SK_A_TILE + r * SK_AST;
+            double *row = tp.ttab + ((b * n_stages + j / SK_KC) * tp.n_ytiles + yt) * (int64_t)SK_A_TILE + r * SK_AST;
             *reinterpret_cast<double2 *>(row + 2 * kc) = make_double2(c, s);
             if (kc == 0) {
 #pragma unroll
@@ -271,6 +280,10 @@ struct SkParams {
     int n_ytiles, n_col_tiles, n_stages, ncomp;
     int64_t n_slow, n_in;     // slow = outer * n_in + inner: row of (slow, iy) = (outer * ly + iy) * n_in + inner
     int64_t ly, lc;
+    // virtual row space of a field: slow index s owns the rows [s * lyp, s * lyp + ly); tile vt covers the virtual
+    // rows [128 vt, 128 vt + 128).  lyp = n_ytiles * 128 (nothing packed) or ly rounded up to 8 (packed).
+    int64_t lyp, vrows;       // vrows = n_slow * lyp
+    int64_t n_vt;             // row tiles per field = ceil(vrows / 128)
     int n_modes_pad;
     double *out;              // field (batch, comp) at out + (batch*ncomp + comp)*out_fstride; row r at + r*lc
     int64_t out_fstride;
@@ -301,9 +314,10 @@ __device__ __forceinline__ void sk_st_release(unsigned *p, unsigned v)
 // One pipeline stage of a warp: NI row groups (1 or 2) x JV column groups (4, 8, 12 or 16), all compile-time, so
 // that partial tiles run the same straight-line, software-pipelined code as full ones (a first version predicated
 // every column group at run time: each LDS was followed by its dependent DMMA, 2x slower on partial tiles).
-template <bool SCALE, int JV, int NI>
+// PACK: the two row groups of the warp may belong to different slow indices -> two blocks of slow-axis factors.
+template <bool SCALE, bool PACK, int JV, int NI>
 __device__ __forceinline__ void sk_stage(const double *S, double (&acc)[2][16][2], int a_off0, int a_off1, int b_off,
-                                         int c_off)
+                                         int c_off0, int c_off1)
 {
 #pragma unroll
     for (int q = 0; q < SK_KC / 4; ++q) {
@@ -313,13 +327,15 @@ __device__ __forceinline__ void sk_stage(const double *S, double (&acc)[2][16][2
         double2 e1 = make_double2(0.0, 0.0);
         if (NI > 1) e1 = *reinterpret_cast<const double2 *>(S + a_off1 + 8 * q);
         if (SCALE) {
-            const double2 cc = *reinterpret_cast<const double2 *>(S + c_off + 8 * q);
+            const double2 cc = *reinterpret_cast<const double2 *>(S + c_off0 + 8 * q);
             //  Re(c e) = cr cos - ci sin        -Im(c e) = -(cr sin + ci cos)
             ar[0] = fma(cc.x, e0.x, -(cc.y * e0.y));
             ai[0] = fma(-cc.x, e0.y, -(cc.y * e0.x));
             if (NI > 1) {
-                ar[1] = fma(cc.x, e1.x, -(cc.y * e1.y));
-                ai[1] = fma(-cc.x, e1.y, -(cc.y * e1.x));
+                double2 c1 = cc;
+                if (PACK) c1 = *reinterpret_cast<const double2 *>(S + c_off1 + 8 * q);
+                ar[1] = fma(c1.x, e1.x, -(c1.y * e1.y));
+                ai[1] = fma(-c1.x, e1.y, -(c1.y * e1.x));
             }
         } else {
             ar[0] = e0.x; ai[0] = e0.y;
@@ -338,11 +354,62 @@ __device__ __forceinline__ void sk_stage(const double *S, double (&acc)[2][16][2
     }
 }
 
+// Row geometry of tile vt (warp-uniform): the segments of the virtual row space it covers.  Segment k holds
+// `rows[k]` tile rows from tile row `row0[k]` on, they are the rows iy0[k] .. of slow index slow[k].
+template <bool PACK>
+struct SkTileGeo {
+    static constexpr int NS = PACK ? SK_MAXSEG : 1;
+    int nseg;
+    int groups;          // 8-row groups of the tile that hold mesh rows (a prefix of the 16)
+    int row0[NS], rows[NS], iy0[NS];
+    int64_t slow[NS];
+};
+
+template <bool PACK>
+__device__ __forceinline__ void sk_tile_geo(const SkParams &prm, int64_t vt, SkTileGeo<PACK> &g)
+{
+    const int64_t v0 = vt * SK_TM;
+    int64_t slow = v0 / prm.lyp;
+    int iy = (int)(v0 - slow * prm.lyp);
+    if (!PACK) {
+        // lyp is a multiple of 128: the tile lies inside one slow index; rows beyond ly are padding
+        const int rows = (int)min((int64_t)SK_TM, prm.ly - iy);
+        g.nseg = 1;
+        g.groups = (rows + 7) >> 3;
+        g.row0[0] = 0;
+        g.rows[0] = g.groups * 8;
+        g.iy0[0] = iy;
+        g.slow[0] = slow;
+        return;
+    }
+    // lyp = ly rounded up to 8: every group of a slow index holds at least one mesh row
+    const int avail = (int)min((int64_t)SK_TM, prm.vrows - v0);
+    int covered = 0, n = 0;
+#pragma unroll
+    for (int k = 0; k < SK_MAXSEG; ++k) {
+        if (covered < avail) {
+            const int take = min(avail - covered, (int)prm.lyp - iy);
+            g.row0[k] = covered;
+            g.rows[k] = take;
+            g.iy0[k] = iy;
+            g.slow[k] = slow;
+            covered += take;
+            n = k + 1;
+            ++slow;
+            iy = 0;
+        }
+    }
+    g.nseg = n;
+    g.groups = avail >> 3;
+}
+
 // SCALE   : rescale the T fragments by the slow-axis factor (meshes with prefix axes); false: the T table is A itself
-// PARTIAL : tiles may hang over the mesh edge (ly % 128 or lc % 128 != 0): skip the row / column groups outside
-template <bool SCALE, bool PARTIAL>
+// PARTIAL : tiles may hang over the mesh edge: skip the row / column groups outside
+// PACK    : row tiles span slow indices (see the file header); implies SCALE and PARTIAL
+template <bool SCALE, bool PARTIAL, bool PACK>
 __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid_constant__ SkParams prm)
 {
+    static_assert(!PACK || (SCALE && PARTIAL), "packing needs slow axes and handles partial tiles");
     extern __shared__ __align__(128) unsigned char sk_smem_raw[];
     double *stage_base = reinterpret_cast<double *>(sk_smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + SK_STAGES * SK_STAGE_DOUBLES);
@@ -353,6 +420,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid
     const int lane = tid & 31;
     const int n_stages = prm.n_stages;
     const int cta = blockIdx.x;
+    const int64_t lyt = (int64_t)prm.n_ytiles * SK_TM;           // table rows per stage
 
     if (tid == 0) {
         for (int s = 0; s < SK_STAGES; ++s) {
@@ -376,29 +444,58 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid
     int pf_slot = 0;
     uint32_t pf_round = 0;
     const double *pf_a = nullptr, *pf_b = nullptr, *pf_c = nullptr;
+    int64_t pf_vt = 0;
+    int pf_arows = SK_TM;
     auto pf_decode = [&]() {
         const int ct = (int)(pf_tile % prm.n_col_tiles);
-        int64_t rest = pf_tile / prm.n_col_tiles;
-        const int yt = (int)(rest % prm.n_ytiles);
-        rest /= prm.n_ytiles;
-        const int64_t slow = rest % prm.n_slow;
-        const int64_t z = rest / prm.n_slow;
+        const int64_t rest = pf_tile / prm.n_col_tiles;
+        pf_vt = rest % prm.n_vt;
+        const int64_t z = rest / prm.n_vt;
         const int comp = (int)(z % prm.ncomp);
         const int64_t b = z / prm.ncomp;
-        pf_a = prm.ttab + ((b * prm.n_ytiles + yt) * (int64_t)n_stages) * SK_A_TILE;
+        pf_a = prm.ttab + b * (int64_t)n_stages * lyt * SK_AST;
         pf_b = prm.btile + (((b * prm.ncomp + comp) * prm.n_col_tiles + ct) * (int64_t)n_stages) * SK_B_TILE;
-        if (SCALE) pf_c = reinterpret_cast<const double *>(prm.ctab + (b * prm.n_slow + slow) * prm.n_modes_pad);
+        if (SCALE) pf_c = reinterpret_cast<const double *>(prm.ctab + b * prm.n_slow * prm.n_modes_pad);
+        if (!PACK) {
+            SkTileGeo<false> geo;
+            sk_tile_geo<false>(prm, pf_vt, geo);
+            pf_a += (int64_t)geo.iy0[0] * SK_AST;
+            if (SCALE) pf_c += 2 * geo.slow[0] * prm.n_modes_pad;
+            pf_arows = PARTIAL ? geo.rows[0] : SK_TM;
+        }
         pf_send = (pf_tile == hi.tile) ? hi.stage : n_stages;
     };
     auto pf_issue = [&]() {   // one thread
         double *A = stage_base + pf_slot * SK_STAGE_DOUBLES;
-        constexpr uint32_t bytes = (SK_A_TILE + SK_B_TILE + (SCALE ? SK_C_BLOCK : 0)) * sizeof(double);
-        mbar_arrive_expect_tx(&full[pf_slot], bytes);
-        bulk_g2s(A, pf_a + (int64_t)pf_s * SK_A_TILE, SK_A_TILE * sizeof(double), &full[pf_slot]);
-        bulk_g2s(A + SK_A_TILE, pf_b + (int64_t)pf_s * SK_B_TILE, SK_B_TILE * sizeof(double), &full[pf_slot]);
-        if (SCALE)
-            bulk_g2s(A + SK_A_TILE + SK_B_TILE, pf_c + (int64_t)pf_s * SK_C_BLOCK, SK_C_BLOCK * sizeof(double),
-                     &full[pf_slot]);
+        const double *ta = pf_a + (int64_t)pf_s * lyt * SK_AST;
+        if (!PACK) {
+            const uint32_t a_bytes = (uint32_t)(pf_arows * SK_AST * sizeof(double));
+            const uint32_t bytes = a_bytes + (SK_B_TILE + (SCALE ? SK_C_BLOCK : 0)) * (uint32_t)sizeof(double);
+            mbar_arrive_expect_tx(&full[pf_slot], bytes);
+            bulk_g2s(A, ta, a_bytes, &full[pf_slot]);
+            bulk_g2s(A + SK_A_TILE, pf_b + (int64_t)pf_s * SK_B_TILE, SK_B_TILE * sizeof(double), &full[pf_slot]);
+            if (SCALE)
+                bulk_g2s(A + SK_A_TILE + SK_B_TILE, pf_c + (int64_t)pf_s * SK_C_BLOCK, SK_C_BLOCK * sizeof(double),
+                         &full[pf_slot]);
+        } else {
+            // the geometry is recomputed by the issuing lane (two integer divisions once per stage and CTA) instead of
+            // living in registers of all 256 threads across the stage loop
+            SkTileGeo<true> geo;
+            sk_tile_geo<true>(prm, pf_vt, geo);
+            const uint32_t bytes = (uint32_t)((geo.groups * 8 * SK_AST + SK_B_TILE + geo.nseg * SK_C_BLOCK) * sizeof(double));
+            mbar_arrive_expect_tx(&full[pf_slot], bytes);
+#pragma unroll
+            for (int k = 0; k < SK_MAXSEG; ++k) {
+                if (k < geo.nseg) {
+                    bulk_g2s(A + geo.row0[k] * SK_AST, ta + (int64_t)geo.iy0[k] * SK_AST,
+                             (uint32_t)(geo.rows[k] * SK_AST * sizeof(double)), &full[pf_slot]);
+                    bulk_g2s(A + SK_A_TILE + SK_B_TILE + k * SK_C_BLOCK,
+                             pf_c + 2 * geo.slow[k] * prm.n_modes_pad + (int64_t)pf_s * SK_C_BLOCK,
+                             SK_C_BLOCK * sizeof(double), &full[pf_slot]);
+                }
+            }
+            bulk_g2s(A + SK_A_TILE, pf_b + (int64_t)pf_s * SK_B_TILE, SK_B_TILE * sizeof(double), &full[pf_slot]);
+        }
     };
     auto pf_advance = [&]() {   // all threads, uniform
         if (++pf_slot == SK_STAGES) { pf_slot = 0; ++pf_round; }
@@ -427,7 +524,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid
     const int a_off0 = (8 * warp + g) * SK_AST + 2 * t;            // + q * 8   (q = quad of modes)
     const int a_off1 = (8 * (warp + 8) + g) * SK_AST + 2 * t;
     const int b_off = SK_A_TILE + t * SK_BST + g;                  // + (8q + 4 part) * SK_BST + 8 j
-    const int c_off = SK_A_TILE + SK_B_TILE + 2 * t;               // + q * 8
+    const int c_base = SK_A_TILE + SK_B_TILE + 2 * t;              // + segment * SK_C_BLOCK + q * 8
 
     int slot = 0;
     uint32_t round = 0;
@@ -436,11 +533,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid
         const int s_begin = (tile == lo.tile) ? lo.stage : 0;
         const int s_end = (tile == hi.tile) ? hi.stage : n_stages;
         const int ct = (int)(tile % prm.n_col_tiles);
-        int64_t rest = tile / prm.n_col_tiles;
-        const int yt = (int)(rest % prm.n_ytiles);
-        rest /= prm.n_ytiles;
-        const int64_t slow = rest % prm.n_slow;
-        const int64_t z = rest / prm.n_slow;
+        const int64_t rest = tile / prm.n_col_tiles;
+        const int64_t vt = rest % prm.n_vt;
+        const int64_t z = rest / prm.n_vt;
 
         double acc[2][16][2];
 #pragma unroll
@@ -451,12 +546,25 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid
         // compile-time variants of the stage: column groups rounded up to 2 (the B tile is zero beyond the mesh),
         // row groups of this warp inside the mesh; variant = 2 * (jv2 - 1) + (ni - 1), 15 = the full tile, -1 = idle
         int variant = 15;
+        int c_off0 = c_base, c_off1 = c_base;
         if (PARTIAL) {
+            SkTileGeo<PACK> geo;
+            sk_tile_geo<PACK>(prm, vt, geo);
             const int cols = (int)min((int64_t)SK_TN, prm.lc - (int64_t)ct * SK_TN);
-            const int rows = (int)min((int64_t)SK_TM, prm.ly - (int64_t)yt * SK_TM);
             const int jv2 = (cols + 15) >> 4;
-            const int ni = (8 * warp < rows ? 1 : 0) + (8 * (warp + 8) < rows ? 1 : 0);
+            const int ni = (warp < geo.groups ? 1 : 0) + (warp + 8 < geo.groups ? 1 : 0);
             variant = ni > 0 ? 2 * (jv2 - 1) + (ni - 1) : -1;
+            if (PACK) {
+                // the segment (= block of slow-axis factors) of each of the warp's row groups
+                int s0 = 0, s1 = 0;
+#pragma unroll
+                for (int k = 1; k < SK_MAXSEG; ++k) {
+                    if (k < geo.nseg && geo.row0[k] <= 8 * warp) s0 = k;
+                    if (k < geo.nseg && geo.row0[k] <= 8 * (warp + 8)) s1 = k;
+                }
+                c_off0 = c_base + s0 * SK_C_BLOCK;
+                c_off1 = c_base + s1 * SK_C_BLOCK;
+            }
         }
 
         for (int s = s_begin; s < s_end; ++s) {
@@ -472,11 +580,11 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid
             mbar_wait(&full[slot], round & 1);
             const double *S = stage_base + slot * SK_STAGE_DOUBLES;
             if (!PARTIAL || variant == 15) {
-                sk_stage<SCALE, 16, 2>(S, acc, a_off0, a_off1, b_off, c_off);
+                sk_stage<SCALE, PACK, 16, 2>(S, acc, a_off0, a_off1, b_off, c_off0, c_off1);
             } else {
-#define GSB_SK_CASE(JV)                                                                                     \
-                case 2 * (JV / 2 - 1): sk_stage<SCALE, JV, 1>(S, acc, a_off0, a_off1, b_off, c_off); break;  \
-                case 2 * (JV / 2 - 1) + 1: sk_stage<SCALE, JV, 2>(S, acc, a_off0, a_off1, b_off, c_off); break;
+#define GSB_SK_CASE(JV)                                                                                               \
+                case 2 * (JV / 2 - 1): sk_stage<SCALE, PACK, JV, 1>(S, acc, a_off0, a_off1, b_off, c_off0, c_off1); break; \
+                case 2 * (JV / 2 - 1) + 1: sk_stage<SCALE, PACK, JV, 2>(S, acc, a_off0, a_off1, b_off, c_off0, c_off1); break;
                 switch (variant) {       // warp-uniform
                     GSB_SK_CASE(2) GSB_SK_CASE(4) GSB_SK_CASE(6) GSB_SK_CASE(8)
                     GSB_SK_CASE(10) GSB_SK_CASE(12) GSB_SK_CASE(14) GSB_SK_CASE(16)
@@ -534,10 +642,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid
         double *out = prm.out + z * prm.out_fstride;
         const bool vec2 = (prm.lc & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
         const int64_t col0 = (int64_t)ct * SK_TN;
-        const int64_t iy0 = (int64_t)yt * SK_TM;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int64_t iy = iy0 + 8 * (warp + 8 * i) + g;
+            // virtual row of this thread -> (slow index, row of the tile axis)
+            const int64_t v = vt * SK_TM + 8 * (warp + 8 * i) + g;
+            if (v >= prm.vrows) continue;
+            const int64_t slow = v / prm.lyp;
+            const int64_t iy = v - slow * prm.lyp;
             if (iy >= prm.ly) continue;
             const int64_t row = ((slow / prm.n_in) * prm.ly + iy) * prm.n_in + slow % prm.n_in;
 #pragma unroll
@@ -560,22 +671,26 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_contract_kernel(const __grid
     }
 }
 
-inline int sk_launch(const SkParams &prm, int grid, bool scale, bool partial, cudaStream_t st)
+inline int sk_launch(const SkParams &prm, int grid, bool scale, bool partial, bool pack, cudaStream_t st)
 {
     static std::atomic<uint64_t> attr_set{0};
     if (first_launch_on_device(attr_set)) {
 #define GSB_SK_ATTR(K)                                                                                               \
         GSB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM_BYTES));
-        GSB_SK_ATTR((sk_contract_kernel<false, false>)) GSB_SK_ATTR((sk_contract_kernel<false, true>))
-        GSB_SK_ATTR((sk_contract_kernel<true, false>)) GSB_SK_ATTR((sk_contract_kernel<true, true>))
+        GSB_SK_ATTR((sk_contract_kernel<false, false, false>)) GSB_SK_ATTR((sk_contract_kernel<false, true, false>))
+        GSB_SK_ATTR((sk_contract_kernel<true, false, false>)) GSB_SK_ATTR((sk_contract_kernel<true, true, false>))
+        GSB_SK_ATTR((sk_contract_kernel<true, true, true>))
 #undef GSB_SK_ATTR
     }
-    if (scale) {
-        if (partial) sk_contract_kernel<true, true><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
-        else sk_contract_kernel<true, false><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
+    if (pack) {
+        if (!scale) return fail(GSB_ERR_ARGUMENT, "internal: row packing without slow axes");
+        sk_contract_kernel<true, true, true><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
+    } else if (scale) {
+        if (partial) sk_contract_kernel<true, true, false><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
+        else sk_contract_kernel<true, false, false><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
     } else {
-        if (partial) sk_contract_kernel<false, true><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
-        else sk_contract_kernel<false, false><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
+        if (partial) sk_contract_kernel<false, true, false><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
+        else sk_contract_kernel<false, false, false><<<grid, SK_THREADS, SK_SMEM_BYTES, st>>>(prm);
     }
     g_launches.fetch_add(1);
     GSB_CUDA(cudaGetLastError());

@@ -120,3 +120,59 @@ def test_sk_odd_and_thin_meshes(shape, sk, oracle_mod):
     dev = sk.summate_structured(*(torch.tensor(a, device="cuda:0") for a in (cov, z1, z2)),
                                 [torch.tensor(a, device="cuda:0") for a in axes], mat)
     assert maxabs(dev.cpu().numpy(), got) <= 1e-3 * raw_tol(130)
+
+
+PACK_CASES = [
+    (3, (5, 200, 136), 96),        # 200 rows per slow index: tiles span two slow indices
+    (3, (9, 72, 130), 64),         # 72 rows: up to three slow indices per tile
+    (3, (7, 50, 300), 40),         # 50 rows (padded to 56): four segments per tile
+    (3, (4, 300, 140), 72),
+    (3, (23, 100, 100), 130),      # the 100^3 family
+    (4, (3, 5, 100, 129), 48),     # two outer slow axes
+    (3, (33, 129, 64), 50),        # one row more than a tile
+]
+
+
+@pytest.mark.parametrize("dim,lens,n_modes", PACK_CASES)
+@pytest.mark.parametrize("grid", [0, 7])
+def test_sk_row_packing_vs_oracle(dim, lens, n_modes, grid, sk, oracle_mod):
+    """Row tiles packed across the slow indices (sk_pack = 2: whenever the layout allows it): scalar and vector
+    fields, device and host route (several pieces), batches, fused epilogue -- against the CPU oracle."""
+    import torch
+
+    cov, z1, z2 = synth_modes(dim, n_modes, seed=3 + dim)
+    rs = np.random.RandomState(11)
+    axes = [np.sort(rs.uniform(0, 150, L)) for L in lens]
+    mat = rs.normal(size=(dim, dim))
+    pos = mat @ np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+    want = oracle_mod.summate(cov, z1, z2, pos).reshape(lens)
+    sk.set_option("sk_grid", grid)
+    sk.set_option("sk_pack", 2)
+    try:
+        before = sk.get_counter("packed_calls")
+        dev = sk.summate_structured(*(torch.tensor(a, device="cuda:0") for a in (cov, z1, z2)),
+                                    [torch.tensor(a, device="cuda:0") for a in axes], mat)
+        assert sk.get_counter("packed_calls") == before + 1, "the packed kernel did not run"
+        assert maxabs(dev.cpu().numpy(), want) <= raw_tol(n_modes)
+        for pieces in (0, 5):
+            sk.set_option("host_pieces", pieces)
+            host = sk.summate_structured(cov, z1, z2, axes, mat)
+            assert maxabs(host, want) <= raw_tol(n_modes)
+        sk.set_option("host_pieces", 3)
+        if dim == 3:
+            wv = oracle_mod.summate_incompr(cov, z1, z2, pos).reshape((3,) + tuple(lens))
+            assert maxabs(sk.summate_incompr_structured(cov, z1, z2, axes, mat), wv) <= raw_tol(n_modes)
+        covb = np.stack([cov, 0.5 * cov, -cov])
+        z1b, z2b = np.stack([z1, z1, z2]), np.stack([z2, z1, z1])
+        got = sk.summate_structured(covb, z1b, z2b, axes, mat)
+        assert maxabs(got[0], want) <= raw_tol(n_modes)
+        assert maxabs(got[2], oracle_mod.summate(-cov, z2, z1, pos).reshape(lens)) <= raw_tol(n_modes)
+        fused = sk.summate_structured(cov, z1, z2, axes, mat, epilogue=(0.25, [1.0]))
+        assert maxabs(fused, 0.25 * want + 1.0) <= raw_tol(n_modes)
+        # packed against unpacked: the same sums in another tiling
+        sk.set_option("sk_pack", 1)
+        plain = sk.summate_structured(cov, z1, z2, axes, mat)
+        assert maxabs(plain, host) <= 1e-3 * raw_tol(n_modes)
+    finally:
+        sk.set_option("sk_pack", 0)
+        sk.set_option("host_pieces", 0)
