@@ -392,19 +392,30 @@ def run_b200_arm(args, cfg):
 
     # ---- --gather: the same step delivered as ONE device array on rank 0 (sum + gather) ----
     gather = None
-    if args.gather != "none" and world > 1 and structured and not batched:
+    gather_mode = args.gather
+    if gather_mode == "auto":     # default: measure the p2p gather next to the plain step, leave `value` alone
+        gather_mode = "p2p" if (world > 1 and structured and not batched) else "none"
+    if gather_mode != "none" and world > 1 and structured and not batched:
         from gstools_b200 import dist as gdist
 
         g_axes = [torch.tensor(np.ascontiguousarray(a), device=dev) for a in cfg["axes"]]
 
         def step_gather():
             return gdist.summate_structured_gathered(d_cov, d_z1, d_z2, g_axes, cfg.get("matrix"), dst=0,
-                                                     incompr=vec, mode=args.gather, pieces=args.pieces,
+                                                     incompr=vec, mode=gather_mode, pieces=args.pieces,
                                                      reserve_sms=args.reserve_sms)
 
-        for _ in range(args.warmup):
-            out = step_gather()
-            del out
+        try:
+            for _ in range(args.warmup):
+                out = step_gather()
+                del out
+        except RuntimeError as exc:       # raised on every rank together (open_peer_field): fall back, do not hang
+            if rank == 0:
+                print(f"bench.py: p2p gather unavailable ({exc}); using the NCCL gather", file=sys.stderr)
+            gather_mode = "nccl"
+            for _ in range(args.warmup):
+                out = step_gather()
+                del out
         barrier()
         gpairs = []
         for _ in range(args.steps):
@@ -422,19 +433,23 @@ def run_b200_arm(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         g_s = float(t.item())
         n_full = int(np.prod([len(a) for a in cfg["axes"]])) * (cfg["dim"] if vec else 1)
-        gather = {"mode": args.gather, "pieces": args.pieces if args.gather == "nccl" else 1,
-                  "reserve_sms": args.reserve_sms if args.gather == "nccl" else 0,
+        gather = {"mode": gather_mode, "pieces": args.pieces if gather_mode == "nccl" else 1,
+                  "reserve_sms": args.reserve_sms if gather_mode == "nccl" else 0,
                   "ms_per_step": 1e3 * g_s / args.steps, "compute_only_ms_per_step": 1e3 * dev_s / args.steps,
                   "exposed_ms": 1e3 * (g_s - dev_s) / args.steps,
                   "bytes_into_rank0_per_step": int(8 * n_full * (world - 1) / world),
                   "value_no_gather": value,
                   "what": "rank 0 ends the step holding the whole field as one CUDA tensor; "
                           + ("row pieces sent with grouped NCCL send/recv on a side stream while the next piece contracts"
-                             if args.gather == "nccl" else
+                             if gather_mode == "nccl" else
                              "every rank's contraction kernel stores its slab into rank 0's tensor over NVLink (CUDA IPC "
                              "mapping), a one-element all-reduce orders the step")}
-        value = args.steps * total_pairs / g_s
-        dev_s_for_line = g_s
+        gather["value"] = args.steps * total_pairs / g_s
+        if args.gather == "auto":
+            dev_s_for_line = dev_s            # headline stays the plain step; the gathered step is reported beside it
+        else:
+            value = gather["value"]
+            dev_s_for_line = g_s
         gdist.close_peer_fields()
     else:
         dev_s_for_line = dev_s
@@ -852,9 +867,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5cond", "krige"])
-    ap.add_argument("--gather", default="none", choices=["none", "nccl", "p2p"],
-                    help="N > 1, structured workloads: deliver the field as one device array on rank 0; `value` then "
-                         "is compute + gather")
+    ap.add_argument("--gather", default="auto", choices=["auto", "none", "nccl", "p2p"],
+                    help="N > 1, structured workloads: deliver the field as one device array on rank 0.  nccl / p2p: "
+                         "`value` is compute + gather; auto (default): `value` is the plain step and the p2p-gathered "
+                         "step is measured and reported beside it under \"gather\"; none: skip")
     ap.add_argument("--pieces", type=int, default=1, help="row pieces per rank of --gather nccl")
     ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left to NCCL while pieces travel (--gather nccl)")
     ap.add_argument("--plan", type=int, default=0, help="single-process mode: drive this many GPUs through gsb_plan")

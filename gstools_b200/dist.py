@@ -212,14 +212,26 @@ def open_peer_field(shape, dst=0, group=None, device=None):
         payload = [(bytes(handle), int(off.value))]
     if world > 1:
         dist.broadcast_object_list(payload, src=_global_rank(dst, group), group=group)
+    entry, problem = None, None
     if rank == dst:
         entry = dict(full=full, ptr=full.data_ptr(), base=None, device=dev_index)
     else:
-        raw, off = payload[0]
-        base = ctypes.c_void_p()
-        buf = (ctypes.c_ubyte * 64).from_buffer_copy(raw)
-        _lib.check(lib.gsb_ipc_open(buf, dev_index, ctypes.byref(base)), "ipc_open")
-        entry = dict(full=None, ptr=int(base.value) + off, base=int(base.value), device=dev_index)
+        try:
+            raw, off = payload[0]
+            base = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(raw)
+            _lib.check(lib.gsb_ipc_open(buf, dev_index, ctypes.byref(base)), "ipc_open")
+            entry = dict(full=None, ptr=int(base.value) + off, base=int(base.value), device=dev_index)
+        except Exception as exc:  # noqa: BLE001  (reported on EVERY rank below: nobody may run ahead into a collective)
+            problem = exc
+    if world > 1:
+        ok = torch.tensor([0.0 if problem is not None else 1.0], device=torch.device("cuda", dev_index))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if float(ok.item()) < 1.0:
+            if entry is not None and entry["base"] is not None:
+                lib.gsb_ipc_close(entry["base"], dev_index)
+            raise RuntimeError("open_peer_field: mapping the destination into every rank failed"
+                               + (f" on this rank: {problem}" if problem is not None else " on another rank"))
     _PEER[key] = entry
     return entry["full"], entry["ptr"]
 

@@ -51,12 +51,35 @@ def run(k, variant, reps=5):
             "ms": best * 1e3}
 
 
+def numa_nodes():
+    import glob
+
+    return sorted(int(p.rsplit("node", 1)[1]) for p in glob.glob("/sys/devices/system/node/node[0-9]*"))
+
+
+def interleave_policy(nodes):
+    """set_mempolicy(MPOL_INTERLEAVE) for this thread: pages of later (pinned) allocations alternate over `nodes`."""
+    import ctypes
+
+    mask = ctypes.c_ulong(sum(1 << n for n in nodes))
+    libc = ctypes.CDLL(None, use_errno=True)
+    rc = libc.syscall(238, 3, ctypes.byref(mask), ctypes.c_ulong(65))       # SYS_set_mempolicy, MPOL_INTERLEAVE
+    return rc == 0
+
+
 def main():
+    nodes = numa_nodes()
+    print(json.dumps({"numa_nodes_visible": nodes}), flush=True)
     total = torch.cuda.device_count()
     ks = [k for k in (1, 2, 4, 8) if k <= total]
     for k in ks:
         for variant in ("own_pinned", "one_pinned", "registered"):
             print(json.dumps(run(k, variant)), flush=True)
+    if len(nodes) > 1 and interleave_policy(nodes):
+        for k in ks:
+            r = run(k, "own_pinned")
+            r["variant"] = "own_pinned_numa_interleaved"
+            print(json.dumps(r), flush=True)
     # H2D for comparison
     n = MB * (1 << 20) // 8
     for k in ks:
