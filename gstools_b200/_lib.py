@@ -177,13 +177,22 @@ def set_option(name: str, value: int):
     check(load().gsb_set_option(name.encode(), int(value)), "gsb_set_option")
 
 
-def release_memory(device=None):
-    """Return the scratch memory the library keeps cached in the device's memory pool to the driver."""
+def release_memory(device=None, pinned=True):
+    """Return the scratch memory the library keeps cached in the device's memory pool to the driver and
+    (``pinned=True``) the page-locked host blocks of result arrays that have been freed: they otherwise stay
+    in torch's pinned-memory cache for reuse by the next call (result arrays still alive stay pinned)."""
     if device is None:
         from . import backend
 
         device = backend.get_device()
     check(load().gsb_release_memory(int(device)), "gsb_release_memory")
+    if pinned:
+        try:
+            import torch
+
+            torch._C._host_emptyCache()
+        except Exception:  # noqa: BLE001  (older torch: nothing to trim)
+            pass
 
 
 def get_counter(name: str) -> int:
