@@ -44,6 +44,7 @@ __all__ = [
     "cond_scaling",
     "to_device",
     "to_host",
+    "to_host_async",
     "set_device",
     "get_device",
     "Plan",
@@ -150,6 +151,29 @@ def to_host(t):
     if out.size:
         torch.from_numpy(out).copy_(t)
     return out
+
+
+_COPY_STREAMS = {}
+
+
+def to_host_async(t):
+    """Start copying CUDA tensor ``t`` into a fresh (pinned) host array on a side stream and return
+    ``(array, event)``: the array holds the data once ``event.synchronize()`` has returned.  Lets a D2H copy travel
+    while the host does something else (the plugin overlaps the krige-side results of a conditioned realisation with
+    the sampling of its mode set)."""
+    torch = _torch()
+    out = _empty_host(tuple(t.shape))
+    key = t.device.index
+    side = _COPY_STREAMS.get(key)
+    if side is None:
+        side = _COPY_STREAMS[key] = torch.cuda.Stream(device=t.device)
+    side.wait_stream(torch.cuda.current_stream(t.device))
+    event = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        if out.size:
+            torch.from_numpy(out).copy_(t, non_blocking=True)
+        event.record(side)
+    return out, event
 
 
 def _as_f64(a, name):

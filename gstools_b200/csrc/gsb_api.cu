@@ -210,7 +210,7 @@ static int pack_modes(const double *d_cov, const double *d_z1, const double *d_z
 static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const double *d_pos,
                             int64_t pos_ld, int dim, bool vec, int64_t n_pts, double *d_out,
                             int64_t out_ld, const Epi &epi, const DeviceState &dev, Scratch &scr,
-                            cudaStream_t st)
+                            cudaStream_t st, bool allow_tail_split = true)
 {
     if (n_pts == 0) return GSB_OK;
     // Launch configuration by a small cost model: time ~ waves x points per SM and wave / relative speed.  The
@@ -218,23 +218,51 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
     // quantises into waves of 2 x 1024 points per SM; mid-sized point sets are better off with smaller CTAs.
     // (A point's bits do not depend on the configuration: the per-point instruction sequence is the same.)
     const int64_t want = 2LL * dev.sm_count;
-    int cfg = 0;
-    {
-        static const double speed[3] = {0.756, 0.906, 1.00};   // tools/direct_size_sweep.py
-        static const int resident[3] = {8, 4, 2};
+    static const double speed[3] = {0.756, 0.906, 1.00};   // tools/direct_size_sweep.py
+    static const int resident[3] = {8, 4, 2};
+    auto model_time = [&](int c, int64_t n) -> double {
+        const int64_t ppc = direct_cfg_points(c, dim);
+        const int64_t nc = (n + ppc - 1) / ppc;
+        const int64_t slots = (int64_t)resident[c] * dev.sm_count;
+        return (double)((nc + slots - 1) / slots) * (double)(resident[c] * ppc) / speed[c];
+    };
+    auto best_cfg = [&](int64_t n, double *t_out) -> int {
         double best = 1e300;
+        int cfg = 0;
         for (int c = 0; c < 3; ++c) {
-            const int64_t ppc = direct_cfg_points(c, dim);
-            const int64_t nc = (n_pts + ppc - 1) / ppc;
-            const int64_t slots = (int64_t)resident[c] * dev.sm_count;
-            const double t = (double)((nc + slots - 1) / slots) * (double)(resident[c] * ppc) / speed[c];
+            const double t = model_time(c, n);
             if (t < best * 0.999) {
                 best = t;
                 cfg = c;
             }
         }
-    }
+        if (t_out) *t_out = best;
+        return cfg;
+    };
+    double t_single = 0.0;
+    int cfg = best_cfg(n_pts, &t_single);
     if (g_opt_direct_cfg.load() >= 0) cfg = (int)g_opt_direct_cfg.load();
+    // Tail split: a point set of 8.25 waves of the big configuration would run 9 (2.5 M points per rank of config 3
+    // on eight GPUs: 92 % of the time useful).  The full waves keep that configuration; the remaining quarter wave goes
+    // to a second launch whose smaller CTAs spread it over all SMs.  Same bits: the per-point sequence does not change.
+    if (allow_tail_split && g_opt_direct_cfg.load() < 0) {
+        const int64_t ppc = direct_cfg_points(cfg, dim);
+        const int64_t wave_pts = (int64_t)resident[cfg] * dev.sm_count * ppc;
+        const int64_t n_main = n_pts / wave_pts * wave_pts;
+        if (n_main > 0 && n_main < n_pts) {
+            double t_tail = 0.0;
+            best_cfg(n_pts - n_main, &t_tail);
+            const double t_split = model_time(cfg, n_main) + t_tail + 0.02 * model_time(cfg, wave_pts);   // + one launch
+            if (t_split < 0.98 * t_single) {
+                GSB_TRY(direct_on_device(d_recs, n_modes_pad, d_pos, pos_ld, dim, vec, n_main, d_out, out_ld, epi, dev, scr,
+                                         st, false));
+                GSB_TRY(direct_on_device(d_recs, n_modes_pad, d_pos + n_main, pos_ld, dim, vec, n_pts - n_main,
+                                         d_out + n_main, out_ld, epi_shift(epi, n_main), dev, scr, st, false));
+                g_cnt_direct.fetch_sub(1);      // one call, two launches
+                return GSB_OK;
+            }
+        }
+    }
     const int64_t ctas = (n_pts + direct_cfg_points(cfg, dim) - 1) / direct_cfg_points(cfg, dim);
     const int n_tiles = (int)((n_modes_pad + DIRECT_TM - 1) / DIRECT_TM);
     int n_split = 1;

@@ -611,17 +611,16 @@ def _build_cond_call(r):
         terms = _post_terms(self, post_process)
         if spec is None or terms is None:
             return fallback()
-        # update the model/seed in the generator if any changes were made   (cond_srf.py:116)
-        self.generator.update(model, seed)
-        generator = self.generator
-        if generator.zero_var:
-            return orig_cond_call(self, pos, np.nan, mesh_type, post_process, store, krige_store, **kwargs)
         iso_pos, shape, info = self.pre_pos(pos, mesh_type, info=True)                 # cond_srf.py:118
         entry = ke.evaluate(krige, spec, kwargs.get("ext_drift"), True, want_device=True)
         dev = entry["dev"]
-        # what self.krige(**kwargs) and the two krige-side post_field calls leave behind (cond_srf.py:133-141)
+        # what self.krige(**kwargs) and the two krige-side post_field calls leave behind (cond_srf.py:133-141):
+        # fresh host copies of the kriging variance and the (post-processed) kriging field on every call.  They are
+        # device-resident constants of the system, so their copies START here and travel while the host samples the
+        # mode set below (2 of the 4 ms of a realisation); they are stored once the field is done.
+        pending = []
         if krige_save[1]:
-            krige.post_field(backend.to_host(dev["krige_var"]), krige_name[1], False, True)
+            pending.append((backend.to_host_async(dev["krige_var"]), krige_name[1]))
         if krige_save[0]:
             # the post-processed kriging field is a pure function of the constants in `terms`: the reference's
             # arithmetic runs once (field/base.py:325-336), the result stays on the device next to the raw one
@@ -629,7 +628,12 @@ def _build_cond_call(r):
             if dev.get("pp_key") != pkey:
                 done = krige.post_field(backend.to_host(dev["field"]), krige_name[0], post_process, False)
                 dev["pp_field"], dev["pp_key"] = backend.to_device(done), pkey
-            krige.post_field(backend.to_host(dev["pp_field"]), krige_name[0], False, True)
+            pending.append((backend.to_host_async(dev["pp_field"]), krige_name[0]))
+        # update the model/seed in the generator if any changes were made   (cond_srf.py:116)
+        self.generator.update(model, seed)
+        generator = self.generator
+        if generator.zero_var:
+            return orig_cond_call(self, None, np.nan, self.mesh_type, post_process, store, krige_store, **kwargs)
         # sqrt(var/N) * summed + 0.0 (generator.py:269-270, add_nugget=False); var_scale * rawfield;
         # rawkrige + ...; + nugget (int 0); then post_field's constant mean and trend
         epi = backend.make_epilogue(np.sqrt(model.var / generator._mode_no), [0.0])
@@ -641,6 +645,9 @@ def _build_cond_call(r):
         else:
             field = backend.summate(generator._cov_sample, generator._z_1, generator._z_2,
                                     np.asarray(iso_pos, dtype=np.double), epilogue=epi, point_epilogue=pepi)
+        for (host, event), kname in pending:
+            event.synchronize()
+            krige.post_field(host, kname, False, True)
         return self.post_field(np.reshape(field, shape), name[0], False, save[0])        # cond_srf.py:145-150
 
     return _like(cond_call, orig_cond_call)

@@ -536,3 +536,32 @@ def test_badly_filled_tiles_go_to_the_direct_kernel(gsb, oracle_mod):
     assert gsb.get_counter("direct_calls") == before[0] + 1 and gsb.get_counter("separable_calls") == before[1]
     grid = np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
     assert maxabs(got.reshape(-1), oracle_mod.summate(cov, z1, z2, grid)) <= raw_tol(64)
+
+
+def test_direct_tail_split_keeps_the_bits(gsb, oracle_mod):
+    """A point set of a few full waves plus a fraction runs as two launches (full waves in the big-CTA configuration,
+    the tail in smaller CTAs): same bits as a forced single configuration, one direct call counted."""
+    import torch
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n = 2 * sms * 2 * 1024 + 70001           # two waves of the 8-points-per-thread configuration (2-D) and a bit
+    cov, z1, z2 = synth_modes(2, 40, seed=2)
+    pos = np.random.RandomState(0).uniform(0, 100, (2, n))
+    before = gsb.get_counter("direct_calls"), gsb.get_counter("launches")
+    got = gsb.summate(cov, z1, z2, torch.tensor(pos, device="cuda:0")).cpu().numpy()
+    assert gsb.get_counter("direct_calls") == before[0] + 1
+    assert gsb.get_counter("launches") == before[1] + 3          # mode records + two direct launches
+    gsb.set_option("direct_cfg", 2)
+    try:
+        one = gsb.summate(cov, z1, z2, torch.tensor(pos, device="cuda:0")).cpu().numpy()
+    finally:
+        gsb.set_option("direct_cfg", -1)
+    assert np.array_equal(got, one)
+    idx = np.r_[0:1000, n - 1000:n]
+    assert np.max(np.abs(got[idx] - oracle_mod.summate(cov, z1, z2, pos[:, idx]))) <= 1e-9 * np.sqrt(40)
+    # per-point epilogue arrays follow the tail
+    gain = torch.rand(n, device="cuda:0", dtype=torch.float64)
+    pe = gsb.make_point_epilogue(gain, None, [0.5])
+    fused = gsb.summate(cov, z1, z2, torch.tensor(pos, device="cuda:0"), epilogue=gsb.make_epilogue(2.0, []),
+                        point_epilogue=pe).cpu().numpy()
+    assert np.array_equal(fused, gain.cpu().numpy() * (2.0 * got) + 0.5)

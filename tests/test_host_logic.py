@@ -238,6 +238,12 @@ def _fake_backend(monkeypatch, oracle_mod, calls):
 
     monkeypatch.setattr(backend, "to_device", to_device)
     monkeypatch.setattr(backend, "to_host", lambda t: t.numpy().copy())
+
+    class Done:
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(backend, "to_host_async", lambda t: (t.numpy().copy(), Done()))
     monkeypatch.setattr(backend, "cond_scaling", cond_scaling)
     monkeypatch.setattr(backend, "make_point_epilogue", lambda gain=None, offset=None, adds=(): (gain, offset, list(adds)))
 
