@@ -860,13 +860,98 @@ def run_c5cond_arm(args, edge=128, n_cond=1000):
     gsb.disable()
 
 
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json configs[4] as ONE call: gstools_b200.ensemble(cond_srf, 256 seeds) (--workload c5ens)
+# ----------------------------------------------------------------------------------------------
+def run_c5ens_arm(args, edge=128, n_cond=1000, n_seeds=256):
+    """A "step" is the WHOLE ensemble: 256 seeds from MasterRNG(20170519) -> 256 conditioned 128^3 fields as one host
+    array, through ``gstools_b200.ensemble(gs.CondSRF(krige), seeds)``: mode sets of all seeds drawn natively on the
+    host cores, one batched summation with the kriging results fused into the stores (``--plan G``: seeds dealt out to
+    G GPUs from this one process), 4.3 GB copied to the host.  Host in, host out: value == e2e."""
+    import torch
+
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import refharness
+
+    if not refharness.have_reference():
+        raise SystemExit("bench.py --workload c5ens needs the reference gstools (baseline/_ref)")
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    gs = refharness.import_gstools()
+    import gstools_b200 as gsb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 backend has no CPU fallback)")
+    gsb.set_device(0)
+    gsb.enable()
+    n_gpus = 1
+    if args.plan > 1:
+        gsb.use_devices(list(range(args.plan)), min_pairs=0)
+        n_gpus = args.plan
+    rs = np.random.RandomState(20170519)
+    cond_pos = rs.uniform(0, edge - 1, (3, n_cond))
+    cond_val = rs.normal(size=n_cond)
+    model = gs.Exponential(dim=3, var=1, len_scale=10)
+    krige = gs.krige.Ordinary(model, cond_pos, cond_val)
+    crf = gs.CondSRF(krige)
+    axes = [np.arange(float(edge))] * 3
+    crf.set_pos(axes, "structured")
+    master = gs.random.MasterRNG(20170519)
+    seeds = [master() for _ in range(n_seeds)]
+    n_modes = 1000
+    t0 = time.perf_counter()
+    out = gsb.ensemble(crf, seeds[:8])            # evaluates the kriging system, warms pools
+    t_first = time.perf_counter() - t0
+    del out
+    for _ in range(max(1, args.warmup - 2)):
+        out = gsb.ensemble(crf, seeds)
+        del out
+    t0 = time.perf_counter()
+    gsb.sample_modes_batch("Exponential", 3, model.len_rescaled, 0.0, seeds, n_modes)
+    t_modes = time.perf_counter() - t0
+    launches0 = gsb.get_counter("launches")
+    steps = max(1, min(args.steps, 5))
+    with ClockSampler(0) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = gsb.ensemble(crf, seeds)
+            nbytes = out.nbytes
+            del out
+        torch.cuda.synchronize()
+        total = time.perf_counter() - t0
+    launches = gsb.get_counter("launches") - launches0
+    pairs = n_seeds * edge ** 3 * n_modes
+    value = steps * pairs / total
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": max(1, args.warmup - 2),
+        "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5 as ONE call: gstools_b200.ensemble(gs.CondSRF(Ordinary kriging on {n_cond} points, "
+                               f"Exponential 3D), {n_seeds} seeds from MasterRNG(20170519)) on the {edge}^3 mesh, mode_no={n_modes}",
+                   "baseline_config": "C5", "path": "native batch sampler -> batched stream-K contraction with the per-point epilogue",
+                   "mode_no": n_modes, "dim": 3, "step": f"the whole ensemble of {n_seeds} realisations, seeds in -> host array out",
+                   "sharding": ("one GPU" if n_gpus == 1 else f"ONE process, seeds dealt out to {n_gpus} GPUs (gsb_plan)"),
+                   "l2": "4.3 GB of output per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(8 * 5 * n_modes * n_seeds),
+                "d2h_bytes_per_step": int(nbytes), "ms_per_step": 1e3 * total / steps,
+                "api": "gstools_b200.ensemble(gs.CondSRF(krige), seeds) -> numpy (pinned)"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "breakdown_ms": {"first_call_8_seeds_incl_kriging_evaluation": 1e3 * t_first,
+                         "mode_sets_of_all_seeds_native_batch": 1e3 * t_modes, "host_threads": host_threads()},
+        "roofline": None, "wall_s_timed_region": total,
+    }
+    print(json.dumps(line), flush=True)
+    gsb.use_devices(None)
+    gsb.disable()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5cond", "krige"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5cond", "c5ens", "krige"])
     ap.add_argument("--gather", default="auto", choices=["auto", "none", "nccl", "p2p"],
                     help="N > 1, structured workloads: deliver the field as one device array on rank 0.  nccl / p2p: "
                          "`value` is compute + gather; auto (default): `value` is the plain step and the p2p-gathered "
@@ -884,6 +969,10 @@ def main():
         if args.impl == "reference":
             return run_reference_arm(args, make_workload("c5"))
         return run_c5cond_arm(args)
+    if args.workload == "c5ens":
+        if args.impl == "reference":
+            return run_reference_arm(args, make_workload("c5"))
+        return run_c5ens_arm(args)
     cfg = make_workload(args.workload)
     if args.impl == "reference":
         run_reference_arm(args, cfg)

@@ -21,6 +21,7 @@ from .backend import (
     cov_model_spec,
     krige_evaluate,
     sample_radii_mcmc,
+    sample_modes_batch,
     get_device,
     cond_scaling,
     make_epilogue,
@@ -37,7 +38,7 @@ from .backend import (
     use_devices,
     current_plan,
 )
-from .plugin import disable, enable, is_enabled, prewarm, unfused_methods
+from .plugin import disable, enable, ensemble, is_enabled, prewarm, unfused_methods
 
 __version__ = "0.1.0"
 
@@ -53,6 +54,7 @@ __all__ = [
     "krige_evaluate",
     "cov_model_spec",
     "sample_radii_mcmc",
+    "sample_modes_batch",
     "scale_shift_",
     "make_epilogue",
     "make_point_epilogue",
@@ -61,6 +63,7 @@ __all__ = [
     "disable",
     "is_enabled",
     "prewarm",
+    "ensemble",
     "unfused_methods",
     "set_device",
     "get_device",

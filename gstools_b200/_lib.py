@@ -98,6 +98,8 @@ SIGNATURES = {
     "gsb_sample_radii_mcmc": (_int, [_int, _int, ctypes.c_double, ctypes.c_double, _vp, _int, _vp, _int, _vp,
                                      _int, _int, _int, _vp]),
     "gsb_sample_radii_mcmc_cb": (_int, [_vp, _vp, _vp, _int, _vp, _int, _vp, _int, _int, _int, _vp]),
+    "gsb_sample_modes_batch": (_int, [_int, _int, ctypes.c_double, ctypes.c_double, _vp, _i64, _i64, _int, _int, _i64,
+                                      ctypes.c_double, ctypes.c_double, _int, _vp, _vp, _vp, _vp, _vp]),
     "gsb_scale_shift": (_int, [_vp, _i64, ctypes.c_double, ctypes.c_double, _int, _vp]),
     "gsb_plan_create": (_int, [ctypes.POINTER(_int), _int, ctypes.POINTER(_vp)]),
     "gsb_plan_destroy": (_int, [_vp]),

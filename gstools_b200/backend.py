@@ -38,6 +38,7 @@ __all__ = [
     "krige_evaluate",
     "cov_model_spec",
     "sample_radii_mcmc",
+    "sample_modes_batch",
     "scale_shift_",
     "make_epilogue",
     "make_point_epilogue",
@@ -1064,6 +1065,45 @@ def sample_radii_mcmc(kind, dim, len_rescaled, nu, burn_state, main_state, init,
                                    _ptr(x0), x0.shape[0], int(burn_in), int(n_steps), _ptr(chain))
     _lib.check(rc, "sample_radii_mcmc")
     return chain
+
+
+def sample_modes_batch(kind, dim, len_rescaled, nu, seeds, mode_no, nwalkers=50, burn_in=20, oversampling_factor=10,
+                       num_threads=None):
+    """Mode sets ``(cov_samples (S, dim, N), z_1 (S, N), z_2 (S, N))`` of ``RandMeth(model, mode_no=N, seed=s)`` for every
+    seed ``s`` of ``seeds``, bit for bit what ``RandMeth.reset_seed`` (generator.py:346-387) draws one seed at a time --
+    for models whose radii come from ``RNG.sample_ln_pdf`` and have a native log-pdf (``kind`` in ``_lib.PDF_KINDS``).
+    The random streams (normal, uniform, the emcee chain, choice) run natively, one seed per task on ``num_threads``
+    host threads (default: all cores); the sphere coordinates are finished with numpy on the whole batch."""
+    if kind not in _lib.PDF_KINDS:
+        raise ValueError(f"no native log-pdf for model '{kind}': {sorted(_lib.PDF_KINDS)}")
+    if dim not in (1, 2, 3):
+        raise ValueError("sample_sphere supports dim 1, 2 and 3 natively")
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64).reshape(-1)
+    n_seeds, n = seeds.shape[0], int(mode_no)
+    sample_size = int(max(burn_in, (n / nwalkers) * oversampling_factor))          # rng.py:78-83
+    if num_threads is None:
+        try:
+            num_threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            num_threads = os.cpu_count() or 1
+    z1, z2, ang1, rad = (np.empty((n_seeds, n)) for _ in range(4))
+    ang2 = np.empty((n_seeds, n)) if dim == 3 else None
+    rc = _lib.load().gsb_sample_modes_batch(_lib.PDF_KINDS[kind], int(dim), float(len_rescaled), float(nu), _ptr(seeds),
+                                            n_seeds, n, int(nwalkers), int(burn_in), sample_size,
+                                            1.0 / float(len_rescaled), 2 * np.pi, int(num_threads), _ptr(z1), _ptr(z2),
+                                            _ptr(ang1), _ptr(ang2) if ang2 is not None else None, _ptr(rad))
+    _lib.check(rc, "sample_modes_batch")
+    coord = np.empty((n_seeds, dim, n))
+    if dim == 1:                                                                     # rng.py:163-174
+        coord[:, 0] = ang1
+    elif dim == 2:
+        coord[:, 0] = np.cos(ang1)
+        coord[:, 1] = np.sin(ang1)
+    else:
+        coord[:, 0] = np.sqrt(1.0 - ang2**2) * np.cos(ang1)
+        coord[:, 1] = np.sqrt(1.0 - ang2**2) * np.sin(ang1)
+        coord[:, 2] = ang2
+    return rad[:, None, :] * coord, z1, z2                                           # generator.py:387
 
 
 def scale_shift_(field, scale, shift=0.0):

@@ -1832,7 +1832,7 @@ int gsb_sample_radii_mcmc(int pdf_kind, int dim, double len_rescaled, double nu,
         return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: unknown pdf kind");
     if (dim < 1 || !(len_rescaled > 0.0) || (pdf_kind == GSB_PDF_MATERN && !(nu > 0.0)))
         return fail(GSB_ERR_ARGUMENT, "sample_radii_mcmc: bad model parameters");
-    const RadPdf pdf{pdf_kind, dim, len_rescaled, nu};
+    const RadPdf pdf(pdf_kind, dim, len_rescaled, nu);
     auto eval = [&pdf](const double *q, int n, double *out) -> int {
         for (int k = 0; k < n; ++k) out[k] = pdf.ln_pdf(q[k]);
         return 0;
@@ -1849,6 +1849,45 @@ int gsb_sample_radii_mcmc_cb(gsb_ln_pdf_fn ln_pdf, void *user, const uint32_t *m
     auto eval = [ln_pdf, user](const double *q, int n, double *out) -> int { return ln_pdf(q, n, out, user); };
     return sample_radii_impl(eval, mt_key_burn, mt_pos_burn, mt_key_main, mt_pos_main, init, nwalkers, burn_in, n_steps,
                              chain);
+}
+
+int gsb_sample_modes_batch(int pdf_kind, int dim, double len_rescaled, double nu, const int64_t *seeds, int64_t n_seeds,
+                           int64_t mode_no, int nwalkers, int burn_in, int64_t n_steps, double sample_around,
+                           double two_pi, int n_threads, double *z_1, double *z_2, double *ang_1, double *ang_2,
+                           double *rad)
+{
+    if (pdf_kind != GSB_PDF_EXPONENTIAL && pdf_kind != GSB_PDF_MATERN && pdf_kind != GSB_PDF_GAUSSIAN)
+        return fail(GSB_ERR_ARGUMENT, "sample_modes_batch: unknown pdf kind");
+    if (dim < 1 || dim > 3 || !(len_rescaled > 0.0) || (pdf_kind == GSB_PDF_MATERN && !(nu > 0.0)))
+        return fail(GSB_ERR_ARGUMENT, "sample_modes_batch: bad model parameters (dim must be 1, 2 or 3)");
+    if (n_seeds < 0 || mode_no < 1 || nwalkers < 2 || (nwalkers & 1) || burn_in < 0 || n_steps < 1 ||
+        n_steps * (int64_t)nwalkers > (int64_t)0x7fffffff)
+        return fail(GSB_ERR_ARGUMENT, "sample_modes_batch: bad sizes");
+    if (n_seeds > 0 && (!seeds || !z_1 || !z_2 || !ang_1 || !rad || (dim == 3 && !ang_2)))
+        return fail(GSB_ERR_ARGUMENT, "sample_modes_batch: NULL pointer");
+    for (int64_t i = 0; i < n_seeds; ++i)
+        if (seeds[i] < 0 || seeds[i] > (int64_t)0xffffffffLL)
+            return fail(GSB_ERR_ARGUMENT, "sample_modes_batch: seeds must fit 32 bits (numpy legacy seeding)");
+    ModeBatchArgs a{RadPdf(pdf_kind, dim, len_rescaled, nu), dim, mode_no, nwalkers, burn_in, n_steps, sample_around, two_pi};
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_threads > 0 ? n_threads : 1, n_seeds), 256));
+    std::atomic<int64_t> next{0};
+    std::atomic<int> bad{0};
+    auto work = [&]() {
+        std::vector<double> chain;
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n_seeds) break;
+            if (sample_modes_one(a, (uint32_t)seeds[i], z_1 + i * mode_no, z_2 + i * mode_no, ang_1 + i * mode_no,
+                                 dim == 3 ? ang_2 + i * mode_no : nullptr, rad + i * mode_no, chain))
+                bad.store(1);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto &th : pool) th.join();
+    if (bad.load()) return fail(GSB_ERR_ARGUMENT, "sample_modes_batch: proposal or log-pdf not finite");
+    return GSB_OK;
 }
 
 int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int device, void *stream)

@@ -65,6 +65,15 @@ struct Mt19937 {
         const int32_t a = (int32_t)(next32() >> 5), b = (int32_t)(next32() >> 6);
         return (a * 67108864.0 + b) / 9007199254740992.0;
     }
+    // numpy.random.RandomState(seed) for an integer seed: init_genrand (legacy seeding), position at the end
+    void seed(uint32_t s)
+    {
+        for (int i = 0; i < 624; ++i) {
+            key[i] = s;
+            s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+        }
+        pos = 624;
+    }
     // uniform integer in [0, max] by masked rejection (numpy random_interval / bounded_masked_uint32)
     uint32_t bounded(uint32_t max)
     {
@@ -97,6 +106,27 @@ struct RadPdf {
     int kind;   // GSB_PDF_EXPONENTIAL / GSB_PDF_MATERN / GSB_PDF_GAUSSIAN
     int dim;
     double len_rescaled, nu;
+    // factors of the densities that do not depend on k: the SAME sub-expressions the per-call formulas evaluate,
+    // computed once (bit-identical results; pow / tgamma / lgamma were 80 % of a chain's time)
+    double c_fac = 0.0, c_exp = 0.0, c_lg1 = 0.0, c_lg2 = 0.0, c_lg3 = 0.0, c_rad = 0.0;
+
+    RadPdf(int kind_, int dim_, double len_, double nu_) : kind(kind_), dim(dim_), len_rescaled(len_), nu(nu_)
+    {
+        const double l = len_rescaled;
+        if (kind == GSB_PDF_GAUSSIAN) {
+            c_fac = std::pow(l / 2.0 / std::sqrt(M_PI), dim);
+        } else if (kind == GSB_PDF_EXPONENTIAL) {
+            c_fac = std::pow(l, dim) * std::tgamma((dim + 1) / 2.0);
+            c_exp = (dim + 1) / 2.0;
+        } else {
+            c_fac = std::pow(l / std::sqrt(M_PI), dim);
+            c_exp = -(nu + dim / 2.0);
+            c_lg1 = std::lgamma(nu + dim / 2.0);
+            c_lg2 = std::lgamma(nu);
+            c_lg3 = dim * std::log(std::sqrt(nu));
+        }
+        if (dim > 3) c_rad = std::pow(std::sqrt(M_PI), dim) / std::tgamma(dim / 2.0 + 1);
+    }
 
     double rad_fac(double r) const   // covmodel/tools.py:118-140
     {
@@ -110,18 +140,14 @@ struct RadPdf {
         const double l = len_rescaled;
         if (kind == GSB_PDF_GAUSSIAN) {    // models.py:147-151
             const double h = k * l / 2.0;
-            return std::pow(l / 2.0 / std::sqrt(M_PI), dim) * std::exp(-(h * h));
+            return c_fac * std::exp(-(h * h));
         }
         if (kind == GSB_PDF_EXPONENTIAL)   // models.py:217-224
-            return std::pow(l, dim) * std::tgamma((dim + 1) / 2.0) /
-                   np_pow(M_PI * (1.0 + (k * l) * (k * l)), (dim + 1) / 2.0);
+            return c_fac / np_pow(M_PI * (1.0 + (k * l) * (k * l)), c_exp);
         const double x = (k * l) * (k * l);   // Matern, models.py:434-449
         if (nu > 20.0)
-            return std::pow(l / std::sqrt(M_PI), dim) * std::exp(-x) * (1 + 0.5 * (x * x) / nu) *
-                   std::pow(std::sqrt(1 + x / nu), -dim);
-        return std::pow(l / std::sqrt(M_PI), dim) *
-               std::exp(-(nu + dim / 2.0) * std::log(1.0 + x / nu) + std::lgamma(nu + dim / 2.0) - std::lgamma(nu) -
-                        dim * std::log(std::sqrt(nu)));
+            return c_fac * std::exp(-x) * (1 + 0.5 * (x * x) / nu) * std::pow(std::sqrt(1 + x / nu), -dim);
+        return c_fac * std::exp(c_exp * std::log(1.0 + x / nu) + c_lg1 - c_lg2 - c_lg3);
     }
     // np.log(spectral_rad_pdf(model, r)), covmodel/tools.py:374-406 and covmodel/base.py:557-560
     double ln_pdf(double r) const
@@ -194,6 +220,101 @@ static inline int stretch_run(Eval &&eval, Mt19937 &rng, int nwalkers, int nstep
         if (chain)
             for (int i = 0; i < nwalkers; ++i) chain[(size_t)step * nwalkers + i] = coords[i];
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mode sets of MANY seeds at once (ensembles): the random streams of RandMeth.reset_seed
+// (src/gstools/field/generator.py:346-387) restated natively, one seed per task, tasks spread over host threads.
+//   RNG(seed)             -> MasterRNG(seed): RandomState(seed).randint(1, 2**16) per access of RNG.random
+//                            (random/tools.py:30-35, random/rng.py:193-203)
+//   z_1, z_2              -> RandomState(s).normal(size=N): numpy's legacy polar Box-Muller with its cached second value
+//   sample_sphere         -> uniform(0, 2 pi, N) [and uniform(-1, 1, N) in 3-D] (rng.py:163-174); the trigonometry
+//                            stays in numpy (its SIMD cos / sin are not libm's) and runs on the whole batch at once
+//   sample_ln_pdf         -> rand(nwalkers), two generator states, the stretch-move chain above, choice(chain, N)
+// Outputs per seed: z1[N], z2[N], ang1[N], ang2[N] (3-D only), rad[N].
+// ---------------------------------------------------------------------------------------------
+struct LegacyGauss {     // numpy legacy_gauss
+    Mt19937 &rng;
+    bool has = false;
+    double stored = 0.0;
+    explicit LegacyGauss(Mt19937 &r) : rng(r) {}
+    double next()
+    {
+        if (has) {
+            has = false;
+            return stored;
+        }
+        double x1, x2, r2;
+        do {
+            x1 = 2.0 * rng.next_double() - 1.0;
+            x2 = 2.0 * rng.next_double() - 1.0;
+            r2 = x1 * x1 + x2 * x2;
+        } while (r2 >= 1.0 || r2 == 0.0);
+        const double f = std::sqrt(-2.0 * std::log(r2) / r2);
+        stored = f * x1;
+        has = true;
+        return f * x2;
+    }
+};
+
+struct ModeBatchArgs {
+    RadPdf pdf;
+    int dim;
+    int64_t mode_no;
+    int nwalkers, burn_in;
+    int64_t n_steps;
+    double sample_around, two_pi;
+};
+
+// one seed; returns 0, or 1 when the chain hit a non-finite proposal / log-pdf
+static inline int sample_modes_one(const ModeBatchArgs &a, uint32_t seed, double *z1, double *z2, double *ang1,
+                                   double *ang2, double *rad, std::vector<double> &chain)
+{
+    Mt19937 master, rs;
+    master.seed(seed);
+    auto next_stream = [&]() { rs.seed(1u + master.bounded(65534u)); };     // RandomState(randint(1, 2**16))
+    const int64_t N = a.mode_no;
+    next_stream();
+    {
+        LegacyGauss g(rs);
+        for (int64_t k = 0; k < N; ++k) z1[k] = g.next();
+    }
+    next_stream();
+    {
+        LegacyGauss g(rs);
+        for (int64_t k = 0; k < N; ++k) z2[k] = g.next();
+    }
+    if (a.dim == 1) {            // choice([-1, 1], size): randint(0, 2)
+        next_stream();
+        for (int64_t k = 0; k < N; ++k) ang1[k] = rs.bounded(1u) ? 1.0 : -1.0;
+    } else {
+        next_stream();
+        for (int64_t k = 0; k < N; ++k) ang1[k] = 0.0 + a.two_pi * rs.next_double();
+        if (a.dim == 3) {
+            next_stream();
+            for (int64_t k = 0; k < N; ++k) ang2[k] = -1.0 + 2.0 * rs.next_double();
+        }
+    }
+    // RNG.sample_ln_pdf (rng.py:72-104)
+    std::vector<double> coords((size_t)a.nwalkers), logp((size_t)a.nwalkers);
+    next_stream();
+    for (int i = 0; i < a.nwalkers; ++i) coords[(size_t)i] = rs.next_double() * a.sample_around;
+    auto eval = [&](const double *q, int n, double *out) -> int {
+        for (int k = 0; k < n; ++k) out[k] = a.pdf.ln_pdf(q[k]);
+        return 0;
+    };
+    eval(coords.data(), a.nwalkers, logp.data());
+    for (int i = 0; i < a.nwalkers; ++i)
+        if (!std::isfinite(coords[(size_t)i]) || std::isnan(logp[(size_t)i])) return 1;
+    chain.resize((size_t)a.n_steps * a.nwalkers);
+    next_stream();
+    if (stretch_run(eval, rs, a.nwalkers, a.burn_in, coords.data(), logp.data(), nullptr)) return 1;
+    next_stream();
+    if (stretch_run(eval, rs, a.nwalkers, (int)a.n_steps, coords.data(), logp.data(), chain.data())) return 1;
+    next_stream();
+    const uint32_t pop = (uint32_t)chain.size();
+    for (int64_t k = 0; k < N; ++k) rad[k] = chain[rs.bounded(pop - 1u)];       // choice(samples, size): randint(0, pop)
     return 0;
 }
 

@@ -51,7 +51,7 @@ import numpy as np
 
 from . import _lib, backend
 
-__all__ = ["enable", "disable", "is_enabled", "LazyGridPos", "prewarm", "unfused_methods", "source_fingerprint",
+__all__ = ["enable", "disable", "is_enabled", "LazyGridPos", "prewarm", "ensemble", "unfused_methods", "source_fingerprint",
            "KNOWN_SOURCES"]
 
 _STATE = {"enabled": False}
@@ -306,35 +306,53 @@ def _build_pre_pos(r):
     return _like(pre_pos, orig_pre_pos)
 
 
+def _srf_epilogue(r, srf, post_process):
+    """gsb_epilogue equal to everything SRF.__call__ does after the summation, or None."""
+    gen = r.gen
+    generator = srf.generator
+    model = srf.model
+    if type(generator) not in (gen.RandMeth, gen.IncomprRandMeth) or model.nugget > 0:
+        return None
+    vec = type(generator) is gen.IncomprRandMeth
+    if vec and model.dim not in (2, 3):
+        return None
+    root = np.sqrt(model.var / generator._mode_no)
+    if vec:  # mean_u*e1 + mean_u*sqrt(var/N)*summed + nugget     (generator.py:561-567)
+        e1 = [generator.mean_u * 1.0] + [generator.mean_u * 0.0] * (model.dim - 1)
+        scale, adds = generator.mean_u * root, [tuple(e1), 0.0]
+    else:    # sqrt(var/N)*summed + nugget                         (generator.py:269-270)
+        scale, adds = root, [0.0]
+    if post_process:  # field += mean; denormalize; field += trend  (normalizer/tools.py:99-103)
+        if type(srf.normalizer) is not r.Normalizer:
+            return None
+        for value in (srf.mean, srf.trend):
+            term = _const_term(value, srf.value_type, model.dim)
+            if term is None:
+                return None
+            adds.append(term)
+    return backend.make_epilogue(scale, adds)
+
+
+def _cond_post_terms(r, field, post_process):
+    """Constant [mean, trend] that post_field adds to a conditioned field (normalizer/tools.py:99-103), [] without
+    post-processing, or None when it is not a constant affine map."""
+    if not post_process:
+        return []
+    if type(field.normalizer) is not r.Normalizer:
+        return None
+    terms = []
+    for value in (field.mean, field.trend):
+        term = _const_term(value, "scalar", field.model.dim)
+        if term is None or isinstance(term, tuple):
+            return None
+        terms.append(term)
+    return terms
+
+
 # ---- SRF.__call__ with the caller epilogue fused into the kernels (row f2) --------------------------
 def _build_srf_call(r):
     gen = r.gen
     orig_srf_call = r.orig[(r.fsrf.SRF, "__call__")]
-
-    def _fused_epilogue(srf, post_process):
-        """gsb_epilogue equal to everything SRF.__call__ does after the summation, or None."""
-        generator = srf.generator
-        model = srf.model
-        if type(generator) not in (gen.RandMeth, gen.IncomprRandMeth) or model.nugget > 0:
-            return None
-        vec = type(generator) is gen.IncomprRandMeth
-        if vec and model.dim not in (2, 3):
-            return None
-        root = np.sqrt(model.var / generator._mode_no)
-        if vec:  # mean_u*e1 + mean_u*sqrt(var/N)*summed + nugget     (generator.py:561-567)
-            e1 = [generator.mean_u * 1.0] + [generator.mean_u * 0.0] * (model.dim - 1)
-            scale, adds = generator.mean_u * root, [tuple(e1), 0.0]
-        else:    # sqrt(var/N)*summed + nugget                         (generator.py:269-270)
-            scale, adds = root, [0.0]
-        if post_process:  # field += mean; denormalize; field += trend  (normalizer/tools.py:99-103)
-            if type(srf.normalizer) is not r.Normalizer:
-                return None
-            for value in (srf.mean, srf.trend):
-                term = _const_term(value, srf.value_type, model.dim)
-                if term is None:
-                    return None
-                adds.append(term)
-        return backend.make_epilogue(scale, adds)
 
     def srf_call(self, pos=None, seed=np.nan, point_volumes=0.0, mesh_type="unstructured",
                  post_process=True, store=True):
@@ -345,7 +363,7 @@ def _build_srf_call(r):
         # update the model/seed in the generator if any changes were made   (srf.py:152)
         self.generator.update(self.model, seed)
         generator = self.generator
-        epi = None if generator.zero_var else _fused_epilogue(self, post_process)
+        epi = None if generator.zero_var else _srf_epilogue(r, self, post_process)
         if epi is None:  # seed already applied: keep it
             return orig_srf_call(self, pos, np.nan, point_volumes, mesh_type, post_process, store)
         iso_pos, shape = self.pre_pos(pos, mesh_type)
@@ -575,21 +593,6 @@ def _build_cond_call(r):
     ke = r.krige_eval
     allowed_kwargs = {"ext_drift", "chunk_size", "only_mean", "return_var", "post_process", "store"}
 
-    def _post_terms(self, post_process):
-        """Constant [mean, trend] that post_field adds (normalizer/tools.py:99-103), [] without
-        post-processing, or None when it is not a constant affine map."""
-        if not post_process:
-            return []
-        if type(self.normalizer) is not r.Normalizer:
-            return None
-        terms = []
-        for value in (self.mean, self.trend):
-            term = _const_term(value, "scalar", self.model.dim)
-            if term is None or isinstance(term, tuple):
-                return None
-            terms.append(term)
-        return terms
-
     def cond_call(self, pos=None, seed=np.nan, mesh_type="unstructured", post_process=True, store=True,
                   krige_store=True, **kwargs):
         def fallback():
@@ -608,7 +611,7 @@ def _build_cond_call(r):
         if save[1] or save[2] or name[2] in self.field_names:
             return fallback()
         spec = ke.cov_spec(krige)
-        terms = _post_terms(self, post_process)
+        terms = _cond_post_terms(r, self, post_process)
         if spec is None or terms is None:
             return fallback()
         iso_pos, shape, info = self.pre_pos(pos, mesh_type, info=True)                 # cond_srf.py:118
@@ -730,13 +733,21 @@ def _build_sample_ln_pdf(r):
             verdicts[kind] = ok
         return verdicts[kind]
 
-    def sample_ln_pdf(self, ln_pdf, size=None, sample_around=1.0, nwalkers=50, burn_in=20,
-                      oversampling_factor=10):
+    def native_kind(ln_pdf):
+        """Name of the native closed-form log-pdf that equals the bound method ``ln_pdf``, or None."""
         model = getattr(ln_pdf, "__self__", None)
         kind = pdf_models.get(type(model))
         closed_form = (kind is not None and getattr(ln_pdf, "__func__", None) is base_ln_pdf
                        and type(model).spectral_density is getattr(cmodels, kind).spectral_density)
-        if not closed_form:
+        return kind if closed_form else None
+
+    r.native_pdf_kind, r.sampler_ok = native_kind, _stream_compatible
+
+    def sample_ln_pdf(self, ln_pdf, size=None, sample_around=1.0, nwalkers=50, burn_in=20,
+                      oversampling_factor=10):
+        model = getattr(ln_pdf, "__self__", None)
+        kind = native_kind(ln_pdf)
+        if kind is None:
             kind = "callback"        # any other model / density: native stretch move around the caller's log-pdf
         native = (r.on() and callable(ln_pdf) and nwalkers >= 2 and nwalkers % 2 == 0
                   and _stream_compatible(kind, ln_pdf))
@@ -808,6 +819,89 @@ def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True,
     if devices is not None:
         backend.use_devices(devices)
     return r.gstools
+
+
+# ---- ensembles: many seeds, one batched launch (per GPU) --------------------------------------------
+def ensemble(field, seeds, pos=None, mesh_type="unstructured", post_process=True, num_threads=None):
+    """All realisations of an ensemble at once: ``np.stack([field(pos, seed=s, mesh_type=..., store=False) for s in
+    seeds])`` for a ``gs.SRF`` or ``gs.CondSRF`` driven by ``RandMeth`` -- the reference's ensemble idiom
+    (examples/06_conditioned_fields/01_2D_condition_ensemble.py:32-35; README.md:255-257 draws the seeds from a
+    ``MasterRNG``) without the serial Python loop.  Not part of the reference's API; every field has the values the
+    loop would give (same tolerance class as the single calls; conditioned fields: the kriging system is evaluated once).
+
+    * the mode sets of all seeds are drawn by ``gsb_sample_modes_batch`` on all host cores when the model's radii come
+      from ``RNG.sample_ln_pdf`` with a native log-pdf (Exponential, Matern, Gaussian in 3-D; checked against the
+      reference's own ``RandMeth`` for the first seed on every call), else seed by seed through the generator;
+    * ONE batched summation (``n_batch = len(seeds)``) with the caller epilogue -- for ``CondSRF`` the per-point
+      ``rawkrige + var_scale * rawfield`` -- fused into the stores; with ``use_devices`` / ``enable(devices=...)`` the
+      seeds are dealt out to the GPUs of the plan;
+    * nothing is stored on ``field`` and its generator keeps its current seed.
+
+    Falls back to the loop itself whenever the call is not a constant-epilogue structured / flat RandMeth call.
+    """
+    r = _STATE.get("refs")
+    seeds = [int(s) for s in seeds]
+
+    def loop():
+        return np.stack([np.array(field(pos, seed=s, mesh_type=mesh_type, post_process=post_process, store=False))
+                         for s in seeds]) if seeds else np.empty((0,))
+
+    if r is None or not r.on() or not seeds:
+        return loop()
+    gen = r.gen
+    generator = getattr(field, "_generator", None)
+    cond = type(field) is r.cond_cls
+    if type(generator) is not gen.RandMeth or not (cond or type(field) is r.fsrf.SRF) or generator.zero_var:
+        return loop()
+    model = field.model
+    if model.nugget > 0 or not model.var > 0 or model.latlon:
+        return loop()
+    epi = _srf_epilogue(r, field, post_process and not cond)
+    if epi is None:
+        return loop()
+    iso_pos, shape = field.pre_pos(pos, mesh_type)
+    lazy = _lookup_lazy(iso_pos)
+    if lazy is None:
+        return loop()          # flat point sets have no batched entry: the loop already runs on the GPU
+    # ---- mode sets ----
+    n_modes = generator._mode_no
+    ln_pdf = model.ln_spectral_rad_pdf
+    kind = r.native_pdf_kind(ln_pdf) if hasattr(r, "native_pdf_kind") else None
+    inversion = generator.sampling == "inversion" or (generator.sampling == "auto" and model.has_ppf)
+    batch = None
+    if (kind is not None and not inversion and model.dim in (1, 2, 3) and all(0 <= s < 2**32 for s in seeds)
+            and r.sampler_ok(kind, ln_pdf)):
+        batch = backend.sample_modes_batch(kind, model.dim, model.len_rescaled, getattr(model, "nu", 0.0), seeds,
+                                           n_modes, num_threads=num_threads)
+        probe = gen.RandMeth(model, mode_no=n_modes, seed=seeds[0], sampling=generator.sampling)
+        if not (np.array_equal(probe._cov_sample, batch[0][0]) and np.array_equal(probe._z_1, batch[1][0])
+                and np.array_equal(probe._z_2, batch[2][0])):
+            warnings.warn("gstools_b200.ensemble: the native batch sampler does not reproduce RandMeth on this "
+                          "numpy; sampling seed by seed", RuntimeWarning, stacklevel=2)
+            batch = None
+    if batch is None:
+        covs, z1s, z2s = [], [], []
+        for s in seeds:
+            rm = gen.RandMeth(model, mode_no=n_modes, seed=s, sampling=generator.sampling)
+            covs.append(rm._cov_sample), z1s.append(rm._z_1), z2s.append(rm._z_2)
+        batch = (np.stack(covs), np.stack(z1s), np.stack(z2s))
+    # ---- epilogues ----
+    pepi = None
+    if cond:
+        krige = field.krige
+        spec = r.krige_eval.cov_spec(krige)
+        terms = _cond_post_terms(r, field, post_process)
+        if spec is None or terms is None or krige.cond_no == 0:
+            return loop()
+        entry = r.krige_eval.evaluate(krige, spec, None, True, want_device=True)
+        dev = entry["dev"]
+        plan = backend.current_plan()
+        if plan is not None and len(seeds) >= len(plan):
+            pepi = plan.make_point_epilogue(dev["gain"], dev["field"], [0.0] + terms)
+        else:
+            pepi = backend.make_point_epilogue(dev["gain"], dev["field"], [0.0] + terms)
+    out = backend.summate_structured(batch[0], batch[1], batch[2], lazy[0], lazy[1], epilogue=epi, point_epilogue=pepi)
+    return out.reshape((len(seeds),) + tuple(shape))
 
 
 def unfused_methods():

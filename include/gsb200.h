@@ -317,6 +317,24 @@ int gsb_sample_radii_mcmc_cb(gsb_ln_pdf_fn ln_pdf, void *user, const uint32_t *m
                              int burn_in, int n_steps, double *chain);
 
 /*
+ * gsb_sample_modes_batch -- the random streams of RandMeth.reset_seed (src/gstools/field/generator.py:346-387) for
+ * MANY seeds at once, one seed per task on `n_threads` host threads: an ensemble's per-seed set-up
+ * (examples/06_conditioned_fields/01_2D_condition_ensemble.py:32-35 draws one seed per realisation) stops being a
+ * serial Python loop.  Per seed s, bit for bit what the reference draws for RandMeth(model, mode_no, seed=s) with a
+ * model that has no inverse CDF (sampling through RNG.sample_ln_pdf) and a native log-pdf (pdf_kind):
+ *   z_1, z_2 (mode_no,)  RandomState.normal                          generator.py:362-363
+ *   ang_1, ang_2         uniform(0, two_pi) and, in 3-D, uniform(-1, 1) of RNG.sample_sphere (random/rng.py:163-174;
+ *                        dim 1: the +-1 of choice([-1, 1])).  The caller finishes the sphere coordinates with numpy's
+ *                        cos / sin / sqrt on the whole batch (numpy's SIMD trigonometry is not libm's).
+ *   rad                  RNG.sample_ln_pdf(size=mode_no, sample_around)  random/rng.py:38-104
+ * Outputs are (n_seeds, mode_no) row-major; seeds must fit 32 bits (numpy legacy seeding).  Host only.
+ */
+int gsb_sample_modes_batch(int pdf_kind, int dim, double len_rescaled, double nu, const int64_t *seeds,
+                           int64_t n_seeds, int64_t mode_no, int nwalkers, int burn_in, int64_t n_steps,
+                           double sample_around, double two_pi, int n_threads, double *z_1, double *z_2,
+                           double *ang_1, double *ang_2, double *rad);
+
+/*
  * Fused caller epilogue (reference: src/gstools/field/generator.py:269-270):
  *   field[i] = scale * field[i] + shift     in place, device pointers only.
  * Lets a device-resident caller keep the field on the GPU.

@@ -194,3 +194,35 @@ def test_cond_srf_ensemble_timing_and_state(gsb):
         assert np.max(np.abs(f2 - f0)) <= 1e-12 and "raw_field" in crf.field_names
     finally:
         gsb.disable()
+
+
+def test_ensemble_call_equals_the_loop_through_the_plugin(gsb):
+    """gstools_b200.ensemble(cond_srf, seeds): one batched launch, every realisation equal (up to the rounding of
+    another tiling) to the single CondSRF calls through the plugin; the native batch sampler draws the mode sets."""
+    import refharness
+
+    if not refharness.have_reference():
+        pytest.skip("reference gstools not present")
+    gs = refharness.import_gstools()
+    gsb.enable()
+    try:
+        rs = np.random.RandomState(4)
+        model = gs.Exponential(dim=3, var=1.3, len_scale=6.0)
+        krige = gs.krige.Ordinary(model, rs.uniform(0, 30, (3, 40)), rs.normal(size=40))
+        crf = gs.CondSRF(krige, mode_no=200)
+        crf.mean = 0.5
+        axes = [np.arange(33.0), np.arange(40.0), np.arange(136.0)]
+        master = gs.random.MasterRNG(20170519)
+        seeds = [master() for _ in range(7)]
+        want = np.stack([np.array(crf(axes, seed=s, mesh_type="structured", store=False)) for s in seeds])
+        before = gsb.get_counter("sk_calls"), gsb.get_counter("krige_calls")
+        got = gsb.ensemble(crf, seeds, axes, mesh_type="structured")
+        assert gsb.get_counter("sk_calls") == before[0] + 1 and gsb.get_counter("krige_calls") == before[1]
+        assert got.shape == (7, 33, 40, 136)
+        assert np.max(np.abs(got - want)) <= 1e-9 * np.sqrt(1.3)
+        # plain SRF ensembles take the same route
+        srf = gs.SRF(model, mean=-1.0, mode_no=200)
+        want = np.stack([np.array(srf(axes, seed=s, mesh_type="structured", store=False)) for s in seeds])
+        assert np.max(np.abs(gsb.ensemble(srf, seeds, axes, mesh_type="structured") - want)) <= 1e-9 * np.sqrt(1.3)
+    finally:
+        gsb.disable()

@@ -220,6 +220,10 @@ def _fake_backend(monkeypatch, oracle_mod, calls):
         return finish(oracle_mod.summate_incompr(cov, z1, z2, pos), epilogue, True)
 
     def summate_structured(cov, z1, z2, axes, matrix=None, *, epilogue=None, point_epilogue=None):
+        if np.ndim(cov) == 3:      # batched mode sets (ensembles): one field per entry
+            calls.append(("struct_batch", len(cov)))
+            return np.stack([summate_structured(c, a, b, axes, matrix, epilogue=epilogue, point_epilogue=point_epilogue)
+                             for c, a, b in zip(cov, z1, z2)])
         calls.append(("struct", epilogue is not None) + (("pp",) if point_epilogue is not None else ()))
         shape = tuple(len(a) for a in axes)
         out = finish(oracle_mod.summate(cov, z1, z2, grid(axes, matrix)), epilogue, False).reshape(shape)
@@ -666,6 +670,59 @@ def test_log_pdf_errors_surface_from_the_callback(gsb):
         backend.sample_radii_mcmc(lambda r: np.full(len(r), np.nan), 0, 0.0, 0.0, st, st, init, 2, 3)
     chain = backend.sample_radii_mcmc(lambda r: -0.5 * np.asarray(r)[:, 0] ** 2, 0, 0.0, 0.0, st, st, init, 2, 5)
     assert chain.shape == (5, 6) and np.all(np.isfinite(chain))
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["srf_native", "srf_ppf", "cond"])
+def test_ensemble_equals_the_loop(gsb, oracle_mod, monkeypatch, kind):
+    """gstools_b200.ensemble(field, seeds): every realisation has the bits of the reference's own loop
+    field(seed=s) (the CPU stand-ins of the kernels are exact restatements, so equality is bit for bit here); the mode
+    sets of all seeds come from the native batch sampler where the model allows it."""
+    gs = refharness.import_gstools()
+    from gstools_b200 import backend
+
+    calls = []
+    _fake_backend(monkeypatch, oracle_mod, calls)
+
+    def fake_krige(spec, mat, cond, cpos, pos=None, axes=None, matrix=None, unbiased=True, tail_rows=None,
+                   return_var=True):
+        import torch
+
+        g = np.array(np.meshgrid(*[a.numpy() for a in axes], indexing="ij")).reshape(len(axes), -1)
+        g = g if matrix is None else np.dot(matrix, g)
+        f, e = oracle_mod.krige_evaluate(dict(kind="Exponential", var=spec.var, len_rescaled=spec.len_rescaled,
+                                              sill=spec.sill), mat.numpy(), cond.numpy(), cpos.numpy(), g, unbiased, None)
+        return torch.from_numpy(f), torch.from_numpy(e)
+
+    monkeypatch.setattr(backend, "krige_evaluate", fake_krige)
+    axes = [np.linspace(0, 9, 7), np.linspace(0, 5, 6), np.arange(4.0)]
+    seeds = [20170519, 3, 99]
+    batch_calls = []
+    real_batch = backend.sample_modes_batch
+    monkeypatch.setattr(backend, "sample_modes_batch", lambda *a, **k: (batch_calls.append(a[0]), real_batch(*a, **k))[1])
+    if kind == "cond":
+        model = gs.Exponential(dim=3, var=1.5, len_scale=3.0)
+        rs = np.random.RandomState(1)
+        krige = gs.krige.Ordinary(model, rs.uniform(0, 5, (3, 9)), rs.normal(size=9))
+        field = gs.CondSRF(krige, generator="RandMeth", mode_no=32)
+        field.mean = 0.25
+    elif kind == "srf_native":
+        field = gs.SRF(gs.Matern(dim=3, var=2.0, len_scale=3.0, nu=1.5), mean=1.0, mode_no=32)
+    else:
+        field = gs.SRF(gs.Gaussian(dim=2, var=2.0, len_scale=3.0), mode_no=32)
+        axes = axes[:2]
+    want = np.stack([np.array(field(axes, seed=s, mesh_type="structured", store=False)) for s in seeds])
+    gsb.enable()
+    try:
+        seed_before = field.generator.seed
+        got = gsb.ensemble(field, seeds, axes, mesh_type="structured")
+        assert field.generator.seed == seed_before and field.field_names == []
+    finally:
+        gsb.disable()
+    assert got.shape == (3,) + tuple(len(a) for a in axes)
+    assert ("struct_batch", 3) in calls
+    assert batch_calls == ([] if kind == "srf_ppf" else [type(field.model).__name__])
+    assert np.array_equal(got, want)
 
 
 @needs_ref
