@@ -176,3 +176,32 @@ def test_sk_row_packing_vs_oracle(dim, lens, n_modes, grid, sk, oracle_mod):
     finally:
         sk.set_option("sk_pack", 0)
         sk.set_option("host_pieces", 0)
+
+
+def test_sk_row_packing_with_inner_slow_axis(sk, oracle_mod):
+    """Tile axis = axis 0 (100 rows), the 7 entries of axis 1 are an INNER slow axis: packed tiles span slow indices whose
+    rows interleave in the output (row = iy * n_in + inner).  A small table cap rules the folded layout out."""
+    import torch
+
+    lens, n_modes = (100, 7, 140), 64
+    cov, z1, z2 = synth_modes(3, n_modes, seed=12)
+    rs = np.random.RandomState(3)
+    axes = [np.sort(rs.uniform(0, 90, L)) for L in lens]
+    mat = rs.normal(size=(3, 3))
+    pos = mat @ np.stack([g.reshape(-1) for g in np.meshgrid(*axes, indexing="ij")])
+    want = oracle_mod.summate(cov, z1, z2, pos).reshape(lens)
+    sk.set_option("sk_pack", 2)
+    sk.set_option("sk_table_mb", 1)
+    try:
+        before = sk.get_counter("packed_calls")
+        dev = sk.summate_structured(*(torch.tensor(a, device="cuda:0") for a in (cov, z1, z2)),
+                                    [torch.tensor(a, device="cuda:0") for a in axes], mat)
+        assert sk.get_counter("packed_calls") == before + 1
+        assert maxabs(dev.cpu().numpy(), want) <= raw_tol(n_modes)
+        sk.set_option("host_pieces", 3)
+        host = sk.summate_incompr_structured(cov, z1, z2, axes, mat)
+        wv = oracle_mod.summate_incompr(cov, z1, z2, pos).reshape((3,) + lens)
+        assert maxabs(host, wv) <= raw_tol(n_modes)
+    finally:
+        sk.set_option("sk_pack", 0)
+        sk.set_option("host_pieces", 0)

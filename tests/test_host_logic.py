@@ -673,6 +673,42 @@ def test_log_pdf_errors_surface_from_the_callback(gsb):
 
 
 @needs_ref
+@pytest.mark.parametrize("make,kind", [
+    (lambda gs: gs.Exponential(dim=3, var=1.0, len_scale=10.0), "Exponential"),
+    (lambda gs: gs.Matern(dim=2, var=2.0, len_scale=7.0, nu=1.5), "Matern"),
+    (lambda gs: gs.Matern(dim=3, var=2.0, len_scale=7.0, nu=30.0), "Matern"),
+    (lambda gs: gs.Matern(dim=1, var=2.0, len_scale=7.0, nu=0.7), "Matern"),
+    (lambda gs: gs.Gaussian(dim=3, var=1.0, len_scale=4.0, anis=[0.5, 0.25], angles=[0.3, 0.1, 0.2]), "Gaussian"),
+], ids=["Exponential3d", "Matern2d", "Matern3d-nu30", "Matern1d", "Gaussian3d-anis"])
+def test_batch_sampler_reproduces_randmeth_for_every_seed(gsb, make, kind):
+    """gsb_sample_modes_batch restates the random streams of RandMeth.reset_seed (generator.py:346-387: MasterRNG
+    seeding, RandomState.normal / uniform / rand / choice, the emcee chain) natively, many seeds on several threads:
+    cov_samples, z_1 and z_2 of every seed are the reference's, bit for bit -- also for the seeds a MasterRNG deals."""
+    gs = refharness.import_gstools()
+    from gstools.field.generator import RandMeth
+
+    model = make(gs)
+    master = gs.random.MasterRNG(20170519)
+    seeds = [20170519, 1, 65535, 4294967295] + [master() for _ in range(4)]
+    n_modes = 257
+    cov, z1, z2 = gsb.sample_modes_batch(kind, model.dim, model.len_rescaled, getattr(model, "nu", 0.0), seeds, n_modes,
+                                         num_threads=3)
+    assert cov.shape == (len(seeds), model.dim, n_modes) and z1.shape == z2.shape == (len(seeds), n_modes)
+    for i, seed in enumerate(seeds):
+        ref = RandMeth(make(gs), mode_no=n_modes, seed=seed)
+        assert np.array_equal(ref._z_1, z1[i]) and np.array_equal(ref._z_2, z2[i]), seed
+        assert np.array_equal(ref._cov_sample, cov[i]), seed
+    # thread count does not matter; bad input is refused
+    again = gsb.sample_modes_batch(kind, model.dim, model.len_rescaled, getattr(model, "nu", 0.0), seeds, n_modes,
+                                   num_threads=1)
+    assert all(np.array_equal(a, b) for a, b in zip(again, (cov, z1, z2)))
+    with pytest.raises(ValueError):
+        gsb.sample_modes_batch(kind, model.dim, model.len_rescaled, 1.0, [-1], n_modes)
+    with pytest.raises(ValueError):
+        gsb.sample_modes_batch("Spherical", 3, 1.0, 0.0, [1], n_modes)
+
+
+@needs_ref
 @pytest.mark.parametrize("kind", ["srf_native", "srf_ppf", "cond"])
 def test_ensemble_equals_the_loop(gsb, oracle_mod, monkeypatch, kind):
     """gstools_b200.ensemble(field, seeds): every realisation has the bits of the reference's own loop
