@@ -51,6 +51,49 @@ def run(k, variant, reps=5):
             "ms": best * 1e3}
 
 
+def run_write_combined(k, reps=5):
+    """Destination allocated with cudaHostAllocWriteCombined: the CPU caches do not have to be snooped for the
+    incoming writes (reading such memory from the CPU is slow -- a probe of what limits the host, not a product option)."""
+    import ctypes
+
+    rt = None
+    for name in ("libcudart.so.12", "libcudart.so"):
+        try:
+            rt = ctypes.CDLL(name)
+            break
+        except OSError:
+            continue
+    if rt is None:
+        return None
+    n_bytes = MB * (1 << 20)
+    devs = [torch.device("cuda", i) for i in range(k)]
+    src = [torch.ones(n_bytes // 8, dtype=torch.float64, device=d) for d in devs]
+    streams = [torch.cuda.Stream(device=d) for d in devs]
+    dst = []
+    for _ in devs:
+        p = ctypes.c_void_p()
+        if rt.cudaHostAlloc(ctypes.byref(p), ctypes.c_size_t(n_bytes), ctypes.c_uint(0x04 | 0x01)) != 0:   # WC | portable
+            return None
+        dst.append(p)
+    best = 1e9
+    for _ in range(reps):
+        for d in devs:
+            torch.cuda.synchronize(d)
+        t0 = time.perf_counter()
+        for i in range(k):
+            torch.cuda.set_device(devs[i])
+            rt.cudaMemcpyAsync(dst[i], ctypes.c_void_p(src[i].data_ptr()), ctypes.c_size_t(n_bytes), ctypes.c_int(2),
+                               ctypes.c_void_p(streams[i].cuda_stream))
+        for d in devs:
+            torch.cuda.synchronize(d)
+        best = min(best, time.perf_counter() - t0)
+    for p in dst:
+        rt.cudaFreeHost(p)
+    gb = n_bytes / 1e9
+    return {"gpus": k, "variant": "write_combined_pinned", "gbs_aggregate": k * gb / best, "gbs_per_gpu": gb / best,
+            "ms": best * 1e3}
+
+
 def numa_nodes():
     import glob
 
@@ -75,6 +118,13 @@ def main():
     for k in ks:
         for variant in ("own_pinned", "one_pinned", "registered"):
             print(json.dumps(run(k, variant)), flush=True)
+    for k in ks:
+        try:
+            r = run_write_combined(k)
+        except Exception as exc:  # noqa: BLE001
+            r = {"gpus": k, "variant": "write_combined_pinned", "error": str(exc)}
+        if r is not None:
+            print(json.dumps(r), flush=True)
     if len(nodes) > 1 and interleave_policy(nodes):
         for k in ks:
             r = run(k, "own_pinned")
