@@ -151,7 +151,8 @@ class _Refs:
             (kbase, "_calc_field_krige"), (kbase, "_calc_field_krige_and_variance"),
             (fbase.Field, "pre_pos"), (fsrf.SRF, "__call__"), (kbase.Krige, "__call__"),
             (fbase, "apply_mean_norm_trend"), (grng.RNG, "sample_ln_pdf"),
-            (gen.RandMeth, "__call__"), (gen.IncomprRandMeth, "__call__"), (fcond.CondSRF, "__call__"))}
+            (gen.RandMeth, "__call__"), (gen.IncomprRandMeth, "__call__"), (fcond.CondSRF, "__call__"),
+            (gen.RandMeth, "reset_seed"))}
         self.cache_krige = True
         self.cache_krige_mb = 2048
         self.fused_cond = True
@@ -185,6 +186,9 @@ KNOWN_SOURCES = {
     "RNG.sample_ln_pdf": {"d7e2ea3b1a27327b"},             # src/gstools/random/rng.py:38-104
     "CondSRF.get_scaling": {"21606b5f2cae2334"},           # src/gstools/field/cond_srf.py:152-178 (gsb_cond_scaling)
     "Krige._get_krige_vecs": {"ffaa6a1d9a32909e"},         # src/gstools/krige/base.py:359-388 (kvgen_kernel)
+    "RandMeth.reset_seed": {"c2f45a9a1d2cda64"},           # src/gstools/field/generator.py:346-387 (gsb_sample_modes_batch)
+    "RNG.sample_sphere": {"55aecf1402204775"},             # src/gstools/random/rng.py:142-191
+    "MasterRNG.__init__": {"4e5e0ccef60dfeeb"},            # src/gstools/random/tools.py:30-33
 }
 
 
@@ -758,6 +762,70 @@ def _build_sample_ln_pdf(r):
     return _like(sample_ln_pdf, orig)
 
 
+# ---- RandMeth.reset_seed through the native batch sampler (row f4, the whole mode set of a seed) ----
+def _build_reset_seed(r):
+    """generator.py:346-387 for models whose radii come from RNG.sample_ln_pdf with a native log-pdf: z_1, z_2, the
+    sphere angles and the radii of the seed are drawn by gsb_sample_modes_batch (bit for bit the reference's streams),
+    the trigonometry of sample_sphere and `rad * sph_crd` stay numpy's.  2.0 ms -> 0.6 ms per seed: the rest of the
+    reference's path was eight fresh RandomState objects and their state copies.  The first use of a (model class, dim)
+    runs the reference's own reset_seed beside it and keeps the reference's path on any difference."""
+    gen = r.gen
+    orig = r.orig[(gen.RandMeth, "reset_seed")]
+    verdicts = {}
+
+    def native_modes(self, kind, seed):
+        model = self.model
+        cov, z1, z2 = backend.sample_modes_batch(kind, model.dim, model.len_rescaled, getattr(model, "nu", 0.0),
+                                                 [seed], self._mode_no, num_threads=1)
+        rng = r.grng.RNG(seed)
+        # RNG.random was read once per stream: z_1, z_2, the sphere angles (2 in 3-D), and four times in
+        # sample_ln_pdf -- later users of self._rng (nugget draws) continue the master generator from there
+        for _ in range(7 + (1 if model.dim == 3 else 0)):
+            rng._master_rng()
+        return rng, z1[0], z2[0], cov[0]
+
+    def reset_seed(self, seed=np.nan):
+        model = getattr(self, "model", None)
+        new_seed = self._seed if (seed is not None and np.isnan(seed)) else seed
+        kind = None
+        if (r.on() and model is not None and type(self).reset_seed is reset_seed and not self.zero_var
+                and model.dim in (1, 2, 3) and isinstance(new_seed, (int, np.integer)) and 0 <= new_seed < 2**32
+                and not (self.sampling == "inversion" or (self.sampling == "auto" and model.has_ppf))
+                and hasattr(r, "native_pdf_kind")):
+            ln_pdf = model.ln_spectral_rad_pdf
+            kind = r.native_pdf_kind(ln_pdf)
+            if kind is not None and not r.sampler_ok(kind, ln_pdf):
+                kind = None
+        if kind is None:
+            return orig(self, seed)
+        key = (kind, model.dim)
+        if key not in verdicts:
+            orig(self, seed)                             # the reference's own result stays in place
+            try:
+                rng, z1, z2, cov = native_modes(self, kind, int(new_seed))
+                same = (np.array_equal(z1, self._z_1) and np.array_equal(z2, self._z_2)
+                        and np.array_equal(cov, self._cov_sample))
+                if same:                                 # and the master generators continue alike
+                    probe = r.grng.RNG(int(new_seed))
+                    for _ in range(7 + (1 if model.dim == 3 else 0)):
+                        probe._master_rng()
+                    same = probe._master_rng() == rng._master_rng()
+            except Exception:  # noqa: BLE001
+                same = False
+            if not same:
+                warnings.warn(f"gstools_b200: the native mode sampler does not reproduce RandMeth.reset_seed for {key}; "
+                              "keeping the reference's sampler", RuntimeWarning, stacklevel=2)
+            verdicts[key] = same
+            return None
+        if not verdicts[key]:
+            return orig(self, seed)
+        self._seed = new_seed
+        self._rng, self._z_1, self._z_2, self._cov_sample = native_modes(self, kind, int(new_seed))
+        return None
+
+    return _like(reset_seed, orig)
+
+
 def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True, devices=None):
     """Route an unmodified ``gstools`` to the B200 backend (see the module docstring).
 
@@ -788,6 +856,10 @@ def enable(lazy_grid: bool = True, fused: bool = True, cache_krige: bool = True,
 
         if known("RNG.sample_ln_pdf", r.grng.RNG, "sample_ln_pdf"):
             patches[(r.grng.RNG, "sample_ln_pdf")] = _build_sample_ln_pdf(r)
+            if fused and known("RandMeth.reset_seed", r.gen.RandMeth, "reset_seed") \
+                    and _known("RNG.sample_sphere", r.grng.RNG.sample_sphere, unknown) \
+                    and _known("MasterRNG.__init__", r.gstools.random.MasterRNG.__init__, unknown):
+                patches[(r.gen.RandMeth, "reset_seed")] = _build_reset_seed(r)
         if lazy_grid and known("Field.pre_pos", r.fbase.Field, "pre_pos"):
             patches[(r.fbase.Field, "pre_pos")] = _build_pre_pos(r)
         if fused:
@@ -830,8 +902,8 @@ def ensemble(field, seeds, pos=None, mesh_type="unstructured", post_process=True
     loop would give (same tolerance class as the single calls; conditioned fields: the kriging system is evaluated once).
 
     * the mode sets of all seeds are drawn by ``gsb_sample_modes_batch`` on all host cores when the model's radii come
-      from ``RNG.sample_ln_pdf`` with a native log-pdf (Exponential, Matern, Gaussian in 3-D; checked against the
-      reference's own ``RandMeth`` for the first seed on every call), else seed by seed through the generator;
+      from ``RNG.sample_ln_pdf`` with a native log-pdf (Exponential, Matern, Gaussian in 3-D; checked once per model
+      class against the reference's own ``RandMeth.reset_seed``), else seed by seed through the generator;
     * ONE batched summation (``n_batch = len(seeds)``) with the caller epilogue -- for ``CondSRF`` the per-point
       ``rawkrige + var_scale * rawfield`` -- fused into the stores; with ``use_devices`` / ``enable(devices=...)`` the
       seeds are dealt out to the GPUs of the plan;
@@ -873,11 +945,18 @@ def ensemble(field, seeds, pos=None, mesh_type="unstructured", post_process=True
             and r.sampler_ok(kind, ln_pdf)):
         batch = backend.sample_modes_batch(kind, model.dim, model.len_rescaled, getattr(model, "nu", 0.0), seeds,
                                            n_modes, num_threads=num_threads)
-        probe = gen.RandMeth(model, mode_no=n_modes, seed=seeds[0], sampling=generator.sampling)
-        if not (np.array_equal(probe._cov_sample, batch[0][0]) and np.array_equal(probe._z_1, batch[1][0])
-                and np.array_equal(probe._z_2, batch[2][0])):
-            warnings.warn("gstools_b200.ensemble: the native batch sampler does not reproduce RandMeth on this "
-                          "numpy; sampling seed by seed", RuntimeWarning, stacklevel=2)
+        # once per (model class, dim) and process: the first seed against the REFERENCE's own reset_seed
+        checked = r.__dict__.setdefault("ensemble_checked", {})
+        key = (kind, model.dim)
+        if key not in checked:
+            probe = gen.RandMeth(model, mode_no=n_modes, seed=seeds[0], sampling=generator.sampling)
+            r.orig[(gen.RandMeth, "reset_seed")](probe, seeds[0])
+            checked[key] = (np.array_equal(probe._cov_sample, batch[0][0]) and np.array_equal(probe._z_1, batch[1][0])
+                            and np.array_equal(probe._z_2, batch[2][0]))
+            if not checked[key]:
+                warnings.warn("gstools_b200.ensemble: the native batch sampler does not reproduce RandMeth on this "
+                              "numpy; sampling seed by seed", RuntimeWarning, stacklevel=2)
+        if not checked[key]:
             batch = None
     if batch is None:
         covs, z1s, z2s = [], [], []

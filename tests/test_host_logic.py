@@ -709,6 +709,54 @@ def test_batch_sampler_reproduces_randmeth_for_every_seed(gsb, make, kind):
 
 
 @needs_ref
+@pytest.mark.parametrize("make", [
+    lambda gs: gs.Exponential(dim=3, var=1.0, len_scale=10.0, nugget=0.3),
+    lambda gs: gs.Matern(dim=2, var=2.0, len_scale=7.0, nu=1.5, nugget=0.1),
+    lambda gs: gs.Gaussian(dim=3, var=1.0, len_scale=4.0),
+], ids=["Exponential3d", "Matern2d", "Gaussian3d"])
+def test_wrapped_reset_seed_is_the_references(gsb, make):
+    """The fused RandMeth.reset_seed draws the whole mode set of a seed natively: same arrays as the reference for
+    construction, reseeding and seed=nan, and later users of the generator's RNG (nugget draws, generator.py:272-292)
+    continue the master stream exactly where the reference would."""
+    gs = refharness.import_gstools()
+    from gstools.field.generator import IncomprRandMeth, RandMeth
+
+    def run(cls, **kw):
+        out = []
+        rm = cls(make(gs), mode_no=97, seed=11, **kw)
+        for step in range(4):
+            if step == 1:
+                rm.seed = 12345
+            elif step == 2:
+                rm.reset_seed()                  # seed = nan: same seed, modes recalculated
+            elif step == 3:
+                rm.update(make(gs), 777)
+            out.append((rm._z_1.copy(), rm._z_2.copy(), rm._cov_sample.copy(), np.array(rm.get_nugget((6,))),
+                        rm._rng.random.rand(3)))
+        return out
+
+    for cls, kw in ((RandMeth, {}), (IncomprRandMeth, dict(mean_velocity=0.5))):
+        if cls is IncomprRandMeth and make(gs).dim == 2 and False:
+            continue
+        want = run(cls, **kw)
+        gsb.enable()
+        try:
+            assert RandMeth.reset_seed is not gsb.plugin._STATE["refs"].orig[(RandMeth, "reset_seed")]
+            got = run(cls, **kw)
+        finally:
+            gsb.disable()
+        for w, g in zip(want, got):
+            assert all(np.array_equal(a, b) for a, b in zip(w, g))
+    # a random seed (None) keeps the reference's path
+    gsb.enable()
+    try:
+        rm = RandMeth(make(gs), mode_no=16, seed=None)
+        assert rm._cov_sample.shape == (make(gs).dim, 16)
+    finally:
+        gsb.disable()
+
+
+@needs_ref
 @pytest.mark.parametrize("kind", ["srf_native", "srf_ppf", "cond"])
 def test_ensemble_equals_the_loop(gsb, oracle_mod, monkeypatch, kind):
     """gstools_b200.ensemble(field, seeds): every realisation has the bits of the reference's own loop
@@ -757,7 +805,8 @@ def test_ensemble_equals_the_loop(gsb, oracle_mod, monkeypatch, kind):
         gsb.disable()
     assert got.shape == (3,) + tuple(len(a) for a in axes)
     assert ("struct_batch", 3) in calls
-    assert batch_calls == ([] if kind == "srf_ppf" else [type(field.model).__name__])
+    # (the batch of the three seeds; the wrapped RandMeth.reset_seed uses the same sampler for its own single seeds)
+    assert set(batch_calls) == (set() if kind == "srf_ppf" else {type(field.model).__name__})
     assert np.array_equal(got, want)
 
 
@@ -818,7 +867,7 @@ def test_native_radius_sampler_reference_literals_and_fallthrough(gsb, monkeypat
     real = backend.sample_radii_mcmc
     monkeypatch.setattr(backend, "sample_radii_mcmc", lambda *a: (calls.append(a[0]), real(*a))[1])
     orig = grng.RNG.sample_ln_pdf
-    gsb.enable()
+    gsb.enable(fused=False)         # RNG.sample_ln_pdf alone (the fused RandMeth.reset_seed would bypass it)
     try:
         assert grng.RNG.sample_ln_pdf is not orig
         rm = RandMeth(gs.Exponential(dim=3, var=1.5, len_scale=3.5), mode_no=100, seed=19031977)
