@@ -416,17 +416,23 @@ int gsb_ipc_open(const unsigned char *handle, int device, void **base);
 int gsb_ipc_close(void *base, int device);
 
 /*
- * Tuning / introspection.
- *   gsb_set_option("structured_min_tiles", v): meshes with fewer 128x128 output tiles than v
- *       are expanded on the device and sent through the direct kernel (default 64).
- *   gsb_set_option("force_path", 0|1|2): 0 auto, 1 always direct, 2 always separable.
- *   gsb_set_option("scratch_mb", v): budget (MiB) for the pre-tiled A operand of the structured
- *       path; larger meshes are processed in row chunks (default 3072).
- *   gsb_set_option("fold_axes", 0|1|2): fold the last two axes of a thin mesh into one column axis of the
- *       structured path: 0 never, 1 when it improves the tile utilisation (default), 2 whenever it fits.
- *   gsb_set_option("time_kernels", 0|1): see gsb_kernel_times().
+ * Tuning / introspection (defaults in brackets; none of them changes results beyond the rounding of another tiling).
+ *   gsb_set_option("force_path", 0|1|2): structured meshes: [0] cost model, 1 always direct, 2 always separable.
+ *   gsb_set_option("structured_min_tiles", v): meshes with fewer 128x128 output tiles than v go to the direct kernel [0].
+ *   gsb_set_option("fold_axes", 0|1|2): fold the last two axes of a thin mesh into one column axis of the structured
+ *       path: 0 never, [1] when the cost model prefers it, 2 whenever it fits.
+ *   gsb_set_option("sk_pack", 0|1|2): row tiles packed across slow indices: [0] cost model, 1 never, 2 whenever possible.
+ *   gsb_set_option("sk_table_mb", v): cap (MiB) on the tile-axis table of a folded tile axis [256].
+ *   gsb_set_option("sk_grid", v): CTAs of the persistent contraction, 0 = [one per SM] (tests force small / odd grids).
+ *   gsb_set_option("host_pieces", n): host route: n equal pieces instead of [0] = growing pieces.
+ *   gsb_set_option("host_chunk_points", v): host route of the direct path: points per chunk [4 Mi].
+ *   gsb_set_option("direct_cfg", -1|0|1|2): direct kernel: [-1] cost model, else 1 / 2 / 8 points per thread.
+ *   gsb_set_option("scratch_mb", v): scratch budget (MiB) of the kriging right-hand sides generated on the device [3072].
+ *   gsb_set_option("krige_host_chunk_mb", v): host route of the native-signature kriging entry: chunk size [256].
+ *   gsb_set_option("time_kernels", 0|1): see gsb_kernel_times().   gsb_set_option("trace", 0|1): print the timeline of the
+ *       contraction launches and D2H pieces of a structured call to stderr (single caller only).
  *   gsb_get_counter("launches"): CUDA kernels launched by this library so far (process-wide);
- *   "direct_calls" / "separable_calls": how often each path ran.
+ *   "direct_calls" / "separable_calls" / "sk_calls" / "packed_calls" / "folded_calls" / "krige_calls": how often each path ran.
  */
 int gsb_set_option(const char *name, int64_t value);
 
