@@ -199,3 +199,48 @@ def _srf_on_all(gs, gsb, torch):
     finally:
         gsb.use_devices(None, min_pairs=4e9)
     assert maxabs(one, many) <= 1e-12 * np.sqrt(2.0)
+
+
+def test_plan_batch_shares_of_vector_fields(plan, gsb):
+    """Ensembles of vector fields: whole (batch entry, component) blocks per device."""
+    lens, n_modes, nb = (5, 33, 130), 48, 4
+    sets = [synth_modes(3, n_modes, seed=40 + b) for b in range(nb)]
+    cov, z1, z2 = (np.stack([s[k] for s in sets]) for k in range(3))
+    axes = [np.arange(float(L)) for L in lens]
+    got = plan.summate_incompr_structured(cov, z1, z2, axes)
+    assert got.shape == (nb, 3) + lens
+    for b in range(nb):
+        assert maxabs(got[b], gsb.summate_incompr_structured(*sets[b], axes)) <= tight(n_modes)
+
+
+def test_ensemble_over_the_plan_equals_one_device(gsb):
+    """gstools_b200.ensemble with the process-wide plan: the seeds are dealt out to the devices, the per-point epilogue
+    of the conditioned field is replicated on each; same fields as on one device."""
+    import torch
+
+    import refharness
+
+    if not refharness.have_reference():
+        pytest.skip("reference gstools not present")
+    gs = refharness.import_gstools()
+    gsb.enable()
+    try:
+        rs = np.random.RandomState(5)
+        model = gs.Exponential(dim=3, var=0.8, len_scale=5.0)
+        krige = gs.krige.Ordinary(model, rs.uniform(0, 20, (3, 25)), rs.normal(size=25))
+        crf = gs.CondSRF(krige, mode_no=128)
+        axes = [np.arange(20.0), np.arange(24.0), np.arange(130.0)]
+        seeds = [11, 12, 13, 14, 15]
+        one = gsb.ensemble(crf, seeds, axes, mesh_type="structured")
+        plan = gsb.use_devices("all" if torch.cuda.device_count() > 1 else [0, 0], min_pairs=0)
+        try:
+            before = gsb.get_counter("sk_calls")
+            many = gsb.ensemble(crf, seeds, axes, mesh_type="structured")
+            assert gsb.get_counter("sk_calls") - before == min(len(plan), len(seeds))
+        finally:
+            gsb.use_devices(None, min_pairs=4e9)
+        assert maxabs(one, many) <= 1e-12
+        single = np.array(crf(axes, seed=13, mesh_type="structured", store=False))
+        assert maxabs(many[2], single) <= 1e-9 * np.sqrt(0.8)
+    finally:
+        gsb.disable()
