@@ -104,8 +104,8 @@ struct DirectParams {
     int64_t n_pts;
     double *out;            // scalar: (n_pts,)   vector: (D, n_pts) row stride out_ld
     int64_t out_ld;
-    int n_split;            // mode splits (gridDim.y); >1 writes partials to `partial`
-    double *partial;        // (n_split, ncomp, n_pts) when n_split > 1
+    int n_split;            // mode splits (gridDim.y); >1 writes the per-tile sums to `partial`
+    double *partial;        // (n_tiles, ncomp, n_pts) when n_split > 1
     Epi epi;                // fused caller epilogue (off: raw sums)
 };
 
@@ -134,8 +134,12 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
     const int tid = threadIdx.x;
     const int64_t base = (int64_t)blockIdx.x * (THREADS * P) + tid;
 
+    // Summation order of a point (the same in every launch configuration AND with the mode loop split over CTAs):
+    // modes are summed in ascending order inside a tile of 64 (`tacc`), the tile sums are added in ascending order
+    // (`acc`).  A CTA that owns only some tiles stores their sums and reduce_partials_kernel adds them in the same
+    // order, so a point's bits depend neither on what else is in the call nor on how the work was cut.
     double x[P][D];
-    double acc[P][NC];
+    double acc[P][NC], tacc[P][NC];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int64_t i = base + (int64_t)p * THREADS;
@@ -174,6 +178,10 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
 
         const int cnt = (int)min((int64_t)TM, prm.n_modes_pad - (int64_t)t * TM);
         const char *T = reinterpret_cast<const char *>(&tile[b][0]);
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) tacc[p][c] = 0.0;
 #pragma unroll DIRECT_UNROLL
         for (int j = 0; j < cnt; ++j) {
             const double *R = reinterpret_cast<const double *>(T + j * (REC * 8));
@@ -203,36 +211,46 @@ __global__ void __launch_bounds__(THREADS, MINB) direct_kernel(const DirectParam
                 qt_polys(z, ps, pc);
                 const double wr = w.y * r;
                 if (!VEC) {
-                    acc[p][0] = fma(wr, ps, acc[p][0]);
-                    acc[p][0] = fma(w.x, pc, acc[p][0]);
+                    tacc[p][0] = fma(wr, ps, tacc[p][0]);
+                    tacc[p][0] = fma(w.x, pc, tacc[p][0]);
                 } else {
                     const double a = fma(w.x, pc, wr * ps);
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) acc[p][c] = fma(pj[c], a, acc[p][c]);
+                    for (int c = 0; c < NC; ++c) tacc[p][c] = fma(pj[c], a, tacc[p][c]);
+                }
+            }
+        }
+        if (prm.n_split == 1) {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[p][c] = __dadd_rn(acc[p][c], tacc[p][c]);
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int64_t i = base + (int64_t)p * THREADS;
+                if (i < prm.n_pts) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) prm.partial[((int64_t)t * NC + c) * prm.n_pts + i] = tacc[p][c];
                 }
             }
         }
         __syncthreads();  // everyone is done with buffer b before it is refilled
     }
+    if (prm.n_split > 1) return;
 
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int64_t i = base + (int64_t)p * THREADS;
         if (i < prm.n_pts) {
-            if (prm.n_split == 1) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) prm.out[c * prm.out_ld + i] = epi_apply(prm.epi, acc[p][c], c, i);
-            } else {
-#pragma unroll
-                for (int c = 0; c < NC; ++c)
-                    prm.partial[((int64_t)blockIdx.y * NC + c) * prm.n_pts + i] = acc[p][c];
-            }
+            for (int c = 0; c < NC; ++c) prm.out[c * prm.out_ld + i] = epi_apply(prm.epi, acc[p][c], c, i);
         }
     }
 }
 
-// fixed-order reduction of mode-split partial sums (deterministic: split 0, 1, 2, ...)
-__global__ void reduce_partials_kernel(const double *__restrict__ partial, int n_split, int ncomp,
+// the tile sums of a mode-split launch added in ascending tile order: the unsplit kernel's own order and bits
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, int n_tiles, int ncomp,
                                        int64_t n_pts, double *__restrict__ out, int64_t out_ld,
                                        const Epi epi)
 {
@@ -240,7 +258,7 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, int n
     const int c = blockIdx.y;
     if (i >= n_pts) return;
     double s = 0.0;
-    for (int k = 0; k < n_split; ++k) s += partial[((int64_t)k * ncomp + c) * n_pts + i];
+    for (int k = 0; k < n_tiles; ++k) s = __dadd_rn(s, partial[((int64_t)k * ncomp + c) * n_pts + i]);
     out[c * out_ld + i] = epi_apply(epi, s, c, i);
 }
 

@@ -427,6 +427,7 @@ int gsb_ipc_close(void *base, int device);
  *   gsb_set_option("host_pieces", n): host route: n equal pieces instead of [0] = growing pieces.
  *   gsb_set_option("host_chunk_points", v): host route of the direct path: points per chunk [4 Mi].
  *   gsb_set_option("direct_cfg", -1|0|1|2): direct kernel: [-1] cost model, else 1 / 2 / 8 points per thread.
+ *   gsb_set_option("direct_split", 0|1): direct kernel: [1] small point sets split the mode loop over CTAs (same bits).
  *   gsb_set_option("scratch_mb", v): scratch budget (MiB) of the kriging right-hand sides generated on the device [3072].
  *   gsb_set_option("krige_host_chunk_mb", v): host route of the native-signature kriging entry: chunk size [256].
  *   gsb_set_option("time_kernels", 0|1): see gsb_kernel_times().   gsb_set_option("trace", 0|1): print the timeline of the

@@ -88,17 +88,33 @@ def test_direct_incompr_vs_oracle(dim, n, n_modes, gsb, oracle_mod):
     assert maxabs(got, want) <= raw_tol(n_modes)
 
 
-def test_mode_split_path_small_n_many_modes(gsb, oracle_mod):
-    """n so small that the grid cannot fill the SMs: modes are split over CTAs and reduced in
-    fixed order (deterministic)."""
-    cov, z1, z2 = synth_modes(3, 5000, seed=3)
-    pos = np.random.RandomState(0).uniform(0, 100, (3, 200))
+@pytest.mark.parametrize("dim,n_modes,n", [(3, 5000, 200), (2, 1000, 10000), (3, 130, 7), (1, 64, 33)])
+def test_mode_split_path_small_point_sets(gsb, oracle_mod, dim, n_modes, n):
+    """Small point sets (config 1: 10 000 points) split the mode loop over CTAs; every CTA stores the sums of its
+    64-mode tiles and the reduce kernel adds them in the unsplit kernel's order: the SAME bits as without the split and as
+    the same points inside a big call."""
+    cov, z1, z2 = synth_modes(dim, n_modes, seed=3)
+    pos = np.random.RandomState(0).uniform(0, 100, (dim, n))
+    before = gsb.get_counter("launches")
     a = gsb.summate(cov, z1, z2, pos)
-    b = gsb.summate(cov, z1, z2, pos)
-    assert np.array_equal(a, b)
-    assert maxabs(a, oracle_mod.summate(cov, z1, z2, pos)) <= raw_tol(5000)
-    av = gsb.summate_incompr(cov, z1, z2, pos)
-    assert maxabs(av, oracle_mod.summate_incompr(cov, z1, z2, pos)) <= raw_tol(5000)
+    split_ran = gsb.get_counter("launches") - before == 3            # records + direct + reduce
+    assert split_ran == (n_modes > 64)
+    assert maxabs(a, oracle_mod.summate(cov, z1, z2, pos)) <= raw_tol(n_modes)
+    gsb.set_option("direct_split", 0)
+    try:
+        assert np.array_equal(gsb.summate(cov, z1, z2, pos), a)
+        if dim in (2, 3):
+            unsplit_v = gsb.summate_incompr(cov, z1, z2, pos)
+    finally:
+        gsb.set_option("direct_split", 1)
+    if dim in (2, 3):
+        av = gsb.summate_incompr(cov, z1, z2, pos)
+        assert np.array_equal(av, unsplit_v)
+        assert maxabs(av, oracle_mod.summate_incompr(cov, z1, z2, pos)) <= raw_tol(n_modes)
+    # the same points as the head of a call big enough for the 8-points-per-thread configuration
+    big = np.concatenate([pos, np.random.RandomState(1).uniform(0, 100, (dim, 700000))], axis=1)
+    assert np.array_equal(gsb.summate(cov[:, :256], z1[:256], z2[:256], big)[:n],
+                          gsb.summate(cov[:, :256], z1[:256], z2[:256], pos))
 
 
 def test_edge_cases(gsb, oracle_mod):
