@@ -368,6 +368,7 @@ class Plan:
         if _PLAN["plan"] is self:
             _PLAN["plan"] = None
         self._finalizer()
+        self._handle = None
 
     def __enter__(self):
         return self
@@ -377,6 +378,13 @@ class Plan:
 
     def __len__(self):
         return len(self.devices)
+
+    @property
+    def handle(self):
+        """The ``gsb_plan *`` of this plan; using a closed plan is an error, not a crash."""
+        if self._handle is None:
+            raise ValueError("this Plan has been closed")
+        return self._handle
 
     def share(self, n, part):
         """``[lo, hi)`` of the units device number ``part`` of the plan gets out of ``n``."""
@@ -473,7 +481,7 @@ def _flat(cov_samples, z_1, z_2, pos, vec, sf=None, epilogue=None, point_epilogu
     if plan is not None:
         out = _empty_host((dim, n) if vec else (n,))
         pe = point_epilogue.ref(n) if point_epilogue is not None else None
-        rc = lib.gsb_plan_summate(plan._handle, _ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n, _ptr(out),
+        rc = lib.gsb_plan_summate(plan.handle, _ptr(cov), _ptr(z1), _ptr(z2), _ptr(p), ld, dim, n_modes, n, _ptr(out),
                                   max(n, 1), int(vec), epi, pe, _lib.MEM_HOST, 0, None)
         _lib.check(rc, "plan_summate")
         return out
@@ -531,7 +539,7 @@ def _flat_device(lib, cov_samples, z_1, z_2, pos, vec, sf=None, epi=None, pepi=N
     if plan is not None:
         out = torch.empty((dim, n) if vec else (n,), dtype=torch.float64, device=dev)
         pe = pepi.ref(n) if pepi is not None else None
-        rc = lib.gsb_plan_summate(plan._handle, cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), ld, dim,
+        rc = lib.gsb_plan_summate(plan.handle, cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), p.data_ptr(), ld, dim,
                                   n_modes, n, out.data_ptr(), max(n, 1), int(vec), epi, pe, _lib.MEM_DEVICE, dev.index,
                                   stream)
         _lib.check(rc, "plan_summate")
@@ -654,7 +662,7 @@ def _structured(cov_samples, z_1, z_2, axes, matrix, vec, epilogue=None, point_e
     plan = _pick_plan(plan, float(n_pts) * n_modes * n_batch, point_epilogue)
     if plan is not None:
         pe = point_epilogue.ref(n_pts) if point_epilogue is not None else None
-        rc = lib.gsb_plan_summate_structured(plan._handle, _ptr(cov3), _ptr(z1b), _ptr(z2b), _ptr(cat),
+        rc = lib.gsb_plan_summate_structured(plan.handle, _ptr(cov3), _ptr(z1b), _ptr(z2b), _ptr(cat),
                                              lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch,
                                              _ptr(out), int(vec), epi, pe, _lib.MEM_HOST, 0, None)
         _lib.check(rc, "plan_summate_structured")
@@ -710,7 +718,7 @@ def _structured_device(lib, cov_samples, z_1, z_2, axes, matrix, vec, epi=None, 
     plan = _pick_plan(plan, float(n_pts) * n_modes * n_batch, pepi, dev.index)
     if plan is not None:
         pe = pepi.ref(n_pts) if pepi is not None else None
-        rc = lib.gsb_plan_summate_structured(plan._handle, cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), cat.data_ptr(),
+        rc = lib.gsb_plan_summate_structured(plan.handle, cov.data_ptr(), z1.data_ptr(), z2.data_ptr(), cat.data_ptr(),
                                              lens.ctypes.data_as(_lib._c_int64_p), mat_ptr, dim, n_modes, n_batch,
                                              out.data_ptr(), int(vec), epi, pe, _lib.MEM_DEVICE, dev.index, stream)
         _lib.check(rc, "plan_summate_structured")

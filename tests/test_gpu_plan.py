@@ -244,3 +244,11 @@ def test_ensemble_over_the_plan_equals_one_device(gsb):
         assert maxabs(many[2], single) <= 1e-9 * np.sqrt(0.8)
     finally:
         gsb.disable()
+
+
+def test_closed_plan_is_refused(gsb):
+    p = gsb.Plan([0])
+    p.close()
+    p.close()
+    with pytest.raises(ValueError, match="closed"):
+        p.summate_structured(*synth_modes(2, 8, seed=1), [np.arange(4.0), np.arange(5.0)])
