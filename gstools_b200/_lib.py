@@ -109,6 +109,8 @@ SIGNATURES = {
                                 _int, _vp]),
     "gsb_plan_summate_structured": (_int, [_vp, _vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64, _i64, _vp, _int,
                                            _epi_p, _vp, _int, _int, _vp]),
+    "gsb_plan_krige_evaluate": (_int, [_vp, _cov_p, _vp, _vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _vp, _c_int64_p, _vp,
+                                       _int, _vp, _i64, _vp, _vp, _int, _int, _vp]),
     "gsb_summate_structured_slab": (_int, [_vp, _vp, _vp, _vp, _c_int64_p, _vp, _int, _i64, _i64, _i64, _i64, _vp, _int,
                                            _epi_p, _vp, _int, _int, _vp]),
     "gsb_ipc_export": (_int, [_vp, _int, _vp, _c_int64_p]),

@@ -408,6 +408,12 @@ class Plan:
     def summate_incompr_structured(self, cov_samples, z_1, z_2, axes, matrix=None, *, epilogue=None):
         return _structured(cov_samples, z_1, z_2, axes, matrix, vec=True, epilogue=epilogue, plan=self)
 
+    def krige_evaluate(self, model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=None, unbiased=True,
+                       tail_rows=None, return_var=True):
+        """:func:`krige_evaluate` with the evaluation points dealt out to the devices of the plan."""
+        return krige_evaluate(model, krig_mat, cond, cond_pos, pos=pos, axes=axes, matrix=matrix, unbiased=unbiased,
+                              tail_rows=tail_rows, return_var=return_var, plan=self)
+
 
 def use_devices(devices="all", min_pairs=None):
     """Route the host-array entry points of this module (and with them ``gs.SRF`` / ``gs.CondSRF`` under
@@ -874,7 +880,7 @@ def cov_model_spec(kind, var, len_rescaled, sill=None, param=0.0, exact=False):
 
 
 def _krige_evaluate_device(lib, model, krig_mat, cond, cond_pos, pos, axes, matrix, unbiased, tail_rows,
-                           return_var):
+                           return_var, plan=None):
     """Device-resident variant: CUDA tensors in, CUDA tensors out, work enqueued on the current stream."""
     torch = _torch()
     cands = [krig_mat, cond, cond_pos, pos, tail_rows] + (list(axes) if axes is not None else [])
@@ -924,7 +930,15 @@ def _krige_evaluate_device(lib, model, krig_mat, cond, cond_pos, pos, axes, matr
     error = torch.empty(n, dtype=torch.float64, device=dev) if return_var else None
     err_ptr = error.data_ptr() if return_var else None
     stream = torch.cuda.current_stream(dev).cuda_stream
-    if axes is not None:
+    plan = _pick_plan(plan, float(n) * size * size / 4.0, None, dev.index)
+    if plan is not None:
+        rc = lib.gsb_plan_krige_evaluate(plan.handle, ctypes.byref(model), mat.data_ptr(), c.data_ptr(), size,
+                                         cp.data_ptr(), cond_no, dim, None if axes is not None else p.data_ptr(),
+                                         max(n, 1), n, cat.data_ptr() if axes is not None else None,
+                                         lens.ctypes.data_as(_lib._c_int64_p) if axes is not None else None,
+                                         mat_ptr if axes is not None else None, int(bool(unbiased)), tail_ptr, tail_ld,
+                                         field.data_ptr(), err_ptr, _lib.MEM_DEVICE, dev.index, stream)
+    elif axes is not None:
         rc = lib.gsb_krige_evaluate_structured(ctypes.byref(model), mat.data_ptr(), c.data_ptr(), size,
                                                cp.data_ptr(), cond_no, dim, cat.data_ptr(),
                                                lens.ctypes.data_as(_lib._c_int64_p), mat_ptr,
@@ -940,7 +954,7 @@ def _krige_evaluate_device(lib, model, krig_mat, cond, cond_pos, pos, axes, matr
 
 
 def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=None, unbiased=True,
-                   tail_rows=None, return_var=True):
+                   tail_rows=None, return_var=True, plan=None):
     """The evaluation loop of ``Krige.__call__`` (krige/base.py:278-294) on the device.
 
     The right-hand sides of ``Krige._get_krige_vecs`` (base.py:359-388) -- ``model`` evaluated at
@@ -950,7 +964,8 @@ def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=
     (dim, n), isometrised, or the mesh ``axes`` (+ isometrisation ``matrix``).  Host arrays in,
     host arrays out -- or CUDA tensors in, CUDA tensors out (nothing is copied, work is enqueued on the
     current torch stream).  Returns ``(field, error)`` or ``field`` (``return_var=False``); for a mesh
-    the results have the mesh shape.
+    the results have the mesh shape.  ``plan`` (or the process-wide plan of :func:`use_devices` for big systems):
+    the points are dealt out to the GPUs of the plan -- slabs along axis 0 of a mesh, ranges of a flat point set.
     """
     lib = _lib.load()
     if not isinstance(model, _lib.CovModelSpec):
@@ -958,7 +973,7 @@ def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=
     tensors = [krig_mat, cond, cond_pos, pos, tail_rows] + (list(axes) if axes is not None else [])
     if any(_is_cuda_tensor(x) for x in tensors):
         return _krige_evaluate_device(lib, model, krig_mat, cond, cond_pos, pos, axes, matrix, unbiased,
-                                      tail_rows, return_var)
+                                      tail_rows, return_var, plan)
     mat = np.ascontiguousarray(_as_f64(krig_mat, "krig_mat"))
     c = np.ascontiguousarray(_as_f64(cond, "cond"))
     cp = np.ascontiguousarray(_as_f64(cond_pos, "cond_pos"))
@@ -1003,7 +1018,15 @@ def krige_evaluate(model, krig_mat, cond, cond_pos, pos=None, axes=None, matrix=
     field = _empty_host((n,))
     error = _empty_host((n,)) if return_var else None
     err_ptr = _ptr(error) if return_var else None
-    if axes is not None:
+    plan = _pick_plan(plan, float(n) * size * size / 4.0, None)
+    if plan is not None:
+        rc = lib.gsb_plan_krige_evaluate(plan.handle, ctypes.byref(model), _ptr(mat), _ptr(c), size, _ptr(cp), cond_no,
+                                         dim, None if axes is not None else _ptr(p), ld if axes is None else 1, n,
+                                         _ptr(cat) if axes is not None else None,
+                                         lens.ctypes.data_as(_lib._c_int64_p) if axes is not None else None,
+                                         mat_ptr if axes is not None else None, int(bool(unbiased)), tail_ptr, tail_ld,
+                                         _ptr(field), err_ptr, _lib.MEM_HOST, 0, None)
+    elif axes is not None:
         rc = lib.gsb_krige_evaluate_structured(ctypes.byref(model), _ptr(mat), _ptr(c), size, _ptr(cp),
                                                cond_no, dim, _ptr(cat), lens.ctypes.data_as(_lib._c_int64_p),
                                                mat_ptr, int(bool(unbiased)), tail_ptr, tail_ld, _ptr(field),

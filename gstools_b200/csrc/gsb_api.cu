@@ -1096,6 +1096,9 @@ struct KrigeEvalArgs {
     const double *tail;
     int64_t tail_ld;
     double *field, *error;
+    // share of a multi-GPU plan: evaluate the points [first, first + count) only; pos / tail / field / error still
+    // describe (and are indexed by) the FULL point set.  count < 0: all points.
+    int64_t first = 0, count = -1;
 };
 
 template <int D>
@@ -1146,7 +1149,8 @@ static int krige_eval_on_device(const KrigeEvalArgs &a, const MeshInfo *mesh, co
     gp.tail = a.tail;
     gp.tail_ld = a.tail_ld;
     gp.w = op.w;
-    const int64_t n = a.n;
+    const int64_t first = a.count < 0 ? 0 : a.first;
+    const int64_t n = a.count < 0 ? a.n : a.count;
 #define GSB_KRG_DIM_SWITCH(CALL)                                                              \
     switch (D) {                                                                              \
     case 1: CALL(1); break;                                                                   \
@@ -1156,9 +1160,9 @@ static int krige_eval_on_device(const KrigeEvalArgs &a, const MeshInfo *mesh, co
     default: return fail(GSB_ERR_ARGUMENT, "krige_evaluate: dim must be in 1..4");            \
     }
     if (!a.error) {
-        gp.col_begin = 0;
+        gp.col_begin = first;
         gp.n = n;
-        gp.field = a.field;
+        gp.field = a.field + first;
 #define GSB_CALL(DD) GSB_TRY(launch_field_gen<DD>(gp, st))
         GSB_KRG_DIM_SWITCH(GSB_CALL)
 #undef GSB_CALL
@@ -1188,7 +1192,7 @@ static int krige_eval_on_device(const KrigeEvalArgs &a, const MeshInfo *mesh, co
     for (int64_t c0 = 0; c0 < n; c0 += chunk_tiles * SEP_TN) {
         const int64_t m = std::min<int64_t>(chunk_tiles * SEP_TN, n - c0);
         const int64_t n_ct = (m + SEP_TN - 1) / SEP_TN;
-        gp.col_begin = c0;
+        gp.col_begin = first + c0;
         gp.n = m;
 #define GSB_CALL(DD) launch_kvgen<DD>(gp, gp.n_dstages, n_ct, st)
         GSB_KRG_DIM_SWITCH(GSB_CALL)
@@ -1198,13 +1202,13 @@ static int krige_eval_on_device(const KrigeEvalArgs &a, const MeshInfo *mesh, co
         kp.n = m;
         kp.n_copy = m;
         kp.n_col_tiles = n_ct;
-        kp.field = a.field + c0;
+        kp.field = a.field + first + c0;
         {
             KernelTimer timer(st);
             GSB_TRY(launch_krige(kp, true, dev.sm_count, st));
         }
         const int blocks = (int)std::min<int64_t>((m + 255) / 256, 8LL * dev.sm_count);
-        krige_finish_kernel<<<blocks, 256, 0, st>>>(d_partial, kp.n_pairs, m, a.error + c0);
+        krige_finish_kernel<<<blocks, 256, 0, st>>>(d_partial, kp.n_pairs, m, a.error + first + c0);
         g_launches.fetch_add(1);
         GSB_CUDA(cudaGetLastError());
     }
@@ -1248,6 +1252,8 @@ static int krige_eval_impl(KrigeEvalArgs a, bool structured, int mem, int device
     }
     if (a.n < 0) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: n_pts must be >= 0");
     if (a.n == 0) return GSB_OK;
+    if (a.count >= 0 && (a.first < 0 || a.first + a.count > a.n)) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: share outside the point set");
+    if (a.count == 0) return GSB_OK;
     if (!a.field) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: field must not be NULL");
     if (structured ? !a.axes : (!a.pos || a.pos_ld < a.n)) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: bad positions");
     if (n_tail > 0 && (!a.tail || a.tail_ld < a.n)) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: drift rows missing");
@@ -1260,6 +1266,12 @@ static int krige_eval_impl(KrigeEvalArgs a, bool structured, int mem, int device
     cudaStream_t s0 = dev->streams[0];
     Scratch scr(s0);
     KrigeEvalArgs d = a;
+    // this call's points: [first, first + cnt).  The device code indexes positions, drift rows and outputs by the
+    // GLOBAL point index, so the staged copies of the share are addressed through pointers shifted by -first.
+    const int64_t first = a.count < 0 ? 0 : a.first;
+    const int64_t cnt = a.count < 0 ? a.n : a.count;
+    d.first = first;
+    d.count = cnt;
     double *p = nullptr;
     auto up = [&](const double *src, size_t count, const double **dst) -> int {
         GSB_TRY(scr.alloc(&p, count));
@@ -1274,30 +1286,30 @@ static int krige_eval_impl(KrigeEvalArgs a, bool structured, int mem, int device
         GSB_TRY(up(a.axes, (size_t)mesh.total_axes, &d.axes));
     } else {
         double *dp = nullptr;
-        GSB_TRY(scr.alloc(&dp, (size_t)a.dim * a.n));
-        GSB_CUDA(cudaMemcpy2DAsync(dp, sizeof(double) * a.n, a.pos, sizeof(double) * a.pos_ld, sizeof(double) * a.n,
+        GSB_TRY(scr.alloc(&dp, (size_t)a.dim * cnt));
+        GSB_CUDA(cudaMemcpy2DAsync(dp, sizeof(double) * cnt, a.pos + first, sizeof(double) * a.pos_ld, sizeof(double) * cnt,
                                    a.dim, cudaMemcpyHostToDevice, s0));
-        d.pos = dp;
-        d.pos_ld = a.n;
+        d.pos = dp - first;
+        d.pos_ld = cnt;
     }
     if (n_tail > 0) {
         double *dt = nullptr;
-        GSB_TRY(scr.alloc(&dt, (size_t)n_tail * a.n));
-        GSB_CUDA(cudaMemcpy2DAsync(dt, sizeof(double) * a.n, a.tail, sizeof(double) * a.tail_ld, sizeof(double) * a.n,
-                                   n_tail, cudaMemcpyHostToDevice, s0));
-        d.tail = dt;
-        d.tail_ld = a.n;
+        GSB_TRY(scr.alloc(&dt, (size_t)n_tail * cnt));
+        GSB_CUDA(cudaMemcpy2DAsync(dt, sizeof(double) * cnt, a.tail + first, sizeof(double) * a.tail_ld,
+                                   sizeof(double) * cnt, n_tail, cudaMemcpyHostToDevice, s0));
+        d.tail = dt - first;
+        d.tail_ld = cnt;
     }
     double *df = nullptr, *de = nullptr;
-    GSB_TRY(scr.alloc(&df, (size_t)a.n));
-    d.field = df;
+    GSB_TRY(scr.alloc(&df, (size_t)cnt));
+    d.field = df - first;
     if (a.error) {
-        GSB_TRY(scr.alloc(&de, (size_t)a.n));
-        d.error = de;
+        GSB_TRY(scr.alloc(&de, (size_t)cnt));
+        d.error = de - first;
     }
     GSB_TRY(krige_eval_on_device(d, structured ? &mesh : nullptr, *dev, s0));
-    GSB_CUDA(cudaMemcpyAsync(a.field, df, sizeof(double) * a.n, cudaMemcpyDeviceToHost, s0));
-    if (a.error) GSB_CUDA(cudaMemcpyAsync(a.error, de, sizeof(double) * a.n, cudaMemcpyDeviceToHost, s0));
+    GSB_CUDA(cudaMemcpyAsync(a.field + first, df, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s0));
+    if (a.error) GSB_CUDA(cudaMemcpyAsync(a.error + first, de, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s0));
     GSB_CUDA(cudaStreamSynchronize(s0));
     return GSB_OK;
 }
@@ -1612,6 +1624,62 @@ static int plan_structured_impl(gsb_plan *plan, const double *cov, const double 
     });
 }
 
+static int plan_krige_impl(gsb_plan *plan, KrigeEvalArgs a, bool structured, int mem, int home_device, void *stream)
+{
+    if (!plan) return fail(GSB_ERR_ARGUMENT, "plan must not be NULL");
+    std::lock_guard<std::mutex> lock(plan->call_mutex);
+    const int G = (int)plan->workers.size();
+    int home_idx = -1;
+    GSB_TRY(plan_home(plan, mem, home_device, &home_idx));
+    if (a.dim < 1 || a.dim > 4) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: dim must be in 1..4");
+    // points are independent, the kriging system is replicated: meshes are cut into slabs along axis 0 (contiguous
+    // ranges of the C-ordered point index), flat point sets into contiguous ranges
+    int64_t units = a.n, per_unit = 1, total_axes = 0;
+    if (structured) {
+        if (!a.axis_len) return fail(GSB_ERR_ARGUMENT, "axis_len must not be NULL");
+        int64_t n = 1;
+        for (int t = 0; t < a.dim; ++t) {
+            if (a.axis_len[t] < 0) return fail(GSB_ERR_ARGUMENT, "axis_len must be >= 0");
+            n *= a.axis_len[t];
+            total_axes += a.axis_len[t];
+        }
+        units = a.axis_len[0];
+        per_unit = units > 0 ? n / units : 0;
+    }
+    if (units < 0) return fail(GSB_ERR_ARGUMENT, "krige_evaluate: n_pts must be >= 0");
+    auto share_call = [=](int g, KrigeEvalArgs args, int device, void *st) -> int {
+        int64_t lo, hi;
+        plan_share(units, G, g, &lo, &hi);
+        if (hi == lo) return GSB_OK;
+        args.first = lo * per_unit;
+        args.count = (hi - lo) * per_unit;
+        return krige_eval_impl(args, structured, mem, device, st);
+    };
+    if (mem == GSB_MEM_HOST) {
+        std::vector<std::function<int()>> jobs((size_t)G);
+        for (int g = 0; g < G; ++g) {
+            const int device = plan->workers[(size_t)g]->device;
+            jobs[(size_t)g] = [=]() { return share_call(g, a, device, nullptr); };
+        }
+        return plan_run(plan, jobs);
+    }
+    const int64_t n_tail = a.K - a.C - (a.unbiased ? 1 : 0);
+    (void)n_tail;
+    return plan_run_device(plan, home_idx, stream, [&](int g, cudaStream_t st, Scratch &scr) -> int {
+        const bool local = (g == home_idx);
+        KrigeEvalArgs args = a;
+        // the system (K x K), the conditioning values / positions and the axes are re-read by every tile: private
+        // copies; positions of a flat point set and drift rows are read once per point, straight from the home device
+        if (a.K > 0) {
+            GSB_TRY(plan_stage(a.mat, (size_t)a.K * a.K, local, &args.mat, scr, st));
+            GSB_TRY(plan_stage(a.cond, (size_t)a.K, local, &args.cond, scr, st));
+        }
+        if (a.C > 0 && a.cond_pos) GSB_TRY(plan_stage(a.cond_pos, (size_t)a.dim * a.C, local, &args.cond_pos, scr, st));
+        if (structured) GSB_TRY(plan_stage(a.axes, (size_t)total_axes, local, &args.axes, scr, st));
+        return share_call(g, args, plan->workers[(size_t)g]->device, st);
+    });
+}
+
 }  // namespace gsb
 
 namespace gsb {
@@ -1907,6 +1975,18 @@ int gsb_scale_shift(double *field, int64_t n, double scale, double shift, int de
     g_launches.fetch_add(1);
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;
+}
+
+int gsb_plan_krige_evaluate(gsb_plan *plan, const gsb_cov_model *model, const double *krig_mat, const double *cond,
+                            int64_t krige_size, const double *cond_pos, int64_t cond_no, int dim, const double *pos,
+                            int64_t pos_ld, int64_t n_pts, const double *axes, const int64_t *axis_len,
+                            const double *matrix, int unbiased, const double *tail_rows, int64_t tail_ld, double *field,
+                            double *error, int mem, int home_device, void *stream)
+{
+    const bool structured = (pos == nullptr);
+    KrigeEvalArgs a{model, krig_mat, cond, cond_pos, krige_size, cond_no, dim, pos, pos_ld, n_pts, axes, axis_len,
+                    matrix, unbiased, tail_rows, tail_ld, field, error};
+    return plan_krige_impl(plan, a, structured, mem, home_device, stream);
 }
 
 int gsb_summate_structured_slab(const double *cov_samples, const double *z_1, const double *z_2, const double *axes,

@@ -391,6 +391,19 @@ int gsb_plan_summate_structured(gsb_plan *plan, const double *cov_samples, const
                                 int home_device, void *stream);
 
 /*
+ * gsb_plan_krige_evaluate -- gsb_krige_evaluate[_structured] (row f1: the chunk loop of Krige.__call__,
+ * src/gstools/krige/base.py:278-294, with the right-hand sides of :359-388 generated on the device) over the devices
+ * of a plan.  Points are independent and the kriging system is replicated: meshes (pos == NULL: `axes` / `axis_len` /
+ * `matrix`) are cut into slabs along axis 0, flat point sets (`pos` (dim, n_pts), row stride pos_ld) into contiguous
+ * ranges; drift rows follow their points.  mem / home_device / stream as for gsb_plan_summate_structured.
+ */
+int gsb_plan_krige_evaluate(gsb_plan *plan, const gsb_cov_model *model, const double *krig_mat, const double *cond,
+                            int64_t krige_size, const double *cond_pos, int64_t cond_no, int dim, const double *pos,
+                            int64_t pos_ld, int64_t n_pts, const double *axes, const int64_t *axis_len,
+                            const double *matrix, int unbiased, const double *tail_rows, int64_t tail_ld,
+                            double *field, double *error, int mem, int home_device, void *stream);
+
+/*
  * gsb_summate_structured_slab -- one share of a mesh for callers that do their own fan-out (one process per GPU,
  * gstools_b200/dist.py): evaluates the entries [slab_lo, slab_hi) of axis 0 only, while `out` (and the per-point
  * arrays of `pepi`) describe the FULL mesh: the slab of field z lands at out + z*n + slab_lo*(n/axis_len[0]).

@@ -252,3 +252,40 @@ def test_closed_plan_is_refused(gsb):
     p.close()
     with pytest.raises(ValueError, match="closed"):
         p.summate_structured(*synth_modes(2, 8, seed=1), [np.arange(4.0), np.arange(5.0)])
+
+
+def test_plan_krige_evaluate_equals_one_device(plan, gsb):
+    """Row f1 over the plan: slabs of a mesh / ranges of a flat point set per device, the kriging system replicated,
+    drift rows following their points.  A point's kriging sums do not depend on how the points are cut: same bits."""
+    import torch
+
+    rs = np.random.RandomState(7)
+    cpos = rs.uniform(0, 30, (3, 40))
+    kmat, kcond = rs.normal(size=(42, 42)) / 40, np.concatenate([rs.normal(size=40), [0.0, 0.0]])
+    spec = dict(kind="Exponential", var=1.0, len_rescaled=6.0)
+    axes = [np.arange(33.0), np.arange(16.0), np.arange(24.0)]
+    n = 33 * 16 * 24
+    drift = rs.normal(size=(1, n))
+    want_f, want_e = gsb.krige_evaluate(spec, kmat, kcond, cpos, axes=axes, tail_rows=drift)
+    got_f, got_e = plan.krige_evaluate(spec, kmat, kcond, cpos, axes=axes, tail_rows=drift)
+    assert got_f.shape == (33, 16, 24)
+    assert np.array_equal(got_f, want_f) and np.array_equal(got_e, want_e)
+    only_f = plan.krige_evaluate(spec, kmat, kcond, cpos, axes=axes, tail_rows=drift, return_var=False)
+    assert maxabs(only_f, want_f) <= 1e-12
+    pos = rs.uniform(0, 30, (3, 5003))
+    dr = rs.normal(size=(1, 5003))
+    wf, we = gsb.krige_evaluate(spec, kmat, kcond, cpos, pos=pos, tail_rows=dr)
+    gf, ge = plan.krige_evaluate(spec, kmat, kcond, cpos, pos=pos, tail_rows=dr)
+    assert np.array_equal(gf, wf) and np.array_equal(ge, we)
+    # device route: tensors on one device of the plan, the others store their share into them
+    if len(set(plan.devices)) == 1 or plan.peer_access:
+        home = torch.device("cuda", plan.devices[-1])
+        up = lambda a: torch.tensor(a, device=home)            # noqa: E731
+        with torch.cuda.device(home):
+            df, de = plan.krige_evaluate(spec, up(kmat), up(kcond), up(cpos), axes=[up(a) for a in axes],
+                                         tail_rows=up(drift))
+            pf, pe = plan.krige_evaluate(spec, up(kmat), up(kcond), up(cpos), pos=up(pos), tail_rows=up(dr))
+            torch.cuda.synchronize()
+        assert df.device == home
+        assert np.array_equal(df.cpu().numpy(), want_f) and np.array_equal(de.cpu().numpy(), want_e)
+        assert np.array_equal(pf.cpu().numpy(), wf) and np.array_equal(pe.cpu().numpy(), we)
