@@ -617,6 +617,8 @@ static int sk_on_device(const double *d_cov, const double *d_z1, const double *d
                                                                        (int64_t)L.n_col_tiles * SK_TN),
                                                     scale ? L.n_slow : 1);
         const int64_t work = max_width * n_modes_pad;
+        tp.small_index = (work < ((int64_t)1 << 31) && L.ly < ((int64_t)1 << 31) && L.lc < ((int64_t)1 << 31) &&
+                          L.n_slow < ((int64_t)1 << 31)) ? 1 : 0;
         dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 4096), scale ? 3u : 2u, (unsigned)n_batch);
         sk_tables_kernel<<<grid, 256, 0, st>>>(tp);
         g_launches.fetch_add(1);

@@ -90,6 +90,7 @@ struct SkTableParams {
                                         //   carries (z1 - i z2) sf itself and stores (Re A, -Im A)
     unsigned *flags;                    // stream-K flags, zeroed here (n_flags entries)
     int n_flags;
+    int small_index;                    // every table of the call has < 2^31 entries: 32-bit entry arithmetic
 };
 
 __device__ __forceinline__ double sk_kprime(const SkTableParams &tp, const double *cov, int t, int64_t j)
@@ -101,15 +102,16 @@ __device__ __forceinline__ double sk_kprime(const SkTableParams &tp, const doubl
 }
 
 // phase of mode j at entry i of the axis obtained by folding mesh axes [t0, t0 + nt) (last fastest)
-__device__ __forceinline__ double sk_folded_phase(const SkTableParams &tp, const double *cov, int t0, int nt,
-                                                  int64_t i, int64_t j)
+template <typename I>
+__device__ __forceinline__ double sk_folded_phase(const SkTableParams &tp, const double *cov, int t0, int nt, I i, I j)
 {
     double phase = 0.0;
-    int64_t rem = i;
+    I rem = i;
     for (int t = t0 + nt - 1; t >= t0; --t) {
-        const int64_t it = rem % tp.axis_len[t];
-        rem /= tp.axis_len[t];
-        phase = fma(sk_kprime(tp, cov, t, j), tp.axes[tp.axis_off[t] + it], phase);
+        const I len = (I)tp.axis_len[t];
+        const I it = rem % len;
+        rem /= len;
+        phase = fma(sk_kprime(tp, cov, t, (int64_t)j), tp.axes[tp.axis_off[t] + (int64_t)it], phase);
     }
     return phase;
 }
@@ -117,7 +119,11 @@ __device__ __forceinline__ double sk_folded_phase(const SkTableParams &tp, const
 // All tables of a call in one launch.  blockIdx.y: 0 = T table (tile axis), 1 = B table (column axis),
 // 2 = slow-axis factors;  blockIdx.z = batch entry.  Full-accuracy sincos (libdevice), O((ly + lc + n_slow) N).
 // The padding columns of the pre-tiled blocks travel with the bulk copies: they are written (zero) here too.
-__global__ void sk_tables_kernel(const SkTableParams tp)
+// I: index type of the entry loop -- 32-bit whenever every table has fewer than 2^31 entries (always, in practice):
+// the two divisions per entry that decode (axis entry, mode) and those of folded axes then cost a quarter of their
+// 64-bit versions, which is a third of this kernel's time.
+template <typename I>
+__device__ __forceinline__ void sk_tables_body(const SkTableParams &tp)
 {
     const int which = blockIdx.y;
     const int64_t b = blockIdx.z;
@@ -125,24 +131,24 @@ __global__ void sk_tables_kernel(const SkTableParams tp)
     const int n_stages = tp.n_modes_pad / SK_KC;
     if (which == 0 && b == 0 && blockIdx.x == 0)
         for (int i = threadIdx.x; i < tp.n_flags; i += blockDim.x) tp.flags[i] = 0u;
-    int64_t width;
-    if (which == 0) width = (int64_t)tp.n_ytiles * SK_TM;
-    else if (which == 1) width = (int64_t)tp.n_col_tiles * SK_TN;
-    else width = tp.n_slow;
-    const int64_t total = width * tp.n_modes_pad;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
+    I width;
+    if (which == 0) width = (I)((int64_t)tp.n_ytiles * SK_TM);
+    else if (which == 1) width = (I)((int64_t)tp.n_col_tiles * SK_TN);
+    else width = (I)tp.n_slow;
+    const I n_pad = (I)tp.n_modes_pad;
+    const I total = width * n_pad;
+    for (I idx = (I)(blockIdx.x * (int64_t)blockDim.x + threadIdx.x); idx < total; idx += (I)((int64_t)gridDim.x * blockDim.x)) {
         const bool mode_major = which != 2;     // T / B: consecutive threads walk along the axis; C: along the modes
-        const int64_t j = mode_major ? idx / width : idx % tp.n_modes_pad;
-        const int64_t i = mode_major ? idx - j * width : idx / tp.n_modes_pad;
-        const bool live = j < tp.n_modes;
+        const I j = mode_major ? idx / width : idx % n_pad;
+        const I i = mode_major ? idx - j * width : idx / n_pad;
+        const bool live = (int64_t)j < tp.n_modes;
         if (which == 0) {
             double c = 0.0, s = 0.0;
-            if (live && i < tp.ly) {
-                sincos(sk_folded_phase(tp, cov, tp.n_prefix, tp.n_tile_axes, i, j), &s, &c);
+            if (live && (int64_t)i < tp.ly) {
+                sincos(sk_folded_phase<I>(tp, cov, tp.n_prefix, tp.n_tile_axes, i, j), &s, &c);
                 if (!tp.ctab) {
-                    const double w = tp.sf ? tp.sf[b * tp.n_modes + j] : 1.0;
-                    const double a = w * tp.z1[b * tp.n_modes + j], bb = w * tp.z2[b * tp.n_modes + j];
+                    const double w = tp.sf ? tp.sf[b * tp.n_modes + (int64_t)j] : 1.0;
+                    const double a = w * tp.z1[b * tp.n_modes + (int64_t)j], bb = w * tp.z2[b * tp.n_modes + (int64_t)j];
                     const double re = a * c + bb * s;      // (a - i bb)(c + i s)
                     const double im = a * s - bb * c;
                     c = re;
@@ -151,7 +157,7 @@ __global__ void sk_tables_kernel(const SkTableParams tp)
             }
             const int yt = (int)(i / SK_TM), r = (int)(i % SK_TM);
             const int kc = (int)(j % SK_KC);
-            double *row = tp.ttab + ((b * n_stages + j / SK_KC) * tp.n_ytiles + yt) * (int64_t)SK_A_TILE + r * SK_AST;
+            double *row = tp.ttab + ((b * n_stages + (int64_t)(j / SK_KC)) * tp.n_ytiles + yt) * (int64_t)SK_A_TILE + r * SK_AST;
             *reinterpret_cast<double2 *>(row + 2 * kc) = make_double2(c, s);
             if (kc == 0) {
 #pragma unroll
@@ -160,15 +166,15 @@ __global__ void sk_tables_kernel(const SkTableParams tp)
             }
         } else if (which == 1) {
             double c = 0.0, s = 0.0;
-            if (live && i < tp.lc)
-                sincos(sk_folded_phase(tp, cov, tp.n_prefix + tp.n_tile_axes + tp.n_inner, tp.n_col_axes, i, j), &s, &c);
+            if (live && (int64_t)i < tp.lc)
+                sincos(sk_folded_phase<I>(tp, cov, tp.n_prefix + tp.n_tile_axes + tp.n_inner, tp.n_col_axes, i, j), &s, &c);
             double k2 = 0.0, k0 = 0.0;
             if (tp.ncomp > 1 && live) {
                 for (int s2 = 0; s2 < tp.dim; ++s2) {
-                    const double k = cov[(int64_t)s2 * tp.n_modes + j];
+                    const double k = cov[(int64_t)s2 * tp.n_modes + (int64_t)j];
                     k2 += k * k;
                 }
-                k0 = cov[j];
+                k0 = cov[(int64_t)j];
             }
             const int ct = (int)(i / SK_TN), col = (int)(i % SK_TN);
             const int st = (int)(j / SK_KC), kc = (int)(j % SK_KC);
@@ -178,7 +184,7 @@ __global__ void sk_tables_kernel(const SkTableParams tp)
                 if (tp.ncomp > 1) {
                     // incompressible projector on the ORIGINAL wave vector (generator.py:479-495)
                     p = 0.0;
-                    if (live) p = ((comp == 0) ? 1.0 : 0.0) - cov[(int64_t)comp * tp.n_modes + j] * k0 / k2;
+                    if (live) p = ((comp == 0) ? 1.0 : 0.0) - cov[(int64_t)comp * tp.n_modes + (int64_t)j] * k0 / k2;
                 }
                 double *tile = tp.btile +
                                (((b * tp.ncomp + comp) * tp.n_col_tiles + ct) * n_stages + st) * (int64_t)SK_B_TILE;
@@ -194,16 +200,23 @@ __global__ void sk_tables_kernel(const SkTableParams tp)
             double2 e = make_double2(0.0, 0.0);
             if (live) {
                 double c, s;
-                const double phase = sk_folded_phase(tp, cov, 0, tp.n_prefix, i / tp.n_in, j) +
-                                     sk_folded_phase(tp, cov, tp.n_prefix + tp.n_tile_axes, tp.n_inner, i % tp.n_in, j);
+                const I n_in = (I)tp.n_in;
+                const double phase = sk_folded_phase<I>(tp, cov, 0, tp.n_prefix, i / n_in, j) +
+                                     sk_folded_phase<I>(tp, cov, tp.n_prefix + tp.n_tile_axes, tp.n_inner, i % n_in, j);
                 sincos(phase, &s, &c);
-                const double w = tp.sf ? tp.sf[b * tp.n_modes + j] : 1.0;
-                const double a = w * tp.z1[b * tp.n_modes + j], bb = w * tp.z2[b * tp.n_modes + j];
+                const double w = tp.sf ? tp.sf[b * tp.n_modes + (int64_t)j] : 1.0;
+                const double a = w * tp.z1[b * tp.n_modes + (int64_t)j], bb = w * tp.z2[b * tp.n_modes + (int64_t)j];
                 e = make_double2(a * c + bb * s, a * s - bb * c);
             }
-            tp.ctab[(b * tp.n_slow + i) * tp.n_modes_pad + j] = e;
+            tp.ctab[(b * tp.n_slow + (int64_t)i) * tp.n_modes_pad + (int64_t)j] = e;
         }
     }
+}
+
+__global__ void sk_tables_kernel(const SkTableParams tp)
+{
+    if (tp.small_index) sk_tables_body<unsigned>(tp);
+    else sk_tables_body<int64_t>(tp);
 }
 
 // ---------------------------------------------------------------------------------------------
