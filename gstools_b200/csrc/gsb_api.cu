@@ -271,7 +271,9 @@ static int direct_on_device(const double *d_recs, int64_t n_modes_pad, const dou
     // every thread walks 1000 modes alone): the mode tiles are dealt out to gridDim.y CTAs per point block, each stores
     // its tile sums, and the reduce kernel adds them in the unsplit kernel's order -- same bits, ~4x less latency.
     const int64_t thread_slots = 8LL * 64 * dev.sm_count;
-    if (cfg == 0 && n_tiles >= 2 && 2 * n_pts < thread_slots && g_opt_direct_split.load() != 0)
+    const int ncomp_split = vec ? dim : 1;
+    if (cfg == 0 && n_tiles >= 2 && 2 * n_pts < thread_slots && g_opt_direct_split.load() != 0 &&
+        (int64_t)n_tiles * ncomp_split * n_pts <= ((int64_t)1 << 25))          // tile sums: at most 256 MiB of scratch
         n_split = (int)std::min<int64_t>(n_tiles, (thread_slots + n_pts - 1) / n_pts);
     (void)want;
     DirectParams prm;
