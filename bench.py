@@ -217,7 +217,7 @@ def cpu_baseline(cfg, target_seconds=12.0):
     probe = 65536
     t = cpu_run(cfg, cpu_sample_points(cfg, probe))
     rate = probe * n_modes / max(t, 1e-9)
-    m = int(min(max(probe, rate * target_seconds / n_modes), 4_000_000))
+    m = int(min(max(probe, rate * target_seconds / n_modes), 16_000_000))
     t = cpu_run(cfg, cpu_sample_points(cfg, m))
     return {"value": m * n_modes / t, "unit": UNIT, "cores": host_threads(), "kind": "port",
             "sample": f"{m} contiguous points of the workload x {n_modes} modes "
