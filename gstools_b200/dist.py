@@ -252,9 +252,11 @@ def summate_structured_gathered(cov_samples, z_1, z_2, axes, matrix=None, group=
     """The structured sum, sharded into slabs along axis 0 over the ranks of ``group``, delivered as ONE array on
     rank ``dst`` (``dst=None``: on every rank; ``mode="nccl"`` only).  Other ranks get ``None``.
 
-    ``mode="nccl"``: every rank cuts its slab into ``pieces`` row pieces of decreasing size (:func:`piece_bounds`);
-    piece k travels (grouped NCCL send/recv, straight into its rows of the destination) on a side stream while
-    piece k+1 contracts, so only the last, smallest piece's transfer is exposed.
+    ``mode="nccl"``: the finished slab travels as one grouped NCCL send/recv straight into its rows of the destination
+    (``pieces=1``, the default).  With ``pieces > 1`` every rank cuts its slab into row pieces of decreasing size
+    (:func:`piece_bounds`) and piece k travels on a side stream while piece k+1 contracts -- implemented and tested,
+    but measured NOT to pay on B200: the contraction is a persistent kernel that owns every SM, so NCCL's kernels get
+    no SM until it ends (profiles/r02_gather_variants_2gpu.log).
     ``mode="p2p"``: no collective on the data path at all -- :func:`open_peer_field` maps the destination into every
     rank and each rank's ONE contraction launch stores its slab there from the kernel's epilogue; a barrier
     (stream-ordered) tells ``dst`` that the field is complete.  CUDA tensors in, CUDA tensor out.
