@@ -223,3 +223,20 @@ def test_backends_agree_and_switch_at_runtime(gs_b200, gsb):
     g_gpu = srf.structured([np.arange(12.0)] * 3)
     assert np.max(np.abs(f_gpu - f_ref)) <= TOL * np.sqrt(2.0)
     assert np.max(np.abs(g_gpu - g_ref)) <= TOL * np.sqrt(2.0)
+
+
+def test_prewarm_and_release_memory(gsb):
+    """The start-up helpers: prewarm pays context / pool / pinned-cache costs, release_memory gives the cached device
+    scratch and the freed pinned blocks back; results afterwards are unchanged."""
+    from conftest import synth_modes
+
+    cov, z1, z2 = synth_modes(3, 64, seed=1)
+    axes = [np.arange(12.0), np.arange(20.0), np.arange(130.0)]
+    before = gsb.summate_structured(cov, z1, z2, axes)
+    launches = gsb.get_counter("launches")
+    gsb.prewarm((12, 20, 130), mode_no=64)
+    gsb.prewarm((12, 20, 130), mode_no=64, incompr=True)
+    gsb.prewarm((500,), mode_no=16)
+    assert gsb.get_counter("launches") > launches
+    gsb.release_memory()
+    assert np.array_equal(gsb.summate_structured(cov, z1, z2, axes), before)
